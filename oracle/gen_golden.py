@@ -1,0 +1,341 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (under oracle/chainer_shim).
+
+TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python oracle/gen_golden.py [--out tests/golden] [--games 1000]
+
+The reference has no tests and no golden vectors of its own, so these files are the
+pins: every array below is the output of the reference's own functions.  Instrumentation is by
+wrapping (logging) reference methods, never by changing what they compute.
+
+Files:
+  rules.npz     legal_actions / place_stone on reachable positions, pass positions and arbitrary boards;
+                perft(1..6) from the reference rules
+  simulate.npz  mcts_self_play.Simulate full games: per-game np.random seed, the uniforms that seed
+                yields (RandomState(seed).random_sample), move list, final board, result
+  nets.npz      SLPolicy (sl_model, rl_model), Value, RolloutPolicy outputs on harvested positions
+  selfplay.npz  src/rl_self_play.Game trajectories (normal and 'head/tail switched' openings)
+  mcts.npz      MCTS.playout sequences: per-playout v / z / priors and the resulting tree
+"""
+import argparse
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_harness  # noqa: E402
+
+
+def start_board():
+    s = np.zeros([8, 8], dtype=np.float32)
+    s[4, 3] = 1
+    s[3, 4] = 1
+    s[3, 3] = 2
+    s[4, 4] = 2
+    return s
+
+
+def u8(x):
+    return np.asarray(x).astype(np.uint8)
+
+
+def legal_mask(actions):
+    m = 0
+    for a in actions:
+        m |= 1 << int(a)
+    return np.uint64(m)
+
+
+def gen_simulate(mods, n_games, seed0, out):
+    Sim = mods["mcts_self_play"].Simulate
+    gf = mods["game"].GameFunctions
+    orig_place, orig_legal = Sim.place_stone, Sim.legal_actions
+    harvest = []  # (state u8[64], color, legal list)
+
+    def place(self, state, action, color):
+        self._moves.append(int(action))
+        self._movers.append(int(color))
+        return orig_place(self, state, action, color)
+
+    def legal(self, color):
+        acts = orig_legal(self, color)
+        if self._harvest:
+            harvest.append((u8(self.state).reshape(64).copy(), int(color), list(acts)))
+        return acts
+
+    Sim.place_stone, Sim.legal_actions = place, legal
+    try:
+        seeds, moves, movers, finals, results, nmoves, uniforms, starts, colors = [], [], [], [], [], [], [], [], []
+
+        def run(state, color, seed, do_harvest):
+            np.random.seed(seed)
+            sim = Sim(state)
+            sim._moves, sim._movers, sim._harvest = [], [], do_harvest
+            r = sim(color)
+            nxt = np.random.random_sample()
+            u = np.random.RandomState(seed).random_sample(64)
+            # exactly one uniform per stone placed, none per pass (mcts_self_play.py:106)
+            assert nxt == u[len(sim._moves)], "np.random.choice consumed an unexpected number of draws"
+            mv = np.full(64, -1, np.int8)
+            mv[:len(sim._moves)] = sim._moves
+            mr = np.zeros(64, np.int8)
+            mr[:len(sim._movers)] = sim._movers
+            seeds.append(seed); moves.append(mv); movers.append(mr); finals.append(u8(sim.state).reshape(64))
+            results.append(r); nmoves.append(len(sim._moves)); uniforms.append(u)
+            starts.append(u8(state).reshape(64)); colors.append(color)
+            return sim
+
+        # (i) from the opening, colour 1 first (BASELINE config 1)
+        for g in range(n_games):
+            run(start_board(), 1, seed0 + g, do_harvest=(g < 60))
+        # (ii) from mid-game positions, both colours to move (what MCTS leaves look like)
+        n_mid = max(8, n_games // 5)
+        for g in range(n_mid):
+            s = start_board()
+            c = 1
+            ply = 8 + (g * 7) % 40
+            for a, who in zip(moves[g][:ply], movers[g][:ply]):
+                if a < 0:
+                    break
+                gf.place_stone(s, int(a), int(who))
+                c = 3 - int(who)
+            if g % 3 == 2:
+                c = 3 - c  # also the "wrong" side to move: exercises immediate passes
+            run(s, c, seed0 + 100000 + g, do_harvest=(g < 30))
+        out["simulate"] = dict(
+            seed=np.array(seeds, np.int64), start=np.array(starts, np.uint8), color=np.array(colors, np.int8),
+            uniforms=np.array(uniforms, np.float64), moves=np.array(moves, np.int8),
+            movers=np.array(movers, np.int8), n_moves=np.array(nmoves, np.int32),
+            final=np.array(finals, np.uint8), result=np.array(results, np.int8))
+    finally:
+        Sim.place_stone, Sim.legal_actions = orig_place, orig_legal
+    return harvest
+
+
+def gen_rules(mods, harvest, out, rng):
+    gf = mods["game"].GameFunctions
+    states, colors, masks = [], [], []
+    ps_state, ps_color, ps_action, ps_after = [], [], [], []
+
+    def add(state64, color, n_place, any_cell=0):
+        s = state64.reshape(8, 8).astype(np.float32)
+        acts = gf.legal_actions(s, color)
+        states.append(u8(state64)); colors.append(color); masks.append(legal_mask(acts))
+        todo = list(acts) if n_place is None else list(rng.permutation(acts)[:n_place])
+        todo += [int(a) for a in rng.integers(0, 64, size=any_cell)]  # place_stone has no legality check
+        for a in todo:
+            t = s.copy()
+            r = gf.place_stone(t, int(a), color)
+            assert r is t
+            ps_state.append(u8(state64)); ps_color.append(color); ps_action.append(int(a)); ps_after.append(u8(t).reshape(64))
+
+    seen = set()
+    for st, c, _ in harvest:
+        key = (st.tobytes(), c)
+        if key in seen:
+            continue
+        seen.add(key)
+        add(st, c, None)
+        add(st, 3 - c, 2)
+    # arbitrary (mostly unreachable) boards at every fill density
+    for i in range(1500):
+        fill = rng.random()
+        r = rng.random(64)
+        st = np.where(r < fill * 0.5, 1, np.where(r < fill, 2, 0)).astype(np.uint8)
+        if i % 50 == 0:
+            st[:] = [0, 1, 2][(i // 50) % 3]
+        add(st, 1 + i % 2, 3, any_cell=2)
+    # action -1 is a no-op (game.py:181-182)
+    s = start_board()
+    assert gf.place_stone(s, -1, 1) is s and (s == start_board()).all()
+
+    def perft(s, color, depth, passed=False):
+        if depth == 0:
+            return 1
+        acts = gf.legal_actions(s, color)
+        if not acts:
+            return 1 if passed else perft(s, 3 - color, depth - 1, True)
+        tot = 0
+        for a in acts:
+            t = s.copy()
+            gf.place_stone(t, a, color)
+            tot += perft(t, 3 - color, depth - 1)
+        return tot
+
+    out["rules"] = dict(
+        state=np.array(states, np.uint8), color=np.array(colors, np.int8), legal_mask=np.array(masks, np.uint64),
+        ps_state=np.array(ps_state, np.uint8), ps_color=np.array(ps_color, np.int8),
+        ps_action=np.array(ps_action, np.int8), ps_after=np.array(ps_after, np.uint8),
+        perft=np.array([perft(start_board(), 1, d) for d in range(1, 7)], np.int64),
+        start_legal_1=np.array(gf.legal_actions(start_board(), 1), np.int8),
+        start_legal_2=np.array(gf.legal_actions(start_board(), 2), np.int8))
+
+
+def gen_nets(mods, harvest, out, rng, n_pos=768):
+    net, ser, gf = mods["network"], mods["chainer"].serializers, mods["game"].GameFunctions
+    idx = rng.permutation(len(harvest))[:n_pos]
+    st = np.array([harvest[i][0] for i in idx], np.uint8)
+    col = np.array([harvest[i][1] for i in idx], np.int8)
+    st = np.concatenate([start_board().astype(np.uint8).reshape(1, 64)] * 2 + [st])
+    col = np.concatenate([np.array([1, 2], np.int8), col])
+    x = np.concatenate([gf.make_state_var(s.reshape(8, 8).astype(np.float32), int(c)).data for s, c in zip(st, col)])
+    sl = net.SLPolicy(); ser.load_npz("./models/sl_model.npz", sl)
+    rl = net.SLPolicy(); ser.load_npz("./models/rl_model.npz", rl, path="predictor/")
+    va = net.Value(); ser.load_npz("./models/value_model.npz", va)
+    ro = net.RolloutPolicy(); ser.load_npz("./models/rollout_model.npz", ro)
+    B = 64
+    cat = lambda f: np.concatenate([f(x[i:i + B]).data for i in range(0, len(x), B)])
+    legal = np.array([legal_mask(gf.legal_actions(s.reshape(8, 8).astype(np.float32), int(c))) for s, c in zip(st, col)])
+    out["nets"] = dict(state=st, color=col, x=x.astype(np.uint8), legal_mask=legal,
+                       sl_prob=cat(sl), rl_prob=cat(rl), value=cat(va), rollout_prob=cat(ro))
+
+
+def gen_selfplay(mods, out, seed0):
+    import random
+    net, ser = mods["network"], mods["chainer"].serializers
+    Game = mods["rl_self_play"].Game
+    m1 = net.SLPolicy(); ser.load_npz("./models/RL/model2.npz", m1)
+    m2 = net.SLPolicy(); ser.load_npz("./models/RL/model0.npz", m2)
+    orig_place = Game.place_stone
+
+    def place(self, state, action, color):
+        self._moves.append(int(action)); self._movers.append(int(color))
+        return orig_place(self, state, action, color)
+
+    Game.place_stone = place
+    try:
+        rec = dict(seed=[], extra=[], moves=[], movers=[], n_moves=[], uniforms=[], final=[], judge=[],
+                   n_states=[], states=[], actions=[])
+        for g in range(8):
+            seed = seed0 + g
+            np.random.seed(seed); random.seed(seed)
+            game = Game(m1, m2)
+            game._moves, game._movers = [], []
+            extra = -1
+            if g % 2 == 1:  # src/train_rl.py:43-46 'switch head and tail' (no flip, no stone_num += 1)
+                pos = random.choice([[2, 4], [3, 5], [4, 2], [5, 3]])
+                game.state[pos[0], pos[1]] = 2
+                extra = pos[0] * 8 + pos[1]
+            states, actions, judge = game()
+            nxt = np.random.random_sample()
+            u = np.random.RandomState(seed).random_sample(64)
+            assert nxt == u[len(game._moves)]
+            mv = np.full(64, -1, np.int8); mv[:len(game._moves)] = game._moves
+            mr = np.zeros(64, np.int8); mr[:len(game._movers)] = game._movers
+            ss = np.zeros((32, 64), np.uint8); ss[:len(states)] = u8(np.array(states)).reshape(-1, 64)
+            aa = np.full(32, -1, np.int8); aa[:len(actions)] = actions
+            for k, v in dict(seed=seed, extra=extra, moves=mv, movers=mr, n_moves=len(game._moves), uniforms=u,
+                             final=u8(game.state).reshape(64), judge=judge, n_states=len(states), states=ss,
+                             actions=aa).items():
+                rec[k].append(v)
+        out["selfplay"] = {k: np.array(v) for k, v in rec.items()}
+    finally:
+        Game.place_stone = orig_place
+
+
+def flatten_tree(root):
+    """BFS; children in dict insertion order (= ascending action, as expand() inserts them)."""
+    nodes, parent, action = [root], [-1], [0]
+    i = 0
+    while i < len(nodes):
+        for a, ch in nodes[i].children.items():
+            nodes.append(ch); parent.append(i); action.append(int(a))
+        i += 1
+    return dict(parent=np.array(parent, np.int32), action=np.array(action, np.int8),
+                n=np.array([nd.n_visits for nd in nodes], np.int32),
+                Q=np.array([float(nd.Q) for nd in nodes], np.float64),
+                P=np.array([float(nd.P) for nd in nodes], np.float64),
+                q_is_f32=np.array([isinstance(nd.Q, np.float32) for nd in nodes], np.bool_))
+
+
+def gen_mcts(mods, out, sim_rec):
+    M, gf = mods["MCTS"], mods["game"].GameFunctions
+    cases = []
+
+    def position(game, ply):
+        s, c = start_board(), 1
+        for a, who in zip(sim_rec["moves"][game][:ply], sim_rec["movers"][game][:ply]):
+            gf.place_stone(s, int(a), int(who)); c = 3 - int(who)
+        return s, c
+
+    s19 = start_board(); gf.place_stone(s19, 19, 1)
+    specs = [("after19", s19, 2, dict(), 400),
+             ("mid30", *position(3, 30), dict(), 300),
+             ("late52_lam1_thr2", *position(5, 52), dict(lmbda=1.0, n_thr=2), 300),
+             ("late56_lam0_thr1", *position(7, 56), dict(lmbda=0.0, n_thr=1), 200)]
+    for name, state, color, kw, n_play in specs:
+        m = M.MCTS(**kw)
+        log = dict(v=[], z=[], prior_state=[], prior_color=[], prior=[])
+        vf, rf, pf = m.value_func, m.evaluate_rollout, m.policy_func
+        cur = {}
+
+        def value_func(st, c, vf=vf, cur=cur):
+            cur["v"] = vf(st, c); return cur["v"]
+
+        def evaluate_rollout(st, c, rf=rf, cur=cur):
+            cur["z"] = rf(st, c); return cur["z"]
+
+        def policy_func(st, c, actions, pf=pf, log=log):
+            ap = pf(st, c, actions)
+            pr = np.zeros(64, np.float32)
+            for a, p in ap:
+                pr[a] = p
+            log["prior_state"].append(u8(st).reshape(64).copy()); log["prior_color"].append(c); log["prior"].append(pr)
+            return ap
+
+        m.value_func, m.evaluate_rollout, m.policy_func = value_func, evaluate_rollout, policy_func
+        for k in range(n_play):
+            np.random.seed(7000 + k)
+            cur.clear()
+            m.playout(state.copy(), color, m.root)
+            log["v"].append(float(cur.get("v", 0.0))); log["z"].append(int(cur.get("z", 0)))
+        tree = flatten_tree(m.root)
+        best = max(m.root.children.items(), key=lambda an: an[1].n_visits)[0]
+        case = dict(root_state=u8(state).reshape(64), root_color=np.int8(color),
+                    lmbda=np.float64(m.lmbda), c_puct=np.float64(m.c_puct), n_thr=np.int32(m.n_thr),
+                    n_playouts=np.int32(n_play), v=np.array(log["v"], np.float32), z=np.array(log["z"], np.int8),
+                    prior_state=np.array(log["prior_state"], np.uint8).reshape(-1, 64),
+                    prior_color=np.array(log["prior_color"], np.int8),
+                    prior=np.array(log["prior"], np.float32).reshape(-1, 64), best=np.int8(best),
+                    **{"tree_" + k: v for k, v in tree.items()})
+        cases.append((name, case))
+    flat = {"cases": np.array([n for n, _ in cases])}
+    for n, c in cases:
+        for k, v in c.items():
+            flat[f"{n}/{k}"] = v
+    out["mcts"] = flat
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default=os.path.join(os.path.dirname(HERE), "tests", "golden"))
+    ap.add_argument("--games", type=int, default=1000)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    outdir = os.path.abspath(args.out)
+    mods = ref_harness.load()
+    rng = np.random.default_rng(20261017)
+    out = {}
+    harvest = gen_simulate(mods, args.games, 12345, out)
+    print("simulate done", len(harvest), "harvested positions", flush=True)
+    only = set(args.only.split(",")) if args.only else None
+    if not only or "rules" in only:
+        gen_rules(mods, harvest, out, rng); print("rules done", flush=True)
+    if not only or "nets" in only:
+        gen_nets(mods, harvest, out, rng); print("nets done", flush=True)
+    if not only or "selfplay" in only:
+        gen_selfplay(mods, out, 777); print("selfplay done", flush=True)
+    if not only or "mcts" in only:
+        gen_mcts(mods, out, out["simulate"]); print("mcts done", flush=True)
+    os.makedirs(outdir, exist_ok=True)
+    for name, d in out.items():
+        if only and name not in only and not (name == "simulate" and "simulate" in only):
+            continue
+        np.savez_compressed(os.path.join(outdir, name + ".npz"), **d)
+        print("wrote", name, {k: getattr(v, "shape", None) for k, v in list(d.items())[:6]})
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,64 @@
+"""ctypes binding of libiago_b200.so — signatures mirror include/iago_b200.h one to one."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO_PATH = os.path.join(HERE, "libiago_b200.so")
+
+
+class IagoError(RuntimeError):
+    pass
+
+
+class IagoRng(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("stream_id", C.c_uint32), ("seed", C.c_uint64), ("game_id0", C.c_uint64),
+                ("uniforms", C.c_void_p), ("u_stride", C.c_int64), ("forced", C.c_void_p), ("f_stride", C.c_int64)]
+
+
+_P = C.c_void_p
+# name -> argtypes (restype is int unless listed in _RESTYPE); this table is also what tests compare with the header
+SIGNATURES = {
+    "iago_abi_version": [],
+    "iago_last_error": [],
+    "iago_ctx_create": [C.c_int, C.POINTER(_P)],
+    "iago_ctx_destroy": [_P],
+    "iago_ctx_sync": [_P],
+    "iago_ctx_stream": [_P],
+    "iago_load_rollout": [_P, _P, _P],
+    "iago_legal_actions": [_P, _P, _P, _P, _P, C.c_int64, _P],
+    "iago_place_stone": [_P, _P, _P, _P, _P, C.c_int64, _P],
+    "iago_rollout": [_P, _P, _P, _P, C.c_int64, C.POINTER(IagoRng), _P, _P, _P, _P, _P, _P, _P],
+    "iago_rollout_host": [_P, _P, _P, _P, C.c_int64, C.POINTER(IagoRng), _P, _P, _P, _P, _P, _P],
+    "iago_rollout_sample": [_P, _P, _P, _P, C.c_int64, C.POINTER(IagoRng), C.c_uint32, _P, _P],
+    "iago_rollout_logits": [_P, _P, _P, _P, _P, C.c_int64, _P],
+    "iago_measure_int_peak": [_P, C.c_int, C.POINTER(C.c_double)],
+    "iago_last_kernel_ms": [_P, C.POINTER(C.c_float)],
+}
+_RESTYPE = {"iago_last_error": C.c_char_p, "iago_ctx_stream": _P}
+
+_lib = None
+
+
+def load_library():
+    """Loads the CUDA library or raises — there is deliberately no fallback implementation."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(SO_PATH):
+        raise IagoError(f"{SO_PATH} is missing: build it with `python -m iago_b200.build` "
+                        "(iago_b200 has no CPU fallback)")
+    lib = C.CDLL(SO_PATH)
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here = header/library mismatch
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPE.get(name, C.c_int)
+    if lib.iago_abi_version() != 1:
+        raise IagoError("libiago_b200.so ABI version mismatch")
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        msg = load_library().iago_last_error()
+        raise IagoError(f"libiago_b200 error {rc}: {msg.decode() if msg else '?'}")

@@ -1,0 +1,70 @@
+// common.cuh — context object and error plumbing shared by the translation units of libiago_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/iago_b200.h"
+
+namespace iago {
+
+void set_error(const char *fmt, ...);
+
+// Rollout policy in the form the kernel consumes (built on the host in the canonical summation order).
+struct RolloutWeights {
+    float lut[2][512];  // lut[c][pattern] = sum over taps t ascending of W[c][t] for set bits of the 9-bit pattern
+    float bias[64];
+};
+
+struct Staging {
+    void *host = nullptr;  // pinned
+    void *dev = nullptr;
+    size_t bytes = 0;
+};
+
+}  // namespace iago
+
+struct iago_ctx {
+    int device = -1;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    iago::RolloutWeights *d_rollout = nullptr;
+    bool rollout_loaded = false;
+    iago::Staging stage;
+    uint64_t *d_counters = nullptr;
+    void *trunk = nullptr;  // conv-net state (trunk.cu)
+};
+
+#define IAGO_CUDA(expr)                                                                      \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            iago::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return IAGO_E_CUDA;                                                              \
+        }                                                                                    \
+    } while (0)
+
+#define IAGO_REQUIRE(cond, msg)                     \
+    do {                                            \
+        if (!(cond)) {                              \
+            iago::set_error("invalid argument: %s", msg); \
+            return IAGO_E_INVALID;                  \
+        }                                           \
+    } while (0)
+
+namespace iago {
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        ok = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+int ensure_staging(iago_ctx *ctx, size_t bytes);
+}  // namespace iago

@@ -1,0 +1,42 @@
+// philox.cuh — Philox4x32-10 counter-based uniforms (Salmon et al., Random123), host + device.
+// The reference draws from the global numpy MT19937 (np.random.choice, mcts_self_play.py:106); a batched
+// engine needs a stream that does not depend on scheduling, so games are keyed by their global id:
+//   key = seed (lo, hi), counter = (game_lo, game_hi, draw index, stream id)
+//   m53 = (a >> 5) * 2^26 + (b >> 6)      — numpy's 53-bit recipe; u = m53 / 2^53
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define IAGO_PHD __host__ __device__ __forceinline__
+#else
+#define IAGO_PHD inline
+#endif
+
+namespace iago {
+
+IAGO_PHD void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c3, uint32_t k0, uint32_t k1) {
+#if defined(__CUDA_ARCH__)
+    const uint32_t h0 = __umulhi(0xD2511F53u, c0), l0 = 0xD2511F53u * c0;
+    const uint32_t h1 = __umulhi(0xCD9E8D57u, c2), l1 = 0xCD9E8D57u * c2;
+#else
+    const uint64_t p0 = (uint64_t)0xD2511F53u * c0, p1 = (uint64_t)0xCD9E8D57u * c2;
+    const uint32_t h0 = (uint32_t)(p0 >> 32), l0 = (uint32_t)p0, h1 = (uint32_t)(p1 >> 32), l1 = (uint32_t)p1;
+#endif
+    const uint32_t n0 = h1 ^ c1 ^ k0, n2 = h0 ^ c3 ^ k1;
+    c0 = n0; c1 = l1; c2 = n2; c3 = l0;
+}
+
+// 53-bit integer m with u = m / 2^53.
+IAGO_PHD uint64_t philox_m53(uint64_t seed, uint64_t game, uint32_t draw, uint32_t stream) {
+    uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = draw, c3 = stream;
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; r++) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return ((uint64_t)(c0 >> 5) << 26) | (uint64_t)(c1 >> 6);
+}
+
+}  // namespace iago

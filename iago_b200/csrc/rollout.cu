@@ -1,0 +1,530 @@
+// rollout.cu — K1+K2: the lockstep rollout kernel and the batched rules entry points.
+//
+// One thread owns one game: its board lives in four 32-bit registers (two 64-bit bitboards, mover's view),
+// plus stone_num / pass_flg / counters.  A turn is
+//   legal_moves (shift-and-mask, bitboard.cuh)                    <- GameFunctions.legal_actions
+//   rollout policy at the legal cells only: two 512-entry LUT reads (9-bit 3x3 neighbourhood of each
+//   plane) + bias, shared memory                                  <- RolloutPolicy.__call__ network.py:59-64
+//   exp32 (bit-exact with the oracle), fixed-point inverse cdf against one Philox / replayed uniform
+//                                                                  <- Simulate.get_action mcts_self_play.py:100-110
+//   flips + board update                                           <- place_stone
+//   pass / terminal bookkeeping exactly as Simulate.turn / __call__ (mcts_self_play.py:25-29,124-134)
+// and the game ends with judge (mcts_self_play.py:113-121).  Nothing goes to global memory during the game
+// except the optional move log; algorithmic HBM traffic is 17 B in + 17-21 B out per game.
+//
+// Canonical rollout arithmetic (identical, bit for bit, in oracle/othello_ref.c):
+//   logit = (S0 + S1) + bias[k], S_c = taps ascending; e = exp32(logit - max_legal); q = floor(e * 2^50);
+//   pick the first legal k (ascending) with cum_q > floor(m53 * total / 2^53).
+#include <string.h>
+
+#include "bitboard.cuh"
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace iago {
+
+constexpr int kBlock = 64;     // threads (= games) per CTA
+constexpr int kMaxLegal = 34;  // scratch slots per game; reachable Othello positions have <= 33 legal moves
+
+// ---------------------------------------------------------------- device helpers
+
+// 9-bit pattern of the 3x3 neighbourhood of cell (i, j) on one plane; bit t = ky*3+kx <-> cell (i+ky-1, j+kx-1),
+// off-board cells read 0 (zero padding of the conv).
+__device__ __forceinline__ uint32_t pattern9(u64 bb, int i, int j) {
+    const u64 x = (i == 0) ? (bb << 8) : (bb >> ((i - 1) * 8));  // rows i-1, i, i+1 in bytes 0, 1, 2
+    const uint32_t x3 = (uint32_t)x;
+    // three 10-bit fields, each row shifted left by one so that column -1 is an explicit zero
+    const uint32_t xp = ((x3 & 0xFFu) << 1) | ((x3 & 0xFF00u) << 3) | ((x3 & 0xFF0000u) << 5);
+    const uint32_t t = (xp >> j) & 0x00701C07u;   // 3 bits of each field
+    return ((t * 0x4081u) >> 14) & 0x1FFu;        // gather fields at 0/10/20 into 9 contiguous bits
+}
+
+// exp(x) for x <= 0, every step a single IEEE rounding (same sequence as exp32_neg in the oracle).
+__device__ __forceinline__ float exp32_neg(float x) {
+    if (x < -80.0f) return 0.0f;
+    const float z = __fmul_rn(x, 1.44269504088896341f);
+    const float n = rintf(z);
+    float r = __fmaf_rn(n, -0.693145751953125f, x);
+    r = __fmaf_rn(n, -1.42860682030941723e-6f, r);
+    float p = 1.9875691500e-4f;
+    p = __fmaf_rn(p, r, 1.3981999507e-3f);
+    p = __fmaf_rn(p, r, 8.3334519073e-3f);
+    p = __fmaf_rn(p, r, 4.1665795894e-2f);
+    p = __fmaf_rn(p, r, 1.6666665459e-1f);
+    p = __fmaf_rn(p, r, 5.0000001201e-1f);
+    const float r2 = __fmul_rn(r, r);
+    float y = __fmaf_rn(p, r2, r);
+    y = __fadd_rn(y, 1.0f);
+    const float s = __int_as_float(((int)n + 127) << 23);
+    return __fmul_rn(y, s);
+}
+
+struct PolicySmem {
+    float lut[2][512];
+    float bias[64];
+};
+
+__device__ __forceinline__ float logit_at(const PolicySmem &w, u64 own, u64 opp, int k) {
+    const int i = k >> 3, j = k & 7;
+    const float s0 = w.lut[0][pattern9(opp, i, j)];  // channel 0 = opponent stones (game.py:167-174)
+    const float s1 = w.lut[1][pattern9(own, i, j)];  // channel 1 = mover's stones
+    return __fadd_rn(__fadd_rn(s0, s1), w.bias[k]);
+}
+
+__device__ __forceinline__ u64 q_of(float e) { return __float2ull_rz(__fmul_rn(e, 1125899906842624.0f)); }
+
+__device__ __forceinline__ u64 threshold(u64 m53, u64 total) {
+    return (__umul64hi(m53, total) << 11) | ((m53 * total) >> 53);
+}
+
+// Samples one legal cell. scratch_a/scratch_b: this thread's column of the shared scratch (stride kBlock).
+__device__ __forceinline__ int sample_move(const PolicySmem &w, u64 own, u64 opp, u64 legal, u64 m53,
+                                           uint32_t *sa, uint32_t *sb) {
+    const int n = __popcll(legal);
+    if (n == 1) return __ffsll((long long)legal) - 1;  // same answer as the general path, no arithmetic needed
+    if (n <= kMaxLegal) {
+        float mx = -3.0e38f;
+        u64 m = legal;
+        for (int i = 0; i < n; i++) {
+            const int k = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            const float l = logit_at(w, own, opp, k);
+            mx = fmaxf(mx, l);
+            sa[i * kBlock] = __float_as_uint(l);
+            sb[i * kBlock] = (uint32_t)k << 24;
+        }
+        u64 cum = 0;
+        for (int i = 0; i < n; i++) {
+            const float l = __uint_as_float(sa[i * kBlock]);
+            cum += q_of(exp32_neg(__fsub_rn(l, mx)));
+            sa[i * kBlock] = (uint32_t)cum;
+            sb[i * kBlock] |= (uint32_t)(cum >> 32);  // cum < 34 * 2^50 < 2^56
+        }
+        const u64 T = threshold(m53, cum);
+        int idx = 0;
+        for (int i = 0; i < n; i++) {
+            const u64 c = ((u64)(sb[i * kBlock] & 0xFFFFFFu) << 32) | sa[i * kBlock];
+            idx += (c <= T) ? 1 : 0;
+        }
+        idx = min(idx, n - 1);
+        return (int)(sb[idx * kBlock] >> 24);
+    }
+    // > kMaxLegal legal moves: unreachable in real play, possible on arbitrary boards. Recompute instead of storing.
+    float mx = -3.0e38f;
+    for (u64 m = legal; m; m &= m - 1) mx = fmaxf(mx, logit_at(w, own, opp, __ffsll((long long)m) - 1));
+    u64 total = 0;
+    for (u64 m = legal; m; m &= m - 1)
+        total += q_of(exp32_neg(__fsub_rn(logit_at(w, own, opp, __ffsll((long long)m) - 1), mx)));
+    const u64 T = threshold(m53, total);
+    u64 cum = 0;
+    int last = 0;
+    for (u64 m = legal; m; m &= m - 1) {
+        last = __ffsll((long long)m) - 1;
+        cum += q_of(exp32_neg(__fsub_rn(logit_at(w, own, opp, last), mx)));
+        if (cum > T) return last;
+    }
+    return last;
+}
+
+// ---------------------------------------------------------------- kernels
+
+struct RolloutArgs {
+    const u64 *p1, *p2;
+    const uint8_t *color;
+    long long n;
+    uint32_t stream_id;
+    u64 seed, game_id0;
+    const double *uniforms;
+    long long u_stride;
+    const int8_t *forced;
+    long long f_stride;
+    int8_t *result;
+    u64 *final_p1, *final_p2;
+    int32_t *n_moves;
+    int8_t *move_log;
+    u64 *counters;
+};
+
+template <int MODE, bool LOG>
+__global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const RolloutWeights *__restrict__ gw) {
+    __shared__ PolicySmem w;
+    __shared__ uint32_t scratch_a[kMaxLegal * kBlock];
+    __shared__ uint32_t scratch_b[kMaxLegal * kBlock];
+    {
+        const float *src = reinterpret_cast<const float *>(gw);
+        float *dst = reinterpret_cast<float *>(&w);
+        for (int i = threadIdx.x; i < (int)(sizeof(PolicySmem) / sizeof(float)); i += kBlock) dst[i] = src[i];
+    }
+    __syncthreads();
+
+    const long long g = (long long)blockIdx.x * kBlock + threadIdx.x;
+    int placed = 0, turns = 0;
+    if (g < a.n) {
+        const int color = a.color[g];
+        u64 own = (color == 1) ? a.p1[g] : a.p2[g];
+        u64 opp = (color == 1) ? a.p2[g] : a.p1[g];
+        int stone_num = __popcll(own | opp);  // 64 - sum(state == 0), mcts_self_play.py:15
+        bool pass_flg = false;
+        uint32_t *sa = scratch_a + threadIdx.x, *sb = scratch_b + threadIdx.x;
+        while (stone_num < 64) {  // mcts_self_play.py:26 — the end test runs once per PAIR of turns
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+                const u64 legal = legal_moves(own, opp);
+                turns++;
+                if (legal) {
+                    int k;
+                    if (MODE == IAGO_RNG_FORCED) {
+                        k = (placed < a.f_stride) ? a.forced[g * a.f_stride + placed] : -1;
+                    } else {
+                        u64 m53;
+                        if (MODE == IAGO_RNG_UNIFORMS)
+                            m53 = __double2ull_rz(a.uniforms[g * a.u_stride + placed] * 9007199254740992.0);
+                        else
+                            m53 = philox_m53(a.seed, a.game_id0 + (u64)g, (uint32_t)placed, a.stream_id);
+                        k = sample_move(w, own, opp, legal, m53, sa, sb);
+                    }
+                    if (MODE == IAGO_RNG_FORCED && (k < 0 || k > 63)) {
+                        stone_num = 64;  // replay stream exhausted: stop this game where it stands
+                    } else {
+                        place(1ULL << k, own, opp);
+                        if (LOG) a.move_log[g * 64 + placed] = (int8_t)k;
+                        placed++;
+                        pass_flg = false;
+                        stone_num++;
+                    }
+                } else {
+                    if (pass_flg) stone_num = 64;  // two consecutive passes end the game
+                    pass_flg = true;
+                }
+                const u64 t = own; own = opp; opp = t;
+            }
+        }
+        // an even number of swaps happened: own = stones of `color` again
+        const int me = __popcll(own), op = __popcll(opp);
+        a.result[g] = (int8_t)((me > op) - (me < op));
+        a.final_p1[g] = (color == 1) ? own : opp;
+        a.final_p2[g] = (color == 1) ? opp : own;
+        if (a.n_moves) a.n_moves[g] = placed;
+        if (LOG)
+            for (int i = placed; i < 64; i++) a.move_log[g * 64 + i] = -1;
+    }
+    if (a.counters) {
+        unsigned p = (unsigned)placed, t = (unsigned)turns;
+        p = __reduce_add_sync(0xFFFFFFFFu, p);
+        t = __reduce_add_sync(0xFFFFFFFFu, t);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(a.counters + 0, (u64)p);
+            atomicAdd(a.counters + 1, (u64)t);
+        }
+    }
+}
+
+// One policy draw per board, no board update: Simulate.get_action (mcts_self_play.py:100-110). action -1 = no legal move.
+template <int MODE>
+__global__ void __launch_bounds__(kBlock) rollout_sample_kernel(const u64 *__restrict__ p1, const u64 *__restrict__ p2,
+                                                                const uint8_t *__restrict__ color, long long n,
+                                                                uint32_t stream_id, u64 seed, u64 game_id0, uint32_t draw,
+                                                                const double *__restrict__ uniforms,
+                                                                int8_t *__restrict__ action,
+                                                                const RolloutWeights *__restrict__ gw) {
+    __shared__ PolicySmem w;
+    __shared__ uint32_t scratch_a[kMaxLegal * kBlock];
+    __shared__ uint32_t scratch_b[kMaxLegal * kBlock];
+    {
+        const float *src = reinterpret_cast<const float *>(gw);
+        float *dst = reinterpret_cast<float *>(&w);
+        for (int i = threadIdx.x; i < (int)(sizeof(PolicySmem) / sizeof(float)); i += kBlock) dst[i] = src[i];
+    }
+    __syncthreads();
+    const long long g = (long long)blockIdx.x * kBlock + threadIdx.x;
+    if (g >= n) return;
+    const bool first = color[g] == 1;
+    const u64 own = first ? p1[g] : p2[g], opp = first ? p2[g] : p1[g];
+    const u64 legal = legal_moves(own, opp);
+    if (!legal) { action[g] = -1; return; }
+    const u64 m53 = (MODE == IAGO_RNG_UNIFORMS) ? __double2ull_rz(uniforms[g] * 9007199254740992.0)
+                                                 : philox_m53(seed, game_id0 + (u64)g, draw, stream_id);
+    action[g] = (int8_t)sample_move(w, own, opp, legal, m53, scratch_a + threadIdx.x, scratch_b + threadIdx.x);
+}
+
+__global__ void legal_actions_kernel(const u64 *__restrict__ p1, const u64 *__restrict__ p2,
+                                     const uint8_t *__restrict__ color, u64 *__restrict__ moves, long long n) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const bool first = color[g] == 1;
+    const u64 a = p1[g], b = p2[g];
+    moves[g] = legal_moves(first ? a : b, first ? b : a);
+}
+
+__global__ void place_stone_kernel(u64 *__restrict__ p1, u64 *__restrict__ p2, const int8_t *__restrict__ action,
+                                   const uint8_t *__restrict__ color, long long n) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const int k = action[g];
+    if (k < 0 || k > 63) return;  // -1 = pass = no-op (game.py:181-182)
+    const bool first = color[g] == 1;
+    u64 own = first ? p1[g] : p2[g], opp = first ? p2[g] : p1[g];
+    place(1ULL << k, own, opp);
+    p1[g] = first ? own : opp;
+    p2[g] = first ? opp : own;
+}
+
+__global__ void rollout_logits_kernel(const u64 *__restrict__ p1, const u64 *__restrict__ p2,
+                                      const uint8_t *__restrict__ color, float *__restrict__ logits, long long n,
+                                      const RolloutWeights *__restrict__ gw) {
+    __shared__ PolicySmem w;
+    {
+        const float *src = reinterpret_cast<const float *>(gw);
+        float *dst = reinterpret_cast<float *>(&w);
+        for (int i = threadIdx.x; i < (int)(sizeof(PolicySmem) / sizeof(float)); i += blockDim.x) dst[i] = src[i];
+    }
+    __syncthreads();
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (game, cell)
+    const long long g = idx >> 6;
+    if (g >= n) return;
+    const bool first = color[g] == 1;
+    const u64 a = p1[g], b = p2[g];
+    logits[idx] = logit_at(w, first ? a : b, first ? b : a, (int)(idx & 63));
+}
+
+// Integer-issue roofline denominator: 8 independent rotate+xor chains per thread (SHF + LOP3 on the alu pipe).
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters, uint32_t salt) {
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = threadIdx.x * 0x9E3779B9u + blockIdx.x + i * 0x85EBCA6Bu + salt;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                uint32_t r;
+                asm volatile("shf.l.wrap.b32 %0, %1, %1, 5;" : "=r"(r) : "r"(x[i]));
+                asm volatile("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(x[i]) : "r"(r), "r"(x[(i + 1) & 7]), "r"(salt));
+            }
+        }
+    }
+    uint32_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc ^= x[i];
+    if (acc == 0x12345678u) out[0] = acc;  // practically never; keeps the chains alive
+}
+
+// ---------------------------------------------------------------- host side
+
+static void build_rollout_weights(const float *W, const float *b, RolloutWeights *out) {
+    for (int c = 0; c < 2; c++)
+        for (int pat = 0; pat < 512; pat++) {
+            float acc = 0.0f;
+            for (int t = 0; t < 9; t++)
+                if (pat >> t & 1) acc = acc + W[c * 9 + t];
+            out->lut[c][pat] = acc;
+        }
+    memcpy(out->bias, b, 64 * sizeof(float));
+}
+
+template <int MODE>
+static void launch_rollout(const RolloutArgs &a, const RolloutWeights *w, cudaStream_t s) {
+    const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
+    if (a.move_log)
+        rollout_kernel<MODE, true><<<grid, kBlock, 0, s>>>(a, w);
+    else
+        rollout_kernel<MODE, false><<<grid, kBlock, 0, s>>>(a, w);
+}
+
+static int rollout_launch(iago_ctx *ctx, const RolloutArgs &a, int mode, cudaStream_t s) {
+    IAGO_CUDA(cudaEventRecord(ctx->ev0, s));
+    switch (mode) {
+        case IAGO_RNG_PHILOX: launch_rollout<IAGO_RNG_PHILOX>(a, ctx->d_rollout, s); break;
+        case IAGO_RNG_UNIFORMS: launch_rollout<IAGO_RNG_UNIFORMS>(a, ctx->d_rollout, s); break;
+        default: launch_rollout<IAGO_RNG_FORCED>(a, ctx->d_rollout, s); break;
+    }
+    IAGO_CUDA(cudaGetLastError());
+    IAGO_CUDA(cudaEventRecord(ctx->ev1, s));
+    ctx->timed = true;
+    return IAGO_OK;
+}
+
+static int check_rng(const iago_rng *rng, bool need_weights, const iago_ctx *ctx) {
+    IAGO_REQUIRE(rng != nullptr, "rng is NULL");
+    IAGO_REQUIRE(rng->mode >= IAGO_RNG_PHILOX && rng->mode <= IAGO_RNG_FORCED, "rng.mode");
+    if (rng->mode == IAGO_RNG_UNIFORMS) IAGO_REQUIRE(rng->uniforms && rng->u_stride > 0, "rng.uniforms / u_stride");
+    if (rng->mode == IAGO_RNG_FORCED) IAGO_REQUIRE(rng->forced && rng->f_stride > 0, "rng.forced / f_stride");
+    if (need_weights && rng->mode != IAGO_RNG_FORCED && !ctx->rollout_loaded) {
+        set_error("rollout weights not loaded (call iago_load_rollout first)");
+        return IAGO_E_STATE;
+    }
+    return IAGO_OK;
+}
+
+}  // namespace iago
+
+using namespace iago;
+
+extern "C" {
+
+int iago_load_rollout(iago_ctx *ctx, const float *conv1_W, const float *bias2_b) {
+    IAGO_REQUIRE(ctx && conv1_W && bias2_b, "NULL argument");
+    DeviceGuard guard(ctx->device);
+    RolloutWeights *h = new RolloutWeights();
+    build_rollout_weights(conv1_W, bias2_b, h);
+    cudaError_t e = cudaMemcpyAsync(ctx->d_rollout, h, sizeof *h, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    delete h;
+    IAGO_CUDA(e);
+    ctx->rollout_loaded = true;
+    return IAGO_OK;
+}
+
+int iago_legal_actions(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
+                       uint64_t *moves, int64_t n, void *stream) {
+    IAGO_REQUIRE(ctx && p1 && p2 && color && moves, "NULL argument");
+    IAGO_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    legal_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const u64 *)p1, (const u64 *)p2, color,
+                                                                      (u64 *)moves, n);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+int iago_place_stone(iago_ctx *ctx, uint64_t *p1, uint64_t *p2, const int8_t *action, const uint8_t *color,
+                     int64_t n, void *stream) {
+    IAGO_REQUIRE(ctx && p1 && p2 && action && color, "NULL argument");
+    IAGO_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    place_stone_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((u64 *)p1, (u64 *)p2, action, color, n);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+int iago_rollout_logits(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
+                        float *logits, int64_t n, void *stream) {
+    IAGO_REQUIRE(ctx && p1 && p2 && color && logits, "NULL argument");
+    IAGO_REQUIRE(n >= 0, "n < 0");
+    if (!ctx->rollout_loaded) {
+        set_error("rollout weights not loaded (call iago_load_rollout first)");
+        return IAGO_E_STATE;
+    }
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    rollout_logits_kernel<<<(unsigned)((n * 64 + 255) / 256), 256, 0, s>>>((const u64 *)p1, (const u64 *)p2, color,
+                                                                           logits, n, ctx->d_rollout);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+int iago_rollout_sample(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
+                        const iago_rng *rng, uint32_t draw, int8_t *action, void *stream) {
+    IAGO_REQUIRE(ctx && p1 && p2 && color && action, "NULL argument");
+    IAGO_REQUIRE(n >= 0, "n < 0");
+    int rc = check_rng(rng, true, ctx);
+    if (rc) return rc;
+    IAGO_REQUIRE(rng->mode != IAGO_RNG_FORCED, "rng.mode FORCED is meaningless for a single draw");
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
+    if (rng->mode == IAGO_RNG_UNIFORMS)
+        rollout_sample_kernel<IAGO_RNG_UNIFORMS><<<grid, kBlock, 0, s>>>((const u64 *)p1, (const u64 *)p2, color, n,
+            rng->stream_id, rng->seed, rng->game_id0, draw, rng->uniforms, action, ctx->d_rollout);
+    else
+        rollout_sample_kernel<IAGO_RNG_PHILOX><<<grid, kBlock, 0, s>>>((const u64 *)p1, (const u64 *)p2, color, n,
+            rng->stream_id, rng->seed, rng->game_id0, draw, nullptr, action, ctx->d_rollout);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+int iago_rollout(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
+                 const iago_rng *rng, int8_t *result, uint64_t *final_p1, uint64_t *final_p2,
+                 int32_t *n_moves, int8_t *move_log, uint64_t *counters, void *stream) {
+    IAGO_REQUIRE(ctx && p1 && p2 && color && result && final_p1 && final_p2, "NULL argument");
+    IAGO_REQUIRE(n >= 0, "n < 0");
+    int rc = check_rng(rng, true, ctx);
+    if (rc) return rc;
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    RolloutArgs a{(const u64 *)p1, (const u64 *)p2, color, n, rng->stream_id, rng->seed, rng->game_id0,
+                  rng->uniforms, rng->u_stride, rng->forced, rng->f_stride, result, (u64 *)final_p1,
+                  (u64 *)final_p2, n_moves, move_log, (u64 *)counters};
+    return rollout_launch(ctx, a, rng->mode, s);
+}
+
+int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
+                      const iago_rng *rng, int8_t *result, uint64_t *final_p1, uint64_t *final_p2,
+                      int32_t *n_moves, int8_t *move_log, uint64_t *counters_host) {
+    IAGO_REQUIRE(ctx && p1 && p2 && color && result && final_p1 && final_p2, "NULL argument");
+    IAGO_REQUIRE(n >= 0, "n < 0");
+    int rc = check_rng(rng, true, ctx);
+    if (rc) return rc;
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    auto up8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
+    const size_t N = (size_t)n;
+    // input block: p1 | p2 | color | replay stream ; output block: fp1 | fp2 | n_moves | counters | result | log
+    const size_t o_p1 = 0, o_p2 = o_p1 + 8 * N, o_col = o_p2 + 8 * N;
+    size_t o_rep = o_col + up8(N), rep_bytes = 0;
+    if (rng->mode == IAGO_RNG_UNIFORMS) rep_bytes = 8 * N * (size_t)rng->u_stride;
+    if (rng->mode == IAGO_RNG_FORCED) rep_bytes = up8(N * (size_t)rng->f_stride);
+    const size_t in_bytes = o_rep + rep_bytes;
+    const size_t o_f1 = in_bytes, o_f2 = o_f1 + 8 * N, o_nm = o_f2 + 8 * N, o_cnt = o_nm + up8(4 * N);
+    const size_t o_res = o_cnt + 16, o_log = o_res + up8(N);
+    const size_t out_end = o_log + (move_log ? 64 * N : 0);
+    rc = ensure_staging(ctx, out_end);
+    if (rc) return rc;
+    char *h = (char *)ctx->stage.host, *d = (char *)ctx->stage.dev;
+    memcpy(h + o_p1, p1, 8 * N);
+    memcpy(h + o_p2, p2, 8 * N);
+    memcpy(h + o_col, color, N);
+    if (rng->mode == IAGO_RNG_UNIFORMS) memcpy(h + o_rep, rng->uniforms, rep_bytes);
+    if (rng->mode == IAGO_RNG_FORCED) memcpy(h + o_rep, rng->forced, N * (size_t)rng->f_stride);
+    cudaStream_t s = ctx->stream;
+    IAGO_CUDA(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));
+    IAGO_CUDA(cudaMemsetAsync(d + o_cnt, 0, 16, s));
+    RolloutArgs a{(const u64 *)(d + o_p1), (const u64 *)(d + o_p2), (const uint8_t *)(d + o_col), n,
+                  rng->stream_id, rng->seed, rng->game_id0, (const double *)(d + o_rep), rng->u_stride,
+                  (const int8_t *)(d + o_rep), rng->f_stride, (int8_t *)(d + o_res), (u64 *)(d + o_f1),
+                  (u64 *)(d + o_f2), (int32_t *)(d + o_nm), move_log ? (int8_t *)(d + o_log) : nullptr,
+                  (u64 *)(d + o_cnt)};
+    rc = rollout_launch(ctx, a, rng->mode, s);
+    if (rc) return rc;
+    IAGO_CUDA(cudaMemcpyAsync(h + o_f1, d + o_f1, out_end - o_f1, cudaMemcpyDeviceToHost, s));
+    IAGO_CUDA(cudaStreamSynchronize(s));
+    memcpy(final_p1, h + o_f1, 8 * N);
+    memcpy(final_p2, h + o_f2, 8 * N);
+    memcpy(result, h + o_res, N);
+    if (n_moves) memcpy(n_moves, h + o_nm, 4 * N);
+    if (move_log) memcpy(move_log, h + o_log, 64 * N);
+    if (counters_host) memcpy(counters_host, h + o_cnt, 16);
+    return IAGO_OK;
+}
+
+int iago_measure_int_peak(iago_ctx *ctx, int iters, double *lane_ops_per_s) {
+    IAGO_REQUIRE(ctx && lane_ops_per_s && iters > 0, "bad argument");
+    DeviceGuard guard(ctx->device);
+    cudaStream_t s = ctx->stream;
+    const int blocks = ctx->sm_count * 8, threads = 256;  // 2048 threads / SM: full occupancy
+    uint32_t *d_out = (uint32_t *)ctx->d_counters + 8;    // scratch word inside the counters allocation
+    int_peak_kernel<<<blocks, threads, 0, s>>>(d_out, 64, 1u);  // warm-up
+    float best = 1e30f;
+    for (int rep = 0; rep < 3; rep++) {
+        IAGO_CUDA(cudaEventRecord(ctx->ev0, s));
+        int_peak_kernel<<<blocks, threads, 0, s>>>(d_out, iters, 2u + rep);
+        IAGO_CUDA(cudaEventRecord(ctx->ev1, s));
+        IAGO_CUDA(cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        IAGO_CUDA(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (ms < best) best = ms;
+    }
+    IAGO_CUDA(cudaGetLastError());
+    ctx->timed = false;
+    const double ops = (double)blocks * threads * (double)iters * 4.0 * 8.0 * 2.0;  // SHF + LOP3 per chain step
+    *lane_ops_per_s = ops / (best * 1e-3);
+    return IAGO_OK;
+}
+
+}  // extern "C"

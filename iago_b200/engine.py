@@ -1,0 +1,267 @@
+"""Engine: one CUDA context of libiago_b200.so (one per GPU / per process) with tensor-level entry points.
+
+Device API  : torch CUDA tensors in and out (int64 tensors carry the 64-bit bitboards), launches are ordered
+              on torch's current stream, nothing synchronises.
+Host API    : numpy arrays in and out through the library's *_host entry points (pinned staging, H2D, kernel,
+              D2H inside the call) — what the reference-style facade classes use.
+"""
+import ctypes as C
+import dataclasses
+from typing import Optional
+
+import numpy as np
+
+from . import _lib
+from ._lib import IagoError, IagoRng, check
+
+RNG_PHILOX, RNG_UNIFORMS, RNG_FORCED = 0, 1, 2
+STREAM_ROLLOUT, STREAM_SELFPLAY, STREAM_MCTS = 0, 1, 2
+
+
+@dataclasses.dataclass
+class Rng:
+    """How games draw moves (include/iago_b200.h `iago_rng`). One uniform per stone placed, none per pass."""
+    mode: int = RNG_PHILOX
+    seed: int = 0
+    game_id0: int = 0
+    stream_id: int = STREAM_ROLLOUT
+    uniforms: object = None  # [n, stride] float64 (torch cuda tensor for the device API, ndarray for the host API)
+    forced: object = None    # [n, stride] int8
+
+    @staticmethod
+    def philox(seed=0, game_id0=0, stream_id=STREAM_ROLLOUT):
+        return Rng(RNG_PHILOX, seed, game_id0, stream_id)
+
+    @staticmethod
+    def replay_uniforms(uniforms):
+        return Rng(RNG_UNIFORMS, uniforms=uniforms)
+
+    @staticmethod
+    def replay_moves(forced):
+        return Rng(RNG_FORCED, forced=forced)
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _nptr(a):
+    return C.c_void_p(a.ctypes.data) if a is not None else None
+
+
+class Engine:
+    def __init__(self, device: int = 0):
+        self.lib = _lib.load_library()
+        self.device = int(device)
+        ctx = C.c_void_p()
+        check(self.lib.iago_ctx_create(self.device, C.byref(ctx)))
+        self.ctx = ctx
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "ctx", None):
+            self.lib.iago_ctx_destroy(self.ctx)
+            self.ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_rollout(self, conv1_W, bias2_b):
+        """RolloutPolicy parameters (network.py:49-64): conv1/W (1,2,3,3), bias2/b (64,)."""
+        W = np.ascontiguousarray(conv1_W, np.float32).reshape(18)
+        b = np.ascontiguousarray(bias2_b, np.float32).reshape(64)
+        check(self.lib.iago_load_rollout(self.ctx, _nptr(W), _nptr(b)))
+
+    def load_rollout_npz(self, path):
+        with np.load(path) as z:
+            pre = "predictor/" if "predictor/conv1/W" in z.files else ""
+            self.load_rollout(z[pre + "conv1/W"], z[pre + "bias2/b"])
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self, stream):
+        if stream is not None:
+            return C.c_void_p(int(stream))
+        return C.c_void_p(_torch().cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self):
+        return _torch().device("cuda", self.device)
+
+    def _check_i64(self, *ts):
+        torch = _torch()
+        n = ts[0].numel()
+        for t in ts:
+            if not (t.is_cuda and t.dtype == torch.int64 and t.is_contiguous() and t.numel() == n):
+                raise IagoError("bitboard tensors must be contiguous CUDA int64 tensors of equal length")
+        return n
+
+    def _rng_struct(self, rng: Rng, n: int, host: bool):
+        r = IagoRng(mode=rng.mode, stream_id=rng.stream_id, seed=rng.seed & (2**64 - 1), game_id0=rng.game_id0,
+                    uniforms=None, u_stride=0, forced=None, f_stride=0)
+        keep = None
+        if rng.mode == RNG_UNIFORMS:
+            if host:
+                keep = np.ascontiguousarray(rng.uniforms, np.float64).reshape(n, -1)
+                r.uniforms, r.u_stride = keep.ctypes.data, keep.shape[1]
+            else:
+                keep = rng.uniforms.contiguous().view(n, -1)
+                assert keep.is_cuda and keep.dtype == _torch().float64
+                r.uniforms, r.u_stride = keep.data_ptr(), keep.shape[1]
+        elif rng.mode == RNG_FORCED:
+            if host:
+                keep = np.ascontiguousarray(rng.forced, np.int8).reshape(n, -1)
+                r.forced, r.f_stride = keep.ctypes.data, keep.shape[1]
+            else:
+                keep = rng.forced.contiguous().view(n, -1)
+                assert keep.is_cuda and keep.dtype == _torch().int8
+                r.forced, r.f_stride = keep.data_ptr(), keep.shape[1]
+        return r, keep
+
+    # ------------------------------------------------------------------ device API (torch tensors)
+    def legal_actions(self, p1, p2, color, stream=None):
+        """Batched GameFunctions.legal_actions: int64 mask per board (bit k = action k legal for `color`)."""
+        torch = _torch()
+        n = self._check_i64(p1, p2)
+        assert color.is_cuda and color.dtype == torch.uint8 and color.numel() == n
+        out = torch.empty(n, dtype=torch.int64, device=self._dev())
+        check(self.lib.iago_legal_actions(self.ctx, _ptr(p1), _ptr(p2), _ptr(color), _ptr(out), n, self._stream(stream)))
+        return out
+
+    def place_stone(self, p1, p2, action, color, stream=None):
+        """Batched GameFunctions.place_stone, in place on p1/p2 (action -1 = no-op)."""
+        torch = _torch()
+        n = self._check_i64(p1, p2)
+        assert action.is_cuda and action.dtype == torch.int8 and action.numel() == n
+        assert color.is_cuda and color.dtype == torch.uint8 and color.numel() == n
+        check(self.lib.iago_place_stone(self.ctx, _ptr(p1), _ptr(p2), _ptr(action), _ptr(color), n, self._stream(stream)))
+        return p1, p2
+
+    def rollout_logits(self, p1, p2, color, stream=None):
+        torch = _torch()
+        n = self._check_i64(p1, p2)
+        out = torch.empty((n, 64), dtype=torch.float32, device=self._dev())
+        check(self.lib.iago_rollout_logits(self.ctx, _ptr(p1), _ptr(p2), _ptr(color), _ptr(out), n, self._stream(stream)))
+        return out
+
+    def rollout_sample(self, p1, p2, color, rng: Optional[Rng] = None, draw=0, stream=None):
+        """One Simulate.get_action draw per board; int8 actions, -1 where the mover must pass."""
+        torch = _torch()
+        rng = rng or Rng()
+        n = self._check_i64(p1, p2)
+        out = torch.empty(n, dtype=torch.int8, device=self._dev())
+        r, keep = self._rng_struct(rng, n, host=False)
+        check(self.lib.iago_rollout_sample(self.ctx, _ptr(p1), _ptr(p2), _ptr(color), n, C.byref(r), int(draw),
+                                           _ptr(out), self._stream(stream)))
+        return out
+
+    def rollout(self, p1, p2, color, rng: Optional[Rng] = None, want_moves=False, counters=None, out=None, stream=None):
+        """n independent Simulate(state)(color) games in one lockstep kernel. Returns a dict of CUDA tensors."""
+        torch = _torch()
+        rng = rng or Rng()
+        n = self._check_i64(p1, p2)
+        assert color.is_cuda and color.dtype == torch.uint8 and color.numel() == n
+        dev = self._dev()
+        if out is None:
+            out = dict(result=torch.empty(n, dtype=torch.int8, device=dev),
+                       final_p1=torch.empty(n, dtype=torch.int64, device=dev),
+                       final_p2=torch.empty(n, dtype=torch.int64, device=dev),
+                       n_moves=torch.empty(n, dtype=torch.int32, device=dev),
+                       moves=torch.empty((n, 64), dtype=torch.int8, device=dev) if want_moves else None)
+        r, keep = self._rng_struct(rng, n, host=False)
+        check(self.lib.iago_rollout(self.ctx, _ptr(p1), _ptr(p2), _ptr(color), n, C.byref(r), _ptr(out["result"]),
+                                    _ptr(out["final_p1"]), _ptr(out["final_p2"]), _ptr(out.get("n_moves")),
+                                    _ptr(out.get("moves")), _ptr(counters), self._stream(stream)))
+        return out
+
+    # ------------------------------------------------------------------ host API (numpy arrays)
+    def rollout_host(self, p1, p2, color, rng: Optional[Rng] = None, want_moves=False, out=None):
+        """Same as rollout() with HOST buffers: H2D + kernel + D2H inside the C call (synchronous)."""
+        rng = rng or Rng()
+        p1 = np.ascontiguousarray(p1, np.uint64).reshape(-1)
+        n = p1.shape[0]
+        p2 = np.ascontiguousarray(p2, np.uint64).reshape(n)
+        color = np.ascontiguousarray(np.broadcast_to(np.asarray(color, np.uint8), (n,)))
+        if out is None:
+            out = dict(result=np.empty(n, np.int8), final_p1=np.empty(n, np.uint64), final_p2=np.empty(n, np.uint64),
+                       n_moves=np.empty(n, np.int32), moves=np.empty((n, 64), np.int8) if want_moves else None,
+                       counters=np.zeros(2, np.uint64))
+        r, keep = self._rng_struct(rng, n, host=True)
+        check(self.lib.iago_rollout_host(self.ctx, _nptr(p1), _nptr(p2), _nptr(color), n, C.byref(r),
+                                         _nptr(out["result"]), _nptr(out["final_p1"]), _nptr(out["final_p2"]),
+                                         _nptr(out.get("n_moves")), _nptr(out.get("moves")), _nptr(out.get("counters"))))
+        return out
+
+    def _to_dev(self, a, dtype):
+        torch = _torch()
+        return torch.from_numpy(np.ascontiguousarray(a).view(dtype) if dtype is not None else a).to(self._dev())
+
+    def legal_actions_host(self, p1, p2, color):
+        p1 = np.ascontiguousarray(p1, np.uint64).reshape(-1)
+        n = p1.shape[0]
+        p2 = np.ascontiguousarray(p2, np.uint64).reshape(n)
+        color = np.ascontiguousarray(np.broadcast_to(np.asarray(color, np.uint8), (n,)))
+        m = self.legal_actions(self._to_dev(p1, np.int64), self._to_dev(p2, np.int64), self._to_dev(color, None))
+        return m.cpu().numpy().view(np.uint64)
+
+    def place_stone_host(self, p1, p2, action, color):
+        p1 = np.ascontiguousarray(p1, np.uint64).reshape(-1)
+        n = p1.shape[0]
+        p2 = np.ascontiguousarray(p2, np.uint64).reshape(n)
+        action = np.ascontiguousarray(np.broadcast_to(np.asarray(action, np.int8), (n,)))
+        color = np.ascontiguousarray(np.broadcast_to(np.asarray(color, np.uint8), (n,)))
+        d1, d2 = self._to_dev(p1, np.int64), self._to_dev(p2, np.int64)
+        self.place_stone(d1, d2, self._to_dev(action, None), self._to_dev(color, None))
+        return d1.cpu().numpy().view(np.uint64), d2.cpu().numpy().view(np.uint64)
+
+    def rollout_sample_host(self, p1, p2, color, rng: Optional[Rng] = None, draw=0):
+        torch = _torch()
+        p1 = np.ascontiguousarray(p1, np.uint64).reshape(-1)
+        n = p1.shape[0]
+        p2 = np.ascontiguousarray(p2, np.uint64).reshape(n)
+        color = np.ascontiguousarray(np.broadcast_to(np.asarray(color, np.uint8), (n,)))
+        rng = rng or Rng()
+        if rng.mode == RNG_UNIFORMS:
+            rng = Rng.replay_uniforms(torch.from_numpy(np.ascontiguousarray(rng.uniforms, np.float64).reshape(n, 1)).to(self._dev()))
+        out = self.rollout_sample(self._to_dev(p1, np.int64), self._to_dev(p2, np.int64), self._to_dev(color, None),
+                                  rng=rng, draw=draw)
+        return out.cpu().numpy()
+
+    def rollout_logits_host(self, p1, p2, color):
+        p1 = np.ascontiguousarray(p1, np.uint64).reshape(-1)
+        n = p1.shape[0]
+        p2 = np.ascontiguousarray(p2, np.uint64).reshape(n)
+        color = np.ascontiguousarray(np.broadcast_to(np.asarray(color, np.uint8), (n,)))
+        out = self.rollout_logits(self._to_dev(p1, np.int64), self._to_dev(p2, np.int64), self._to_dev(color, None))
+        return out.cpu().numpy()
+
+    # ------------------------------------------------------------------ measurement helpers
+    def last_kernel_ms(self):
+        ms = C.c_float()
+        check(self.lib.iago_last_kernel_ms(self.ctx, C.byref(ms)))
+        return float(ms.value)
+
+    def measure_int_peak(self, iters=4096):
+        v = C.c_double()
+        check(self.lib.iago_measure_int_peak(self.ctx, int(iters), C.byref(v)))
+        return float(v.value)
+
+    def sync(self):
+        check(self.lib.iago_ctx_sync(self.ctx))
+
+
+_default = {}
+
+
+def default_engine(device: int = 0) -> Engine:
+    """Process-wide engine per device (the reference keeps global state too: chainer.config, np.random)."""
+    if device not in _default:
+        _default[device] = Engine(device)
+    return _default[device]

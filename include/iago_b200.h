@@ -1,0 +1,133 @@
+/*
+ * iago_b200.h — C ABI of libiago_b200.so, the B200-native drop-in for IaGo's rollout / self-play /
+ * PV-MCTS hot path.
+ *
+ * The reference (/root/reference) is pure Python and has no FFI of its own; its "plugin API" for this
+ * path is the importable Python surface.  This header is what a ctypes stub on the
+ * reference side binds; every entry point cites the reference interface it replaces.
+ *
+ * Conventions
+ *   - Every function returns int: 0 = ok, < 0 = error (IAGO_E_*); iago_last_error() gives a thread-local
+ *     message.  No C++ exception crosses this boundary.
+ *   - Plain pointers and sizes only.  Unless a function name ends in _host, data pointers are DEVICE
+ *     pointers owned by the caller (e.g. torch tensors); they are never freed or retained past the call.
+ *     Small model parameters (weights) are HOST pointers and are copied.
+ *   - Launches are asynchronous on the cudaStream_t passed as `void *stream` (NULL = the context's own
+ *     stream).  *_host entry points take HOST buffers, do H2D + kernel + D2H, and synchronise before return.
+ *   - Boards are bitboard pairs: bit k <-> action k = row*8+col of the reference's 8x8 array
+ *     (game.py:126,184).  p1 = stones of colour 1 (moves first), p2 = colour 2.  colour in {1,2}.
+ *   - One context per device; a context is not re-entrant.  Different contexts may be used from
+ *     different host threads.
+ *   - There is NO CPU fallback: every compute entry point fails with IAGO_E_CUDA if no sm_100 device
+ *     is usable.
+ */
+#ifndef IAGO_B200_H
+#define IAGO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IAGO_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define IAGO_API __attribute__((visibility("default")))
+#else
+#define IAGO_API
+#endif
+
+enum {
+    IAGO_OK = 0,
+    IAGO_E_INVALID = -1,   /* bad argument */
+    IAGO_E_CUDA = -2,      /* CUDA runtime / driver error, or no usable device */
+    IAGO_E_STATE = -3,     /* call order (e.g. weights not loaded) */
+    IAGO_E_NOMEM = -4
+};
+
+typedef struct iago_ctx iago_ctx;
+
+/* How a game draws its moves.  Exactly one uniform is consumed per stone placed and none per pass
+ * (mcts_self_play.py:100-110 -> np.random.choice -> one random_sample()). */
+enum {
+    IAGO_RNG_PHILOX = 0,    /* u = Philox4x32-10(key = seed, ctr = (game_lo, game_hi, draw, stream_id));
+                               u = ((a>>5)*2^26 + (b>>6)) / 2^53, game = game_id0 + index              */
+    IAGO_RNG_UNIFORMS = 1,  /* replay: the k-th stone of game g uses uniforms[g*u_stride + k]           */
+    IAGO_RNG_FORCED = 2     /* replay: the k-th stone of game g is forced[g*f_stride + k] (no policy)   */
+};
+
+typedef struct iago_rng {
+    int32_t mode;
+    uint32_t stream_id;
+    uint64_t seed;
+    uint64_t game_id0;
+    const double *uniforms; /* device (or host for *_host calls) */
+    int64_t u_stride;
+    const int8_t *forced;   /* device (or host for *_host calls) */
+    int64_t f_stride;
+} iago_rng;
+
+IAGO_API int iago_abi_version(void);
+IAGO_API const char *iago_last_error(void);
+
+/* Device + stream + weight slots.  Replaces the per-object model construction of the reference
+ * (mcts_self_play.py:18-19 reloads rollout_model.npz for every rollout). */
+IAGO_API int iago_ctx_create(int device, iago_ctx **out);
+IAGO_API int iago_ctx_destroy(iago_ctx *ctx);
+IAGO_API int iago_ctx_sync(iago_ctx *ctx);
+/* cudaStream_t of the context (for callers that want to order their own work after ours). */
+IAGO_API void *iago_ctx_stream(iago_ctx *ctx);
+
+/* RolloutPolicy parameters: conv1/W [1][2][3][3] and bias2/b [64] (network.py:49-64). HOST pointers. */
+IAGO_API int iago_load_rollout(iago_ctx *ctx, const float *conv1_W, const float *bias2_b);
+
+/* GameFunctions.legal_actions(state, color) (game.py:209-235; clones mcts_self_play.py:64-89,
+ * src/rl_self_play.py:63-88, rl_env.py:114-138).  moves[i] = bit mask of legal actions (ascending bit
+ * order = the reference's ascending list). */
+IAGO_API int iago_legal_actions(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
+                       uint64_t *moves, int64_t n, void *stream);
+
+/* GameFunctions.place_stone(state, action, color) (game.py:179-207), in place, no legality check,
+ * action -1 = no-op (game.py:181-182). */
+IAGO_API int iago_place_stone(iago_ctx *ctx, uint64_t *p1, uint64_t *p2, const int8_t *action, const uint8_t *color,
+                     int64_t n, void *stream);
+
+/* Simulate(state)(color) for n independent games (mcts_self_play.py:9-134), one lockstep kernel.
+ *   in : p1, p2 [n] start boards; color [n] = the side that moves first AND the side the result is for
+ *   out: result [n] in {+1,0,-1} (judge, mcts_self_play.py:113-121); final_p1/final_p2 [n];
+ *        n_moves [n] stones placed (nullable); move_log [n][64] actions in order, -1 padded (nullable);
+ *        counters[2] += {stones placed, turns taken} over the batch (nullable, device uint64)          */
+IAGO_API int iago_rollout(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
+                 const iago_rng *rng, int8_t *result, uint64_t *final_p1, uint64_t *final_p2,
+                 int32_t *n_moves, int8_t *move_log, uint64_t *counters, void *stream);
+
+/* Same, HOST buffers in and out (pinned staging inside the context); synchronous.  This is the call the
+ * Python facade `Simulate` / `simulate_batch` makes and the one bench.py's e2e figure times. */
+IAGO_API int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
+                      const iago_rng *rng, int8_t *result, uint64_t *final_p1, uint64_t *final_p2,
+                      int32_t *n_moves, int8_t *move_log, uint64_t *counters_host);
+
+/* One Simulate.get_action draw per board (mcts_self_play.py:100-110): legal moves, rollout policy, masked
+ * renormalised inverse-cdf sample.  No board update.  action[i] = -1 when the side to move has no legal move.
+ * PHILOX: the draw-th uniform of game game_id0+i; UNIFORMS: uniforms[i] (u_stride ignored). */
+IAGO_API int iago_rollout_sample(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
+                        const iago_rng *rng, uint32_t draw, int8_t *action, void *stream);
+
+/* RolloutPolicy forward on make_state_var(state, color) (network.py:59-64, game.py:167-174):
+ * logits [n][64] (pre-softmax) in the canonical summation order of DESIGN.md. */
+IAGO_API int iago_rollout_logits(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
+                        float *logits, int64_t n, void *stream);
+
+/* Integer-issue micro-benchmark used as the roofline denominator of the rollout kernel:
+ * runs `iters` rounds of dependent LOP3/SHF chains on every SM and returns int32 lane-ops/s. */
+IAGO_API int iago_measure_int_peak(iago_ctx *ctx, int iters, double *lane_ops_per_s);
+
+/* Timing helper for callers that cannot create CUDA events themselves (ctypes): elapsed ms of the last
+ * iago_rollout* launch measured with CUDA events on the launching stream (kernel only). */
+IAGO_API int iago_last_kernel_ms(iago_ctx *ctx, float *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IAGO_B200_H */

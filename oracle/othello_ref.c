@@ -27,8 +27,9 @@
  *   e[k]     = exp32(logit[k] - max over LEGAL k)   only at legal cells (the reference's softmax
  *              denominator and its fp32 division cancel in p/sum(p); dropping them changes
  *              p by <= a few ulp_f32, the same size as numpy-vs-libm exp differences)
- *   choice   = first legal k (ascending) with cum_k > u * total, cum in float64
- *              == searchsorted(cumsum(p)/cumsum(p)[-1], u, 'right') up to 1 ulp_f64 of the edge
+ *   choice   = fixed-point inverse cdf: q_k = floor(e_k * 2^50), cum in uint64 (exact, associative),
+ *              first legal k (ascending) with cum_k > floor(m53 * total / 2^53), m53 = floor(u * 2^53)
+ *              == searchsorted(cumsum(p)/cumsum(p)[-1], u, 'right') of np.random.choice up to ~2^-50
  *   exp32    = Cephes-style range reduction + degree-5 polynomial, every step an explicit
  *              fmaf / single rounding, so gcc and nvcc produce identical bits.
  *   uniforms = Philox4x32-10, key = seed, counter = (game_lo, game_hi, draw, stream);
@@ -145,11 +146,15 @@ EXPORT void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], u
     philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1], out);
 }
 
-static inline double philox_uniform(uint64_t seed, uint64_t game, uint32_t draw, uint32_t stream) {
+static inline uint64_t philox_m53(uint64_t seed, uint64_t game, uint32_t draw, uint32_t stream) {
     uint32_t o[4];
     philox4x32_10((uint32_t)game, (uint32_t)(game >> 32), draw, stream,
                   (uint32_t)seed, (uint32_t)(seed >> 32), o);
-    return ((double)(o[0] >> 5) * 67108864.0 + (double)(o[1] >> 6)) * (1.0 / 9007199254740992.0);
+    return ((uint64_t)(o[0] >> 5) << 26) | (uint64_t)(o[1] >> 6);
+}
+
+static inline double philox_uniform(uint64_t seed, uint64_t game, uint32_t draw, uint32_t stream) {
+    return (double)philox_m53(seed, game, draw, stream) * (1.0 / 9007199254740992.0);
 }
 
 EXPORT double oracle_philox_uniform(uint64_t seed, uint64_t game, uint32_t draw, uint32_t stream) {
@@ -181,56 +186,61 @@ static inline float exp32_neg(float x) {
 
 EXPORT float oracle_exp32_neg(float x) { return exp32_neg(x); }
 
-/* network.py:59-64 on make_state_var(state, color): channel 0 = opponent, channel 1 = mover.
- * logits[64] before softmax, canonical summation order. */
-EXPORT void oracle_rollout_logits(const float *state, int color, const float *W /*[2][3][3]*/,
-                                  const float *b /*[64]*/, float *logits) {
-    float st[64];
-    for (int k = 0; k < 64; k++) {
-        float s = state[k];
-        /* game.py:169-171: state*(3-state)*(3-state)/2 swaps 1<->2 exactly in fp32 */
-        st[k] = (color == 1) ? s * (3.0f - s) * (3.0f - s) / 2.0f : s;
-    }
-    for (int i = 0; i < 8; i++)
-        for (int j = 0; j < 8; j++) {
-            float S[2];
-            for (int c = 0; c < 2; c++) {
-                float acc = 0.0f;
-                for (int ky = 0; ky < 3; ky++)
-                    for (int kx = 0; kx < 3; kx++) {
-                        int y = i + ky - 1, x = j + kx - 1;
-                        if (is_outside(y, x)) continue;
-                        float xv = (st[y * 8 + x] == (float)(c + 1)) ? 1.0f : 0.0f;
-                        if (xv != 0.0f) acc = acc + W[c * 9 + ky * 3 + kx] * xv;
-                    }
-                S[c] = acc;
+/* network.py:59-64 on make_state_var(state, color): channel 0 = opponent, channel 1 = mover
+ * (game.py:169-171 swaps 1<->2 for colour 1 via state*(3-state)*(3-state)/2, exact in fp32, then
+ * channel c = (state == c+1); the net effect is channel 0 = (cell == 3-color), channel 1 = (cell == color)).
+ * One output cell, canonical summation order. */
+static inline float rollout_logit_at(const float *state, int color, const float *W, const float *b, int i, int j) {
+    float S[2];
+    for (int c = 0; c < 2; c++) {
+        const float who = (c == 0) ? (float)(3 - color) : (float)color;
+        float acc = 0.0f;
+        for (int ky = 0; ky < 3; ky++)
+            for (int kx = 0; kx < 3; kx++) {
+                int y = i + ky - 1, x = j + kx - 1;
+                if (is_outside(y, x)) continue;
+                if (state[y * 8 + x] == who) acc = acc + W[c * 9 + ky * 3 + kx];
             }
-            logits[i * 8 + j] = (S[0] + S[1]) + b[i * 8 + j];
-        }
+        S[c] = acc;
+    }
+    return (S[0] + S[1]) + b[i * 8 + j];
 }
 
-/* mcts_self_play.py:100-110 with the uniform supplied by the caller. */
+/* logits[64] before softmax */
+EXPORT void oracle_rollout_logits(const float *state, int color, const float *W /*[2][3][3]*/,
+                                  const float *b /*[64]*/, float *logits) {
+    for (int k = 0; k < 64; k++) logits[k] = rollout_logit_at(state, color, W, b, k / 8, k % 8);
+}
+
+/* mcts_self_play.py:100-110 with the uniform supplied by the caller as m53 = floor(u * 2^53).
+ * Fixed-point inverse-cdf: q_k = floor(e_k * 2^50) (exact for e_k >= 2^-26), cum in uint64,
+ * choice = first legal k (ascending) with cum_k > floor(m53 * total / 2^53)
+ *        <=> cum_k / total > u, i.e. searchsorted(cdf, u, 'right') of np.random.choice. */
 static int sample_action(const float *state, int color, const int *actions, int n,
-                         const float *W, const float *b, double u) {
+                         const float *W, const float *b, uint64_t m53) {
     float logits[64];
-    oracle_rollout_logits(state, color, W, b, logits);
+    /* only the legal cells survive the mask (mcts_self_play.py:103-105) */
+    for (int a = 0; a < n; a++) logits[actions[a]] = rollout_logit_at(state, color, W, b, actions[a] / 8, actions[a] % 8);
     float m = logits[actions[0]];
     for (int a = 1; a < n; a++) if (logits[actions[a]] > m) m = logits[actions[a]];
-    double cum[64], total = 0.0;
+    uint64_t cum[64], total = 0;
     for (int a = 0; a < n; a++) {
-        total = total + (double)exp32_neg(logits[actions[a]] - m);
+        float e = exp32_neg(logits[actions[a]] - m);
+        total += (uint64_t)(e * 1125899906842624.0f); /* 2^50: exact scaling, truncating convert */
         cum[a] = total;
     }
-    double t = u * total;
-    for (int a = 0; a < n; a++) if (cum[a] > t) return actions[a];
+    uint64_t T = (uint64_t)(((unsigned __int128)m53 * total) >> 53);
+    for (int a = 0; a < n; a++) if (cum[a] > T) return actions[a];
     return actions[n - 1];
 }
+
+static inline uint64_t m53_of_double(double u) { return (uint64_t)(u * 9007199254740992.0); }
 
 EXPORT int oracle_rollout_sample(const float *state, int color, const float *W, const float *b, double u) {
     int acts[64];
     int n = oracle_legal_actions(state, color, acts);
     if (n == 0) return -1;
-    return sample_action(state, color, acts, n, W, b, u);
+    return sample_action(state, color, acts, n, W, b, m53_of_double(u));
 }
 
 /* ------------------------------------------------------------------ Simulate */
@@ -265,10 +275,10 @@ static int simulate_one(float *state, int color, uint64_t game_id, int64_t g, co
                 if (rng->mode == RNG_FORCED) {
                     action = rng->forced[g * rng->f_stride + placed];
                 } else {
-                    double u = rng->mode == RNG_UNIFORMS
-                                   ? rng->uniforms[g * rng->u_stride + placed]
-                                   : philox_uniform(rng->seed, game_id, (uint32_t)placed, rng->stream);
-                    action = sample_action(state, c, acts, n, W, b, u);
+                    uint64_t m = rng->mode == RNG_UNIFORMS
+                                     ? m53_of_double(rng->uniforms[g * rng->u_stride + placed])
+                                     : philox_m53(rng->seed, game_id, (uint32_t)placed, rng->stream);
+                    action = sample_action(state, c, acts, n, W, b, m);
                 }
                 oracle_place_stone(state, action, c);
                 if (moves) moves[placed] = (int8_t)action;

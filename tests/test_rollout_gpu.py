@@ -1,0 +1,177 @@
+"""The lockstep rollout kernel (through the C ABI) vs the reference goldens and the CPU oracle — bit exact."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def bb(states):
+    from iago_b200 import boards
+    return boards.to_bitboards(states)
+
+
+def test_golden_trajectories_uniform_replay(engine, golden_simulate):
+    """1,200 games of the UNMODIFIED reference, replayed on the GPU from the same uniform stream."""
+    from iago_b200 import Rng, boards
+    g = golden_simulate
+    p1, p2 = bb(g["start"])
+    out = engine.rollout_host(p1, p2, g["color"].astype(np.uint8), rng=Rng.replay_uniforms(g["uniforms"]), want_moves=True)
+    assert (out["moves"] == g["moves"]).all()
+    assert (out["n_moves"] == g["n_moves"]).all()
+    assert (out["result"] == g["result"]).all()
+    final = boards.from_bitboards(out["final_p1"], out["final_p2"]).reshape(-1, 64).astype(np.uint8)
+    assert (final == g["final"]).all()
+    assert int(out["counters"][0]) == int(g["n_moves"].sum())
+
+
+def test_golden_forced_replay(engine, golden_simulate):
+    from iago_b200 import Rng, boards
+    g = golden_simulate
+    p1, p2 = bb(g["start"])
+    out = engine.rollout_host(p1, p2, g["color"].astype(np.uint8), rng=Rng.replay_moves(g["moves"]), want_moves=True)
+    final = boards.from_bitboards(out["final_p1"], out["final_p2"]).reshape(-1, 64).astype(np.uint8)
+    assert (final == g["final"]).all() and (out["result"] == g["result"]).all()
+    assert (out["moves"] == g["moves"]).all()
+
+
+def test_65536_games_philox_vs_oracle(engine, cref, rollout_weights):
+    """BASELINE config 2: 65,536 lockstep games from the opening, every trajectory bit-exact vs the CPU oracle."""
+    from iago_b200 import Rng, boards
+    W, b = rollout_weights
+    n = 65536
+    p1 = np.full(n, boards.START_P1, np.uint64)
+    p2 = np.full(n, boards.START_P2, np.uint64)
+    out = engine.rollout_host(p1, p2, np.ones(n, np.uint8), rng=Rng.philox(seed=2026, game_id0=0), want_moves=True)
+    st = np.tile(boards.start_state().reshape(1, 64), (n, 1))
+    ref = cref.simulate_batch(st, 1, W, b, mode=cref.RNG_PHILOX, seed=2026, game_id0=0, threads=0)
+    assert (out["moves"] == ref["moves"]).all()
+    assert (out["result"] == ref["results"]).all()
+    assert (out["n_moves"] == ref["n_moves"]).all()
+    r1, r2 = bb(ref["final"])
+    assert (out["final_p1"] == r1).all() and (out["final_p2"] == r2).all()
+    assert int(out["counters"][0]) == int(ref["n_moves"].sum()) and int(out["counters"][1]) == int(ref["n_turns"].sum())
+    # shape of the workload (BASELINE.md §2 probe: 59.8 stones / game)
+    assert 59.0 < out["n_moves"].mean() + 0.0 < 60.0
+
+
+def test_midgame_both_colours_vs_oracle(engine, cref, rollout_weights, golden_rules):
+    """Rollouts from harvested mid-game positions (what MCTS leaves look like), either side to move, incl. passes."""
+    from iago_b200 import Rng
+    W, b = rollout_weights
+    st = golden_rules["state"][:6000].astype(np.float32)
+    col = golden_rules["color"][:6000].astype(np.uint8)
+    p1, p2 = bb(st)
+    out = engine.rollout_host(p1, p2, col, rng=Rng.philox(seed=5, game_id0=10**12, stream_id=3), want_moves=True)
+    ref = cref.simulate_batch(st, col.astype(np.int32), W, b, mode=cref.RNG_PHILOX, seed=5, game_id0=10**12, stream=3, threads=0)
+    assert (out["moves"] == ref["moves"]).all() and (out["result"] == ref["results"]).all()
+    r1, r2 = bb(ref["final"])
+    assert (out["final_p1"] == r1).all() and (out["final_p2"] == r2).all()
+
+
+def test_arbitrary_boards_sample_vs_oracle(engine, cref, rollout_weights):
+    """Single draws on arbitrary boards, including > 34 legal moves (the kernel's recompute path)."""
+    from iago_b200 import Rng
+    W, b = rollout_weights
+    rng = np.random.default_rng(3)
+    n = 3000
+    st = np.zeros((n, 64), np.float32)
+    for i in range(n):
+        if i % 3 == 0:  # checker-ish boards with many empties next to brackets -> many legal moves
+            s = np.zeros((8, 8), np.float32)
+            s[1::3, :] = 2; s[2::3, :] = 1
+            s[rng.random((8, 8)) < 0.1] = 0
+            st[i] = s.reshape(64)
+        else:
+            fill = rng.random()
+            r = rng.random(64)
+            st[i] = np.where(r < fill * 0.5, 1, np.where(r < fill, 2, 0))
+    col = rng.integers(1, 3, n).astype(np.uint8)
+    u = rng.random(n)
+    p1, p2 = bb(st)
+    got = engine.rollout_sample_host(p1, p2, col, rng=Rng.replay_uniforms(u))
+    nmax = 0
+    for i in range(n):
+        nmax = max(nmax, len(cref.legal_actions(st[i], int(col[i]))))
+        assert int(got[i]) == cref.rollout_sample(st[i], int(col[i]), W, b, float(u[i]))
+    assert nmax > 34  # the slow path was exercised
+
+
+def test_logits_vs_oracle_and_reference(engine, cref, rollout_weights, golden_nets):
+    W, b = rollout_weights
+    g = golden_nets
+    p1, p2 = bb(g["state"])
+    got = engine.rollout_logits_host(p1, p2, g["color"].astype(np.uint8))
+    for i in range(len(p1)):
+        assert (got[i] == cref.rollout_logits(g["state"][i].astype(np.float32), int(g["color"][i]), W, b)).all()  # bit exact
+    e = np.exp(got.astype(np.float64) - got.max(axis=1, keepdims=True))
+    assert np.abs(e / e.sum(axis=1, keepdims=True) - g["rollout_prob"]).max() < 1e-6  # vs the reference's softmax output
+
+
+def test_device_api_and_properties_at_full_size(engine):
+    """Device-pointer entry point at 2^20 games: size-independent properties of a finished game."""
+    import torch
+    from iago_b200 import Rng, boards
+    n = 1 << 20
+    dev = torch.device("cuda", 0)
+    p1 = torch.full((n,), boards.START_P1, dtype=torch.int64, device=dev)
+    p2 = torch.full((n,), boards.START_P2, dtype=torch.int64, device=dev)
+    col = torch.ones(n, dtype=torch.uint8, device=dev)
+    cnt = torch.zeros(2, dtype=torch.int64, device=dev)
+    out = engine.rollout(p1, p2, col, rng=Rng.philox(seed=1), counters=cnt)
+    torch.cuda.synchronize()
+    f1, f2 = out["final_p1"].cpu().numpy().view(np.uint64), out["final_p2"].cpu().numpy().view(np.uint64)
+    assert (f1 & f2 == 0).all()                                     # no cell holds both colours
+    pc = lambda x: np.array([bin(int(v)).count("1") for v in x[:20000]])
+    n1, n2 = pc(f1), pc(f2)
+    nm = out["n_moves"].cpu().numpy()
+    assert (n1 + n2 == 4 + nm[:20000]).all()                         # one stone per placement
+    assert (np.sign(n1 - n2) == out["result"].cpu().numpy()[:20000]).all()  # judge
+    assert int(cnt[0]) == int(nm.sum())
+    # terminal: neither side has a legal move on any final board
+    lm1 = engine.legal_actions(out["final_p1"], out["final_p2"], col)
+    lm2 = engine.legal_actions(out["final_p1"], out["final_p2"], col + 1)
+    assert int((lm1 != 0).sum()) == 0 and int((lm2 != 0).sum()) == 0
+    # determinism + sharding invariance: a slice computed alone equals the same game ids in the big batch
+    sub = engine.rollout(p1[:4096], p2[:4096], col[:4096], rng=Rng.philox(seed=1, game_id0=65536))
+    assert torch.equal(sub["final_p1"], out["final_p1"][65536:65536 + 4096])
+
+
+def test_facade_simulate(engine, golden_simulate):
+    from iago_b200.mcts_self_play import Simulate, simulate_batch
+    from iago_b200 import boards
+    g = golden_simulate
+    for i in (0, 1, 1005):
+        s = g["start"][i].reshape(8, 8).astype(np.float32)
+        sim = Simulate(s, uniforms=g["uniforms"][i])
+        assert sim.stone_num == int((s != 0).sum()) and sim.pass_flg is False
+        r = sim(int(g["color"][i]))
+        assert r == g["result"][i] and (sim.state.reshape(64).astype(np.uint8) == g["final"][i]).all()
+        assert sim.moves == [int(a) for a in g["moves"][i] if a >= 0]
+        assert sim.judge(int(g["color"][i])) == r
+        assert (s.reshape(64).astype(np.uint8) == g["start"][i]).all()  # caller's board untouched (deepcopy)
+    # step-wise API: turn() by turn() reproduces the same game
+    i = 2
+    sim = Simulate(g["start"][i].reshape(8, 8).astype(np.float32), uniforms=g["uniforms"][i])
+    c = int(g["color"][i])
+    while sim.stone_num < 64:
+        sim.turn(c); sim.turn(3 - c)
+    assert (sim.state.reshape(64).astype(np.uint8) == g["final"][i]).all()
+    # default Philox path: deterministic per (seed, game id)
+    out = simulate_batch(np.tile(boards.start_state(), (8, 1, 1)), 1)
+    assert set(np.unique(out["result"])) <= {-1, 0, 1}
+
+
+def test_empty_and_error_paths(engine):
+    import torch
+    import iago_b200
+    from iago_b200 import Rng
+    out = engine.rollout_host(np.zeros(0, np.uint64), np.zeros(0, np.uint64), np.zeros(0, np.uint8))
+    assert out["result"].shape == (0,)
+    full = np.array([0xFFFFFFFF00000000, 0], np.uint64), np.array([0x00000000FFFFFFFF, 0], np.uint64)
+    out = engine.rollout_host(full[0], full[1], np.array([1, 2], np.uint8))   # full board / empty board
+    assert out["n_moves"].tolist() == [0, 0] and out["result"].tolist() == [0, 0]
+    with pytest.raises(iago_b200.IagoError):
+        engine.rollout_host(full[0], full[1], np.ones(2, np.uint8), rng=Rng(mode=7))
+    with pytest.raises(iago_b200.IagoError):
+        engine.legal_actions(torch.zeros(4, dtype=torch.int32, device="cuda"), torch.zeros(4, dtype=torch.int32, device="cuda"),
+                             torch.ones(4, dtype=torch.uint8, device="cuda"))

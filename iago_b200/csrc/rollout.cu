@@ -24,7 +24,7 @@
 namespace iago {
 
 constexpr int kBlock = 64;     // threads (= games) per CTA
-constexpr int kMaxLegal = 34;  // scratch slots per game; reachable Othello positions have <= 33 legal moves
+constexpr int kMaxLegal = 32;  // scratch slots per game; more legal moves than this (hill-climbed maximum is 34) take the recompute path
 
 // ---------------------------------------------------------------- device helpers
 
@@ -98,7 +98,7 @@ __device__ __forceinline__ int sample_move(const PolicySmem &w, u64 own, u64 opp
             const float l = __uint_as_float(sa[i * kBlock]);
             cum += q_of(exp32_neg(__fsub_rn(l, mx)));
             sa[i * kBlock] = (uint32_t)cum;
-            sb[i * kBlock] |= (uint32_t)(cum >> 32);  // cum < 34 * 2^50 < 2^56
+            sb[i * kBlock] |= (uint32_t)(cum >> 32);  // cum < 32 * 2^50 < 2^56
         }
         const u64 T = threshold(m53, cum);
         int idx = 0;
@@ -381,7 +381,7 @@ int iago_legal_actions(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, co
     IAGO_REQUIRE(n >= 0, "n < 0");
     if (n == 0) return IAGO_OK;
     DeviceGuard guard(ctx->device);
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t s = (cudaStream_t)stream;
     legal_actions_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((const u64 *)p1, (const u64 *)p2, color,
                                                                       (u64 *)moves, n);
     IAGO_CUDA(cudaGetLastError());
@@ -394,7 +394,7 @@ int iago_place_stone(iago_ctx *ctx, uint64_t *p1, uint64_t *p2, const int8_t *ac
     IAGO_REQUIRE(n >= 0, "n < 0");
     if (n == 0) return IAGO_OK;
     DeviceGuard guard(ctx->device);
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t s = (cudaStream_t)stream;
     place_stone_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>((u64 *)p1, (u64 *)p2, action, color, n);
     IAGO_CUDA(cudaGetLastError());
     return IAGO_OK;
@@ -410,7 +410,7 @@ int iago_rollout_logits(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, c
     }
     if (n == 0) return IAGO_OK;
     DeviceGuard guard(ctx->device);
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t s = (cudaStream_t)stream;
     rollout_logits_kernel<<<(unsigned)((n * 64 + 255) / 256), 256, 0, s>>>((const u64 *)p1, (const u64 *)p2, color,
                                                                            logits, n, ctx->d_rollout);
     IAGO_CUDA(cudaGetLastError());
@@ -426,7 +426,7 @@ int iago_rollout_sample(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, c
     IAGO_REQUIRE(rng->mode != IAGO_RNG_FORCED, "rng.mode FORCED is meaningless for a single draw");
     if (n == 0) return IAGO_OK;
     DeviceGuard guard(ctx->device);
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t s = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
     if (rng->mode == IAGO_RNG_UNIFORMS)
         rollout_sample_kernel<IAGO_RNG_UNIFORMS><<<grid, kBlock, 0, s>>>((const u64 *)p1, (const u64 *)p2, color, n,
@@ -447,7 +447,7 @@ int iago_rollout(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const ui
     if (rc) return rc;
     if (n == 0) return IAGO_OK;
     DeviceGuard guard(ctx->device);
-    cudaStream_t s = stream ? (cudaStream_t)stream : ctx->stream;
+    cudaStream_t s = (cudaStream_t)stream;
     RolloutArgs a{(const u64 *)p1, (const u64 *)p2, color, n, rng->stream_id, rng->seed, rng->game_id0,
                   rng->uniforms, rng->u_stride, rng->forced, rng->f_stride, result, (u64 *)final_p1,
                   (u64 *)final_p2, n_moves, move_log, (u64 *)counters};

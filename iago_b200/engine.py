@@ -201,7 +201,8 @@ class Engine:
 
     def _to_dev(self, a, dtype):
         torch = _torch()
-        return torch.from_numpy(np.ascontiguousarray(a).view(dtype) if dtype is not None else a).to(self._dev())
+        a = np.array(a, copy=True)  # broadcast views are read-only; torch wants a writable buffer
+        return torch.from_numpy(a.view(dtype) if dtype is not None else a).to(self._dev())
 
     def legal_actions_host(self, p1, p2, color):
         p1 = np.ascontiguousarray(p1, np.uint64).reshape(-1)

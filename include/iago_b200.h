@@ -12,8 +12,10 @@
  *   - Plain pointers and sizes only.  Unless a function name ends in _host, data pointers are DEVICE
  *     pointers owned by the caller (e.g. torch tensors); they are never freed or retained past the call.
  *     Small model parameters (weights) are HOST pointers and are copied.
- *   - Launches are asynchronous on the cudaStream_t passed as `void *stream` (NULL = the context's own
- *     stream).  *_host entry points take HOST buffers, do H2D + kernel + D2H, and synchronise before return.
+ *   - Launches are asynchronous on the cudaStream_t passed as `void *stream`; NULL is CUDA's legacy default
+ *     stream, exactly as in the runtime API (pass iago_ctx_stream(ctx) for the context's own non-blocking
+ *     stream).  *_host entry points take HOST buffers, do H2D + kernel + D2H on the context's stream, and
+ *     synchronise before return.
  *   - Boards are bitboard pairs: bit k <-> action k = row*8+col of the reference's 8x8 array
  *     (game.py:126,184).  p1 = stones of colour 1 (moves first), p2 = colour 2.  colour in {1,2}.
  *   - One context per device; a context is not re-entrant.  Different contexts may be used from

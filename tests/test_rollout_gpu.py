@@ -68,32 +68,42 @@ def test_midgame_both_colours_vs_oracle(engine, cref, rollout_weights, golden_ru
     assert (out["final_p1"] == r1).all() and (out["final_p2"] == r2).all()
 
 
+MANY_MOVES = [  # hill-climbed boards with 34 / 34 / 33 legal moves for colour 1 (more than the kernel's 32 scratch slots)
+    "0120100002100220021201200021011001010120021220200212000000000021",
+    "0000002112020000211122200220110000002120000001101201222011100000",
+    "0000110020221202100110012021000000021220001011200210222101100000",
+]
+
+
 def test_arbitrary_boards_sample_vs_oracle(engine, cref, rollout_weights):
-    """Single draws on arbitrary boards, including > 34 legal moves (the kernel's recompute path)."""
+    """Single draws on arbitrary boards, including > 32 legal moves (the kernel's recompute path)."""
     from iago_b200 import Rng
     W, b = rollout_weights
     rng = np.random.default_rng(3)
     n = 3000
     st = np.zeros((n, 64), np.float32)
+    many = np.array([[int(ch) for ch in s] for s in MANY_MOVES], np.float32)
     for i in range(n):
-        if i % 3 == 0:  # checker-ish boards with many empties next to brackets -> many legal moves
-            s = np.zeros((8, 8), np.float32)
-            s[1::3, :] = 2; s[2::3, :] = 1
-            s[rng.random((8, 8)) < 0.1] = 0
-            st[i] = s.reshape(64)
+        if i % 3 == 0:
+            st[i] = many[(i // 3) % 3]
+            if i >= 9:  # perturb a few cells, keeps the move count high
+                idx = rng.integers(0, 64, 2)
+                st[i, idx] = rng.integers(0, 3, 2)
         else:
             fill = rng.random()
             r = rng.random(64)
             st[i] = np.where(r < fill * 0.5, 1, np.where(r < fill, 2, 0))
     col = rng.integers(1, 3, n).astype(np.uint8)
+    col[::3] = 1
     u = rng.random(n)
+    u[:9] = [0.0, 0.999999999, 0.5, 1 - 2.0**-53, 0.25, 0.75, 0.1, 0.9, 0.33]
     p1, p2 = bb(st)
     got = engine.rollout_sample_host(p1, p2, col, rng=Rng.replay_uniforms(u))
-    nmax = 0
+    counts = []
     for i in range(n):
-        nmax = max(nmax, len(cref.legal_actions(st[i], int(col[i]))))
+        counts.append(len(cref.legal_actions(st[i], int(col[i]))))
         assert int(got[i]) == cref.rollout_sample(st[i], int(col[i]), W, b, float(u[i]))
-    assert nmax > 34  # the slow path was exercised
+    assert max(counts) >= 34 and sum(c > 32 for c in counts) >= 3  # the recompute path was exercised
 
 
 def test_logits_vs_oracle_and_reference(engine, cref, rollout_weights, golden_nets):

@@ -31,6 +31,9 @@ SIGNATURES = {
     "iago_rollout_host": [_P, _P, _P, _P, C.c_int64, C.POINTER(IagoRng), _P, _P, _P, _P, _P, _P],
     "iago_rollout_sample": [_P, _P, _P, _P, C.c_int64, C.POINTER(IagoRng), C.c_uint32, _P, _P],
     "iago_rollout_logits": [_P, _P, _P, _P, _P, C.c_int64, _P],
+    "iago_load_net": [_P, C.c_int, C.c_int, _P, C.c_int64],
+    "iago_policy_forward": [_P, C.c_int, _P, _P, _P, C.c_int64, _P, C.c_int, C.c_int, _P],
+    "iago_value_forward": [_P, C.c_int, _P, _P, _P, C.c_int64, _P, C.c_int, _P],
     "iago_measure_int_peak": [_P, C.c_int, C.POINTER(C.c_double)],
     "iago_last_kernel_ms": [_P, C.POINTER(C.c_float)],
 }

@@ -1,5 +1,586 @@
-// trunk.cu — placeholder until the conv-net kernels land.
+// trunk.cu — K3/K4: SLPolicy / Value forward as ONE fused, persistent tcgen05 kernel per batch.
+//
+// Reference: network.py:5-13 (Block = 3x3 conv pad 1 + bias + ReLU), network.py:15-47 (SLPolicy: 8 blocks,
+// conv9 1x1 128->1 no bias, +bias10.b[64], softmax), network.py:66-96 (Value: same trunk, block9 3x3 128->1
+// + bias + ReLU, fc10 64->128 no bias, dropout off at inference, fc11 128->1 no bias), input encoding
+// game.py:167-174 (channel 0 = opponent stones, channel 1 = mover's stones).
+//
+// Design (DESIGN.md "conv trunk"):
+//   * One CTA owns a tile of 2 boards = 128 positions = the M of one tcgen05.mma (cta_group::1, M=128).
+//     Row m of the tile is (board-row r, board b, column c) with m = (r*2+b)*8 + c, so that an 8-row UMMA core
+//     matrix is one board row and consecutive core matrices are a constant 160 B apart.
+//   * The whole trunk stays on chip.  The activation tile lives in shared memory as
+//     [channel-group of 8][padded row 0..9][board 0..1][padded col 0..9][8 x fp16] (no-swizzle K-major canonical
+//     layout).  A 3x3 tap (dy,dx) is then just a different descriptor START ADDRESS on the same tile — implicit
+//     GEMM with the zero halo supplying the conv padding; nothing is ever re-laid-out or written to HBM.
+//   * Weights are pre-packed on the host into the B-operand core-matrix layout, one "unit" per
+//     (layer, tap, 64-channel chunk), and streamed L2 -> smem with cp.async.bulk (TMA 1D) through a 3-stage
+//     mbarrier ring by a producer thread that runs ahead across layer and tile boundaries.
+//   * Accumulators live in TMEM (128 fp32 columns).  The epilogue warps read them with tcgen05.ld, add bias,
+//     ReLU, and write the next layer's activation tile in place (the MMAs of the layer are complete by then).
+//   * Precision: fp16 operands, fp32 accumulate.  precision=3 splits both operands into hi + lo fp16 parts and
+//     issues three MMAs per step (hi*hi + lo*hi + hi*lo), which recovers ~fp32 accuracy (max-abs logit error
+//     ~1e-4 on sl_model.npz); precision=1 is the single-pass fp16 path (max-abs ~0.1).  SURVEY.md §0.5.
+//   * Heads: policy = per-row dot with conv9 (fp32, CUDA cores) in the layer-8 epilogue (+bias10, optional
+//     softmax); value = block9 as a ninth MMA layer with N padded to 16, then relu and the collapsed
+//     fc11*fc10 64-vector.
+#include <cuda_fp16.h>
+#include <string.h>
+
+#include <vector>
+
+#include "bitboard.cuh"
 #include "common.cuh"
+
 namespace iago {
-void trunk_destroy(iago_ctx *) {}
+
+// ---------------------------------------------------------------- geometry
+constexpr int kTileRows = 128;                    // M of the MMA = 2 boards
+constexpr int kGroupBytes = 10 * 2 * 10 * 16;     // one 8-channel group of the padded tile: 3200 B  (= LBO of A)
+constexpr int kRowPitch = 10 * 16;                // 160 B between consecutive 8-row core matrices     (= SBO of A)
+constexpr int kActBytes = 16 * kGroupBytes;       // 128 channels: 51,200 B per precision part
+constexpr int kA1Bytes = 4 * kTileRows * 16;      // layer-1 explicit im2col tile, K = 32: 8,192 B
+constexpr int kStageBytes = 32768;                // one weight unit: hi [8][128][8] + lo
+constexpr int kStages = 3;
+constexpr int kMaxLayers = 9;
+constexpr int kThreads = 192;                     // warps 0-3 epilogue (TMEM lanes 32w..), warp 4 producer, warp 5 MMA
+constexpr int kTmemCols = 128;
+
+constexpr int OFF_AHI = 0;
+constexpr int OFF_ALO = OFF_AHI + kActBytes;
+constexpr int OFF_A1 = OFF_ALO + kActBytes;
+constexpr int OFF_STAGE = OFF_A1 + kA1Bytes;
+constexpr int OFF_BIAS = OFF_STAGE + kStages * kStageBytes;   // float [9][128]
+constexpr int OFF_HEAD = OFF_BIAS + kMaxLayers * 128 * 4;      // float w9[128], b10[64], wfc[64]
+constexpr int OFF_SCRATCH = OFF_HEAD + 256 * 4;                // float [2][64]
+constexpr int OFF_BAR = OFF_SCRATCH + 128 * 4;                 // mbarriers + tmem pointer
+constexpr int kSmemBytes = OFF_BAR + 128;
+
+struct LayerDesc {
+    int n_units;     // weight units (tap x 64-channel chunk), consumed in order
+    int ksteps;      // K=16 MMA steps per unit
+    int n;           // N of the MMA (output channels, padded)
+    int unit_bytes;  // hi + lo
+    int lo_off;      // byte offset of the lo block inside a unit
+    int b_lbo;       // B operand: bytes between K-adjacent core matrices (= n * 16)
+    int chunks;      // 64-channel chunks per tap (1 or 2); 0 for the explicit layer 1
+};
+
+struct NetDesc {
+    int n_layers;    // 8 (policy) or 9 (value)
+    int kind;        // 0 = SL policy, 1 = value
+    LayerDesc layer[kMaxLayers];
+    long long unit_base[kMaxLayers];  // byte offset of the layer's first unit in the weight blob
+};
+
+// ---------------------------------------------------------------- PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+// Spins on the phase parity.  A generous clock-based watchdog turns a protocol bug into a trap instead of a hang.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    const long long t0 = clock64();
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 2 GHz
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t &v) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
+// LBO>>4 [16,30) = bytes between K-adjacent core matrices, SBO>>4 [32,46) = bytes between M/N-adjacent core
+// matrices, version=1 [46,48), layout_type=0 (SWIZZLE_NONE) [61,64).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo, uint32_t sbo) {
+    return (uint64_t)((addr >> 4) & 0x3FFF) | ((uint64_t)((lbo >> 4) & 0x3FFF) << 16) |
+           ((uint64_t)((sbo >> 4) & 0x3FFF) << 32) | (1ULL << 46);
+}
+// cute::UMMA::InstrDescriptor for kind::f16: c_format=F32 [4,6), a/b_format=F16 (0), K-major both, N>>3 [17,23), M>>4 [24,29)
+__device__ __forceinline__ uint32_t instr_desc(int m, int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24); }
+
+struct TrunkArgs {
+    const u64 *p1, *p2;
+    const uint8_t *color;
+    long long n;          // positions
+    float *out;           // policy: [n][64]; value: [n]
+    int out_kind;         // policy: 0 = logits, 1 = softmax probabilities
+    int precision;        // 1 = fp16 single pass, 3 = hi/lo split (3 MMAs)
+    const uint8_t *blob;  // packed weight units
+    const float *bias;    // [n_layers][128]
+    const float *head;    // policy: w9[128], b10[64]; value: b9 at [0], wfc[64] at [128..192)
+};
+
+__global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const NetDesc *__restrict__ gnet) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ NetDesc net;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar_full = sbase + OFF_BAR, bar_empty = bar_full + 8 * kStages;
+    const uint32_t bar_acc = bar_empty + 8 * kStages, bar_act = bar_acc + 8;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 * (2 * kStages + 2));
+
+    // ---- one-time setup
+    for (int i = tid; i < (int)(sizeof(NetDesc) / 4); i += kThreads) reinterpret_cast<int *>(&net)[i] = reinterpret_cast<const int *>(gnet)[i];
+    for (int i = tid; i < (OFF_A1 + kA1Bytes) / 16; i += kThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
+    __syncthreads();
+    {
+        float *sb = reinterpret_cast<float *>(smem + OFF_BIAS);
+        for (int i = tid; i < net.n_layers * 128; i += kThreads) sb[i] = a.bias[i];
+        float *sh = reinterpret_cast<float *>(smem + OFF_HEAD);
+        for (int i = tid; i < 256; i += kThreads) sh[i] = a.head[i];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < kStages; s++) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        mbar_init(bar_act, 128);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 4) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    const long long n_tiles = (a.n + 1) / 2;
+    const int L = net.n_layers;
+    const bool split = a.precision >= 3;
+
+    if (warp == 4) {
+        // ================= producer: stream weight units L2 -> smem ring =================
+        if ((tid & 31) == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int l = 0; l < L; l++) {
+                    const LayerDesc ld = net.layer[l];
+                    const uint8_t *src = a.blob + net.unit_base[l];
+                    const uint32_t bytes = split ? (uint32_t)ld.unit_bytes : (uint32_t)ld.lo_off;  // single pass needs hi only
+                    for (int u = 0; u < ld.n_units; u++) {
+                        mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        mbar_expect_tx(bar_full + 8 * stage, bytes);
+                        bulk_g2s(sbase + OFF_STAGE + stage * kStageBytes, src + (long long)u * ld.unit_bytes, bytes, bar_full + 8 * stage);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ================= MMA issuer: one thread =================
+        if ((tid & 31) == 0) {
+            uint32_t stage = 0, phase = 0, act_phase = 0;
+            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+                for (int l = 0; l < L; l++) {
+                    const LayerDesc ld = net.layer[l];
+                    const uint32_t idesc = instr_desc(kTileRows, ld.n);
+                    mbar_wait(bar_act, act_phase);  // activation tile of this layer is written, TMEM is drained
+                    act_phase ^= 1;
+                    tc_fence_after();
+                    uint32_t acc = 0;
+                    for (int u = 0; u < ld.n_units; u++) {
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        const uint32_t bst = sbase + OFF_STAGE + stage * kStageBytes;
+                        uint32_t a_hi, a_lo, a_lbo, a_sbo;
+                        if (ld.chunks == 0) {  // layer 1: explicit im2col tile [4][128][16 B]
+                            a_hi = sbase + OFF_A1; a_lo = a_hi; a_lbo = kTileRows * 16; a_sbo = 128;
+                        } else {
+                            const int tap = u / ld.chunks, chunk = u - tap * ld.chunks;
+                            const int ky = tap / 3, kx = tap - ky * 3;  // (dy,dx) = (ky-1,kx-1); the halo is at padded index 0
+                            const uint32_t off = (uint32_t)chunk * 8 * kGroupBytes + (uint32_t)((ky * 2) * 10 + kx) * 16;
+                            a_hi = sbase + OFF_AHI + off; a_lo = sbase + OFF_ALO + off; a_lbo = kGroupBytes; a_sbo = kRowPitch;
+                        }
+                        for (int ks = 0; ks < ld.ksteps; ks++) {
+                            const uint64_t ah = smem_desc(a_hi + 2 * ks * a_lbo, a_lbo, a_sbo);
+                            const uint64_t bh = smem_desc(bst + 2 * ks * ld.b_lbo, ld.b_lbo, 128);
+                            umma_f16(tmem, ah, bh, idesc, acc);
+                            acc = 1;
+                            if (split) {
+                                const uint64_t bl = smem_desc(bst + ld.lo_off + 2 * ks * ld.b_lbo, ld.b_lbo, 128);
+                                umma_f16(tmem, ah, bl, idesc, 1);
+                                if (ld.chunks != 0) {  // layer-1 inputs are exactly 0/1: no lo part
+                                    const uint64_t al = smem_desc(a_lo + 2 * ks * a_lbo, a_lbo, a_sbo);
+                                    umma_f16(tmem, al, bh, idesc, 1);
+                                }
+                            }
+                        }
+                        umma_commit(bar_empty + 8 * stage);  // frees the weight stage when these MMAs retire
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    }
+                    umma_commit(bar_acc);  // accumulator of this layer complete
+                }
+            }
+        }
+    } else {
+        // ================= epilogue warps: thread m owns tile row m = TMEM lane m =================
+        const int m = tid;
+        const int g = m >> 3, c = m & 7, r = g >> 1, b = g & 1;
+        const uint32_t row_off = (uint32_t)(((r + 1) * 2 + b) * 10 + (c + 1)) * 16;  // interior cell of the padded tile
+        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        const float *sbias = reinterpret_cast<const float *>(smem + OFF_BIAS);
+        const float *shead = reinterpret_cast<const float *>(smem + OFF_HEAD);
+        float *scratch = reinterpret_cast<float *>(smem + OFF_SCRATCH);
+        const int cell = r * 8 + c;
+        uint32_t acc_phase = 0;
+        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const long long pos = tile * 2 + b;
+            const bool valid = pos < a.n;
+            // ---- layer-1 input: explicit im2col of the two bit planes, k = tap*2 + channel (0 = opponent, 1 = mover)
+            {
+                u64 own = 0, opp = 0;
+                if (valid) {
+                    const bool first = a.color[pos] == 1;
+                    const u64 x1 = a.p1[pos], x2 = a.p2[pos];
+                    own = first ? x1 : x2;
+                    opp = first ? x2 : x1;
+                }
+                uint32_t bits = 0;
+#pragma unroll
+                for (int t = 0; t < 9; t++) {
+                    const int y = r + t / 3 - 1, x = c + t % 3 - 1;
+                    if (y >= 0 && y < 8 && x >= 0 && x < 8) {
+                        const int k = y * 8 + x;
+                        bits |= (uint32_t)((opp >> k) & 1) << (2 * t);
+                        bits |= (uint32_t)((own >> k) & 1) << (2 * t + 1);
+                    }
+                }
+#pragma unroll
+                for (int kg = 0; kg < 4; kg++) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const uint32_t lo = (bits >> (kg * 8 + 2 * e)) & 1, hi = (bits >> (kg * 8 + 2 * e + 1)) & 1;
+                        w[e] = (lo ? 0x3C00u : 0u) | (hi ? 0x3C000000u : 0u);  // fp16 1.0 = 0x3C00
+                    }
+                    *reinterpret_cast<uint4 *>(smem + OFF_A1 + kg * (kTileRows * 16) + m * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            fence_async_smem();
+            tc_fence_before();
+            mbar_arrive(bar_act);
+
+            for (int l = 0; l < L; l++) {
+                const LayerDesc ld = net.layer[l];
+                mbar_wait(bar_acc, acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                const bool last_trunk = (l == 7);
+                const bool value_head = (l == 8);
+                if (!value_head) {
+                    float dot = 0.0f;
+                    for (int cb = 0; cb < ld.n / 32; cb++) {
+                        uint32_t v[32];
+                        tmem_ld32(lane_addr + cb * 32, v);
+                        tmem_wait_ld();
+                        float x[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) x[j] = fmaxf(__uint_as_float(v[j]) + sbias[l * 128 + cb * 32 + j], 0.0f);
+                        if (last_trunk && net.kind == 0) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) dot = fmaf(x[j], shead[cb * 32 + j], dot);
+                        }
+                        if (!last_trunk || net.kind == 1) {
+#pragma unroll
+                            for (int q = 0; q < 4; q++) {
+                                uint32_t hw[4], lw[4];
+#pragma unroll
+                                for (int e = 0; e < 4; e++) {
+                                    const float f0 = x[q * 8 + 2 * e], f1 = x[q * 8 + 2 * e + 1];
+                                    const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
+                                    const __half l0 = __float2half_rn(f0 - __half2float(h0)), l1 = __float2half_rn(f1 - __half2float(h1));
+                                    hw[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
+                                    lw[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
+                                }
+                                const uint32_t off = (uint32_t)(cb * 4 + q) * kGroupBytes + row_off;
+                                *reinterpret_cast<uint4 *>(smem + OFF_AHI + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+                                if (split) *reinterpret_cast<uint4 *>(smem + OFF_ALO + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+                            }
+                        }
+                    }
+                    if (last_trunk && net.kind == 0) {
+                        // policy head: conv9 (1x1, no bias) + bias10[cell] (network.py:44-46)
+                        const float logit = dot + shead[128 + cell];
+                        if (a.out_kind == 0) {
+                            if (valid) a.out[pos * 64 + cell] = logit;
+                        } else {
+                            scratch[b * 64 + cell] = logit;
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                            float mx = -3.0e38f;
+                            for (int i = 0; i < 64; i++) mx = fmaxf(mx, scratch[b * 64 + i]);
+                            float sum = 0.0f;
+                            for (int i = 0; i < 64; i++) sum += __expf(scratch[b * 64 + i] - mx);
+                            if (valid) a.out[pos * 64 + cell] = __expf(logit - mx) / sum;
+                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                        }
+                    }
+                } else {
+                    // value head: relu(block9 + b9) . (fc11 * fc10)  (network.py:92-95, dropout off)
+                    uint32_t v;
+                    tmem_ld1(lane_addr, v);
+                    tmem_wait_ld();
+                    const float h = fmaxf(__uint_as_float(v) + shead[0], 0.0f);
+                    scratch[b * 64 + cell] = h * shead[128 + cell];
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (warp < 2) {
+                        float s = scratch[warp * 64 + (tid & 31)] + scratch[warp * 64 + 32 + (tid & 31)];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+                        const long long p = tile * 2 + warp;
+                        if ((tid & 31) == 0 && p < a.n) a.out[p] = s;
+                    }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                if (l + 1 < L) {
+                    fence_async_smem();
+                    tc_fence_before();
+                    mbar_arrive(bar_act);
+                } else {
+                    tc_fence_before();  // TMEM reads done before the next tile's first MMA (ordered by the next bar_act arrive)
+                }
+            }
+        }
+    }
+
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+}
+
+// ---------------------------------------------------------------- host side: packing + launch
+
+struct NetSlot {
+    bool loaded = false;
+    NetDesc desc;
+    NetDesc *d_desc = nullptr;
+    uint8_t *d_blob = nullptr;
+    float *d_bias = nullptr;
+    float *d_head = nullptr;
+};
+
+struct TrunkState {
+    NetSlot slot[8];
+    bool attr_set = false;
+};
+
+static TrunkState *state(iago_ctx *ctx) {
+    if (!ctx->trunk) ctx->trunk = new TrunkState();
+    return static_cast<TrunkState *>(ctx->trunk);
+}
+
+void trunk_destroy(iago_ctx *ctx) {
+    if (!ctx->trunk) return;
+    TrunkState *st = static_cast<TrunkState *>(ctx->trunk);
+    for (auto &s : st->slot) {
+        cudaFree(s.d_desc);
+        cudaFree(s.d_blob);
+        cudaFree(s.d_bias);
+        cudaFree(s.d_head);
+    }
+    delete st;
+    ctx->trunk = nullptr;
+}
+
+static inline void split_half(float w, uint16_t &hi, uint16_t &lo) {
+    const __half h = __float2half_rn(w);
+    const __half l = __float2half_rn(w - __half2float(h));
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(l);
+}
+
+// One unit = hi block [kgroups][n_pad][8] followed by the lo block.  get(n, k) returns the fp32 weight of output n,
+// reduction index k (0 <= k < kgroups*8) or 0 for padding.
+template <class F>
+static void pack_unit(std::vector<uint8_t> &blob, int kgroups, int n_pad, F get) {
+    const size_t half_elems = (size_t)kgroups * n_pad * 8;
+    const size_t base = blob.size();
+    blob.resize(base + half_elems * 4);
+    uint16_t *hi = reinterpret_cast<uint16_t *>(blob.data() + base);
+    uint16_t *lo = hi + half_elems;
+    for (int kg = 0; kg < kgroups; kg++)
+        for (int n = 0; n < n_pad; n++)
+            for (int e = 0; e < 8; e++) split_half(get(n, kg * 8 + e), hi[((size_t)kg * n_pad + n) * 8 + e], lo[((size_t)kg * n_pad + n) * 8 + e]);
+}
+
 }  // namespace iago
+
+using namespace iago;
+
+extern "C" {
+
+int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_t n_floats) {
+    IAGO_REQUIRE(ctx && params, "NULL argument");
+    IAGO_REQUIRE(slot >= 0 && slot < 8, "slot out of range (0..7)");
+    IAGO_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (SL policy) or 1 (value)");
+    const int cin[8] = {2, 64, 128, 128, 128, 128, 128, 128}, cout[8] = {64, 128, 128, 128, 128, 128, 128, 128};
+    int64_t need = 0;
+    for (int l = 0; l < 8; l++) need += (int64_t)cout[l] * cin[l] * 9 + cout[l];
+    need += kind == 0 ? 128 + 64 : 1152 + 1 + 128 * 64 + 128;
+    if (n_floats != need) {
+        set_error("iago_load_net: expected %lld floats for kind %d, got %lld", (long long)need, kind, (long long)n_floats);
+        return IAGO_E_INVALID;
+    }
+    DeviceGuard guard(ctx->device);
+    NetSlot &s = state(ctx)->slot[slot];
+    NetDesc d;
+    memset(&d, 0, sizeof d);
+    d.kind = kind;
+    d.n_layers = kind == 0 ? 8 : 9;
+    std::vector<uint8_t> blob;
+    std::vector<float> bias((size_t)kMaxLayers * 128, 0.0f), head(256, 0.0f);
+    const float *p = params;
+    for (int l = 0; l < 8; l++) {
+        const float *W = p, *B = p + (size_t)cout[l] * cin[l] * 9;
+        p = B + cout[l];
+        for (int n = 0; n < cout[l]; n++) bias[(size_t)l * 128 + n] = B[n];
+        LayerDesc &ld = d.layer[l];
+        d.unit_base[l] = (long long)blob.size();
+        ld.n = cout[l];
+        ld.b_lbo = ld.n * 16;
+        if (l == 0) {
+            // explicit im2col: k = tap*2 + channel, K padded 18 -> 32
+            ld.n_units = 1; ld.ksteps = 2; ld.chunks = 0;
+            pack_unit(blob, 4, ld.n, [&](int n, int k) { return k < 18 ? W[((size_t)n * 2 + (k & 1)) * 9 + (k >> 1)] : 0.0f; });
+            ld.lo_off = 4 * ld.n * 16;
+        } else {
+            ld.chunks = cin[l] / 64; ld.n_units = 9 * ld.chunks; ld.ksteps = 4;
+            for (int tap = 0; tap < 9; tap++)
+                for (int ch = 0; ch < ld.chunks; ch++)
+                    pack_unit(blob, 8, ld.n, [&](int n, int k) { return W[((size_t)n * cin[l] + ch * 64 + k) * 9 + tap]; });
+            ld.lo_off = 8 * ld.n * 16;
+        }
+        ld.unit_bytes = 2 * ld.lo_off;
+    }
+    if (kind == 0) {
+        for (int i = 0; i < 128; i++) head[i] = p[i];          // conv9/W [1][128][1][1]
+        for (int i = 0; i < 64; i++) head[128 + i] = p[128 + i];  // bias10/b
+    } else {
+        const float *W9 = p, *b9 = p + 1152, *fc10 = b9 + 1, *fc11 = fc10 + 128 * 64;
+        LayerDesc &ld = d.layer[8];
+        d.unit_base[8] = (long long)blob.size();
+        ld.n = 16; ld.b_lbo = 16 * 16; ld.chunks = 2; ld.n_units = 18; ld.ksteps = 4;
+        for (int tap = 0; tap < 9; tap++)
+            for (int ch = 0; ch < 2; ch++)
+                pack_unit(blob, 8, 16, [&](int n, int k) { return n == 0 ? W9[(size_t)(ch * 64 + k) * 9 + tap] : 0.0f; });
+        ld.lo_off = 8 * 16 * 16;
+        ld.unit_bytes = 2 * ld.lo_off;
+        head[0] = b9[0];
+        // fc11 (1x128) * fc10 (128x64): no nonlinearity between them at inference (dropout is identity), collapse in fp64
+        for (int j = 0; j < 64; j++) {
+            double acc = 0.0;
+            for (int i = 0; i < 128; i++) acc += (double)fc11[i] * (double)fc10[(size_t)i * 64 + j];
+            head[128 + j] = (float)acc;
+        }
+    }
+    cudaFree(s.d_desc); cudaFree(s.d_blob); cudaFree(s.d_bias); cudaFree(s.d_head);
+    s = NetSlot();
+    IAGO_CUDA(cudaMalloc(&s.d_desc, sizeof(NetDesc)));
+    IAGO_CUDA(cudaMalloc(&s.d_blob, blob.size()));
+    IAGO_CUDA(cudaMalloc(&s.d_bias, bias.size() * 4));
+    IAGO_CUDA(cudaMalloc(&s.d_head, head.size() * 4));
+    IAGO_CUDA(cudaMemcpy(s.d_desc, &d, sizeof d, cudaMemcpyHostToDevice));
+    IAGO_CUDA(cudaMemcpy(s.d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
+    IAGO_CUDA(cudaMemcpy(s.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+    IAGO_CUDA(cudaMemcpy(s.d_head, head.data(), head.size() * 4, cudaMemcpyHostToDevice));
+    s.desc = d;
+    s.loaded = true;
+    return IAGO_OK;
+}
+
+static int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
+                        int64_t n, float *out, int out_kind, int precision, void *stream) {
+    IAGO_REQUIRE(ctx && p1 && p2 && color && out, "NULL argument");
+    IAGO_REQUIRE(slot >= 0 && slot < 8, "slot out of range (0..7)");
+    IAGO_REQUIRE(n >= 0, "n < 0");
+    IAGO_REQUIRE(precision == 1 || precision == 3, "precision must be 1 (fp16) or 3 (hi/lo split)");
+    TrunkState *st = state(ctx);
+    NetSlot &s = st->slot[slot];
+    if (!s.loaded || s.desc.kind != want_kind) {
+        set_error("net slot %d holds no %s network (call iago_load_net)", slot, want_kind == 0 ? "policy" : "value");
+        return IAGO_E_STATE;
+    }
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    if (!st->attr_set) {
+        IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        st->attr_set = true;
+    }
+    const long long tiles = (n + 1) / 2;
+    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    TrunkArgs a{(const u64 *)p1, (const u64 *)p2, color, n, out, out_kind, precision, s.d_blob, s.d_bias, s.d_head};
+    cudaStream_t cs = (cudaStream_t)stream;
+    IAGO_CUDA(cudaEventRecord(ctx->ev0, cs));
+    trunk_kernel<<<grid, kThreads, kSmemBytes, cs>>>(a, s.d_desc);
+    IAGO_CUDA(cudaGetLastError());
+    IAGO_CUDA(cudaEventRecord(ctx->ev1, cs));
+    ctx->timed = true;
+    return IAGO_OK;
+}
+
+int iago_policy_forward(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
+                        float *out, int out_kind, int precision, void *stream) {
+    IAGO_REQUIRE(out_kind == 0 || out_kind == 1, "out_kind must be 0 (logits) or 1 (probabilities)");
+    return trunk_launch(ctx, slot, 0, p1, p2, color, n, out, out_kind, precision, stream);
+}
+
+int iago_value_forward(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
+                       float *out, int precision, void *stream) {
+    return trunk_launch(ctx, slot, 1, p1, p2, color, n, out, 0, precision, stream);
+}
+
+}  // extern "C"

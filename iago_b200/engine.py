@@ -86,6 +86,16 @@ class Engine:
             pre = "predictor/" if "predictor/conv1/W" in z.files else ""
             self.load_rollout(z[pre + "conv1/W"], z[pre + "bias2/b"])
 
+    def load_net(self, slot, params, kind=None):
+        """SLPolicy / Value weights into a resident slot (0..7). `params`: dict in the reference's npz key layout, or a path."""
+        from . import npz
+        if isinstance(params, (str, bytes)) or hasattr(params, "__fspath__"):
+            params = npz.read_npz(params)
+        kind = npz.detect_kind(params) if kind is None else kind
+        flat = npz.flatten(params, kind)
+        check(self.lib.iago_load_net(self.ctx, int(slot), int(kind), _nptr(flat), flat.size))
+        return kind
+
     # ------------------------------------------------------------------ helpers
     def _stream(self, stream):
         if stream is not None:
@@ -149,6 +159,26 @@ class Engine:
         n = self._check_i64(p1, p2)
         out = torch.empty((n, 64), dtype=torch.float32, device=self._dev())
         check(self.lib.iago_rollout_logits(self.ctx, _ptr(p1), _ptr(p2), _ptr(color), _ptr(out), n, self._stream(stream)))
+        return out
+
+    def policy_forward(self, slot, p1, p2, color, probs=True, precision=3, out=None, stream=None):
+        """SLPolicy forward for n bitboard positions -> (n,64) float32 CUDA tensor (probabilities, or logits if probs=False)."""
+        torch = _torch()
+        n = self._check_i64(p1, p2)
+        if out is None:
+            out = torch.empty((n, 64), dtype=torch.float32, device=self._dev())
+        check(self.lib.iago_policy_forward(self.ctx, int(slot), _ptr(p1), _ptr(p2), _ptr(color), n, _ptr(out),
+                                           1 if probs else 0, int(precision), self._stream(stream)))
+        return out
+
+    def value_forward(self, slot, p1, p2, color, precision=3, out=None, stream=None):
+        """Value forward for n bitboard positions -> (n,) float32 CUDA tensor."""
+        torch = _torch()
+        n = self._check_i64(p1, p2)
+        if out is None:
+            out = torch.empty(n, dtype=torch.float32, device=self._dev())
+        check(self.lib.iago_value_forward(self.ctx, int(slot), _ptr(p1), _ptr(p2), _ptr(color), n, _ptr(out),
+                                          int(precision), self._stream(stream)))
         return out
 
     def rollout_sample(self, p1, p2, color, rng: Optional[Rng] = None, draw=0, stream=None):
@@ -234,6 +264,19 @@ class Engine:
         out = self.rollout_sample(self._to_dev(p1, np.int64), self._to_dev(p2, np.int64), self._to_dev(color, None),
                                   rng=rng, draw=draw)
         return out.cpu().numpy()
+
+    def _host_boards(self, p1, p2, color):
+        p1 = np.ascontiguousarray(p1, np.uint64).reshape(-1)
+        n = p1.shape[0]
+        p2 = np.ascontiguousarray(p2, np.uint64).reshape(n)
+        color = np.ascontiguousarray(np.broadcast_to(np.asarray(color, np.uint8), (n,)))
+        return self._to_dev(p1, np.int64), self._to_dev(p2, np.int64), self._to_dev(color, None)
+
+    def policy_forward_host(self, slot, p1, p2, color, probs=True, precision=3):
+        return self.policy_forward(slot, *self._host_boards(p1, p2, color), probs=probs, precision=precision).cpu().numpy()
+
+    def value_forward_host(self, slot, p1, p2, color, precision=3):
+        return self.value_forward(slot, *self._host_boards(p1, p2, color), precision=precision).cpu().numpy()
 
     def rollout_logits_host(self, p1, p2, color):
         p1 = np.ascontiguousarray(p1, np.uint64).reshape(-1)

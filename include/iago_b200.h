@@ -121,6 +121,27 @@ IAGO_API int iago_rollout_sample(iago_ctx *ctx, const uint64_t *p1, const uint64
 IAGO_API int iago_rollout_logits(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
                         float *logits, int64_t n, void *stream);
 
+/* ---- SLPolicy / Value networks (network.py:15-47, 66-96) on the fused tcgen05 trunk kernel ----
+ *
+ * iago_load_net: replaces serializers.load_npz(path, model) (MCTS.py:83,85, game.py:20, src/train_rl.py:23,37).
+ * `params` is a HOST array of fp32 in this order (the npz key layout of the reference, 'predictor/' prefix stripped):
+ *   block1/conv/W [64][2][3][3], block1/conv/b [64], block2/conv/W [128][64][3][3], b [128],
+ *   block3..8/conv/W [128][128][3][3], b [128],
+ *   kind 0 (SLPolicy, 960,768 floats): conv9/W [1][128][1][1], bias10/b [64]
+ *   kind 1 (Value,    970,049 floats): block9/conv/W [1][128][3][3], block9/conv/b [1], fc10/W [128][64], fc11/W [1][128]
+ * The fp16 hi/lo split and the tensor-core operand layout are produced inside.  slot in 0..7. */
+IAGO_API int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_t n_floats);
+
+/* SLPolicy.__call__ on make_state_var(state, color) for n positions given as bitboards.
+ * out [n][64]: out_kind 0 = pre-softmax logits, 1 = softmax probabilities (what the reference returns).
+ * precision 3 = error-compensated fp16 hi/lo split (3 MMAs, ~fp32 accuracy), 1 = single-pass fp16. */
+IAGO_API int iago_policy_forward(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
+                                 int64_t n, float *out, int out_kind, int precision, void *stream);
+
+/* Value.__call__ (inference: dropout off, MCTS.py:86) -> out [n]. */
+IAGO_API int iago_value_forward(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
+                                int64_t n, float *out, int precision, void *stream);
+
 /* Integer-issue micro-benchmark used as the roofline denominator of the rollout kernel:
  * runs `iters` rounds of dependent LOP3/SHF chains on every SM and returns int32 lane-ops/s. */
 IAGO_API int iago_measure_int_peak(iago_ctx *ctx, int iters, double *lane_ops_per_s);

@@ -1,0 +1,119 @@
+"""SLPolicy / Value forward on the tcgen05 trunk kernel vs the reference outputs (tests/golden/nets.npz, produced by
+the unmodified reference under the numpy Chainer stand-in) and vs the fp64 numpy oracle as the error yard-stick.
+
+Tolerances (stated, north_star: "max-abs <= 1e-2 on logits, identical argmax on >= 99.9 % of positions"):
+  precision=3 (hi/lo fp16 split, 3 MMAs): max-abs logit error <= 2e-3, legal-argmax agreement 100 %,
+                                           probabilities max-abs <= 1e-4, value max-abs <= 1e-4
+  precision=1 (single-pass fp16)        : max-abs logit error <= 0.5, legal-argmax agreement >= 99 %
+"""
+import numpy as np
+import pytest
+
+from conftest import model_file
+
+pytestmark = pytest.mark.gpu
+
+
+def bb(states):
+    from iago_b200 import boards
+    return boards.to_bitboards(states)
+
+
+@pytest.fixture(scope="module")
+def oracle_nets():
+    from oracle import nets
+    return nets
+
+
+def legal_argmax(logits, masks):
+    bits = ((masks.reshape(-1, 1) >> np.arange(64, dtype=np.uint64)) & np.uint64(1)).astype(bool)
+    l = np.where(bits, logits, -np.inf)
+    return l.argmax(axis=1), bits.any(axis=1)
+
+
+@pytest.mark.parametrize("model,key", [("sl_model.npz", "sl_prob"), ("rl_model.npz", "rl_prob")])
+def test_policy_vs_reference(engine, golden_nets, oracle_nets, model, key):
+    g = golden_nets
+    engine.load_net(0, model_file(model))
+    p1, p2 = bb(g["state"])
+    col = g["color"].astype(np.uint8)
+    p64 = oracle_nets.load_params(model_file(model), np.float64)
+    ref_logits = oracle_nets.sl_logits(p64, oracle_nets.planes_from_state(g["state"].reshape(-1, 8, 8), g["color"], np.float64))
+    ref_arg, has = legal_argmax(ref_logits, g["legal_mask"])
+
+    logits = engine.policy_forward_host(0, p1, p2, col, probs=False, precision=3)
+    err = np.abs(logits - ref_logits).max()
+    arg, _ = legal_argmax(logits, g["legal_mask"])
+    print(f"{model} precision=3: max-abs logit err {err:.2e}, legal-argmax agreement {(arg == ref_arg)[has].mean():.4%}")
+    assert err <= 2e-3
+    assert (arg == ref_arg)[has].all()
+
+    probs = engine.policy_forward_host(0, p1, p2, col, probs=True, precision=3)
+    assert np.abs(probs - g[key]).max() <= 1e-4            # vs the reference's own softmax output
+    assert np.abs(probs.sum(axis=1) - 1).max() < 1e-5
+
+    l1 = engine.policy_forward_host(0, p1, p2, col, probs=False, precision=1)
+    err1 = np.abs(l1 - ref_logits).max()
+    arg1, _ = legal_argmax(l1, g["legal_mask"])
+    print(f"{model} precision=1: max-abs logit err {err1:.2e}, legal-argmax agreement {(arg1 == ref_arg)[has].mean():.4%}")
+    assert err1 <= 0.5 and (arg1 == ref_arg)[has].mean() >= 0.99
+
+
+def test_policy_known_answer(engine):
+    """start position, colour 1 to move: top-2 = action 44 (p=0.9999236), 37 (7.448e-05)."""
+    from iago_b200 import boards
+    engine.load_net(0, model_file("sl_model.npz"))
+    p = engine.policy_forward_host(0, [boards.START_P1], [boards.START_P2], 1)[0]
+    top = np.argsort(-p)[:2]
+    assert top.tolist() == [44, 37]
+    assert abs(p[44] - 0.9999236) < 2e-6 and abs(p[37] - 7.448e-05) < 2e-7
+
+
+def test_value_vs_reference(engine, golden_nets, oracle_nets):
+    g = golden_nets
+    engine.load_net(1, model_file("value_model.npz"))
+    p1, p2 = bb(g["state"])
+    col = g["color"].astype(np.uint8)
+    v = engine.value_forward_host(1, p1, p2, col, precision=3)
+    p64 = oracle_nets.load_params(model_file("value_model.npz"), np.float64)
+    ref = oracle_nets.value(p64, oracle_nets.planes_from_state(g["state"].reshape(-1, 8, 8), g["color"], np.float64))
+    print(f"value precision=3: max-abs err vs fp64 {np.abs(v - ref).max():.2e}, vs reference fp32 {np.abs(v - g['value']).max():.2e}")
+    assert np.abs(v - ref).max() <= 1e-4
+    assert np.abs(v - g["value"]).max() <= 1e-4
+    assert abs(v[0] - (-0.0263806)) < 1e-5                 # SURVEY.md §4 known answer (start position, colour 1)
+    v1 = engine.value_forward_host(1, p1, p2, col, precision=1)
+    assert np.abs(v1 - ref).max() <= 2e-2
+
+
+def test_ragged_batches_and_slots(engine, golden_nets):
+    """Odd batch sizes (half-filled last tile), one position, many tiles per CTA, two nets resident at once."""
+    g = golden_nets
+    engine.load_net(0, model_file("sl_model.npz"))
+    engine.load_net(2, model_file("rl_model.npz"))
+    p1, p2 = bb(g["state"])
+    col = g["color"].astype(np.uint8)
+    full0 = engine.policy_forward_host(0, p1, p2, col, probs=False)
+    full2 = engine.policy_forward_host(2, p1, p2, col, probs=False)
+    assert np.abs(full0 - full2).max() > 1e-3              # different nets
+    for n in (1, 2, 3, 297, 301):
+        part = engine.policy_forward_host(0, p1[:n], p2[:n], col[:n], probs=False)
+        assert (part == full0[:n]).all()                    # bit-identical regardless of batch shape
+    big = np.tile(np.arange(len(p1)), 7)[:5001]
+    out = engine.policy_forward_host(0, p1[big], p2[big], col[big], probs=False)
+    assert (out == full0[big]).all()
+
+
+def test_facade_network_classes(engine, golden_nets):
+    from iago_b200 import network
+    from iago_b200.game import GameFunctions as gf
+    g = golden_nets
+    sl = network.SLPolicy().load(model_file("sl_model.npz"))
+    va = network.Value().load(model_file("value_model.npz"))
+    ro = network.RolloutPolicy().load(model_file("rollout_model.npz"))
+    x = g["x"][:64].astype(np.float32)
+    assert np.abs(sl(x).data - g["sl_prob"][:64]).max() <= 1e-4
+    assert np.abs(va(x).data - g["value"][:64]).max() <= 1e-4
+    assert np.abs(ro(x).data - g["rollout_prob"][:64]).max() <= 1e-6
+    s = g["state"][5].reshape(8, 8).astype(np.float32)
+    prob = sl(gf.make_state_var(s, int(g["color"][5]))).data.reshape(64)   # the reference's call shape (MCTS.py:95)
+    assert np.abs(prob - g["sl_prob"][5]).max() <= 1e-4

@@ -43,8 +43,9 @@ constexpr int kA1Bytes = 4 * kTileRows * 16;      // layer-1 explicit im2col til
 constexpr int kStageBytes = 32768;                // one weight unit: hi [8][128][8] + lo
 constexpr int kStages = 3;
 constexpr int kMaxLayers = 9;
-constexpr int kThreads = 192;                     // warps 0-3 epilogue (TMEM lanes 32w..), warp 4 producer, warp 5 MMA
-constexpr int kTmemCols = 128;
+constexpr int kEpiThreads = 256;                  // warps 0-7
+constexpr int kThreads = 320;                     // + warp 8 producer, warp 9 MMA issuer
+constexpr int kTmemCols = 256;                    // two 128-column fp32 accumulators
 
 constexpr int OFF_AHI = 0;
 constexpr int OFF_ALO = OFF_AHI + kActBytes;
@@ -52,8 +53,8 @@ constexpr int OFF_A1 = OFF_ALO + kActBytes;
 constexpr int OFF_STAGE = OFF_A1 + kA1Bytes;
 constexpr int OFF_BIAS = OFF_STAGE + kStages * kStageBytes;   // float [9][128]
 constexpr int OFF_HEAD = OFF_BIAS + kMaxLayers * 128 * 4;      // float w9[128], b10[64], wfc[64]
-constexpr int OFF_SCRATCH = OFF_HEAD + 256 * 4;                // float [2][64]
-constexpr int OFF_BAR = OFF_SCRATCH + 128 * 4;                 // mbarriers + tmem pointer
+constexpr int OFF_SCRATCH = OFF_HEAD + 256 * 4;                // float [2][128] partial dots + [2][64] logits
+constexpr int OFF_BAR = OFF_SCRATCH + 384 * 4;                 // mbarriers + tmem pointer
 constexpr int kSmemBytes = OFF_BAR + 128;
 
 struct LayerDesc {
@@ -85,20 +86,24 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-// Spins on the phase parity.  A generous clock-based watchdog turns a protocol bug into a trap instead of a hang.
+// Waits on the phase parity.  try_wait suspends the thread in hardware for a bounded time, so the loop body runs
+// rarely; a coarse watchdog turns a protocol bug into a trap instead of a hang.
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    const long long t0 = clock64();
-    for (;;) {
-        uint32_t done;
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-        if (clock64() - t0 > 4000000000LL) __trap();  // ~2 s at 2 GHz
+    if (mbar_try(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!mbar_try(bar, parity)) {
+        if (++spins > 2000u) __trap();  // each try suspends up to 10 ms: ~20 s without progress
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
@@ -160,14 +165,42 @@ struct TrunkArgs {
     const float *head;    // policy: w9[128], b10[64]; value: b9 at [0], wfc[64] at [128..192)
 };
 
+// bias + ReLU + hi/lo fp16 split of 32 accumulator columns, written as 4 channel groups of this thread's tile row.
+__device__ __forceinline__ void store_act32(uint8_t *smem, const float (&x)[32], uint32_t group0_off, bool split) {
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t hw[4], lw[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float f0 = x[q * 8 + 2 * e], f1 = x[q * 8 + 2 * e + 1];
+            const __half2 h = __floats2half2_rn(f0, f1);
+            const float2 hf = __half22float2(h);
+            const __half2 l = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+            hw[e] = *reinterpret_cast<const uint32_t *>(&h);
+            lw[e] = *reinterpret_cast<const uint32_t *>(&l);
+        }
+        const uint32_t off = group0_off + (uint32_t)q * kGroupBytes;
+        *reinterpret_cast<uint4 *>(smem + OFF_AHI + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+        if (split) *reinterpret_cast<uint4 *>(smem + OFF_ALO + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+}
+
+// Thread layout: warps 0-7 epilogue (warp w reads TMEM lanes 32*(w%4)..; warps 0-3 take columns [0,32)+[64,96),
+// warps 4-7 take [32,64)+[96,128)), warp 8 = weight producer, warp 9 = MMA issuer.
+//
+// Pipeline per tile (DESIGN.md "trunk pipeline"): the accumulator is double-buffered in TMEM (layer l uses buffer
+// l&1) and weight units are ordered chunk-major, so the MMAs of layer l+1 on input channels 0..63 start as soon as
+// the epilogue of layer l has written those channels, while it is still converting channels 64..127.
 __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const NetDesc *__restrict__ gnet) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ NetDesc net;
     const int tid = threadIdx.x, warp = tid >> 5;
     const uint32_t sbase = smem_u32(smem);
     const uint32_t bar_full = sbase + OFF_BAR, bar_empty = bar_full + 8 * kStages;
-    const uint32_t bar_acc = bar_empty + 8 * kStages, bar_act = bar_acc + 8;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 * (2 * kStages + 2));
+    const uint32_t bar_acc = bar_empty + 8 * kStages;  // [2] accumulator buffer complete
+    const uint32_t bar_act = bar_acc + 16;              // [2] input channels 0..63 / 64..127 of the next layer written
+    const uint32_t bar_a1 = bar_act + 16;               // layer-1 im2col tile written, TMEM buffer 0 drained
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 * (2 * kStages + 5));
 
     // ---- one-time setup
     for (int i = tid; i < (int)(sizeof(NetDesc) / 4); i += kThreads) reinterpret_cast<int *>(&net)[i] = reinterpret_cast<const int *>(gnet)[i];
@@ -185,10 +218,13 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
-        mbar_init(bar_act, 128);
+        mbar_init(bar_acc + 8, 1);
+        mbar_init(bar_act, kEpiThreads);
+        mbar_init(bar_act + 8, kEpiThreads);
+        mbar_init(bar_a1, kEpiThreads);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 4) {
+    if (warp == 8) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -202,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
     const int L = net.n_layers;
     const bool split = a.precision >= 3;
 
-    if (warp == 4) {
+    if (warp == 8) {
         // ================= producer: stream weight units L2 -> smem ring =================
         if ((tid & 31) == 0) {
             uint32_t stage = 0, phase = 0;
@@ -214,74 +250,96 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                     for (int u = 0; u < ld.n_units; u++) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         mbar_expect_tx(bar_full + 8 * stage, bytes);
-                        bulk_g2s(sbase + OFF_STAGE + stage * kStageBytes, src + (long long)u * ld.unit_bytes, bytes, bar_full + 8 * stage);
+                        bulk_g2s(sbase + OFF_STAGE + stage * kStageBytes, src, bytes, bar_full + 8 * stage);
+                        src += ld.unit_bytes;
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         // ================= MMA issuer: one thread =================
         if ((tid & 31) == 0) {
-            uint32_t stage = 0, phase = 0, act_phase = 0;
+            uint32_t stage = 0, phase = 0, act_phase[2] = {0, 0}, a1_phase = 0;
+            const uint64_t desc_hi_a = ((uint64_t)(kRowPitch >> 4) << 32) | (1ULL << 46);  // SBO + version; LBO/start in the low word
+            const uint64_t desc_hi_b = ((uint64_t)(128 >> 4) << 32) | (1ULL << 46);
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int l = 0; l < L; l++) {
                     const LayerDesc ld = net.layer[l];
                     const uint32_t idesc = instr_desc(kTileRows, ld.n);
-                    mbar_wait(bar_act, act_phase);  // activation tile of this layer is written, TMEM is drained
-                    act_phase ^= 1;
-                    tc_fence_after();
+                    const uint32_t d_tmem = tmem + (uint32_t)(l & 1) * 128u;
+                    const uint32_t b_step = (uint32_t)(2 * ld.b_lbo) >> 4;              // descriptor units (16 B) per K=16 step
+                    const uint32_t b_lo_word = ((uint32_t)(ld.b_lbo >> 4) << 16);
                     uint32_t acc = 0;
-                    for (int u = 0; u < ld.n_units; u++) {
+                    if (ld.chunks == 0) {
+                        // layer 1: explicit im2col tile [4][128][16 B], LBO = 2048, SBO = 128
+                        mbar_wait(bar_a1, a1_phase);
+                        a1_phase ^= 1;
                         mbar_wait(bar_full + 8 * stage, phase);
                         tc_fence_after();
                         const uint32_t bst = sbase + OFF_STAGE + stage * kStageBytes;
-                        uint32_t a_hi, a_lo, a_lbo, a_sbo;
-                        if (ld.chunks == 0) {  // layer 1: explicit im2col tile [4][128][16 B]
-                            a_hi = sbase + OFF_A1; a_lo = a_hi; a_lbo = kTileRows * 16; a_sbo = 128;
-                        } else {
-                            const int tap = u / ld.chunks, chunk = u - tap * ld.chunks;
-                            const int ky = tap / 3, kx = tap - ky * 3;  // (dy,dx) = (ky-1,kx-1); the halo is at padded index 0
-                            const uint32_t off = (uint32_t)chunk * 8 * kGroupBytes + (uint32_t)((ky * 2) * 10 + kx) * 16;
-                            a_hi = sbase + OFF_AHI + off; a_lo = sbase + OFF_ALO + off; a_lbo = kGroupBytes; a_sbo = kRowPitch;
-                        }
+                        const uint64_t a1_hi = ((uint64_t)(128 >> 4) << 32) | (1ULL << 46);
+                        uint32_t aw = ((sbase + OFF_A1) >> 4) | ((uint32_t)((kTileRows * 16) >> 4) << 16);
+                        uint32_t bw = (bst >> 4) | b_lo_word, blw = ((bst + ld.lo_off) >> 4) | b_lo_word;
                         for (int ks = 0; ks < ld.ksteps; ks++) {
-                            const uint64_t ah = smem_desc(a_hi + 2 * ks * a_lbo, a_lbo, a_sbo);
-                            const uint64_t bh = smem_desc(bst + 2 * ks * ld.b_lbo, ld.b_lbo, 128);
-                            umma_f16(tmem, ah, bh, idesc, acc);
+                            umma_f16(d_tmem, a1_hi | aw, desc_hi_b | bw, idesc, acc);
                             acc = 1;
-                            if (split) {
-                                const uint64_t bl = smem_desc(bst + ld.lo_off + 2 * ks * ld.b_lbo, ld.b_lbo, 128);
-                                umma_f16(tmem, ah, bl, idesc, 1);
-                                if (ld.chunks != 0) {  // layer-1 inputs are exactly 0/1: no lo part
-                                    const uint64_t al = smem_desc(a_lo + 2 * ks * a_lbo, a_lbo, a_sbo);
-                                    umma_f16(tmem, al, bh, idesc, 1);
+                            if (split) umma_f16(d_tmem, a1_hi | aw, desc_hi_b | blw, idesc, 1);  // inputs are exactly 0/1: no lo part
+                            aw += (2 * kTileRows * 16) >> 4; bw += b_step; blw += b_step;
+                        }
+                        umma_commit(bar_empty + 8 * stage);
+                        if (++stage == kStages) { stage = 0; phase ^= 1; }
+                    } else {
+                        const uint32_t a_lo_word = ((uint32_t)(kGroupBytes >> 4) << 16);
+                        for (int chunk = 0; chunk < ld.chunks; chunk++) {
+                            mbar_wait(bar_act + 8 * chunk, act_phase[chunk]);  // these 64 input channels are written
+                            act_phase[chunk] ^= 1;
+                            tc_fence_after();
+                            const uint32_t a_chunk = (uint32_t)chunk * 8 * kGroupBytes;
+#pragma unroll 1
+                            for (int tap = 0; tap < 9; tap++) {
+                                const int ky = tap / 3, kx = tap - ky * 3;  // (dy,dx) = (ky-1,kx-1); the halo sits at padded index 0
+                                const uint32_t off = a_chunk + (uint32_t)(ky * 20 + kx) * 16;
+                                mbar_wait(bar_full + 8 * stage, phase);
+                                tc_fence_after();
+                                const uint32_t bst = sbase + OFF_STAGE + stage * kStageBytes;
+                                uint32_t ahw = ((sbase + OFF_AHI + off) >> 4) | a_lo_word, alw = ((sbase + OFF_ALO + off) >> 4) | a_lo_word;
+                                uint32_t bw = (bst >> 4) | b_lo_word, blw = ((bst + ld.lo_off) >> 4) | b_lo_word;
+#pragma unroll
+                                for (int ks = 0; ks < 4; ks++) {
+                                    umma_f16(d_tmem, desc_hi_a | ahw, desc_hi_b | bw, idesc, acc);
+                                    acc = 1;
+                                    if (split) {
+                                        umma_f16(d_tmem, desc_hi_a | ahw, desc_hi_b | blw, idesc, 1);
+                                        umma_f16(d_tmem, desc_hi_a | alw, desc_hi_b | bw, idesc, 1);
+                                    }
+                                    ahw += (2 * kGroupBytes) >> 4; alw += (2 * kGroupBytes) >> 4; bw += b_step; blw += b_step;
                                 }
+                                umma_commit(bar_empty + 8 * stage);  // frees the weight stage when these MMAs retire
+                                if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
                         }
-                        umma_commit(bar_empty + 8 * stage);  // frees the weight stage when these MMAs retire
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(bar_acc);  // accumulator of this layer complete
+                    umma_commit(bar_acc + 8 * (l & 1));  // accumulator of this layer complete
                 }
             }
         }
     } else {
-        // ================= epilogue warps: thread m owns tile row m = TMEM lane m =================
-        const int m = tid;
+        // ================= epilogue warps: thread pair (m, m+128) owns tile row m = TMEM lane m =================
+        const int m = tid & 127, half = tid >> 7;  // half 0: columns [0,32)+[64,96); half 1: [32,64)+[96,128)
         const int g = m >> 3, c = m & 7, r = g >> 1, b = g & 1;
         const uint32_t row_off = (uint32_t)(((r + 1) * 2 + b) * 10 + (c + 1)) * 16;  // interior cell of the padded tile
-        const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const float *sbias = reinterpret_cast<const float *>(smem + OFF_BIAS);
         const float *shead = reinterpret_cast<const float *>(smem + OFF_HEAD);
-        float *scratch = reinterpret_cast<float *>(smem + OFF_SCRATCH);
+        float *scratch = reinterpret_cast<float *>(smem + OFF_SCRATCH);   // [2][128] partial dots / [2][64] logits
         const int cell = r * 8 + c;
-        uint32_t acc_phase = 0;
+        uint32_t acc_phase[2] = {0, 0};
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const long long pos = tile * 2 + b;
             const bool valid = pos < a.n;
             // ---- layer-1 input: explicit im2col of the two bit planes, k = tap*2 + channel (0 = opponent, 1 = mover)
-            {
+            if (half == 0) {
                 u64 own = 0, opp = 0;
                 if (valid) {
                     const bool first = a.color[pos] == 1;
@@ -312,86 +370,79 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
             }
             fence_async_smem();
             tc_fence_before();
-            mbar_arrive(bar_act);
+            mbar_arrive(bar_a1);
 
             for (int l = 0; l < L; l++) {
                 const LayerDesc ld = net.layer[l];
-                mbar_wait(bar_acc, acc_phase);
-                acc_phase ^= 1;
+                mbar_wait(bar_acc + 8 * (l & 1), acc_phase[l & 1]);
+                acc_phase[l & 1] ^= 1;
                 tc_fence_after();
-                const bool last_trunk = (l == 7);
-                const bool value_head = (l == 8);
-                if (!value_head) {
+                const uint32_t t_addr = lane_addr + (uint32_t)(l & 1) * 128u;
+                const bool policy_head = (l == 7 && net.kind == 0);
+                const bool writes_act = (l + 1 < L);
+                if (l < 8) {
                     float dot = 0.0f;
-                    for (int cb = 0; cb < ld.n / 32; cb++) {
+                    const int passes = ld.n / 64;  // 1 for the 64-channel layer, else 2
+                    for (int ps = 0; ps < passes; ps++) {
+                        const int col0 = ps * 64 + half * 32;
                         uint32_t v[32];
-                        tmem_ld32(lane_addr + cb * 32, v);
+                        tmem_ld32(t_addr + col0, v);
                         tmem_wait_ld();
                         float x[32];
 #pragma unroll
-                        for (int j = 0; j < 32; j++) x[j] = fmaxf(__uint_as_float(v[j]) + sbias[l * 128 + cb * 32 + j], 0.0f);
-                        if (last_trunk && net.kind == 0) {
+                        for (int j = 0; j < 32; j++) x[j] = fmaxf(__uint_as_float(v[j]) + sbias[l * 128 + col0 + j], 0.0f);
+                        if (policy_head) {
 #pragma unroll
-                            for (int j = 0; j < 32; j++) dot = fmaf(x[j], shead[cb * 32 + j], dot);
+                            for (int j = 0; j < 32; j++) dot = fmaf(x[j], shead[col0 + j], dot);
                         }
-                        if (!last_trunk || net.kind == 1) {
-#pragma unroll
-                            for (int q = 0; q < 4; q++) {
-                                uint32_t hw[4], lw[4];
-#pragma unroll
-                                for (int e = 0; e < 4; e++) {
-                                    const float f0 = x[q * 8 + 2 * e], f1 = x[q * 8 + 2 * e + 1];
-                                    const __half h0 = __float2half_rn(f0), h1 = __float2half_rn(f1);
-                                    const __half l0 = __float2half_rn(f0 - __half2float(h0)), l1 = __float2half_rn(f1 - __half2float(h1));
-                                    hw[e] = (uint32_t)__half_as_ushort(h0) | ((uint32_t)__half_as_ushort(h1) << 16);
-                                    lw[e] = (uint32_t)__half_as_ushort(l0) | ((uint32_t)__half_as_ushort(l1) << 16);
-                                }
-                                const uint32_t off = (uint32_t)(cb * 4 + q) * kGroupBytes + row_off;
-                                *reinterpret_cast<uint4 *>(smem + OFF_AHI + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-                                if (split) *reinterpret_cast<uint4 *>(smem + OFF_ALO + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
-                            }
+                        if (writes_act) {
+                            store_act32(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
+                            fence_async_smem();
+                            tc_fence_before();
+                            mbar_arrive(bar_act + 8 * ps);  // input channels [64*ps, 64*ps+64) of the next layer are in place
                         }
                     }
-                    if (last_trunk && net.kind == 0) {
-                        // policy head: conv9 (1x1, no bias) + bias10[cell] (network.py:44-46)
-                        const float logit = dot + shead[128 + cell];
-                        if (a.out_kind == 0) {
-                            if (valid) a.out[pos * 64 + cell] = logit;
-                        } else {
-                            scratch[b * 64 + cell] = logit;
-                            asm volatile("bar.sync 1, 128;" ::: "memory");
-                            float mx = -3.0e38f;
-                            for (int i = 0; i < 64; i++) mx = fmaxf(mx, scratch[b * 64 + i]);
-                            float sum = 0.0f;
-                            for (int i = 0; i < 64; i++) sum += __expf(scratch[b * 64 + i] - mx);
-                            if (valid) a.out[pos * 64 + cell] = __expf(logit - mx) / sum;
-                            asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (policy_head) {
+                        // policy head: conv9 (1x1, no bias) + bias10[cell] (network.py:44-46); the row's two threads hold half each
+                        scratch[half * 128 + m] = dot;
+                        asm volatile("bar.sync 1, 256;" ::: "memory");
+                        if (half == 0) {
+                            const float logit = scratch[m] + scratch[128 + m] + shead[128 + cell];
+                            if (a.out_kind == 0) {
+                                if (valid) a.out[pos * 64 + cell] = logit;
+                            } else {
+                                float *lg = scratch + 256;
+                                lg[b * 64 + cell] = logit;
+                                asm volatile("bar.sync 2, 128;" ::: "memory");
+                                float mx = -3.0e38f;
+                                for (int i = 0; i < 64; i++) mx = fmaxf(mx, lg[b * 64 + i]);
+                                float sum = 0.0f;
+                                for (int i = 0; i < 64; i++) sum += __expf(lg[b * 64 + i] - mx);
+                                if (valid) a.out[pos * 64 + cell] = __expf(logit - mx) / sum;
+                            }
                         }
+                        asm volatile("bar.sync 1, 256;" ::: "memory");  // scratch is reused by the next tile
                     }
                 } else {
                     // value head: relu(block9 + b9) . (fc11 * fc10)  (network.py:92-95, dropout off)
-                    uint32_t v;
-                    tmem_ld1(lane_addr, v);
-                    tmem_wait_ld();
-                    const float h = fmaxf(__uint_as_float(v) + shead[0], 0.0f);
-                    scratch[b * 64 + cell] = h * shead[128 + cell];
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
-                    if (warp < 2) {
-                        float s = scratch[warp * 64 + (tid & 31)] + scratch[warp * 64 + 32 + (tid & 31)];
+                    if (half == 0) {
+                        uint32_t v;
+                        tmem_ld1(t_addr, v);
+                        tmem_wait_ld();
+                        const float h = fmaxf(__uint_as_float(v) + shead[0], 0.0f);
+                        scratch[b * 64 + cell] = h * shead[128 + cell];
+                        asm volatile("bar.sync 2, 128;" ::: "memory");
+                        if (warp < 2) {
+                            float s = scratch[warp * 64 + (tid & 31)] + scratch[warp * 64 + 32 + (tid & 31)];
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-                        const long long p = tile * 2 + warp;
-                        if ((tid & 31) == 0 && p < a.n) a.out[p] = s;
+                            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
+                            const long long p = tile * 2 + warp;
+                            if ((tid & 31) == 0 && p < a.n) a.out[p] = s;
+                        }
+                        asm volatile("bar.sync 2, 128;" ::: "memory");
                     }
-                    asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
-                if (l + 1 < L) {
-                    fence_async_smem();
-                    tc_fence_before();
-                    mbar_arrive(bar_act);
-                } else {
-                    tc_fence_before();  // TMEM reads done before the next tile's first MMA (ordered by the next bar_act arrive)
-                }
+                tc_fence_before();
             }
         }
     }
@@ -399,7 +450,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
     // ---- teardown
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
 }
 
 // ---------------------------------------------------------------- host side: packing + launch
@@ -499,8 +550,8 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
             ld.lo_off = 4 * ld.n * 16;
         } else {
             ld.chunks = cin[l] / 64; ld.n_units = 9 * ld.chunks; ld.ksteps = 4;
-            for (int tap = 0; tap < 9; tap++)
-                for (int ch = 0; ch < ld.chunks; ch++)
+            for (int ch = 0; ch < ld.chunks; ch++)  // chunk-major: all taps of input channels 0..63 first
+                for (int tap = 0; tap < 9; tap++)
                     pack_unit(blob, 8, ld.n, [&](int n, int k) { return W[((size_t)n * cin[l] + ch * 64 + k) * 9 + tap]; });
             ld.lo_off = 8 * ld.n * 16;
         }
@@ -514,8 +565,8 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
         LayerDesc &ld = d.layer[8];
         d.unit_base[8] = (long long)blob.size();
         ld.n = 16; ld.b_lbo = 16 * 16; ld.chunks = 2; ld.n_units = 18; ld.ksteps = 4;
-        for (int tap = 0; tap < 9; tap++)
-            for (int ch = 0; ch < 2; ch++)
+        for (int ch = 0; ch < 2; ch++)
+            for (int tap = 0; tap < 9; tap++)
                 pack_unit(blob, 8, 16, [&](int n, int k) { return n == 0 ? W9[(size_t)(ch * 64 + k) * 9 + tap] : 0.0f; });
         ld.lo_off = 8 * 16 * 16;
         ld.unit_bytes = 2 * ld.lo_off;

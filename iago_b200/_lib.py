@@ -34,6 +34,8 @@ SIGNATURES = {
     "iago_load_net": [_P, C.c_int, C.c_int, _P, C.c_int64],
     "iago_policy_forward": [_P, C.c_int, _P, _P, _P, C.c_int64, _P, C.c_int, C.c_int, _P],
     "iago_value_forward": [_P, C.c_int, _P, _P, _P, C.c_int64, _P, C.c_int, _P],
+    "iago_selfplay": [_P, C.c_int, C.c_int, C.c_int64, _P, _P, C.c_int, C.c_int, C.POINTER(IagoRng), _P, _P, _P, _P, _P, _P,
+                      _P, C.c_int, _P, _P, _P],
     "iago_measure_int_peak": [_P, C.c_int, C.POINTER(C.c_double)],
     "iago_last_kernel_ms": [_P, C.POINTER(C.c_float)],
 }

@@ -28,6 +28,7 @@ int ensure_staging(iago_ctx *ctx, size_t bytes) {
 }
 
 void trunk_destroy(iago_ctx *ctx);
+void selfplay_destroy(iago_ctx *ctx);
 
 }  // namespace iago
 
@@ -72,6 +73,7 @@ int iago_ctx_destroy(iago_ctx *ctx) {
     iago::DeviceGuard guard(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     iago::trunk_destroy(ctx);
+    iago::selfplay_destroy(ctx);
     if (ctx->stage.host) cudaFreeHost(ctx->stage.host);
     if (ctx->stage.dev) cudaFree(ctx->stage.dev);
     cudaFree(ctx->d_rollout);

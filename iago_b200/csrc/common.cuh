@@ -34,7 +34,9 @@ struct iago_ctx {
     bool rollout_loaded = false;
     iago::Staging stage;
     uint64_t *d_counters = nullptr;
-    void *trunk = nullptr;  // conv-net state (trunk.cu)
+    void *trunk = nullptr;     // conv-net state (trunk.cu)
+    void *selfplay = nullptr;  // self-play workspace (selfplay.cu)
+    void *mcts = nullptr;      // search trees (mcts.cu)
 };
 
 #define IAGO_CUDA(expr)                                                                      \
@@ -67,4 +69,7 @@ struct DeviceGuard {
     }
 };
 int ensure_staging(iago_ctx *ctx, size_t bytes);
+// trunk.cu: SLPolicy (want_kind 0) / Value (1) forward on device bitboards; out_kind 0 = logits, 1 = probabilities.
+int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
+                 int64_t n, float *out, int out_kind, int precision, void *stream);
 }  // namespace iago

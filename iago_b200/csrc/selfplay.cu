@@ -1,0 +1,246 @@
+// selfplay.cu — batched learner-vs-opponent self-play with the SL-size policy nets.
+//
+// Reference: src/rl_self_play.py:8-145.  Game(model1, model2)() plays colour 1 (learner, model1) against colour 2
+// (opponent, model2) with `while stone_num < 64: turn(1); turn(2)`; turn (:130-145) = legal_actions, get_action
+// (:111-127: SLPolicy forward -> float32 probabilities * float64 validity mask, renormalise, np.random.choice = one
+// uniform per move), record the learner's swapped pre-move board + action (:134-138), place_stone; two consecutive
+// passes set stone_num = 64; judge (:91-100) is from colour 1's view.  stone_num starts at 4 whatever the caller
+// poked into `state` (src/train_rl.py:43-46 drops an extra un-flipped colour-2 stone on odd games), so it is a
+// counter here too, not a popcount.
+//
+// All n games advance in lockstep: one fused trunk forward (trunk.cu) for every game's position, then one light
+// kernel (one thread per game) that masks, samples / arg-maxes, flips and does the pass / terminal bookkeeping.
+#include <vector>
+
+#include "bitboard.cuh"
+#include "common.cuh"
+#include "philox.cuh"
+
+namespace iago {
+
+enum { SEL_SAMPLE = 0, SEL_GREEDY = 1 };
+
+struct SelfplayArgs {
+    u64 *p1, *p2;
+    int32_t *stone_num;
+    uint8_t *pass_flg;
+    int32_t *placed;     // stones placed so far = index of the next uniform
+    long long n;
+    int color;           // side to move in this half-step: 1 = learner, 2 = opponent
+    int select;          // SEL_SAMPLE / SEL_GREEDY
+    int rng_mode;
+    uint32_t stream_id;
+    u64 seed, game_id0;
+    const double *uniforms;
+    long long u_stride;
+    const int8_t *forced;
+    long long f_stride;
+    const float *logits;  // [n][64] from the trunk for the side to move
+    // records of the learner's decisions (rl_self_play.py:134-138)
+    u64 *rec_own, *rec_opp;
+    int8_t *rec_action;
+    int32_t *n_rec;
+    int rec_cap;
+    int8_t *move_log;     // [n][64] nullable
+    int32_t *active;      // device counter: games with stone_num < 64 after this half-step
+};
+
+__global__ void __launch_bounds__(128) selfplay_turn_kernel(SelfplayArgs a) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.n) return;
+    int stone_num = a.stone_num[g];
+    if (stone_num >= 64) return;  // finished games take no more turns (the reference loop has exited)
+    const u64 b1 = a.p1[g], b2 = a.p2[g];
+    u64 own = a.color == 1 ? b1 : b2, opp = a.color == 1 ? b2 : b1;
+    const u64 legal = legal_moves(own, opp);
+    if (legal) {
+        const int placed = a.placed[g];
+        int k = -1;
+        if (a.rng_mode == IAGO_RNG_FORCED) {
+            k = placed < a.f_stride ? a.forced[g * a.f_stride + placed] : -1;
+        } else {
+            const float *lg = a.logits + g * 64;
+            if (a.select == SEL_GREEDY) {
+                // arg-max of the logits over legal moves, lowest index on ties (BASELINE configs[2])
+                float best = -3.0e38f;
+                for (u64 m = legal; m; m &= m - 1) {
+                    const int c = __ffsll((long long)m) - 1;
+                    const float v = lg[c];
+                    if (v > best) { best = v; k = c; }
+                }
+            } else {
+                // float32 softmax over all 64 cells, then float64 masked renormalisation and inverse cdf
+                float mx = -3.0e38f;
+                for (int i = 0; i < 64; i++) mx = fmaxf(mx, lg[i]);
+                float sum = 0.0f;
+                for (int i = 0; i < 64; i++) sum += expf(lg[i] - mx);
+                double total = 0.0;
+                for (u64 m = legal; m; m &= m - 1) total += (double)(expf(lg[__ffsll((long long)m) - 1] - mx) / sum);
+                double u;
+                if (a.rng_mode == IAGO_RNG_UNIFORMS)
+                    u = a.uniforms[g * a.u_stride + placed];
+                else
+                    u = (double)philox_m53(a.seed, a.game_id0 + (u64)g, (uint32_t)placed, a.stream_id) * (1.0 / 9007199254740992.0);
+                const double t = u * total;
+                double cum = 0.0;
+                for (u64 m = legal; m; m &= m - 1) {
+                    k = __ffsll((long long)m) - 1;
+                    cum += (double)(expf(lg[k] - mx) / sum);
+                    if (cum > t) break;
+                }
+            }
+        }
+        if (k < 0 || k > 63) {
+            stone_num = 64;  // replay stream exhausted
+        } else {
+            if (a.color == 1) {
+                const int r = a.n_rec[g];
+                if (r < a.rec_cap) {
+                    a.rec_own[g * a.rec_cap + r] = own;
+                    a.rec_opp[g * a.rec_cap + r] = opp;
+                    a.rec_action[g * a.rec_cap + r] = (int8_t)k;
+                }
+                a.n_rec[g] = r + 1;
+            }
+            place(1ULL << k, own, opp);
+            if (a.move_log) a.move_log[g * 64 + placed] = (int8_t)k;
+            a.placed[g] = placed + 1;
+            a.pass_flg[g] = 0;
+            stone_num += 1;
+            a.p1[g] = a.color == 1 ? own : opp;
+            a.p2[g] = a.color == 1 ? opp : own;
+        }
+    } else {
+        if (a.pass_flg[g]) stone_num = 64;
+        a.pass_flg[g] = 1;
+    }
+    a.stone_num[g] = stone_num;
+    if (a.color == 2 && stone_num < 64) atomicAdd(a.active, 1);
+}
+
+__global__ void selfplay_init_kernel(u64 *p1, u64 *p2, const u64 *in1, const u64 *in2, int32_t *stone_num, uint8_t *pass_flg,
+                                     int32_t *placed, int32_t *n_rec, int8_t *move_log, uint8_t *c1, uint8_t *c2, long long n) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    p1[g] = in1 ? in1[g] : ((1ULL << 35) | (1ULL << 28));  // game.py:26-30 / rl_self_play.py:12-16
+    p2[g] = in2 ? in2[g] : ((1ULL << 27) | (1ULL << 36));
+    stone_num[g] = 4;  // rl_self_play.py:20 — a counter, not a popcount
+    pass_flg[g] = 0;
+    placed[g] = 0;
+    n_rec[g] = 0;
+    c1[g] = 1;
+    c2[g] = 2;
+    if (move_log)
+        for (int i = 0; i < 64; i++) move_log[g * 64 + i] = -1;
+}
+
+__global__ void selfplay_judge_kernel(const u64 *p1, const u64 *p2, int8_t *result, long long n) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const int a = __popcll(p1[g]), b = __popcll(p2[g]);
+    result[g] = (int8_t)((a > b) - (a < b));
+}
+
+struct SelfplayWs {
+    long long cap = 0;
+    int32_t *stone_num = nullptr, *placed = nullptr, *active = nullptr;
+    uint8_t *pass_flg = nullptr, *c1 = nullptr, *c2 = nullptr;
+    float *logits = nullptr;
+    int32_t *h_active = nullptr;  // pinned
+};
+
+static int ws_ensure(iago_ctx *ctx, long long n, SelfplayWs **out) {
+    if (!ctx->selfplay) ctx->selfplay = new SelfplayWs();
+    SelfplayWs *w = static_cast<SelfplayWs *>(ctx->selfplay);
+    if (w->cap < n) {
+        cudaFree(w->stone_num); cudaFree(w->placed); cudaFree(w->pass_flg); cudaFree(w->c1); cudaFree(w->c2); cudaFree(w->logits);
+        IAGO_CUDA(cudaMalloc(&w->stone_num, n * 4));
+        IAGO_CUDA(cudaMalloc(&w->placed, n * 4));
+        IAGO_CUDA(cudaMalloc(&w->pass_flg, n));
+        IAGO_CUDA(cudaMalloc(&w->c1, n));
+        IAGO_CUDA(cudaMalloc(&w->c2, n));
+        IAGO_CUDA(cudaMalloc(&w->logits, n * 64 * 4));
+        w->cap = n;
+    }
+    if (!w->active) {
+        IAGO_CUDA(cudaMalloc(&w->active, 4));
+        IAGO_CUDA(cudaMallocHost(&w->h_active, 4));
+    }
+    *out = w;
+    return IAGO_OK;
+}
+
+void selfplay_destroy(iago_ctx *ctx) {
+    if (!ctx->selfplay) return;
+    SelfplayWs *w = static_cast<SelfplayWs *>(ctx->selfplay);
+    cudaFree(w->stone_num); cudaFree(w->placed); cudaFree(w->pass_flg); cudaFree(w->c1); cudaFree(w->c2); cudaFree(w->logits);
+    cudaFree(w->active);
+    if (w->h_active) cudaFreeHost(w->h_active);
+    delete w;
+    ctx->selfplay = nullptr;
+}
+
+}  // namespace iago
+
+using namespace iago;
+
+extern "C" {
+
+int iago_selfplay(iago_ctx *ctx, int slot_learner, int slot_opponent, int64_t n, const uint64_t *init_p1,
+                  const uint64_t *init_p2, int select, int precision, const iago_rng *rng, uint64_t *final_p1,
+                  uint64_t *final_p2, int8_t *result, uint64_t *rec_own, uint64_t *rec_opp, int8_t *rec_action,
+                  int32_t *n_rec, int rec_cap, int8_t *move_log, int64_t *stats, void *stream) {
+    IAGO_REQUIRE(ctx && rng && final_p1 && final_p2 && result && rec_own && rec_opp && rec_action && n_rec, "NULL argument");
+    IAGO_REQUIRE(n >= 0 && rec_cap > 0, "n < 0 or rec_cap <= 0");
+    IAGO_REQUIRE(select == SEL_SAMPLE || select == SEL_GREEDY, "select must be 0 (sample) or 1 (greedy)");
+    IAGO_REQUIRE(rng->mode >= IAGO_RNG_PHILOX && rng->mode <= IAGO_RNG_FORCED, "rng.mode");
+    if (rng->mode == IAGO_RNG_UNIFORMS) IAGO_REQUIRE(rng->uniforms && rng->u_stride > 0, "rng.uniforms / u_stride");
+    if (rng->mode == IAGO_RNG_FORCED) IAGO_REQUIRE(rng->forced && rng->f_stride > 0, "rng.forced / f_stride");
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    SelfplayWs *w = nullptr;
+    int rc = ws_ensure(ctx, n, &w);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    u64 *p1 = (u64 *)final_p1, *p2 = (u64 *)final_p2;  // the game state lives in the caller's output arrays
+    selfplay_init_kernel<<<grid, 128, 0, s>>>(p1, p2, (const u64 *)init_p1, (const u64 *)init_p2, w->stone_num, w->pass_flg,
+                                               w->placed, n_rec, move_log, w->c1, w->c2, n);
+    IAGO_CUDA(cudaGetLastError());
+    SelfplayArgs a{p1, p2, w->stone_num, w->pass_flg, w->placed, n, 1, select, rng->mode, rng->stream_id, rng->seed,
+                   rng->game_id0, rng->uniforms, rng->u_stride, rng->forced, rng->f_stride, w->logits, (u64 *)rec_own,
+                   (u64 *)rec_opp, rec_action, n_rec, rec_cap, move_log, w->active};
+    const bool need_net = rng->mode != IAGO_RNG_FORCED;
+    long long pairs = 0, forwards = 0;
+    for (;;) {
+        IAGO_CUDA(cudaMemsetAsync(w->active, 0, 4, s));
+        for (int color = 1; color <= 2; color++) {
+            if (need_net) {
+                rc = trunk_launch(ctx, color == 1 ? slot_learner : slot_opponent, 0, final_p1, final_p2,
+                                  color == 1 ? w->c1 : w->c2, n, w->logits, 0, precision, s);
+                if (rc) return rc;
+                forwards++;
+            }
+            a.color = color;
+            selfplay_turn_kernel<<<grid, 128, 0, s>>>(a);
+            IAGO_CUDA(cudaGetLastError());
+        }
+        pairs++;
+        IAGO_CUDA(cudaMemcpyAsync(w->h_active, w->active, 4, cudaMemcpyDeviceToHost, s));
+        IAGO_CUDA(cudaStreamSynchronize(s));
+        if (*w->h_active == 0) break;
+        if (pairs > 70) {  // every pair of turns places a stone or ends the game; 60 empties bound the loop
+            set_error("iago_selfplay: games did not terminate after %lld turn pairs", pairs);
+            return IAGO_E_STATE;
+        }
+    }
+    selfplay_judge_kernel<<<grid, 128, 0, s>>>(p1, p2, result, n);
+    IAGO_CUDA(cudaGetLastError());
+    if (stats) {
+        stats[0] = pairs;
+        stats[1] = forwards;
+    }
+    return IAGO_OK;
+}
+
+}  // extern "C"

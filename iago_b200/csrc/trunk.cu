@@ -593,7 +593,10 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
     return IAGO_OK;
 }
 
-static int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
+}  // extern "C"
+
+namespace iago {
+int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
                         int64_t n, float *out, int out_kind, int precision, void *stream) {
     IAGO_REQUIRE(ctx && p1 && p2 && color && out, "NULL argument");
     IAGO_REQUIRE(slot >= 0 && slot < 8, "slot out of range (0..7)");
@@ -622,6 +625,9 @@ static int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *
     ctx->timed = true;
     return IAGO_OK;
 }
+}  // namespace iago
+
+extern "C" {
 
 int iago_policy_forward(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
                         float *out, int out_kind, int precision, void *stream) {

@@ -211,6 +211,32 @@ class Engine:
                                     _ptr(out.get("moves")), _ptr(counters), self._stream(stream)))
         return out
 
+    def selfplay(self, slot_learner, slot_opponent, n, init_p1=None, init_p2=None, greedy=False, precision=3,
+                 rng: Optional[Rng] = None, rec_cap=40, want_moves=False, stream=None):
+        """n lockstep rl_self_play.Game(model1, model2)() games. Returns a dict of CUDA tensors (+ 'stats' host ints)."""
+        torch = _torch()
+        rng = rng or Rng(stream_id=STREAM_SELFPLAY)
+        dev = self._dev()
+        if init_p1 is not None:
+            self._check_i64(init_p1, init_p2)
+            assert init_p1.numel() == n
+        out = dict(final_p1=torch.empty(n, dtype=torch.int64, device=dev), final_p2=torch.empty(n, dtype=torch.int64, device=dev),
+                   result=torch.empty(n, dtype=torch.int8, device=dev),
+                   rec_own=torch.zeros((n, rec_cap), dtype=torch.int64, device=dev),
+                   rec_opp=torch.zeros((n, rec_cap), dtype=torch.int64, device=dev),
+                   rec_action=torch.full((n, rec_cap), -1, dtype=torch.int8, device=dev),
+                   n_rec=torch.empty(n, dtype=torch.int32, device=dev),
+                   moves=torch.empty((n, 64), dtype=torch.int8, device=dev) if want_moves else None)
+        stats = (C.c_int64 * 2)()
+        r, keep = self._rng_struct(rng, n, host=False)
+        check(self.lib.iago_selfplay(self.ctx, int(slot_learner), int(slot_opponent), n, _ptr(init_p1), _ptr(init_p2),
+                                     1 if greedy else 0, int(precision), C.byref(r), _ptr(out["final_p1"]),
+                                     _ptr(out["final_p2"]), _ptr(out["result"]), _ptr(out["rec_own"]), _ptr(out["rec_opp"]),
+                                     _ptr(out["rec_action"]), _ptr(out["n_rec"]), int(rec_cap), _ptr(out["moves"]),
+                                     C.cast(stats, C.c_void_p), self._stream(stream)))
+        out["stats"] = dict(turn_pairs=int(stats[0]), forwards=int(stats[1]))
+        return out
+
     # ------------------------------------------------------------------ host API (numpy arrays)
     def rollout_host(self, p1, p2, color, rng: Optional[Rng] = None, want_moves=False, out=None):
         """Same as rollout() with HOST buffers: H2D + kernel + D2H inside the C call (synchronous)."""

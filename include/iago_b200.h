@@ -142,6 +142,23 @@ IAGO_API int iago_policy_forward(iago_ctx *ctx, int slot, const uint64_t *p1, co
 IAGO_API int iago_value_forward(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
                                 int64_t n, float *out, int precision, void *stream);
 
+/* ---- batched learner-vs-opponent self-play: rl_self_play.Game(model1, model2)() (src/rl_self_play.py:8-145) ----
+ * n games in lockstep; colour 1 = learner (net in slot_learner), colour 2 = opponent (slot_opponent).
+ *   init_p1/init_p2 : start boards (NULL = the opening, rl_self_play.py:12-16).  stone_num starts at 4 whatever the
+ *                     boards hold, exactly like the reference (src/train_rl.py:43-46 pokes an extra stone in).
+ *   select          : 0 = sample from the masked, renormalised policy (rl_self_play.py:111-127; one uniform per move,
+ *                     rng as for iago_rollout), 1 = greedy arg-max of the logits over legal moves (lowest index on ties)
+ *   final_p1/final_p2 [n] : in/out game state, final boards on return;  result [n] = judge from colour 1's view
+ *   rec_own/rec_opp [n][rec_cap], rec_action [n][rec_cap], n_rec [n] : the learner's pre-move positions (own =
+ *                     learner's stones; the reference stores the same board with colours swapped,
+ *                     rl_self_play.py:134-138) and chosen actions
+ *   move_log [n][64] nullable; stats (HOST int64[2], nullable) = {turn pairs executed, trunk forwards launched}
+ * Synchronises the stream once per pair of turns (termination test).  All other pointers are device pointers. */
+IAGO_API int iago_selfplay(iago_ctx *ctx, int slot_learner, int slot_opponent, int64_t n, const uint64_t *init_p1,
+                           const uint64_t *init_p2, int select, int precision, const iago_rng *rng, uint64_t *final_p1,
+                           uint64_t *final_p2, int8_t *result, uint64_t *rec_own, uint64_t *rec_opp, int8_t *rec_action,
+                           int32_t *n_rec, int rec_cap, int8_t *move_log, int64_t *stats, void *stream);
+
 /* Integer-issue micro-benchmark used as the roofline denominator of the rollout kernel:
  * runs `iters` rounds of dependent LOP3/SHF chains on every SM and returns int32 lane-ops/s. */
 IAGO_API int iago_measure_int_peak(iago_ctx *ctx, int iters, double *lane_ops_per_s);

@@ -15,6 +15,13 @@ class IagoRng(C.Structure):
                 ("uniforms", C.c_void_p), ("u_stride", C.c_int64), ("forced", C.c_void_p), ("f_stride", C.c_int64)]
 
 
+class IagoMctsParams(C.Structure):
+    _fields_ = [("lmbda", C.c_double), ("c_puct", C.c_double), ("virtual_loss", C.c_double), ("n_thr", C.c_int32),
+                ("leaf_batch", C.c_int32), ("n_playouts", C.c_int32), ("slot_policy", C.c_int32), ("slot_value", C.c_int32),
+                ("precision", C.c_int32), ("cache_value", C.c_int32), ("reserved", C.c_int32), ("seed", C.c_uint64),
+                ("forced_v", C.c_void_p), ("forced_z", C.c_void_p), ("forced_stride", C.c_int64)]
+
+
 _P = C.c_void_p
 # name -> argtypes (restype is int unless listed in _RESTYPE); this table is also what tests compare with the header
 SIGNATURES = {
@@ -36,6 +43,15 @@ SIGNATURES = {
     "iago_value_forward": [_P, C.c_int, _P, _P, _P, C.c_int64, _P, C.c_int, _P],
     "iago_selfplay": [_P, C.c_int, C.c_int, C.c_int64, _P, _P, C.c_int, C.c_int, C.POINTER(IagoRng), _P, _P, _P, _P, _P, _P,
                       _P, C.c_int, _P, _P, _P],
+    "iago_mcts_create": [_P, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(_P)],
+    "iago_mcts_destroy": [_P],
+    "iago_mcts_set_roots": [_P, _P, _P, _P, C.c_int, _P],
+    "iago_mcts_get_roots": [_P, _P, _P, _P, _P, _P],
+    "iago_mcts_search": [_P, C.POINTER(IagoMctsParams), _P],
+    "iago_mcts_root_stats": [_P, _P, _P, _P, _P],
+    "iago_mcts_advance": [_P, _P, _P, _P],
+    "iago_mcts_export_tree": [_P, C.c_int, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_int32), _P],
+    "iago_mcts_overflows": [_P, C.POINTER(C.c_int64)],
     "iago_measure_int_peak": [_P, C.c_int, C.POINTER(C.c_double)],
     "iago_last_kernel_ms": [_P, C.POINTER(C.c_float)],
 }

@@ -143,6 +143,7 @@ struct RolloutArgs {
     int32_t *n_moves;
     int8_t *move_log;
     u64 *counters;
+    const u64 *game_ids;  // nullable: Philox game id of game g (default game_id0 + g)
 };
 
 template <int MODE, bool LOG>
@@ -161,6 +162,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const Ro
     int placed = 0, turns = 0;
     if (g < a.n) {
         const int color = a.color[g];
+        const u64 gid = a.game_ids ? a.game_ids[g] : a.game_id0 + (u64)g;
         u64 own = (color == 1) ? a.p1[g] : a.p2[g];
         u64 opp = (color == 1) ? a.p2[g] : a.p1[g];
         int stone_num = __popcll(own | opp);  // 64 - sum(state == 0), mcts_self_play.py:15
@@ -180,7 +182,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const Ro
                         if (MODE == IAGO_RNG_UNIFORMS)
                             m53 = __double2ull_rz(a.uniforms[g * a.u_stride + placed] * 9007199254740992.0);
                         else
-                            m53 = philox_m53(a.seed, a.game_id0 + (u64)g, (uint32_t)placed, a.stream_id);
+                            m53 = philox_m53(a.seed, gid, (uint32_t)placed, a.stream_id);
                         k = sample_move(w, own, opp, legal, m53, sa, sb);
                     }
                     if (MODE == IAGO_RNG_FORCED && (k < 0 || k > 63)) {
@@ -356,6 +358,21 @@ static int check_rng(const iago_rng *rng, bool need_weights, const iago_ctx *ctx
     return IAGO_OK;
 }
 
+int rollout_launch_ids(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
+                       uint64_t seed, uint32_t stream_id, const uint64_t *game_ids, int8_t *result, uint64_t *final_p1,
+                       uint64_t *final_p2, void *stream) {
+    if (!ctx->rollout_loaded) {
+        set_error("rollout weights not loaded (call iago_load_rollout first)");
+        return IAGO_E_STATE;
+    }
+    if (n == 0) return IAGO_OK;
+    RolloutArgs a{(const u64 *)p1, (const u64 *)p2, color, n, stream_id, seed, 0, nullptr, 0, nullptr, 0, result,
+                  (u64 *)final_p1, (u64 *)final_p2, nullptr, nullptr, nullptr, (const u64 *)game_ids};
+    launch_rollout<IAGO_RNG_PHILOX>(a, ctx->d_rollout, (cudaStream_t)stream);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
 }  // namespace iago
 
 using namespace iago;
@@ -450,7 +467,7 @@ int iago_rollout(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const ui
     cudaStream_t s = (cudaStream_t)stream;
     RolloutArgs a{(const u64 *)p1, (const u64 *)p2, color, n, rng->stream_id, rng->seed, rng->game_id0,
                   rng->uniforms, rng->u_stride, rng->forced, rng->f_stride, result, (u64 *)final_p1,
-                  (u64 *)final_p2, n_moves, move_log, (u64 *)counters};
+                  (u64 *)final_p2, n_moves, move_log, (u64 *)counters, nullptr};
     return rollout_launch(ctx, a, rng->mode, s);
 }
 
@@ -489,7 +506,7 @@ int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, con
                   rng->stream_id, rng->seed, rng->game_id0, (const double *)(d + o_rep), rng->u_stride,
                   (const int8_t *)(d + o_rep), rng->f_stride, (int8_t *)(d + o_res), (u64 *)(d + o_f1),
                   (u64 *)(d + o_f2), (int32_t *)(d + o_nm), move_log ? (int8_t *)(d + o_log) : nullptr,
-                  (u64 *)(d + o_cnt)};
+                  (u64 *)(d + o_cnt), nullptr};
     rc = rollout_launch(ctx, a, rng->mode, s);
     if (rc) return rc;
     IAGO_CUDA(cudaMemcpyAsync(h + o_f1, d + o_f1, out_end - o_f1, cudaMemcpyDeviceToHost, s));

@@ -163,6 +163,7 @@ struct TrunkArgs {
     const uint8_t *blob;  // packed weight units
     const float *bias;    // [n_layers][128]
     const float *head;    // policy: w9[128], b10[64]; value: b9 at [0], wfc[64] at [128..192)
+    const int *n_dev;     // nullable: the live position count is min(n, *n_dev) (request lists built on the device, mcts.cu)
 };
 
 // bias + ReLU + hi/lo fp16 split of 32 accumulator columns, written as 4 channel groups of this thread's tile row.
@@ -234,7 +235,9 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    const long long n_tiles = (a.n + 1) / 2;
+    long long n_pos = a.n;
+    if (a.n_dev) n_pos = min(n_pos, (long long)*a.n_dev);
+    const long long n_tiles = (n_pos + 1) / 2;
     const int L = net.n_layers;
     const bool split = a.precision >= 3;
 
@@ -337,7 +340,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
         uint32_t acc_phase[2] = {0, 0};
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const long long pos = tile * 2 + b;
-            const bool valid = pos < a.n;
+            const bool valid = pos < n_pos;
             // ---- layer-1 input: explicit im2col of the two bit planes, k = tap*2 + channel (0 = opponent, 1 = mover)
             if (half == 0) {
                 u64 own = 0, opp = 0;
@@ -437,7 +440,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
                             const long long p = tile * 2 + warp;
-                            if ((tid & 31) == 0 && p < a.n) a.out[p] = s;
+                            if ((tid & 31) == 0 && p < n_pos) a.out[p] = s;
                         }
                         asm volatile("bar.sync 2, 128;" ::: "memory");
                     }
@@ -472,6 +475,12 @@ struct TrunkState {
 static TrunkState *state(iago_ctx *ctx) {
     if (!ctx->trunk) ctx->trunk = new TrunkState();
     return static_cast<TrunkState *>(ctx->trunk);
+}
+
+bool trunk_slot_holds(iago_ctx *ctx, int slot, int kind) {
+    if (slot < 0 || slot >= 8 || !ctx->trunk) return false;
+    const NetSlot &s = static_cast<TrunkState *>(ctx->trunk)->slot[slot];
+    return s.loaded && s.desc.kind == kind;
 }
 
 void trunk_destroy(iago_ctx *ctx) {
@@ -597,7 +606,7 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
 
 namespace iago {
 int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
-                        int64_t n, float *out, int out_kind, int precision, void *stream) {
+                 int64_t n, float *out, int out_kind, int precision, void *stream, const int *n_dev) {
     IAGO_REQUIRE(ctx && p1 && p2 && color && out, "NULL argument");
     IAGO_REQUIRE(slot >= 0 && slot < 8, "slot out of range (0..7)");
     IAGO_REQUIRE(n >= 0, "n < 0");
@@ -616,7 +625,7 @@ int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, con
     }
     const long long tiles = (n + 1) / 2;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    TrunkArgs a{(const u64 *)p1, (const u64 *)p2, color, n, out, out_kind, precision, s.d_blob, s.d_bias, s.d_head};
+    TrunkArgs a{(const u64 *)p1, (const u64 *)p2, color, n, out, out_kind, precision, s.d_blob, s.d_bias, s.d_head, n_dev};
     cudaStream_t cs = (cudaStream_t)stream;
     IAGO_CUDA(cudaEventRecord(ctx->ev0, cs));
     trunk_kernel<<<grid, kThreads, kSmemBytes, cs>>>(a, s.d_desc);

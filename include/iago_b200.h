@@ -159,6 +159,57 @@ IAGO_API int iago_selfplay(iago_ctx *ctx, int slot_learner, int slot_opponent, i
                            uint64_t *final_p2, int8_t *result, uint64_t *rec_own, uint64_t *rec_opp, int8_t *rec_action,
                            int32_t *n_rec, int rec_cap, int8_t *move_log, int64_t *stats, void *stream);
 
+/* ---- PV-MCTS: MCTS.py:10-154 on a GPU-resident node pool, n_trees independent searches in lockstep ----
+ * One iago_mcts holds n_trees trees (one per game) of at most max_nodes nodes each.  A search runs waves of up to
+ * leaf_batch playouts per tree: leaf-parallel selection with virtual visits / virtual loss, ONE batched SLPolicy launch
+ * for the expansions, ONE batched Value launch and ONE lockstep rollout launch for the leaves, then backup.
+ * With leaf_batch = 1 the search is the reference's sequential playout loop, numpy scalar type for scalar type
+ * (DESIGN.md "PV-MCTS"); that mode is what the parity tests compare with the reference's own trees. */
+typedef struct iago_mcts iago_mcts;
+
+typedef struct iago_mcts_params {
+    double lmbda;          /* MCTS(lmbda=0.5): leaf_value = (1-lmbda) v + lmbda z        (MCTS.py:80,123-125) */
+    double c_puct;         /* MCTS(c_puct=1)                                              (MCTS.py:48-49)     */
+    double virtual_loss;   /* value subtracted per in-flight descent through a child (batched mode only)       */
+    int32_t n_thr;         /* MCTS(n_thr=15): a leaf is expanded once it has n_thr visits (MCTS.py:108)        */
+    int32_t leaf_batch;    /* playouts per tree per wave, 1 = the reference's sequential algorithm             */
+    int32_t n_playouts;    /* playouts per tree in this call (the reference runs until time_limit, MCTS.py:139) */
+    int32_t slot_policy;   /* net slots loaded with iago_load_net ('./models/sl_model.npz', value_model.npz)    */
+    int32_t slot_value;
+    int32_t precision;     /* 1 or 3, as for iago_policy_forward                                               */
+    int32_t cache_value;   /* 1 = keep Value(position) in the node instead of re-running it (same outputs)     */
+    int32_t reserved;
+    uint64_t seed;         /* Philox key of the rollouts: game id = (tree id << 32) | playout index, stream 2  */
+    const float *forced_v; /* HOST, nullable: [n_trees][forced_stride] leaf values v by playout index (replay) */
+    const int8_t *forced_z;/* HOST, nullable: rollout results z by playout index                                */
+    int64_t forced_stride;
+} iago_mcts_params;
+
+IAGO_API int iago_mcts_create(iago_ctx *ctx, int n_trees, int max_nodes, int max_leaf_batch, uint64_t tree_id0,
+                              iago_mcts **out);
+IAGO_API int iago_mcts_destroy(iago_mcts *m);
+/* Root positions (HOST arrays [n_trees]); reset_tree != 0 also starts fresh trees, root = Node(None, 1.0) (MCTS.py:81). */
+IAGO_API int iago_mcts_set_roots(iago_mcts *m, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
+                                 int reset_tree, void *stream);
+IAGO_API int iago_mcts_get_roots(iago_mcts *m, uint64_t *p1, uint64_t *p2, uint8_t *color, int64_t *playouts_done,
+                                 void *stream);
+/* MCTS.playout x n_playouts on every tree (MCTS.py:105-133, the loop of get_move :139-145). Synchronises at the end. */
+IAGO_API int iago_mcts_search(iago_mcts *m, const iago_mcts_params *params, void *stream);
+/* get_move's answer (MCTS.py:147): HOST outputs visits [n_trees][65], q [n_trees][65] (index = action, 64 = pass),
+ * best [n_trees] = most visited child, lowest action on ties; -2 if the root has no children yet (the reference
+ * raises ValueError there). */
+IAGO_API int iago_mcts_root_stats(iago_mcts *m, int32_t *visits, float *q, int8_t *best, void *stream);
+/* update_with_move(last_move) (MCTS.py:149-154) per tree: re-root on the child (its subtree is kept) or start a fresh
+ * tree if the move is not a child; the root position follows the move (-1 = pass).  action, mask: HOST [n_trees];
+ * mask nullable, trees with mask 0 do not move. */
+IAGO_API int iago_mcts_advance(iago_mcts *m, const int8_t *action, const uint8_t *mask, void *stream);
+/* Tree dump for tests: nodes in pool order (children of a node contiguous, ascending action). HOST outputs. */
+IAGO_API int iago_mcts_export_tree(iago_mcts *m, int tree, int32_t capacity, int32_t *parent, int8_t *action,
+                                   int32_t *n_visits, double *Q, double *P, int32_t *first_child, int32_t *n_children,
+                                   int32_t *count, void *stream);
+/* Expansions skipped because a tree's pool was full during the last search (0 in a correctly sized pool). */
+IAGO_API int iago_mcts_overflows(iago_mcts *m, int64_t *count);
+
 /* Integer-issue micro-benchmark used as the roofline denominator of the rollout kernel:
  * runs `iters` rounds of dependent LOP3/SHF chains on every SM and returns int32 lane-ops/s. */
 IAGO_API int iago_measure_int_peak(iago_ctx *ctx, int iters, double *lane_ops_per_s);

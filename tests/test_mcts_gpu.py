@@ -1,0 +1,195 @@
+"""PV-MCTS on the GPU node pool (csrc/mcts.cu through iago_mcts_*) against the reference's trees and the CPU oracle.
+
+  * replayed leaf values: leaf_batch = 1 with the reference's logged v / z (tests/golden/mcts.npz) must rebuild the
+    reference's tree — visit counts exactly; priors come from the GPU SL net, so P is compared within the net tolerance
+  * live evaluators: the oracle restatement (oracle/mcts_ref.py, itself pinned to the golden trees) is driven with the
+    GPU's own value / rollout / policy outputs; the device search must build the identical tree, bit for bit, both in
+    the sequential (leaf_batch = 1) and in the leaf-parallel mode (the device search is deterministic)
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden, model_file
+
+pytestmark = pytest.mark.gpu
+
+SEED = 99
+
+
+@pytest.fixture(scope="module")
+def nets(engine):
+    from iago_b200 import network
+    sl = network.SLPolicy().load(model_file("sl_model.npz"))
+    va = network.Value().load(model_file("value_model.npz"))
+    return sl, va
+
+
+def bb(state):
+    from iago_b200 import boards
+    p1, p2 = boards.to_bitboards(state)
+    return p1, p2
+
+
+def make_pool(engine, n_trees=1, leaf_batch=1, tree_id0=0, max_nodes=8192):
+    from iago_b200.search import SearchPool
+    return SearchPool(n_trees, max_nodes=max_nodes, max_leaf_batch=leaf_batch, tree_id0=tree_id0, engine=engine)
+
+
+def oracle_with_gpu_evaluators(engine, nets, state, color, tree_id=0, **kw):
+    from iago_b200 import Rng
+    from oracle import mcts_ref
+    sl, va = nets
+
+    def value_func(st, c):
+        p1, p2 = bb(st)
+        return np.float32(engine.value_forward_host(va.slot, p1, p2, c)[0])
+
+    def rollout_func(st, c, k):
+        p1, p2 = bb(st)
+        out = engine.rollout_host(p1, p2, c, rng=Rng.philox(seed=SEED, game_id0=(tree_id << 32) | k, stream_id=2))
+        return int(out["result"][0])
+
+    def policy_func(st, c):
+        p1, p2 = bb(st)
+        return engine.policy_forward_host(sl.slot, p1, p2, c, probs=True)[0]
+
+    return mcts_ref.RefSearch(state, color, value_func, rollout_func, policy_func, **kw)
+
+
+def assert_same_tree(dev, ref, exact_q=True):
+    assert len(dev["n"]) == len(ref["n"])
+    assert (dev["parent"] == ref["parent"]).all()
+    assert (dev["action"] == ref["action"]).all()
+    assert (dev["n"] == ref["n"]).all()
+    assert (dev["P"] == ref["P"]).all()
+    if exact_q:
+        assert (dev["Q"] == ref["Q"]).all()
+    else:
+        np.testing.assert_allclose(dev["Q"], ref["Q"], rtol=0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name", ["after19", "mid30", "late52_lam1_thr2", "late56_lam0_thr1"])
+def test_replayed_leaf_values_rebuild_the_reference_tree(engine, nets, name):
+    from iago_b200.search import flatten_bfs
+    g = load_golden("mcts")
+    sl, va = nets
+    state = g[f"{name}/root_state"].reshape(8, 8)
+    n = int(g[f"{name}/n_playouts"])
+    pool = make_pool(engine)
+    pool.set_roots(*bb(state), int(g[f"{name}/root_color"]))
+    pool.search(n, slot_policy=sl.slot, slot_value=va.slot, lmbda=float(g[f"{name}/lmbda"]), c_puct=float(g[f"{name}/c_puct"]),
+                n_thr=int(g[f"{name}/n_thr"]), leaf_batch=1, forced_v=g[f"{name}/v"].reshape(1, -1),
+                forced_z=g[f"{name}/z"].reshape(1, -1))
+    t = flatten_bfs(pool.export_tree(0))
+    assert (t["parent"] == g[f"{name}/tree_parent"]).all()
+    assert (t["action"] == g[f"{name}/tree_action"]).all()
+    assert (t["n"] == g[f"{name}/tree_n"]).all()
+    np.testing.assert_allclose(t["P"], g[f"{name}/tree_P"], rtol=0, atol=2e-4)   # priors: GPU SL net vs the reference's fp32 forward
+    assert (t["Q"] == g[f"{name}/tree_Q"]).all()                                   # same leaf values, same running mean, same scalar types
+    _, _, best = pool.root_stats()
+    assert int(best[0]) == int(g[f"{name}/best"])
+    assert pool.overflows() == 0
+
+
+@pytest.mark.parametrize("lmbda,n_thr,ply", [(0.5, 15, 0), (0.5, 4, 24), (1.0, 2, 50), (0.0, 3, 40)])
+def test_sequential_mode_equals_oracle_on_live_evaluators(engine, nets, golden_simulate, cref, lmbda, n_thr, ply):
+    from iago_b200.search import flatten_bfs
+    sl, va = nets
+    state, color = cref.start_board(), 1
+    for a, who in zip(golden_simulate["moves"][2][:ply], golden_simulate["movers"][2][:ply]):
+        cref.place_stone(state, int(a), int(who))
+        color = 3 - int(who)
+    n = 150
+    ref = oracle_with_gpu_evaluators(engine, nets, state, color, tree_id=5, lmbda=lmbda, c_puct=1, n_thr=n_thr)
+    ref.search(n, leaf_batch=1)
+    pool = make_pool(engine, tree_id0=5)
+    pool.set_roots(*bb(state), color)
+    pool.search(n, slot_policy=sl.slot, slot_value=va.slot, lmbda=lmbda, c_puct=1, n_thr=n_thr, leaf_batch=1, seed=SEED)
+    assert_same_tree(flatten_bfs(pool.export_tree(0)), ref.flatten())
+    _, _, best = pool.root_stats()
+    assert int(best[0]) == ref.best_move()
+
+
+@pytest.mark.parametrize("leaf_batch,vloss,cache", [(8, 1.0, True), (32, 1.0, False), (16, 0.0, True)])
+def test_leaf_parallel_mode_equals_oracle(engine, nets, cref, leaf_batch, vloss, cache):
+    from iago_b200.search import flatten_bfs
+    sl, va = nets
+    state = cref.start_board()
+    cref.place_stone(state, 19, 1)
+    n = 320
+    ref = oracle_with_gpu_evaluators(engine, nets, state, 2, tree_id=0, lmbda=0.5, c_puct=1, n_thr=6, cache_value=cache)
+    ref.search(n, leaf_batch=leaf_batch, virtual_loss=vloss)
+    pool = make_pool(engine, leaf_batch=leaf_batch)
+    pool.set_roots(*bb(state), 2)
+    pool.search(n, slot_policy=sl.slot, slot_value=va.slot, lmbda=0.5, c_puct=1, n_thr=6, leaf_batch=leaf_batch,
+                virtual_loss=vloss, cache_value=cache, seed=SEED)
+    assert_same_tree(flatten_bfs(pool.export_tree(0)), ref.flatten(exact=False), exact_q=False)
+    assert pool.overflows() == 0
+
+
+def test_trees_are_independent_and_keyed_by_tree_id(engine, nets, cref):
+    """4 trees in one pool: tree i equals a 1-tree pool created with tree_id0 = i (sharding never changes a result)."""
+    from iago_b200.search import flatten_bfs
+    sl, va = nets
+    state = cref.start_board()
+    kw = dict(slot_policy=sl.slot, slot_value=va.slot, lmbda=0.5, c_puct=1, n_thr=5, leaf_batch=8, seed=SEED)
+    big = make_pool(engine, n_trees=4, leaf_batch=8, tree_id0=10)
+    big.set_roots(*bb(state), 1)
+    big.search(160, **kw)
+    for i in (0, 3):
+        one = make_pool(engine, n_trees=1, leaf_batch=8, tree_id0=10 + i)
+        one.set_roots(*bb(state), 1)
+        one.search(160, **kw)
+        a, b = flatten_bfs(big.export_tree(i)), flatten_bfs(one.export_tree(0))
+        assert_same_tree(a, b)
+    v, q, best = big.root_stats()
+    assert v.shape == (4, 65) and (v.sum(axis=1) <= 160).all() and (best >= 0).all()
+
+
+def test_update_with_move_keeps_the_subtree(engine, nets, cref):
+    from iago_b200.search import flatten_bfs
+    sl, va = nets
+    state = cref.start_board()
+    kw = dict(slot_policy=sl.slot, slot_value=va.slot, lmbda=0.5, c_puct=1, n_thr=5, leaf_batch=1, seed=SEED)
+    ref = oracle_with_gpu_evaluators(engine, nets, state, 1, tree_id=0, lmbda=0.5, c_puct=1, n_thr=5)
+    ref.search(120, leaf_batch=1)
+    pool = make_pool(engine)
+    pool.set_roots(*bb(state), 1)
+    pool.search(120, **kw)
+    mv = ref.best_move()
+    ref.update_with_move(mv)
+    cref.place_stone(ref.state, mv, 1)
+    ref.color = 2
+    pool.advance([mv])
+    assert_same_tree(flatten_bfs(pool.export_tree(0)), ref.flatten())
+    p1, p2, color, done = pool.get_roots()
+    q1, q2 = bb(ref.state)
+    assert p1[0] == q1[0] and p2[0] == q2[0] and color[0] == 2 and done[0] == 120
+    # the search goes on from the kept subtree, still in step with the oracle
+    ref.search(60, leaf_batch=1)
+    pool.search(60, **kw)
+    assert_same_tree(flatten_bfs(pool.export_tree(0)), ref.flatten())
+    # a move that is not a child starts a fresh tree (MCTS.py:153-154)
+    pool.advance([63])
+    t = pool.export_tree(0)
+    assert len(t["n"]) == 1 and t["n"][0] == 0 and t["P"][0] == 1.1
+
+
+def test_mcts_facade(engine, nets, cref):
+    from iago_b200.MCTS import MCTS
+    m = MCTS(n_playouts=200, leaf_batch=8, seed=3)
+    state = cref.start_board()
+    cref.place_stone(state, 19, 1)
+    a = m.get_move(state, 2)
+    assert a in cref.legal_actions(state, 2)
+    root = m.root
+    assert root.n_visits == 200 and a in root.children
+    assert root.children[a].n_visits == max(ch.n_visits for ch in root.children.values())
+    kept = root.children[a].n_visits
+    m.update_with_move(a)
+    assert m.root.n_visits == kept and m.root.is_root()
+    m2 = MCTS(n_playouts=5)   # fewer playouts than n_thr: the root is never expanded, as in the reference
+    with pytest.raises(ValueError):
+        m2.get_move(state, 2)
+    p = m.policy_func(state, 2, cref.legal_actions(state, 2))
+    assert len(p) == len(cref.legal_actions(state, 2)) and abs(float(m.value_func(state, 2))) < 1.5

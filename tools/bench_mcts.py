@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""PV-MCTS playouts/s (BASELINE configs[3]): n_trees searches in lockstep, fixed playouts per move, leaf batch 256.
+
+    python tools/bench_mcts.py [--trees 64] [--playouts 16384] [--leaf-batch 256] [--moves 1] [--no-cache]
+
+One JSON line: playouts/s over all trees (CUDA events around iago_mcts_search), per-wave time, and what the
+value cache saved.  Root = the opening after move 19, colour 2 to move.
+"""
+import argparse, json, os, sys
+import numpy as np
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--trees", type=int, default=64)
+    ap.add_argument("--playouts", type=int, default=16384)
+    ap.add_argument("--leaf-batch", type=int, default=256)
+    ap.add_argument("--moves", type=int, default=1)
+    ap.add_argument("--warm", type=int, default=1)
+    ap.add_argument("--precision", type=int, default=3)
+    ap.add_argument("--no-cache", action="store_true")
+    ap.add_argument("--max-nodes", type=int, default=65536)
+    args = ap.parse_args()
+    import torch
+    import iago_b200
+    from iago_b200 import boards
+    from iago_b200.search import SearchPool
+    eng = iago_b200.Engine(0)
+    mdir = os.path.join(ROOT, "baseline", "_ref", "models")
+    eng.load_net(0, os.path.join(mdir, "sl_model.npz"))
+    eng.load_net(1, os.path.join(mdir, "value_model.npz"))
+    eng.load_rollout_npz(os.path.join(mdir, "rollout_model.npz"))
+    pool = SearchPool(args.trees, max_nodes=args.max_nodes, max_leaf_batch=args.leaf_batch, engine=eng)
+    # the opening after colour 1 plays 19 (known answer in SURVEY.md §4)
+    p1 = (1 << 19) | (1 << 27) | (1 << 28) | (1 << 35)
+    p2 = 1 << 36
+    kw = dict(slot_policy=0, slot_value=1, lmbda=0.5, c_puct=1, n_thr=15, leaf_batch=args.leaf_batch, virtual_loss=1.0,
+              precision=args.precision, cache_value=not args.no_cache, seed=1)
+    res = []
+    for rep in range(args.warm + 1):
+        pool.set_roots(p1, p2, 2, reset_tree=True)
+        ms = []
+        for mv in range(args.moves):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            pool.search(args.playouts, **kw)
+            b.record()
+            torch.cuda.synchronize()
+            ms.append(a.elapsed_time(b))
+            visits, q, best = pool.root_stats()
+            if mv + 1 < args.moves:
+                pool.advance(best)
+        res = ms
+    waves = -(-args.playouts // args.leaf_batch)
+    tot = args.trees * args.playouts * args.moves
+    t = sum(res) / 1e3
+    nodes = [len(pool.export_tree(i)["n"]) for i in range(min(args.trees, 4))]
+    print(json.dumps({"metric": "mcts_playouts_per_s", "value": tot / t, "trees": args.trees, "playouts_per_move": args.playouts,
+                      "leaf_batch": args.leaf_batch, "moves": args.moves, "ms_per_move": res, "ms_per_wave": res[0] / waves,
+                      "cache_value": not args.no_cache, "precision": args.precision, "overflows": pool.overflows(),
+                      "nodes_in_first_trees": nodes, "root_visits_tree0": visits[0][visits[0] > 0].tolist(), "best": best[:4].tolist()}))
+
+
+if __name__ == "__main__":
+    main()

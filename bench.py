@@ -138,6 +138,57 @@ print(json.dumps({{"plies_per_s": plies / dt, "games": {n_games}, "seconds": dt}
         return {"error": repr(e)[:200]}
 
 
+def _run_reference_snippet(body, timeout=600):
+    """Runs `body` (python source that prints one JSON line) with the UNMODIFIED reference modules loaded as `m`."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref, "mcts_self_play.py")):
+        return None
+    code = f"""
+import os, sys, time, json
+os.environ["IAGO_REFERENCE"] = {ref!r}
+sys.path.insert(0, {os.path.join(ROOT, 'oracle')!r})
+import numpy as np, ref_harness
+m = ref_harness.load()
+""" + body
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    try:
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=timeout, env=env)
+        return json.loads(res.stdout.strip().splitlines()[-1])
+    except Exception as e:
+        return {"error": repr(e)[:200]}
+
+
+def python_reference_selfplay(n_games=3):
+    """The unmodified src/rl_self_play.Game (sl_model vs sl_model) under the chainer stand-in, one core."""
+    return _run_reference_snippet(f"""
+net, ser = m["network"], m["chainer"].serializers
+a = net.SLPolicy(); ser.load_npz("./models/sl_model.npz", a)
+b = net.SLPolicy(); ser.load_npz("./models/sl_model.npz", b)
+np.random.seed(3)
+t0 = time.perf_counter()
+for g in range({n_games}):
+    m["rl_self_play"].Game(a, b)()
+dt = time.perf_counter() - t0
+print(json.dumps({{"games_per_s": {n_games} / dt, "games": {n_games}, "seconds": dt}}))
+""")
+
+
+def python_reference_mcts(n_playouts=60):
+    """The unmodified MCTS.playout (sl/value/rollout nets, lmbda 0.5) from the position after move 19, one core."""
+    return _run_reference_snippet(f"""
+gf = m["game"].GameFunctions
+s = np.zeros([8, 8], np.float32); s[4, 3] = s[3, 4] = 1; s[3, 3] = s[4, 4] = 2
+gf.place_stone(s, 19, 1)
+mc = m["MCTS"].MCTS()
+np.random.seed(5)
+t0 = time.perf_counter()
+for k in range({n_playouts}):
+    mc.playout(s.copy(), 2, mc.root)
+dt = time.perf_counter() - t0
+print(json.dumps({{"playouts_per_s": {n_playouts} / dt, "playouts": {n_playouts}, "seconds": dt}}))
+""")
+
+
 def cpu_baseline_block(budget_s=12.0):
     rate, threads, _, _ = cpu_port_throughput(8192)
     n = int(min(max(rate * budget_s / 60.0, 8192), 4_000_000))
@@ -296,10 +347,134 @@ def run_ours(args, rank, world, local_rank):
         }
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_block()
+    extra = {}
+    for name, fn in (("selfplay", section_selfplay), ("mcts", section_mcts)):
+        if name in args.sections:
+            try:
+                extra[name] = fn(eng, args, rank, world, dev, dist, barrier)
+            except Exception as e:  # a failed extra section must not lose the headline line
+                extra[name] = {"error": repr(e)[:300]}
+    if rank == 0:
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+SL_FLOP, VALUE_FLOP = 122847232, 122994944   # per position
+
+
+def model_path(name):
+    p = os.path.join(ROOT, "baseline", "_ref", "models", name)
+    if not os.path.isfile(p):
+        raise FileNotFoundError(f"{p}: run oracle/fetch_ref.py in the build container (baseline/_ref ships with gpurun)")
+    return p
+
+
+def bf16_peak():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"], "MEASURED_PEAKS.json bf16_tflops_sustained"
+    except Exception:
+        return 1386.3, "fallback (B200_PROFILING.md sustained bf16)"
+
+
+def section_selfplay(eng, args, rank, world, dev, dist, barrier):
+    """BASELINE configs[2]: SL-policy greedy self-play, 16,384-game lockstep batch per GPU, sl_model.npz both sides."""
+    import torch
+    from iago_b200 import Rng
+    n = args.selfplay_games
+    eng.load_net(0, model_path("sl_model.npz"))
+    reps = max(1, args.selfplay_steps)
+    eng.selfplay(0, 0, min(n, 2048), greedy=True, rng=Rng.philox(seed=1, stream_id=1))  # warm-up
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    fwd = pairs = 0
+    res = None
+    for i in range(reps):
+        ev[i][0].record()
+        res = eng.selfplay(0, 0, n, greedy=True, rng=Rng.philox(seed=args.seed, game_id0=(i * world + rank) * n, stream_id=1))
+        ev[i][1].record()
+        fwd += res["stats"]["forwards"]
+        pairs += res["stats"]["turn_pairs"]
+    barrier()
+    t = sum(a.elapsed_time(b) for a, b in ev) / 1e3
+    wins = torch.stack([(res["result"] == 1).sum(), (res["result"] == 0).sum(), (res["result"] == -1).sum()]).to(torch.int64)
+    tt = torch.tensor([t], dtype=torch.float64, device=dev)
+    cc = torch.tensor([reps * n, fwd * n], dtype=torch.int64, device=dev)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        dist.all_reduce(wins, op=dist.ReduceOp.SUM)   # win statistics: the only cross-GPU exchange of this workload
+    t = float(tt[0])
+    games, positions = cc.tolist()
+    peak, src = bf16_peak()
+    ach = positions * SL_FLOP / t / 1e12
+    out = {"metric": "selfplay_games_per_s", "value": games / t, "unit": "games/s", "ms_per_step": 1e3 * t / reps,
+           "config": {"workload": "SL-policy greedy self-play, lockstep batch per GPU, sl_model.npz vs sl_model.npz "
+                                  "(BASELINE configs[2])", "games_per_step_per_gpu": n, "steps": reps, "precision": "fp16 hi/lo split, 3 MMAs"},
+           "positions_per_s": positions / t, "trunk_forwards_per_game": fwd / reps,
+           "last_step_w_d_l": wins.tolist(),
+           "roofline": {"bound": "tensor", "kernel": "trunk_kernel", "achieved": ach, "peak": peak * world, "unit": "TFLOP/s",
+                        "frac": ach / (peak * world), "traffic": None, "peak_source": src,
+                        "note": "algorithmic FLOP (122,847,232 per position, counted once) over the whole self-play step incl. the turn "
+                                "kernels; the hi/lo split issues 3x this many MMA FLOP"}}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        py = python_reference_selfplay()
+        if py:
+            out["cpu_baseline"] = dict(py, unit="games/s", value=py.get("games_per_s"), cores=1, kind="reference",
+                                       sample="unmodified src/rl_self_play.Game under the numpy chainer stand-in, sampled moves")
+    return out
+
+
+def section_mcts(eng, args, rank, world, dev, dist, barrier):
+    """BASELINE configs[3]: PV-MCTS, fixed 16K playouts per move, virtual-loss leaf batch 256, many trees per GPU."""
+    import torch
+    from iago_b200.search import SearchPool
+    eng.load_net(0, model_path("sl_model.npz"))
+    eng.load_net(1, model_path("value_model.npz"))
+    T, B, N = args.mcts_trees, 256, args.mcts_playouts
+    pool = SearchPool(T, max_nodes=32768, max_leaf_batch=B, tree_id0=rank * T, engine=eng)
+    p1, p2 = (1 << 19) | (1 << 27) | (1 << 28) | (1 << 35), 1 << 36   # the opening after colour 1 plays 19
+    out = {}
+    for cache in (True, False):
+        kw = dict(slot_policy=0, slot_value=1, lmbda=0.5, c_puct=1, n_thr=15, leaf_batch=B, virtual_loss=1.0, precision=3,
+                  cache_value=cache, seed=args.seed)
+        pool.set_roots(p1, p2, 2, reset_tree=True)
+        pool.search(2 * B, **kw)   # warm-up waves
+        pool.set_roots(p1, p2, 2, reset_tree=True)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        pool.search(N, **kw)
+        b.record()
+        barrier()
+        tt = torch.tensor([a.elapsed_time(b) / 1e3], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t = float(tt[0])
+        visits, q, best = pool.root_stats()
+        out["cached" if cache else "uncached"] = {"value": T * N * world / t, "ms_per_move": 1e3 * t, "best_move_tree0": int(best[0]),
+                                                  "pool_overflows": pool.overflows()}
+    peak, src = bf16_peak()
+    unc = out["uncached"]["value"]
+    res = {"metric": "mcts_playouts_per_s", "value": out["cached"]["value"], "unit": "playouts/s",
+           "config": {"workload": "PV-MCTS, sl/value/rollout nets, lmbda 0.5, c_puct 1, n_thr 15, leaf batch 256, virtual loss 1, root = "
+                                  "opening after move 19, one move (BASELINE configs[3])", "trees_per_gpu": T, "playouts_per_move": N},
+           "value_cache_on": out["cached"], "value_cache_off": out["uncached"],
+           "roofline": {"bound": "tensor", "kernel": "trunk_kernel (value net, cache off: one forward per playout)",
+                        "achieved": unc * VALUE_FLOP / 1e12, "peak": peak * world, "unit": "TFLOP/s",
+                        "frac": unc * VALUE_FLOP / 1e12 / (peak * world), "traffic": None, "peak_source": src,
+                        "note": "algorithmic value-net FLOP per playout x playouts/s with the value cache OFF (the reference's work per "
+                                "playout); with the cache on most playouts need no net evaluation and the search is bound by the select "
+                                "kernel and the rollouts"}}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        py = python_reference_mcts()
+        if py:
+            res["cpu_baseline"] = dict(py, unit="playouts/s", value=py.get("playouts_per_s"), cores=1, kind="reference",
+                                       sample="unmodified MCTS.playout under the numpy chainer stand-in")
+    pool.close()
+    return res
 
 
 def main():
@@ -311,6 +486,11 @@ def main():
     ap.add_argument("--games", type=int, default=0, help="games per step per GPU (default 65,536; reference arm 16,384)")
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--sections", default="rollout,selfplay,mcts", help="extra sections to run after the headline rollout bench")
+    ap.add_argument("--selfplay-games", type=int, default=16384)
+    ap.add_argument("--selfplay-steps", type=int, default=2)
+    ap.add_argument("--mcts-trees", type=int, default=256)
+    ap.add_argument("--mcts-playouts", type=int, default=16384)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -141,12 +141,140 @@ __global__ void selfplay_judge_kernel(const u64 *p1, const u64 *p2, int8_t *resu
     result[g] = (int8_t)((a > b) - (a < b));
 }
 
+// ---------------------------------------------------------------- rl_env.GameEnv.step (rl_env.py:41-74) for n environments
+struct EnvArgs {
+    u64 *p1, *p2;
+    int32_t *stone_num;
+    uint8_t *pass_flg, *done;
+    int32_t *draws;          // uniforms consumed so far per environment (index of the next one)
+    const int8_t *action;    // learner's action (phase 1)
+    int8_t *opp_action;      // opponent's answer, -1 = pass (phase 2, nullable)
+    const float *probs;      // [n][64] SLPolicy output for colour 2 to move (phase 2)
+    long long n;
+    int rng_mode;
+    uint32_t stream_id;
+    u64 seed, game_id0;
+    const double *uniforms;
+    long long u_stride;
+    int32_t *errors;         // [0] rejection loops that hit the reference's recursion limit
+};
+
+__device__ __forceinline__ double env_uniform(const EnvArgs &a, long long g, int k) {
+    if (a.rng_mode == IAGO_RNG_UNIFORMS) return k < a.u_stride ? a.uniforms[g * a.u_stride + k] : 0.5;
+    return (double)philox_m53(a.seed, a.game_id0 + (u64)g, (uint32_t)k, a.stream_id) * (1.0 / 9007199254740992.0);
+}
+
+// Phase 1: the learner (colour 1) plays `action`; an illegal action is replaced by positions[floor(u * len)] (the reference
+// calls Python's random.choice there, rl_env.py:46-48); no legal move = pass, a second consecutive pass ends the game.
+__global__ void __launch_bounds__(128) env_learner_kernel(EnvArgs a) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.n) return;
+    a.done[g] = 0;
+    u64 own = a.p1[g], opp = a.p2[g];
+    const u64 legal = legal_moves(own, opp);
+    if (legal) {
+        int k = a.action[g];
+        if (k < 0 || k > 63 || !((legal >> k) & 1)) {
+            const int cnt = __popcll(legal);
+            const int d = a.draws[g];
+            int idx = (int)(env_uniform(a, g, d) * (double)cnt);
+            idx = idx < cnt ? idx : cnt - 1;
+            a.draws[g] = d + 1;
+            u64 m = legal;
+            for (int j = 0; j < idx; j++) m &= m - 1;
+            k = __ffsll((long long)m) - 1;
+        }
+        place(1ULL << k, own, opp);
+        a.p1[g] = own;
+        a.p2[g] = opp;
+        a.stone_num[g] += 1;
+        a.pass_flg[g] = 0;
+    } else {
+        if (a.pass_flg[g]) a.done[g] = 1;
+        a.pass_flg[g] = 1;
+    }
+}
+
+// get_position (rl_env.py:152-172, self_play.py:8-30): p = out - min(out) over ALL 64 cells in float32 (numpy's pairwise sum
+// order), np.random.choice = float64 cdf + searchsorted(right), re-drawn with the next uniform until the cell is legal.
+// Returns the cell or -1 when the reference's recursion limit (10,000, rl_env.py:8) is hit; d = index of the next uniform.
+__device__ __forceinline__ int unmasked_draw(const EnvArgs &a, long long g, const float *pr, u64 legal, int &d) {
+    float mn = pr[0];
+    for (int i = 1; i < 64; i++) mn = fminf(mn, pr[i]);
+    float r[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) r[j] = __fsub_rn(pr[j], mn);
+    for (int i = 8; i < 64; i += 8)
+#pragma unroll
+        for (int j = 0; j < 8; j++) r[j] = __fadd_rn(r[j], __fsub_rn(pr[i + j], mn));
+    const float sum = __fadd_rn(__fadd_rn(__fadd_rn(r[0], r[1]), __fadd_rn(r[2], r[3])),
+                                __fadd_rn(__fadd_rn(r[4], r[5]), __fadd_rn(r[6], r[7])));
+    double total = 0.0;
+    for (int i = 0; i < 64; i++) total = __dadd_rn(total, (double)__fdiv_rn(__fsub_rn(pr[i], mn), sum));
+    for (int attempt = 0; attempt < 10000; attempt++) {
+        const double u = env_uniform(a, g, d++);
+        double cum = 0.0;
+        int idx = 64;
+        for (int i = 0; i < 64; i++) {
+            cum = __dadd_rn(cum, (double)__fdiv_rn(__fsub_rn(pr[i], mn), sum));
+            if (__ddiv_rn(cum, total) > u) { idx = i; break; }
+        }
+        if (idx < 64 && ((legal >> idx) & 1)) return idx;
+    }
+    return -1;
+}
+
+// Phase 2: the opponent (colour 2) answers.
+__global__ void __launch_bounds__(128) env_opponent_kernel(EnvArgs a) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.n) return;
+    u64 own = a.p2[g], opp = a.p1[g];
+    const u64 legal = legal_moves(own, opp);
+    int chosen = -1;
+    if (legal) {
+        int d = a.draws[g];
+        chosen = unmasked_draw(a, g, a.probs + g * 64, legal, d);
+        a.draws[g] = d;
+        if (chosen < 0) {
+            atomicAdd(a.errors, 1);
+            a.done[g] = 1;
+        } else {
+            place(1ULL << chosen, own, opp);
+            a.p2[g] = own;
+            a.p1[g] = opp;
+            a.stone_num[g] += 1;
+            a.pass_flg[g] = 0;
+        }
+    } else {
+        if (a.pass_flg[g]) a.done[g] = 1;
+        a.pass_flg[g] = 1;
+    }
+    if (a.stone_num[g] >= 64) a.done[g] = 1;
+    if (a.opp_action) a.opp_action[g] = (int8_t)chosen;
+}
+
+// The sampler alone: p1 = mover's stones, p2 = the other side's; action -1 = no legal move, -2 = recursion limit.
+__global__ void __launch_bounds__(128) sample_unmasked_kernel(EnvArgs a) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.n) return;
+    const u64 legal = legal_moves(a.p1[g], a.p2[g]);
+    int chosen = -1;
+    if (legal) {
+        int d = a.draws[g];
+        chosen = unmasked_draw(a, g, a.probs + g * 64, legal, d);
+        a.draws[g] = d;
+        if (chosen < 0) { atomicAdd(a.errors, 1); chosen = -2; }
+    }
+    a.opp_action[g] = (int8_t)chosen;
+}
+
 struct SelfplayWs {
     long long cap = 0;
     int32_t *stone_num = nullptr, *placed = nullptr, *active = nullptr;
     uint8_t *pass_flg = nullptr, *c1 = nullptr, *c2 = nullptr;
     float *logits = nullptr;
     int32_t *h_active = nullptr;  // pinned
+    int32_t *env_err = nullptr;
 };
 
 static int ws_ensure(iago_ctx *ctx, long long n, SelfplayWs **out) {
@@ -175,6 +303,7 @@ void selfplay_destroy(iago_ctx *ctx) {
     SelfplayWs *w = static_cast<SelfplayWs *>(ctx->selfplay);
     cudaFree(w->stone_num); cudaFree(w->placed); cudaFree(w->pass_flg); cudaFree(w->c1); cudaFree(w->c2); cudaFree(w->logits);
     cudaFree(w->active);
+    cudaFree(w->env_err);
     if (w->h_active) cudaFreeHost(w->h_active);
     delete w;
     ctx->selfplay = nullptr;
@@ -239,6 +368,67 @@ int iago_selfplay(iago_ctx *ctx, int slot_learner, int slot_opponent, int64_t n,
     if (stats) {
         stats[0] = pairs;
         stats[1] = forwards;
+    }
+    return IAGO_OK;
+}
+
+int iago_env_step(iago_ctx *ctx, int slot_opponent, int precision, int64_t n, uint64_t *p1, uint64_t *p2, int32_t *stone_num,
+                  uint8_t *pass_flg, const int8_t *action, const iago_rng *rng, int32_t *draws, uint8_t *done,
+                  int8_t *opp_action, int32_t *errors_host, void *stream) {
+    IAGO_REQUIRE(ctx && p1 && p2 && stone_num && pass_flg && action && rng && draws && done, "NULL argument");
+    IAGO_REQUIRE(n >= 0, "n < 0");
+    IAGO_REQUIRE(rng->mode == IAGO_RNG_PHILOX || rng->mode == IAGO_RNG_UNIFORMS, "rng.mode must be PHILOX or UNIFORMS");
+    if (rng->mode == IAGO_RNG_UNIFORMS) IAGO_REQUIRE(rng->uniforms && rng->u_stride > 0, "rng.uniforms / u_stride");
+    if (errors_host) *errors_host = 0;
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    SelfplayWs *w = nullptr;
+    int rc = ws_ensure(ctx, n, &w);
+    if (rc) return rc;
+    if (!w->env_err) IAGO_CUDA(cudaMalloc(&w->env_err, 4));
+    cudaStream_t s = (cudaStream_t)stream;
+    IAGO_CUDA(cudaMemsetAsync(w->env_err, 0, 4, s));
+    const unsigned grid = (unsigned)((n + 127) / 128);
+    EnvArgs a{(u64 *)p1, (u64 *)p2, stone_num, pass_flg, done, draws, action, opp_action, w->logits, n, rng->mode,
+              rng->stream_id, rng->seed, rng->game_id0, rng->uniforms, rng->u_stride, w->env_err};
+    env_learner_kernel<<<grid, 128, 0, s>>>(a);
+    IAGO_CUDA(cudaGetLastError());
+    IAGO_CUDA(cudaMemsetAsync(w->c2, 2, (size_t)n, s));
+    rc = trunk_launch(ctx, slot_opponent, 0, p1, p2, w->c2, n, w->logits, 1, precision, s);  // probabilities, colour 2 to move
+    if (rc) return rc;
+    env_opponent_kernel<<<grid, 128, 0, s>>>(a);
+    IAGO_CUDA(cudaGetLastError());
+    if (errors_host) {
+        IAGO_CUDA(cudaMemcpyAsync(w->h_active, w->env_err, 4, cudaMemcpyDeviceToHost, s));
+        IAGO_CUDA(cudaStreamSynchronize(s));
+        *errors_host = *w->h_active;
+    }
+    return IAGO_OK;
+}
+
+int iago_sample_unmasked(iago_ctx *ctx, const float *probs, const uint64_t *own, const uint64_t *opp, int64_t n,
+                         const iago_rng *rng, int32_t *draws, int8_t *action, int32_t *errors_host, void *stream) {
+    IAGO_REQUIRE(ctx && probs && own && opp && rng && draws && action, "NULL argument");
+    IAGO_REQUIRE(n >= 0, "n < 0");
+    IAGO_REQUIRE(rng->mode == IAGO_RNG_PHILOX || rng->mode == IAGO_RNG_UNIFORMS, "rng.mode must be PHILOX or UNIFORMS");
+    if (rng->mode == IAGO_RNG_UNIFORMS) IAGO_REQUIRE(rng->uniforms && rng->u_stride > 0, "rng.uniforms / u_stride");
+    if (errors_host) *errors_host = 0;
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    SelfplayWs *w = nullptr;
+    int rc = ws_ensure(ctx, 1, &w);
+    if (rc) return rc;
+    if (!w->env_err) IAGO_CUDA(cudaMalloc(&w->env_err, 4));
+    cudaStream_t s = (cudaStream_t)stream;
+    IAGO_CUDA(cudaMemsetAsync(w->env_err, 0, 4, s));
+    EnvArgs a{(u64 *)own, (u64 *)opp, nullptr, nullptr, nullptr, draws, nullptr, action, probs, n, rng->mode,
+              rng->stream_id, rng->seed, rng->game_id0, rng->uniforms, rng->u_stride, w->env_err};
+    sample_unmasked_kernel<<<(unsigned)((n + 127) / 128), 128, 0, s>>>(a);
+    IAGO_CUDA(cudaGetLastError());
+    if (errors_host) {
+        IAGO_CUDA(cudaMemcpyAsync(w->h_active, w->env_err, 4, cudaMemcpyDeviceToHost, s));
+        IAGO_CUDA(cudaStreamSynchronize(s));
+        *errors_host = *w->h_active;
     }
     return IAGO_OK;
 }

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import IagoError, IagoRng, check
 
 RNG_PHILOX, RNG_UNIFORMS, RNG_FORCED = 0, 1, 2
-STREAM_ROLLOUT, STREAM_SELFPLAY, STREAM_MCTS = 0, 1, 2
+STREAM_ROLLOUT, STREAM_SELFPLAY, STREAM_MCTS, STREAM_ENV = 0, 1, 2, 3
 
 
 @dataclasses.dataclass
@@ -235,6 +235,37 @@ class Engine:
                                      _ptr(out["rec_action"]), _ptr(out["n_rec"]), int(rec_cap), _ptr(out["moves"]),
                                      C.cast(stats, C.c_void_p), self._stream(stream)))
         out["stats"] = dict(turn_pairs=int(stats[0]), forwards=int(stats[1]))
+        return out
+
+    def env_step(self, slot_opponent, p1, p2, stone_num, pass_flg, action, draws, rng: Optional[Rng] = None, precision=3,
+                 want_errors=True, stream=None):
+        """rl_env.GameEnv.step for n environments, in place on the CUDA state tensors (p1/p2 int64, stone_num/draws int32,
+        pass_flg uint8); action int8. Returns (done uint8[n], opp_action int8[n], rejection-limit errors)."""
+        torch = _torch()
+        rng = rng or Rng(stream_id=STREAM_ENV)
+        n = self._check_i64(p1, p2)
+        dev = self._dev()
+        done = torch.empty(n, dtype=torch.uint8, device=dev)
+        opp = torch.empty(n, dtype=torch.int8, device=dev)
+        err = C.c_int32(0)
+        r, keep = self._rng_struct(rng, n, host=False)
+        check(self.lib.iago_env_step(self.ctx, int(slot_opponent), int(precision), n, _ptr(p1), _ptr(p2), _ptr(stone_num),
+                                     _ptr(pass_flg), _ptr(action), C.byref(r), _ptr(draws), _ptr(done), _ptr(opp),
+                                     C.cast(C.byref(err), C.c_void_p) if want_errors else None, self._stream(stream)))
+        return done, opp, int(err.value)
+
+    def sample_unmasked(self, probs, own, opp, draws, rng: Optional[Rng] = None, stream=None):
+        """get_position's sampler (rl_env.py:152-172) on device tensors: int8 actions (-1 no legal move)."""
+        torch = _torch()
+        rng = rng or Rng(stream_id=STREAM_ENV)
+        n = self._check_i64(own, opp)
+        out = torch.empty(n, dtype=torch.int8, device=self._dev())
+        err = C.c_int32(0)
+        r, keep = self._rng_struct(rng, n, host=False)
+        check(self.lib.iago_sample_unmasked(self.ctx, _ptr(probs), _ptr(own), _ptr(opp), n, C.byref(r), _ptr(draws), _ptr(out),
+                                            C.cast(C.byref(err), C.c_void_p), self._stream(stream)))
+        if err.value:
+            raise RecursionError("maximum recursion depth exceeded")
         return out
 
     # ------------------------------------------------------------------ host API (numpy arrays)

@@ -159,6 +159,25 @@ IAGO_API int iago_selfplay(iago_ctx *ctx, int slot_learner, int slot_opponent, i
                            uint64_t *final_p2, int8_t *result, uint64_t *rec_own, uint64_t *rec_opp, int8_t *rec_action,
                            int32_t *n_rec, int rec_cap, int8_t *move_log, int64_t *stats, void *stream);
 
+/* ---- gym-style environment: rl_env.GameEnv.step(action) for n environments (rl_env.py:41-74) ----
+ * In/out DEVICE state per environment: p1/p2 boards, stone_num (starts at 4, rl_env.py:34), pass_flg, draws (uniforms consumed
+ * so far).  The learner (colour 1) plays action[i]; an illegal action is replaced by positions[floor(u * len)] with the next
+ * uniform (the reference calls Python's random.choice there, rl_env.py:46-48, a stream that cannot be replayed from doubles).
+ * The opponent (colour 2, SLPolicy in slot_opponent) answers through get_position (rl_env.py:152-172): p = out - min(out)
+ * over ALL 64 cells, renormalised, np.random.choice, re-drawn (one more uniform) until the cell is legal.
+ * done[i] = two consecutive passes or stone_num >= 64.  opp_action (nullable) = the opponent's move, -1 = pass.
+ * errors_host (HOST, nullable; reading it synchronises) = rejection loops that exceeded the reference's recursion limit
+ * of 10,000 (rl_env.py:8; the reference dies with RecursionError there).  rng.mode PHILOX or UNIFORMS. */
+IAGO_API int iago_env_step(iago_ctx *ctx, int slot_opponent, int precision, int64_t n, uint64_t *p1, uint64_t *p2,
+                           int32_t *stone_num, uint8_t *pass_flg, const int8_t *action, const iago_rng *rng,
+                           int32_t *draws, uint8_t *done, int8_t *opp_action, int32_t *errors_host, void *stream);
+
+/* The sampler of get_position / get_position_self alone (rl_env.py:152-172, self_play.py:8-30): probs [n][64] DEVICE (SLPolicy
+ * output for the mover), own/opp = mover's / other side's stones; action[i] = sampled legal cell, -1 = no legal move,
+ * -2 = recursion limit hit.  draws in/out as for iago_env_step. */
+IAGO_API int iago_sample_unmasked(iago_ctx *ctx, const float *probs, const uint64_t *own, const uint64_t *opp, int64_t n,
+                                  const iago_rng *rng, int32_t *draws, int8_t *action, int32_t *errors_host, void *stream);
+
 /* ---- PV-MCTS: MCTS.py:10-154 on a GPU-resident node pool, n_trees independent searches in lockstep ----
  * One iago_mcts holds n_trees trees (one per game) of at most max_nodes nodes each.  A search runs waves of up to
  * leaf_batch playouts per tree: leaf-parallel selection with virtual visits / virtual loss, ONE batched SLPolicy launch

@@ -15,6 +15,7 @@ Files:
                 yields (RandomState(seed).random_sample), move list, final board, result
   nets.npz      SLPolicy (sl_model, rl_model), Value, RolloutPolicy outputs on harvested positions
   selfplay.npz  src/rl_self_play.Game trajectories (normal and 'head/tail switched' openings)
+  env.npz       rl_env.GameEnv.step sequences (numpy standing in for cupy): actions, opponent answers, uniforms consumed
   mcts.npz      MCTS.playout sequences: per-playout v / z / priors and the resulting tree
 """
 import argparse
@@ -235,6 +236,52 @@ def gen_selfplay(mods, out, seed0):
         Game.place_stone = orig_place
 
 
+def gen_env(mods, out, seed0):
+    """rl_env.GameEnv (UNMODIFIED, imported with numpy standing in for cupy): learner plays scripted legal actions, the
+    opponent (RL/model0 wrapped like L.Classifier) answers; logs per-step opponent probabilities and the uniforms consumed."""
+    import importlib
+    import types
+    net, ser = mods["network"], mods["chainer"].serializers
+    rl_env = importlib.import_module("rl_env")
+    gf = mods["game"].GameFunctions
+    m2 = net.SLPolicy(); ser.load_npz("./models/RL/model0.npz", m2)
+    wrapped = types.SimpleNamespace(predictor=m2)
+    rec = dict(seed=[], actions=[], opp_actions=[], n_steps=[], uniforms=[], n_draws=[], final=[], judge=[], done_step=[], probs=[])
+    for g in range(6):
+        seed = seed0 + g
+        np.random.seed(seed)
+        env = rl_env.GameEnv(None, wrapped)
+        env.reset()
+        lrng = np.random.default_rng(seed)      # the learner's scripted choices (not part of the reference's streams)
+        acts, opps, probs = [], [], []
+        done, steps = False, 0
+        while not done and steps < 40:
+            legal = gf.legal_actions(env.state.copy(), 1)
+            a = int(legal[lrng.integers(len(legal))]) if legal else 0
+            before = env.state.copy()
+            obs, r, done, info = env.step(a)
+            # opponent's move = the colour-2 stone that appeared on a previously empty cell
+            mid = before.copy()
+            if legal:
+                gf.place_stone(mid, a, 1)
+            new2 = np.argwhere((env.state == 2) & (mid == 0))
+            opps.append(int(new2[0][0] * 8 + new2[0][1]) if len(new2) else -1)
+            pr = m2(np.stack([mid == 1, mid == 2], axis=0).astype(np.float32).reshape(1, 2, 8, 8)).data.reshape(64)
+            probs.append(pr.astype(np.float32))
+            acts.append(a)
+            steps += 1
+        nxt = np.random.random_sample()
+        u = np.random.RandomState(seed).random_sample(4096)
+        nd = int(np.argmax(u == nxt))
+        assert u[nd] == nxt
+        pad = lambda v, fill: np.concatenate([np.array(v, np.int8), np.full(40 - len(v), fill, np.int8)])
+        pp = np.zeros((40, 64), np.float32); pp[:len(probs)] = np.array(probs)
+        for k, v in dict(seed=seed, actions=pad(acts, -1), opp_actions=pad(opps, -1), n_steps=steps, uniforms=u[:512], n_draws=nd,
+                         final=u8(env.state).reshape(64), judge=env(), done_step=steps, probs=pp).items():
+            rec[k].append(v)
+    out["env"] = {k: np.array(v) for k, v in rec.items()}
+
+
 def flatten_tree(root):
     """BFS; children in dict insertion order (= ascending action, as expand() inserts them)."""
     nodes, parent, action = [root], [-1], [0]
@@ -327,6 +374,8 @@ def main():
         gen_nets(mods, harvest, out, rng); print("nets done", flush=True)
     if not only or "selfplay" in only:
         gen_selfplay(mods, out, 777); print("selfplay done", flush=True)
+    if not only or "env" in only:
+        gen_env(mods, out, 4242); print("env done", flush=True)
     if not only or "mcts" in only:
         gen_mcts(mods, out, out["simulate"]); print("mcts done", flush=True)
     os.makedirs(outdir, exist_ok=True)

@@ -1,0 +1,506 @@
+// reinforce.cu — K6: the REINFORCE update of src/train_rl.py:55-66 for the SL-size policy net, fp32 on the CUDA cores.
+//
+// Reference: x = stack([states==1, states==2]) (channel 0 = opponent, channel 1 = learner; the recorded states are
+// colour-swapped, rl_self_play.py:134-138), pred = SLPolicy(x) — already softmax PROBABILITIES (network.py:47) —
+// c = softmax_cross_entropy(pred, y, reduce='no') (a second log-softmax on the probabilities: reference quirk, kept),
+// loss = mean(c * r), backward, Adam (Chainer defaults alpha 1e-3 / 5e-4, beta 0.9 / 0.999, eps 1e-8) with the
+// WeightDecay(5e-4) hook (grad += 5e-4 * w) (src/train_rl.py:24-26).
+//
+// Layout: activations [M][C][64] fp32, kept for every layer (the backward needs them); parameters, gradients and Adam
+// moments are flat fp32 arrays in the reference's npz key order (include/iago_b200.h iago_load_net).  The gradient
+// returned is that of SUM_i c_i r_i (not the mean) plus the loss numerator and the position count, so that data-parallel
+// ranks can all-reduce sums and divide once (DESIGN.md "multi-GPU").
+//
+// Kernels: implicit-GEMM 3x3 conv on a 2-board x BN-channel CTA tile with 8 x (BN/16) register tiles (forward with
+// bias + ReLU; dgrad = the same kernel on transposed, tap-flipped weights with a ReLU-mask epilogue), a weight-gradient
+// kernel (o x c x 9 register tiles, positions split over CTAs, deterministic two-stage reduction), the head (1x1 conv,
+// per-cell bias, double softmax loss) and a fused WeightDecay + Adam step.  Every reduction runs in a fixed order: the
+// gradient is bit-reproducible run to run.
+#include <math.h>
+#include <string.h>
+
+#include <vector>
+
+#include "bitboard.cuh"
+#include "common.cuh"
+
+namespace iago {
+
+constexpr int kNP = 960768;  // SLPolicy parameters
+static const int kCin[8] = {2, 64, 128, 128, 128, 128, 128, 128};
+static const int kCout[8] = {64, 128, 128, 128, 128, 128, 128, 128};
+
+// ---------------------------------------------------------------- input planes
+__global__ void planes_kernel(const u64 *__restrict__ own, const u64 *__restrict__ opp, float *__restrict__ x, long long m) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (position, cell)
+    if (i >= m * 64) return;
+    const long long p = i >> 6;
+    const int cell = (int)(i & 63);
+    x[(p * 2 + 0) * 64 + cell] = (float)((opp[p] >> cell) & 1);  // channel 0 = opponent stones (game.py:167-174)
+    x[(p * 2 + 1) * 64 + cell] = (float)((own[p] >> cell) & 1);  // channel 1 = mover's (learner's) stones
+}
+
+// ---------------------------------------------------------------- weight re-layout
+// forward : Wk[(c*9 + tap)][o]      = W[o][c][tap]
+// dgrad   : Wk[(o*9 + tap)][c]      = W[o][c][8 - tap]      (inputs of the dgrad conv are the o channels)
+__global__ void relayout_kernel(const float *__restrict__ W, float *__restrict__ Wf, float *__restrict__ Wd, int cin, int cout, int cin_pad) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= cout * cin * 9) return;
+    const int tap = i % 9, c = (i / 9) % cin, o = i / (9 * cin);
+    const float w = W[i];
+    Wf[(size_t)(c * 9 + tap) * cout + o] = w;
+    if (Wd) Wd[(size_t)(o * 9 + (8 - tap)) * cin + c] = w;
+    (void)cin_pad;
+}
+
+// ---------------------------------------------------------------- 3x3 conv, implicit GEMM, fp32
+// CTA tile: 2 boards (128 rows) x BN output channels; thread (ty, tx): ty = board row (b = ty / 8, r = ty % 8) -> the 8
+// cells of that row, tx -> BN/16 consecutive output channels.
+enum { EPI_FWD = 0, EPI_DGRAD = 1 };
+
+template <int BN, int EPI>
+__global__ void __launch_bounds__(256) conv3x3_kernel(const float *__restrict__ in, const float *__restrict__ Wk,
+                                                      const float *__restrict__ bias, const float *__restrict__ mask_src,
+                                                      float *__restrict__ out, long long m, int cin, int cout) {
+    constexpr int TN = BN / 16;
+    __shared__ float in_s[8][2][10][10];
+    __shared__ __align__(16) float w_s[72][BN];
+    const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
+    const int b = ty >> 3, r = ty & 7;
+    const long long pos0 = (long long)blockIdx.x * 2;
+    const int n0 = blockIdx.y * BN + tx * TN;
+    float acc[8][TN];
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+#pragma unroll
+        for (int j = 0; j < TN; j++) acc[i][j] = 0.0f;
+    for (int i = tid; i < 8 * 2 * 100; i += 256) (&in_s[0][0][0][0])[i] = 0.0f;  // halo stays zero
+    const int chunks = (cin + 7) / 8;
+    for (int ch0 = 0; ch0 < chunks * 8; ch0 += 8) {
+        __syncthreads();
+        // input chunk: 8 channels x 2 boards x 64 cells
+        for (int i = tid; i < 8 * 2 * 64; i += 256) {
+            const int cell = i & 63, bb = (i >> 6) & 1, c = i >> 7;
+            const long long p = pos0 + bb;
+            float v = 0.0f;
+            if (p < m && ch0 + c < cin) v = in[(p * cin + ch0 + c) * 64 + cell];
+            in_s[c][bb][(cell >> 3) + 1][(cell & 7) + 1] = v;
+        }
+        // weight chunk: rows (ch0*9 .. ch0*9+71) x BN columns of this CTA
+        for (int i = tid; i < 72 * (BN / 4); i += 256) {
+            const int row = i / (BN / 4), c4 = i % (BN / 4);
+            const int krow = ch0 * 9 + row;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (krow < cin * 9) v = *reinterpret_cast<const float4 *>(Wk + (size_t)krow * cout + blockIdx.y * BN + c4 * 4);
+            *reinterpret_cast<float4 *>(&w_s[row][c4 * 4]) = v;
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int c = 0; c < 8; c++) {
+#pragma unroll
+            for (int dy = 0; dy < 3; dy++) {
+                float a[10];
+#pragma unroll
+                for (int i = 0; i < 10; i++) a[i] = in_s[c][b][r + dy][i];
+#pragma unroll
+                for (int dx = 0; dx < 3; dx++) {
+                    float w[TN];
+#pragma unroll
+                    for (int j = 0; j < TN; j += 4) {
+                        const float4 v = *reinterpret_cast<const float4 *>(&w_s[c * 9 + dy * 3 + dx][tx * TN + j]);
+                        w[j] = v.x; w[j + 1] = v.y; w[j + 2] = v.z; w[j + 3] = v.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; i++)
+#pragma unroll
+                        for (int j = 0; j < TN; j++) acc[i][j] = fmaf(a[i + dx], w[j], acc[i][j]);
+                }
+            }
+        }
+    }
+    const long long p = pos0 + b;
+    if (p >= m) return;
+#pragma unroll
+    for (int j = 0; j < TN; j++) {
+        const int n = n0 + j;
+        if (n >= cout) continue;
+        float v[8];
+        const size_t off = ((size_t)p * cout + n) * 64 + r * 8;
+        if (EPI == EPI_FWD) {
+            const float bj = bias[n];
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = fmaxf(acc[i][j] + bj, 0.0f);
+        } else {
+            const float4 m0 = *reinterpret_cast<const float4 *>(mask_src + off), m1 = *reinterpret_cast<const float4 *>(mask_src + off + 4);
+            const float mk[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = mk[i] > 0.0f ? acc[i][j] : 0.0f;
+        }
+        *reinterpret_cast<float4 *>(out + off) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(out + off + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+// ---------------------------------------------------------------- weight gradient
+// dW[o][c][tap] = sum over positions and cells of dY[p][o][cell] * X[p][c][cell + tap]; db[o] = sum dY[p][o][cell].
+// grid = (c tiles of 16, position slices); thread (og, ci): 8 output channels x 1 input channel x 9 taps.
+// partial[slice] holds [cout][cin][9] then [cout] bias sums (written by the c tile 0 CTAs).
+__global__ void __launch_bounds__(256) wgrad3x3_kernel(const float *__restrict__ x, const float *__restrict__ dy,
+                                                       float *__restrict__ partial, long long m, int cin, int cout,
+                                                       int pos_per_slice, size_t partial_stride) {
+    __shared__ float dy_s[128][65];
+    __shared__ float x_s[16][101];
+    const int tid = threadIdx.x, og = tid >> 4, ci = tid & 15;
+    const int c = blockIdx.x * 16 + ci;
+    const long long p_begin = (long long)blockIdx.y * pos_per_slice;
+    const long long p_end = min(m, p_begin + pos_per_slice);
+    float acc[8][9], bsum[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        bsum[j] = 0.0f;
+#pragma unroll
+        for (int t = 0; t < 9; t++) acc[j][t] = 0.0f;
+    }
+    for (int i = tid; i < 16 * 101; i += 256) (&x_s[0][0])[i] = 0.0f;
+    const int o_tiles = (cout + 127) / 128;  // cout <= 128 here
+    (void)o_tiles;
+    for (long long p = p_begin; p < p_end; p++) {
+        __syncthreads();
+        for (int i = tid; i < cout * 64; i += 256) dy_s[i >> 6][i & 63] = dy[(size_t)p * cout * 64 + i];
+        for (int i = tid; i < 16 * 64; i += 256) {
+            const int cc = i >> 6, cell = i & 63, cg = blockIdx.x * 16 + cc;
+            x_s[cc][((cell >> 3) + 1) * 10 + (cell & 7) + 1] = cg < cin ? x[((size_t)p * cin + cg) * 64 + cell] : 0.0f;
+        }
+        __syncthreads();
+        if (og * 8 < cout) {
+#pragma unroll 1
+            for (int row = 0; row < 8; row++) {
+                float xv[3][10];
+#pragma unroll
+                for (int dyy = 0; dyy < 3; dyy++)
+#pragma unroll
+                    for (int i = 0; i < 10; i++) xv[dyy][i] = x_s[ci][(row + dyy) * 10 + i];
+#pragma unroll
+                for (int col = 0; col < 8; col++) {
+#pragma unroll
+                    for (int j = 0; j < 8; j++) {
+                        const float d = dy_s[og * 8 + j][row * 8 + col];
+                        bsum[j] += d;
+#pragma unroll
+                        for (int t = 0; t < 9; t++) acc[j][t] = fmaf(d, xv[t / 3][col + t % 3], acc[j][t]);
+                    }
+                }
+            }
+        }
+    }
+    float *dst = partial + (size_t)blockIdx.y * partial_stride;
+    if (og * 8 < cout && c < cin) {
+#pragma unroll
+        for (int j = 0; j < 8; j++)
+#pragma unroll
+            for (int t = 0; t < 9; t++) dst[((size_t)(og * 8 + j) * cin + c) * 9 + t] = acc[j][t];
+    }
+    if (blockIdx.x == 0 && ci == 0 && og * 8 < cout) {
+#pragma unroll
+        for (int j = 0; j < 8; j++) dst[(size_t)cout * cin * 9 + og * 8 + j] = bsum[j];
+    }
+}
+
+// out[i] (+)= sum over slices of partial[s][i], slices in order.
+__global__ void reduce_slices_kernel(const float *__restrict__ partial, float *__restrict__ out, int count, int slices,
+                                     size_t stride, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    float s = 0.0f;
+    for (int k = 0; k < slices; k++) s += partial[(size_t)k * stride + i];
+    out[i] = accumulate ? out[i] + s : s;
+}
+
+// ---------------------------------------------------------------- head: conv9 (1x1) + bias10 + softmax + CE(softmax) * r
+// one CTA of 64 threads (= cells) per position.
+__device__ __forceinline__ float block64_max(float v, float *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xFFFFFFFFu, v, o));
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    const float r = fmaxf(red[0], red[1]);
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ float block64_sum(float v, float *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    const float r = red[0] + red[1];
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(64) head_kernel(const float *__restrict__ act8, const float *__restrict__ w9, const float *__restrict__ b10,
+                                                  const int8_t *__restrict__ action, const float *__restrict__ reward,
+                                                  float *__restrict__ dlogit, float *__restrict__ dact8, float *__restrict__ loss_terms,
+                                                  float *__restrict__ probs_out, long long m) {
+    __shared__ float red[2];
+    const long long p = blockIdx.x;
+    const int cell = threadIdx.x;
+    const float *a = act8 + (size_t)p * 128 * 64;
+    float logit = 0.0f;
+    for (int c = 0; c < 128; c++) logit = fmaf(w9[c], a[c * 64 + cell], logit);
+    logit += b10[cell];
+    // pred = softmax(logits)                                             network.py:47
+    const float mx = block64_max(logit, red);
+    const float e = expf(logit - mx);
+    const float pred = e / block64_sum(e, red);
+    if (probs_out) probs_out[p * 64 + cell] = pred;
+    // c = -log_softmax(pred)[y]; loss term = c * r                       src/train_rl.py:62-64
+    const float mx2 = block64_max(pred, red);
+    const float e2 = expf(pred - mx2);
+    const float s2 = block64_sum(e2, red);
+    const float q = e2 / s2;                      // softmax(pred)
+    const int y = action[p];
+    const float r = reward[p];
+    if (cell == y) loss_terms[p] = -(pred - mx2 - logf(s2)) * r;
+    const float dpred = r * (q - (cell == y ? 1.0f : 0.0f));
+    // back through pred = softmax(logits): dlogit = pred * (dpred - sum_k dpred_k pred_k)
+    const float dot = block64_sum(dpred * pred, red);
+    const float dl = pred * (dpred - dot);
+    dlogit[p * 64 + cell] = dl;
+    float *da = dact8 + (size_t)p * 128 * 64;
+    for (int c = 0; c < 128; c++) da[c * 64 + cell] = a[c * 64 + cell] > 0.0f ? w9[c] * dl : 0.0f;
+}
+
+// dw9[c] = sum_{p,cell} dlogit[p][cell] * act8[p][c][cell]  (block c < 128); db10[cell] = sum_p dlogit[p][cell] (block 128 + cell);
+// block 192: loss numerator = sum_p loss_terms[p].  Fixed-order tree per block.
+__global__ void __launch_bounds__(256) head_grad_kernel(const float *__restrict__ act8, const float *__restrict__ dlogit,
+                                                        const float *__restrict__ loss_terms, float *__restrict__ gw9,
+                                                        float *__restrict__ gb10, float *__restrict__ gloss, long long m, int accumulate) {
+    __shared__ float red[256];
+    const int blk = blockIdx.x, tid = threadIdx.x;
+    float s = 0.0f;
+    if (blk < 128) {
+        for (long long i = tid; i < m * 64; i += 256) s += dlogit[i] * act8[((i >> 6) * 128 + blk) * 64 + (i & 63)];
+    } else if (blk < 192) {
+        for (long long p = tid; p < m; p += 256) s += dlogit[p * 64 + (blk - 128)];
+    } else {
+        for (long long p = tid; p < m; p += 256) s += loss_terms[p];
+    }
+    red[tid] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) {
+        float *dst = blk < 128 ? gw9 + blk : (blk < 192 ? gb10 + (blk - 128) : gloss);
+        *dst = accumulate ? *dst + red[0] : red[0];
+    }
+}
+
+// ---------------------------------------------------------------- WeightDecay hook + Adam (Chainer: optimizers.Adam, optimizer_hooks.WeightDecay)
+__global__ void adam_kernel(float *__restrict__ p, float *__restrict__ mo, float *__restrict__ ve, const float *__restrict__ g,
+                            int n, float inv_count, float wd, float beta1, float beta2, float eps, float lr_t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float w = p[i];
+    const float grad = fmaf(wd, w, g[i] * inv_count);       // hook: grad += rate * param
+    const float m1 = mo[i] + (1.0f - beta1) * (grad - mo[i]);
+    const float v1 = ve[i] + (1.0f - beta2) * (grad * grad - ve[i]);
+    mo[i] = m1;
+    ve[i] = v1;
+    p[i] = w - lr_t * m1 / (sqrtf(v1) + eps);
+}
+
+}  // namespace iago
+
+using namespace iago;
+
+struct iago_trainer {
+    iago_ctx *ctx = nullptr;
+    int max_pos = 0;
+    float *params = nullptr, *adam_m = nullptr, *adam_v = nullptr;  // [kNP]
+    long long t = 0;
+    float *wf[8] = {}, *wd[8] = {};   // conv-kernel weight layouts
+    float *act[9] = {};               // act[0] = input planes, act[l] = output of block l
+    float *dbuf[2] = {};              // dY ping-pong [max_pos][128][64]
+    float *dlogit = nullptr, *loss_terms = nullptr, *partial = nullptr;
+    size_t partial_stride = 0;
+    int slices = 0;
+    size_t w_off[8], b_off[8], w9_off, b10_off;
+    std::vector<void *> allocs;
+};
+
+template <class T_>
+static int tr_alloc(iago_trainer *t, T_ **p, size_t count) {
+    IAGO_CUDA(cudaMalloc((void **)p, count * sizeof(T_)));
+    IAGO_CUDA(cudaMemset(*p, 0, count * sizeof(T_)));
+    t->allocs.push_back(*p);
+    return IAGO_OK;
+}
+
+static void relayout_all(iago_trainer *t, cudaStream_t s) {
+    for (int l = 0; l < 8; l++) {
+        const int n = kCout[l] * kCin[l] * 9;
+        relayout_kernel<<<(n + 255) / 256, 256, 0, s>>>(t->params + t->w_off[l], t->wf[l], l > 0 ? t->wd[l] : nullptr, kCin[l], kCout[l], 0);
+    }
+}
+
+extern "C" {
+
+int iago_reinforce_create(iago_ctx *ctx, const float *params, int64_t n_floats, int max_positions, iago_trainer **out) {
+    IAGO_REQUIRE(ctx && params && out, "NULL argument");
+    IAGO_REQUIRE(n_floats == kNP, "SLPolicy parameter vector must hold 960,768 floats (iago_load_net order)");
+    IAGO_REQUIRE(max_positions > 0 && max_positions <= (1 << 20), "max_positions out of range");
+    *out = nullptr;
+    DeviceGuard guard(ctx->device);
+    iago_trainer *t = new iago_trainer();
+    t->ctx = ctx;
+    t->max_pos = max_positions;
+    size_t off = 0;
+    for (int l = 0; l < 8; l++) {
+        t->w_off[l] = off; off += (size_t)kCout[l] * kCin[l] * 9;
+        t->b_off[l] = off; off += kCout[l];
+    }
+    t->w9_off = off; off += 128;
+    t->b10_off = off; off += 64;
+    int rc = 0;
+    const size_t M = max_positions;
+#define A(ptr, cnt) if (!rc) rc = tr_alloc(t, &(ptr), (cnt))
+    A(t->params, kNP); A(t->adam_m, kNP); A(t->adam_v, kNP);
+    for (int l = 0; l < 8; l++) {
+        A(t->wf[l], (size_t)kCout[l] * kCin[l] * 9);
+        if (l > 0) A(t->wd[l], (size_t)kCout[l] * kCin[l] * 9);
+    }
+    A(t->act[0], M * 2 * 64);
+    for (int l = 0; l < 8; l++) A(t->act[l + 1], M * kCout[l] * 64);
+    A(t->dbuf[0], M * 128 * 64); A(t->dbuf[1], M * 128 * 64);
+    A(t->dlogit, M * 64); A(t->loss_terms, M);
+    t->slices = 24;
+    t->partial_stride = (size_t)128 * 128 * 9 + 128;
+    A(t->partial, (size_t)t->slices * t->partial_stride);
+#undef A
+    if (rc) {
+        for (void *p : t->allocs) cudaFree(p);
+        delete t;
+        return rc;
+    }
+    IAGO_CUDA(cudaMemcpy(t->params, params, (size_t)kNP * 4, cudaMemcpyHostToDevice));
+    *out = t;
+    return IAGO_OK;
+}
+
+int iago_reinforce_destroy(iago_trainer *t) {
+    if (!t) return IAGO_OK;
+    DeviceGuard guard(t->ctx->device);
+    cudaDeviceSynchronize();
+    for (void *p : t->allocs) cudaFree(p);
+    delete t;
+    return IAGO_OK;
+}
+
+int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *opp, const int8_t *action, const float *reward,
+                        int64_t m, float *grad, int accumulate, float *probs_out, void *stream) {
+    IAGO_REQUIRE(t && own && opp && action && reward && grad, "NULL argument");
+    IAGO_REQUIRE(m >= 0 && m <= t->max_pos, "m exceeds the trainer's max_positions");
+    if (m == 0) return IAGO_OK;
+    DeviceGuard guard(t->ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    relayout_all(t, s);
+    planes_kernel<<<(unsigned)((m * 64 + 255) / 256), 256, 0, s>>>((const u64 *)own, (const u64 *)opp, t->act[0], m);
+    const unsigned tiles = (unsigned)((m + 1) / 2);
+    // ---- forward, activations kept
+    for (int l = 0; l < 8; l++) {
+        const float *b = t->params + t->b_off[l];
+        if (kCout[l] == 64)
+            conv3x3_kernel<64, EPI_FWD><<<dim3(tiles, 1), 256, 0, s>>>(t->act[l], t->wf[l], b, nullptr, t->act[l + 1], m, kCin[l], kCout[l]);
+        else
+            conv3x3_kernel<128, EPI_FWD><<<dim3(tiles, 1), 256, 0, s>>>(t->act[l], t->wf[l], b, nullptr, t->act[l + 1], m, kCin[l], kCout[l]);
+    }
+    IAGO_CUDA(cudaGetLastError());
+    // ---- head forward + backward
+    head_kernel<<<(unsigned)m, 64, 0, s>>>(t->act[8], t->params + t->w9_off, t->params + t->b10_off, action, reward, t->dlogit,
+                                          t->dbuf[0], t->loss_terms, probs_out, m);
+    head_grad_kernel<<<193, 256, 0, s>>>(t->act[8], t->dlogit, t->loss_terms, grad + t->w9_off, grad + t->b10_off, grad + kNP, m, accumulate);
+    IAGO_CUDA(cudaGetLastError());
+    // ---- backward through the 8 blocks
+    int cur = 0;
+    const int pos_per_slice = (int)((m + t->slices - 1) / t->slices);
+    const int slices = (int)((m + pos_per_slice - 1) / pos_per_slice);
+    for (int l = 7; l >= 0; l--) {
+        const float *dy = t->dbuf[cur];
+        wgrad3x3_kernel<<<dim3((kCin[l] + 15) / 16, slices), 256, 0, s>>>(t->act[l], dy, t->partial, m, kCin[l], kCout[l], pos_per_slice,
+                                                                          t->partial_stride);
+        const int count = kCout[l] * kCin[l] * 9 + kCout[l];  // W then b are adjacent in the flat layout as well
+        reduce_slices_kernel<<<(count + 255) / 256, 256, 0, s>>>(t->partial, grad + t->w_off[l], count, slices, t->partial_stride, accumulate);
+        if (l > 0) {
+            float *dx = t->dbuf[cur ^ 1];
+            if (kCin[l] == 64)
+                conv3x3_kernel<64, EPI_DGRAD><<<dim3(tiles, 1), 256, 0, s>>>(dy, t->wd[l], nullptr, t->act[l], dx, m, kCout[l], kCin[l]);
+            else
+                conv3x3_kernel<128, EPI_DGRAD><<<dim3(tiles, 1), 256, 0, s>>>(dy, t->wd[l], nullptr, t->act[l], dx, m, kCout[l], kCin[l]);
+            cur ^= 1;
+        }
+    }
+    IAGO_CUDA(cudaGetLastError());
+    // position count rides along with the gradient (element kNP + 1)
+    float mf = (float)m;
+    float *cnt = grad + kNP + 1;
+    if (accumulate) {
+        // add on the device, in stream order, without a host round trip
+        adam_kernel<<<1, 1, 0, s>>>(cnt, t->loss_terms, t->loss_terms + 1, cnt, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);  // no-op launch keeps ordering trivial
+        float h = 0.f;
+        IAGO_CUDA(cudaMemcpyAsync(&h, cnt, 4, cudaMemcpyDeviceToHost, s));
+        IAGO_CUDA(cudaStreamSynchronize(s));
+        mf += h;
+    }
+    IAGO_CUDA(cudaMemcpyAsync(cnt, &mf, 4, cudaMemcpyHostToDevice, s));
+    IAGO_CUDA(cudaStreamSynchronize(s));
+    return IAGO_OK;
+}
+
+int iago_reinforce_adam_step(iago_trainer *t, const float *grad, double count, double alpha, double beta1, double beta2, double eps,
+                             double weight_decay, void *stream) {
+    IAGO_REQUIRE(t && grad, "NULL argument");
+    IAGO_REQUIRE(count > 0, "count must be positive");
+    DeviceGuard guard(t->ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    t->t += 1;
+    const double fix1 = 1.0 - pow(beta1, (double)t->t), fix2 = 1.0 - pow(beta2, (double)t->t);
+    const float lr_t = (float)(alpha * sqrt(fix2) / fix1);   // Chainer AdamRule.lr
+    adam_kernel<<<(kNP + 255) / 256, 256, 0, s>>>(t->params, t->adam_m, t->adam_v, grad, kNP, (float)(1.0 / count), (float)weight_decay,
+                                                  (float)beta1, (float)beta2, (float)eps, lr_t);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+int iago_reinforce_get_state(iago_trainer *t, float *params, float *adam_m, float *adam_v, int64_t *step) {
+    IAGO_REQUIRE(t, "NULL argument");
+    DeviceGuard guard(t->ctx->device);
+    IAGO_CUDA(cudaDeviceSynchronize());
+    if (params) IAGO_CUDA(cudaMemcpy(params, t->params, (size_t)kNP * 4, cudaMemcpyDeviceToHost));
+    if (adam_m) IAGO_CUDA(cudaMemcpy(adam_m, t->adam_m, (size_t)kNP * 4, cudaMemcpyDeviceToHost));
+    if (adam_v) IAGO_CUDA(cudaMemcpy(adam_v, t->adam_v, (size_t)kNP * 4, cudaMemcpyDeviceToHost));
+    if (step) *step = t->t;
+    return IAGO_OK;
+}
+
+int iago_reinforce_set_state(iago_trainer *t, const float *params, const float *adam_m, const float *adam_v, int64_t step) {
+    IAGO_REQUIRE(t, "NULL argument");
+    DeviceGuard guard(t->ctx->device);
+    IAGO_CUDA(cudaDeviceSynchronize());
+    if (params) IAGO_CUDA(cudaMemcpy(t->params, params, (size_t)kNP * 4, cudaMemcpyHostToDevice));
+    if (adam_m) IAGO_CUDA(cudaMemcpy(t->adam_m, adam_m, (size_t)kNP * 4, cudaMemcpyHostToDevice));
+    if (adam_v) IAGO_CUDA(cudaMemcpy(t->adam_v, adam_v, (size_t)kNP * 4, cudaMemcpyHostToDevice));
+    if (step >= 0) t->t = step;
+    return IAGO_OK;
+}
+
+int iago_reinforce_sync_slot(iago_trainer *t, int slot) {
+    IAGO_REQUIRE(t, "NULL argument");
+    std::vector<float> h(kNP);
+    int rc = iago_reinforce_get_state(t, h.data(), nullptr, nullptr, nullptr);
+    if (rc) return rc;
+    return iago_load_net(t->ctx, slot, 0, h.data(), kNP);
+}
+
+}  // extern "C"

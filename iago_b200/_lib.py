@@ -54,6 +54,13 @@ SIGNATURES = {
     "iago_mcts_advance": [_P, _P, _P, _P],
     "iago_mcts_export_tree": [_P, C.c_int, C.c_int32, _P, _P, _P, _P, _P, _P, _P, C.POINTER(C.c_int32), _P],
     "iago_mcts_overflows": [_P, C.POINTER(C.c_int64)],
+    "iago_reinforce_create": [_P, _P, C.c_int64, C.c_int, C.POINTER(_P)],
+    "iago_reinforce_destroy": [_P],
+    "iago_reinforce_grad": [_P, _P, _P, _P, _P, C.c_int64, _P, C.c_int, _P, _P],
+    "iago_reinforce_adam_step": [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P],
+    "iago_reinforce_get_state": [_P, _P, _P, _P, C.POINTER(C.c_int64)],
+    "iago_reinforce_set_state": [_P, _P, _P, _P, C.c_int64],
+    "iago_reinforce_sync_slot": [_P, C.c_int],
     "iago_measure_int_peak": [_P, C.c_int, C.POINTER(C.c_double)],
     "iago_last_kernel_ms": [_P, C.POINTER(C.c_float)],
 }

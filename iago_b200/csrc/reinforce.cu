@@ -311,6 +311,8 @@ __global__ void adam_kernel(float *__restrict__ p, float *__restrict__ mo, float
     p[i] = w - lr_t * m1 / (sqrtf(v1) + eps);
 }
 
+__global__ void set_count_kernel(float *dst, float m, int accumulate) { *dst = accumulate ? *dst + m : m; }
+
 }  // namespace iago
 
 using namespace iago;
@@ -442,19 +444,9 @@ int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *op
         }
     }
     IAGO_CUDA(cudaGetLastError());
-    // position count rides along with the gradient (element kNP + 1)
-    float mf = (float)m;
-    float *cnt = grad + kNP + 1;
-    if (accumulate) {
-        // add on the device, in stream order, without a host round trip
-        adam_kernel<<<1, 1, 0, s>>>(cnt, t->loss_terms, t->loss_terms + 1, cnt, 0, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);  // no-op launch keeps ordering trivial
-        float h = 0.f;
-        IAGO_CUDA(cudaMemcpyAsync(&h, cnt, 4, cudaMemcpyDeviceToHost, s));
-        IAGO_CUDA(cudaStreamSynchronize(s));
-        mf += h;
-    }
-    IAGO_CUDA(cudaMemcpyAsync(cnt, &mf, 4, cudaMemcpyHostToDevice, s));
-    IAGO_CUDA(cudaStreamSynchronize(s));
+    // the position count rides along with the gradient (element kNP + 1), so ranks all-reduce numerator and count together
+    set_count_kernel<<<1, 1, 0, s>>>(grad + kNP + 1, (float)m, accumulate);
+    IAGO_CUDA(cudaGetLastError());
     return IAGO_OK;
 }
 

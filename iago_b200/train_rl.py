@@ -1,0 +1,143 @@
+"""REINFORCE self-play training — the update of /root/reference/src/train_rl.py:39-66 on the GPU, sharded over ranks.
+
+    trainer = ReinforceTrainer("models/RL/model2.npz", alpha=1e-3)          # src/train_rl.py:22-26
+    stats = trainer.train_set(opponent, n_games=64)                          # one `while` body of src/train_rl.py:32-66
+
+One set = 2N games of rl_self_play.Game(model1, model2) — odd-numbered games start from a 'head/tail switched' opening
+(an extra, un-flipped colour-2 stone on one of (2,4),(3,5),(4,2),(5,3), src/train_rl.py:43-46) — then ONE update:
+loss = mean(softmax_cross_entropy(model1(x), y, reduce='no') * r), Adam + WeightDecay(5e-4).
+
+Data parallel: every rank plays its own games (global game ids key the RNG) and computes the gradient of SUM c*r over its
+own positions; the flat vector [gradient | SUM c*r | position count] (3.84 MB) is all-reduced (NCCL, sum) and every rank
+applies the identical Adam step to its replica — exactly the update one process would make on the union of the games.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import boards, npz
+from ._lib import check
+from .engine import Rng, STREAM_SELFPLAY, default_engine
+
+N_PARAMS = npz.N_PARAMS[npz.KIND_POLICY]
+SWITCH_CELLS = [2 * 8 + 4, 3 * 8 + 5, 4 * 8 + 2, 5 * 8 + 3]   # src/train_rl.py:45
+
+
+class ReinforceTrainer:
+    def __init__(self, params, alpha=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=5e-4, max_positions=8192,
+                 device=0, slot=6, precision=3, group=None):
+        self.eng = default_engine(device)
+        self.lib = self.eng.lib
+        self.device, self.slot, self.precision, self.group = device, slot, precision, group
+        self.hp = dict(alpha=alpha, beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay)
+        if isinstance(params, (str, bytes)) or hasattr(params, "__fspath__"):
+            params = npz.read_npz(params)
+        flat = npz.flatten(params, npz.KIND_POLICY)
+        h = C.c_void_p()
+        check(self.lib.iago_reinforce_create(self.eng.ctx, flat.ctypes.data, flat.size, int(max_positions), C.byref(h)))
+        self.h, self.max_positions = h, int(max_positions)
+        self.grad = torch.zeros(N_PARAMS + 2, dtype=torch.float32, device=torch.device("cuda", device))
+        self.sync_slot()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.iago_reinforce_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- the learner as a playable model (rl_self_play.play_games wants .slot / .precision)
+    def sync_slot(self):
+        check(self.lib.iago_reinforce_sync_slot(self.h, int(self.slot)))
+
+    # ---- gradient of SUM c*r over a batch of recorded decisions (device tensors)
+    def gradient(self, own, opp, action, reward, accumulate=False, want_probs=False):
+        m = own.numel()
+        probs = torch.empty((m, 64), dtype=torch.float32, device=own.device) if want_probs else None
+        for lo in range(0, m, self.max_positions):
+            hi = min(m, lo + self.max_positions)
+            sl = slice(lo, hi)
+            check(self.lib.iago_reinforce_grad(self.h, C.c_void_p(own[sl].data_ptr()), C.c_void_p(opp[sl].data_ptr()),
+                                               C.c_void_p(action[sl].data_ptr()), C.c_void_p(reward[sl].data_ptr()), hi - lo,
+                                               C.c_void_p(self.grad.data_ptr()), 1 if (accumulate or lo > 0) else 0,
+                                               C.c_void_p(probs[sl].data_ptr()) if want_probs else None, self.eng._stream(None)))
+        return probs
+
+    def all_reduce(self):
+        """Sum [gradient | loss numerator | count] over the ranks (the only collective of the training path)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
+
+    def update(self):
+        """optimizer.update(): all-reduce, WeightDecay hook, Adam, refresh the playing slot. Returns (mean loss, positions)."""
+        self.all_reduce()
+        tail = self.grad[N_PARAMS:].tolist()
+        count = tail[1]
+        if count <= 0:
+            return 0.0, 0
+        hp = self.hp
+        check(self.lib.iago_reinforce_adam_step(self.h, C.c_void_p(self.grad.data_ptr()), float(count), hp["alpha"], hp["beta1"],
+                                                hp["beta2"], hp["eps"], hp["weight_decay"], self.eng._stream(None)))
+        self.sync_slot()
+        return tail[0] / count, int(count)
+
+    # ---- one set of games + one update
+    def play_set(self, opponent, n_games, seed=0, game_id0=0, switch_rng=None):
+        """2N games vs `opponent` (an SLPolicy with a resident slot). Returns flattened learner decisions on the device."""
+        dev = self.grad.device
+        init = np.tile(boards.start_state(), (n_games, 1, 1))
+        switch_rng = switch_rng or np.random.default_rng(seed + 7919 * (game_id0 + 1))
+        for i in range(1, n_games, 2):   # "switch head and tail" on odd games
+            c = SWITCH_CELLS[int(switch_rng.integers(4))]
+            init[i, c // 8, c % 8] = 2
+        q1, q2 = boards.to_bitboards(init)
+        i1 = torch.from_numpy(q1.view(np.int64).copy()).to(dev)
+        i2 = torch.from_numpy(q2.view(np.int64).copy()).to(dev)
+        out = self.eng.selfplay(self.slot, opponent.slot, n_games, i1, i2, greedy=False, precision=self.precision,
+                                rng=Rng.philox(seed=seed, game_id0=game_id0, stream_id=STREAM_SELFPLAY))
+        cap = out["rec_own"].shape[1]
+        valid = torch.arange(cap, device=dev)[None, :] < out["n_rec"].clamp(max=cap)[:, None]
+        reward = out["result"].to(torch.float32)[:, None].expand(-1, cap)
+        return dict(own=out["rec_own"][valid].contiguous(), opp=out["rec_opp"][valid].contiguous(),
+                    action=out["rec_action"][valid].contiguous(), reward=reward[valid].contiguous(),
+                    wins=int((out["result"] == 1).sum()), games=n_games)
+
+    def train_set(self, opponent, n_games=64, seed=0, game_id0=0):
+        d = self.play_set(opponent, n_games, seed=seed, game_id0=game_id0)
+        self.gradient(d["own"], d["opp"], d["action"], d["reward"])
+        loss, count = self.update()
+        return dict(rate=d["wins"] / d["games"], loss=loss, positions=count)
+
+    # ---- checkpoints in the reference's formats (serializers.save_npz of the model and of the optimizer)
+    def state(self):
+        p, m, v = (np.empty(N_PARAMS, np.float32) for _ in range(3))
+        t = C.c_int64()
+        check(self.lib.iago_reinforce_get_state(self.h, p.ctypes.data, m.ctypes.data, v.ctypes.data, C.byref(t)))
+        return p, m, v, int(t.value)
+
+    def params(self):
+        return npz.unflatten(self.state()[0], npz.KIND_POLICY)
+
+    def load_state(self, params=None, adam_m=None, adam_v=None, step=-1):
+        a = lambda x: None if x is None else np.ascontiguousarray(x, np.float32).ctypes.data
+        keep = [None if x is None else np.ascontiguousarray(x, np.float32) for x in (params, adam_m, adam_v)]
+        check(self.lib.iago_reinforce_set_state(self.h, *[None if k is None else k.ctypes.data for k in keep], int(step)))
+        self.sync_slot()
+
+    def save_model(self, path, prefix=""):
+        npz.save_npz(path, self.params(), prefix=prefix)
+
+    def save_optimizer(self, path):
+        """Chainer optimizer archive layout (as models/rollout_optimizer.npz): 't', 'epoch' and per parameter '<path>/t', '/m', '/v'."""
+        p, m, v, t = self.state()
+        M, V = npz.unflatten(m, npz.KIND_POLICY), npz.unflatten(v, npz.KIND_POLICY)
+        d = {"t": np.array(t, np.int32), "epoch": np.array(0, np.int32)}
+        for k in M:
+            d[f"{k}/t"], d[f"{k}/m"], d[f"{k}/v"] = np.array(t, np.int32), M[k], V[k]
+        np.savez_compressed(path, **d)

@@ -229,6 +229,31 @@ IAGO_API int iago_mcts_export_tree(iago_mcts *m, int tree, int32_t capacity, int
 /* Expansions skipped because a tree's pool was full during the last search (0 in a correctly sized pool). */
 IAGO_API int iago_mcts_overflows(iago_mcts *m, int64_t *count);
 
+/* ---- REINFORCE update of the SL-size policy: src/train_rl.py:55-66 (K6) ----
+ * A trainer owns the learner's fp32 parameters (flat, iago_load_net order, kind 0), Adam moments and the activation
+ * workspace for up to max_positions positions per call. */
+typedef struct iago_trainer iago_trainer;
+IAGO_API int iago_reinforce_create(iago_ctx *ctx, const float *params, int64_t n_floats, int max_positions, iago_trainer **out);
+IAGO_API int iago_reinforce_destroy(iago_trainer *t);
+/* Gradient of SUM_i c_i * r_i, c = softmax_cross_entropy(SLPolicy(x), y, reduce='no') on the PROBABILITIES the net returns
+ * (the reference's double softmax, src/train_rl.py:61-64), for m recorded learner decisions: own/opp = learner's / opponent's
+ * stones before the move (rl_self_play.py:134-138), action = y, reward = the game's judge per position.  DEVICE pointers.
+ * grad: DEVICE float[960768 + 2]: the gradient in parameter order, then SUM c*r, then the position count — divide by the
+ * count (after an all-reduce across ranks, if any) to get the reference's mean.  accumulate != 0 adds to grad.
+ * probs_out (nullable, DEVICE [m][64]) receives pred. */
+IAGO_API int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *opp, const int8_t *action,
+                                 const float *reward, int64_t m, float *grad, int accumulate, float *probs_out, void *stream);
+/* optimizer.update() with Chainer's Adam + WeightDecay hook (src/train_rl.py:24-26,66): g = grad / count + weight_decay * w;
+ * m += (1-b1)(g-m); v += (1-b2)(g*g-v); w -= alpha*sqrt(1-b2^t)/(1-b1^t) * m / (sqrt(v)+eps).  grad: DEVICE. */
+IAGO_API int iago_reinforce_adam_step(iago_trainer *t, const float *grad, double count, double alpha, double beta1, double beta2,
+                                      double eps, double weight_decay, void *stream);
+/* Parameters / Adam state to and from HOST arrays (checkpoints: serializers.save_npz of model and optimizer,
+ * src/train_rl.py:76-77); any pointer may be NULL; step < 0 keeps t. */
+IAGO_API int iago_reinforce_get_state(iago_trainer *t, float *params, float *adam_m, float *adam_v, int64_t *step);
+IAGO_API int iago_reinforce_set_state(iago_trainer *t, const float *params, const float *adam_m, const float *adam_v, int64_t step);
+/* Makes the trainer's current parameters the policy in net slot `slot` (what self-play then plays with). */
+IAGO_API int iago_reinforce_sync_slot(iago_trainer *t, int slot);
+
 /* Integer-issue micro-benchmark used as the roofline denominator of the rollout kernel:
  * runs `iters` rounds of dependent LOP3/SHF chains on every SM and returns int32 lane-ops/s. */
 IAGO_API int iago_measure_int_peak(iago_ctx *ctx, int iters, double *lane_ops_per_s);

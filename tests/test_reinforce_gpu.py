@@ -1,0 +1,135 @@
+"""K6 — the REINFORCE gradient and Adam step (iago_reinforce_*) vs the torch float64 autograd restatement of
+src/train_rl.py:55-66 (oracle/reinforce_ref.py) on the reference's own recorded games (tests/golden/selfplay.npz).
+
+Tolerance (fp32 arithmetic on the GPU, float64 in the oracle): per parameter tensor, max |g_gpu - g_ref| <= 1e-3 * max |g_ref|
+(+1e-6 absolute); loss numerator relative 1e-5; the Adam + WeightDecay rule applied to the GPU's gradient within 1e-6 absolute per step."""
+import numpy as np
+import pytest
+
+from conftest import load_golden, model_file
+
+pytestmark = pytest.mark.gpu
+
+
+def golden_batch():
+    g = load_golden("selfplay")
+    states, actions, rewards = [], [], []
+    for i in range(len(g["seed"])):
+        k = int(g["n_states"][i])
+        states.append(g["states"][i][:k].reshape(k, 8, 8))
+        actions.append(g["actions"][i][:k])
+        rewards.append(np.full(k, g["judge"][i], np.float32))
+    return np.concatenate(states), np.concatenate(actions).astype(np.int64), np.concatenate(rewards)
+
+
+def to_device(states):
+    import torch
+    from iago_b200 import boards
+    # recorded states are colour-swapped: learner's stones are 2, the opponent's 1 (rl_self_play.py:134-138)
+    opp, own = boards.to_bitboards(states)
+    t = lambda a: torch.from_numpy(a.view(np.int64).copy()).cuda()
+    return t(own), t(opp)
+
+
+def per_tensor_errors(flat_gpu, ref_grads):
+    from oracle import reinforce_ref
+    out, o = {}, 0
+    for k in reinforce_ref.KEYS:
+        n = ref_grads[k].size
+        a, b = flat_gpu[o:o + n], ref_grads[k].reshape(-1)
+        out[k] = (np.abs(a - b).max(), np.abs(b).max())
+        o += n
+    return out
+
+
+def test_gradient_matches_autograd(engine):
+    import torch
+    from iago_b200 import npz
+    from iago_b200.train_rl import ReinforceTrainer, N_PARAMS
+    from oracle import nets, reinforce_ref
+    path = model_file("RL/model2.npz")
+    states, actions, rewards = golden_batch()
+    tr = ReinforceTrainer(path, max_positions=256)      # 242 positions -> one chunk
+    own, opp = to_device(states)
+    a = torch.from_numpy(actions.astype(np.int8)).cuda()
+    r = torch.from_numpy(rewards).cuda()
+    probs = tr.gradient(own, opp, a, r, want_probs=True)
+    torch.cuda.synchronize()
+    g = tr.grad.cpu().numpy().astype(np.float64)
+    total, ref, pred = reinforce_ref.loss_and_grad(nets.load_params(path, np.float64), states, actions, rewards)
+    assert g[N_PARAMS + 1] == len(states)
+    assert abs(g[N_PARAMS] - total) <= 1e-5 * abs(total) + 1e-6
+    assert np.abs(probs.cpu().numpy() - pred).max() <= 5e-5    # fp32 forward, logits up to ~130
+    errs = per_tensor_errors(g[:N_PARAMS], ref)
+    print("worst relative gradient error per tensor:", max(e / s_ for e, s_ in errs.values() if s_ > 0))
+    for k, (e, scale) in errs.items():
+        assert e <= 1e-3 * scale + 1e-6, (k, e, scale)
+    # chunked accumulation (max_positions smaller than the batch) gives the same gradient
+    tr2 = ReinforceTrainer(path, max_positions=100, slot=5)
+    tr2.gradient(own, opp, a, r)
+    torch.cuda.synchronize()
+    g2 = tr2.grad.cpu().numpy().astype(np.float64)
+    assert g2[N_PARAMS + 1] == len(states)
+    errs = per_tensor_errors(g2[:N_PARAMS], ref)
+    for k, (e, scale) in errs.items():
+        assert e <= 1e-3 * scale + 1e-6, (k, e, scale)
+    # bit-reproducible run to run
+    tr.gradient(own, opp, a, r)
+    torch.cuda.synchronize()
+    assert (tr.grad.cpu().numpy().astype(np.float64) == g).all()
+
+
+def test_adam_steps_match_chainer_rule(engine):
+    import torch
+    from iago_b200 import npz
+    from iago_b200.train_rl import ReinforceTrainer, N_PARAMS
+    from oracle import nets, reinforce_ref
+    path = model_file("RL/model2.npz")
+    states, actions, rewards = golden_batch()
+    tr = ReinforceTrainer(path, alpha=1e-3, max_positions=256)
+    own, opp = to_device(states)
+    a = torch.from_numpy(actions.astype(np.int8)).cuda()
+    r = torch.from_numpy(rewards).cuda()
+    p64 = nets.load_params(path, np.float64)
+    w = reinforce_ref.flat(p64)
+    m, v, t = np.zeros_like(w), np.zeros_like(w), 0
+    for step in range(2):
+        tr.gradient(own, opp, a, r)
+        torch.cuda.synchronize()
+        g = tr.grad.cpu().numpy().astype(np.float64)      # the Adam rule is checked on the GPU's own gradient: at t = 1 the step is
+        loss, count = tr.update()                         # alpha * sign(g), so gradient noise on near-zero entries would otherwise
+        assert count == len(states)                       # dominate (gradient parity is the previous test)
+        assert abs(loss - g[N_PARAMS] / count) <= 1e-6 * abs(loss) + 1e-9
+        w, m, v, t = reinforce_ref.adam_step(w, g[:N_PARAMS] / count, m, v, t)
+        got, gm, gv, gt = tr.state()
+        assert gt == t
+        assert np.abs(got - w).max() <= 1e-6, np.abs(got - w).max()
+        assert np.abs(gm - m).max() <= 1e-6 * max(1.0, np.abs(m).max()) and np.abs(gv - v).max() <= 1e-6 * max(1.0, np.abs(v).max())
+        w = got.astype(np.float64)                        # follow the fp32 replica, as a second rank would
+    # the playing slot follows the update: the policy output of the trainer's slot equals the fp32 forward of the new weights
+    from iago_b200 import boards
+    p1, p2 = boards.to_bitboards(boards.start_state())
+    out = engine.policy_forward_host(tr.slot, p1, p2, 1, probs=True)[0]
+    new = npz.unflatten(w.astype(np.float32), npz.KIND_POLICY)
+    ref_prob = nets.sl_policy({k: x.astype(np.float64) for k, x in new.items()}, nets.planes_from_state(boards.start_state()[None], 1, np.float64))[0]
+    assert np.abs(out - ref_prob).max() <= 1e-4
+
+
+def test_train_set_runs_and_checkpoints(engine, tmp_path):
+    from iago_b200 import network, npz
+    from iago_b200.train_rl import ReinforceTrainer
+    opp = network.SLPolicy().load(model_file("RL/model0.npz"))
+    tr = ReinforceTrainer(model_file("RL/model2.npz"), max_positions=4096)
+    before = tr.state()[0].copy()
+    stats = tr.train_set(opp, n_games=64, seed=1)
+    assert 0.0 <= stats["rate"] <= 1.0 and 64 * 20 <= stats["positions"] <= 64 * 34 and np.isfinite(stats["loss"])
+    after, m, v, t = tr.state()
+    assert t == 1 and np.abs(after - before).max() > 0 and np.abs(after - before).max() <= 1.1e-3   # |Adam step| <= alpha at t = 1
+    tr.save_model(tmp_path / "model.npz")
+    tr.save_optimizer(tmp_path / "opt.npz")
+    z = np.load(tmp_path / "model.npz")
+    assert sorted(z.files) == sorted(npz.TRUNK_KEYS + npz.HEAD_KEYS[npz.KIND_POLICY])
+    o = np.load(tmp_path / "opt.npz")
+    assert int(o["t"]) == 1 and o["block3/conv/W/m"].shape == (128, 128, 3, 3) and "bias10/b/v" in o.files
+    again = network.SLPolicy().load(tmp_path / "model.npz")   # loadable like any reference archive
+    assert again.params["conv9/W"].shape == (1, 128, 1, 1)

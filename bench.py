@@ -252,7 +252,7 @@ def run_ours(args, rank, world, local_rank):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step(i, timed=None):
-        gid0 = (i * world + rank) * n  # global game ids: results do not depend on the number of ranks
+        gid0 = (i * world + rank) * n  # = parallel.game_id0: global game ids, results do not depend on the number of ranks
         flush.fill_(i & 0xFF)
         if timed is not None:
             timed[0].record()
@@ -348,7 +348,7 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_block()
     extra = {}
-    for name, fn in (("selfplay", section_selfplay), ("mcts", section_mcts)):
+    for name, fn in (("selfplay", section_selfplay), ("mcts", section_mcts), ("reinforce", section_reinforce)):
         if name in args.sections:
             try:
                 extra[name] = fn(eng, args, rank, world, dev, dist, barrier)
@@ -477,6 +477,37 @@ def section_mcts(eng, args, rank, world, dev, dist, barrier):
     return res
 
 
+def section_reinforce(eng, args, rank, world, dev, dist, barrier):
+    """BASELINE configs[4]: train_rl.py-style REINFORCE self-play, rl_model.npz vs RL/model0.npz, games sharded over the ranks,
+    [gradient | loss | count] all-reduced over NCCL once per update."""
+    import torch
+    from iago_b200 import network, parallel
+    from iago_b200.train_rl import ReinforceTrainer
+    n = args.reinforce_games
+    opp = network.SLPolicy(device=eng.device).load(model_path("RL/model0.npz"))
+    tr = ReinforceTrainer(model_path("rl_model.npz"), alpha=1e-3, max_positions=8192, device=eng.device)
+    tr.train_set(opp, n_games=min(n, 256), seed=args.seed, game_id0=parallel.game_id0(0, rank, world, n))   # warm-up update
+    barrier()
+    steps = max(1, args.reinforce_steps)
+    stats = []
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(steps):
+        stats.append(tr.train_set(opp, n_games=n, seed=args.seed, game_id0=parallel.game_id0(1 + i, rank, world, n)))
+    b.record()
+    barrier()
+    tt = torch.tensor([a.elapsed_time(b) / 1e3], dtype=torch.float64, device=dev)
+    parallel.all_reduce_max_(tt)
+    t = float(tt[0])
+    positions = sum(s["positions"] for s in stats)    # already global: the count rides in the all-reduced vector
+    return {"metric": "reinforce_games_per_s", "value": steps * n * world / t, "unit": "games/s", "ms_per_update": 1e3 * t / steps,
+            "config": {"workload": "REINFORCE sets: self-play (sampled, odd games head/tail switched) + gradient + all-reduce + Adam/WD, "
+                                   "rl_model.npz learner vs RL/model0.npz (BASELINE configs[4])", "games_per_update_per_gpu": n,
+                       "updates": steps, "gradient_arithmetic": "fp32 CUDA cores (tensor-core backward: next round)"},
+            "positions_per_update": positions / steps, "last": stats[-1],
+            "allreduce_bytes_per_update": (960768 + 2) * 4}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -486,7 +517,9 @@ def main():
     ap.add_argument("--games", type=int, default=0, help="games per step per GPU (default 65,536; reference arm 16,384)")
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--sections", default="rollout,selfplay,mcts", help="extra sections to run after the headline rollout bench")
+    ap.add_argument("--reinforce-games", type=int, default=2048)
+    ap.add_argument("--reinforce-steps", type=int, default=1)
+    ap.add_argument("--sections", default="rollout,selfplay,mcts,reinforce", help="extra sections to run after the headline rollout bench")
     ap.add_argument("--selfplay-games", type=int, default=16384)
     ap.add_argument("--selfplay-steps", type=int, default=2)
     ap.add_argument("--mcts-trees", type=int, default=256)

@@ -1,0 +1,58 @@
+"""Host-side sharding of independent games / trees over ranks (one process per GPU) and the two collectives of the path.
+
+Games and search trees are independent units: rank r of R plays the global ids
+    game_id0(step, r, R, n) ... + n - 1   =   (step * R + r) * n ...
+and every random draw is keyed by the global id, so the union of all ranks' results for a step is exactly what one process
+would produce for the same ids — results never depend on R.  The only exchanges are sum all-reduces of (a) int64 result /
+win counters at report time and (b) the fp32 vector [gradient | loss numerator | position count] once per REINFORCE update.
+torch.distributed is the plumbing (NCCL on GPUs, gloo in the CPU tests).
+"""
+import torch
+import torch.distributed as dist
+
+
+def world(group=None):
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def game_id0(step, rank, world_size, n_per_rank):
+    """First global game id of `rank` in `step` when every rank plays n_per_rank games per step (weak scaling)."""
+    return (step * world_size + rank) * n_per_rank
+
+
+def shard_range(n_total, rank, world_size):
+    """[lo, hi) of a fixed total of n_total units split over the ranks (strong scaling), remainder to the low ranks."""
+    base, rem = divmod(n_total, world_size)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def all_reduce_sum_(t, group=None):
+    """In-place sum over ranks; a no-op without a process group."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def all_reduce_max_(t, group=None):
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return t
+
+
+def reduce_counters(counters, device=None, group=None):
+    """dict name -> int, summed over ranks (wins / draws / losses / plies / games / playouts)."""
+    keys = sorted(counters)
+    t = torch.tensor([int(counters[k]) for k in keys], dtype=torch.int64, device=device)
+    all_reduce_sum_(t, group)
+    return dict(zip(keys, t.tolist()))
+
+
+def mean_gradient_(flat, n_params, group=None):
+    """flat = [sum-gradient (n_params) | loss numerator | position count] of this rank. All-reduces it and returns
+    (mean loss, total count); flat[:n_params] / count is then the gradient of the reference's mean loss over ALL ranks' positions."""
+    all_reduce_sum_(flat, group)
+    num, count = flat[n_params:n_params + 2].tolist()
+    return (num / count if count > 0 else 0.0), count

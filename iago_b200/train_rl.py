@@ -16,7 +16,7 @@ import ctypes as C
 import numpy as np
 import torch
 
-from . import boards, npz
+from . import boards, npz, parallel
 from ._lib import check
 from .engine import Rng, STREAM_SELFPLAY, default_engine
 
@@ -68,24 +68,17 @@ class ReinforceTrainer:
                                                C.c_void_p(probs[sl].data_ptr()) if want_probs else None, self.eng._stream(None)))
         return probs
 
-    def all_reduce(self):
-        """Sum [gradient | loss numerator | count] over the ranks (the only collective of the training path)."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=self.group)
-
     def update(self):
-        """optimizer.update(): all-reduce, WeightDecay hook, Adam, refresh the playing slot. Returns (mean loss, positions)."""
-        self.all_reduce()
-        tail = self.grad[N_PARAMS:].tolist()
-        count = tail[1]
+        """optimizer.update(): all-reduce [gradient | loss numerator | count] over the ranks (the only collective of the training
+        path), WeightDecay hook, Adam, refresh the playing slot. Returns (mean loss, positions)."""
+        loss, count = parallel.mean_gradient_(self.grad, N_PARAMS, self.group)
         if count <= 0:
             return 0.0, 0
         hp = self.hp
         check(self.lib.iago_reinforce_adam_step(self.h, C.c_void_p(self.grad.data_ptr()), float(count), hp["alpha"], hp["beta1"],
                                                 hp["beta2"], hp["eps"], hp["weight_decay"], self.eng._stream(None)))
         self.sync_slot()
-        return tail[0] / count, int(count)
+        return loss, int(count)
 
     # ---- one set of games + one update
     def play_set(self, opponent, n_games, seed=0, game_id0=0, switch_rng=None):

@@ -299,6 +299,24 @@ def run_ours(args, rank, world, local_rank):
     t_e2e = time.perf_counter() - t0
     barrier()
 
+    # movegen / flip alone: the same kernel replaying the games' own move logs (no policy, no sampling) — the integer path
+    # whose issue utilisation the north star asks for separately
+    log = eng.rollout(p1, p2, col, rng=Rng.philox(seed=args.seed, game_id0=rank * n), want_moves=True)
+    forced = Rng.replay_moves(log["moves"])
+    mg_counters = torch.zeros(2, dtype=torch.int64, device=dev)
+    for i in range(3):
+        eng.rollout(p1, p2, col, rng=forced, out=out)
+    barrier()
+    mg_ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in mg_ev:
+        flush.fill_(1)
+        a.record()
+        eng.rollout(p1, p2, col, rng=forced, counters=mg_counters, out=out)
+        b.record()
+    barrier()
+    t_mg = sum(a.elapsed_time(b) for a, b in mg_ev) / 1e3
+    mg_plies = int(mg_counters[0].item())
+
     if dist is not None:
         tt = torch.tensor([t_dev, t_e2e, t_wall], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -340,6 +358,10 @@ def run_ours(args, rank, world, local_rank):
                          "traffic": None,
                          "note": "issue-bound path: 676 algorithmic int32 lane-ops/ply x plies per launch / mean launch "
                                  "time; peak = SHF+LOP3 micro-kernel measured in this run (iago_measure_int_peak)"},
+            "roofline_movegen": {"bound": "alu", "kernel": "rollout_kernel<FORCED> (legal_moves + flips + pass/terminal/score only, moves "
+                                 "replayed from a 64 B/game log)", "plies_per_s": mg_plies / t_mg,
+                                 "achieved": OPS_PER_PLY * mg_plies / t_mg / 1e12, "peak": int_peak / 1e12, "unit": "Tint32op/s",
+                                 "frac": OPS_PER_PLY * mg_plies / t_mg / int_peak, "traffic": None, "scope": "rank 0"},
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                              "frac": hbm_ach / hbm_peak, "traffic": None,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",

@@ -13,8 +13,8 @@
 // except the optional move log; algorithmic HBM traffic is 17 B in + 17-21 B out per game.
 //
 // Canonical rollout arithmetic (identical, bit for bit, in oracle/othello_ref.c):
-//   logit = (S0 + S1) + bias[k], S_c = taps ascending; e = exp32(logit - max_legal); q = floor(e * 2^50);
-//   pick the first legal k (ascending) with cum_q > floor(m53 * total / 2^53).
+//   logit = (S0 + S1) + bias[k], S_c = taps ascending; e = exp32(logit - max_legal); q = floor(e * 2^26) (uint32);
+//   pick the first legal k (ascending) with cum_q > floor((m53 >> 21) * total / 2^32).
 #include <string.h>
 
 #include "bitboard.cuh"
@@ -71,17 +71,14 @@ __device__ __forceinline__ float logit_at(const PolicySmem &w, u64 own, u64 opp,
     return __fadd_rn(__fadd_rn(s0, s1), w.bias[k]);
 }
 
-__device__ __forceinline__ u64 q_of(float e) { return __float2ull_rz(__fmul_rn(e, 1125899906842624.0f)); }
+__device__ __forceinline__ uint32_t q_of(float e) { return __float2uint_rz(__fmul_rn(e, 67108864.0f)); }  // floor(e * 2^26)
 
-__device__ __forceinline__ u64 threshold(u64 m53, u64 total) {
-    return (__umul64hi(m53, total) << 11) | ((m53 * total) >> 53);
-}
-
-// Samples one legal cell. scratch_a/scratch_b: this thread's column of the shared scratch (stride kBlock).
+// Samples one legal cell. sa / sc: this thread's columns of the shared scratch (stride kBlock).
 __device__ __forceinline__ int sample_move(const PolicySmem &w, u64 own, u64 opp, u64 legal, u64 m53,
-                                           uint32_t *sa, uint32_t *sb) {
+                                           uint32_t *sa, uint8_t *sc) {
     const int n = __popcll(legal);
     if (n == 1) return __ffsll((long long)legal) - 1;  // same answer as the general path, no arithmetic needed
+    const uint32_t u32 = (uint32_t)(m53 >> 21);
     if (n <= kMaxLegal) {
         float mx = -3.0e38f;
         u64 m = legal;
@@ -91,32 +88,28 @@ __device__ __forceinline__ int sample_move(const PolicySmem &w, u64 own, u64 opp
             const float l = logit_at(w, own, opp, k);
             mx = fmaxf(mx, l);
             sa[i * kBlock] = __float_as_uint(l);
-            sb[i * kBlock] = (uint32_t)k << 24;
+            sc[i * kBlock] = (uint8_t)k;
         }
-        u64 cum = 0;
+        uint32_t cum = 0;
         for (int i = 0; i < n; i++) {
             const float l = __uint_as_float(sa[i * kBlock]);
-            cum += q_of(exp32_neg(__fsub_rn(l, mx)));
-            sa[i * kBlock] = (uint32_t)cum;
-            sb[i * kBlock] |= (uint32_t)(cum >> 32);  // cum < 32 * 2^50 < 2^56
+            cum += q_of(exp32_neg(__fsub_rn(l, mx)));   // at most 63 terms of at most 2^26: no overflow
+            sa[i * kBlock] = cum;
         }
-        const u64 T = threshold(m53, cum);
+        const uint32_t T = __umulhi(u32, cum);
         int idx = 0;
-        for (int i = 0; i < n; i++) {
-            const u64 c = ((u64)(sb[i * kBlock] & 0xFFFFFFu) << 32) | sa[i * kBlock];
-            idx += (c <= T) ? 1 : 0;
-        }
+        for (int i = 0; i < n; i++) idx += (sa[i * kBlock] <= T) ? 1 : 0;
         idx = min(idx, n - 1);
-        return (int)(sb[idx * kBlock] >> 24);
+        return (int)sc[idx * kBlock];
     }
     // > kMaxLegal legal moves: unreachable in real play, possible on arbitrary boards. Recompute instead of storing.
     float mx = -3.0e38f;
     for (u64 m = legal; m; m &= m - 1) mx = fmaxf(mx, logit_at(w, own, opp, __ffsll((long long)m) - 1));
-    u64 total = 0;
+    uint32_t total = 0;
     for (u64 m = legal; m; m &= m - 1)
         total += q_of(exp32_neg(__fsub_rn(logit_at(w, own, opp, __ffsll((long long)m) - 1), mx)));
-    const u64 T = threshold(m53, total);
-    u64 cum = 0;
+    const uint32_t T = __umulhi(u32, total);
+    uint32_t cum = 0;
     int last = 0;
     for (u64 m = legal; m; m &= m - 1) {
         last = __ffsll((long long)m) - 1;
@@ -150,7 +143,7 @@ template <int MODE, bool LOG>
 __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const RolloutWeights *__restrict__ gw) {
     __shared__ PolicySmem w;
     __shared__ uint32_t scratch_a[kMaxLegal * kBlock];
-    __shared__ uint32_t scratch_b[kMaxLegal * kBlock];
+    __shared__ uint8_t scratch_b[kMaxLegal * kBlock];
     {
         const float *src = reinterpret_cast<const float *>(gw);
         float *dst = reinterpret_cast<float *>(&w);
@@ -167,7 +160,8 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const Ro
         u64 opp = (color == 1) ? a.p2[g] : a.p1[g];
         int stone_num = __popcll(own | opp);  // 64 - sum(state == 0), mcts_self_play.py:15
         bool pass_flg = false;
-        uint32_t *sa = scratch_a + threadIdx.x, *sb = scratch_b + threadIdx.x;
+        uint32_t *sa = scratch_a + threadIdx.x;
+        uint8_t *sb = scratch_b + threadIdx.x;
         while (stone_num < 64) {  // mcts_self_play.py:26 — the end test runs once per PAIR of turns
 #pragma unroll 1
             for (int half = 0; half < 2; half++) {
@@ -231,7 +225,7 @@ __global__ void __launch_bounds__(kBlock) rollout_sample_kernel(const u64 *__res
                                                                 const RolloutWeights *__restrict__ gw) {
     __shared__ PolicySmem w;
     __shared__ uint32_t scratch_a[kMaxLegal * kBlock];
-    __shared__ uint32_t scratch_b[kMaxLegal * kBlock];
+    __shared__ uint8_t scratch_b[kMaxLegal * kBlock];
     {
         const float *src = reinterpret_cast<const float *>(gw);
         float *dst = reinterpret_cast<float *>(&w);

@@ -27,9 +27,11 @@
  *   e[k]     = exp32(logit[k] - max over LEGAL k)   only at legal cells (the reference's softmax
  *              denominator and its fp32 division cancel in p/sum(p); dropping them changes
  *              p by <= a few ulp_f32, the same size as numpy-vs-libm exp differences)
- *   choice   = fixed-point inverse cdf: q_k = floor(e_k * 2^50), cum in uint64 (exact, associative),
- *              first legal k (ascending) with cum_k > floor(m53 * total / 2^53), m53 = floor(u * 2^53)
- *              == searchsorted(cumsum(p)/cumsum(p)[-1], u, 'right') of np.random.choice up to ~2^-50
+ *   choice   = fixed-point inverse cdf: q_k = floor(e_k * 2^26) (uint32; e_k <= 1 and at most 63 legal cells, so the
+ *              running sum fits 32 bits; exact, associative), first legal k (ascending) with
+ *              cum_k > floor(u32 * total / 2^32), u32 = floor(u * 2^32) = m53 >> 21, m53 = floor(u * 2^53)
+ *              == searchsorted(cumsum(p)/cumsum(p)[-1], u, 'right') of np.random.choice up to ~n * 2^-26 in cdf
+ *              units — the same size as the rounding error of the fp32 exp itself
  *   exp32    = Cephes-style range reduction + degree-5 polynomial, every step an explicit
  *              fmaf / single rounding, so gcc and nvcc produce identical bits.
  *   uniforms = Philox4x32-10, key = seed, counter = (game_lo, game_hi, draw, stream);
@@ -213,8 +215,8 @@ EXPORT void oracle_rollout_logits(const float *state, int color, const float *W 
 }
 
 /* mcts_self_play.py:100-110 with the uniform supplied by the caller as m53 = floor(u * 2^53).
- * Fixed-point inverse-cdf: q_k = floor(e_k * 2^50) (exact for e_k >= 2^-26), cum in uint64,
- * choice = first legal k (ascending) with cum_k > floor(m53 * total / 2^53)
+ * Fixed-point inverse-cdf: q_k = floor(e_k * 2^26), cum in uint32,
+ * choice = first legal k (ascending) with cum_k > floor((m53 >> 21) * total / 2^32)
  *        <=> cum_k / total > u, i.e. searchsorted(cdf, u, 'right') of np.random.choice. */
 static int sample_action(const float *state, int color, const int *actions, int n,
                          const float *W, const float *b, uint64_t m53) {
@@ -223,13 +225,13 @@ static int sample_action(const float *state, int color, const int *actions, int 
     for (int a = 0; a < n; a++) logits[actions[a]] = rollout_logit_at(state, color, W, b, actions[a] / 8, actions[a] % 8);
     float m = logits[actions[0]];
     for (int a = 1; a < n; a++) if (logits[actions[a]] > m) m = logits[actions[a]];
-    uint64_t cum[64], total = 0;
+    uint32_t cum[64], total = 0;
     for (int a = 0; a < n; a++) {
         float e = exp32_neg(logits[actions[a]] - m);
-        total += (uint64_t)(e * 1125899906842624.0f); /* 2^50: exact scaling, truncating convert */
+        total += (uint32_t)(e * 67108864.0f); /* 2^26: exact scaling, truncating convert */
         cum[a] = total;
     }
-    uint64_t T = (uint64_t)(((unsigned __int128)m53 * total) >> 53);
+    uint32_t T = (uint32_t)(((uint64_t)(uint32_t)(m53 >> 21) * total) >> 32);
     for (int a = 0; a < n; a++) if (cum[a] > T) return actions[a];
     return actions[n - 1];
 }

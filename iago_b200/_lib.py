@@ -3,7 +3,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(HERE, "libiago_b200.so")
+SO_PATH = os.environ.get("IAGO_B200_LIB") or os.path.join(HERE, "libiago_b200.so")   # override: A/B builds of the kernels
 
 
 class IagoError(RuntimeError):

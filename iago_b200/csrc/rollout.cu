@@ -81,20 +81,27 @@ __device__ __forceinline__ int sample_move(const PolicySmem &w, u64 own, u64 opp
     const uint32_t u32 = (uint32_t)(m53 >> 21);
     if (n <= kMaxLegal) {
         float mx = -3.0e38f;
-        u64 m = legal;
-        for (int i = 0; i < n; i++) {
-            const int k = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            const float l = logit_at(w, own, opp, k);
-            mx = fmaxf(mx, l);
-            sa[i * kBlock] = __float_as_uint(l);
-            sc[i * kBlock] = (uint8_t)k;
+        {
+            u64 m = legal;
+            for (int i = 0; i < n; i++) {
+                const int k = __ffsll((long long)m) - 1;
+                m &= m - 1;
+                const float l = logit_at(w, own, opp, k);
+                mx = fmaxf(mx, l);
+                sa[i * kBlock] = __float_as_uint(l);
+                sc[i * kBlock] = (uint8_t)k;
+            }
         }
         uint32_t cum = 0;
-        for (int i = 0; i < n; i++) {
-            const float l = __uint_as_float(sa[i * kBlock]);
-            cum += q_of(exp32_neg(__fsub_rn(l, mx)));   // at most 63 terms of at most 2^26: no overflow
+        for (int i = 0; i < n; i += 2) {   // two independent exp chains per trip; the odd tail contributes exp(-inf) = 0
+            const bool two = i + 1 < n;
+            const float l0 = __uint_as_float(sa[i * kBlock]);
+            const float l1 = two ? __uint_as_float(sa[(i + 1) * kBlock]) : -3.0e38f;
+            const uint32_t q0 = q_of(exp32_neg(__fsub_rn(l0, mx))), q1 = q_of(exp32_neg(__fsub_rn(l1, mx)));
+            cum += q0;                                  // at most 63 terms of at most 2^26: no overflow
             sa[i * kBlock] = cum;
+            cum += q1;
+            if (two) sa[(i + 1) * kBlock] = cum;
         }
         const uint32_t T = __umulhi(u32, cum);
         int idx = 0;

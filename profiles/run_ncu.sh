@@ -4,7 +4,7 @@
 #   rollout.ncu-rep : full-set capture of the rollout kernel
 set -x
 mkdir -p gpurun_out
-CMD="python bench.py --steps 3 --warmup 3 --no-cpu"
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu --sections rollout"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv $CMD > gpurun_out/ncu_bench_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:rollout_kernel -s 3 -c 2 -f -o gpurun_out/rollout $CMD > gpurun_out/ncu_bench_full.log 2>&1
 ls -la gpurun_out

@@ -34,6 +34,7 @@ sys.path.insert(0, ROOT)
 GAMES_PER_STEP = 65536
 OPS_PER_PLY = 676          # int32 ALU lane-ops per ply: movegen 314 + flip 352 + ~10
 BYTES_PER_GAME = 17 + 21   # p1,p2,colour in; final p1,p2,n_moves,result out
+NCU_DRAM_BYTES_PER_LAUNCH = 1145856   # profiles/r01_ncu_rollout_v2_summary.csv (dram__bytes_read.sum; write 0), 65,536-game launch
 METRIC = "rollout_plies_per_s"
 
 
@@ -355,9 +356,11 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clk.summary(),
             "roofline": {"bound": "alu", "kernel": "rollout_kernel<PHILOX>", "achieved": achieved / 1e12,
                          "peak": int_peak / 1e12, "unit": "Tint32op/s", "frac": achieved / int_peak,
-                         "traffic": None,
+                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == GAMES_PER_STEP else None,
                          "note": "issue-bound path: 676 algorithmic int32 lane-ops/ply x plies per launch / mean launch "
-                                 "time; peak = SHF+LOP3 micro-kernel measured in this run (iago_measure_int_peak)"},
+                                 "time; peak = SHF+LOP3 micro-kernel measured in this run (iago_measure_int_peak); traffic = "
+                                 "dram__bytes_read+write per launch from the ncu --set full capture in profiles/r01_ncu_rollout_v2_summary.csv "
+                                 "(algorithmic bytes per launch: 38 B x 65,536 games = 2.49 MB; outputs stay in L2 during the capture)"},
             "roofline_movegen": {"bound": "alu", "kernel": "rollout_kernel<FORCED> (legal_moves + flips + pass/terminal/score only, moves "
                                  "replayed from a 64 B/game log)", "plies_per_s": mg_plies / t_mg,
                                  "achieved": OPS_PER_PLY * mg_plies / t_mg / 1e12, "peak": int_peak / 1e12, "unit": "Tint32op/s",

@@ -45,6 +45,7 @@ SIGNATURES = {
                       _P, C.c_int, _P, _P, _P],
     "iago_env_step": [_P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(IagoRng), _P, _P, _P, _P, _P],
     "iago_sample_unmasked": [_P, _P, _P, _P, C.c_int64, C.POINTER(IagoRng), _P, _P, _P, _P],
+    "iago_sample_masked": [_P, _P, _P, _P, C.c_int64, C.POINTER(IagoRng), _P, _P, _P],
     "iago_mcts_create": [_P, C.c_int, C.c_int, C.c_int, C.c_uint64, C.POINTER(_P)],
     "iago_mcts_destroy": [_P],
     "iago_mcts_set_roots": [_P, _P, _P, _P, C.c_int, _P],

@@ -268,6 +268,30 @@ __global__ void __launch_bounds__(128) sample_unmasked_kernel(EnvArgs a) {
     a.opp_action[g] = (int8_t)chosen;
 }
 
+// get_action_auto / get_action (game.py:101-108, rl_self_play.py:111-127) for given probabilities: p = prob (float32) * validity
+// mask (float64), renormalised, np.random.choice with ONE uniform.  action -1 = no legal move.
+__global__ void __launch_bounds__(128) sample_masked_kernel(EnvArgs a) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= a.n) return;
+    const u64 legal = legal_moves(a.p1[g], a.p2[g]);
+    int chosen = -1;
+    if (legal) {
+        const float *pr = a.probs + g * 64;
+        double total = 0.0;
+        for (u64 m = legal; m; m &= m - 1) total = __dadd_rn(total, (double)pr[__ffsll((long long)m) - 1]);
+        const int d = a.draws[g];
+        const double t = __dmul_rn(env_uniform(a, g, d), total);
+        a.draws[g] = d + 1;
+        double cum = 0.0;
+        for (u64 m = legal; m; m &= m - 1) {
+            chosen = __ffsll((long long)m) - 1;
+            cum = __dadd_rn(cum, (double)pr[chosen]);
+            if (cum > t) break;
+        }
+    }
+    a.opp_action[g] = (int8_t)chosen;
+}
+
 struct SelfplayWs {
     long long cap = 0;
     int32_t *stone_num = nullptr, *placed = nullptr, *active = nullptr;
@@ -430,6 +454,21 @@ int iago_sample_unmasked(iago_ctx *ctx, const float *probs, const uint64_t *own,
         IAGO_CUDA(cudaStreamSynchronize(s));
         *errors_host = *w->h_active;
     }
+    return IAGO_OK;
+}
+
+int iago_sample_masked(iago_ctx *ctx, const float *probs, const uint64_t *own, const uint64_t *opp, int64_t n,
+                       const iago_rng *rng, int32_t *draws, int8_t *action, void *stream) {
+    IAGO_REQUIRE(ctx && probs && own && opp && rng && draws && action, "NULL argument");
+    IAGO_REQUIRE(n >= 0, "n < 0");
+    IAGO_REQUIRE(rng->mode == IAGO_RNG_PHILOX || rng->mode == IAGO_RNG_UNIFORMS, "rng.mode must be PHILOX or UNIFORMS");
+    if (rng->mode == IAGO_RNG_UNIFORMS) IAGO_REQUIRE(rng->uniforms && rng->u_stride > 0, "rng.uniforms / u_stride");
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    EnvArgs a{(u64 *)own, (u64 *)opp, nullptr, nullptr, nullptr, draws, nullptr, action, probs, n, rng->mode,
+              rng->stream_id, rng->seed, rng->game_id0, rng->uniforms, rng->u_stride, nullptr};
+    sample_masked_kernel<<<(unsigned)((n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(a);
+    IAGO_CUDA(cudaGetLastError());
     return IAGO_OK;
 }
 

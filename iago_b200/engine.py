@@ -268,6 +268,17 @@ class Engine:
             raise RecursionError("maximum recursion depth exceeded")
         return out
 
+    def sample_masked(self, probs, own, opp, draws, rng: Optional[Rng] = None, stream=None):
+        """get_action_auto's sampler (game.py:101-108) on device tensors: one uniform per board, int8 actions (-1 = no legal move)."""
+        torch = _torch()
+        rng = rng or Rng(stream_id=STREAM_ENV)
+        n = self._check_i64(own, opp)
+        out = torch.empty(n, dtype=torch.int8, device=self._dev())
+        r, keep = self._rng_struct(rng, n, host=False)
+        check(self.lib.iago_sample_masked(self.ctx, _ptr(probs), _ptr(own), _ptr(opp), n, C.byref(r), _ptr(draws), _ptr(out),
+                                          self._stream(stream)))
+        return out
+
     # ------------------------------------------------------------------ host API (numpy arrays)
     def rollout_host(self, p1, p2, color, rng: Optional[Rng] = None, want_moves=False, out=None):
         """Same as rollout() with HOST buffers: H2D + kernel + D2H inside the C call (synchronous)."""

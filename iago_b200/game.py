@@ -55,3 +55,149 @@ class GameFunctions:
         q1, q2 = cls.place_stone_batch(p1, p2, action, color)
         state[...] = boards.from_bitboards(q1, q2, dtype=state.dtype)[0]
         return state
+
+
+class Game:
+    """Drop-in for game.Game (game.py:13-151): human (or SLPolicy when auto) as colour 1 against PV-MCTS as colour 2.
+
+    Same attributes and turn semantics as the reference: `turn(color, auto)` (game.py:115-142) with update_with_move on
+    both sides' moves and on passes (-1), the `stone_num > 62` shortcut of get_action_auto (game.py:97-98), gamelog format
+    and save_gamelog.  Keyword extras are forwarded to iago_b200.MCTS.MCTS (n_playouts, leaf_batch, ...)."""
+
+    def __init__(self, auto, seed=0, verbose=True, **mcts_kw):
+        import torch
+        from datetime import datetime
+        from . import network
+        from .MCTS import MCTS
+        from .paths import model_path
+        if auto:
+            self.p1 = "IaGo(SLPolicy)"
+            self.model = network.SLPolicy().load(model_path("sl_model.npz"))
+        else:
+            self.p1 = "You"
+            self.model = None
+        self.p2 = "IaGo(PV-MCTS)"
+        self.state = boards.start_state()
+        self.stone_num, self.play_num, self.pass_flg = 4, 1, False
+        self.date = datetime.now().strftime("%Y-%m-%d-%H-%M")
+        self.gamelog = "IaGo \n" + self.date + "\n"
+        self.mcts = MCTS(**mcts_kw)
+        self.verbose, self.seed = verbose, seed
+        self._draws = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", GameFunctions.device))
+
+    def show(self):
+        print("   1   2   3   4   5   6   7   8   ")
+        for i in range(8):
+            print(" " + "-" * 33)
+            print(str(i + 1) + "|" + "|".join({0: "   ", 1: " X ", 2: " O "}[int(v)] for v in self.state[i]) + "|")
+        print(" " + "-" * 33)
+        print(self.p1 + "(X):" + str(int(np.sum(self.state == 1))) + ", " + self.p2 + "(O):" + str(int(np.sum(self.state == 2)))
+              + ", Empty:" + str(int(np.sum(self.state == 0))))
+        print("\n")
+
+    def judge(self):
+        p1, p2 = int(np.sum(self.state == 1)), int(np.sum(self.state == 2))
+        if self.verbose:
+            print((self.p1 + " WIN!") if p1 > p2 else ((self.p2 + " WIN") if p1 < p2 else "DRAW"))
+        return self.p1 + ":" + str(p1) + ", " + self.p2 + ":" + str(p2) + ", Empty:" + str(int(np.sum(self.state == 0)))
+
+    def safeinput(self):
+        import re
+        while True:
+            line = input()
+            if re.fullmatch(r"\d[,]\d", line):
+                return line.split(",")
+            print("Try again.")
+
+    def get_action(self, color, actions):
+        if color == 1:
+            while True:
+                print("Your turn. Choose a position!")
+                position = [int(e) for e in self.safeinput()]
+                action = (position[0] - 1) * 8 + (position[1] - 1)
+                if action in actions:
+                    break
+                print("This position is invalid. Choose another position")
+            self.mcts.update_with_move(action)
+        else:
+            if self.verbose:
+                print("Thinking... Wait a second.")
+            action = self.mcts.get_move(self.state, 2)
+            self.mcts.update_with_move(action)
+        return action
+
+    def get_action_auto(self, color, actions):
+        import torch
+        from .engine import Rng, STREAM_ENV
+        if self.stone_num > 62 and len(actions) == 1:
+            return actions[0]                      # game.py:97-98 (the trees are not advanced on this path either)
+        if color == 1:
+            eng = default_engine(GameFunctions.device)
+            p1, p2 = boards.to_bitboards(self.state)
+            dev = self._draws.device
+            t1 = torch.from_numpy(p1.view(np.int64).copy()).to(dev)
+            t2 = torch.from_numpy(p2.view(np.int64).copy()).to(dev)
+            col = torch.ones(1, dtype=torch.uint8, device=dev)
+            probs = eng.policy_forward(self.model.slot, t1, t2, col, probs=True, precision=self.model.precision)
+            action = int(eng.sample_masked(probs, t1, t2, self._draws, Rng.philox(seed=self.seed, stream_id=STREAM_ENV))[0])
+            self.mcts.update_with_move(action)
+        else:
+            action = self.mcts.get_move(self.state, 2)
+            self.mcts.update_with_move(action)
+        return action
+
+    def turn(self, color, auto):
+        players = [self.p1, self.p2]
+        actions = GameFunctions.legal_actions(self.state, color)
+        if self.verbose:
+            print("Valid choice:", GameFunctions.ac2pos(actions))
+        if len(actions) > 0:
+            action = self.get_action_auto(color, actions) if auto else self.get_action(color, actions)
+            position = [action // 8 + 1, action % 8 + 1]
+            if self.verbose:
+                print(position)
+            self.state = GameFunctions.place_stone(self.state, action, color)
+            self.stone_num += 1
+            if self.verbose:
+                self.show()
+            self.pass_flg = False
+            self.gamelog += "[" + str(self.play_num) + "]" + players[color - 1] + ": " + str(position) + "\n"
+        else:
+            if self.pass_flg:
+                self.stone_num = 64
+            if self.verbose:
+                print(players[color - 1] + " pass.")
+            self.pass_flg = True
+            self.mcts.update_with_move(-1)
+            self.gamelog += "[" + str(self.play_num) + "]" + players[color - 1] + ": Pass\n"
+        self.play_num += 1
+
+    def save_gamelog(self):
+        import os
+        filename = "./gamelog/" + self.date + ".txt"
+        os.makedirs(os.path.dirname(filename), exist_ok=True)
+        with open(filename, "w") as f:
+            f.write(self.gamelog)
+
+
+def main():
+    import argparse
+    parser = argparse.ArgumentParser(description="IaGo:")
+    parser.add_argument("--auto", "-a", type=bool, default=False, help="Set True for auto play between MCTS and SLPolicy")
+    parser.add_argument("--playouts", type=int, default=None, help="fixed playouts per move instead of the 10 s budget")
+    args = parser.parse_args()
+    print("\n" + "*" * 34 + "\n" + "*" * 11 + "Game Start!!" + "*" * 11 + "\n" + "*" * 34 + "\n")
+    game = Game(args.auto, n_playouts=args.playouts, leaf_batch=64 if args.playouts else 1)
+    game.show()
+    while game.stone_num < 64:
+        game.turn(1, args.auto)
+        game.turn(2, args.auto)
+    print("\n" + "*" * 34 + "\n" + "*" * 12 + "Game End!!" + "*" * 12 + "\n" + "*" * 34)
+    jd = game.judge()
+    print(jd)
+    game.gamelog += jd + "\n"
+    game.save_gamelog()
+
+
+if __name__ == "__main__":
+    main()

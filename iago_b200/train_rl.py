@@ -134,3 +134,91 @@ class ReinforceTrainer:
         for k in M:
             d[f"{k}/t"], d[f"{k}/m"], d[f"{k}/v"] = np.array(t, np.int32), M[k], V[k]
         np.savez_compressed(path, **d)
+
+
+class PoolSchedule:
+    """The bookkeeping of src/train_rl.py:29-81: `models` counts the snapshots in the opponent pool, `cnt` the sets won
+    (rate > 0.5) since the last snapshot; a snapshot is taken when cnt > 4*sqrt(models) and rate > 0.6 (:73-79); training
+    stops when rate < 0.2 (:80-81) or models > 20 (:32)."""
+
+    def __init__(self, models=1, max_models=20):
+        self.models, self.cnt, self.max_models = int(models), 0, int(max_models)
+
+    def running(self):
+        return self.models <= self.max_models
+
+    def step(self, rate):
+        """Returns (snapshot_index or None, stop)."""
+        snap = None
+        if rate > 0.5:
+            self.cnt += 1
+        if self.cnt > 4 * np.sqrt(self.models) and rate > 0.6:
+            snap = self.models
+            self.models += 1
+            self.cnt = 0
+        return snap, rate < 0.2
+
+
+def train(model_dir, start="model2.npz", models=1, n_games=64, alpha=1e-3, max_sets=None, seed=0, log=None, device=0,
+          group=None, on_set=None):
+    """The outer loop of src/train_rl.py:22-81 on the GPU trainer: random opponent from model_dir/*.npz per set
+    (np.random.choice over the glob, :35-37), one update per set, win-rate log line, pool snapshots
+    model<k>.npz + optimizers/<k>.npz in the reference's archive layouts, early stop. Returns the list of per-set stats."""
+    import glob
+    import os
+    from . import network, parallel
+    rank, world = parallel.world(group)
+    trainer = ReinforceTrainer(os.path.join(model_dir, start), alpha=alpha, device=device, group=group)
+    opt = os.path.join(model_dir, "optimizers", os.path.splitext(start)[0].replace("model", "") + ".npz")
+    if os.path.isfile(opt):   # src/train_rl.py:27 resumes the optimizer when its archive exists
+        with np.load(opt) as z:
+            keys = npz.TRUNK_KEYS + npz.HEAD_KEYS[npz.KIND_POLICY]
+            m = np.concatenate([np.asarray(z[k + "/m"], np.float32).reshape(-1) for k in keys])
+            v = np.concatenate([np.asarray(z[k + "/v"], np.float32).reshape(-1) for k in keys])
+            trainer.load_state(None, m, v, int(z["t"]))
+    sched = PoolSchedule(models)
+    rng = np.random.RandomState(seed)     # the same draw on every rank: all ranks face the same opponent
+    opponent = network.SLPolicy(device=device)
+    history, s = [], 0
+    while sched.running() and (max_sets is None or s < max_sets):
+        pool = sorted(glob.glob(os.path.join(model_dir, "*.npz")))
+        path = pool[rng.randint(len(pool))]
+        opponent.load(path)
+        st = trainer.play_set(opponent, n_games, seed=seed, game_id0=parallel.game_id0(s, rank, world, n_games))
+        trainer.gradient(st["own"], st["opp"], st["action"], st["reward"])
+        loss, count = trainer.update()
+        wins = parallel.reduce_counters(dict(wins=st["wins"], games=st["games"]), device=trainer.grad.device, group=group)
+        rate = wins["wins"] / wins["games"]
+        snap, stop = sched.step(rate)
+        rec = dict(set=s, opponent=os.path.basename(path), rate=rate, loss=loss, positions=count, models=sched.models, snapshot=snap)
+        history.append(rec)
+        if rank == 0:
+            if log:
+                with open(log, "a") as f:
+                    f.write(str(rate) + ", \n")          # src/train_rl.py:69-70
+            if snap is not None:
+                os.makedirs(os.path.join(model_dir, "optimizers"), exist_ok=True)
+                trainer.save_model(os.path.join(model_dir, f"model{snap}.npz"))
+                trainer.save_optimizer(os.path.join(model_dir, "optimizers", f"{snap}.npz"))
+        if on_set:
+            on_set(rec)
+        s += 1
+        if stop:
+            break
+    return history
+
+
+def main():
+    import argparse
+    ap = argparse.ArgumentParser(description="IaGo: REINFORCE self-play on B200 (src/train_rl.py)")
+    ap.add_argument("--models", "-m", type=int, default=1, help="Number of trained models")
+    ap.add_argument("--set", "-s", type=int, default=1000, help="Number of game sets played to train")
+    ap.add_argument("--dir", default="../models/RL")
+    ap.add_argument("--games", type=int, default=64, help="games per set (2N, N = 32 in the reference)")
+    args = ap.parse_args()
+    train(args.dir, models=args.models, n_games=args.games, max_sets=args.set, log="../log/rl.txt",
+          on_set=lambda r: print("Models:" + str(r["models"]) + ", Result:" + str(r["rate"]) + ", Loss:" + str(r["loss"])))
+
+
+if __name__ == "__main__":
+    main()

@@ -178,6 +178,12 @@ IAGO_API int iago_env_step(iago_ctx *ctx, int slot_opponent, int precision, int6
 IAGO_API int iago_sample_unmasked(iago_ctx *ctx, const float *probs, const uint64_t *own, const uint64_t *opp, int64_t n,
                                   const iago_rng *rng, int32_t *draws, int8_t *action, int32_t *errors_host, void *stream);
 
+/* The masked sampler of get_action_auto / rl_self_play.get_action (game.py:101-108, rl_self_play.py:111-127) for given
+ * probabilities: p = prob * validity mask, renormalised, np.random.choice with ONE uniform.  Arguments as for
+ * iago_sample_unmasked; action -1 = no legal move. */
+IAGO_API int iago_sample_masked(iago_ctx *ctx, const float *probs, const uint64_t *own, const uint64_t *opp, int64_t n,
+                                const iago_rng *rng, int32_t *draws, int8_t *action, void *stream);
+
 /* ---- PV-MCTS: MCTS.py:10-154 on a GPU-resident node pool, n_trees independent searches in lockstep ----
  * One iago_mcts holds n_trees trees (one per game) of at most max_nodes nodes each.  A search runs waves of up to
  * leaf_batch playouts per tree: leaf-parallel selection with virtual visits / virtual loss, ONE batched SLPolicy launch

@@ -62,6 +62,7 @@ SIGNATURES = {
     "iago_reinforce_get_state": [_P, _P, _P, _P, C.POINTER(C.c_int64)],
     "iago_reinforce_set_state": [_P, _P, _P, _P, C.c_int64],
     "iago_reinforce_sync_slot": [_P, C.c_int],
+    "iago_reinforce_set_option": [_P, C.c_int],
     "iago_measure_int_peak": [_P, C.c_int, C.POINTER(C.c_double)],
     "iago_last_kernel_ms": [_P, C.POINTER(C.c_float)],
 }

@@ -22,7 +22,10 @@
 #include <vector>
 
 #include "bitboard.cuh"
+#include <cuda_bf16.h>
+
 #include "common.cuh"
+#include "tc.cuh"
 
 namespace iago {
 
@@ -206,6 +209,177 @@ __global__ void __launch_bounds__(256) wgrad3x3_kernel(const float *__restrict__
     }
 }
 
+// ---------------------------------------------------------------- weight gradient on the tensor cores (layers with Cout = 128)
+// dW[o][c][tap] = sum_{p, cell} dY[p][o][cell] * X[p][c][cell + tap] as 9 GEMMs D_tap[o][c] += A[o][k] * B_tap[c][k], k = (p, cell).
+// One CTA owns one kernel row ky (3 taps, 3 x N fp32 TMEM columns) and one slice of positions; per position (one pipeline
+// stage, K = 64) the producer warps read dY and X (fp32, [p][ch][64]) once, round to bf16 and lay them out as no-swizzle
+// K-major core matrices: A = [o group][board row][o % 8][8 cells]; B = three column-shifted copies (kx = 0, 1, 2 <-> dx = -1, 0, +1,
+// zero filled) of [c group][padded row 0..9][c % 8][8 cells], so that a tap is just a descriptor start address: copy kx, padded
+// row y + ky.  One thread issues 4 K=16 MMAs per tap and stage; accumulators stay in TMEM until the slice is done.
+// Output: partial[slice][tap][o][c] (coalesced); reduce_taps_kernel sums the slices in order and writes [o][c][tap].
+constexpr int kWgThreads = 288;               // warps 0-7 producers (0-3 also epilogue), warp 8 = MMA issuer
+constexpr int kWgATile = 16 * 8 * 128;        // dY tile: 16 o-groups x 8 rows x 128 B = 16,384
+constexpr int kWgXCopy = 16 * 10 * 128;       // one shifted copy of the X tile: 20,480
+constexpr int kWgStage = kWgATile + 3 * kWgXCopy;   // 77,824
+constexpr int kWgStages = 2;
+constexpr int kWgSmem = kWgStages * kWgStage + 64;
+
+__device__ __forceinline__ uint4 pack_bf16x8(const float4 a, const float4 b) {
+    const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    const __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    return make_uint4(*reinterpret_cast<const uint32_t *>(&p0), *reinterpret_cast<const uint32_t *>(&p1),
+                      *reinterpret_cast<const uint32_t *>(&p2), *reinterpret_cast<const uint32_t *>(&p3));
+}
+
+__global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dy,
+                                                                  float *__restrict__ partial, long long m, int cin,
+                                                                  int pos_per_slice, size_t partial_stride) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int ky = blockIdx.y;                       // kernel row of this CTA: taps ky*3 + {0,1,2}
+    const int N = cin;                               // 64 or 128 input channels = N of the MMA
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar_full = sbase + kWgStages * kWgStage, bar_empty = bar_full + 8 * kWgStages, bar_acc = bar_empty + 8 * kWgStages;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + kWgStages * kWgStage + 8 * (2 * kWgStages + 1));
+    const long long p_begin = (long long)blockIdx.x * pos_per_slice;
+    const long long p_end = min(m, p_begin + pos_per_slice);
+    const int n_pos = (int)max(0LL, p_end - p_begin);
+
+    for (int i = tid; i < kWgStages * kWgStage / 16; i += kWgThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);  // halo rows stay zero
+    if (tid == 0) {
+        for (int s = 0; s < kWgStages; s++) {
+            mbar_init(bar_full + 8 * s, 256);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        mbar_init(bar_acc, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 8) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp < 8) {
+        // ================= producers: fp32 global -> bf16 core matrices in shared memory =================
+        uint32_t stage = 0, phase = 0;
+        for (int ip = 0; ip < n_pos; ip++) {
+            const long long p = p_begin + ip;
+            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+            uint8_t *st = smem + stage * kWgStage;
+            // dY: 128 o x 8 rows of 8 cells
+            const float *dsrc = dy + (size_t)p * 128 * 64;
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+                const int chunk = tid + it * 256;           // (o, row): consecutive threads read consecutive 32 B
+                const int o = chunk >> 3, row = chunk & 7;
+                const float4 a = *reinterpret_cast<const float4 *>(dsrc + chunk * 8), b = *reinterpret_cast<const float4 *>(dsrc + chunk * 8 + 4);
+                *reinterpret_cast<uint4 *>(st + (((o >> 3) * 8 + row) * 8 + (o & 7)) * 16) = pack_bf16x8(a, b);
+            }
+            // X: cin channels x 8 rows, three column-shifted copies
+            const float *xsrc = x + (size_t)p * cin * 64;
+            for (int chunk = tid; chunk < cin * 8; chunk += 256) {
+                const int c = chunk >> 3, row = chunk & 7;
+                const float4 a = *reinterpret_cast<const float4 *>(xsrc + chunk * 8), b = *reinterpret_cast<const float4 *>(xsrc + chunk * 8 + 4);
+                const uint4 v = pack_bf16x8(a, b);
+                const uint32_t off = kWgATile + (((c >> 3) * 10 + row + 1) * 8 + (c & 7)) * 16;
+                // kx = 0: out[x] = in[x - 1]; kx = 1: in[x]; kx = 2: out[x] = in[x + 1]   (zero beyond the board edge)
+                const uint4 left = make_uint4(v.x << 16, __funnelshift_l(v.x, v.y, 16), __funnelshift_l(v.y, v.z, 16), __funnelshift_l(v.z, v.w, 16));
+                const uint4 right = make_uint4(__funnelshift_r(v.x, v.y, 16), __funnelshift_r(v.y, v.z, 16), __funnelshift_r(v.z, v.w, 16), v.w >> 16);
+                *reinterpret_cast<uint4 *>(st + off) = left;
+                *reinterpret_cast<uint4 *>(st + off + kWgXCopy) = v;
+                *reinterpret_cast<uint4 *>(st + off + 2 * kWgXCopy) = right;
+            }
+            fence_async_smem();
+            mbar_arrive(bar_full + 8 * stage);
+            if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+    } else if ((tid & 31) == 0) {
+        // ================= MMA issuer =================
+        const uint32_t idesc = instr_desc_bf16(128, N);
+        const uint64_t hi_a = ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46);   // SBO = 1,024 B between o groups
+        const uint64_t hi_b = ((uint64_t)(1280 >> 4) << 32) | (1ULL << 46);   // SBO = 1,280 B between c groups (10 padded rows)
+        const uint32_t lbo_word = (uint32_t)(128 >> 4) << 16;                 // LBO = 128 B between K-adjacent core matrices (board rows)
+        uint32_t stage = 0, phase = 0;
+        for (int ip = 0; ip < n_pos; ip++) {
+            mbar_wait(bar_full + 8 * stage, phase);
+            tc_fence_after();
+            const uint32_t st = sbase + stage * kWgStage;
+#pragma unroll
+            for (int kx = 0; kx < 3; kx++) {
+#pragma unroll
+                for (int ks = 0; ks < 4; ks++) {   // board rows (2 ks, 2 ks + 1) of dY against padded rows (2 ks + ky, 2 ks + ky + 1) of X
+                    const uint32_t aw = ((st + ks * 256) >> 4) | lbo_word;
+                    const uint32_t bw = ((st + kWgATile + kx * kWgXCopy + (2 * ks + ky) * 128) >> 4) | lbo_word;
+                    umma_f16(tmem + kx * 128, hi_a | aw, hi_b | bw, idesc, (ip > 0 || ks > 0) ? 1u : 0u);
+                }
+            }
+            umma_commit(bar_empty + 8 * stage);
+            if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_acc);
+    }
+
+    // ================= epilogue: TMEM -> partial[slice][tap][o][c] =================
+    if (warp < 4) {
+        float *dst = partial + (size_t)blockIdx.x * partial_stride;
+        const int o = tid;   // TMEM lane = output channel
+        if (n_pos > 0) {
+            mbar_wait(bar_acc, 0);
+            tc_fence_after();
+        }
+        for (int kx = 0; kx < 3; kx++) {
+            const int tap = ky * 3 + kx;
+            for (int c0 = 0; c0 < N; c0 += 32) {
+                uint32_t v[32];
+                if (n_pos > 0) {
+                    tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16) + kx * 128 + c0, v);
+                    tmem_wait_ld();
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; j++) v[j] = 0;
+                }
+                float *row = dst + ((size_t)tap * 128 + o) * N + c0;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4 *>(row + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+}
+
+// grad[(o*cin + c)*9 + tap] (+)= sum over slices (in order) of partial[s][tap][o][c]
+__global__ void reduce_taps_kernel(const float *__restrict__ partial, float *__restrict__ out, int cin, int slices, size_t stride, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;   // index into [tap][o][c]
+    if (i >= 9 * 128 * cin) return;
+    const int c = i % cin, o = (i / cin) % 128, tap = i / (cin * 128);
+    float s = 0.0f;
+    for (int k = 0; k < slices; k++) s += partial[(size_t)k * stride + i];
+    float *dst = out + ((size_t)o * cin + c) * 9 + tap;
+    *dst = accumulate ? *dst + s : s;
+}
+
+// db[o] (+)= sum_{p, cell} dY[p][o][cell]; one block per output channel, fixed-order tree.
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict__ dy, float *__restrict__ out, long long m, int cout, int accumulate) {
+    __shared__ float red[256];
+    const int o = blockIdx.x, tid = threadIdx.x;
+    float s = 0.0f;
+    for (long long i = tid; i < m * 64; i += 256) s += dy[((i >> 6) * cout + o) * 64 + (i & 63)];
+    red[tid] = s;
+    __syncthreads();
+    for (int k = 128; k > 0; k >>= 1) {
+        if (tid < k) red[tid] += red[tid + k];
+        __syncthreads();
+    }
+    if (tid == 0) out[o] = accumulate ? out[o] + red[0] : red[0];
+}
+
 // out[i] (+)= sum over slices of partial[s][i], slices in order.
 __global__ void reduce_slices_kernel(const float *__restrict__ partial, float *__restrict__ out, int count, int slices,
                                      size_t stride, int accumulate) {
@@ -328,6 +502,8 @@ struct iago_trainer {
     float *dlogit = nullptr, *loss_terms = nullptr, *partial = nullptr;
     size_t partial_stride = 0;
     int slices = 0;
+    int tc_slices = 0;
+    bool use_tc = true, tc_attr = false;
     size_t w_off[8], b_off[8], w9_off, b10_off;
     std::vector<void *> allocs;
 };
@@ -378,8 +554,9 @@ int iago_reinforce_create(iago_ctx *ctx, const float *params, int64_t n_floats, 
     A(t->dbuf[0], M * 128 * 64); A(t->dbuf[1], M * 128 * 64);
     A(t->dlogit, M * 64); A(t->loss_terms, M);
     t->slices = 24;
+    t->tc_slices = (ctx->sm_count + 2) / 3;          // 3 kernel rows x slices ~ one CTA per SM
     t->partial_stride = (size_t)128 * 128 * 9 + 128;
-    A(t->partial, (size_t)t->slices * t->partial_stride);
+    A(t->partial, (size_t)(t->tc_slices > t->slices ? t->tc_slices : t->slices) * t->partial_stride);
 #undef A
     if (rc) {
         for (void *p : t->allocs) cudaFree(p);
@@ -430,10 +607,22 @@ int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *op
     const int slices = (int)((m + pos_per_slice - 1) / pos_per_slice);
     for (int l = 7; l >= 0; l--) {
         const float *dy = t->dbuf[cur];
-        wgrad3x3_kernel<<<dim3((kCin[l] + 15) / 16, slices), 256, 0, s>>>(t->act[l], dy, t->partial, m, kCin[l], kCout[l], pos_per_slice,
-                                                                          t->partial_stride);
-        const int count = kCout[l] * kCin[l] * 9 + kCout[l];  // W then b are adjacent in the flat layout as well
-        reduce_slices_kernel<<<(count + 255) / 256, 256, 0, s>>>(t->partial, grad + t->w_off[l], count, slices, t->partial_stride, accumulate);
+        if (t->use_tc && kCout[l] == 128) {
+            if (!t->tc_attr) {
+                IAGO_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
+                t->tc_attr = true;
+            }
+            const int pps = (int)((m + t->tc_slices - 1) / t->tc_slices);
+            const int sl = (int)((m + pps - 1) / pps);
+            wgrad_tc_kernel<<<dim3(sl, 3), kWgThreads, kWgSmem, s>>>(t->act[l], dy, t->partial, m, kCin[l], pps, t->partial_stride);
+            reduce_taps_kernel<<<(9 * 128 * kCin[l] + 255) / 256, 256, 0, s>>>(t->partial, grad + t->w_off[l], kCin[l], sl, t->partial_stride, accumulate);
+            bias_grad_kernel<<<kCout[l], 256, 0, s>>>(dy, grad + t->b_off[l], m, kCout[l], accumulate);
+        } else {
+            wgrad3x3_kernel<<<dim3((kCin[l] + 15) / 16, slices), 256, 0, s>>>(t->act[l], dy, t->partial, m, kCin[l], kCout[l], pos_per_slice,
+                                                                              t->partial_stride);
+            const int count = kCout[l] * kCin[l] * 9 + kCout[l];  // W then b are adjacent in the flat layout as well
+            reduce_slices_kernel<<<(count + 255) / 256, 256, 0, s>>>(t->partial, grad + t->w_off[l], count, slices, t->partial_stride, accumulate);
+        }
         if (l > 0) {
             float *dx = t->dbuf[cur ^ 1];
             if (kCin[l] == 64)
@@ -484,6 +673,12 @@ int iago_reinforce_set_state(iago_trainer *t, const float *params, const float *
     if (adam_m) IAGO_CUDA(cudaMemcpy(t->adam_m, adam_m, (size_t)kNP * 4, cudaMemcpyHostToDevice));
     if (adam_v) IAGO_CUDA(cudaMemcpy(t->adam_v, adam_v, (size_t)kNP * 4, cudaMemcpyHostToDevice));
     if (step >= 0) t->t = step;
+    return IAGO_OK;
+}
+
+int iago_reinforce_set_option(iago_trainer *t, int use_tensor_cores) {
+    IAGO_REQUIRE(t, "NULL argument");
+    t->use_tc = use_tensor_cores != 0;
     return IAGO_OK;
 }
 

@@ -26,7 +26,7 @@ SWITCH_CELLS = [2 * 8 + 4, 3 * 8 + 5, 4 * 8 + 2, 5 * 8 + 3]   # src/train_rl.py:
 
 class ReinforceTrainer:
     def __init__(self, params, alpha=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=5e-4, max_positions=8192,
-                 device=0, slot=6, precision=3, group=None):
+                 device=0, slot=6, precision=3, group=None, tensor_cores=True):
         self.eng = default_engine(device)
         self.lib = self.eng.lib
         self.device, self.slot, self.precision, self.group = device, slot, precision, group
@@ -37,6 +37,7 @@ class ReinforceTrainer:
         h = C.c_void_p()
         check(self.lib.iago_reinforce_create(self.eng.ctx, flat.ctypes.data, flat.size, int(max_positions), C.byref(h)))
         self.h, self.max_positions = h, int(max_positions)
+        check(self.lib.iago_reinforce_set_option(self.h, 1 if tensor_cores else 0))
         self.grad = torch.zeros(N_PARAMS + 2, dtype=torch.float32, device=torch.device("cuda", device))
         self.sync_slot()
 

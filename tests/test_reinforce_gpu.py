@@ -49,7 +49,7 @@ def test_gradient_matches_autograd(engine):
     from oracle import nets, reinforce_ref
     path = model_file("RL/model2.npz")
     states, actions, rewards = golden_batch()
-    tr = ReinforceTrainer(path, max_positions=256)      # 242 positions -> one chunk
+    tr = ReinforceTrainer(path, max_positions=256, tensor_cores=False)      # 242 positions -> one chunk; fp32 kernels
     own, opp = to_device(states)
     a = torch.from_numpy(actions.astype(np.int8)).cuda()
     r = torch.from_numpy(rewards).cuda()
@@ -65,7 +65,7 @@ def test_gradient_matches_autograd(engine):
     for k, (e, scale) in errs.items():
         assert e <= 1e-3 * scale + 1e-6, (k, e, scale)
     # chunked accumulation (max_positions smaller than the batch) gives the same gradient
-    tr2 = ReinforceTrainer(path, max_positions=100, slot=5)
+    tr2 = ReinforceTrainer(path, max_positions=100, slot=5, tensor_cores=False)
     tr2.gradient(own, opp, a, r)
     torch.cuda.synchronize()
     g2 = tr2.grad.cpu().numpy().astype(np.float64)
@@ -77,6 +77,38 @@ def test_gradient_matches_autograd(engine):
     tr.gradient(own, opp, a, r)
     torch.cuda.synchronize()
     assert (tr.grad.cpu().numpy().astype(np.float64) == g).all()
+
+
+def test_tensor_core_wgrad_vs_cuda_core_path(engine):
+    """The bf16 tcgen05 weight-gradient kernel against the fp32 CUDA-core kernels on the same activations (same forward, same
+    dgrad): per tensor max |g_tc - g_fp32| <= 1e-2 * max |g_fp32| (bf16 operands, fp32 accumulation), biases identical."""
+    import torch
+    from iago_b200.train_rl import ReinforceTrainer, N_PARAMS
+    from oracle import reinforce_ref
+    path = model_file("RL/model2.npz")
+    states, actions, rewards = golden_batch()
+    own, opp = to_device(states)
+    a = torch.from_numpy(actions.astype(np.int8)).cuda()
+    r = torch.from_numpy(rewards).cuda()
+    g = {}
+    for tc in (False, True):
+        tr = ReinforceTrainer(path, max_positions=256, tensor_cores=tc, slot=4)
+        tr.gradient(own, opp, a, r)
+        torch.cuda.synchronize()
+        g[tc] = tr.grad.cpu().numpy().astype(np.float64)
+        tr.close()
+    o, worst = 0, 0.0
+    shapes = {k: v.shape for k, v in __import__("iago_b200").npz.unflatten(np.zeros(N_PARAMS, np.float32), 0).items()}
+    for k in reinforce_ref.KEYS:
+        n = int(np.prod(shapes[k]))
+        ref, got = g[False][o:o + n], g[True][o:o + n]
+        scale = np.abs(ref).max()
+        err = np.abs(got - ref).max()
+        worst = max(worst, err / scale if scale > 0 else 0.0)
+        assert err <= 1e-2 * scale + 1e-7, (k, err, scale)
+        o += n
+    print("tensor-core wgrad: worst per-tensor error relative to max|g|:", worst)
+    assert g[True][N_PARAMS] == g[False][N_PARAMS] and g[True][N_PARAMS + 1] == g[False][N_PARAMS + 1]
 
 
 def test_adam_steps_match_chainer_rule(engine):

@@ -12,6 +12,46 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
+def multi_stream(args):
+    """args.streams engines, each with trees/streams trees on its own CUDA stream, driven from host threads: the select kernel of
+    one group overlaps the trunk / rollout launches of the others."""
+    import threading, time
+    import torch
+    import iago_b200
+    from iago_b200.search import SearchPool
+    mdir = os.path.join(ROOT, "baseline", "_ref", "models")
+    T = args.trees // args.streams
+    p1, p2 = (1 << 19) | (1 << 27) | (1 << 28) | (1 << 35), 1 << 36
+    kw = dict(slot_policy=0, slot_value=1, lmbda=0.5, c_puct=1, n_thr=15, leaf_batch=args.leaf_batch, virtual_loss=1.0,
+              precision=args.precision, cache_value=not args.no_cache, seed=1)
+    groups = []
+    for i in range(args.streams):
+        eng = iago_b200.Engine(0)
+        eng.load_net(0, os.path.join(mdir, "sl_model.npz"))
+        eng.load_net(1, os.path.join(mdir, "value_model.npz"))
+        eng.load_rollout_npz(os.path.join(mdir, "rollout_model.npz"))
+        groups.append((eng, SearchPool(T, max_nodes=args.max_nodes, max_leaf_batch=args.leaf_batch, tree_id0=i * T, engine=eng),
+                       torch.cuda.Stream()))
+
+    def work(eng, pool, stream, n):
+        with torch.cuda.stream(stream):
+            pool.set_roots(p1, p2, 2, reset_tree=True)
+            pool.search(n, **kw)
+
+    for n in (2 * args.leaf_batch, args.playouts):     # warm-up, then the timed move
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        th = [threading.Thread(target=work, args=(e, p, s, n)) for e, p, s in groups]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+    best = [int(p.root_stats()[2][0]) for _, p, _ in groups]
+    print(json.dumps({"metric": "mcts_playouts_per_s", "value": T * args.streams * args.playouts / dt, "trees": T * args.streams,
+                      "streams": args.streams, "playouts_per_move": args.playouts, "leaf_batch": args.leaf_batch,
+                      "ms_per_move": dt * 1e3, "cache_value": not args.no_cache, "best": best, "timing": "host wall clock around the threads"}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--trees", type=int, default=64)
@@ -22,11 +62,14 @@ def main():
     ap.add_argument("--precision", type=int, default=3)
     ap.add_argument("--no-cache", action="store_true")
     ap.add_argument("--max-nodes", type=int, default=65536)
+    ap.add_argument("--streams", type=int, default=1, help="independent engines (contexts + streams) searching concurrently from host threads")
     args = ap.parse_args()
     import torch
     import iago_b200
     from iago_b200 import boards
     from iago_b200.search import SearchPool
+    if args.streams > 1:
+        return multi_stream(args)
     eng = iago_b200.Engine(0)
     mdir = os.path.join(ROOT, "baseline", "_ref", "models")
     eng.load_net(0, os.path.join(mdir, "sl_model.npz"))

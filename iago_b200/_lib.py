@@ -40,6 +40,7 @@ SIGNATURES = {
     "iago_rollout_logits": [_P, _P, _P, _P, _P, C.c_int64, _P],
     "iago_load_net": [_P, C.c_int, C.c_int, _P, C.c_int64],
     "iago_policy_forward": [_P, C.c_int, _P, _P, _P, C.c_int64, _P, C.c_int, C.c_int, _P],
+    "iago_policy_forward_acts": [_P, C.c_int, _P, _P, _P, C.c_int64, _P, _P, C.c_int, _P],
     "iago_value_forward": [_P, C.c_int, _P, _P, _P, C.c_int64, _P, C.c_int, _P],
     "iago_selfplay": [_P, C.c_int, C.c_int, C.c_int64, _P, _P, C.c_int, C.c_int, C.POINTER(IagoRng), _P, _P, _P, _P, _P, _P,
                       _P, C.c_int, _P, _P, _P],

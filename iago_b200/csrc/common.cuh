@@ -72,7 +72,8 @@ int ensure_staging(iago_ctx *ctx, size_t bytes);
 // trunk.cu: SLPolicy (want_kind 0) / Value (1) forward on device bitboards; out_kind 0 = logits, 1 = probabilities.
 // n_dev (nullable, device): the live count is min(n, *n_dev) — for request lists whose length only the device knows.
 int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
-                 int64_t n, float *out, int out_kind, int precision, void *stream, const int *n_dev = nullptr);
+                 int64_t n, float *out, int out_kind, int precision, void *stream, const int *n_dev = nullptr,
+                 float *const *dump = nullptr);  // dump[l] (nullable): fp32 [n][channels][64] output of block l+1
 // rollout.cu: Simulate for n device-resident games whose Philox game ids are given one by one (mcts.cu leaf batches).
 int rollout_launch_ids(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
                        uint64_t seed, uint32_t stream_id, const uint64_t *game_ids, int8_t *result, uint64_t *final_p1,

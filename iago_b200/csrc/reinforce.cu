@@ -504,6 +504,9 @@ struct iago_trainer {
     int slices = 0;
     int tc_slices = 0;
     bool use_tc = true, tc_attr = false;
+    int synced_slot = -1;             // trunk slot that holds the CURRENT parameters (-1: stale)
+    uint8_t *ones = nullptr;          // colour array (all 1) for the trunk launch
+    float *logits_scratch = nullptr;
     size_t w_off[8], b_off[8], w9_off, b10_off;
     std::vector<void *> allocs;
 };
@@ -552,7 +555,7 @@ int iago_reinforce_create(iago_ctx *ctx, const float *params, int64_t n_floats, 
     A(t->act[0], M * 2 * 64);
     for (int l = 0; l < 8; l++) A(t->act[l + 1], M * kCout[l] * 64);
     A(t->dbuf[0], M * 128 * 64); A(t->dbuf[1], M * 128 * 64);
-    A(t->dlogit, M * 64); A(t->loss_terms, M);
+    A(t->dlogit, M * 64); A(t->loss_terms, M); A(t->ones, M); A(t->logits_scratch, M * 64);
     t->slices = 24;
     t->tc_slices = (ctx->sm_count + 2) / 3;          // 3 kernel rows x slices ~ one CTA per SM
     t->partial_stride = (size_t)128 * 128 * 9 + 128;
@@ -564,6 +567,7 @@ int iago_reinforce_create(iago_ctx *ctx, const float *params, int64_t n_floats, 
         return rc;
     }
     IAGO_CUDA(cudaMemcpy(t->params, params, (size_t)kNP * 4, cudaMemcpyHostToDevice));
+    IAGO_CUDA(cudaMemset(t->ones, 1, M));
     *out = t;
     return IAGO_OK;
 }
@@ -585,15 +589,21 @@ int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *op
     DeviceGuard guard(t->ctx->device);
     cudaStream_t s = (cudaStream_t)stream;
     relayout_all(t, s);
-    planes_kernel<<<(unsigned)((m * 64 + 255) / 256), 256, 0, s>>>((const u64 *)own, (const u64 *)opp, t->act[0], m);
     const unsigned tiles = (unsigned)((m + 1) / 2);
     // ---- forward, activations kept
-    for (int l = 0; l < 8; l++) {
-        const float *b = t->params + t->b_off[l];
-        if (kCout[l] == 64)
-            conv3x3_kernel<64, EPI_FWD><<<dim3(tiles, 1), 256, 0, s>>>(t->act[l], t->wf[l], b, nullptr, t->act[l + 1], m, kCin[l], kCout[l]);
-        else
-            conv3x3_kernel<128, EPI_FWD><<<dim3(tiles, 1), 256, 0, s>>>(t->act[l], t->wf[l], b, nullptr, t->act[l + 1], m, kCin[l], kCout[l]);
+    planes_kernel<<<(unsigned)((m * 64 + 255) / 256), 256, 0, s>>>((const u64 *)own, (const u64 *)opp, t->act[0], m);
+    if (t->use_tc && t->synced_slot >= 0) {
+        // the fused tcgen05 trunk (trunk.cu) on the slot that holds these parameters, dumping every block's output in fp32
+        int rc = trunk_launch(t->ctx, t->synced_slot, 0, own, opp, t->ones, m, t->logits_scratch, 0, 3, stream, nullptr, t->act + 1);
+        if (rc) return rc;
+    } else {
+        for (int l = 0; l < 8; l++) {
+            const float *b = t->params + t->b_off[l];
+            if (kCout[l] == 64)
+                conv3x3_kernel<64, EPI_FWD><<<dim3(tiles, 1), 256, 0, s>>>(t->act[l], t->wf[l], b, nullptr, t->act[l + 1], m, kCin[l], kCout[l]);
+            else
+                conv3x3_kernel<128, EPI_FWD><<<dim3(tiles, 1), 256, 0, s>>>(t->act[l], t->wf[l], b, nullptr, t->act[l + 1], m, kCin[l], kCout[l]);
+        }
     }
     IAGO_CUDA(cudaGetLastError());
     // ---- head forward + backward
@@ -646,6 +656,7 @@ int iago_reinforce_adam_step(iago_trainer *t, const float *grad, double count, d
     DeviceGuard guard(t->ctx->device);
     cudaStream_t s = (cudaStream_t)stream;
     t->t += 1;
+    t->synced_slot = -1;   // the slot no longer holds these parameters until iago_reinforce_sync_slot
     const double fix1 = 1.0 - pow(beta1, (double)t->t), fix2 = 1.0 - pow(beta2, (double)t->t);
     const float lr_t = (float)(alpha * sqrt(fix2) / fix1);   // Chainer AdamRule.lr
     adam_kernel<<<(kNP + 255) / 256, 256, 0, s>>>(t->params, t->adam_m, t->adam_v, grad, kNP, (float)(1.0 / count), (float)weight_decay,
@@ -669,7 +680,10 @@ int iago_reinforce_set_state(iago_trainer *t, const float *params, const float *
     IAGO_REQUIRE(t, "NULL argument");
     DeviceGuard guard(t->ctx->device);
     IAGO_CUDA(cudaDeviceSynchronize());
-    if (params) IAGO_CUDA(cudaMemcpy(t->params, params, (size_t)kNP * 4, cudaMemcpyHostToDevice));
+    if (params) {
+        IAGO_CUDA(cudaMemcpy(t->params, params, (size_t)kNP * 4, cudaMemcpyHostToDevice));
+        t->synced_slot = -1;
+    }
     if (adam_m) IAGO_CUDA(cudaMemcpy(t->adam_m, adam_m, (size_t)kNP * 4, cudaMemcpyHostToDevice));
     if (adam_v) IAGO_CUDA(cudaMemcpy(t->adam_v, adam_v, (size_t)kNP * 4, cudaMemcpyHostToDevice));
     if (step >= 0) t->t = step;
@@ -687,7 +701,9 @@ int iago_reinforce_sync_slot(iago_trainer *t, int slot) {
     std::vector<float> h(kNP);
     int rc = iago_reinforce_get_state(t, h.data(), nullptr, nullptr, nullptr);
     if (rc) return rc;
-    return iago_load_net(t->ctx, slot, 0, h.data(), kNP);
+    rc = iago_load_net(t->ctx, slot, 0, h.data(), kNP);
+    if (rc == IAGO_OK) t->synced_slot = slot;
+    return rc;
 }
 
 }  // extern "C"

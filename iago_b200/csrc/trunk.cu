@@ -86,6 +86,7 @@ struct TrunkArgs {
     const float *bias;    // [n_layers][128]
     const float *head;    // policy: w9[128], b10[64]; value: b9 at [0], wfc[64] at [128..192)
     const int *n_dev;     // nullable: the live position count is min(n, *n_dev) (request lists built on the device, mcts.cu)
+    float *dump[8];       // nullable each: post-ReLU output of block l+1 as fp32 [n][channels][64] (kept for the backward pass, reinforce.cu)
 };
 
 // bias + ReLU + hi/lo fp16 split of 32 accumulator columns, written as 4 channel groups of this thread's tile row.
@@ -320,6 +321,11 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
 #pragma unroll
                             for (int j = 0; j < 32; j++) dot = fmaf(x[j], shead[col0 + j], dot);
                         }
+                        if (a.dump[l] != nullptr && valid) {
+                            float *dst = a.dump[l] + ((size_t)pos * ld.n + col0) * 64 + cell;
+#pragma unroll
+                            for (int j = 0; j < 32; j++) dst[(size_t)j * 64] = x[j];
+                        }
                         if (writes_act) {
                             store_act32(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
                             fence_async_smem();
@@ -528,7 +534,7 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
 
 namespace iago {
 int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
-                 int64_t n, float *out, int out_kind, int precision, void *stream, const int *n_dev) {
+                 int64_t n, float *out, int out_kind, int precision, void *stream, const int *n_dev, float *const *dump) {
     IAGO_REQUIRE(ctx && p1 && p2 && color && out, "NULL argument");
     IAGO_REQUIRE(slot >= 0 && slot < 8, "slot out of range (0..7)");
     IAGO_REQUIRE(n >= 0, "n < 0");
@@ -547,7 +553,8 @@ int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, con
     }
     const long long tiles = (n + 1) / 2;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    TrunkArgs a{(const u64 *)p1, (const u64 *)p2, color, n, out, out_kind, precision, s.d_blob, s.d_bias, s.d_head, n_dev};
+    TrunkArgs a{(const u64 *)p1, (const u64 *)p2, color, n, out, out_kind, precision, s.d_blob, s.d_bias, s.d_head, n_dev, {}};
+    for (int l = 0; l < 8; l++) a.dump[l] = dump ? dump[l] : nullptr;
     cudaStream_t cs = (cudaStream_t)stream;
     IAGO_CUDA(cudaEventRecord(ctx->ev0, cs));
     trunk_kernel<<<grid, kThreads, kSmemBytes, cs>>>(a, s.d_desc);
@@ -569,6 +576,12 @@ int iago_policy_forward(iago_ctx *ctx, int slot, const uint64_t *p1, const uint6
 int iago_value_forward(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
                        float *out, int precision, void *stream) {
     return trunk_launch(ctx, slot, 1, p1, p2, color, n, out, 0, precision, stream);
+}
+
+int iago_policy_forward_acts(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
+                             float *logits, float *const *acts, int precision, void *stream) {
+    IAGO_REQUIRE(acts != nullptr, "acts is NULL");
+    return trunk_launch(ctx, slot, 0, p1, p2, color, n, logits, 0, precision, stream, nullptr, acts);
 }
 
 }  // extern "C"

@@ -138,6 +138,12 @@ IAGO_API int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *param
 IAGO_API int iago_policy_forward(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
                                  int64_t n, float *out, int out_kind, int precision, void *stream);
 
+/* SLPolicy forward that also keeps every block's output: acts[l] (DEVICE, nullable each) receives the post-ReLU output of
+ * block l+1 (network.py:36-43) as fp32 [n][channels][64] (channels = 64 for l = 0, else 128); logits [n][64].  This is the
+ * forward pass of the REINFORCE update (the backward needs the activations) and a test hook for layer-by-layer parity. */
+IAGO_API int iago_policy_forward_acts(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
+                                      int64_t n, float *logits, float *const *acts, int precision, void *stream);
+
 /* Value.__call__ (inference: dropout off, MCTS.py:86) -> out [n]. */
 IAGO_API int iago_value_forward(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
                                 int64_t n, float *out, int precision, void *stream);

@@ -22,20 +22,27 @@ def to_torch(params, dtype=torch.float64):
     return {k: torch.tensor(np.asarray(params[k]), dtype=dtype, requires_grad=True) for k in KEYS}
 
 
-def forward(p, x):
+def forward(p, x, masks=None, keep=None):
+    """masks (optional): 8 boolean arrays (M,C,8,8); when given, block i multiplies by masks[i-1] instead of applying ReLU — the
+    derivative of ReLU at a pre-activation within rounding noise of 0 is ambiguous, and a checker for a lower-precision forward
+    must take that forward's own on/off decisions as given (DESIGN.md "K6")."""
     h = x
     for i in range(1, 9):
-        h = F.relu(F.conv2d(h, p[f"block{i}/conv/W"], p[f"block{i}/conv/b"], padding=1))
+        h = F.conv2d(h, p[f"block{i}/conv/W"], p[f"block{i}/conv/b"], padding=1)
+        if keep is not None:
+            keep.append(h.detach().numpy())
+        h = F.relu(h) if masks is None else h * torch.tensor(np.asarray(masks[i - 1]), dtype=h.dtype)
     h = F.conv2d(h, p["conv9/W"]).reshape(-1, 64) + p["bias10/b"]
     return F.softmax(h, dim=1)
 
 
-def loss_and_grad(params, states, actions, rewards, dtype=torch.float64):
-    """states (M,8,8) in {0,1,2} as recorded by rl_self_play.Game (swapped). Returns (sum c*r, grads dict of d(sum c*r), pred)."""
+def loss_and_grad(params, states, actions, rewards, dtype=torch.float64, masks=None, keep=None):
+    """states (M,8,8) in {0,1,2} as recorded by rl_self_play.Game (swapped). Returns (sum c*r, grads dict of d(sum c*r), pred).
+    keep (optional list) receives the 8 pre-activation arrays."""
     p = to_torch(params, dtype)
     s = torch.tensor(np.asarray(states).reshape(-1, 8, 8))
     x = torch.stack([s == 1, s == 2], dim=1).to(dtype)
-    pred = forward(p, x)
+    pred = forward(p, x, masks, keep)
     c = F.cross_entropy(pred, torch.tensor(np.asarray(actions), dtype=torch.long), reduction="none")
     total = (c * torch.tensor(np.asarray(rewards), dtype=dtype)).sum()
     total.backward()

@@ -79,36 +79,45 @@ def test_gradient_matches_autograd(engine):
     assert (tr.grad.cpu().numpy().astype(np.float64) == g).all()
 
 
-def test_tensor_core_wgrad_vs_cuda_core_path(engine):
-    """The bf16 tcgen05 weight-gradient kernel against the fp32 CUDA-core kernels on the same activations (same forward, same
-    dgrad): per tensor max |g_tc - g_fp32| <= 1e-2 * max |g_fp32| (bf16 operands, fp32 accumulation), biases identical."""
+def test_tensor_core_path(engine):
+    """tensor_cores=True: forward on the fused tcgen05 trunk (fp16 hi/lo split), weight gradients as bf16 tcgen05 GEMMs.
+    (1) The forward's activations equal the float64 forward within 2e-4; its ReLU on/off decisions differ from the float64
+        ones ONLY on units whose pre-activation is within 2e-4 of zero (the kink, where the derivative is ambiguous).
+    (2) With those on/off decisions taken as given, the gradient equals float64 autograd within 1e-2 * max|g| per tensor
+        (bf16 operands, fp32 accumulation); loss numerator within 1e-4 relative."""
     import torch
+    from iago_b200 import npz
     from iago_b200.train_rl import ReinforceTrainer, N_PARAMS
-    from oracle import reinforce_ref
+    from oracle import nets, reinforce_ref
     path = model_file("RL/model2.npz")
     states, actions, rewards = golden_batch()
     own, opp = to_device(states)
     a = torch.from_numpy(actions.astype(np.int8)).cuda()
     r = torch.from_numpy(rewards).cuda()
-    g = {}
-    for tc in (False, True):
-        tr = ReinforceTrainer(path, max_positions=256, tensor_cores=tc, slot=4)
-        tr.gradient(own, opp, a, r)
-        torch.cuda.synchronize()
-        g[tc] = tr.grad.cpu().numpy().astype(np.float64)
-        tr.close()
-    o, worst = 0, 0.0
-    shapes = {k: v.shape for k, v in __import__("iago_b200").npz.unflatten(np.zeros(N_PARAMS, np.float32), 0).items()}
-    for k in reinforce_ref.KEYS:
-        n = int(np.prod(shapes[k]))
-        ref, got = g[False][o:o + n], g[True][o:o + n]
-        scale = np.abs(ref).max()
-        err = np.abs(got - ref).max()
-        worst = max(worst, err / scale if scale > 0 else 0.0)
-        assert err <= 1e-2 * scale + 1e-7, (k, err, scale)
-        o += n
-    print("tensor-core wgrad: worst per-tensor error relative to max|g|:", worst)
-    assert g[True][N_PARAMS] == g[False][N_PARAMS] and g[True][N_PARAMS + 1] == g[False][N_PARAMS + 1]
+    tr = ReinforceTrainer(path, max_positions=256, tensor_cores=True, slot=4)
+    tr.gradient(own, opp, a, r)
+    torch.cuda.synchronize()
+    g = tr.grad.cpu().numpy().astype(np.float64)
+    col = torch.ones(own.numel(), dtype=torch.uint8, device="cuda")
+    _, acts = engine.policy_forward_acts(tr.slot, own, opp, col)
+    acts = [x.cpu().numpy() for x in acts]
+    p64 = nets.load_params(path, np.float64)
+    pre = []
+    reinforce_ref.loss_and_grad(p64, states, actions, rewards, keep=pre)           # float64 pre-activations
+    flips = 0
+    for l in range(8):
+        assert np.abs(acts[l] - np.maximum(pre[l], 0)).max() <= 2e-4
+        diff = (acts[l] > 0) != (pre[l] > 0)
+        flips += int(diff.sum())
+        assert not diff.any() or np.abs(pre[l][diff]).max() <= 2e-4, l
+    total, ref, _ = reinforce_ref.loss_and_grad(p64, states, actions, rewards, masks=[x > 0 for x in acts])
+    assert abs(g[N_PARAMS] - total) <= 1e-4 * abs(total) + 1e-6
+    errs = per_tensor_errors(g[:N_PARAMS], ref)
+    worst = max(e / s_ for e, s_ in errs.values() if s_ > 0)
+    print(f"tensor-core path: {flips} ReLU decisions at the kink differ from float64; worst per-tensor gradient error {worst:.2e} of max|g|")
+    for k, (e, scale) in errs.items():
+        assert e <= 1e-2 * scale + 1e-6, (k, e, scale)
+    tr.close()
 
 
 def test_adam_steps_match_chainer_rule(engine):
@@ -118,7 +127,7 @@ def test_adam_steps_match_chainer_rule(engine):
     from oracle import nets, reinforce_ref
     path = model_file("RL/model2.npz")
     states, actions, rewards = golden_batch()
-    tr = ReinforceTrainer(path, alpha=1e-3, max_positions=256)
+    tr = ReinforceTrainer(path, alpha=1e-3, max_positions=256, tensor_cores=False)
     own, opp = to_device(states)
     a = torch.from_numpy(actions.astype(np.int8)).cuda()
     r = torch.from_numpy(rewards).cuda()

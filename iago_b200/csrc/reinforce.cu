@@ -266,37 +266,62 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
 
     if (warp < 8) {
         // ================= producers: fp32 global -> bf16 core matrices in shared memory =================
+        // Software-pipelined through registers: the 16 x 16-byte loads of position p+1 are in flight while position p is
+        // converted and stored, so HBM/L2 latency is covered without a third shared-memory stage.
         uint32_t stage = 0, phase = 0;
+        const int xchunks = cin >> 5;                 // (cin * 8 rows) / 256 threads = 4 (cin 128) or 2 (cin 64)
+        float4 cur[16], nxt[16];
+        auto load = [&](float4 (&r)[16], long long p) {
+            const float *dsrc = dy + (size_t)p * 128 * 64;
+            const float *xsrc = x + (size_t)p * cin * 64;
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+                const int chunk = tid + it * 256;       // (o, row): consecutive threads read consecutive 32 B
+                r[2 * it] = __ldg(reinterpret_cast<const float4 *>(dsrc + chunk * 8));
+                r[2 * it + 1] = __ldg(reinterpret_cast<const float4 *>(dsrc + chunk * 8 + 4));
+            }
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+                if (it < xchunks) {
+                    const int chunk = tid + it * 256;   // (c, row)
+                    r[8 + 2 * it] = __ldg(reinterpret_cast<const float4 *>(xsrc + chunk * 8));
+                    r[8 + 2 * it + 1] = __ldg(reinterpret_cast<const float4 *>(xsrc + chunk * 8 + 4));
+                }
+            }
+        };
+        if (n_pos > 0) load(cur, p_begin);
         for (int ip = 0; ip < n_pos; ip++) {
-            const long long p = p_begin + ip;
+            if (ip + 1 < n_pos) load(nxt, p_begin + ip + 1);
             mbar_wait(bar_empty + 8 * stage, phase ^ 1);
             uint8_t *st = smem + stage * kWgStage;
             // dY: 128 o x 8 rows of 8 cells
-            const float *dsrc = dy + (size_t)p * 128 * 64;
 #pragma unroll
             for (int it = 0; it < 4; it++) {
-                const int chunk = tid + it * 256;           // (o, row): consecutive threads read consecutive 32 B
+                const int chunk = tid + it * 256;
                 const int o = chunk >> 3, row = chunk & 7;
-                const float4 a = *reinterpret_cast<const float4 *>(dsrc + chunk * 8), b = *reinterpret_cast<const float4 *>(dsrc + chunk * 8 + 4);
-                *reinterpret_cast<uint4 *>(st + (((o >> 3) * 8 + row) * 8 + (o & 7)) * 16) = pack_bf16x8(a, b);
+                *reinterpret_cast<uint4 *>(st + (((o >> 3) * 8 + row) * 8 + (o & 7)) * 16) = pack_bf16x8(cur[2 * it], cur[2 * it + 1]);
             }
             // X: cin channels x 8 rows, three column-shifted copies
-            const float *xsrc = x + (size_t)p * cin * 64;
-            for (int chunk = tid; chunk < cin * 8; chunk += 256) {
-                const int c = chunk >> 3, row = chunk & 7;
-                const float4 a = *reinterpret_cast<const float4 *>(xsrc + chunk * 8), b = *reinterpret_cast<const float4 *>(xsrc + chunk * 8 + 4);
-                const uint4 v = pack_bf16x8(a, b);
-                const uint32_t off = kWgATile + (((c >> 3) * 10 + row + 1) * 8 + (c & 7)) * 16;
-                // kx = 0: out[x] = in[x - 1]; kx = 1: in[x]; kx = 2: out[x] = in[x + 1]   (zero beyond the board edge)
-                const uint4 left = make_uint4(v.x << 16, __funnelshift_l(v.x, v.y, 16), __funnelshift_l(v.y, v.z, 16), __funnelshift_l(v.z, v.w, 16));
-                const uint4 right = make_uint4(__funnelshift_r(v.x, v.y, 16), __funnelshift_r(v.y, v.z, 16), __funnelshift_r(v.z, v.w, 16), v.w >> 16);
-                *reinterpret_cast<uint4 *>(st + off) = left;
-                *reinterpret_cast<uint4 *>(st + off + kWgXCopy) = v;
-                *reinterpret_cast<uint4 *>(st + off + 2 * kWgXCopy) = right;
+#pragma unroll
+            for (int it = 0; it < 4; it++) {
+                if (it < xchunks) {
+                    const int chunk = tid + it * 256;
+                    const int c = chunk >> 3, row = chunk & 7;
+                    const uint4 v = pack_bf16x8(cur[8 + 2 * it], cur[8 + 2 * it + 1]);
+                    const uint32_t off = kWgATile + (((c >> 3) * 10 + row + 1) * 8 + (c & 7)) * 16;
+                    // kx = 0: out[x] = in[x - 1]; kx = 1: in[x]; kx = 2: out[x] = in[x + 1]   (zero beyond the board edge)
+                    const uint4 left = make_uint4(v.x << 16, __funnelshift_l(v.x, v.y, 16), __funnelshift_l(v.y, v.z, 16), __funnelshift_l(v.z, v.w, 16));
+                    const uint4 right = make_uint4(__funnelshift_r(v.x, v.y, 16), __funnelshift_r(v.y, v.z, 16), __funnelshift_r(v.z, v.w, 16), v.w >> 16);
+                    *reinterpret_cast<uint4 *>(st + off) = left;
+                    *reinterpret_cast<uint4 *>(st + off + kWgXCopy) = v;
+                    *reinterpret_cast<uint4 *>(st + off + 2 * kWgXCopy) = right;
+                }
             }
             fence_async_smem();
             mbar_arrive(bar_full + 8 * stage);
             if (++stage == kWgStages) { stage = 0; phase ^= 1; }
+#pragma unroll
+            for (int i = 0; i < 16; i++) cur[i] = nxt[i];
         }
     } else if ((tid & 31) == 0) {
         // ================= MMA issuer =================
@@ -365,19 +390,23 @@ __global__ void reduce_taps_kernel(const float *__restrict__ partial, float *__r
     *dst = accumulate ? *dst + s : s;
 }
 
-// db[o] (+)= sum_{p, cell} dY[p][o][cell]; one block per output channel, fixed-order tree.
-__global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict__ dy, float *__restrict__ out, long long m, int cout, int accumulate) {
+// db[o] = sum_{p, cell} dY[p][o][cell]: block (o, slice) sums its slice of positions with a fixed-order tree into
+// partial[slice][o]; reduce_slices_kernel then adds the slices in order.
+constexpr int kBiasSlices = 16;
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict__ dy, float *__restrict__ partial, long long m, int cout) {
     __shared__ float red[256];
     const int o = blockIdx.x, tid = threadIdx.x;
+    const long long per = (m + gridDim.y - 1) / gridDim.y;
+    const long long p0 = (long long)blockIdx.y * per, p1 = min(m, p0 + per);
     float s = 0.0f;
-    for (long long i = tid; i < m * 64; i += 256) s += dy[((i >> 6) * cout + o) * 64 + (i & 63)];
+    for (long long i = p0 * 64 + tid; i < p1 * 64; i += 256) s += dy[((i >> 6) * cout + o) * 64 + (i & 63)];
     red[tid] = s;
     __syncthreads();
     for (int k = 128; k > 0; k >>= 1) {
         if (tid < k) red[tid] += red[tid + k];
         __syncthreads();
     }
-    if (tid == 0) out[o] = accumulate ? out[o] + red[0] : red[0];
+    if (tid == 0) partial[(size_t)blockIdx.y * cout + o] = red[0];
 }
 
 // out[i] (+)= sum over slices of partial[s][i], slices in order.
@@ -498,11 +527,14 @@ struct iago_trainer {
     long long t = 0;
     float *wf[8] = {}, *wd[8] = {};   // conv-kernel weight layouts
     float *act[9] = {};               // act[0] = input planes, act[l] = output of block l
-    float *dbuf[2] = {};              // dY ping-pong [max_pos][128][64]
-    float *dlogit = nullptr, *loss_terms = nullptr, *partial = nullptr;
+    float *dyb[8] = {};               // dyb[l]: gradient w.r.t. the pre-activation output of block l+1, [max_pos][cout_l][64]
+    uint8_t *bwd_blob = nullptr;      // bf16 hi/lo weight units of the data-gradient chain (trunk.cu, backward mode)
+    void *bwd_desc = nullptr;
+    int bwd_precision = 3;
+    float *dlogit = nullptr, *loss_terms = nullptr, *partial = nullptr, *bias_partial = nullptr;
     size_t partial_stride = 0;
     int slices = 0;
-    int tc_slices = 0;
+    int tc_slices = 0, slices0 = 0;
     bool use_tc = true, tc_attr = false;
     int synced_slot = -1;             // trunk slot that holds the CURRENT parameters (-1: stale)
     uint8_t *ones = nullptr;          // colour array (all 1) for the trunk launch
@@ -554,9 +586,13 @@ int iago_reinforce_create(iago_ctx *ctx, const float *params, int64_t n_floats, 
     }
     A(t->act[0], M * 2 * 64);
     for (int l = 0; l < 8; l++) A(t->act[l + 1], M * kCout[l] * 64);
-    A(t->dbuf[0], M * 128 * 64); A(t->dbuf[1], M * 128 * 64);
+    for (int l = 0; l < 8; l++) A(t->dyb[l], M * kCout[l] * 64);
+    A(t->bwd_blob, trunk_backward_blob_bytes());
+    { uint8_t *d = nullptr; A(d, trunk_desc_bytes()); t->bwd_desc = d; }
     A(t->dlogit, M * 64); A(t->loss_terms, M); A(t->ones, M); A(t->logits_scratch, M * 64);
-    t->slices = 24;
+    A(t->bias_partial, (size_t)kBiasSlices * 128);
+    t->slices = 24;                                  // fp32 weight-gradient kernel: position slices of the 64/128-input-channel layers
+    t->slices0 = 2 * ctx->sm_count;                  // ... and of block 1 (2 input channels: one c tile, so the slices are the whole grid)
     t->tc_slices = (ctx->sm_count + 2) / 3;          // 3 kernel rows x slices ~ one CTA per SM
     t->partial_stride = (size_t)128 * 128 * 9 + 128;
     A(t->partial, (size_t)(t->tc_slices > t->slices ? t->tc_slices : t->slices) * t->partial_stride);
@@ -588,7 +624,7 @@ int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *op
     if (m == 0) return IAGO_OK;
     DeviceGuard guard(t->ctx->device);
     cudaStream_t s = (cudaStream_t)stream;
-    relayout_all(t, s);
+    if (!(t->use_tc && t->synced_slot >= 0)) relayout_all(t, s);   // Wf / Wd feed the fp32 conv kernels only
     const unsigned tiles = (unsigned)((m + 1) / 2);
     // ---- forward, activations kept
     planes_kernel<<<(unsigned)((m * 64 + 255) / 256), 256, 0, s>>>((const u64 *)own, (const u64 *)opp, t->act[0], m);
@@ -608,15 +644,29 @@ int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *op
     IAGO_CUDA(cudaGetLastError());
     // ---- head forward + backward
     head_kernel<<<(unsigned)m, 64, 0, s>>>(t->act[8], t->params + t->w9_off, t->params + t->b10_off, action, reward, t->dlogit,
-                                          t->dbuf[0], t->loss_terms, probs_out, m);
+                                          t->dyb[7], t->loss_terms, probs_out, m);
     head_grad_kernel<<<193, 256, 0, s>>>(t->act[8], t->dlogit, t->loss_terms, grad + t->w9_off, grad + t->b10_off, grad + kNP, m, accumulate);
     IAGO_CUDA(cudaGetLastError());
     // ---- backward through the 8 blocks
-    int cur = 0;
-    const int pos_per_slice = (int)((m + t->slices - 1) / t->slices);
-    const int slices = (int)((m + pos_per_slice - 1) / pos_per_slice);
+    if (t->use_tc) {
+        // data gradients of blocks 8..2 as ONE fused tcgen05 launch (bf16 hi/lo, the tile stays on chip between layers)
+        const float *W[8], *mask[7];
+        float *dx[7];
+        for (int l = 0; l < 8; l++) W[l] = t->params + t->w_off[l];
+        for (int i = 0; i < 7; i++) {
+            mask[i] = t->act[7 - i];
+            dx[i] = t->dyb[6 - i];
+        }
+        int rc = trunk_backward_pack(t->ctx, W, t->bwd_blob, t->bwd_desc, stream);
+        if (rc) return rc;
+        rc = trunk_backward_launch(t->ctx, t->bwd_desc, t->bwd_blob, t->dyb[7], mask, dx, m, t->bwd_precision, stream);
+        if (rc) return rc;
+    }
     for (int l = 7; l >= 0; l--) {
-        const float *dy = t->dbuf[cur];
+        const int want = l == 0 ? t->slices0 : t->slices;
+        const int pos_per_slice = (int)((m + want - 1) / want);
+        const int slices = (int)((m + pos_per_slice - 1) / pos_per_slice);
+        const float *dy = t->dyb[l];
         if (t->use_tc && kCout[l] == 128) {
             if (!t->tc_attr) {
                 IAGO_CUDA(cudaFuncSetAttribute(wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWgSmem));
@@ -626,20 +676,20 @@ int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *op
             const int sl = (int)((m + pps - 1) / pps);
             wgrad_tc_kernel<<<dim3(sl, 3), kWgThreads, kWgSmem, s>>>(t->act[l], dy, t->partial, m, kCin[l], pps, t->partial_stride);
             reduce_taps_kernel<<<(9 * 128 * kCin[l] + 255) / 256, 256, 0, s>>>(t->partial, grad + t->w_off[l], kCin[l], sl, t->partial_stride, accumulate);
-            bias_grad_kernel<<<kCout[l], 256, 0, s>>>(dy, grad + t->b_off[l], m, kCout[l], accumulate);
+            bias_grad_kernel<<<dim3(kCout[l], kBiasSlices), 256, 0, s>>>(dy, t->bias_partial, m, kCout[l]);
+            reduce_slices_kernel<<<1, 256, 0, s>>>(t->bias_partial, grad + t->b_off[l], kCout[l], kBiasSlices, (size_t)kCout[l], accumulate);
         } else {
-            wgrad3x3_kernel<<<dim3((kCin[l] + 15) / 16, slices), 256, 0, s>>>(t->act[l], dy, t->partial, m, kCin[l], kCout[l], pos_per_slice,
-                                                                              t->partial_stride);
             const int count = kCout[l] * kCin[l] * 9 + kCout[l];  // W then b are adjacent in the flat layout as well
-            reduce_slices_kernel<<<(count + 255) / 256, 256, 0, s>>>(t->partial, grad + t->w_off[l], count, slices, t->partial_stride, accumulate);
+            const size_t stride = l == 0 ? (size_t)count : t->partial_stride;
+            wgrad3x3_kernel<<<dim3((kCin[l] + 15) / 16, slices), 256, 0, s>>>(t->act[l], dy, t->partial, m, kCin[l], kCout[l], pos_per_slice, stride);
+            reduce_slices_kernel<<<(count + 255) / 256, 256, 0, s>>>(t->partial, grad + t->w_off[l], count, slices, stride, accumulate);
         }
-        if (l > 0) {
-            float *dx = t->dbuf[cur ^ 1];
+        if (!t->use_tc && l > 0) {
+            float *dx = t->dyb[l - 1];
             if (kCin[l] == 64)
                 conv3x3_kernel<64, EPI_DGRAD><<<dim3(tiles, 1), 256, 0, s>>>(dy, t->wd[l], nullptr, t->act[l], dx, m, kCout[l], kCin[l]);
             else
                 conv3x3_kernel<128, EPI_DGRAD><<<dim3(tiles, 1), 256, 0, s>>>(dy, t->wd[l], nullptr, t->act[l], dx, m, kCout[l], kCin[l]);
-            cur ^= 1;
         }
     }
     IAGO_CUDA(cudaGetLastError());
@@ -698,10 +748,19 @@ int iago_reinforce_set_option(iago_trainer *t, int use_tensor_cores) {
 
 int iago_reinforce_sync_slot(iago_trainer *t, int slot) {
     IAGO_REQUIRE(t, "NULL argument");
-    std::vector<float> h(kNP);
-    int rc = iago_reinforce_get_state(t, h.data(), nullptr, nullptr, nullptr);
-    if (rc) return rc;
-    rc = iago_load_net(t->ctx, slot, 0, h.data(), kNP);
+    int rc;
+    if (trunk_slot_holds(t->ctx, slot, 0)) {
+        // the slot's buffers exist: repack on the device (after whatever stream the Adam step ran on has drained)
+        DeviceGuard guard(t->ctx->device);
+        IAGO_CUDA(cudaDeviceSynchronize());
+        rc = trunk_refresh_policy_slot(t->ctx, slot, t->params, t->ctx->stream);
+        if (rc == IAGO_OK) IAGO_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    } else {
+        std::vector<float> h(kNP);
+        rc = iago_reinforce_get_state(t, h.data(), nullptr, nullptr, nullptr);
+        if (rc) return rc;
+        rc = iago_load_net(t->ctx, slot, 0, h.data(), kNP);
+    }
     if (rc == IAGO_OK) t->synced_slot = slot;
     return rc;
 }

@@ -24,6 +24,7 @@
 //   * Heads: policy = per-row dot with conv9 (fp32, CUDA cores) in the layer-8 epilogue (+bias10, optional
 //     softmax); value = block9 as a ninth MMA layer with N padded to 16, then relu and the collapsed
 //     fc11*fc10 64-vector.
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <string.h>
 
@@ -87,9 +88,14 @@ struct TrunkArgs {
     const float *head;    // policy: w9[128], b10[64]; value: b9 at [0], wfc[64] at [128..192)
     const int *n_dev;     // nullable: the live position count is min(n, *n_dev) (request lists built on the device, mcts.cu)
     float *dump[8];       // nullable each: post-ReLU output of block l+1 as fp32 [n][channels][64] (kept for the backward pass, reinforce.cu)
+    // backward mode only (trunk_kernel<1>, the data-gradient chain of reinforce.cu):
+    const float *dy_in;   // [n][128][64] gradient w.r.t. the output of block 8, entering the chain
+    const float *mask[8]; // mask[i]: [n][N_i][64] forward activation whose sign gates the output of chain layer i (ReLU backward)
 };
 
-// bias + ReLU + hi/lo fp16 split of 32 accumulator columns, written as 4 channel groups of this thread's tile row.
+// hi/lo split (fp16 in the forward, bf16 in the backward chain: gradients need the exponent range) of 32 values of this
+// thread's tile row, written as 4 channel groups of the activation tile.
+template <bool BF16>
 __device__ __forceinline__ void store_act32(uint8_t *smem, const float (&x)[32], uint32_t group0_off, bool split) {
 #pragma unroll
     for (int q = 0; q < 4; q++) {
@@ -97,11 +103,19 @@ __device__ __forceinline__ void store_act32(uint8_t *smem, const float (&x)[32],
 #pragma unroll
         for (int e = 0; e < 4; e++) {
             const float f0 = x[q * 8 + 2 * e], f1 = x[q * 8 + 2 * e + 1];
-            const __half2 h = __floats2half2_rn(f0, f1);
-            const float2 hf = __half22float2(h);
-            const __half2 l = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
-            hw[e] = *reinterpret_cast<const uint32_t *>(&h);
-            lw[e] = *reinterpret_cast<const uint32_t *>(&l);
+            if (BF16) {
+                const __nv_bfloat162 h = __floats2bfloat162_rn(f0, f1);
+                const float2 hf = __bfloat1622float2(h);
+                const __nv_bfloat162 l = __floats2bfloat162_rn(f0 - hf.x, f1 - hf.y);
+                hw[e] = *reinterpret_cast<const uint32_t *>(&h);
+                lw[e] = *reinterpret_cast<const uint32_t *>(&l);
+            } else {
+                const __half2 h = __floats2half2_rn(f0, f1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn(f0 - hf.x, f1 - hf.y);
+                hw[e] = *reinterpret_cast<const uint32_t *>(&h);
+                lw[e] = *reinterpret_cast<const uint32_t *>(&l);
+            }
         }
         const uint32_t off = group0_off + (uint32_t)q * kGroupBytes;
         *reinterpret_cast<uint4 *>(smem + OFF_AHI + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
@@ -115,6 +129,12 @@ __device__ __forceinline__ void store_act32(uint8_t *smem, const float (&x)[32],
 // Pipeline per tile (DESIGN.md "trunk pipeline"): the accumulator is double-buffered in TMEM (layer l uses buffer
 // l&1) and weight units are ordered chunk-major, so the MMAs of layer l+1 on input channels 0..63 start as soon as
 // the epilogue of layer l has written those channels, while it is still converting channels 64..127.
+//
+// MODE 0 = forward (SLPolicy / Value).  MODE 1 = the backward data-gradient chain of the REINFORCE update (reinforce.cu):
+// chain layer i is the transposed, tap-flipped conv of block 8-i in bf16 hi/lo; the tile entering the chain is read from
+// HBM (dy_in), every layer's output is gated by the sign of the forward activation (mask[i]) and written to HBM (dump[i])
+// for the weight-gradient kernel as well as to the activation tile for the next chain layer.
+template <int MODE>
 __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const NetDesc *__restrict__ gnet) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ NetDesc net;
@@ -130,7 +150,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
     for (int i = tid; i < (int)(sizeof(NetDesc) / 4); i += kThreads) reinterpret_cast<int *>(&net)[i] = reinterpret_cast<const int *>(gnet)[i];
     for (int i = tid; i < (OFF_A1 + kA1Bytes) / 16; i += kThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
-    {
+    if (MODE == 0) {
         float *sb = reinterpret_cast<float *>(smem + OFF_BIAS);
         for (int i = tid; i < net.n_layers * 128; i += kThreads) sb[i] = a.bias[i];
         float *sh = reinterpret_cast<float *>(smem + OFF_HEAD);
@@ -192,12 +212,12 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
                 for (int l = 0; l < L; l++) {
                     const LayerDesc ld = net.layer[l];
-                    const uint32_t idesc = instr_desc(kTileRows, ld.n);
+                    const uint32_t idesc = MODE == 0 ? instr_desc(kTileRows, ld.n) : instr_desc_bf16(kTileRows, ld.n);
                     const uint32_t d_tmem = tmem + (uint32_t)(l & 1) * 128u;
                     const uint32_t b_step = (uint32_t)(2 * ld.b_lbo) >> 4;              // descriptor units (16 B) per K=16 step
                     const uint32_t b_lo_word = ((uint32_t)(ld.b_lbo >> 4) << 16);
                     uint32_t acc = 0;
-                    if (ld.chunks == 0) {
+                    if (MODE == 0 && ld.chunks == 0) {
                         // layer 1: explicit im2col tile [4][128][16 B], LBO = 2048, SBO = 128
                         mbar_wait(bar_a1, a1_phase);
                         a1_phase ^= 1;
@@ -264,39 +284,55 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
         for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
             const long long pos = tile * 2 + b;
             const bool valid = pos < n_pos;
+            if (MODE == 1) {
+                // ---- chain entry: the gradient tile [128 channels][cell] of this row's position -> bf16 hi/lo activation tile
+                const float *src = a.dy_in + (size_t)pos * 128 * 64 + cell;
+#pragma unroll 1
+                for (int ps = 0; ps < 2; ps++) {
+                    const int col0 = ps * 64 + half * 32;
+                    float x[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j++) x[j] = valid ? __ldg(src + (size_t)(col0 + j) * 64) : 0.0f;
+                    store_act32<true>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
+                    fence_async_smem();
+                    tc_fence_before();
+                    mbar_arrive(bar_act + 8 * ps);
+                }
+            } else {
             // ---- layer-1 input: explicit im2col of the two bit planes, k = tap*2 + channel (0 = opponent, 1 = mover)
-            if (half == 0) {
-                u64 own = 0, opp = 0;
-                if (valid) {
-                    const bool first = a.color[pos] == 1;
-                    const u64 x1 = a.p1[pos], x2 = a.p2[pos];
-                    own = first ? x1 : x2;
-                    opp = first ? x2 : x1;
-                }
-                uint32_t bits = 0;
+                if (half == 0) {
+                    u64 own = 0, opp = 0;
+                    if (valid) {
+                        const bool first = a.color[pos] == 1;
+                        const u64 x1 = a.p1[pos], x2 = a.p2[pos];
+                        own = first ? x1 : x2;
+                        opp = first ? x2 : x1;
+                    }
+                    uint32_t bits = 0;
 #pragma unroll
-                for (int t = 0; t < 9; t++) {
-                    const int y = r + t / 3 - 1, x = c + t % 3 - 1;
-                    if (y >= 0 && y < 8 && x >= 0 && x < 8) {
-                        const int k = y * 8 + x;
-                        bits |= (uint32_t)((opp >> k) & 1) << (2 * t);
-                        bits |= (uint32_t)((own >> k) & 1) << (2 * t + 1);
+                    for (int t = 0; t < 9; t++) {
+                        const int y = r + t / 3 - 1, x = c + t % 3 - 1;
+                        if (y >= 0 && y < 8 && x >= 0 && x < 8) {
+                            const int k = y * 8 + x;
+                            bits |= (uint32_t)((opp >> k) & 1) << (2 * t);
+                            bits |= (uint32_t)((own >> k) & 1) << (2 * t + 1);
+                        }
+                    }
+#pragma unroll
+                    for (int kg = 0; kg < 4; kg++) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int e = 0; e < 4; e++) {
+                            const uint32_t lo = (bits >> (kg * 8 + 2 * e)) & 1, hi = (bits >> (kg * 8 + 2 * e + 1)) & 1;
+                            w[e] = (lo ? 0x3C00u : 0u) | (hi ? 0x3C000000u : 0u);  // fp16 1.0 = 0x3C00
+                        }
+                        *reinterpret_cast<uint4 *>(smem + OFF_A1 + kg * (kTileRows * 16) + m * 16) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
-#pragma unroll
-                for (int kg = 0; kg < 4; kg++) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        const uint32_t lo = (bits >> (kg * 8 + 2 * e)) & 1, hi = (bits >> (kg * 8 + 2 * e + 1)) & 1;
-                        w[e] = (lo ? 0x3C00u : 0u) | (hi ? 0x3C000000u : 0u);  // fp16 1.0 = 0x3C00
-                    }
-                    *reinterpret_cast<uint4 *>(smem + OFF_A1 + kg * (kTileRows * 16) + m * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                }
+                fence_async_smem();
+                tc_fence_before();
+                mbar_arrive(bar_a1);
             }
-            fence_async_smem();
-            tc_fence_before();
-            mbar_arrive(bar_a1);
 
             for (int l = 0; l < L; l++) {
                 const LayerDesc ld = net.layer[l];
@@ -306,7 +342,34 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                 const uint32_t t_addr = lane_addr + (uint32_t)(l & 1) * 128u;
                 const bool policy_head = (l == 7 && net.kind == 0);
                 const bool writes_act = (l + 1 < L);
-                if (l < 8) {
+                if (MODE == 1) {
+                    const int passes = ld.n / 64;
+                    const float *mk = a.mask[l] + ((size_t)pos * ld.n) * 64 + cell;
+                    float *dst = a.dump[l] + ((size_t)pos * ld.n) * 64 + cell;
+#pragma unroll 1
+                    for (int ps = 0; ps < passes; ps++) {
+                        const int col0 = ps * 64 + half * 32;
+                        float g[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) g[j] = valid ? __ldg(mk + (size_t)(col0 + j) * 64) : 0.0f;   // in flight during the TMEM read
+                        uint32_t v[32];
+                        tmem_ld32(t_addr + col0, v);
+                        tmem_wait_ld();
+                        float x[32];
+#pragma unroll
+                        for (int j = 0; j < 32; j++) x[j] = g[j] > 0.0f ? __uint_as_float(v[j]) : 0.0f;
+                        if (valid) {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) dst[(size_t)(col0 + j) * 64] = x[j];
+                        }
+                        if (writes_act) {
+                            store_act32<true>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
+                            fence_async_smem();
+                            tc_fence_before();
+                            mbar_arrive(bar_act + 8 * ps);
+                        }
+                    }
+                } else if (l < 8) {
                     float dot = 0.0f;
                     const int passes = ld.n / 64;  // 1 for the 64-channel layer, else 2
                     for (int ps = 0; ps < passes; ps++) {
@@ -327,7 +390,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                             for (int j = 0; j < 32; j++) dst[(size_t)j * 64] = x[j];
                         }
                         if (writes_act) {
-                            store_act32(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
+                            store_act32<false>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
                             fence_async_smem();
                             tc_fence_before();
                             mbar_arrive(bar_act + 8 * ps);  // input channels [64*ps, 64*ps+64) of the next layer are in place
@@ -548,19 +611,156 @@ int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, con
     if (n == 0) return IAGO_OK;
     DeviceGuard guard(ctx->device);
     if (!st->attr_set) {
-        IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         st->attr_set = true;
     }
     const long long tiles = (n + 1) / 2;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    TrunkArgs a{(const u64 *)p1, (const u64 *)p2, color, n, out, out_kind, precision, s.d_blob, s.d_bias, s.d_head, n_dev, {}};
+    TrunkArgs a{(const u64 *)p1, (const u64 *)p2, color, n, out, out_kind, precision, s.d_blob, s.d_bias, s.d_head, n_dev, {}, nullptr, {}};
     for (int l = 0; l < 8; l++) a.dump[l] = dump ? dump[l] : nullptr;
     cudaStream_t cs = (cudaStream_t)stream;
     IAGO_CUDA(cudaEventRecord(ctx->ev0, cs));
-    trunk_kernel<<<grid, kThreads, kSmemBytes, cs>>>(a, s.d_desc);
+    trunk_kernel<0><<<grid, kThreads, kSmemBytes, cs>>>(a, s.d_desc);
     IAGO_CUDA(cudaGetLastError());
     IAGO_CUDA(cudaEventRecord(ctx->ev1, cs));
     ctx->timed = true;
+    return IAGO_OK;
+}
+
+// ---------------------------------------------------------------- refresh a policy slot from DEVICE parameters
+// The same blob iago_load_net builds on the host (same roundings, bit-identical), written by kernels: the REINFORCE
+// trainer refreshes its playing slot after every Adam step without a device -> host -> device round trip.
+__global__ void pack_forward_kernel(const float *__restrict__ W, uint8_t *__restrict__ units, int cin, int cout, int first) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int kgroups = first ? 4 : 8, n_units = first ? 1 : 9 * (cin / 64);
+    const int total = n_units * kgroups * cout * 8;
+    if (idx >= total) return;
+    const int e = idx & 7, n = (idx >> 3) % cout, kg = ((idx >> 3) / cout) % kgroups, ut = (idx >> 3) / cout / kgroups;
+    const int k = kg * 8 + e;
+    float w;
+    if (first) {
+        w = k < 18 ? W[((size_t)n * 2 + (k & 1)) * 9 + (k >> 1)] : 0.0f;       // explicit im2col: k = tap*2 + channel
+    } else {
+        const int ch = ut / 9, tap = ut % 9;                                   // chunk-major units
+        w = W[((size_t)n * cin + ch * 64 + k) * 9 + tap];
+    }
+    const __half h = __float2half_rn(w);
+    const __half l = __float2half_rn(w - __half2float(h));
+    const size_t half_elems = (size_t)kgroups * cout * 8;
+    __half *unit = reinterpret_cast<__half *>(units) + (size_t)ut * 2 * half_elems;
+    const size_t off = ((size_t)kg * cout + n) * 8 + e;
+    unit[off] = h;
+    unit[half_elems + off] = l;
+}
+
+__global__ void pack_bias_head_kernel(const float *__restrict__ params, float *__restrict__ bias, float *__restrict__ head) {
+    // params: iago_load_net order, kind 0.  bias[l][128] (zero padded), head = w9[128] | b10[64] | 0...
+    const int cin[8] = {2, 64, 128, 128, 128, 128, 128, 128}, cout[8] = {64, 128, 128, 128, 128, 128, 128, 128};
+    size_t off = 0;
+    for (int l = 0; l < 8; l++) {
+        off += (size_t)cout[l] * cin[l] * 9;
+        for (int i = threadIdx.x; i < 128; i += blockDim.x) bias[l * 128 + i] = i < cout[l] ? params[off + i] : 0.0f;
+        off += cout[l];
+    }
+    for (int i = threadIdx.x; i < 192; i += blockDim.x) head[i] = params[off + i];
+}
+
+int trunk_refresh_policy_slot(iago_ctx *ctx, int slot, const float *d_params, void *stream) {
+    IAGO_REQUIRE(ctx && d_params, "NULL argument");
+    IAGO_REQUIRE(slot >= 0 && slot < 8, "slot out of range (0..7)");
+    NetSlot &s = state(ctx)->slot[slot];
+    if (!s.loaded || s.desc.kind != 0) {
+        set_error("net slot %d holds no policy network to refresh (call iago_load_net once first)", slot);
+        return IAGO_E_STATE;
+    }
+    const int cin[8] = {2, 64, 128, 128, 128, 128, 128, 128}, cout[8] = {64, 128, 128, 128, 128, 128, 128, 128};
+    cudaStream_t cs = (cudaStream_t)stream;
+    size_t off = 0;
+    for (int l = 0; l < 8; l++) {
+        const int total = (l == 0 ? 4 * cout[l] * 8 : 9 * (cin[l] / 64) * 8 * cout[l] * 8);
+        pack_forward_kernel<<<(total + 255) / 256, 256, 0, cs>>>(d_params + off, s.d_blob + s.desc.unit_base[l], cin[l], cout[l], l == 0);
+        off += (size_t)cout[l] * cin[l] * 9 + cout[l];
+    }
+    pack_bias_head_kernel<<<1, 128, 0, cs>>>(d_params, s.d_bias, s.d_head);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+// ---------------------------------------------------------------- backward data-gradient chain (reinforce.cu)
+// Chain layer i = dgrad of block 8-i (i = 0..6): dX[c] = sum_{o,tap} dY[o] (shifted by tap) * W[o][c][8-tap], K = 128 output
+// channels of the block in two 64-channel chunks, N = its input channels (128, or 64 for block 2).
+size_t trunk_backward_blob_bytes() {
+    size_t b = 0;
+    for (int i = 0; i < 7; i++) b += (size_t)18 * 2 * 8 * (i == 6 ? 64 : 128) * 16;
+    return b;
+}
+
+// blob unit (chunk ch, tap): hi [8 k-groups][N][8] bf16 then lo; element (kg, n, e) = W_l[o = ch*64 + kg*8 + e][c = n][8 - tap].
+__global__ void pack_dgrad_kernel(const float *__restrict__ W, uint8_t *__restrict__ units, int cin) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over [ch 2][tap 9][kg 8][n cin][e 8]
+    const int total = 2 * 9 * 8 * cin * 8;
+    if (idx >= total) return;
+    const int e = idx & 7, n = (idx >> 3) % cin, kg = ((idx >> 3) / cin) & 7, ut = (idx >> 3) / cin / 8;   // ut = ch*9 + tap
+    const int ch = ut / 9, tap = ut % 9;
+    const int o = ch * 64 + kg * 8 + e;
+    const float w = W[((size_t)o * cin + n) * 9 + (8 - tap)];
+    const __nv_bfloat16 h = __float2bfloat16_rn(w);
+    const __nv_bfloat16 l = __float2bfloat16_rn(w - __bfloat162float(h));
+    const size_t half_elems = (size_t)8 * cin * 8;
+    __nv_bfloat16 *unit = reinterpret_cast<__nv_bfloat16 *>(units) + (size_t)ut * 2 * half_elems;
+    const size_t off = ((size_t)kg * cin + n) * 8 + e;
+    unit[off] = h;
+    unit[half_elems + off] = l;
+}
+
+int trunk_backward_pack(iago_ctx *ctx, const float *const *W /* W[l], l = 1..7: [128][cin_l][3][3] on the device */, uint8_t *blob,
+                        void *desc_dev, void *stream) {
+    NetDesc d;
+    memset(&d, 0, sizeof d);
+    d.n_layers = 7;
+    d.kind = 2;
+    size_t off = 0;
+    cudaStream_t cs = (cudaStream_t)stream;
+    for (int i = 0; i < 7; i++) {
+        const int l = 7 - i, cin = l == 1 ? 64 : 128;
+        LayerDesc &ld = d.layer[i];
+        ld.n_units = 18; ld.ksteps = 4; ld.n = cin; ld.lo_off = 8 * cin * 16; ld.unit_bytes = 2 * ld.lo_off; ld.b_lbo = cin * 16; ld.chunks = 2;
+        d.unit_base[i] = (long long)off;
+        const int total = 2 * 9 * 8 * cin * 8;
+        pack_dgrad_kernel<<<(total + 255) / 256, 256, 0, cs>>>(W[l], blob + off, cin);
+        off += (size_t)18 * ld.unit_bytes;
+    }
+    IAGO_CUDA(cudaGetLastError());
+    if (desc_dev) IAGO_CUDA(cudaMemcpyAsync(desc_dev, &d, sizeof d, cudaMemcpyHostToDevice, cs));
+    (void)ctx;
+    return IAGO_OK;
+}
+
+size_t trunk_desc_bytes() { return sizeof(NetDesc); }
+
+int trunk_backward_launch(iago_ctx *ctx, const void *desc_dev, const uint8_t *blob, const float *dy_in, const float *const *mask,
+                          float *const *dx_out, int64_t n, int precision, void *stream) {
+    IAGO_REQUIRE(ctx && desc_dev && blob && dy_in && mask && dx_out, "NULL argument");
+    IAGO_REQUIRE(precision == 1 || precision == 3, "precision must be 1 (bf16) or 3 (bf16 hi/lo split)");
+    if (n <= 0) return IAGO_OK;
+    TrunkState *st = state(ctx);
+    if (!st->attr_set) {
+        IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+        st->attr_set = true;
+    }
+    const long long tiles = (n + 1) / 2;
+    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    TrunkArgs a{nullptr, nullptr, nullptr, n, nullptr, 0, precision, blob, nullptr, nullptr, nullptr, {}, dy_in, {}};
+    for (int i = 0; i < 7; i++) {
+        a.dump[i] = dx_out[i];
+        a.mask[i] = mask[i];
+    }
+    a.dump[7] = nullptr;
+    a.mask[7] = nullptr;
+    trunk_kernel<1><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, static_cast<const NetDesc *>(desc_dev));
+    IAGO_CUDA(cudaGetLastError());
     return IAGO_OK;
 }
 }  // namespace iago

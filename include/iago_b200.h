@@ -263,8 +263,9 @@ IAGO_API int iago_reinforce_adam_step(iago_trainer *t, const float *grad, double
  * src/train_rl.py:76-77); any pointer may be NULL; step < 0 keeps t. */
 IAGO_API int iago_reinforce_get_state(iago_trainer *t, float *params, float *adam_m, float *adam_v, int64_t *step);
 IAGO_API int iago_reinforce_set_state(iago_trainer *t, const float *params, const float *adam_m, const float *adam_v, int64_t step);
-/* use_tensor_cores != 0 (default): weight gradients of the 128-output-channel layers run as bf16 tcgen05 GEMMs with fp32
- * accumulation; 0: every kernel in fp32 on the CUDA cores (the checker for the tensor-core path). */
+/* use_tensor_cores != 0 (default 1): forward on the fused tcgen05 trunk, the data gradients of blocks 8..2 as one fused
+ * tcgen05 launch (bf16 hi/lo split, 3 MMAs; a single bf16 pass was measured at up to 4e-2 of max|g| and is not offered), weight gradients of the 128-output-channel layers as
+ * bf16 tcgen05 GEMMs, all with fp32 accumulation; 0: every kernel in fp32 on the CUDA cores (the checker for that path). */
 IAGO_API int iago_reinforce_set_option(iago_trainer *t, int use_tensor_cores);
 /* Makes the trainer's current parameters the policy in net slot `slot` (what self-play then plays with). */
 IAGO_API int iago_reinforce_sync_slot(iago_trainer *t, int slot);

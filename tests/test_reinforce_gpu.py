@@ -79,12 +79,13 @@ def test_gradient_matches_autograd(engine):
     assert (tr.grad.cpu().numpy().astype(np.float64) == g).all()
 
 
-def test_tensor_core_path(engine):
-    """tensor_cores=True: forward on the fused tcgen05 trunk (fp16 hi/lo split), weight gradients as bf16 tcgen05 GEMMs.
+def test_tensor_core_path(engine, mode=1):
+    """tensor_cores=1: forward on the fused tcgen05 trunk (fp16 hi/lo split), data gradients as one fused tcgen05 chain (bf16
+    hi/lo split), weight gradients as bf16 tcgen05 GEMMs.
     (1) The forward's activations equal the float64 forward within 2e-4; its ReLU on/off decisions differ from the float64
         ones ONLY on units whose pre-activation is within 2e-4 of zero (the kink, where the derivative is ambiguous).
     (2) With those on/off decisions taken as given, the gradient equals float64 autograd within 1e-2 * max|g| per tensor
-        (bf16 operands, fp32 accumulation); loss numerator within 1e-4 relative."""
+        (bf16 weight-gradient operands, fp32 accumulation); loss numerator within 1e-4 relative."""
     import torch
     from iago_b200 import npz
     from iago_b200.train_rl import ReinforceTrainer, N_PARAMS
@@ -94,7 +95,7 @@ def test_tensor_core_path(engine):
     own, opp = to_device(states)
     a = torch.from_numpy(actions.astype(np.int8)).cuda()
     r = torch.from_numpy(rewards).cuda()
-    tr = ReinforceTrainer(path, max_positions=256, tensor_cores=True, slot=4)
+    tr = ReinforceTrainer(path, max_positions=256, tensor_cores=mode, slot=4)
     tr.gradient(own, opp, a, r)
     torch.cuda.synchronize()
     g = tr.grad.cpu().numpy().astype(np.float64)
@@ -114,7 +115,7 @@ def test_tensor_core_path(engine):
     assert abs(g[N_PARAMS] - total) <= 1e-4 * abs(total) + 1e-6
     errs = per_tensor_errors(g[:N_PARAMS], ref)
     worst = max(e / s_ for e, s_ in errs.values() if s_ > 0)
-    print(f"tensor-core path: {flips} ReLU decisions at the kink differ from float64; worst per-tensor gradient error {worst:.2e} of max|g|")
+    print(f"tensor-core path (mode {mode}): {flips} ReLU decisions at the kink differ from float64; worst per-tensor gradient error {worst:.2e} of max|g|")
     for k, (e, scale) in errs.items():
         assert e <= 1e-2 * scale + 1e-6, (k, e, scale)
     tr.close()
@@ -154,6 +155,10 @@ def test_adam_steps_match_chainer_rule(engine):
     new = npz.unflatten(w.astype(np.float32), npz.KIND_POLICY)
     ref_prob = nets.sl_policy({k: x.astype(np.float64) for k, x in new.items()}, nets.planes_from_state(boards.start_state()[None], 1, np.float64))[0]
     assert np.abs(out - ref_prob).max() <= 1e-4
+    # ... and the device-side repack of the slot (iago_reinforce_sync_slot) is bit-identical to iago_load_net of the same weights
+    engine.load_net(3, npz.unflatten(got, npz.KIND_POLICY))
+    q1, q2 = boards.to_bitboards(states[:64])
+    assert (engine.policy_forward_host(tr.slot, q1, q2, 1, probs=False) == engine.policy_forward_host(3, q1, q2, 1, probs=False)).all()
 
 
 def test_train_set_runs_and_checkpoints(engine, tmp_path):

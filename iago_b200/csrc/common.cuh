@@ -10,10 +10,15 @@ namespace iago {
 
 void set_error(const char *fmt, ...);
 
-// Rollout policy in the form the kernel consumes (built on the host in the canonical summation order).
+// Rollout policy in the form the kernels consume (built on the host in the canonical summation order).
+// LUT index of a 3x3 neighbourhood: tap t = ky*3 + kx (cell (i+ky-1, j+kx-1)) sits at bit 6 - 3*ky + kx, i.e. row i+1 in bits
+// 0-2, row i in bits 3-5, row i-1 in bits 6-8 (the order the kernel's multiply-gather produces, rollout.cu pat_index).
 struct RolloutWeights {
-    float lut[2][512];  // lut[c][pattern] = sum over taps t ascending of W[c][t] for set bits of the 9-bit pattern
+    float lut[2][512];   // lut[c][index]  = sum over taps t ascending of W[c][t] for the set taps of the pattern
     float bias[64];
+    uint32_t colmask[8]; // 3x3 window mask for column j: 0x070707 without the wrapped column at j = 0 / j = 7
+    double elut[2][512]; // elut[c][index] = canon_exp(lut[c][index])                  (fast sampler: e = elut0 * elut1 * ebias)
+    double ebias[64];    // ebias[k]       = canon_exp(bias[k])
 };
 
 struct Staging {
@@ -32,6 +37,7 @@ struct iago_ctx {
     bool timed = false;
     iago::RolloutWeights *d_rollout = nullptr;
     bool rollout_loaded = false;
+    bool rollout_fast = false;   // every possible |logit| <= 300: the product-of-exponentials sampler cannot over/underflow in double
     iago::Staging stage;
     uint64_t *d_counters = nullptr;
     void *trunk = nullptr;     // conv-net state (trunk.cu)

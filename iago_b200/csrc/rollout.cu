@@ -12,9 +12,15 @@
 // and the game ends with judge (mcts_self_play.py:113-121).  Nothing goes to global memory during the game
 // except the optional move log; algorithmic HBM traffic is 17 B in + 17-21 B out per game.
 //
-// Canonical rollout arithmetic (identical, bit for bit, in oracle/othello_ref.c):
-//   logit = (S0 + S1) + bias[k], S_c = taps ascending; e = exp32(logit - max_legal); q = floor(e * 2^26) (uint32);
-//   pick the first legal k (ascending) with cum_q > floor((m53 >> 21) * total / 2^32).
+// Canonical rollout arithmetic (identical, bit for bit, in oracle/othello_ref.c).  S_c = sum of the set taps of plane c in
+// ascending tap order, logit = (S0 + S1) + bias[k].
+//   FAST (max|S0| + max|S1| + max|bias| <= 300, i.e. any finite sanely trained rollout net; decided when the weights are loaded):
+//     e_k = (E0 * E1) * EB in double with E_c = canon_exp(S_c), EB = canon_exp(bias[k]) from look-up tables — the softmax
+//     numerator as a product of exponentials, no exp and no max pass in the kernel; cum_k = double running sum over the legal
+//     cells ascending (the reference's cdf is float64 too); pick the first legal k with cum_k > u * total, u = m53 / 2^53.
+//   SAFE (any other weights): e = exp32(logit - max_legal); q = floor(e * 2^26) (uint32); pick the first legal k with
+//     cum_q > floor((m53 >> 21) * total / 2^32).
+#include <math.h>
 #include <string.h>
 
 #include "bitboard.cuh"
@@ -28,15 +34,30 @@ constexpr int kMaxLegal = 32;  // scratch slots per game; more legal moves than 
 
 // ---------------------------------------------------------------- device helpers
 
-// 9-bit pattern of the 3x3 neighbourhood of cell (i, j) on one plane; bit t = ky*3+kx <-> cell (i+ky-1, j+kx-1),
-// off-board cells read 0 (zero padding of the conv).
-__device__ __forceinline__ uint32_t pattern9(u64 bb, int i, int j) {
-    const u64 x = (i == 0) ? (bb << 8) : (bb >> ((i - 1) * 8));  // rows i-1, i, i+1 in bytes 0, 1, 2
-    const uint32_t x3 = (uint32_t)x;
-    // three 10-bit fields, each row shifted left by one so that column -1 is an explicit zero
-    const uint32_t xp = ((x3 & 0xFFu) << 1) | ((x3 & 0xFF00u) << 3) | ((x3 & 0xFF0000u) << 5);
-    const uint32_t t = (xp >> j) & 0x00701C07u;   // 3 bits of each field
-    return ((t * 0x4081u) >> 14) & 0x1FFu;        // gather fields at 0/10/20 into 9 contiguous bits
+// A board plane pre-shifted left by 9 as three 32-bit words: the 19-bit window starting at bit k then holds columns j-1..j+1 of
+// rows i-1, i, i+1 of cell k = i*8 + j at bits 0-2, 8-10, 16-18.  Rows outside the board read 0 (the conv's zero padding); the
+// column that wraps around at j = 0 / j = 7 is removed by colmask[j].
+struct Plane3 {
+    uint32_t w0, w1, w2;
+};
+__device__ __forceinline__ Plane3 plane3(u64 bb) {
+    const uint32_t lo = (uint32_t)bb, hi = (uint32_t)(bb >> 32);
+    Plane3 p;
+    p.w0 = lo << 9;
+    p.w1 = __funnelshift_l(lo, hi, 9);
+    p.w2 = hi >> 23;
+    return p;
+}
+// Byte offset (index * 4) into a 512-entry pattern table: the multiply gathers the three 3-bit fields into 9 contiguous bits
+// (row i+1 -> bits 0-2, row i -> 3-5, row i-1 -> 6-8; all partial products land on disjoint bits, so there are no carries).
+__device__ __forceinline__ uint32_t pat_offset(const Plane3 &p, int k, uint32_t cm) {
+    const bool up = k >= 32;
+    const uint32_t a = up ? p.w1 : p.w0, b = up ? p.w2 : p.w1;
+    const uint32_t t = __funnelshift_r(a, b, (uint32_t)k) & cm;  // shift amount is taken mod 32
+    return ((t * 0x400801u) >> 14) & 0x7FCu;
+}
+__device__ __forceinline__ float table_at(const float *table, uint32_t byte_off) {
+    return *reinterpret_cast<const float *>(reinterpret_cast<const char *>(table) + byte_off);
 }
 
 // exp(x) for x <= 0, every step a single IEEE rounding (same sequence as exp32_neg in the oracle).
@@ -59,25 +80,42 @@ __device__ __forceinline__ float exp32_neg(float x) {
     return __fmul_rn(y, s);
 }
 
-struct PolicySmem {
-    float lut[2][512];
-    float bias[64];
+// Shared-memory copy of the tables one kernel needs: float (lut, bias) for logits and the SAFE sampler, double (elut, ebias)
+// for FAST.  t0 = channel 0 = opponent stones, t1 = channel 1 = mover's stones (game.py:167-174).
+template <class T>
+struct PolicySmemT {
+    T t0[512], t1[512];
+    T tb[64];
+    uint32_t colmask[8];
 };
+typedef PolicySmemT<float> PolicySmem;
+typedef PolicySmemT<double> PolicySmemD;
 
-__device__ __forceinline__ float logit_at(const PolicySmem &w, u64 own, u64 opp, int k) {
-    const int i = k >> 3, j = k & 7;
-    const float s0 = w.lut[0][pattern9(opp, i, j)];  // channel 0 = opponent stones (game.py:167-174)
-    const float s1 = w.lut[1][pattern9(own, i, j)];  // channel 1 = mover's stones
-    return __fadd_rn(__fadd_rn(s0, s1), w.bias[k]);
+__device__ __forceinline__ void load_policy(PolicySmem &w, const RolloutWeights *__restrict__ gw, int tid, int nthreads) {
+    const float *src = &gw->lut[0][0];                                   // [2][512] then [64], contiguous
+    for (int i = tid; i < 1024 + 64; i += nthreads) w.t0[i] = src[i];   // t0, t1, tb are contiguous too
+    if (tid < 8) w.colmask[tid] = gw->colmask[tid];
+}
+__device__ __forceinline__ void load_policy(PolicySmemD &w, const RolloutWeights *__restrict__ gw, int tid, int nthreads) {
+    const double *src = &gw->elut[0][0];
+    for (int i = tid; i < 1024 + 64; i += nthreads) w.t0[i] = src[i];
+    if (tid < 8) w.colmask[tid] = gw->colmask[tid];
+}
+
+__device__ __forceinline__ float logit_at(const PolicySmem &w, const Plane3 &pm, const Plane3 &po, int k) {
+    const uint32_t cm = w.colmask[k & 7];
+    const float s0 = table_at(w.t0, pat_offset(po, k, cm));
+    const float s1 = table_at(w.t1, pat_offset(pm, k, cm));
+    return __fadd_rn(__fadd_rn(s0, s1), w.tb[k]);
 }
 
 __device__ __forceinline__ uint32_t q_of(float e) { return __float2uint_rz(__fmul_rn(e, 67108864.0f)); }  // floor(e * 2^26)
 
-// Samples one legal cell. sa / sc: this thread's columns of the shared scratch (stride kBlock).
-__device__ __forceinline__ int sample_move(const PolicySmem &w, u64 own, u64 opp, u64 legal, u64 m53,
-                                           uint32_t *sa, uint8_t *sc) {
+// SAFE sampler. sa / sc: this thread's columns of the shared scratch (stride kBlock).
+__device__ __noinline__ int sample_move_safe(const PolicySmem &w, u64 own, u64 opp, u64 legal, u64 m53, uint32_t *sa, uint8_t *sc) {
     const int n = __popcll(legal);
     if (n == 1) return __ffsll((long long)legal) - 1;  // same answer as the general path, no arithmetic needed
+    const Plane3 pm = plane3(own), po = plane3(opp);
     const uint32_t u32 = (uint32_t)(m53 >> 21);
     if (n <= kMaxLegal) {
         float mx = -3.0e38f;
@@ -86,22 +124,16 @@ __device__ __forceinline__ int sample_move(const PolicySmem &w, u64 own, u64 opp
             for (int i = 0; i < n; i++) {
                 const int k = __ffsll((long long)m) - 1;
                 m &= m - 1;
-                const float l = logit_at(w, own, opp, k);
+                const float l = logit_at(w, pm, po, k);
                 mx = fmaxf(mx, l);
                 sa[i * kBlock] = __float_as_uint(l);
                 sc[i * kBlock] = (uint8_t)k;
             }
         }
         uint32_t cum = 0;
-        for (int i = 0; i < n; i += 2) {   // two independent exp chains per trip; the odd tail contributes exp(-inf) = 0
-            const bool two = i + 1 < n;
-            const float l0 = __uint_as_float(sa[i * kBlock]);
-            const float l1 = two ? __uint_as_float(sa[(i + 1) * kBlock]) : -3.0e38f;
-            const uint32_t q0 = q_of(exp32_neg(__fsub_rn(l0, mx))), q1 = q_of(exp32_neg(__fsub_rn(l1, mx)));
-            cum += q0;                                  // at most 63 terms of at most 2^26: no overflow
+        for (int i = 0; i < n; i++) {
+            cum += q_of(exp32_neg(__fsub_rn(__uint_as_float(sa[i * kBlock]), mx)));  // at most 63 terms of at most 2^26: no overflow
             sa[i * kBlock] = cum;
-            cum += q1;
-            if (two) sa[(i + 1) * kBlock] = cum;
         }
         const uint32_t T = __umulhi(u32, cum);
         int idx = 0;
@@ -111,20 +143,82 @@ __device__ __forceinline__ int sample_move(const PolicySmem &w, u64 own, u64 opp
     }
     // > kMaxLegal legal moves: unreachable in real play, possible on arbitrary boards. Recompute instead of storing.
     float mx = -3.0e38f;
-    for (u64 m = legal; m; m &= m - 1) mx = fmaxf(mx, logit_at(w, own, opp, __ffsll((long long)m) - 1));
+    for (u64 m = legal; m; m &= m - 1) mx = fmaxf(mx, logit_at(w, pm, po, __ffsll((long long)m) - 1));
     uint32_t total = 0;
     for (u64 m = legal; m; m &= m - 1)
-        total += q_of(exp32_neg(__fsub_rn(logit_at(w, own, opp, __ffsll((long long)m) - 1), mx)));
+        total += q_of(exp32_neg(__fsub_rn(logit_at(w, pm, po, __ffsll((long long)m) - 1), mx)));
     const uint32_t T = __umulhi(u32, total);
     uint32_t cum = 0;
     int last = 0;
     for (u64 m = legal; m; m &= m - 1) {
         last = __ffsll((long long)m) - 1;
-        cum += q_of(exp32_neg(__fsub_rn(logit_at(w, own, opp, last), mx)));
+        cum += q_of(exp32_neg(__fsub_rn(logit_at(w, pm, po, last), mx)));
         if (cum > T) return last;
     }
     return last;
 }
+
+// FAST sampler: softmax numerators as table products, double running sum, no exp and no max pass.
+__device__ __forceinline__ double weight_at(const PolicySmemD &w, const Plane3 &pm, const Plane3 &po, int k) {
+    const uint32_t cm = w.colmask[k & 7];
+    const double e0 = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(w.t0) + 2 * pat_offset(po, k, cm));
+    const double e1 = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(w.t1) + 2 * pat_offset(pm, k, cm));
+    return __dmul_rn(__dmul_rn(e0, e1), w.tb[k]);
+}
+
+__device__ __forceinline__ int sample_move_fast(const PolicySmemD &w, u64 own, u64 opp, u64 legal, u64 m53, double *sa, uint8_t *sc) {
+    const int n = __popcll(legal);
+    if (n == 1) return __ffsll((long long)legal) - 1;
+    const Plane3 pm = plane3(own), po = plane3(opp);
+    const double u = __dmul_rn((double)(long long)m53, 1.1102230246251565e-16);  // m53 / 2^53, exact
+    if (n <= kMaxLegal) {
+        double cum = 0.0;
+        u64 m = legal;
+        for (int i = 0; i < n; i++) {
+            const int k = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            cum = __dadd_rn(cum, weight_at(w, pm, po, k));
+            sa[i * kBlock] = cum;
+            sc[i * kBlock] = (uint8_t)k;
+        }
+        const double T = __dmul_rn(u, cum);
+        int idx = 0;
+        for (int i = 0; i < n; i++) idx += (sa[i * kBlock] <= T) ? 1 : 0;
+        idx = min(idx, n - 1);
+        return (int)sc[idx * kBlock];
+    }
+    double total = 0.0;
+    for (u64 m = legal; m; m &= m - 1) total = __dadd_rn(total, weight_at(w, pm, po, __ffsll((long long)m) - 1));
+    const double T = __dmul_rn(u, total);
+    double cum = 0.0;
+    int last = 0;
+    for (u64 m = legal; m; m &= m - 1) {
+        last = __ffsll((long long)m) - 1;
+        cum = __dadd_rn(cum, weight_at(w, pm, po, last));
+        if (cum > T) return last;
+    }
+    return last;
+}
+
+// The sampler a kernel instantiation uses, with its shared-memory table and scratch types.
+template <bool FAST>
+struct Sampler;
+template <>
+struct Sampler<true> {
+    typedef PolicySmemD Tables;
+    typedef double Scratch;
+    static __device__ __forceinline__ int pick(const Tables &w, u64 own, u64 opp, u64 legal, u64 m53, Scratch *sa, uint8_t *sc) {
+        return sample_move_fast(w, own, opp, legal, m53, sa, sc);
+    }
+};
+template <>
+struct Sampler<false> {
+    typedef PolicySmem Tables;
+    typedef uint32_t Scratch;
+    static __device__ __forceinline__ int pick(const Tables &w, u64 own, u64 opp, u64 legal, u64 m53, Scratch *sa, uint8_t *sc) {
+        return sample_move_safe(w, own, opp, legal, m53, sa, sc);
+    }
+};
 
 // ---------------------------------------------------------------- kernels
 
@@ -146,16 +240,12 @@ struct RolloutArgs {
     const u64 *game_ids;  // nullable: Philox game id of game g (default game_id0 + g)
 };
 
-template <int MODE, bool LOG>
+template <int MODE, bool LOG, bool FAST>
 __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const RolloutWeights *__restrict__ gw) {
-    __shared__ PolicySmem w;
-    __shared__ uint32_t scratch_a[kMaxLegal * kBlock];
+    __shared__ typename Sampler<FAST>::Tables w;
+    __shared__ typename Sampler<FAST>::Scratch scratch_a[kMaxLegal * kBlock];
     __shared__ uint8_t scratch_b[kMaxLegal * kBlock];
-    {
-        const float *src = reinterpret_cast<const float *>(gw);
-        float *dst = reinterpret_cast<float *>(&w);
-        for (int i = threadIdx.x; i < (int)(sizeof(PolicySmem) / sizeof(float)); i += kBlock) dst[i] = src[i];
-    }
+    if (MODE != IAGO_RNG_FORCED) load_policy(w, gw, threadIdx.x, kBlock);
     __syncthreads();
 
     const long long g = (long long)blockIdx.x * kBlock + threadIdx.x;
@@ -167,7 +257,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const Ro
         u64 opp = (color == 1) ? a.p2[g] : a.p1[g];
         int stone_num = __popcll(own | opp);  // 64 - sum(state == 0), mcts_self_play.py:15
         bool pass_flg = false;
-        uint32_t *sa = scratch_a + threadIdx.x;
+        typename Sampler<FAST>::Scratch *sa = scratch_a + threadIdx.x;
         uint8_t *sb = scratch_b + threadIdx.x;
         while (stone_num < 64) {  // mcts_self_play.py:26 — the end test runs once per PAIR of turns
 #pragma unroll 1
@@ -184,7 +274,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const Ro
                             m53 = __double2ull_rz(a.uniforms[g * a.u_stride + placed] * 9007199254740992.0);
                         else
                             m53 = philox_m53(a.seed, gid, (uint32_t)placed, a.stream_id);
-                        k = sample_move(w, own, opp, legal, m53, sa, sb);
+                        k = Sampler<FAST>::pick(w, own, opp, legal, m53, sa, sb);
                     }
                     if (MODE == IAGO_RNG_FORCED && (k < 0 || k > 63)) {
                         stone_num = 64;  // replay stream exhausted: stop this game where it stands
@@ -223,21 +313,17 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const Ro
 }
 
 // One policy draw per board, no board update: Simulate.get_action (mcts_self_play.py:100-110). action -1 = no legal move.
-template <int MODE>
+template <int MODE, bool FAST>
 __global__ void __launch_bounds__(kBlock) rollout_sample_kernel(const u64 *__restrict__ p1, const u64 *__restrict__ p2,
                                                                 const uint8_t *__restrict__ color, long long n,
                                                                 uint32_t stream_id, u64 seed, u64 game_id0, uint32_t draw,
                                                                 const double *__restrict__ uniforms,
                                                                 int8_t *__restrict__ action,
                                                                 const RolloutWeights *__restrict__ gw) {
-    __shared__ PolicySmem w;
-    __shared__ uint32_t scratch_a[kMaxLegal * kBlock];
+    __shared__ typename Sampler<FAST>::Tables w;
+    __shared__ typename Sampler<FAST>::Scratch scratch_a[kMaxLegal * kBlock];
     __shared__ uint8_t scratch_b[kMaxLegal * kBlock];
-    {
-        const float *src = reinterpret_cast<const float *>(gw);
-        float *dst = reinterpret_cast<float *>(&w);
-        for (int i = threadIdx.x; i < (int)(sizeof(PolicySmem) / sizeof(float)); i += kBlock) dst[i] = src[i];
-    }
+    load_policy(w, gw, threadIdx.x, kBlock);
     __syncthreads();
     const long long g = (long long)blockIdx.x * kBlock + threadIdx.x;
     if (g >= n) return;
@@ -247,7 +333,7 @@ __global__ void __launch_bounds__(kBlock) rollout_sample_kernel(const u64 *__res
     if (!legal) { action[g] = -1; return; }
     const u64 m53 = (MODE == IAGO_RNG_UNIFORMS) ? __double2ull_rz(uniforms[g] * 9007199254740992.0)
                                                  : philox_m53(seed, game_id0 + (u64)g, draw, stream_id);
-    action[g] = (int8_t)sample_move(w, own, opp, legal, m53, scratch_a + threadIdx.x, scratch_b + threadIdx.x);
+    action[g] = (int8_t)Sampler<FAST>::pick(w, own, opp, legal, m53, scratch_a + threadIdx.x, scratch_b + threadIdx.x);
 }
 
 __global__ void legal_actions_kernel(const u64 *__restrict__ p1, const u64 *__restrict__ p2,
@@ -276,18 +362,14 @@ __global__ void rollout_logits_kernel(const u64 *__restrict__ p1, const u64 *__r
                                       const uint8_t *__restrict__ color, float *__restrict__ logits, long long n,
                                       const RolloutWeights *__restrict__ gw) {
     __shared__ PolicySmem w;
-    {
-        const float *src = reinterpret_cast<const float *>(gw);
-        float *dst = reinterpret_cast<float *>(&w);
-        for (int i = threadIdx.x; i < (int)(sizeof(PolicySmem) / sizeof(float)); i += blockDim.x) dst[i] = src[i];
-    }
+    load_policy(w, gw, threadIdx.x, blockDim.x);
     __syncthreads();
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per (game, cell)
     const long long g = idx >> 6;
     if (g >= n) return;
     const bool first = color[g] == 1;
     const u64 a = p1[g], b = p2[g];
-    logits[idx] = logit_at(w, first ? a : b, first ? b : a, (int)(idx & 63));
+    logits[idx] = logit_at(w, plane3(first ? a : b), plane3(first ? b : a), (int)(idx & 63));
 }
 
 // Integer-issue roofline denominator: 8 independent rotate+xor chains per thread (SHF + LOP3 on the alu pipe).
@@ -314,33 +396,66 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *out, int iters,
 
 // ---------------------------------------------------------------- host side
 
-static void build_rollout_weights(const float *W, const float *b, RolloutWeights *out) {
-    for (int c = 0; c < 2; c++)
-        for (int pat = 0; pat < 512; pat++) {
-            float acc = 0.0f;
-            for (int t = 0; t < 9; t++)
-                if (pat >> t & 1) acc = acc + W[c * 9 + t];
-            out->lut[c][pat] = acc;
-        }
-    memcpy(out->bias, b, 64 * sizeof(float));
+// exp(x) in double with a fixed operation sequence (Cody-Waite reduction + degree-13 Taylor, Horner), so that this library and
+// the C oracle compute bit-identical tables whatever libm is installed.  Relative error ~2e-16, far below the float rounding.
+static double canon_exp(double x) {
+    const double n = nearbyint(x * 1.4426950408889634);
+    double r = x - n * 0.693147180369123816490;   // ln2 high part (exact product for |n| < 2^20)
+    r = r - n * 1.90821492927058770002e-10;        // ln2 low part
+    double p = 1.0 / 6227020800.0;                 // 1/13!
+    const double inv[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
+                            1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+    for (int i = 0; i < 13; i++) p = p * r + inv[i];
+    return ldexp(p, (int)n);
 }
 
-template <int MODE>
+// Returns true when the FAST sampler applies: every partial product of exp tables lies within e^-300 .. e^300 (no double
+// overflow / underflow; 63 terms of at most e^300 sum to a finite double).
+static bool build_rollout_weights(const float *W, const float *b, RolloutWeights *out) {
+    float amax[2] = {0.0f, 0.0f}, bmax = 0.0f;
+    for (int c = 0; c < 2; c++)
+        for (int idx = 0; idx < 512; idx++) {
+            float acc = 0.0f;
+            for (int t = 0; t < 9; t++)                       // taps ascending: the canonical summation order
+                if (idx >> (6 - 3 * (t / 3) + t % 3) & 1) acc = acc + W[c * 9 + t];
+            out->lut[c][idx] = acc;
+            out->elut[c][idx] = canon_exp((double)acc);
+            if (fabsf(acc) > amax[c]) amax[c] = fabsf(acc);
+        }
+    memcpy(out->bias, b, 64 * sizeof(float));
+    for (int k = 0; k < 64; k++) {
+        out->ebias[k] = canon_exp((double)b[k]);
+        if (fabsf(b[k]) > bmax) bmax = fabsf(b[k]);
+    }
+    for (int j = 0; j < 8; j++) out->colmask[j] = 0x070707u & ~(j == 0 ? 0x010101u : 0u) & ~(j == 7 ? 0x040404u : 0u);
+    const float span = amax[0] + amax[1] + bmax;
+    return span <= 300.0f;   // NaN / inf weights fail the comparison and take the SAFE path
+}
+
+template <int MODE, bool FAST>
 static void launch_rollout(const RolloutArgs &a, const RolloutWeights *w, cudaStream_t s) {
     const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
     if (a.move_log)
-        rollout_kernel<MODE, true><<<grid, kBlock, 0, s>>>(a, w);
+        rollout_kernel<MODE, true, FAST><<<grid, kBlock, 0, s>>>(a, w);
     else
-        rollout_kernel<MODE, false><<<grid, kBlock, 0, s>>>(a, w);
+        rollout_kernel<MODE, false, FAST><<<grid, kBlock, 0, s>>>(a, w);
+}
+
+static void launch_rollout_mode(const RolloutArgs &a, int mode, bool fast, const RolloutWeights *w, cudaStream_t s) {
+    switch (mode) {
+        case IAGO_RNG_PHILOX:
+            fast ? launch_rollout<IAGO_RNG_PHILOX, true>(a, w, s) : launch_rollout<IAGO_RNG_PHILOX, false>(a, w, s);
+            break;
+        case IAGO_RNG_UNIFORMS:
+            fast ? launch_rollout<IAGO_RNG_UNIFORMS, true>(a, w, s) : launch_rollout<IAGO_RNG_UNIFORMS, false>(a, w, s);
+            break;
+        default: launch_rollout<IAGO_RNG_FORCED, true>(a, w, s); break;   // no sampling: FAST is irrelevant
+    }
 }
 
 static int rollout_launch(iago_ctx *ctx, const RolloutArgs &a, int mode, cudaStream_t s) {
     IAGO_CUDA(cudaEventRecord(ctx->ev0, s));
-    switch (mode) {
-        case IAGO_RNG_PHILOX: launch_rollout<IAGO_RNG_PHILOX>(a, ctx->d_rollout, s); break;
-        case IAGO_RNG_UNIFORMS: launch_rollout<IAGO_RNG_UNIFORMS>(a, ctx->d_rollout, s); break;
-        default: launch_rollout<IAGO_RNG_FORCED>(a, ctx->d_rollout, s); break;
-    }
+    launch_rollout_mode(a, mode, ctx->rollout_fast, ctx->d_rollout, s);
     IAGO_CUDA(cudaGetLastError());
     IAGO_CUDA(cudaEventRecord(ctx->ev1, s));
     ctx->timed = true;
@@ -369,7 +484,7 @@ int rollout_launch_ids(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, co
     if (n == 0) return IAGO_OK;
     RolloutArgs a{(const u64 *)p1, (const u64 *)p2, color, n, stream_id, seed, 0, nullptr, 0, nullptr, 0, result,
                   (u64 *)final_p1, (u64 *)final_p2, nullptr, nullptr, nullptr, (const u64 *)game_ids};
-    launch_rollout<IAGO_RNG_PHILOX>(a, ctx->d_rollout, (cudaStream_t)stream);
+    launch_rollout_mode(a, IAGO_RNG_PHILOX, ctx->rollout_fast, ctx->d_rollout, (cudaStream_t)stream);
     IAGO_CUDA(cudaGetLastError());
     return IAGO_OK;
 }
@@ -384,12 +499,13 @@ int iago_load_rollout(iago_ctx *ctx, const float *conv1_W, const float *bias2_b)
     IAGO_REQUIRE(ctx && conv1_W && bias2_b, "NULL argument");
     DeviceGuard guard(ctx->device);
     RolloutWeights *h = new RolloutWeights();
-    build_rollout_weights(conv1_W, bias2_b, h);
+    const bool fast = build_rollout_weights(conv1_W, bias2_b, h);
     cudaError_t e = cudaMemcpyAsync(ctx->d_rollout, h, sizeof *h, cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     delete h;
     IAGO_CUDA(e);
     ctx->rollout_loaded = true;
+    ctx->rollout_fast = fast;
     return IAGO_OK;
 }
 
@@ -446,12 +562,15 @@ int iago_rollout_sample(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, c
     DeviceGuard guard(ctx->device);
     cudaStream_t s = (cudaStream_t)stream;
     const unsigned grid = (unsigned)((n + kBlock - 1) / kBlock);
-    if (rng->mode == IAGO_RNG_UNIFORMS)
-        rollout_sample_kernel<IAGO_RNG_UNIFORMS><<<grid, kBlock, 0, s>>>((const u64 *)p1, (const u64 *)p2, color, n,
-            rng->stream_id, rng->seed, rng->game_id0, draw, rng->uniforms, action, ctx->d_rollout);
-    else
-        rollout_sample_kernel<IAGO_RNG_PHILOX><<<grid, kBlock, 0, s>>>((const u64 *)p1, (const u64 *)p2, color, n,
-            rng->stream_id, rng->seed, rng->game_id0, draw, nullptr, action, ctx->d_rollout);
+#define IAGO_SAMPLE(MODE_, FAST_, U_)                                                                                          \
+    rollout_sample_kernel<MODE_, FAST_><<<grid, kBlock, 0, s>>>((const u64 *)p1, (const u64 *)p2, color, n, rng->stream_id, \
+                                                                  rng->seed, rng->game_id0, draw, U_, action, ctx->d_rollout)
+    if (rng->mode == IAGO_RNG_UNIFORMS) {
+        if (ctx->rollout_fast) IAGO_SAMPLE(IAGO_RNG_UNIFORMS, true, rng->uniforms); else IAGO_SAMPLE(IAGO_RNG_UNIFORMS, false, rng->uniforms);
+    } else {
+        if (ctx->rollout_fast) IAGO_SAMPLE(IAGO_RNG_PHILOX, true, nullptr); else IAGO_SAMPLE(IAGO_RNG_PHILOX, false, nullptr);
+    }
+#undef IAGO_SAMPLE
     IAGO_CUDA(cudaGetLastError());
     return IAGO_OK;
 }

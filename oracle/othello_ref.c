@@ -24,14 +24,19 @@
  * rollout arithmetic"):
  *   logit[k] = (S0 + S1) + b[k];  S_c = sum over taps t = ky*3+kx ascending of W[c][t]*x[c][..]
  *              (x is 0/1 so every product is exact; zero taps are exact no-ops)
- *   e[k]     = exp32(logit[k] - max over LEGAL k)   only at legal cells (the reference's softmax
- *              denominator and its fp32 division cancel in p/sum(p); dropping them changes
- *              p by <= a few ulp_f32, the same size as numpy-vs-libm exp differences)
- *   choice   = fixed-point inverse cdf: q_k = floor(e_k * 2^26) (uint32; e_k <= 1 and at most 63 legal cells, so the
- *              running sum fits 32 bits; exact, associative), first legal k (ascending) with
- *              cum_k > floor(u32 * total / 2^32), u32 = floor(u * 2^32) = m53 >> 21, m53 = floor(u * 2^53)
- *              == searchsorted(cumsum(p)/cumsum(p)[-1], u, 'right') of np.random.choice up to ~n * 2^-26 in cdf
- *              units — the same size as the rounding error of the fp32 exp itself
+ *   Two samplers, chosen per weight set (the same rule as the product, decided from the weights alone):
+ *   FAST  when max|S0| + max|S1| + max|b| <= 300 over all 512 tap patterns (any finite, sanely trained rollout net):
+ *     w[k]   = (E0 * E1) * EB in double,  E_c = canon_exp((double)S_c), EB = canon_exp((double)b[k])
+ *              — the softmax numerator as a product of exponentials; the reference's max subtraction, denominator
+ *              and fp32 division cancel in p/sum(p), and its float64 cdf is float64 here too
+ *     choice = double running sum over the legal cells ascending, first legal k with cum_k > u * total, u = m53 / 2^53
+ *              == searchsorted(cumsum(p)/cumsum(p)[-1], u, 'right') of np.random.choice, up to the rounding error of the
+ *              reference's own fp32 softmax (~1e-9 in cdf units)
+ *     canon_exp = Cody-Waite reduction + degree-13 Taylor in double, fixed operation order (no libm dependence)
+ *   SAFE  otherwise:
+ *     e[k]   = exp32(logit[k] - max over LEGAL k)   only at legal cells
+ *     choice = fixed-point inverse cdf: q_k = floor(e_k * 2^26) (uint32), first legal k (ascending) with
+ *              cum_k > floor(u32 * total / 2^32), u32 = m53 >> 21, m53 = floor(u * 2^53)
  *   exp32    = Cephes-style range reduction + degree-5 polynomial, every step an explicit
  *              fmaf / single rounding, so gcc and nvcc produce identical bits.
  *   uniforms = Philox4x32-10, key = seed, counter = (game_lo, game_hi, draw, stream);
@@ -214,14 +219,81 @@ EXPORT void oracle_rollout_logits(const float *state, int color, const float *W 
     for (int k = 0; k < 64; k++) logits[k] = rollout_logit_at(state, color, W, b, k / 8, k % 8);
 }
 
-/* mcts_self_play.py:100-110 with the uniform supplied by the caller as m53 = floor(u * 2^53).
- * Fixed-point inverse-cdf: q_k = floor(e_k * 2^26), cum in uint32,
- * choice = first legal k (ascending) with cum_k > floor((m53 >> 21) * total / 2^32)
- *        <=> cum_k / total > u, i.e. searchsorted(cdf, u, 'right') of np.random.choice. */
+/* exp(x) in double, fixed operation sequence (see header). */
+static double canon_exp(double x) {
+    const double n = nearbyint(x * 1.4426950408889634);
+    double r = x - n * 0.693147180369123816490;
+    r = r - n * 1.90821492927058770002e-10;
+    double p = 1.0 / 6227020800.0;
+    const double inv[13] = {1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0, 1.0 / 40320.0, 1.0 / 5040.0,
+                            1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0};
+    for (int i = 0; i < 13; i++) p = p * r + inv[i];
+    return ldexp(p, (int)n);
+}
+EXPORT double oracle_canon_exp(double x) { return canon_exp(x); }
+
+/* Per weight set: which sampler applies, and (FAST) the exponentials of every tap-pattern sum, indexed by the pattern with
+ * bit t = tap t = ky*3+kx set when that neighbour holds the plane's stone. */
+typedef struct {
+    int fast;
+    double E[2][512];
+    double EB[64];
+} policy_tables;
+
+static void build_tables(const float *W, const float *b, policy_tables *t) {
+    float amax[2] = {0.0f, 0.0f}, bmax = 0.0f;
+    for (int c = 0; c < 2; c++)
+        for (int pat = 0; pat < 512; pat++) {
+            float acc = 0.0f;
+            for (int k = 0; k < 9; k++) if (pat >> k & 1) acc = acc + W[c * 9 + k];
+            t->E[c][pat] = canon_exp((double)acc);
+            if (fabsf(acc) > amax[c]) amax[c] = fabsf(acc);
+        }
+    for (int k = 0; k < 64; k++) {
+        t->EB[k] = canon_exp((double)b[k]);
+        if (fabsf(b[k]) > bmax) bmax = fabsf(b[k]);
+    }
+    t->fast = (amax[0] + amax[1] + bmax) <= 300.0f;
+}
+
+EXPORT int oracle_policy_is_fast(const float *W, const float *b) {
+    policy_tables t;
+    build_tables(W, b, &t);
+    return t.fast;
+}
+
+/* FAST weight of one cell: the tap patterns are read off the board exactly as rollout_logit_at walks it. */
+static inline double rollout_weight_at(const float *state, int color, const policy_tables *t, int i, int j) {
+    int pat[2] = {0, 0};
+    for (int c = 0; c < 2; c++) {
+        const float who = (c == 0) ? (float)(3 - color) : (float)color;
+        for (int ky = 0; ky < 3; ky++)
+            for (int kx = 0; kx < 3; kx++) {
+                int y = i + ky - 1, x = j + kx - 1;
+                if (is_outside(y, x)) continue;
+                if (state[y * 8 + x] == who) pat[c] |= 1 << (ky * 3 + kx);
+            }
+    }
+    return (t->E[0][pat[0]] * t->E[1][pat[1]]) * t->EB[i * 8 + j];
+}
+
+/* mcts_self_play.py:100-110 with the uniform supplied by the caller as m53 = floor(u * 2^53). */
 static int sample_action(const float *state, int color, const int *actions, int n,
-                         const float *W, const float *b, uint64_t m53) {
+                         const float *W, const float *b, const policy_tables *t, uint64_t m53) {
+    if (n == 1) return actions[0];
+    if (t->fast) {
+        /* only the legal cells survive the mask (mcts_self_play.py:103-105) */
+        double cum[64], total = 0.0;
+        for (int a = 0; a < n; a++) {
+            total = total + rollout_weight_at(state, color, t, actions[a] / 8, actions[a] % 8);
+            cum[a] = total;
+        }
+        const double u = (double)(int64_t)m53 * 1.1102230246251565e-16; /* m53 / 2^53, exact */
+        const double T = u * total;
+        for (int a = 0; a < n; a++) if (cum[a] > T) return actions[a];
+        return actions[n - 1];
+    }
     float logits[64];
-    /* only the legal cells survive the mask (mcts_self_play.py:103-105) */
     for (int a = 0; a < n; a++) logits[actions[a]] = rollout_logit_at(state, color, W, b, actions[a] / 8, actions[a] % 8);
     float m = logits[actions[0]];
     for (int a = 1; a < n; a++) if (logits[actions[a]] > m) m = logits[actions[a]];
@@ -242,7 +314,9 @@ EXPORT int oracle_rollout_sample(const float *state, int color, const float *W, 
     int acts[64];
     int n = oracle_legal_actions(state, color, acts);
     if (n == 0) return -1;
-    return sample_action(state, color, acts, n, W, b, m53_of_double(u));
+    policy_tables t;
+    build_tables(W, b, &t);
+    return sample_action(state, color, acts, n, W, b, &t, m53_of_double(u));
 }
 
 /* ------------------------------------------------------------------ Simulate */
@@ -261,8 +335,8 @@ typedef struct {
 
 /* One Simulate(state)(color): mcts_self_play.py:11-29,113-134. Returns result for `color`. */
 static int simulate_one(float *state, int color, uint64_t game_id, int64_t g, const rng_spec *rng,
-                        const float *W, const float *b, int8_t *moves /*[64] or NULL*/, int *n_moves,
-                        int *n_turns) {
+                        const float *W, const float *b, const policy_tables *tab, int8_t *moves /*[64] or NULL*/,
+                        int *n_moves, int *n_turns) {
     int stone_num = 0;
     for (int k = 0; k < 64; k++) stone_num += (state[k] != 0.0f); /* 64 - sum(state==0) */
     int pass_flg = 0, placed = 0, turns = 0;
@@ -280,7 +354,7 @@ static int simulate_one(float *state, int color, uint64_t game_id, int64_t g, co
                     uint64_t m = rng->mode == RNG_UNIFORMS
                                      ? m53_of_double(rng->uniforms[g * rng->u_stride + placed])
                                      : philox_m53(rng->seed, game_id, (uint32_t)placed, rng->stream);
-                    action = sample_action(state, c, acts, n, W, b, m);
+                    action = sample_action(state, c, acts, n, W, b, tab, m);
                 }
                 oracle_place_stone(state, action, c);
                 if (moves) moves[placed] = (int8_t)action;
@@ -305,7 +379,7 @@ static int simulate_one(float *state, int color, uint64_t game_id, int64_t g, co
 }
 
 typedef struct {
-    float *states; const int *colors; int64_t n; const float *W; const float *b;
+    float *states; const int *colors; int64_t n; const float *W; const float *b; const policy_tables *tab;
     const rng_spec *rng; uint64_t game_id0;
     int8_t *results; int8_t *moves; int32_t *n_moves; int32_t *n_turns;
     atomic_llong *next;
@@ -320,7 +394,7 @@ static void *batch_worker(void *arg) {
         for (int64_t g = g0; g < g1; g++) {
             int nm = 0, nt = 0;
             int r = simulate_one(j->states + g * 64, j->colors[g], j->game_id0 + (uint64_t)g, g, j->rng,
-                                 j->W, j->b, j->moves ? j->moves + g * 64 : 0, &nm, &nt);
+                                 j->W, j->b, j->tab, j->moves ? j->moves + g * 64 : 0, &nm, &nt);
             j->results[g] = (int8_t)r;
             if (j->n_moves) j->n_moves[g] = nm;
             if (j->n_turns) j->n_turns[g] = nt;
@@ -350,7 +424,9 @@ EXPORT int oracle_simulate_batch(float *states, const int *colors, int64_t n, co
     if (threads <= 0) threads = oracle_max_threads();
     if (threads > 256) threads = 256;
     atomic_llong next = 0;
-    batch_job job = {states, colors, n, W, b, &rng, game_id0, results, moves, n_moves, n_turns, &next};
+    policy_tables tab;
+    if (mode != RNG_FORCED) build_tables(W, b, &tab); else tab.fast = 0;
+    batch_job job = {states, colors, n, W, b, &tab, &rng, game_id0, results, moves, n_moves, n_turns, &next};
     if (threads == 1) { batch_worker(&job); return 1; }
     pthread_t th[256];
     int started = 0;

@@ -1,8 +1,10 @@
 // philox.cuh — Philox4x32-10 counter-based uniforms (Salmon et al., Random123), host + device.
 // The reference draws from the global numpy MT19937 (np.random.choice, mcts_self_play.py:106); a batched
 // engine needs a stream that does not depend on scheduling, so games are keyed by their global id:
-//   key = seed (lo, hi), counter = (game_lo, game_hi, draw index, stream id)
-//   m53 = (a >> 5) * 2^26 + (b >> 6)      — numpy's 53-bit recipe; u = m53 / 2^53
+//   key = seed (lo, hi), counter = (game_lo, game_hi, draw index >> 2, stream id)
+//   One Philox block serves four consecutive draws of a game: draw d takes output word d & 3, u = word / 2^32
+//   (m53 = word << 21, so that u = m53 / 2^53 like a replayed double).  2^-32 is finer than the fp32 rounding of the
+//   reference's own softmax, and the rollout kernel runs the 10 rounds once per four stones instead of once per stone.
 #pragma once
 #include <stdint.h>
 
@@ -26,9 +28,9 @@ IAGO_PHD void philox_round(uint32_t &c0, uint32_t &c1, uint32_t &c2, uint32_t &c
     c0 = n0; c1 = l1; c2 = n2; c3 = l0;
 }
 
-// 53-bit integer m with u = m / 2^53.
-IAGO_PHD uint64_t philox_m53(uint64_t seed, uint64_t game, uint32_t draw, uint32_t stream) {
-    uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = draw, c3 = stream;
+// The four output words of the block that serves draws 4*block .. 4*block + 3 of `game`.
+IAGO_PHD void philox_block(uint64_t seed, uint64_t game, uint32_t block, uint32_t stream, uint32_t (&out)[4]) {
+    uint32_t c0 = (uint32_t)game, c1 = (uint32_t)(game >> 32), c2 = block, c3 = stream;
     uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
     for (int r = 0; r < 10; r++) {
@@ -36,7 +38,15 @@ IAGO_PHD uint64_t philox_m53(uint64_t seed, uint64_t game, uint32_t draw, uint32
         k0 += 0x9E3779B9u;
         k1 += 0xBB67AE85u;
     }
-    return ((uint64_t)(c0 >> 5) << 26) | (uint64_t)(c1 >> 6);
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+// 53-bit integer m with u = m / 2^53 for draw number `draw` of `game`.
+IAGO_PHD uint64_t philox_m53(uint64_t seed, uint64_t game, uint32_t draw, uint32_t stream) {
+    uint32_t o[4];
+    philox_block(seed, game, draw >> 2, stream, o);
+    const uint32_t w = (draw & 2) ? ((draw & 1) ? o[3] : o[2]) : ((draw & 1) ? o[1] : o[0]);
+    return (uint64_t)w << 21;
 }
 
 }  // namespace iago

@@ -173,17 +173,35 @@ __device__ __forceinline__ int sample_move_fast(const PolicySmemD &w, u64 own, u
     const double u = __dmul_rn((double)(long long)m53, 1.1102230246251565e-16);  // m53 / 2^53, exact
     if (n <= kMaxLegal) {
         double cum = 0.0;
-        u64 m = legal;
+        uint32_t lo = (uint32_t)legal, hi = (uint32_t)(legal >> 32);
         for (int i = 0; i < n; i++) {
-            const int k = __ffsll((long long)m) - 1;
-            m &= m - 1;
-            cum = __dadd_rn(cum, weight_at(w, pm, po, k));
+            // lowest set bit of (hi:lo) with 32-bit operations; `up` also selects the words of the pre-shifted planes
+            const bool up = lo == 0;
+            const uint32_t wd = up ? hi : lo;
+            const int sh = __ffs((int)wd) - 1, k = sh + (up ? 32 : 0);
+            const uint32_t rest = wd & (wd - 1);
+            lo = up ? 0u : rest;
+            hi = up ? rest : hi;
+            const uint32_t cm = w.colmask[sh & 7];
+            const uint32_t t0 = __funnelshift_r(up ? po.w1 : po.w0, up ? po.w2 : po.w1, (uint32_t)sh) & cm;
+            const uint32_t t1 = __funnelshift_r(up ? pm.w1 : pm.w0, up ? pm.w2 : pm.w1, (uint32_t)sh) & cm;
+            const double e0 = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(w.t0) + (((t0 * 0x400801u) >> 13) & 0xFF8u));
+            const double e1 = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(w.t1) + (((t1 * 0x400801u) >> 13) & 0xFF8u));
+            cum = __dadd_rn(cum, __dmul_rn(__dmul_rn(e0, e1), w.tb[k]));
             sa[i * kBlock] = cum;
             sc[i * kBlock] = (uint8_t)k;
         }
         const double T = __dmul_rn(u, cum);
+#ifdef IAGO_FIND_LINEAR
         int idx = 0;
         for (int i = 0; i < n; i++) idx += (sa[i * kBlock] <= T) ? 1 : 0;
+#else
+        int idx = 0, end = n;                  // number of cum_i <= T: the running sums are non-decreasing, so bisect
+        while (idx < end) {
+            const int mid = (idx + end) >> 1;
+            if (sa[mid * kBlock] <= T) idx = mid + 1; else end = mid;
+        }
+#endif
         idx = min(idx, n - 1);
         return (int)sc[idx * kBlock];
     }
@@ -259,6 +277,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const Ro
         bool pass_flg = false;
         typename Sampler<FAST>::Scratch *sa = scratch_a + threadIdx.x;
         uint8_t *sb = scratch_b + threadIdx.x;
+        uint32_t rnd[4] = {0, 0, 0, 0};  // the Philox block serving draws 4*(placed >> 2) .. + 3
         while (stone_num < 64) {  // mcts_self_play.py:26 — the end test runs once per PAIR of turns
 #pragma unroll 1
             for (int half = 0; half < 2; half++) {
@@ -272,8 +291,11 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const Ro
                         u64 m53;
                         if (MODE == IAGO_RNG_UNIFORMS)
                             m53 = __double2ull_rz(a.uniforms[g * a.u_stride + placed] * 9007199254740992.0);
-                        else
-                            m53 = philox_m53(a.seed, gid, (uint32_t)placed, a.stream_id);
+                        else {
+                            if ((placed & 3) == 0) philox_block(a.seed, gid, (uint32_t)placed >> 2, a.stream_id, rnd);
+                            const uint32_t wd = (placed & 2) ? ((placed & 1) ? rnd[3] : rnd[2]) : ((placed & 1) ? rnd[1] : rnd[0]);
+                            m53 = (u64)wd << 21;
+                        }
                         k = Sampler<FAST>::pick(w, own, opp, legal, m53, sa, sb);
                     }
                     if (MODE == IAGO_RNG_FORCED && (k < 0 || k > 63)) {

@@ -39,8 +39,8 @@
  *              cum_k > floor(u32 * total / 2^32), u32 = m53 >> 21, m53 = floor(u * 2^53)
  *   exp32    = Cephes-style range reduction + degree-5 polynomial, every step an explicit
  *              fmaf / single rounding, so gcc and nvcc produce identical bits.
- *   uniforms = Philox4x32-10, key = seed, counter = (game_lo, game_hi, draw, stream);
- *              u = ((a >> 5) * 2^26 + (b >> 6)) / 2^53   (numpy's 53-bit recipe)
+ *   uniforms = Philox4x32-10, key = seed, counter = (game_lo, game_hi, draw >> 2, stream);
+ *              draw d uses output word d & 3: u = word / 2^32 (one block serves four consecutive draws)
  */
 #include <math.h>
 #include <stdint.h>
@@ -155,9 +155,10 @@ EXPORT void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], u
 
 static inline uint64_t philox_m53(uint64_t seed, uint64_t game, uint32_t draw, uint32_t stream) {
     uint32_t o[4];
-    philox4x32_10((uint32_t)game, (uint32_t)(game >> 32), draw, stream,
+    /* one block serves four consecutive draws: draw d takes word d & 3 of block d >> 2; u = word / 2^32 */
+    philox4x32_10((uint32_t)game, (uint32_t)(game >> 32), draw >> 2, stream,
                   (uint32_t)seed, (uint32_t)(seed >> 32), o);
-    return ((uint64_t)(o[0] >> 5) << 26) | (uint64_t)(o[1] >> 6);
+    return (uint64_t)o[draw & 3] << 21;
 }
 
 static inline double philox_uniform(uint64_t seed, uint64_t game, uint32_t draw, uint32_t stream) {

@@ -52,8 +52,9 @@ def test_philox_known_answers(cref):
     assert cref.philox([0xffffffff] * 4, [0xffffffff] * 2) == [0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
     assert cref.philox([0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344], [0xa4093822, 0x299f31d0]) == \
         [0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1]
-    a, b, _, _ = cref.philox([5, 0, 7, 0], [11, 0])
-    assert cref.philox_uniform(11, 5, 7, 0) == ((a >> 5) * 67108864.0 + (b >> 6)) / 9007199254740992.0
+    # the engine's stream: draw d of a game = word d & 3 of the block with counter (game_lo, game_hi, d >> 2, stream); u = word / 2^32
+    words = cref.philox([5, 0, 7 >> 2, 0], [11, 0])
+    assert cref.philox_uniform(11, 5, 7, 0) == words[7 & 3] / 4294967296.0
 
 
 def test_exp32_accuracy(cref):

@@ -373,7 +373,8 @@ def run_ours(args, rank, world, local_rank):
         if world == 1 and not args.no_cpu:
             line["cpu_baseline"] = cpu_baseline_block()
     extra = {}
-    for name, fn in (("selfplay", section_selfplay), ("mcts", section_mcts), ("reinforce", section_reinforce)):
+    for name, fn in (("selfplay", section_selfplay), ("mcts", section_mcts), ("reinforce", section_reinforce),
+                     ("valuegen", section_valuegen)):
         if name in args.sections:
             try:
                 extra[name] = fn(eng, args, rank, world, dev, dist, barrier)
@@ -533,6 +534,50 @@ def section_reinforce(eng, args, rank, world, dev, dist, barrier):
             "allreduce_bytes_per_update": (960768 + 2) * 4}
 
 
+def section_valuegen(eng, args, rank, world, dev, dist, barrier):
+    """value-data generation (value_self_play.SelfPlay x gen_value_data.py), lockstep batch per GPU."""
+    import numpy as np
+    import torch
+    from iago_b200 import Rng
+    from iago_b200.engine import STREAM_VALUEGEN
+    n = args.valuegen_games
+    eng.load_net(0, model_path("sl_model.npz"))
+    eng.load_net(2, model_path("rl_model.npz"))
+    stop = torch.from_numpy(np.random.RandomState(args.seed + rank).randint(4, 64, size=n).astype(np.int32)).to(dev)
+    eng.value_selfplay(0, 2, stop[:2048].contiguous(), rng=Rng.philox(seed=1, stream_id=STREAM_VALUEGEN))   # warm-up
+    barrier()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    res = eng.value_selfplay(0, 2, stop, rng=Rng.philox(seed=args.seed, game_id0=rank * n, stream_id=STREAM_VALUEGEN))
+    b.record()
+    barrier()
+    tt = torch.tensor([a.elapsed_time(b) / 1e3], dtype=torch.float64, device=dev)
+    usable = (res["rec_action"] >= 0).sum().to(torch.int64).reshape(1)
+    if dist is not None:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dist.all_reduce(usable, op=dist.ReduceOp.SUM)
+    t = float(tt[0])
+    out = {"metric": "value_records_per_s", "value": n * world / t, "unit": "games/s", "ms_per_step": 1e3 * t,
+           "config": {"workload": "value_self_play.SelfPlay(stop_num ~ randint(4, 64)): sl_model.npz to stop_num, one random move, "
+                                  "rl_model.npz to the end (gen_value_data.py)", "games_per_step_per_gpu": n},
+           "records_with_a_move": int(usable[0]), "turns": res["stats"]["turns"], "trunk_launches": res["stats"]["forwards"]}
+    if rank == 0 and world == 1 and not args.no_cpu:
+        import time
+        from oracle import nets, valuegen_ref
+        psl, prl = nets.load_params(model_path("sl_model.npz")), nets.load_params(model_path("rl_model.npz"))
+        f = lambda p: (lambda st, c: nets.sl_logits(p, nets.planes_from_state(st[None], c))[0])
+        rs = np.random.RandomState(1)
+        t0 = time.perf_counter()
+        k = 3
+        for g in range(k):
+            valuegen_ref.play(int(rs.randint(4, 64)), f(psl), f(prl), rs.random_sample(200))
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": k / dt, "unit": "games/s", "cores": 1, "kind": "port",
+                               "sample": f"{k} games of oracle/valuegen_ref.py with the fp32 numpy nets (the reference file itself is dead at "
+                                         "HEAD: it imports a deleted module and its softmax overflows on sl_model.npz)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -544,7 +589,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--reinforce-games", type=int, default=2048)
     ap.add_argument("--reinforce-steps", type=int, default=1)
-    ap.add_argument("--sections", default="rollout,selfplay,mcts,reinforce", help="extra sections to run after the headline rollout bench")
+    ap.add_argument("--valuegen-games", type=int, default=16384)
+    ap.add_argument("--sections", default="rollout,selfplay,mcts,reinforce,valuegen", help="extra sections to run after the headline rollout bench")
     ap.add_argument("--selfplay-games", type=int, default=16384)
     ap.add_argument("--selfplay-steps", type=int, default=2)
     ap.add_argument("--mcts-trees", type=int, default=256)

@@ -44,6 +44,7 @@ SIGNATURES = {
     "iago_value_forward": [_P, C.c_int, _P, _P, _P, C.c_int64, _P, C.c_int, _P],
     "iago_selfplay": [_P, C.c_int, C.c_int, C.c_int64, _P, _P, C.c_int, C.c_int, C.POINTER(IagoRng), _P, _P, _P, _P, _P, _P,
                       _P, C.c_int, _P, _P, _P],
+    "iago_value_selfplay": [_P, C.c_int, C.c_int, C.c_int64, _P, C.c_int, C.POINTER(IagoRng), _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
     "iago_env_step": [_P, C.c_int, C.c_int, C.c_int64, _P, _P, _P, _P, _P, C.POINTER(IagoRng), _P, _P, _P, _P, _P],
     "iago_sample_unmasked": [_P, _P, _P, _P, C.c_int64, C.POINTER(IagoRng), _P, _P, _P, _P],
     "iago_sample_masked": [_P, _P, _P, _P, C.c_int64, C.POINTER(IagoRng), _P, _P, _P],

@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libiago_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC,-fvisibility=hidden,-Wall", "--expt-relaxed-constexpr"] + os.environ.get("IAGO_NVCC_EXTRA", "").split()
 
 
 def sources():

@@ -29,6 +29,7 @@ int ensure_staging(iago_ctx *ctx, size_t bytes) {
 
 void trunk_destroy(iago_ctx *ctx);
 void selfplay_destroy(iago_ctx *ctx);
+void valuegen_destroy(iago_ctx *ctx);
 
 }  // namespace iago
 
@@ -74,6 +75,7 @@ int iago_ctx_destroy(iago_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     iago::trunk_destroy(ctx);
     iago::selfplay_destroy(ctx);
+    iago::valuegen_destroy(ctx);
     if (ctx->stage.host) cudaFreeHost(ctx->stage.host);
     if (ctx->stage.dev) cudaFree(ctx->stage.dev);
     cudaFree(ctx->d_rollout);

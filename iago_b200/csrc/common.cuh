@@ -43,6 +43,7 @@ struct iago_ctx {
     void *trunk = nullptr;     // conv-net state (trunk.cu)
     void *selfplay = nullptr;  // self-play workspace (selfplay.cu)
     void *mcts = nullptr;      // search trees (mcts.cu)
+    void *valuegen = nullptr;  // value-data generation workspace (valuegen.cu)
 };
 
 #define IAGO_CUDA(expr)                                                                      \
@@ -85,6 +86,7 @@ int rollout_launch_ids(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, co
                        uint64_t seed, uint32_t stream_id, const uint64_t *game_ids, int8_t *result, uint64_t *final_p1,
                        uint64_t *final_p2, void *stream);
 bool trunk_slot_holds(iago_ctx *ctx, int slot, int kind);
+void valuegen_destroy(iago_ctx *ctx);
 // trunk.cu, backward data-gradient chain of the SLPolicy trunk on the tensor cores (used by reinforce.cu):
 //   pack: W[l] (l = 1..7, device fp32 [128][cin_l][3][3]) -> bf16 hi/lo weight units in `blob` + the chain descriptor in `desc_dev`
 //   launch: dy_in = gradient w.r.t. block 8's output [n][128][64]; chain layer i (i = 0..6) writes the gradient w.r.t. the output

@@ -192,16 +192,11 @@ __device__ __forceinline__ int sample_move_fast(const PolicySmemD &w, u64 own, u
             sc[i * kBlock] = (uint8_t)k;
         }
         const double T = __dmul_rn(u, cum);
-#ifdef IAGO_FIND_LINEAR
-        int idx = 0;
-        for (int i = 0; i < n; i++) idx += (sa[i * kBlock] <= T) ? 1 : 0;
-#else
         int idx = 0, end = n;                  // number of cum_i <= T: the running sums are non-decreasing, so bisect
         while (idx < end) {
             const int mid = (idx + end) >> 1;
             if (sa[mid * kBlock] <= T) idx = mid + 1; else end = mid;
         }
-#endif
         idx = min(idx, n - 1);
         return (int)sc[idx * kBlock];
     }

@@ -15,7 +15,7 @@ from . import _lib
 from ._lib import IagoError, IagoRng, check
 
 RNG_PHILOX, RNG_UNIFORMS, RNG_FORCED = 0, 1, 2
-STREAM_ROLLOUT, STREAM_SELFPLAY, STREAM_MCTS, STREAM_ENV = 0, 1, 2, 3
+STREAM_ROLLOUT, STREAM_SELFPLAY, STREAM_MCTS, STREAM_ENV, STREAM_VALUEGEN = 0, 1, 2, 3, 4
 
 
 @dataclasses.dataclass
@@ -247,6 +247,28 @@ class Engine:
                                      _ptr(out["rec_action"]), _ptr(out["n_rec"]), int(rec_cap), _ptr(out["moves"]),
                                      C.cast(stats, C.c_void_p), self._stream(stream)))
         out["stats"] = dict(turn_pairs=int(stats[0]), forwards=int(stats[1]))
+        return out
+
+    def value_selfplay(self, slot_sl, slot_rl, stop_num, precision=3, rng: Optional[Rng] = None, stream=None):
+        """n lockstep value_self_play.SelfPlay(stop_num[g])() games (stop_num: int32 CUDA tensor). Returns a dict of CUDA tensors:
+        rec_own / rec_opp (the recorded position, mover's view), rec_color, rec_action (the random move, -1 = none), result,
+        final_p1 / final_p2, draws (+ 'stats' host ints)."""
+        torch = _torch()
+        rng = rng or Rng(stream_id=STREAM_VALUEGEN)
+        dev = self._dev()
+        assert stop_num.is_cuda and stop_num.dtype == torch.int32 and stop_num.is_contiguous()
+        n = stop_num.numel()
+        i64 = lambda: torch.empty(n, dtype=torch.int64, device=dev)
+        out = dict(rec_own=i64(), rec_opp=i64(), rec_color=torch.empty(n, dtype=torch.uint8, device=dev),
+                   rec_action=torch.empty(n, dtype=torch.int8, device=dev), result=torch.empty(n, dtype=torch.int8, device=dev),
+                   final_p1=i64(), final_p2=i64(), draws=torch.empty(n, dtype=torch.int32, device=dev))
+        stats = (C.c_int64 * 2)()
+        r, keep = self._rng_struct(rng, n, host=False)
+        check(self.lib.iago_value_selfplay(self.ctx, int(slot_sl), int(slot_rl), n, _ptr(stop_num), int(precision), C.byref(r),
+                                           _ptr(out["rec_own"]), _ptr(out["rec_opp"]), _ptr(out["rec_color"]), _ptr(out["rec_action"]),
+                                           _ptr(out["result"]), _ptr(out["final_p1"]), _ptr(out["final_p2"]), _ptr(out["draws"]),
+                                           C.cast(stats, C.c_void_p), self._stream(stream)))
+        out["stats"] = dict(turns=int(stats[0]), forwards=int(stats[1]))
         return out
 
     def env_step(self, slot_opponent, p1, p2, stone_num, pass_flg, action, draws, rng: Optional[Rng] = None, precision=3,

@@ -241,6 +241,20 @@ IAGO_API int iago_mcts_export_tree(iago_mcts *m, int tree, int32_t capacity, int
 /* Expansions skipped because a tree's pool was full during the last search (0 in a correctly sized pool). */
 IAGO_API int iago_mcts_overflows(iago_mcts *m, int64_t *count);
 
+/* ---- value-network training data: value_self_play.py:12-59 driven by gen_value_data.py:12-19 ----
+ * n lockstep SelfPlay(stop_num[g])() games: the policy in slot_sl plays both colours while stone_num < stop_num[g]; the
+ * side to move then records the board from its own view (rec_own = its stones, rec_opp = the other side's; the reference
+ * stores them as 2 and 1) and plays ONE uniformly random legal move; the policy in slot_rl plays the game out; result[g] =
+ * judge(mover) in {1, 0, -1}, or -1 with rec_action -1 when the mover had no legal move at that point (value_self_play.py:47-48).
+ * Sampling is get_position's (:131-149): softmax over all 64 net outputs, one uniform, an illegal cell replaced by
+ * positions[floor(u' * len)] with the game's next uniform.  Uniform k of game g: Philox (seed, game_id0 + g, k, stream_id) or
+ * uniforms[g * u_stride + k].  All arrays are DEVICE arrays [n]; draws[g] = uniforms consumed; stats (HOST, nullable) =
+ * {turns, trunk launches}.  Synchronises the stream. */
+IAGO_API int iago_value_selfplay(iago_ctx *ctx, int slot_sl, int slot_rl, int64_t n, const int32_t *stop_num, int precision,
+                                 const iago_rng *rng, uint64_t *rec_own, uint64_t *rec_opp, uint8_t *rec_color,
+                                 int8_t *rec_action, int8_t *result, uint64_t *final_p1, uint64_t *final_p2, int32_t *draws,
+                                 int64_t *stats, void *stream);
+
 /* ---- REINFORCE update of the SL-size policy: src/train_rl.py:55-66 (K6) ----
  * A trainer owns the learner's fp32 parameters (flat, iago_load_net order, kind 0), Adam moments and the activation
  * workspace for up to max_positions positions per call. */

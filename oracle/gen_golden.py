@@ -282,6 +282,87 @@ def gen_env(mods, out, seed0):
     out["env"] = {k: np.array(v) for k, v in rec.items()}
 
 
+def gen_valuegen(mods, out, seed0, n_games=24):
+    """value_self_play.SelfPlay (UNMODIFIED).  The file is dead at the reference HEAD: it imports a module `SLPolicy` that no
+    longer exists and loads un-prefixed archives into L.Classifier.  Stand-ins, none of which touch the game logic:
+      * module SLPolicy with SLPolicyNet = network.SLPolicy minus its final softmax (the file applies its own softmax to the
+        net output, value_self_play.py:142) — F.softmax is the identity while that net runs;
+      * serializers.load_npz into the Classifier's predictor (rl_model.npz carries the 'predictor/' prefix, sl_model.npz not);
+      * chainer.functions.loss.softmax_cross_entropy importable;
+      * random.choice(seq) -> seq[floor(u * len)] with u the NEXT np.random uniform, so one recorded stream drives the game.
+    Games in which the reference's un-stabilised softmax overflows (np.random.choice raises on NaN) are skipped."""
+    import importlib
+    import random
+    import sys
+    import types
+    net, chainer = mods["network"], mods["chainer"]
+
+    log = []
+
+    class SLPolicyNet(net.SLPolicy):
+        def __call__(self, x):
+            keep = net.F.softmax
+            net.F.softmax = lambda h, axis=1: h
+            try:
+                y = super().__call__(x)
+            finally:
+                net.F.softmax = keep
+            log.append(np.array(y.data, np.float32).reshape(64))
+            return y
+
+    sys.modules["SLPolicy"] = types.SimpleNamespace(SLPolicyNet=SLPolicyNet)
+    loss = types.ModuleType("chainer.functions.loss")
+    sce = types.ModuleType("chainer.functions.loss.softmax_cross_entropy")
+    sce.softmax_cross_entropy = lambda *a, **k: None
+    loss.softmax_cross_entropy = sce
+    sys.modules["chainer.functions.loss"] = loss
+    sys.modules["chainer.functions.loss.softmax_cross_entropy"] = sce
+    ser = chainer.serializers
+    real_load = ser.load_npz
+
+    def load_npz(path, obj, *a, **k):
+        target = getattr(obj, "predictor", obj)
+        with np.load(path) as z:
+            pre = "predictor/" if any(f.startswith("predictor/") for f in z.files) else ""
+        return real_load(path, target, pre) if pre else real_load(path, target)
+
+    vsp = importlib.import_module("value_self_play")
+    vsp.serializers.load_npz = load_npz
+    real_choice = random.choice
+    random.choice = lambda seq: seq[min(int(np.random.random_sample() * len(seq)), len(seq) - 1)]
+    rec = dict(seed=[], stop_num=[], state=[], result=[], uniforms=[], n_draws=[], final=[], logits=[], n_logits=[])
+    skipped = 0
+    try:
+        g = 0
+        while len(rec["seed"]) < n_games:
+            seed = seed0 + g
+            g += 1
+            stop = 4 + (seed * 7) % 60
+            np.random.seed(seed)
+            del log[:]
+            sp = vsp.SelfPlay(stop)
+            try:
+                state, result = sp()
+            except ValueError:
+                skipped += 1
+                continue
+            nxt = np.random.random_sample()
+            u = np.random.RandomState(seed).random_sample(512)
+            nd = int(np.argmax(u == nxt))
+            assert u[nd] == nxt
+            lg = np.zeros((64, 64), np.float32)
+            lg[:len(log)] = np.array(log)
+            for k, v in dict(seed=seed, stop_num=stop, state=u8(state).reshape(64), result=result, uniforms=u[:160], n_draws=nd,
+                             final=u8(sp.state).reshape(64), logits=lg,
+                             n_logits=len(log)).items():
+                rec[k].append(v)
+    finally:
+        random.choice = real_choice
+        vsp.serializers.load_npz = real_load
+    print("valuegen: skipped", skipped, "games whose softmax overflowed in the reference")
+    out["valuegen"] = {k: np.array(v) for k, v in rec.items()}
+
+
 def flatten_tree(root):
     """BFS; children in dict insertion order (= ascending action, as expand() inserts them)."""
     nodes, parent, action = [root], [-1], [0]
@@ -376,6 +457,8 @@ def main():
         gen_selfplay(mods, out, 777); print("selfplay done", flush=True)
     if not only or "env" in only:
         gen_env(mods, out, 4242); print("env done", flush=True)
+    if not only or "valuegen" in only:
+        gen_valuegen(mods, out, 9090); print("valuegen done", flush=True)
     if not only or "mcts" in only:
         gen_mcts(mods, out, out["simulate"]); print("mcts done", flush=True)
     os.makedirs(outdir, exist_ok=True)

@@ -363,6 +363,34 @@ def gen_valuegen(mods, out, seed0, n_games=24):
     out["valuegen"] = {k: np.array(v) for k, v in rec.items()}
 
 
+def gen_load(out, seed=31337, n_lines=140):
+    """load.py (UNMODIFIED) main() on a synthetic policy_data/txt/data.txt: the shuffled npy files it writes."""
+    import importlib.util
+    import tempfile
+    rs = np.random.RandomState(seed)
+    lines = []
+    for i in range(n_lines):
+        cells = rs.randint(0, 3, size=64)
+        lines.append(" ".join(str(int(c)) for c in cells) + f" {rs.randint(1, 9)} {rs.randint(1, 9)} {'BW'[rs.randint(2)]}\n")
+    root = tempfile.mkdtemp()
+    os.makedirs(os.path.join(root, "policy_data", "txt")); os.makedirs(os.path.join(root, "policy_data", "npy")); os.makedirs(os.path.join(root, "run"))
+    with open(os.path.join(root, "policy_data", "txt", "data.txt"), "w") as f:
+        f.writelines(lines)
+    spec = importlib.util.spec_from_file_location("ref_load", os.path.join(ref_harness.REF, "load.py"))
+    ref = importlib.util.module_from_spec(spec); spec.loader.exec_module(ref)
+    cwd = os.getcwd()
+    os.chdir(os.path.join(root, "run"))
+    try:
+        np.random.seed(seed)
+        ref.main()
+    finally:
+        os.chdir(cwd)
+    ld = lambda n: np.load(os.path.join(root, "policy_data", "npy", n))
+    out["load"] = dict(seed=np.array(seed), lines=np.array(lines), states=ld("states.npy").astype(np.int8), actions=ld("actions.npy"),
+                       states_test=ld("states_test.npy").astype(np.int8), actions_test=ld("actions_test.npy"),
+                       rotate=ref.rotate(np.arange(64.0)), transpose=ref.transpose(np.arange(64.0)))
+
+
 def flatten_tree(root):
     """BFS; children in dict insertion order (= ascending action, as expand() inserts them)."""
     nodes, parent, action = [root], [-1], [0]
@@ -459,6 +487,8 @@ def main():
         gen_env(mods, out, 4242); print("env done", flush=True)
     if not only or "valuegen" in only:
         gen_valuegen(mods, out, 9090); print("valuegen done", flush=True)
+    if not only or "load" in only:
+        gen_load(out); print("load done", flush=True)
     if not only or "mcts" in only:
         gen_mcts(mods, out, out["simulate"]); print("mcts done", flush=True)
     os.makedirs(outdir, exist_ok=True)

@@ -529,7 +529,7 @@ def section_reinforce(eng, args, rank, world, dev, dist, barrier):
     return {"metric": "reinforce_games_per_s", "value": steps * n * world / t, "unit": "games/s", "ms_per_update": 1e3 * t / steps,
             "config": {"workload": "REINFORCE sets: self-play (sampled, odd games head/tail switched) + gradient + all-reduce + Adam/WD, "
                                    "rl_model.npz learner vs RL/model0.npz (BASELINE configs[4])", "games_per_update_per_gpu": n,
-                       "updates": steps, "gradient_arithmetic": "tcgen05: fp16 hi/lo forward, fused bf16 hi/lo data-gradient chain, bf16 weight-gradient GEMMs; fp32 accumulate"},
+                       "updates": steps, "gradient_arithmetic": "tcgen05: fp16 hi/lo forward, fused bf16 hi/lo data-gradient chain, fp16 (scaled, hi/lo dY) weight-gradient GEMMs; fp32 accumulate"},
             "positions_per_update": positions / steps, "last": stats[-1],
             "allreduce_bytes_per_update": (960768 + 2) * 4}
 

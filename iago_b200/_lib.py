@@ -41,6 +41,7 @@ SIGNATURES = {
     "iago_load_net": [_P, C.c_int, C.c_int, _P, C.c_int64],
     "iago_policy_forward": [_P, C.c_int, _P, _P, _P, C.c_int64, _P, C.c_int, C.c_int, _P],
     "iago_policy_forward_acts": [_P, C.c_int, _P, _P, _P, C.c_int64, _P, _P, C.c_int, _P],
+    "iago_value_forward_acts": [_P, C.c_int, _P, _P, _P, C.c_int64, _P, _P, C.c_int, _P],
     "iago_value_forward": [_P, C.c_int, _P, _P, _P, C.c_int64, _P, C.c_int, _P],
     "iago_selfplay": [_P, C.c_int, C.c_int, C.c_int64, _P, _P, C.c_int, C.c_int, C.POINTER(IagoRng), _P, _P, _P, _P, _P, _P,
                       _P, C.c_int, _P, _P, _P],
@@ -65,6 +66,16 @@ SIGNATURES = {
     "iago_reinforce_set_state": [_P, _P, _P, _P, C.c_int64],
     "iago_reinforce_sync_slot": [_P, C.c_int],
     "iago_reinforce_set_option": [_P, C.c_int],
+    "iago_trainer_create": [_P, C.c_int, _P, C.c_int64, C.c_int, C.POINTER(_P)],
+    "iago_value_grad": [_P, _P, _P, _P, C.c_int64, _P, C.c_int, C.c_double, C.c_uint64, C.c_uint64, _P, _P, _P],
+    "iago_policy_eval": [_P, _P, C.c_int, _P, C.c_int64, _P, _P],
+    "iago_value_eval": [_P, _P, _P, C.c_int64, _P, _P],
+    "iago_rollout_trainer_create": [_P, _P, _P, C.POINTER(_P)],
+    "iago_rollout_trainer_destroy": [_P],
+    "iago_rollout_trainer_grad": [_P, _P, _P, _P, C.c_int64, _P, C.c_int, _P],
+    "iago_rollout_trainer_adam_step": [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P],
+    "iago_rollout_trainer_get_state": [_P, _P, C.POINTER(C.c_int64)],
+    "iago_rollout_trainer_set_state": [_P, _P, C.c_int64],
     "iago_measure_int_peak": [_P, C.c_int, C.POINTER(C.c_double)],
     "iago_last_kernel_ms": [_P, C.POINTER(C.c_float)],
 }

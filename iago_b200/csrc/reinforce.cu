@@ -23,8 +23,10 @@
 
 #include "bitboard.cuh"
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
+#include "philox.cuh"
 #include "tc.cuh"
 
 namespace iago {
@@ -212,7 +214,8 @@ __global__ void __launch_bounds__(256) wgrad3x3_kernel(const float *__restrict__
 // ---------------------------------------------------------------- weight gradient on the tensor cores (layers with Cout = 128)
 // dW[o][c][tap] = sum_{p, cell} dY[p][o][cell] * X[p][c][cell + tap] as 9 GEMMs D_tap[o][c] += A[o][k] * B_tap[c][k], k = (p, cell).
 // One CTA owns one kernel row ky (3 taps, 3 x N fp32 TMEM columns) and one slice of positions; per position (one pipeline
-// stage, K = 64) the producer warps read dY and X (fp32, [p][ch][64]) once, round to bf16 and lay them out as no-swizzle
+// stage, K = 64) the producer warps read dY and X (fp32, [p][ch][64]) once, convert to fp16 (dY scaled by a power of two taken from the
+// layer's max |dY| and split into hi + lo parts; X as is: activations are bounded) — bf16 operands were measured at 1e-2 of max|g| — and lay them out as no-swizzle
 // K-major core matrices: A = [o group][board row][o % 8][8 cells]; B = three column-shifted copies (kx = 0, 1, 2 <-> dx = -1, 0, +1,
 // zero filled) of [c group][padded row 0..9][c % 8][8 cells], so that a tap is just a descriptor start address: copy kx, padded
 // row y + ky.  One thread issues 4 K=16 MMAs per tap and stage; accumulators stay in TMEM until the slice is done.
@@ -220,20 +223,38 @@ __global__ void __launch_bounds__(256) wgrad3x3_kernel(const float *__restrict__
 constexpr int kWgThreads = 288;               // warps 0-7 producers (0-3 also epilogue), warp 8 = MMA issuer
 constexpr int kWgATile = 16 * 8 * 128;        // dY tile: 16 o-groups x 8 rows x 128 B = 16,384
 constexpr int kWgXCopy = 16 * 10 * 128;       // one shifted copy of the X tile: 20,480
-constexpr int kWgStage = kWgATile + 3 * kWgXCopy;   // 77,824
+constexpr int kWgXBase = 2 * kWgATile;        // dY hi tile, dY lo tile, then the three X copies
+constexpr int kWgStage = kWgXBase + 3 * kWgXCopy;   // 94,208
 constexpr int kWgStages = 2;
 constexpr int kWgSmem = kWgStages * kWgStage + 64;
 
-__device__ __forceinline__ uint4 pack_bf16x8(const float4 a, const float4 b) {
-    const __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
-    const __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+// 8 floats, scaled by a power of two into fp16's range -> fp16 hi parts and fp16 lo parts (x - hi)
+__device__ __forceinline__ void pack_f16x8_split(const float4 a, const float4 b, float scale, uint4 &hi, uint4 &lo) {
+    const float f[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const __half2 ph = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+        const float2 back = __half22float2(ph);
+        const __half2 pl = __floats2half2_rn(f[2 * i] - back.x, f[2 * i + 1] - back.y);
+        h[i] = *reinterpret_cast<const uint32_t *>(&ph);
+        l[i] = *reinterpret_cast<const uint32_t *>(&pl);
+    }
+    hi = make_uint4(h[0], h[1], h[2], h[3]);
+    lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+// 8 floats -> fp16 (activations: bounded range, 11-bit significand)
+__device__ __forceinline__ uint4 pack_f16x8(const float4 a, const float4 b) {
+    const __half2 p0 = __floats2half2_rn(a.x, a.y), p1 = __floats2half2_rn(a.z, a.w);
+    const __half2 p2 = __floats2half2_rn(b.x, b.y), p3 = __floats2half2_rn(b.z, b.w);
     return make_uint4(*reinterpret_cast<const uint32_t *>(&p0), *reinterpret_cast<const uint32_t *>(&p1),
                       *reinterpret_cast<const uint32_t *>(&p2), *reinterpret_cast<const uint32_t *>(&p3));
 }
 
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dy,
                                                                   float *__restrict__ partial, long long m, int cin,
-                                                                  int pos_per_slice, size_t partial_stride) {
+                                                                  int pos_per_slice, size_t partial_stride,
+                                                                  const unsigned *__restrict__ dymax) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int ky = blockIdx.y;                       // kernel row of this CTA: taps ky*3 + {0,1,2}
@@ -244,6 +265,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
     const long long p_begin = (long long)blockIdx.x * pos_per_slice;
     const long long p_end = min(m, p_begin + pos_per_slice);
     const int n_pos = (int)max(0LL, p_end - p_begin);
+    // dY is scaled so that its largest magnitude lands in [1024, 2048): far from fp16 overflow, and everything within 2^-24 of the
+    // maximum keeps at least subnormal precision in the hi part (the lo part extends that by 11 bits)
+    float scale = 1.0f;
+    {
+        const float mx = __uint_as_float(*dymax);
+        if (mx > 0.0f) scale = exp2f((float)(10 - ilogbf(mx)));
+    }
+    const float inv_scale = 1.0f / scale;
 
     for (int i = tid; i < kWgStages * kWgStage / 16; i += kWgThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);  // halo rows stay zero
     if (tid == 0) {
@@ -265,7 +294,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
     const uint32_t tmem = *tmem_slot;
 
     if (warp < 8) {
-        // ================= producers: fp32 global -> bf16 core matrices in shared memory =================
+        // ================= producers: fp32 global -> 16-bit core matrices in shared memory =================
         // Software-pipelined through registers: the 16 x 16-byte loads of position p+1 are in flight while position p is
         // converted and stored, so HBM/L2 latency is covered without a third shared-memory stage.
         uint32_t stage = 0, phase = 0;
@@ -299,7 +328,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
             for (int it = 0; it < 4; it++) {
                 const int chunk = tid + it * 256;
                 const int o = chunk >> 3, row = chunk & 7;
-                *reinterpret_cast<uint4 *>(st + (((o >> 3) * 8 + row) * 8 + (o & 7)) * 16) = pack_bf16x8(cur[2 * it], cur[2 * it + 1]);
+                uint4 hi, lo;
+                pack_f16x8_split(cur[2 * it], cur[2 * it + 1], scale, hi, lo);
+                const uint32_t off = (((o >> 3) * 8 + row) * 8 + (o & 7)) * 16;
+                *reinterpret_cast<uint4 *>(st + off) = hi;
+                *reinterpret_cast<uint4 *>(st + kWgATile + off) = lo;
             }
             // X: cin channels x 8 rows, three column-shifted copies
 #pragma unroll
@@ -307,8 +340,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
                 if (it < xchunks) {
                     const int chunk = tid + it * 256;
                     const int c = chunk >> 3, row = chunk & 7;
-                    const uint4 v = pack_bf16x8(cur[8 + 2 * it], cur[8 + 2 * it + 1]);
-                    const uint32_t off = kWgATile + (((c >> 3) * 10 + row + 1) * 8 + (c & 7)) * 16;
+                    const uint4 v = pack_f16x8(cur[8 + 2 * it], cur[8 + 2 * it + 1]);
+                    const uint32_t off = kWgXBase + (((c >> 3) * 10 + row + 1) * 8 + (c & 7)) * 16;
                     // kx = 0: out[x] = in[x - 1]; kx = 1: in[x]; kx = 2: out[x] = in[x + 1]   (zero beyond the board edge)
                     const uint4 left = make_uint4(v.x << 16, __funnelshift_l(v.x, v.y, 16), __funnelshift_l(v.y, v.z, 16), __funnelshift_l(v.z, v.w, 16));
                     const uint4 right = make_uint4(__funnelshift_r(v.x, v.y, 16), __funnelshift_r(v.y, v.z, 16), __funnelshift_r(v.z, v.w, 16), v.w >> 16);
@@ -325,7 +358,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
         }
     } else if ((tid & 31) == 0) {
         // ================= MMA issuer =================
-        const uint32_t idesc = instr_desc_bf16(128, N);
+        const uint32_t idesc = instr_desc(128, N);   // fp16 operands, fp32 accumulate
         const uint64_t hi_a = ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46);   // SBO = 1,024 B between o groups
         const uint64_t hi_b = ((uint64_t)(1280 >> 4) << 32) | (1ULL << 46);   // SBO = 1,280 B between c groups (10 padded rows)
         const uint32_t lbo_word = (uint32_t)(128 >> 4) << 16;                 // LBO = 128 B between K-adjacent core matrices (board rows)
@@ -338,9 +371,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
             for (int kx = 0; kx < 3; kx++) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {   // board rows (2 ks, 2 ks + 1) of dY against padded rows (2 ks + ky, 2 ks + ky + 1) of X
-                    const uint32_t aw = ((st + ks * 256) >> 4) | lbo_word;
-                    const uint32_t bw = ((st + kWgATile + kx * kWgXCopy + (2 * ks + ky) * 128) >> 4) | lbo_word;
+                    const uint32_t aw = ((st + ks * 256) >> 4) | lbo_word, alw = ((st + kWgATile + ks * 256) >> 4) | lbo_word;
+                    const uint32_t bw = ((st + kWgXBase + kx * kWgXCopy + (2 * ks + ky) * 128) >> 4) | lbo_word;
                     umma_f16(tmem + kx * 128, hi_a | aw, hi_b | bw, idesc, (ip > 0 || ks > 0) ? 1u : 0u);
+                    umma_f16(tmem + kx * 128, hi_a | alw, hi_b | bw, idesc, 1u);
                 }
             }
             umma_commit(bar_empty + 8 * stage);
@@ -370,7 +404,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
                 }
                 float *row = dst + ((size_t)tap * 128 + o) * N + c0;
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4 *>(row + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 32; j += 4)
+                    *reinterpret_cast<float4 *>(row + j) = make_float4(__uint_as_float(v[j]) * inv_scale, __uint_as_float(v[j + 1]) * inv_scale,
+                                                                       __uint_as_float(v[j + 2]) * inv_scale, __uint_as_float(v[j + 3]) * inv_scale);
             }
         }
     }
@@ -393,20 +429,35 @@ __global__ void reduce_taps_kernel(const float *__restrict__ partial, float *__r
 // db[o] = sum_{p, cell} dY[p][o][cell]: block (o, slice) sums its slice of positions with a fixed-order tree into
 // partial[slice][o]; reduce_slices_kernel then adds the slices in order.
 constexpr int kBiasSlices = 16;
-__global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict__ dy, float *__restrict__ partial, long long m, int cout) {
+// It also records max |dY| of the layer (order-free atomic max on the bit pattern of a non-negative float): the tensor-core
+// weight-gradient kernel scales dY by a power of two into fp16's range with it.
+__global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict__ dy, float *__restrict__ partial, long long m, int cout,
+                                                        unsigned *__restrict__ dymax) {
     __shared__ float red[256];
+    __shared__ float redm[256];
     const int o = blockIdx.x, tid = threadIdx.x;
     const long long per = (m + gridDim.y - 1) / gridDim.y;
     const long long p0 = (long long)blockIdx.y * per, p1 = min(m, p0 + per);
-    float s = 0.0f;
-    for (long long i = p0 * 64 + tid; i < p1 * 64; i += 256) s += dy[((i >> 6) * cout + o) * 64 + (i & 63)];
+    float s = 0.0f, mx = 0.0f;
+    for (long long i = p0 * 64 + tid; i < p1 * 64; i += 256) {
+        const float v = dy[((i >> 6) * cout + o) * 64 + (i & 63)];
+        s += v;
+        mx = fmaxf(mx, fabsf(v));
+    }
     red[tid] = s;
+    redm[tid] = mx;
     __syncthreads();
     for (int k = 128; k > 0; k >>= 1) {
-        if (tid < k) red[tid] += red[tid + k];
+        if (tid < k) {
+            red[tid] += red[tid + k];
+            redm[tid] = fmaxf(redm[tid], redm[tid + k]);
+        }
         __syncthreads();
     }
-    if (tid == 0) partial[(size_t)blockIdx.y * cout + o] = red[0];
+    if (tid == 0) {
+        partial[(size_t)blockIdx.y * cout + o] = red[0];
+        if (redm[0] < 3.0e38f) atomicMax(dymax, __float_as_uint(redm[0]));   // NaN / inf stay out: the scale then defaults to 1
+    }
 }
 
 // out[i] (+)= sum over slices of partial[s][i], slices in order.
@@ -500,6 +551,277 @@ __global__ void __launch_bounds__(256) head_grad_kernel(const float *__restrict_
     }
 }
 
+// ---------------------------------------------------------------- Value head (network.py:92-95) forward + backward, train_value.py:50-56
+// One CTA of 128 threads per position.  pre9 = block9 (3x3, 128 -> 1) + b9, h9 = relu(pre9), u = fc10 h9, z = dropout(u, ratio)
+// (Chainer: mask = rand >= ratio, scale 1/(1 - ratio)), v = fc11 z; loss term = (v - y)^2, dv = 2 (v - y)  (mean_squared_error is the
+// mean over the minibatch; the caller divides the summed gradient by the position count once, like the policy trainer).
+// Kept per position for the weight-gradient kernels: h9[64], du[128] (d loss / d u), z[128], dpre9[64], dv.
+// dact8 = gradient w.r.t. block 8's pre-activation (the ReLU mask of act8 applied), the entry of the trunk's backward chain.
+struct ValueHeadArgs {
+    const float *act8, *w9, *b9, *fc10, *fc11, *target;
+    float *pred, *loss_terms, *h9, *du, *z, *dpre9, *dv, *dact8;
+    uint8_t *mask_out;   // nullable [m][128]: 1 = kept
+    long long m;
+    float ratio;
+    u64 seed, pos_id0;
+};
+
+__device__ __forceinline__ float block128_sum(float v, float *red) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    const float r = (red[0] + red[1]) + (red[2] + red[3]);
+    __syncthreads();
+    return r;
+}
+
+__global__ void __launch_bounds__(128) value_head_kernel(ValueHeadArgs a) {
+    __shared__ float a8[128][65];
+    __shared__ float w9s[1152];
+    __shared__ float h9s[64], dps[64], dus[128];
+    __shared__ float red[4];
+    const long long p = blockIdx.x;
+    const int tid = threadIdx.x;
+    const float *src = a.act8 + (size_t)p * 128 * 64;
+    for (int i = tid; i < 128 * 64; i += 128) a8[i >> 6][i & 63] = src[i];
+    for (int i = tid; i < 1152; i += 128) w9s[i] = a.w9[i];
+    __syncthreads();
+    if (tid < 64) {
+        const int y = tid >> 3, x = tid & 7;
+        float acc = 0.0f;
+        for (int c = 0; c < 128; c++)
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+                if (yy >= 0 && yy < 8 && xx >= 0 && xx < 8) acc = fmaf(w9s[c * 9 + t], a8[c][yy * 8 + xx], acc);
+            }
+        acc += a.b9[0];
+        h9s[tid] = fmaxf(acc, 0.0f);
+        a.h9[p * 64 + tid] = h9s[tid];
+    }
+    __syncthreads();
+    float u = 0.0f;
+    {
+        const float *row = a.fc10 + (size_t)tid * 64;
+        for (int j = 0; j < 64; j++) u = fmaf(row[j], h9s[j], u);
+    }
+    float keep = 1.0f, scale = 1.0f;
+    if (a.ratio > 0.0f) {
+        const double r = (double)philox_m53(a.seed, a.pos_id0 + (u64)p, (uint32_t)tid, 5u) * (1.0 / 9007199254740992.0);
+        keep = r >= (double)a.ratio ? 1.0f : 0.0f;      // chainer.functions.dropout: mask = rand >= ratio
+        scale = 1.0f / (1.0f - a.ratio);
+    }
+    if (a.mask_out) a.mask_out[p * 128 + tid] = keep != 0.0f;
+    const float z = u * keep * scale;
+    const float w11 = a.fc11[tid];
+    const float v = block128_sum(w11 * z, red);
+    const float dv = 2.0f * (v - a.target[p]);
+    if (tid == 0) {
+        a.pred[p] = v;
+        a.loss_terms[p] = (v - a.target[p]) * (v - a.target[p]);
+        a.dv[p] = dv;
+    }
+    a.z[p * 128 + tid] = z;
+    const float du = dv * w11 * keep * scale;
+    a.du[p * 128 + tid] = du;
+    dus[tid] = du;
+    __syncthreads();
+    if (tid < 64) {
+        float d = 0.0f;
+        for (int i = 0; i < 128; i++) d = fmaf(a.fc10[(size_t)i * 64 + tid], dus[i], d);
+        d = h9s[tid] > 0.0f ? d : 0.0f;
+        dps[tid] = d;
+        a.dpre9[p * 64 + tid] = d;
+    }
+    __syncthreads();
+    float *dst = a.dact8 + (size_t)p * 128 * 64;
+    for (int i = tid; i < 128 * 64; i += 128) {
+        const int c = i >> 6, cell = i & 63, y = cell >> 3, x = cell & 7;
+        float g = 0.0f;
+        // act8[c][cell] feeds pre9[cell'] with cell' = cell - (tap offset): tap (ky,kx) of output (y - ky + 1, x - kx + 1)
+#pragma unroll
+        for (int t = 0; t < 9; t++) {
+            const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
+            if (yy >= 0 && yy < 8 && xx >= 0 && xx < 8) g = fmaf(w9s[c * 9 + t], dps[yy * 8 + xx], g);
+        }
+        dst[i] = a8[c][cell] > 0.0f ? g : 0.0f;
+    }
+}
+
+// Weight gradients of the value head, every sum in a fixed order.  Blocks [0,128): dW9[c][9 taps]; block 128: db9 and the loss
+// numerator; blocks [129, 129+32): dfc10 rows 4 per block; block 161: dfc11.
+__global__ void __launch_bounds__(256) value_head_grad_kernel(const float *__restrict__ act8, const float *__restrict__ h9,
+                                                              const float *__restrict__ du, const float *__restrict__ z,
+                                                              const float *__restrict__ dpre9, const float *__restrict__ dv,
+                                                              const float *__restrict__ loss_terms, float *__restrict__ gw9,
+                                                              float *__restrict__ gb9, float *__restrict__ gfc10, float *__restrict__ gfc11,
+                                                              float *__restrict__ gloss, long long m, int accumulate) {
+    __shared__ float red[256];
+    const int blk = blockIdx.x, tid = threadIdx.x;
+    auto reduce_store = [&](float v, float *dst) {
+        red[tid] = v;
+        __syncthreads();
+        for (int o = 128; o > 0; o >>= 1) {
+            if (tid < o) red[tid] += red[tid + o];
+            __syncthreads();
+        }
+        if (tid == 0) *dst = accumulate ? *dst + red[0] : red[0];
+        __syncthreads();
+    };
+    if (blk < 128) {
+        float acc[9];
+#pragma unroll
+        for (int t = 0; t < 9; t++) acc[t] = 0.0f;
+        for (long long i = tid; i < m * 64; i += 256) {           // (position, cell)
+            const long long p = i >> 6;
+            const int cell = (int)(i & 63), y = cell >> 3, x = cell & 7;
+            const float d = dpre9[i];
+            const float *a = act8 + ((size_t)p * 128 + blk) * 64;
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+                if (yy >= 0 && yy < 8 && xx >= 0 && xx < 8) acc[t] = fmaf(d, a[yy * 8 + xx], acc[t]);
+            }
+        }
+        for (int t = 0; t < 9; t++) reduce_store(acc[t], gw9 + blk * 9 + t);
+    } else if (blk == 128) {
+        float s = 0.0f, l = 0.0f;
+        for (long long i = tid; i < m * 64; i += 256) s += dpre9[i];
+        for (long long p = tid; p < m; p += 256) l += loss_terms[p];
+        reduce_store(s, gb9);
+        reduce_store(l, gloss);
+    } else if (blk < 161) {
+        // dfc10[i][j] = sum_p du[p][i] * h9[p][j]: 4 rows i per block, thread = (row, j)
+        const int i = (blk - 129) * 4 + (tid >> 6), j = tid & 63;
+        float s = 0.0f;
+        for (long long p = 0; p < m; p++) s = fmaf(du[p * 128 + i], h9[p * 64 + j], s);
+        float *dst = gfc10 + (size_t)i * 64 + j;
+        *dst = accumulate ? *dst + s : s;
+    } else {
+        if (tid < 128) {
+            float s = 0.0f;
+            for (long long p = 0; p < m; p++) s = fmaf(dv[p], z[p * 128 + tid], s);
+            gfc11[tid] = accumulate ? gfc11[tid] + s : s;
+        }
+    }
+}
+
+// Evaluation helpers.  policy: values = probabilities (or logits, is_logits) [n][64]; out[0] += sum of softmax_cross_entropy(pred, y)
+// with pred the PROBABILITIES (the reference applies log-softmax to them again, train_policy.py:62,69), out[1] += correct arg-maxes
+// (F.accuracy).  value: out[0] += sum (v - y)^2.  One block, fixed order.
+__global__ void __launch_bounds__(256) policy_eval_kernel(const float *__restrict__ values, const int8_t *__restrict__ action, long long n,
+                                                          int is_logits, float *__restrict__ out) {
+    __shared__ float red[2][256];
+    const int tid = threadIdx.x;
+    float loss = 0.0f, hits = 0.0f;
+    for (long long p = tid; p < n; p += 256) {
+        const float *v = values + p * 64;
+        float pr[64];
+        float mx = v[0];
+        int arg = 0;
+        for (int i = 1; i < 64; i++) if (v[i] > mx) { mx = v[i]; arg = i; }
+        if (is_logits) {
+            float sum = 0.0f;
+            for (int i = 0; i < 64; i++) { pr[i] = expf(v[i] - mx); sum += pr[i]; }
+            for (int i = 0; i < 64; i++) pr[i] /= sum;
+        } else {
+            for (int i = 0; i < 64; i++) pr[i] = v[i];
+        }
+        float mx2 = pr[0];
+        for (int i = 1; i < 64; i++) mx2 = fmaxf(mx2, pr[i]);
+        float s2 = 0.0f;
+        for (int i = 0; i < 64; i++) s2 += expf(pr[i] - mx2);
+        const int y = action[p];
+        loss += -(pr[y] - mx2 - logf(s2));
+        hits += arg == y ? 1.0f : 0.0f;
+    }
+    red[0][tid] = loss; red[1][tid] = hits;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) { red[0][tid] += red[0][tid + o]; red[1][tid] += red[1][tid + o]; }
+        __syncthreads();
+    }
+    if (tid == 0) { out[0] += red[0][0]; out[1] += red[1][0]; }
+}
+
+__global__ void __launch_bounds__(256) value_eval_kernel(const float *__restrict__ pred, const float *__restrict__ target, long long n,
+                                                         float *__restrict__ out) {
+    __shared__ float red[256];
+    const int tid = threadIdx.x;
+    float s = 0.0f;
+    for (long long p = tid; p < n; p += 256) s += (pred[p] - target[p]) * (pred[p] - target[p]);
+    red[tid] = s;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (tid < o) red[tid] += red[tid + o];
+        __syncthreads();
+    }
+    if (tid == 0) out[0] += red[0];
+}
+
+// ---------------------------------------------------------------- RolloutPolicy (network.py:49-64) supervised gradient, train_policy.py --policy rollout
+// One CTA of 64 threads (= cells) walks positions blockIdx.x, blockIdx.x + gridDim.x, ...; logits = conv1 (2 -> 1, 3x3, no bias) +
+// bias2[cell] straight from the bitboards, pred = softmax, loss = softmax_cross_entropy(pred, y) (log-softmax applied to the
+// probabilities again, as for the SL policy), gradients accumulated per thread and reduced once per CTA in a fixed order.
+// partial[cta] = dW[18] | db[64] | loss numerator.
+__global__ void __launch_bounds__(64) rollout_grad_kernel(const u64 *__restrict__ own, const u64 *__restrict__ opp, const int8_t *__restrict__ action,
+                                                          const float *__restrict__ params, float *__restrict__ partial, long long m) {
+    __shared__ float red[2];
+    __shared__ float wred[64];
+    const int cell = threadIdx.x, y = cell >> 3, x = cell & 7;
+    float W[18];
+#pragma unroll
+    for (int i = 0; i < 18; i++) W[i] = params[i];
+    const float b = params[18 + cell];
+    float gw[18], gb = 0.0f, gl = 0.0f;
+#pragma unroll
+    for (int i = 0; i < 18; i++) gw[i] = 0.0f;
+    for (long long p = blockIdx.x; p < m; p += gridDim.x) {
+        const u64 pl[2] = {opp[p], own[p]};   // channel 0 = opponent stones, channel 1 = mover's stones
+        float xs[18];
+        float s[2] = {0.0f, 0.0f};
+#pragma unroll
+        for (int c = 0; c < 2; c++)
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+                const int yy = y + t / 3 - 1, xx = x + t % 3 - 1;
+                const bool in = yy >= 0 && yy < 8 && xx >= 0 && xx < 8;
+                const float v = in ? (float)((pl[c] >> (yy * 8 + xx)) & 1) : 0.0f;
+                xs[c * 9 + t] = v;
+                if (v != 0.0f) s[c] = __fadd_rn(s[c], W[c * 9 + t]);
+            }
+        const float logit = __fadd_rn(__fadd_rn(s[0], s[1]), b);
+        const float mx = block64_max(logit, red);
+        const float e = expf(logit - mx);
+        const float pred = e / block64_sum(e, red);
+        const float mx2 = block64_max(pred, red);
+        const float e2 = expf(pred - mx2);
+        const float s2 = block64_sum(e2, red);
+        const float q = e2 / s2;
+        const int ya = action[p];
+        if (cell == ya) gl += -(pred - mx2 - logf(s2));
+        const float dpred = q - (cell == ya ? 1.0f : 0.0f);
+        const float dot = block64_sum(dpred * pred, red);
+        const float dl = pred * (dpred - dot);
+        gb += dl;
+#pragma unroll
+        for (int i = 0; i < 18; i++) gw[i] = fmaf(dl, xs[i], gw[i]);
+    }
+    float *dst = partial + (size_t)blockIdx.x * 83;
+    dst[18 + cell] = gb;
+    for (int i = 0; i < 19; i++) {
+        wred[cell] = i < 18 ? gw[i] : gl;
+        __syncthreads();
+        for (int o = 32; o > 0; o >>= 1) {
+            if (cell < o) wred[cell] += wred[cell + o];
+            __syncthreads();
+        }
+        if (cell == 0) dst[i < 18 ? i : 82] = wred[0];
+        __syncthreads();
+    }
+}
+
 // ---------------------------------------------------------------- WeightDecay hook + Adam (Chainer: optimizers.Adam, optimizer_hooks.WeightDecay)
 __global__ void adam_kernel(float *__restrict__ p, float *__restrict__ mo, float *__restrict__ ve, const float *__restrict__ g,
                             int n, float inv_count, float wd, float beta1, float beta2, float eps, float lr_t) {
@@ -520,8 +842,12 @@ __global__ void set_count_kernel(float *dst, float m, int accumulate) { *dst = a
 
 using namespace iago;
 
+constexpr int kNPValue = 970049;  // Value parameters
+
 struct iago_trainer {
     iago_ctx *ctx = nullptr;
+    int kind = 0;                     // 0 = SLPolicy (REINFORCE / supervised policy), 1 = Value (train_value.py)
+    int np = kNP;                     // parameter count
     int max_pos = 0;
     float *params = nullptr, *adam_m = nullptr, *adam_v = nullptr;  // [kNP]
     long long t = 0;
@@ -532,6 +858,7 @@ struct iago_trainer {
     void *bwd_desc = nullptr;
     int bwd_precision = 3;
     float *dlogit = nullptr, *loss_terms = nullptr, *partial = nullptr, *bias_partial = nullptr;
+    unsigned *dymax = nullptr;        // [8] bit pattern of max |dY| per layer (bias_grad_kernel)
     size_t partial_stride = 0;
     int slices = 0;
     int tc_slices = 0, slices0 = 0;
@@ -539,7 +866,9 @@ struct iago_trainer {
     int synced_slot = -1;             // trunk slot that holds the CURRENT parameters (-1: stale)
     uint8_t *ones = nullptr;          // colour array (all 1) for the trunk launch
     float *logits_scratch = nullptr;
-    size_t w_off[8], b_off[8], w9_off, b10_off;
+    size_t w_off[8], b_off[8], w9_off, b10_off;      // policy head: conv9/W [128], bias10/b [64]
+    size_t vw9_off = 0, vb9_off = 0, fc10_off = 0, fc11_off = 0;   // value head: block9/conv/W [1152], /b [1], fc10/W [128][64], fc11/W [128]
+    float *h9 = nullptr, *du = nullptr, *zbuf = nullptr, *dpre9 = nullptr, *dv = nullptr, *vpred = nullptr;
     std::vector<void *> allocs;
 };
 
@@ -560,26 +889,37 @@ static void relayout_all(iago_trainer *t, cudaStream_t s) {
 
 extern "C" {
 
-int iago_reinforce_create(iago_ctx *ctx, const float *params, int64_t n_floats, int max_positions, iago_trainer **out) {
+int iago_trainer_create(iago_ctx *ctx, int kind, const float *params, int64_t n_floats, int max_positions, iago_trainer **out) {
     IAGO_REQUIRE(ctx && params && out, "NULL argument");
-    IAGO_REQUIRE(n_floats == kNP, "SLPolicy parameter vector must hold 960,768 floats (iago_load_net order)");
+    IAGO_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (SL policy) or 1 (value)");
+    IAGO_REQUIRE(n_floats == (kind == 0 ? kNP : kNPValue), "parameter vector must hold 960,768 (policy) / 970,049 (value) floats (iago_load_net order)");
     IAGO_REQUIRE(max_positions > 0 && max_positions <= (1 << 20), "max_positions out of range");
     *out = nullptr;
     DeviceGuard guard(ctx->device);
     iago_trainer *t = new iago_trainer();
     t->ctx = ctx;
+    t->kind = kind;
+    t->np = (int)n_floats;
     t->max_pos = max_positions;
     size_t off = 0;
     for (int l = 0; l < 8; l++) {
         t->w_off[l] = off; off += (size_t)kCout[l] * kCin[l] * 9;
         t->b_off[l] = off; off += kCout[l];
     }
-    t->w9_off = off; off += 128;
-    t->b10_off = off; off += 64;
+    if (kind == 0) {
+        t->w9_off = off; off += 128;
+        t->b10_off = off; off += 64;
+    } else {
+        t->w9_off = t->b10_off = 0;
+        t->vw9_off = off; off += 1152;
+        t->vb9_off = off; off += 1;
+        t->fc10_off = off; off += 128 * 64;
+        t->fc11_off = off; off += 128;
+    }
     int rc = 0;
     const size_t M = max_positions;
 #define A(ptr, cnt) if (!rc) rc = tr_alloc(t, &(ptr), (cnt))
-    A(t->params, kNP); A(t->adam_m, kNP); A(t->adam_v, kNP);
+    A(t->params, t->np); A(t->adam_m, t->np); A(t->adam_v, t->np);
     for (int l = 0; l < 8; l++) {
         A(t->wf[l], (size_t)kCout[l] * kCin[l] * 9);
         if (l > 0) A(t->wd[l], (size_t)kCout[l] * kCin[l] * 9);
@@ -590,7 +930,11 @@ int iago_reinforce_create(iago_ctx *ctx, const float *params, int64_t n_floats, 
     A(t->bwd_blob, trunk_backward_blob_bytes());
     { uint8_t *d = nullptr; A(d, trunk_desc_bytes()); t->bwd_desc = d; }
     A(t->dlogit, M * 64); A(t->loss_terms, M); A(t->ones, M); A(t->logits_scratch, M * 64);
+    if (kind == 1) {
+        A(t->h9, M * 64); A(t->du, M * 128); A(t->zbuf, M * 128); A(t->dpre9, M * 64); A(t->dv, M); A(t->vpred, M);
+    }
     A(t->bias_partial, (size_t)kBiasSlices * 128);
+    A(t->dymax, 8);
     t->slices = 24;                                  // fp32 weight-gradient kernel: position slices of the 64/128-input-channel layers
     t->slices0 = 2 * ctx->sm_count;                  // ... and of block 1 (2 input channels: one c tile, so the slices are the whole grid)
     t->tc_slices = (ctx->sm_count + 2) / 3;          // 3 kernel rows x slices ~ one CTA per SM
@@ -602,10 +946,14 @@ int iago_reinforce_create(iago_ctx *ctx, const float *params, int64_t n_floats, 
         delete t;
         return rc;
     }
-    IAGO_CUDA(cudaMemcpy(t->params, params, (size_t)kNP * 4, cudaMemcpyHostToDevice));
+    IAGO_CUDA(cudaMemcpy(t->params, params, (size_t)t->np * 4, cudaMemcpyHostToDevice));
     IAGO_CUDA(cudaMemset(t->ones, 1, M));
     *out = t;
     return IAGO_OK;
+}
+
+int iago_reinforce_create(iago_ctx *ctx, const float *params, int64_t n_floats, int max_positions, iago_trainer **out) {
+    return iago_trainer_create(ctx, 0, params, n_floats, max_positions, out);
 }
 
 int iago_reinforce_destroy(iago_trainer *t) {
@@ -617,20 +965,16 @@ int iago_reinforce_destroy(iago_trainer *t) {
     return IAGO_OK;
 }
 
-int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *opp, const int8_t *action, const float *reward,
-                        int64_t m, float *grad, int accumulate, float *probs_out, void *stream) {
-    IAGO_REQUIRE(t && own && opp && action && reward && grad, "NULL argument");
-    IAGO_REQUIRE(m >= 0 && m <= t->max_pos, "m exceeds the trainer's max_positions");
-    if (m == 0) return IAGO_OK;
-    DeviceGuard guard(t->ctx->device);
+// Forward through the 8 blocks with every block's output kept in act[1..8] (fp32 [m][C][64]).
+static int forward_acts(iago_trainer *t, const uint64_t *own, const uint64_t *opp, int64_t m, void *stream) {
     cudaStream_t s = (cudaStream_t)stream;
     if (!(t->use_tc && t->synced_slot >= 0)) relayout_all(t, s);   // Wf / Wd feed the fp32 conv kernels only
     const unsigned tiles = (unsigned)((m + 1) / 2);
-    // ---- forward, activations kept
     planes_kernel<<<(unsigned)((m * 64 + 255) / 256), 256, 0, s>>>((const u64 *)own, (const u64 *)opp, t->act[0], m);
     if (t->use_tc && t->synced_slot >= 0) {
         // the fused tcgen05 trunk (trunk.cu) on the slot that holds these parameters, dumping every block's output in fp32
-        int rc = trunk_launch(t->ctx, t->synced_slot, 0, own, opp, t->ones, m, t->logits_scratch, 0, 3, stream, nullptr, t->act + 1);
+        float *out = t->kind == 0 ? t->logits_scratch : t->vpred;
+        int rc = trunk_launch(t->ctx, t->synced_slot, t->kind, own, opp, t->ones, m, out, 0, 3, stream, nullptr, t->act + 1);
         if (rc) return rc;
     } else {
         for (int l = 0; l < 8; l++) {
@@ -642,12 +986,13 @@ int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *op
         }
     }
     IAGO_CUDA(cudaGetLastError());
-    // ---- head forward + backward
-    head_kernel<<<(unsigned)m, 64, 0, s>>>(t->act[8], t->params + t->w9_off, t->params + t->b10_off, action, reward, t->dlogit,
-                                          t->dyb[7], t->loss_terms, probs_out, m);
-    head_grad_kernel<<<193, 256, 0, s>>>(t->act[8], t->dlogit, t->loss_terms, grad + t->w9_off, grad + t->b10_off, grad + kNP, m, accumulate);
-    IAGO_CUDA(cudaGetLastError());
-    // ---- backward through the 8 blocks
+    return IAGO_OK;
+}
+
+// Backward through the 8 blocks from dyb[7] (gradient w.r.t. block 8's pre-activation): weight / bias gradients into `grad`.
+static int backward_trunk(iago_trainer *t, int64_t m, float *grad, int accumulate, void *stream) {
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned tiles = (unsigned)((m + 1) / 2);
     if (t->use_tc) {
         // data gradients of blocks 8..2 as ONE fused tcgen05 launch (bf16 hi/lo, the tile stays on chip between layers)
         const float *W[8], *mask[7];
@@ -674,10 +1019,11 @@ int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *op
             }
             const int pps = (int)((m + t->tc_slices - 1) / t->tc_slices);
             const int sl = (int)((m + pps - 1) / pps);
-            wgrad_tc_kernel<<<dim3(sl, 3), kWgThreads, kWgSmem, s>>>(t->act[l], dy, t->partial, m, kCin[l], pps, t->partial_stride);
-            reduce_taps_kernel<<<(9 * 128 * kCin[l] + 255) / 256, 256, 0, s>>>(t->partial, grad + t->w_off[l], kCin[l], sl, t->partial_stride, accumulate);
-            bias_grad_kernel<<<dim3(kCout[l], kBiasSlices), 256, 0, s>>>(dy, t->bias_partial, m, kCout[l]);
+            IAGO_CUDA(cudaMemsetAsync(t->dymax + l, 0, 4, s));
+            bias_grad_kernel<<<dim3(kCout[l], kBiasSlices), 256, 0, s>>>(dy, t->bias_partial, m, kCout[l], t->dymax + l);
             reduce_slices_kernel<<<1, 256, 0, s>>>(t->bias_partial, grad + t->b_off[l], kCout[l], kBiasSlices, (size_t)kCout[l], accumulate);
+            wgrad_tc_kernel<<<dim3(sl, 3), kWgThreads, kWgSmem, s>>>(t->act[l], dy, t->partial, m, kCin[l], pps, t->partial_stride, t->dymax + l);
+            reduce_taps_kernel<<<(9 * 128 * kCin[l] + 255) / 256, 256, 0, s>>>(t->partial, grad + t->w_off[l], kCin[l], sl, t->partial_stride, accumulate);
         } else {
             const int count = kCout[l] * kCin[l] * 9 + kCout[l];  // W then b are adjacent in the flat layout as well
             const size_t stride = l == 0 ? (size_t)count : t->partial_stride;
@@ -693,8 +1039,77 @@ int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *op
         }
     }
     IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *opp, const int8_t *action, const float *reward,
+                        int64_t m, float *grad, int accumulate, float *probs_out, void *stream) {
+    IAGO_REQUIRE(t && own && opp && action && reward && grad, "NULL argument");
+    IAGO_REQUIRE(t->kind == 0, "this trainer holds a Value network (use iago_value_grad)");
+    IAGO_REQUIRE(m >= 0 && m <= t->max_pos, "m exceeds the trainer's max_positions");
+    if (m == 0) return IAGO_OK;
+    DeviceGuard guard(t->ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = forward_acts(t, own, opp, m, stream);
+    if (rc) return rc;
+    // ---- head forward + backward
+    head_kernel<<<(unsigned)m, 64, 0, s>>>(t->act[8], t->params + t->w9_off, t->params + t->b10_off, action, reward, t->dlogit,
+                                          t->dyb[7], t->loss_terms, probs_out, m);
+    head_grad_kernel<<<193, 256, 0, s>>>(t->act[8], t->dlogit, t->loss_terms, grad + t->w9_off, grad + t->b10_off, grad + kNP, m, accumulate);
+    IAGO_CUDA(cudaGetLastError());
+    rc = backward_trunk(t, m, grad, accumulate, stream);
+    if (rc) return rc;
     // the position count rides along with the gradient (element kNP + 1), so ranks all-reduce numerator and count together
     set_count_kernel<<<1, 1, 0, s>>>(grad + kNP + 1, (float)m, accumulate);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+int iago_value_grad(iago_trainer *t, const uint64_t *own, const uint64_t *opp, const float *target, int64_t m, float *grad,
+                    int accumulate, double dropout_ratio, uint64_t dropout_seed, uint64_t position_id0, float *pred_out,
+                    uint8_t *mask_out, void *stream) {
+    IAGO_REQUIRE(t && own && opp && target && grad, "NULL argument");
+    IAGO_REQUIRE(t->kind == 1, "this trainer holds an SL policy network (use iago_reinforce_grad)");
+    IAGO_REQUIRE(m >= 0 && m <= t->max_pos, "m exceeds the trainer's max_positions");
+    IAGO_REQUIRE(dropout_ratio >= 0.0 && dropout_ratio < 1.0, "dropout_ratio must lie in [0, 1)");
+    if (m == 0) return IAGO_OK;
+    DeviceGuard guard(t->ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = forward_acts(t, own, opp, m, stream);
+    if (rc) return rc;
+    const float *P = t->params;
+    ValueHeadArgs a{t->act[8], P + t->vw9_off, P + t->vb9_off, P + t->fc10_off, P + t->fc11_off, target,
+                    t->vpred, t->loss_terms, t->h9, t->du, t->zbuf, t->dpre9, t->dv, t->dyb[7], mask_out, m,
+                    (float)dropout_ratio, dropout_seed, position_id0};
+    value_head_kernel<<<(unsigned)m, 128, 0, s>>>(a);
+    value_head_grad_kernel<<<162, 256, 0, s>>>(t->act[8], t->h9, t->du, t->zbuf, t->dpre9, t->dv, t->loss_terms, grad + t->vw9_off,
+                                               grad + t->vb9_off, grad + t->fc10_off, grad + t->fc11_off, grad + t->np, m, accumulate);
+    IAGO_CUDA(cudaGetLastError());
+    if (pred_out) IAGO_CUDA(cudaMemcpyAsync(pred_out, t->vpred, (size_t)m * 4, cudaMemcpyDeviceToDevice, s));
+    rc = backward_trunk(t, m, grad, accumulate, stream);
+    if (rc) return rc;
+    set_count_kernel<<<1, 1, 0, s>>>(grad + t->np + 1, (float)m, accumulate);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+/* sums into out[0] (loss) and out[1] (correct arg-maxes); the caller zeroes `out` (device float[2]) */
+int iago_policy_eval(iago_ctx *ctx, const float *values, int is_logits, const int8_t *action, int64_t n, float *out, void *stream) {
+    IAGO_REQUIRE(ctx && values && action && out, "NULL argument");
+    IAGO_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    policy_eval_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(values, action, n, is_logits, out);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+int iago_value_eval(iago_ctx *ctx, const float *pred, const float *target, int64_t n, float *out, void *stream) {
+    IAGO_REQUIRE(ctx && pred && target && out, "NULL argument");
+    IAGO_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    value_eval_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(pred, target, n, out);
     IAGO_CUDA(cudaGetLastError());
     return IAGO_OK;
 }
@@ -709,7 +1124,7 @@ int iago_reinforce_adam_step(iago_trainer *t, const float *grad, double count, d
     t->synced_slot = -1;   // the slot no longer holds these parameters until iago_reinforce_sync_slot
     const double fix1 = 1.0 - pow(beta1, (double)t->t), fix2 = 1.0 - pow(beta2, (double)t->t);
     const float lr_t = (float)(alpha * sqrt(fix2) / fix1);   // Chainer AdamRule.lr
-    adam_kernel<<<(kNP + 255) / 256, 256, 0, s>>>(t->params, t->adam_m, t->adam_v, grad, kNP, (float)(1.0 / count), (float)weight_decay,
+    adam_kernel<<<(t->np + 255) / 256, 256, 0, s>>>(t->params, t->adam_m, t->adam_v, grad, t->np, (float)(1.0 / count), (float)weight_decay,
                                                   (float)beta1, (float)beta2, (float)eps, lr_t);
     IAGO_CUDA(cudaGetLastError());
     return IAGO_OK;
@@ -719,9 +1134,9 @@ int iago_reinforce_get_state(iago_trainer *t, float *params, float *adam_m, floa
     IAGO_REQUIRE(t, "NULL argument");
     DeviceGuard guard(t->ctx->device);
     IAGO_CUDA(cudaDeviceSynchronize());
-    if (params) IAGO_CUDA(cudaMemcpy(params, t->params, (size_t)kNP * 4, cudaMemcpyDeviceToHost));
-    if (adam_m) IAGO_CUDA(cudaMemcpy(adam_m, t->adam_m, (size_t)kNP * 4, cudaMemcpyDeviceToHost));
-    if (adam_v) IAGO_CUDA(cudaMemcpy(adam_v, t->adam_v, (size_t)kNP * 4, cudaMemcpyDeviceToHost));
+    if (params) IAGO_CUDA(cudaMemcpy(params, t->params, (size_t)t->np * 4, cudaMemcpyDeviceToHost));
+    if (adam_m) IAGO_CUDA(cudaMemcpy(adam_m, t->adam_m, (size_t)t->np * 4, cudaMemcpyDeviceToHost));
+    if (adam_v) IAGO_CUDA(cudaMemcpy(adam_v, t->adam_v, (size_t)t->np * 4, cudaMemcpyDeviceToHost));
     if (step) *step = t->t;
     return IAGO_OK;
 }
@@ -731,11 +1146,98 @@ int iago_reinforce_set_state(iago_trainer *t, const float *params, const float *
     DeviceGuard guard(t->ctx->device);
     IAGO_CUDA(cudaDeviceSynchronize());
     if (params) {
-        IAGO_CUDA(cudaMemcpy(t->params, params, (size_t)kNP * 4, cudaMemcpyHostToDevice));
+        IAGO_CUDA(cudaMemcpy(t->params, params, (size_t)t->np * 4, cudaMemcpyHostToDevice));
         t->synced_slot = -1;
     }
-    if (adam_m) IAGO_CUDA(cudaMemcpy(t->adam_m, adam_m, (size_t)kNP * 4, cudaMemcpyHostToDevice));
-    if (adam_v) IAGO_CUDA(cudaMemcpy(t->adam_v, adam_v, (size_t)kNP * 4, cudaMemcpyHostToDevice));
+    if (adam_m) IAGO_CUDA(cudaMemcpy(t->adam_m, adam_m, (size_t)t->np * 4, cudaMemcpyHostToDevice));
+    if (adam_v) IAGO_CUDA(cudaMemcpy(t->adam_v, adam_v, (size_t)t->np * 4, cudaMemcpyHostToDevice));
+    if (step >= 0) t->t = step;
+    return IAGO_OK;
+}
+
+/* ---- RolloutPolicy trainer: 82 parameters (conv1/W [1][2][3][3] then bias2/b [64]); gradient vector = 82 | loss numerator | count */
+struct iago_rollout_trainer {
+    iago_ctx *ctx = nullptr;
+    float *params = nullptr, *adam_m = nullptr, *adam_v = nullptr, *partial = nullptr;
+    int ctas = 0;
+    long long t = 0;
+};
+
+int iago_rollout_trainer_create(iago_ctx *ctx, const float *conv1_W, const float *bias2_b, iago_rollout_trainer **out) {
+    IAGO_REQUIRE(ctx && conv1_W && bias2_b && out, "NULL argument");
+    *out = nullptr;
+    DeviceGuard guard(ctx->device);
+    iago_rollout_trainer *t = new iago_rollout_trainer();
+    t->ctx = ctx;
+    t->ctas = 8 * ctx->sm_count;
+    cudaError_t e = cudaMalloc(&t->params, 3 * 82 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&t->partial, (size_t)t->ctas * 83 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemset(t->params, 0, 3 * 82 * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpy(t->params, conv1_W, 18 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(t->params + 18, bias2_b, 64 * sizeof(float), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        cudaFree(t->params); cudaFree(t->partial);
+        delete t;
+        IAGO_CUDA(e);
+    }
+    t->adam_m = t->params + 82;
+    t->adam_v = t->params + 164;
+    *out = t;
+    return IAGO_OK;
+}
+
+int iago_rollout_trainer_destroy(iago_rollout_trainer *t) {
+    if (!t) return IAGO_OK;
+    DeviceGuard guard(t->ctx->device);
+    cudaDeviceSynchronize();
+    cudaFree(t->params); cudaFree(t->partial);
+    delete t;
+    return IAGO_OK;
+}
+
+int iago_rollout_trainer_grad(iago_rollout_trainer *t, const uint64_t *own, const uint64_t *opp, const int8_t *action, int64_t m,
+                              float *grad, int accumulate, void *stream) {
+    IAGO_REQUIRE(t && own && opp && action && grad, "NULL argument");
+    IAGO_REQUIRE(m >= 0, "m < 0");
+    if (m == 0) return IAGO_OK;
+    DeviceGuard guard(t->ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int ctas = (int)(m < t->ctas ? m : t->ctas);
+    rollout_grad_kernel<<<ctas, 64, 0, s>>>((const u64 *)own, (const u64 *)opp, action, t->params, t->partial, m);
+    reduce_slices_kernel<<<1, 128, 0, s>>>(t->partial, grad, 83, ctas, 83, accumulate);
+    set_count_kernel<<<1, 1, 0, s>>>(grad + 83, (float)m, accumulate);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+int iago_rollout_trainer_adam_step(iago_rollout_trainer *t, const float *grad, double count, double alpha, double beta1, double beta2,
+                                   double eps, double weight_decay, void *stream) {
+    IAGO_REQUIRE(t && grad, "NULL argument");
+    IAGO_REQUIRE(count > 0, "count must be positive");
+    DeviceGuard guard(t->ctx->device);
+    t->t += 1;
+    const double fix1 = 1.0 - pow(beta1, (double)t->t), fix2 = 1.0 - pow(beta2, (double)t->t);
+    adam_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(t->params, t->adam_m, t->adam_v, grad, 82, (float)(1.0 / count), (float)weight_decay,
+                                                    (float)beta1, (float)beta2, (float)eps, (float)(alpha * sqrt(fix2) / fix1));
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+/* state: HOST float[3][82] = params | adam m | adam v */
+int iago_rollout_trainer_get_state(iago_rollout_trainer *t, float *state, int64_t *step) {
+    IAGO_REQUIRE(t && state, "NULL argument");
+    DeviceGuard guard(t->ctx->device);
+    IAGO_CUDA(cudaDeviceSynchronize());
+    IAGO_CUDA(cudaMemcpy(state, t->params, 3 * 82 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (step) *step = t->t;
+    return IAGO_OK;
+}
+
+int iago_rollout_trainer_set_state(iago_rollout_trainer *t, const float *state, int64_t step) {
+    IAGO_REQUIRE(t && state, "NULL argument");
+    DeviceGuard guard(t->ctx->device);
+    IAGO_CUDA(cudaDeviceSynchronize());
+    IAGO_CUDA(cudaMemcpy(t->params, state, 3 * 82 * sizeof(float), cudaMemcpyHostToDevice));
     if (step >= 0) t->t = step;
     return IAGO_OK;
 }
@@ -749,17 +1251,17 @@ int iago_reinforce_set_option(iago_trainer *t, int use_tensor_cores) {
 int iago_reinforce_sync_slot(iago_trainer *t, int slot) {
     IAGO_REQUIRE(t, "NULL argument");
     int rc;
-    if (trunk_slot_holds(t->ctx, slot, 0)) {
+    if (trunk_slot_holds(t->ctx, slot, t->kind)) {
         // the slot's buffers exist: repack on the device (after whatever stream the Adam step ran on has drained)
         DeviceGuard guard(t->ctx->device);
         IAGO_CUDA(cudaDeviceSynchronize());
-        rc = trunk_refresh_policy_slot(t->ctx, slot, t->params, t->ctx->stream);
+        rc = trunk_refresh_slot(t->ctx, slot, t->kind, t->params, t->ctx->stream);
         if (rc == IAGO_OK) IAGO_CUDA(cudaStreamSynchronize(t->ctx->stream));
     } else {
-        std::vector<float> h(kNP);
+        std::vector<float> h(t->np);
         rc = iago_reinforce_get_state(t, h.data(), nullptr, nullptr, nullptr);
         if (rc) return rc;
-        rc = iago_load_net(t->ctx, slot, 0, h.data(), kNP);
+        rc = iago_load_net(t->ctx, slot, t->kind, h.data(), t->np);
     }
     if (rc == IAGO_OK) t->synced_slot = slot;
     return rc;

@@ -654,8 +654,8 @@ __global__ void pack_forward_kernel(const float *__restrict__ W, uint8_t *__rest
     unit[half_elems + off] = l;
 }
 
-__global__ void pack_bias_head_kernel(const float *__restrict__ params, float *__restrict__ bias, float *__restrict__ head) {
-    // params: iago_load_net order, kind 0.  bias[l][128] (zero padded), head = w9[128] | b10[64] | 0...
+__global__ void pack_bias_head_kernel(const float *__restrict__ params, float *__restrict__ bias, float *__restrict__ head, int kind) {
+    // params: iago_load_net order.  bias[l][128] (zero padded); policy head = w9[128] | b10[64] (the value head is packed separately)
     const int cin[8] = {2, 64, 128, 128, 128, 128, 128, 128}, cout[8] = {64, 128, 128, 128, 128, 128, 128, 128};
     size_t off = 0;
     for (int l = 0; l < 8; l++) {
@@ -663,15 +663,42 @@ __global__ void pack_bias_head_kernel(const float *__restrict__ params, float *_
         for (int i = threadIdx.x; i < 128; i += blockDim.x) bias[l * 128 + i] = i < cout[l] ? params[off + i] : 0.0f;
         off += cout[l];
     }
-    for (int i = threadIdx.x; i < 192; i += blockDim.x) head[i] = params[off + i];
+    if (kind == 0)
+        for (int i = threadIdx.x; i < 192; i += blockDim.x) head[i] = params[off + i];
 }
 
-int trunk_refresh_policy_slot(iago_ctx *ctx, int slot, const float *d_params, void *stream) {
+// Value head: block9 units (N padded to 16, only output 0 is real, chunk-major like the trunk layers), b9 and the collapsed
+// fc11 * fc10 64-vector (fp64 accumulation, as iago_load_net does on the host).
+__global__ void pack_value_head_kernel(const float *__restrict__ hp /* W9[1152] | b9 | fc10[128][64] | fc11[128] */,
+                                       uint8_t *__restrict__ units, float *__restrict__ head) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over [ut 18][kg 8][n 16][e 8]
+    if (idx < 18 * 8 * 16 * 8) {
+        const int e = idx & 7, n = (idx >> 3) & 15, kg = (idx >> 7) & 7, ut = idx >> 10;
+        const int ch = ut / 9, tap = ut % 9;
+        const float w = n == 0 ? hp[(size_t)(ch * 64 + kg * 8 + e) * 9 + tap] : 0.0f;
+        const __half h = __float2half_rn(w);
+        const __half l = __float2half_rn(w - __half2float(h));
+        const size_t half_elems = 8 * 16 * 8;
+        __half *unit = reinterpret_cast<__half *>(units) + (size_t)ut * 2 * half_elems;
+        const size_t off = ((size_t)kg * 16 + n) * 8 + e;
+        unit[off] = h;
+        unit[half_elems + off] = l;
+    }
+    if (idx < 64) {
+        const float *fc10 = hp + 1153, *fc11 = fc10 + 128 * 64;
+        double acc = 0.0;
+        for (int i = 0; i < 128; i++) acc += (double)fc11[i] * (double)fc10[(size_t)i * 64 + idx];
+        head[128 + idx] = (float)acc;
+    }
+    if (idx == 64) head[0] = hp[1152];
+}
+
+int trunk_refresh_slot(iago_ctx *ctx, int slot, int kind, const float *d_params, void *stream) {
     IAGO_REQUIRE(ctx && d_params, "NULL argument");
     IAGO_REQUIRE(slot >= 0 && slot < 8, "slot out of range (0..7)");
     NetSlot &s = state(ctx)->slot[slot];
-    if (!s.loaded || s.desc.kind != 0) {
-        set_error("net slot %d holds no policy network to refresh (call iago_load_net once first)", slot);
+    if (!s.loaded || s.desc.kind != kind) {
+        set_error("net slot %d holds no network of kind %d to refresh (call iago_load_net once first)", slot, kind);
         return IAGO_E_STATE;
     }
     const int cin[8] = {2, 64, 128, 128, 128, 128, 128, 128}, cout[8] = {64, 128, 128, 128, 128, 128, 128, 128};
@@ -682,7 +709,8 @@ int trunk_refresh_policy_slot(iago_ctx *ctx, int slot, const float *d_params, vo
         pack_forward_kernel<<<(total + 255) / 256, 256, 0, cs>>>(d_params + off, s.d_blob + s.desc.unit_base[l], cin[l], cout[l], l == 0);
         off += (size_t)cout[l] * cin[l] * 9 + cout[l];
     }
-    pack_bias_head_kernel<<<1, 128, 0, cs>>>(d_params, s.d_bias, s.d_head);
+    pack_bias_head_kernel<<<1, 128, 0, cs>>>(d_params, s.d_bias, s.d_head, kind);
+    if (kind == 1) pack_value_head_kernel<<<(18 * 8 * 16 * 8 + 255) / 256, 256, 0, cs>>>(d_params + off, s.d_blob + s.desc.unit_base[8], s.d_head);
     IAGO_CUDA(cudaGetLastError());
     return IAGO_OK;
 }
@@ -782,6 +810,12 @@ int iago_policy_forward_acts(iago_ctx *ctx, int slot, const uint64_t *p1, const 
                              float *logits, float *const *acts, int precision, void *stream) {
     IAGO_REQUIRE(acts != nullptr, "acts is NULL");
     return trunk_launch(ctx, slot, 0, p1, p2, color, n, logits, 0, precision, stream, nullptr, acts);
+}
+
+int iago_value_forward_acts(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
+                            float *values, float *const *acts, int precision, void *stream) {
+    IAGO_REQUIRE(acts != nullptr, "acts is NULL");
+    return trunk_launch(ctx, slot, 1, p1, p2, color, n, values, 0, precision, stream, nullptr, acts);
 }
 
 }  // extern "C"

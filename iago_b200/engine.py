@@ -183,6 +183,18 @@ class Engine:
                                                 C.cast(ptrs, C.c_void_p), int(precision), self._stream(stream)))
         return logits, acts
 
+    def value_forward_acts(self, slot, p1, p2, color, precision=3, stream=None):
+        """Value forward keeping every trunk block's output: (values (n,), [acts_l (n,C_l,8,8) for the 8 blocks]) CUDA tensors."""
+        torch = _torch()
+        n = self._check_i64(p1, p2)
+        dev = self._dev()
+        values = torch.empty(n, dtype=torch.float32, device=dev)
+        acts = [torch.empty((n, 64 if l == 0 else 128, 8, 8), dtype=torch.float32, device=dev) for l in range(8)]
+        ptrs = (C.c_void_p * 8)(*[a.data_ptr() for a in acts])
+        check(self.lib.iago_value_forward_acts(self.ctx, int(slot), _ptr(p1), _ptr(p2), _ptr(color), n, _ptr(values),
+                                               C.cast(ptrs, C.c_void_p), int(precision), self._stream(stream)))
+        return values, acts
+
     def value_forward(self, slot, p1, p2, color, precision=3, out=None, stream=None):
         """Value forward for n bitboard positions -> (n,) float32 CUDA tensor."""
         torch = _torch()

@@ -143,6 +143,9 @@ IAGO_API int iago_policy_forward(iago_ctx *ctx, int slot, const uint64_t *p1, co
  * forward pass of the REINFORCE update (the backward needs the activations) and a test hook for layer-by-layer parity. */
 IAGO_API int iago_policy_forward_acts(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
                                       int64_t n, float *logits, float *const *acts, int precision, void *stream);
+/* The same for the Value trunk (slot of kind 1): values [n] and the 8 blocks' outputs. */
+IAGO_API int iago_value_forward_acts(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
+                                     int64_t n, float *values, float *const *acts, int precision, void *stream);
 
 /* Value.__call__ (inference: dropout off, MCTS.py:86) -> out [n]. */
 IAGO_API int iago_value_forward(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
@@ -279,10 +282,42 @@ IAGO_API int iago_reinforce_get_state(iago_trainer *t, float *params, float *ada
 IAGO_API int iago_reinforce_set_state(iago_trainer *t, const float *params, const float *adam_m, const float *adam_v, int64_t step);
 /* use_tensor_cores != 0 (default 1): forward on the fused tcgen05 trunk, the data gradients of blocks 8..2 as one fused
  * tcgen05 launch (bf16 hi/lo split, 3 MMAs; a single bf16 pass was measured at up to 4e-2 of max|g| and is not offered), weight gradients of the 128-output-channel layers as
- * bf16 tcgen05 GEMMs, all with fp32 accumulation; 0: every kernel in fp32 on the CUDA cores (the checker for that path). */
+ * fp16 tcgen05 GEMMs (dY scaled by a power of two and split hi/lo), all with fp32 accumulation; 0: every kernel in fp32 on the CUDA cores (the checker for that path). */
 IAGO_API int iago_reinforce_set_option(iago_trainer *t, int use_tensor_cores);
 /* Makes the trainer's current parameters the policy in net slot `slot` (what self-play then plays with). */
 IAGO_API int iago_reinforce_sync_slot(iago_trainer *t, int slot);
+
+/* ---- supervised trainers: train_policy.py:16-84 (SL policy / rollout policy), train_value.py:9-70 ----
+ * The SL policy is trained with the REINFORCE entry points above (reward 1 for every record gives exactly
+ * F.softmax_cross_entropy(model(x), y), train_policy.py:61-62).  A Value trainer is created with kind 1 (970,049 floats in
+ * iago_load_net order) and shares iago_reinforce_{destroy,adam_step,get_state,set_state,set_option,sync_slot}. */
+IAGO_API int iago_trainer_create(iago_ctx *ctx, int kind, const float *params, int64_t n_floats, int max_positions, iago_trainer **out);
+/* train_value.py:50-56 for m records: own / opp = stones of "2" / "1" (channel 1 / channel 0), target = game results.
+ * grad (DEVICE float[970,049 + 2]) = gradient of SUM (v - y)^2 | that sum | m (mean_squared_error = the sum / m; the Adam step
+ * divides once).  Training-mode dropout between fc10 and fc11 (network.py:94, ratio 0.4): unit i of record r is kept when
+ * Philox(dropout_seed, position_id0 + r, i, stream 5) >= ratio, kept units scaled by 1 / (1 - ratio); ratio 0 = evaluation.
+ * pred_out (nullable, DEVICE float[m]) = the forward's outputs; mask_out (nullable, DEVICE u8[m][128]) = the dropout mask. */
+IAGO_API int iago_value_grad(iago_trainer *t, const uint64_t *own, const uint64_t *opp, const float *target, int64_t m, float *grad,
+                             int accumulate, double dropout_ratio, uint64_t dropout_seed, uint64_t position_id0, float *pred_out,
+                             uint8_t *mask_out, void *stream);
+/* Test-set metrics (train_policy.py:66-70, train_value.py:58-62), ADDED into DEVICE float out[2] (zero it first):
+ * policy: values = probabilities [n][64] (or logits when is_logits != 0): out[0] += sum softmax_cross_entropy(pred, y) with pred the
+ * probabilities (the reference applies log-softmax to them again), out[1] += correct arg-maxes (F.accuracy);
+ * value: out[0] += sum (pred - target)^2. */
+IAGO_API int iago_policy_eval(iago_ctx *ctx, const float *values, int is_logits, const int8_t *action, int64_t n, float *out, void *stream);
+IAGO_API int iago_value_eval(iago_ctx *ctx, const float *pred, const float *target, int64_t n, float *out, void *stream);
+/* RolloutPolicy trainer (train_policy.py --policy rollout): 82 parameters = conv1/W [1][2][3][3] then bias2/b [64].
+ * grad (DEVICE float[84]) = gradient of SUM softmax_cross_entropy | that sum | m; state (HOST float[3][82]) = params | Adam m | v. */
+typedef struct iago_rollout_trainer iago_rollout_trainer;
+IAGO_API int iago_rollout_trainer_create(iago_ctx *ctx, const float *conv1_W, const float *bias2_b, iago_rollout_trainer **out);
+IAGO_API int iago_rollout_trainer_destroy(iago_rollout_trainer *t);
+IAGO_API int iago_rollout_trainer_grad(iago_rollout_trainer *t, const uint64_t *own, const uint64_t *opp, const int8_t *action,
+                                       int64_t m, float *grad, int accumulate, void *stream);
+IAGO_API int iago_rollout_trainer_adam_step(iago_rollout_trainer *t, const float *grad, double count, double alpha, double beta1,
+                                            double beta2, double eps, double weight_decay, void *stream);
+IAGO_API int iago_rollout_trainer_get_state(iago_rollout_trainer *t, float *state, int64_t *step);
+IAGO_API int iago_rollout_trainer_set_state(iago_rollout_trainer *t, const float *state, int64_t step);
+
 
 /* Integer-issue micro-benchmark used as the roofline denominator of the rollout kernel:
  * runs `iters` rounds of dependent LOP3/SHF chains on every SM and returns int32 lane-ops/s. */

@@ -81,11 +81,11 @@ def test_gradient_matches_autograd(engine):
 
 def test_tensor_core_path(engine, mode=1):
     """tensor_cores=1: forward on the fused tcgen05 trunk (fp16 hi/lo split), data gradients as one fused tcgen05 chain (bf16
-    hi/lo split), weight gradients as bf16 tcgen05 GEMMs.
+    hi/lo split), weight gradients as fp16 tcgen05 GEMMs.
     (1) The forward's activations equal the float64 forward within 2e-4; its ReLU on/off decisions differ from the float64
         ones ONLY on units whose pre-activation is within 2e-4 of zero (the kink, where the derivative is ambiguous).
-    (2) With those on/off decisions taken as given, the gradient equals float64 autograd within 1e-2 * max|g| per tensor
-        (bf16 weight-gradient operands, fp32 accumulation); loss numerator within 1e-4 relative."""
+    (2) With those on/off decisions taken as given, the gradient equals float64 autograd within 3e-3 * max|g| per tensor
+        (measured 8e-4: fp16 weight-gradient operands with dY scaled and split hi/lo, fp32 accumulation); loss numerator within 1e-4 relative."""
     import torch
     from iago_b200 import npz
     from iago_b200.train_rl import ReinforceTrainer, N_PARAMS
@@ -117,7 +117,7 @@ def test_tensor_core_path(engine, mode=1):
     worst = max(e / s_ for e, s_ in errs.values() if s_ > 0)
     print(f"tensor-core path (mode {mode}): {flips} ReLU decisions at the kink differ from float64; worst per-tensor gradient error {worst:.2e} of max|g|")
     for k, (e, scale) in errs.items():
-        assert e <= 1e-2 * scale + 1e-6, (k, e, scale)
+        assert e <= 3e-3 * scale + 1e-6, (k, e, scale)
     tr.close()
 
 

@@ -82,6 +82,8 @@ int iago_ctx_destroy(iago_ctx *ctx) {
     cudaFree(ctx->d_counters);
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
+    for (int c = 1; c < 4; c++)
+        if (ctx->host_streams[c]) cudaStreamDestroy(ctx->host_streams[c]);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return IAGO_OK;

@@ -33,6 +33,7 @@ struct iago_ctx {
     int device = -1;
     int sm_count = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t host_streams[4] = {};   // iago_rollout_host's chunk pipeline ([0] = stream, the others are created on first use)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timed = false;
     iago::RolloutWeights *d_rollout = nullptr;

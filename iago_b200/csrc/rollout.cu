@@ -608,6 +608,12 @@ int iago_rollout(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const ui
     return rollout_launch(ctx, a, rng->mode, s);
 }
 
+// Host-buffer entry point.  The batch is cut into up to kHostChunks chunks, each with its own region of the pinned / device
+// staging buffers and its own stream: while chunk c runs, chunk c+1 is being copied in and chunk c-1 copied out, and the host-side
+// packing / unpacking of the pinned buffer overlaps with all of it.  Philox game ids stay global (game_id0 + index), so the
+// results do not depend on the chunking.
+constexpr int kHostChunks = 4;
+
 int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
                       const iago_rng *rng, int8_t *result, uint64_t *final_p1, uint64_t *final_p2,
                       int32_t *n_moves, int8_t *move_log, uint64_t *counters_host) {
@@ -615,45 +621,69 @@ int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, con
     IAGO_REQUIRE(n >= 0, "n < 0");
     int rc = check_rng(rng, true, ctx);
     if (rc) return rc;
+    if (counters_host) counters_host[0] = counters_host[1] = 0;
     if (n == 0) return IAGO_OK;
     DeviceGuard guard(ctx->device);
     auto up8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
-    const size_t N = (size_t)n;
-    // input block: p1 | p2 | color | replay stream ; output block: fp1 | fp2 | n_moves | counters | result | log
-    const size_t o_p1 = 0, o_p2 = o_p1 + 8 * N, o_col = o_p2 + 8 * N;
-    size_t o_rep = o_col + up8(N), rep_bytes = 0;
-    if (rng->mode == IAGO_RNG_UNIFORMS) rep_bytes = 8 * N * (size_t)rng->u_stride;
-    if (rng->mode == IAGO_RNG_FORCED) rep_bytes = up8(N * (size_t)rng->f_stride);
-    const size_t in_bytes = o_rep + rep_bytes;
-    const size_t o_f1 = in_bytes, o_f2 = o_f1 + 8 * N, o_nm = o_f2 + 8 * N, o_cnt = o_nm + up8(4 * N);
-    const size_t o_res = o_cnt + 16, o_log = o_res + up8(N);
-    const size_t out_end = o_log + (move_log ? 64 * N : 0);
-    rc = ensure_staging(ctx, out_end);
+    const int chunks = n >= 4 * 4096 ? kHostChunks : 1;
+    const size_t per = (((size_t)n + chunks - 1) / chunks + 63) & ~(size_t)63;   // games per chunk, a whole number of CTAs
+    // per-chunk region: input block p1 | p2 | color | replay stream ; output block fp1 | fp2 | n_moves | counters | result | log
+    const size_t u_stride = rng->mode == IAGO_RNG_UNIFORMS ? (size_t)rng->u_stride : 0;
+    const size_t f_stride = rng->mode == IAGO_RNG_FORCED ? (size_t)rng->f_stride : 0;
+    const size_t o_p1 = 0, o_p2 = o_p1 + 8 * per, o_col = o_p2 + 8 * per, o_rep = o_col + up8(per);
+    const size_t in_bytes = o_rep + 8 * per * u_stride + up8(per * f_stride);
+    const size_t o_f1 = in_bytes, o_f2 = o_f1 + 8 * per, o_nm = o_f2 + 8 * per, o_cnt = o_nm + up8(4 * per);
+    const size_t o_res = o_cnt + 16, o_log = o_res + up8(per);
+    const size_t region = up8(o_log + (move_log ? 64 * per : 0)) + 64;
+    rc = ensure_staging(ctx, region * chunks);
     if (rc) return rc;
-    char *h = (char *)ctx->stage.host, *d = (char *)ctx->stage.dev;
-    memcpy(h + o_p1, p1, 8 * N);
-    memcpy(h + o_p2, p2, 8 * N);
-    memcpy(h + o_col, color, N);
-    if (rng->mode == IAGO_RNG_UNIFORMS) memcpy(h + o_rep, rng->uniforms, rep_bytes);
-    if (rng->mode == IAGO_RNG_FORCED) memcpy(h + o_rep, rng->forced, N * (size_t)rng->f_stride);
-    cudaStream_t s = ctx->stream;
-    IAGO_CUDA(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));
-    IAGO_CUDA(cudaMemsetAsync(d + o_cnt, 0, 16, s));
-    RolloutArgs a{(const u64 *)(d + o_p1), (const u64 *)(d + o_p2), (const uint8_t *)(d + o_col), n,
-                  rng->stream_id, rng->seed, rng->game_id0, (const double *)(d + o_rep), rng->u_stride,
-                  (const int8_t *)(d + o_rep), rng->f_stride, (int8_t *)(d + o_res), (u64 *)(d + o_f1),
-                  (u64 *)(d + o_f2), (int32_t *)(d + o_nm), move_log ? (int8_t *)(d + o_log) : nullptr,
-                  (u64 *)(d + o_cnt), nullptr};
-    rc = rollout_launch(ctx, a, rng->mode, s);
-    if (rc) return rc;
-    IAGO_CUDA(cudaMemcpyAsync(h + o_f1, d + o_f1, out_end - o_f1, cudaMemcpyDeviceToHost, s));
-    IAGO_CUDA(cudaStreamSynchronize(s));
-    memcpy(final_p1, h + o_f1, 8 * N);
-    memcpy(final_p2, h + o_f2, 8 * N);
-    memcpy(result, h + o_res, N);
-    if (n_moves) memcpy(n_moves, h + o_nm, 4 * N);
-    if (move_log) memcpy(move_log, h + o_log, 64 * N);
-    if (counters_host) memcpy(counters_host, h + o_cnt, 16);
+    if (!ctx->host_streams[0]) {
+        ctx->host_streams[0] = ctx->stream;
+        for (int c = 1; c < kHostChunks; c++) IAGO_CUDA(cudaStreamCreateWithFlags(&ctx->host_streams[c], cudaStreamNonBlocking));
+    }
+    for (int c = 0; c < chunks; c++) {
+        const size_t g0 = (size_t)c * per;
+        if (g0 >= (size_t)n) break;
+        const size_t N = ((size_t)n - g0 < per) ? (size_t)n - g0 : per;
+        char *h = (char *)ctx->stage.host + region * c, *d = (char *)ctx->stage.dev + region * c;
+        cudaStream_t s = ctx->host_streams[c];
+        memcpy(h + o_p1, p1 + g0, 8 * N);
+        memcpy(h + o_p2, p2 + g0, 8 * N);
+        memcpy(h + o_col, color + g0, N);
+        if (u_stride) memcpy(h + o_rep, rng->uniforms + g0 * u_stride, 8 * N * u_stride);
+        if (f_stride) memcpy(h + o_rep, rng->forced + g0 * f_stride, N * f_stride);
+        IAGO_CUDA(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));
+        IAGO_CUDA(cudaMemsetAsync(d + o_cnt, 0, 16, s));
+        RolloutArgs a{(const u64 *)(d + o_p1), (const u64 *)(d + o_p2), (const uint8_t *)(d + o_col), (long long)N,
+                      rng->stream_id, rng->seed, rng->game_id0 + g0, (const double *)(d + o_rep), rng->u_stride,
+                      (const int8_t *)(d + o_rep), rng->f_stride, (int8_t *)(d + o_res), (u64 *)(d + o_f1),
+                      (u64 *)(d + o_f2), (int32_t *)(d + o_nm), move_log ? (int8_t *)(d + o_log) : nullptr,
+                      (u64 *)(d + o_cnt), nullptr};
+        if (c == 0) IAGO_CUDA(cudaEventRecord(ctx->ev0, s));
+        launch_rollout_mode(a, rng->mode, ctx->rollout_fast, ctx->d_rollout, s);
+        IAGO_CUDA(cudaGetLastError());
+        if (c == 0) IAGO_CUDA(cudaEventRecord(ctx->ev1, s));   // iago_last_kernel_ms: the first chunk's launch (the whole batch when n < 16,384)
+        IAGO_CUDA(cudaMemcpyAsync(h + o_f1, d + o_f1, (move_log ? o_log + 64 * N : o_res + N) - o_f1, cudaMemcpyDeviceToHost, s));
+    }
+    ctx->timed = true;
+    for (int c = 0; c < chunks; c++) {
+        const size_t g0 = (size_t)c * per;
+        if (g0 >= (size_t)n) break;
+        const size_t N = ((size_t)n - g0 < per) ? (size_t)n - g0 : per;
+        const char *h = (const char *)ctx->stage.host + region * c;
+        IAGO_CUDA(cudaStreamSynchronize(ctx->host_streams[c]));
+        memcpy(final_p1 + g0, h + o_f1, 8 * N);
+        memcpy(final_p2 + g0, h + o_f2, 8 * N);
+        memcpy(result + g0, h + o_res, N);
+        if (n_moves) memcpy(n_moves + g0, h + o_nm, 4 * N);
+        if (move_log) memcpy(move_log + 64 * g0, h + o_log, 64 * N);
+        if (counters_host) {
+            uint64_t cnt[2];
+            memcpy(cnt, h + o_cnt, 16);
+            counters_host[0] += cnt[0];
+            counters_host[1] += cnt[1];
+        }
+    }
     return IAGO_OK;
 }
 

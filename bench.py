@@ -32,9 +32,10 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 GAMES_PER_STEP = 65536
-OPS_PER_PLY = 676          # int32 ALU lane-ops per ply: movegen 314 + flip 352 + ~10
+OPS_PER_PLY = 676          # int32 ALU lane-ops per ply: movegen 314 + flip 352 + ~10 (SURVEY.md §8d, step-by-step 6-step flood)
+OPS_PER_PLY_IMPL = 548     # the same rules with the parallel-prefix flood of bitboard.cuh: movegen 250 + flip 288 + ~10
 BYTES_PER_GAME = 17 + 21   # p1,p2,colour in; final p1,p2,n_moves,result out
-NCU_DRAM_BYTES_PER_LAUNCH = 1145856   # profiles/r01_ncu_rollout_v2_summary.csv (dram__bytes_read.sum; write 0), 65,536-game launch
+NCU_DRAM_BYTES_PER_LAUNCH = 1145856   # profiles/r01_ncu_rollout_v3_summary.csv (dram__bytes_read.sum; write 0), 65,536-game launch
 METRIC = "rollout_plies_per_s"
 
 
@@ -357,14 +358,20 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "alu", "kernel": "rollout_kernel<PHILOX>", "achieved": achieved / 1e12,
                          "peak": int_peak / 1e12, "unit": "Tint32op/s", "frac": achieved / int_peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == GAMES_PER_STEP else None,
-                         "note": "issue-bound path: 676 algorithmic int32 lane-ops/ply x plies per launch / mean launch "
+                         "ops_per_ply_as_implemented": OPS_PER_PLY_IMPL,
+                         "frac_as_implemented": OPS_PER_PLY_IMPL * plies_per_launch / kernel_s / int_peak,
+                         "note": "issue-bound path: 676 algorithmic int32 lane-ops/ply (SURVEY 8d: 6-step flood formulation) x plies per launch / mean launch "
                                  "time; peak = SHF+LOP3 micro-kernel measured in this run (iago_measure_int_peak); traffic = "
-                                 "dram__bytes_read+write per launch from the ncu --set full capture in profiles/r01_ncu_rollout_v2_summary.csv "
+                                 "dram__bytes_read+write per launch from the ncu --set full capture in profiles/r01_ncu_rollout_v3_summary.csv "
                                  "(algorithmic bytes per launch: 38 B x 65,536 games = 2.49 MB; outputs stay in L2 during the capture)"},
             "roofline_movegen": {"bound": "alu", "kernel": "rollout_kernel<FORCED> (legal_moves + flips + pass/terminal/score only, moves "
                                  "replayed from a 64 B/game log)", "plies_per_s": mg_plies / t_mg,
                                  "achieved": OPS_PER_PLY * mg_plies / t_mg / 1e12, "peak": int_peak / 1e12, "unit": "Tint32op/s",
-                                 "frac": OPS_PER_PLY * mg_plies / t_mg / int_peak, "traffic": None, "scope": "rank 0"},
+                                 "frac": OPS_PER_PLY * mg_plies / t_mg / int_peak, "traffic": None, "scope": "rank 0",
+                                 "ops_per_ply_as_implemented": OPS_PER_PLY_IMPL,
+                                 "frac_as_implemented": OPS_PER_PLY_IMPL * mg_plies / t_mg / int_peak,
+                                 "note": "the kernel floods with a parallel-prefix (Kogge-Stone) form that needs ~548 int32 lane-ops per ply "
+                                         "instead of the 676 of the step-by-step form SURVEY 8d counts, so the fraction on the 676 count can exceed 1"},
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                              "frac": hbm_ach / hbm_peak, "traffic": None,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",

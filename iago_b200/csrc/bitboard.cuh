@@ -2,7 +2,7 @@
 //
 // Replaces the reference's per-cell ray walks (GameFunctions.legal_actions game.py:209-235 and
 // place_stone game.py:179-207, copy-pasted into mcts_self_play.py:36-89, src/rl_self_play.py:36-88,
-// rl_env.py:88-138) with shift-and-mask floods.  Bit k <-> action k = row*8+col, so ascending bit
+// rl_env.py:88-138) with shift-and-mask floods (parallel-prefix form).  Bit k <-> action k = row*8+col, so ascending bit
 // order is the reference's ascending action list.
 //
 //   own = stones of the side to move, opp = the other side.
@@ -29,27 +29,31 @@ IAGO_HD u64 shl(u64 x) { return x << S; }
 template <int S>
 IAGO_HD u64 shr(u64 x) { return x >> S; }
 
-// 6-step flood of `gen` through `mask` along +S (left shift) and the bracket cell beyond it.
+// Flood of `gen` through `mask` along +S (left shift) / -S, Kogge-Stone style: after the first two steps a run of up to 2
+// stones is covered, each doubling step (through `pre` = stones whose neighbour in the direction of travel is also in the mask)
+// adds 2 more, so four dependent steps cover the longest possible run on an 8-wide board (6) where a step-by-step flood needs six.
 template <int S>
-IAGO_HD u64 moves_up(u64 own, u64 mask) {
-    u64 t = mask & (own << S);
+IAGO_HD u64 fill_up(u64 gen, u64 mask) {
+    u64 t = mask & (gen << S);
     t |= mask & (t << S);
-    t |= mask & (t << S);
-    t |= mask & (t << S);
-    t |= mask & (t << S);
-    t |= mask & (t << S);
-    return t << S;
+    const u64 pre = mask & (mask << S);
+    t |= pre & (t << (2 * S));
+    t |= pre & (t << (2 * S));
+    return t;
 }
 template <int S>
-IAGO_HD u64 moves_dn(u64 own, u64 mask) {
-    u64 t = mask & (own >> S);
+IAGO_HD u64 fill_dn(u64 gen, u64 mask) {
+    u64 t = mask & (gen >> S);
     t |= mask & (t >> S);
-    t |= mask & (t >> S);
-    t |= mask & (t >> S);
-    t |= mask & (t >> S);
-    t |= mask & (t >> S);
-    return t >> S;
+    const u64 pre = mask & (mask >> S);
+    t |= pre & (t >> (2 * S));
+    t |= pre & (t >> (2 * S));
+    return t;
 }
+template <int S>
+IAGO_HD u64 moves_up(u64 own, u64 mask) { return fill_up<S>(own, mask) << S; }   // the bracket cell beyond the run
+template <int S>
+IAGO_HD u64 moves_dn(u64 own, u64 mask) { return fill_dn<S>(own, mask) >> S; }
 
 // legal_actions: empty cells from which some direction has >= 1 opponent stone and then an own stone.
 IAGO_HD u64 legal_moves(u64 own, u64 opp) {
@@ -63,22 +67,12 @@ IAGO_HD u64 legal_moves(u64 own, u64 opp) {
 
 template <int S>
 IAGO_HD u64 flips_up(u64 mv, u64 own, u64 mask) {
-    u64 t = mask & (mv << S);
-    t |= mask & (t << S);
-    t |= mask & (t << S);
-    t |= mask & (t << S);
-    t |= mask & (t << S);
-    t |= mask & (t << S);
+    const u64 t = fill_up<S>(mv, mask);
     return ((t << S) & own) ? t : 0ULL;
 }
 template <int S>
 IAGO_HD u64 flips_dn(u64 mv, u64 own, u64 mask) {
-    u64 t = mask & (mv >> S);
-    t |= mask & (t >> S);
-    t |= mask & (t >> S);
-    t |= mask & (t >> S);
-    t |= mask & (t >> S);
-    t |= mask & (t >> S);
+    const u64 t = fill_dn<S>(mv, mask);
     return ((t >> S) & own) ? t : 0ULL;
 }
 

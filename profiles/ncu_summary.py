@@ -1,0 +1,32 @@
+#!/usr/bin/env python
+"""Key metrics of the kernels in an ncu report as CSV: python profiles/ncu_summary.py report.ncu-rep [name-substring] > summary.csv"""
+import csv, subprocess, sys
+METRICS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "smsp__inst_executed.sum", "launch__block_size",
+           "launch__grid_size", "launch__registers_per_thread", "launch__waves_per_multiprocessor",
+           "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+           "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+           "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+           "sm__inst_executed_pipe_tensor.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+           "smsp__thread_inst_executed_per_inst_executed.ratio", "sm__warps_active.avg.pct_of_peak_sustained_active",
+           "sm__throughput.avg.pct_of_peak_sustained_elapsed", "dram__throughput.avg.pct_of_peak_sustained_elapsed",
+           "lts__t_bytes.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+           "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio", "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio", "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+           "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio", "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio"]
+out = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, units = rows[0], rows[1]
+want = sys.argv[2] if len(sys.argv) > 2 else ""
+w = csv.writer(sys.stdout)
+w.writerow(["kernel", "metric", "unit", "value"])
+seen = {}
+for r in rows[2:]:
+    name = r[hdr.index("Kernel Name")]
+    if want not in name:
+        continue
+    k = seen[name] = seen.get(name, 0) + 1
+    if k > 1:
+        continue          # first captured launch of each kernel
+    for m in METRICS:
+        if m in hdr:
+            w.writerow([name.split("(")[0][:60], m, units[hdr.index(m)], r[hdr.index(m)]])

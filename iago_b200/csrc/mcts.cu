@@ -142,9 +142,15 @@ __global__ void __launch_bounds__(32) mcts_select_kernel(MctsDev d, MctsParams p
             own = color == 1 ? d.leaf_p1[slot] : d.leaf_p2[slot];
             opp = color == 1 ? d.leaf_p2[slot] : d.leaf_p1[slot];
         }
-        for (;;) {  // ends at a leaf: every step goes one level down a finite pool
+        // Header of the node the descent stands on.  Loaded from memory for the starting node only: while the children are scored
+        // every lane already holds its child's whole node, so the winner's header and action come by shuffle and each level costs
+        // ONE dependent round of loads (the children of the chosen node) instead of three.
+        int nch, flags, n_here, vn_here, fc;
+        {
             const MctsNode *nd = nodes + node;
-            const int nch = nd->nch, flags = nd->flags, n_here = nd->n, vn_here = nd->vn, fc = nd->first_child;
+            nch = nd->nch; flags = nd->flags; n_here = nd->n; vn_here = nd->vn; fc = nd->first_child;
+        }
+        for (;;) {  // ends at a leaf: every step goes one level down a finite pool
             if (nch == 0) {
                 bool park = (flags & F_PENDING) != 0;
                 if (!park && n_here >= p.n_thr) {  // MCTS.py:108-121 expand
@@ -165,6 +171,8 @@ __global__ void __launch_bounds__(32) mcts_select_kernel(MctsDev d, MctsParams p
                         if (k <= 1) {
                             if (lane == 0) { nodes[node].first_child = base; nodes[node].nch = (uint8_t)c; }
                             __syncwarp();
+                            fc = base;
+                            nch = c;
                             continue;  // the playout goes on through the only child (MCTS.py:121)
                         }
                         if (lane == 0) {
@@ -214,34 +222,49 @@ __global__ void __launch_bounds__(32) mcts_select_kernel(MctsDev d, MctsParams p
             const double sq = __dsqrt_rn(n_parent);
             double best = -1.0e300;
             int best_i = 1 << 30;
+            int b_n = 0, b_vn = 0, b_fc = -1, b_meta = 0;   // the best child of THIS lane: n, vn, first_child, action | nch | flags | nch_pending
             for (int i = lane; i < nch; i += 32) {
-                const MctsNode *ch = nodes + fc + i;
-                const int cn = ch->n, cvn = ch->vn;
-                const double cp = (ch->flags & F_P_F64) ? __dmul_rn(p.c_puct, ch->P)
-                                                         : (double)__fmul_rn((float)p.c_puct, (float)ch->P);
+                const uint4 *raw = reinterpret_cast<const uint4 *>(nodes + fc + i);
+                const uint4 w0 = raw[0], w1 = raw[1], w2 = raw[2];       // P Q | W v n | vn parent first_child meta
+                const double cP = __hiloint2double((int)w0.y, (int)w0.x), cQ = __hiloint2double((int)w0.w, (int)w0.z);
+                const long long cW = (long long)(((u64)w1.y << 32) | (u64)w1.x);
+                const int cn = (int)w1.w, cvn = (int)w2.x, cflags = (int)((w2.w >> 16) & 0xFFu);
+                const double cp = (cflags & F_P_F64) ? __dmul_rn(p.c_puct, cP) : (double)__fmul_rn((float)p.c_puct, (float)cP);
                 double q, den;
                 if (p.exact) {
-                    q = ch->Q;
+                    q = cQ;
                     den = __dadd_rn(0.01, (double)cn);
                 } else {
                     const int tot = cn + cvn;
-                    q = tot > 0 ? __ddiv_rn(__dsub_rn((double)ch->W * (1.0 / kFix), __dmul_rn(p.vloss, (double)cvn)), (double)tot) : 0.0;
+                    q = tot > 0 ? __ddiv_rn(__dsub_rn((double)cW * (1.0 / kFix), __dmul_rn(p.vloss, (double)cvn)), (double)tot) : 0.0;
                     den = __dadd_rn(0.01, (double)tot);
                 }
                 const double u = __ddiv_rn(__dmul_rn(cp, sq), den);
                 const double val = __dadd_rn(q, u);
-                if (val > best) { best = val; best_i = i; }  // ascending i: the first maximum stays
+                if (val > best) {  // ascending i: the first maximum stays
+                    best = val; best_i = i;
+                    b_n = cn; b_vn = cvn; b_fc = (int)w2.z; b_meta = (int)w2.w;
+                }
             }
+            int win = lane;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
                 const double ov = shfl_down_d(best, o);
                 const int oi = __shfl_down_sync(0xFFFFFFFFu, best_i, o);
-                if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+                const int ow = __shfl_down_sync(0xFFFFFFFFu, win, o);
+                if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; win = ow; }
             }
+            win = __shfl_sync(0xFFFFFFFFu, win, 0);
             best_i = __shfl_sync(0xFFFFFFFFu, best_i, 0);
             const int child = fc + best_i;
-            const int act = nodes[child].action;
-            if (lane == 0) nodes[child].vn += 1;
+            n_here = __shfl_sync(0xFFFFFFFFu, b_n, win);
+            vn_here = __shfl_sync(0xFFFFFFFFu, b_vn, win) + 1;   // with this descent's own virtual visit, stored below
+            fc = __shfl_sync(0xFFFFFFFFu, b_fc, win);
+            const int meta = __shfl_sync(0xFFFFFFFFu, b_meta, win);
+            const int act = (int)(int8_t)(meta & 0xFF);
+            nch = (meta >> 8) & 0xFF;
+            flags = (meta >> 16) & 0xFF;
+            if (lane == 0) nodes[child].vn = vn_here;
             if (act >= 0) place(1ULL << act, own, opp);   // action -1 = pass = no-op (game.py:181-182)
             { const u64 tmp = own; own = opp; opp = tmp; }
             color = 3 - color;

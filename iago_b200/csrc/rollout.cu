@@ -430,6 +430,7 @@ static double canon_exp(double x) {
 // overflow / underflow; 63 terms of at most e^300 sum to a finite double).
 static bool build_rollout_weights(const float *W, const float *b, RolloutWeights *out) {
     float amax[2] = {0.0f, 0.0f}, bmax = 0.0f;
+    int finite = 1;
     for (int c = 0; c < 2; c++)
         for (int idx = 0; idx < 512; idx++) {
             float acc = 0.0f;
@@ -438,15 +439,17 @@ static bool build_rollout_weights(const float *W, const float *b, RolloutWeights
             out->lut[c][idx] = acc;
             out->elut[c][idx] = canon_exp((double)acc);
             if (fabsf(acc) > amax[c]) amax[c] = fabsf(acc);
+            if (!(fabsf(acc) <= 300.0f)) finite = 0;   /* also catches NaN */
         }
     memcpy(out->bias, b, 64 * sizeof(float));
     for (int k = 0; k < 64; k++) {
         out->ebias[k] = canon_exp((double)b[k]);
         if (fabsf(b[k]) > bmax) bmax = fabsf(b[k]);
+        if (!(fabsf(b[k]) <= 300.0f)) finite = 0;
     }
     for (int j = 0; j < 8; j++) out->colmask[j] = 0x070707u & ~(j == 0 ? 0x010101u : 0u) & ~(j == 7 ? 0x040404u : 0u);
     const float span = amax[0] + amax[1] + bmax;
-    return span <= 300.0f;   // NaN / inf weights fail the comparison and take the SAFE path
+    return finite && span <= 300.0f;   // NaN / inf weights take the SAFE path
 }
 
 template <int MODE, bool FAST>

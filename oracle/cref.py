@@ -46,6 +46,10 @@ def lib():
         L.oracle_exp32_neg.restype = C.c_float
         L.oracle_rollout_logits.argtypes = [_f32p, C.c_int, _f32p, _f32p, _f32p]
         L.oracle_rollout_logits.restype = None
+        L.oracle_policy_is_fast.argtypes = [_f32p, _f32p]
+        L.oracle_policy_is_fast.restype = C.c_int
+        L.oracle_canon_exp.argtypes = [C.c_double]
+        L.oracle_canon_exp.restype = C.c_double
         L.oracle_rollout_sample.argtypes = [_f32p, C.c_int, _f32p, _f32p, C.c_double]
         L.oracle_rollout_sample.restype = C.c_int
         L.oracle_simulate_batch.argtypes = [
@@ -104,6 +108,17 @@ def rollout_logits(state, color, W, b):
                                 np.ascontiguousarray(W, np.float32).reshape(18),
                                 np.ascontiguousarray(b, np.float32).reshape(64), out)
     return out
+
+
+def policy_is_fast(W, b):
+    """Which sampler the weights select (oracle/othello_ref.c header): True = product-of-exponentials tables."""
+    W = np.ascontiguousarray(W, np.float32).reshape(18)
+    b = np.ascontiguousarray(b, np.float32).reshape(64)
+    return bool(lib().oracle_policy_is_fast(W, b))
+
+
+def canon_exp(x):
+    return float(lib().oracle_canon_exp(float(x)))
 
 
 def rollout_sample(state, color, W, b, u):

@@ -243,18 +243,21 @@ typedef struct {
 
 static void build_tables(const float *W, const float *b, policy_tables *t) {
     float amax[2] = {0.0f, 0.0f}, bmax = 0.0f;
+    int finite = 1;
     for (int c = 0; c < 2; c++)
         for (int pat = 0; pat < 512; pat++) {
             float acc = 0.0f;
             for (int k = 0; k < 9; k++) if (pat >> k & 1) acc = acc + W[c * 9 + k];
             t->E[c][pat] = canon_exp((double)acc);
             if (fabsf(acc) > amax[c]) amax[c] = fabsf(acc);
+            if (!(fabsf(acc) <= 300.0f)) finite = 0;   /* also catches NaN */
         }
     for (int k = 0; k < 64; k++) {
         t->EB[k] = canon_exp((double)b[k]);
         if (fabsf(b[k]) > bmax) bmax = fabsf(b[k]);
+        if (!(fabsf(b[k]) <= 300.0f)) finite = 0;
     }
-    t->fast = (amax[0] + amax[1] + bmax) <= 300.0f;
+    t->fast = finite && (amax[0] + amax[1] + bmax) <= 300.0f;
 }
 
 EXPORT int oracle_policy_is_fast(const float *W, const float *b) {

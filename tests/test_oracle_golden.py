@@ -137,3 +137,14 @@ print(json.dumps(out))
     g = golden_simulate
     for i, (r, final) in enumerate(got):
         assert g["seed"][i] == 12345 + i and r == g["result"][i] and final == g["final"][i].tolist()
+
+
+def test_canon_exp_and_sampler_choice(cref, rollout_weights):
+    """canon_exp (the table builder shared, operation for operation, by the oracle and the library) is exp to ~1 ulp of a double,
+    and the committed rollout weights select the table sampler; absurd weights select the exp32 fallback."""
+    xs = np.concatenate([np.linspace(-300, 300, 2001), [0.0, -1e-9, 1e-9, 88.7, -87.3]])
+    got = np.array([cref.canon_exp(x) for x in xs])
+    assert np.max(np.abs(got - np.exp(xs)) / np.exp(xs)) < 5e-16
+    W, b = rollout_weights
+    assert cref.policy_is_fast(W, b)
+    assert not cref.policy_is_fast(W * 40, b) and not cref.policy_is_fast(W * np.float32("nan"), b)

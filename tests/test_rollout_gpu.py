@@ -185,3 +185,33 @@ def test_empty_and_error_paths(engine):
     with pytest.raises(iago_b200.IagoError):
         engine.legal_actions(torch.zeros(4, dtype=torch.int32, device="cuda"), torch.zeros(4, dtype=torch.int32, device="cuda"),
                              torch.ones(4, dtype=torch.uint8, device="cuda"))
+
+
+def test_fallback_sampler_and_host_chunking(engine, cref, rollout_weights):
+    """(1) Weights whose tap sums could leave +-300 take the exp32 + fixed-point sampler in the library and in the oracle alike:
+    trajectories stay bit exact.  (2) iago_rollout_host cuts large batches into pipelined chunks: sizes around the chunk
+    boundaries (not multiples of 64, one game more / less than four CTAs' worth) give the oracle's games, and n = 0 is a no-op."""
+    from iago_b200 import Rng, boards
+    W, b = rollout_weights
+    try:
+        Wbig = (W * 40).astype(np.float32)
+        assert not cref.policy_is_fast(Wbig, b)
+        engine.load_rollout(Wbig, b)
+        n = 4096
+        p1, p2 = np.full(n, boards.START_P1, np.uint64), np.full(n, boards.START_P2, np.uint64)
+        out = engine.rollout_host(p1, p2, np.ones(n, np.uint8), rng=Rng.philox(seed=5), want_moves=True)
+        st = np.tile(boards.start_state().reshape(1, 64), (n, 1))
+        ref = cref.simulate_batch(st, 1, Wbig, b, mode=cref.RNG_PHILOX, seed=5, threads=0)
+        assert (out["moves"] == ref["moves"]).all() and (out["result"] == ref["results"]).all()
+    finally:
+        engine.load_rollout(W, b)
+    for n in (0, 1, 63, 16383, 16384, 16385, 70001):
+        p1, p2 = np.full(n, boards.START_P1, np.uint64), np.full(n, boards.START_P2, np.uint64)
+        out = engine.rollout_host(p1, p2, np.ones(n, np.uint8), rng=Rng.philox(seed=9, game_id0=12345), want_moves=True)
+        if n == 0:
+            assert int(out["counters"][0]) == 0
+            continue
+        st = np.tile(boards.start_state().reshape(1, 64), (n, 1))
+        ref = cref.simulate_batch(st, 1, W, b, mode=cref.RNG_PHILOX, seed=9, game_id0=12345, threads=0)
+        assert (out["moves"] == ref["moves"]).all() and (out["result"] == ref["results"]).all(), n
+        assert int(out["counters"][0]) == int(ref["n_moves"].sum()) and int(out["counters"][1]) == int(ref["n_turns"].sum()), n

@@ -297,24 +297,38 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
         // ================= producers: fp32 global -> 16-bit core matrices in shared memory =================
         // Software-pipelined through registers: the 16 x 16-byte loads of position p+1 are in flight while position p is
         // converted and stored, so HBM/L2 latency is covered without a third shared-memory stage.
+        // Work item = one (channel, board row) chunk of 8 cells = 32 B of fp32 in, one 16-byte core-matrix row out.  Lane bits: channel % 8
+        // in bits 0-2, row % 4 in bits 3-4, so the 8 lanes of a quarter warp write 8 consecutive 16-byte slots (no bank conflicts; the
+        // row-fastest mapping it replaces was an 8-way conflict on every store) while a warp still reads whole 128-byte lines.
         uint32_t stage = 0, phase = 0;
         const int xchunks = cin >> 5;                 // (cin * 8 rows) / 256 threads = 4 (cin 128) or 2 (cin 64)
+        const int lane = tid & 31, ch_low = lane & 7, row_low = lane >> 3;
+        int a_ch[4], a_row[4], x_ch[4], x_row[4];
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            const int ca = (tid >> 5) * 4 + it;       // 0..31 -> (channel group 0..15, upper row half)
+            a_ch[it] = (ca >> 1) * 8 + ch_low;
+            a_row[it] = (ca & 1) * 4 + row_low;
+            const int cx = (tid >> 5) * xchunks + it; // 0..8*xchunks-1 -> (channel group 0..cin/8-1, upper row half)
+            x_ch[it] = (cx >> 1) * 8 + ch_low;
+            x_row[it] = (cx & 1) * 4 + row_low;
+        }
         float4 cur[16], nxt[16];
         auto load = [&](float4 (&r)[16], long long p) {
             const float *dsrc = dy + (size_t)p * 128 * 64;
             const float *xsrc = x + (size_t)p * cin * 64;
 #pragma unroll
             for (int it = 0; it < 4; it++) {
-                const int chunk = tid + it * 256;       // (o, row): consecutive threads read consecutive 32 B
-                r[2 * it] = __ldg(reinterpret_cast<const float4 *>(dsrc + chunk * 8));
-                r[2 * it + 1] = __ldg(reinterpret_cast<const float4 *>(dsrc + chunk * 8 + 4));
+                const float *q = dsrc + a_ch[it] * 64 + a_row[it] * 8;
+                r[2 * it] = __ldg(reinterpret_cast<const float4 *>(q));
+                r[2 * it + 1] = __ldg(reinterpret_cast<const float4 *>(q + 4));
             }
 #pragma unroll
             for (int it = 0; it < 4; it++) {
                 if (it < xchunks) {
-                    const int chunk = tid + it * 256;   // (c, row)
-                    r[8 + 2 * it] = __ldg(reinterpret_cast<const float4 *>(xsrc + chunk * 8));
-                    r[8 + 2 * it + 1] = __ldg(reinterpret_cast<const float4 *>(xsrc + chunk * 8 + 4));
+                    const float *q = xsrc + x_ch[it] * 64 + x_row[it] * 8;
+                    r[8 + 2 * it] = __ldg(reinterpret_cast<const float4 *>(q));
+                    r[8 + 2 * it + 1] = __ldg(reinterpret_cast<const float4 *>(q + 4));
                 }
             }
         };
@@ -326,8 +340,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
             // dY: 128 o x 8 rows of 8 cells
 #pragma unroll
             for (int it = 0; it < 4; it++) {
-                const int chunk = tid + it * 256;
-                const int o = chunk >> 3, row = chunk & 7;
+                const int o = a_ch[it], row = a_row[it];
                 uint4 hi, lo;
                 pack_f16x8_split(cur[2 * it], cur[2 * it + 1], scale, hi, lo);
                 const uint32_t off = (((o >> 3) * 8 + row) * 8 + (o & 7)) * 16;
@@ -338,8 +351,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
 #pragma unroll
             for (int it = 0; it < 4; it++) {
                 if (it < xchunks) {
-                    const int chunk = tid + it * 256;
-                    const int c = chunk >> 3, row = chunk & 7;
+                    const int c = x_ch[it], row = x_row[it];
                     const uint4 v = pack_f16x8(cur[8 + 2 * it], cur[8 + 2 * it + 1]);
                     const uint32_t off = kWgXBase + (((c >> 3) * 10 + row + 1) * 8 + (c & 7)) * 16;
                     // kx = 0: out[x] = in[x - 1]; kx = 1: in[x]; kx = 2: out[x] = in[x + 1]   (zero beyond the board edge)

@@ -507,6 +507,23 @@ def section_mcts(eng, args, rank, world, dev, dist, barrier):
             res["cpu_baseline"] = dict(py, unit="playouts/s", value=py.get("playouts_per_s"), cores=1, kind="reference",
                                        sample="unmodified MCTS.playout under the numpy chainer stand-in")
     pool.close()
+    if rank == 0:
+        # one tree (the reference's usage: one game, one search per move): latency of a 16,384-playout move
+        one = SearchPool(1, max_nodes=65536, max_leaf_batch=B, tree_id0=10_000_000, engine=eng)
+        kw = dict(slot_policy=0, slot_value=1, lmbda=0.5, c_puct=1, n_thr=15, leaf_batch=B, virtual_loss=1.0, precision=3,
+                  cache_value=True, seed=args.seed)
+        one.set_roots(p1, p2, 2, reset_tree=True)
+        one.search(2 * B, **kw)
+        one.set_roots(p1, p2, 2, reset_tree=True)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        one.search(N, **kw)
+        b.record()
+        torch.cuda.synchronize()
+        t1 = a.elapsed_time(b) / 1e3
+        res["single_tree"] = {"playouts_per_s": N / t1, "ms_per_move": 1e3 * t1, "best_move": int(one.root_stats()[2][0]),
+                              "note": "one search tree on one GPU (latency-bound: 64 dependent waves of 256 leaves)"}
+        one.close()
     return res
 
 

@@ -5,7 +5,9 @@
 Differences that are deliberate and documented:
   * the rollout weights are loaded once per process, not re-read from disk per instance (mcts_self_play.py:18-19);
   * uniforms come from a counter-based Philox stream (or a replayed stream), not the global numpy RNG —
-    pass `uniforms=` to replay exactly what np.random would have drawn;
+    pass `uniforms=` to replay exactly what np.random would have drawn, or set `USE_NUMPY_RNG = True` to make every
+    Simulate()(color) consume the global np.random stream exactly as the reference does (one uniform per stone placed, none per
+    pass): the unmodified reference MCTS.py then rebuilds its own trees on top of this module (tests/test_dropin_gpu.py);
   * `simulate_batch` runs N games in one launch; the class form is the N = 1 case of the same kernel.
 """
 import itertools
@@ -15,6 +17,8 @@ import numpy as np
 from . import boards
 from .engine import Rng, default_engine
 from .paths import model_path
+
+USE_NUMPY_RNG = False   # True: Simulate draws from the global np.random like mcts_self_play.py:106 (np.random.choice)
 
 _loaded = {}
 _game_counter = itertools.count()
@@ -55,7 +59,15 @@ class Simulate:
         return Rng.philox(seed=type(self).seed, game_id0=self._game_id)
 
     def __call__(self, color):
-        out = simulate_batch(self.state.reshape(1, 8, 8), color, rng=self._rng(), want_moves=True, device=self.device)
+        rng, np_state = self._rng(), None
+        if self._uniforms is None and USE_NUMPY_RNG:
+            np_state = np.random.get_state()
+            rng = Rng.replay_uniforms(np.random.random_sample(64).reshape(1, -1))
+        out = simulate_batch(self.state.reshape(1, 8, 8), color, rng=rng, want_moves=True, device=self.device)
+        if np_state is not None:     # leave the global stream where the reference would: one draw per stone placed
+            np.random.set_state(np_state)
+            if int(out["n_moves"][0]) > 0:
+                np.random.random_sample(int(out["n_moves"][0]))
         self.state = boards.from_bitboards(out["final_p1"], out["final_p2"])[0]
         self.moves = [int(a) for a in out["moves"][0] if a >= 0]
         if self.stone_num < 64:

@@ -228,6 +228,14 @@ constexpr int kWgStage = kWgXBase + 3 * kWgXCopy;   // 94,208
 constexpr int kWgStages = 2;
 constexpr int kWgSmem = kWgStages * kWgStage + 64;
 
+// One 32-byte sector per lane in ONE request (LDG.256, sm_100): with two 16-byte loads every sector was requested twice and the
+// second half had to survive in an L1 that the kernel's 188 KB of shared memory leaves almost no room for.
+__device__ __forceinline__ void ldg256(const float *p, float4 &a, float4 &b) {
+    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+                 : "l"(p));
+}
+
 // 8 floats, scaled by a power of two into fp16's range -> fp16 hi parts and fp16 lo parts (x - hi)
 __device__ __forceinline__ void pack_f16x8_split(const float4 a, const float4 b, float scale, uint4 &hi, uint4 &lo) {
     const float f[8] = {a.x * scale, a.y * scale, a.z * scale, a.w * scale, b.x * scale, b.y * scale, b.z * scale, b.w * scale};
@@ -319,16 +327,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
             const float *xsrc = x + (size_t)p * cin * 64;
 #pragma unroll
             for (int it = 0; it < 4; it++) {
-                const float *q = dsrc + a_ch[it] * 64 + a_row[it] * 8;
-                r[2 * it] = __ldg(reinterpret_cast<const float4 *>(q));
-                r[2 * it + 1] = __ldg(reinterpret_cast<const float4 *>(q + 4));
+                ldg256(dsrc + a_ch[it] * 64 + a_row[it] * 8, r[2 * it], r[2 * it + 1]);
             }
 #pragma unroll
             for (int it = 0; it < 4; it++) {
                 if (it < xchunks) {
-                    const float *q = xsrc + x_ch[it] * 64 + x_row[it] * 8;
-                    r[8 + 2 * it] = __ldg(reinterpret_cast<const float4 *>(q));
-                    r[8 + 2 * it + 1] = __ldg(reinterpret_cast<const float4 *>(q + 4));
+                    ldg256(xsrc + x_ch[it] * 64 + x_row[it] * 8, r[8 + 2 * it], r[8 + 2 * it + 1]);
                 }
             }
         };

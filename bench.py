@@ -35,7 +35,7 @@ GAMES_PER_STEP = 65536
 OPS_PER_PLY = 676          # int32 ALU lane-ops per ply: movegen 314 + flip 352 + ~10 (SURVEY.md §8d, step-by-step 6-step flood)
 OPS_PER_PLY_IMPL = 548     # the same rules with the parallel-prefix flood of bitboard.cuh: movegen 250 + flip 288 + ~10
 BYTES_PER_GAME = 17 + 21   # p1,p2,colour in; final p1,p2,n_moves,result out
-NCU_DRAM_BYTES_PER_LAUNCH = 1145856   # profiles/r01_ncu_rollout_v3_summary.csv (dram__bytes_read.sum; write 0), 65,536-game launch
+NCU_DRAM_BYTES_PER_LAUNCH = 1146112   # profiles/r01_ncu_rollout_v3_summary.csv (dram__bytes_read.sum; write 0), 65,536-game launch
 METRIC = "rollout_plies_per_s"
 
 

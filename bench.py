@@ -10,7 +10,7 @@ rank plays its own 65,536 games per step; no data-path collective — only the t
 Printed JSON (one line, rank 0):
   value      plies/s over all ranks, inputs resident in HBM, per-step CUDA events on the launching stream,
              L2 flushed between steps, max over ranks
-  e2e        the same metric through the host-buffer C-ABI call (iago_rollout_host): pinned H2D + kernel + D2H
+  e2e        the same metric through the host-buffer C-ABI call (iago_rollout_host) on pinned caller buffers: transfers + kernel
   roofline   achieved int32 lane-ops/s (676 per ply) vs the integer-issue peak measured live with
              iago_measure_int_peak; the path is issue-bound, not HBM-bound (roofline_hbm shows why)
   cpu_baseline   the CPU oracle port (oracle/othello_ref.c, pthreads over all cores) on a bounded sample,
@@ -285,21 +285,24 @@ def run_ours(args, rank, world, local_rank):
     turns = int(counters[1].item())
 
     # end-to-end through the host-buffer C-ABI call
-    hp1 = np.full(n, boards.START_P1, np.uint64)
-    hp2 = np.full(n, boards.START_P2, np.uint64)
-    hcol = np.ones(n, np.uint8)
-    hout = dict(result=np.empty(n, np.int8), final_p1=np.empty(n, np.uint64), final_p2=np.empty(n, np.uint64),
-                n_moves=np.empty(n, np.int32), moves=None, counters=np.zeros(2, np.uint64))
-    for i in range(max(args.warmup, 3)):
-        eng.rollout_host(hp1, hp2, hcol, rng=Rng.philox(seed=args.seed + 1, game_id0=(i * world + rank) * n), out=hout)
-    barrier()
-    e2e_plies = 0
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        eng.rollout_host(hp1, hp2, hcol, rng=Rng.philox(seed=args.seed + 1, game_id0=((100 + i) * world + rank) * n), out=hout)
-        e2e_plies += int(hout["counters"][0])
-    t_e2e = time.perf_counter() - t0
-    barrier()
+    # (caller buffers in pinned host memory, as the bench contract asks; the pageable-buffer figure is reported beside it)
+    def e2e_run(pinned):
+        hp1, hp2, hcol, hout = eng.rollout_host_buffers(n, pinned=pinned)
+        hp1[:], hp2[:], hcol[:] = boards.START_P1, boards.START_P2, 1
+        for i in range(max(args.warmup, 3)):
+            eng.rollout_host(hp1, hp2, hcol, rng=Rng.philox(seed=args.seed + 1, game_id0=(i * world + rank) * n), out=hout)
+        barrier()
+        done = 0
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            eng.rollout_host(hp1, hp2, hcol, rng=Rng.philox(seed=args.seed + 1, game_id0=((100 + i) * world + rank) * n), out=hout)
+            done += int(hout["counters"][0])
+        t = time.perf_counter() - t0
+        barrier()
+        return done, t
+
+    pageable_plies, t_pageable = e2e_run(False)
+    e2e_plies, t_e2e = e2e_run(True)
 
     # movegen / flip alone: the same kernel replaying the games' own move logs (no policy, no sampling) — the integer path
     # whose issue utilisation the north star asks for separately
@@ -351,8 +354,13 @@ def run_ours(args, rank, world, local_rank):
             "plies_per_game": plies / (args.steps * world * n), "turns_per_game": turns / (args.steps * world * n),
             "wall_s_timed_region": t_wall,
             "e2e": {"value": e2e_plies / t_e2e, "unit": "plies/s", "h2d_bytes_per_step": 17 * n,
-                    "d2h_bytes_per_step": 21 * n + 16, "api": "iago_rollout_host (pinned staging, H2D, kernel, D2H, sync)",
-                    "ms_per_step": 1e3 * t_e2e / args.steps},
+                    "d2h_bytes_per_step": 21 * n + 16,
+                    "api": "iago_rollout_host on pinned, device-mapped caller buffers: one launch whose loads / stores cross PCIe "
+                           "(17 B in, 21 B out per game) + 16 B counter copy + stream sync, per call",
+                    "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "pageable_buffers": {"value": pageable_plies / t_pageable, "ms_per_step": 1e3 * t_pageable / args.steps,
+                                         "api": "same call on pageable numpy arrays: packed into pinned staging, 4-chunk "
+                                                "H2D / kernel / D2H pipeline", "scope": "rank 0"}},
             "gpu_launches": args.steps * world,
             "clocks": clk.summary(),
             "roofline": {"bound": "alu", "kernel": "rollout_kernel<PHILOX>", "achieved": achieved / 1e12,

@@ -21,6 +21,7 @@
 //   SAFE (any other weights): e = exp32(logit - max_legal); q = floor(e * 2^26) (uint32); pick the first legal k with
 //     cum_q > floor((m53 >> 21) * total / 2^32).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "bitboard.cuh"
@@ -611,11 +612,30 @@ int iago_rollout(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const ui
     return rollout_launch(ctx, a, rng->mode, s);
 }
 
-// Host-buffer entry point.  The batch is cut into up to kHostChunks chunks, each with its own region of the pinned / device
-// staging buffers and its own stream: while chunk c runs, chunk c+1 is being copied in and chunk c-1 copied out, and the host-side
-// packing / unpacking of the pinned buffer overlaps with all of it.  Philox game ids stay global (game_id0 + index), so the
-// results do not depend on the chunking.
+// Host-buffer entry point.  The batch is cut into up to kHostChunks chunks, each with its own region of the device staging
+// buffer and its own stream: while chunk c runs, chunk c+1 is being copied in and chunk c-1 copied out.  Philox game ids stay
+// global (game_id0 + index), so the results do not depend on the chunking.
+//   pageable caller buffers: packed into / unpacked from the context's pinned staging buffer on the host (that memcpy overlaps
+//                            with the copies and kernels of the other chunks);
+//   pinned caller buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory — every buffer of the call): the async copies
+//                            read and write the caller's memory directly, no host-side packing at all; and when the buffers are
+//                            mapped into the device's address space and the uniforms come from Philox, the kernel itself reads
+//                            and writes them (one launch, see below).
 constexpr int kHostChunks = 4;
+
+// True when p is NULL or page-locked host memory known to CUDA; *dev (optional) receives the address the device can use for it
+// (NULL when the allocation is not mapped into the device's address space).
+static bool is_pinned(const void *p, void **dev = nullptr) {
+    if (dev) *dev = nullptr;
+    if (!p) return true;
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    if (dev) *dev = at.devicePointer;
+    return at.type == cudaMemoryTypeHost;
+}
 
 int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
                       const iago_rng *rng, int8_t *result, uint64_t *final_p1, uint64_t *final_p2,
@@ -628,11 +648,18 @@ int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, con
     if (n == 0) return IAGO_OK;
     DeviceGuard guard(ctx->device);
     auto up8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
-    const int chunks = n >= 4 * 4096 ? kHostChunks : 1;
-    const size_t per = (((size_t)n + chunks - 1) / chunks + 63) & ~(size_t)63;   // games per chunk, a whole number of CTAs
-    // per-chunk region: input block p1 | p2 | color | replay stream ; output block fp1 | fp2 | n_moves | counters | result | log
     const size_t u_stride = rng->mode == IAGO_RNG_UNIFORMS ? (size_t)rng->u_stride : 0;
     const size_t f_stride = rng->mode == IAGO_RNG_FORCED ? (size_t)rng->f_stride : 0;
+    void *m_p1, *m_p2, *m_col, *m_res, *m_f1, *m_f2, *m_nm, *m_log;
+    const bool direct = is_pinned(p1, &m_p1) & is_pinned(p2, &m_p2) & is_pinned(color, &m_col) & is_pinned(result, &m_res) &
+                        is_pinned(final_p1, &m_f1) & is_pinned(final_p2, &m_f2) & is_pinned(n_moves, &m_nm) &
+                        is_pinned(move_log, &m_log) && (!u_stride || is_pinned(rng->uniforms)) && (!f_stride || is_pinned(rng->forced));
+    const bool mapped = direct && rng->mode == IAGO_RNG_PHILOX && m_p1 && m_p2 && m_col && m_res && m_f1 && m_f2 &&
+                        (m_nm || !n_moves) && (m_log || !move_log);
+    // measured at 65,536 games (tools/e2e_probe.py): staged 4 / 2 / 1 chunks 0.43 / 0.46 / 0.52 ms, direct 0.37 / 0.37 / 0.38, mapped 0.33
+    const int chunks = mapped ? 1 : n >= 4 * 4096 ? (direct ? 2 : kHostChunks) : 1;
+    const size_t per = (((size_t)n + chunks - 1) / chunks + 63) & ~(size_t)63;   // games per chunk, a whole number of CTAs
+    // per-chunk region: input block p1 | p2 | color | replay stream ; output block fp1 | fp2 | n_moves | counters | result | log
     const size_t o_p1 = 0, o_p2 = o_p1 + 8 * per, o_col = o_p2 + 8 * per, o_rep = o_col + up8(per);
     const size_t in_bytes = o_rep + 8 * per * u_stride + up8(per * f_stride);
     const size_t o_f1 = in_bytes, o_f2 = o_f1 + 8 * per, o_nm = o_f2 + 8 * per, o_cnt = o_nm + up8(4 * per);
@@ -644,18 +671,46 @@ int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, con
         ctx->host_streams[0] = ctx->stream;
         for (int c = 1; c < kHostChunks; c++) IAGO_CUDA(cudaStreamCreateWithFlags(&ctx->host_streams[c], cudaStreamNonBlocking));
     }
+    const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+    if (mapped) {
+        // Pinned, device-mapped caller buffers and no replay stream: ONE launch over the whole batch whose loads and stores cross
+        // PCIe themselves (17 B in / 21 B out per game, coalesced, once per game) — no staging, no copy engines, full occupancy.
+        cudaStream_t s = ctx->stream;
+        char *h = (char *)ctx->stage.host, *d = (char *)ctx->stage.dev;
+        IAGO_CUDA(cudaMemsetAsync(d + o_cnt, 0, 16, s));
+        RolloutArgs a{(const u64 *)m_p1, (const u64 *)m_p2, (const uint8_t *)m_col, (long long)n, rng->stream_id, rng->seed,
+                      rng->game_id0, nullptr, 0, nullptr, 0, (int8_t *)m_res, (u64 *)m_f1, (u64 *)m_f2, (int32_t *)m_nm,
+                      (int8_t *)m_log, (u64 *)(d + o_cnt), nullptr};
+        IAGO_CUDA(cudaEventRecord(ctx->ev0, s));
+        launch_rollout_mode(a, rng->mode, ctx->rollout_fast, ctx->d_rollout, s);
+        IAGO_CUDA(cudaGetLastError());
+        IAGO_CUDA(cudaEventRecord(ctx->ev1, s));
+        IAGO_CUDA(cudaMemcpyAsync(h + o_cnt, d + o_cnt, 16, D2H, s));
+        ctx->timed = true;
+        IAGO_CUDA(cudaStreamSynchronize(s));
+        if (counters_host) memcpy(counters_host, h + o_cnt, 16);
+        return IAGO_OK;
+    }
     for (int c = 0; c < chunks; c++) {
         const size_t g0 = (size_t)c * per;
         if (g0 >= (size_t)n) break;
         const size_t N = ((size_t)n - g0 < per) ? (size_t)n - g0 : per;
         char *h = (char *)ctx->stage.host + region * c, *d = (char *)ctx->stage.dev + region * c;
         cudaStream_t s = ctx->host_streams[c];
-        memcpy(h + o_p1, p1 + g0, 8 * N);
-        memcpy(h + o_p2, p2 + g0, 8 * N);
-        memcpy(h + o_col, color + g0, N);
-        if (u_stride) memcpy(h + o_rep, rng->uniforms + g0 * u_stride, 8 * N * u_stride);
-        if (f_stride) memcpy(h + o_rep, rng->forced + g0 * f_stride, N * f_stride);
-        IAGO_CUDA(cudaMemcpyAsync(d, h, in_bytes, cudaMemcpyHostToDevice, s));
+        if (direct) {
+            IAGO_CUDA(cudaMemcpyAsync(d + o_p1, p1 + g0, 8 * N, H2D, s));
+            IAGO_CUDA(cudaMemcpyAsync(d + o_p2, p2 + g0, 8 * N, H2D, s));
+            IAGO_CUDA(cudaMemcpyAsync(d + o_col, color + g0, N, H2D, s));
+            if (u_stride) IAGO_CUDA(cudaMemcpyAsync(d + o_rep, rng->uniforms + g0 * u_stride, 8 * N * u_stride, H2D, s));
+            if (f_stride) IAGO_CUDA(cudaMemcpyAsync(d + o_rep, rng->forced + g0 * f_stride, N * f_stride, H2D, s));
+        } else {
+            memcpy(h + o_p1, p1 + g0, 8 * N);
+            memcpy(h + o_p2, p2 + g0, 8 * N);
+            memcpy(h + o_col, color + g0, N);
+            if (u_stride) memcpy(h + o_rep, rng->uniforms + g0 * u_stride, 8 * N * u_stride);
+            if (f_stride) memcpy(h + o_rep, rng->forced + g0 * f_stride, N * f_stride);
+            IAGO_CUDA(cudaMemcpyAsync(d, h, in_bytes, H2D, s));
+        }
         IAGO_CUDA(cudaMemsetAsync(d + o_cnt, 0, 16, s));
         RolloutArgs a{(const u64 *)(d + o_p1), (const u64 *)(d + o_p2), (const uint8_t *)(d + o_col), (long long)N,
                       rng->stream_id, rng->seed, rng->game_id0 + g0, (const double *)(d + o_rep), rng->u_stride,
@@ -666,7 +721,16 @@ int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, con
         launch_rollout_mode(a, rng->mode, ctx->rollout_fast, ctx->d_rollout, s);
         IAGO_CUDA(cudaGetLastError());
         if (c == 0) IAGO_CUDA(cudaEventRecord(ctx->ev1, s));   // iago_last_kernel_ms: the first chunk's launch (the whole batch when n < 16,384)
-        IAGO_CUDA(cudaMemcpyAsync(h + o_f1, d + o_f1, (move_log ? o_log + 64 * N : o_res + N) - o_f1, cudaMemcpyDeviceToHost, s));
+        if (direct) {
+            IAGO_CUDA(cudaMemcpyAsync(final_p1 + g0, d + o_f1, 8 * N, D2H, s));
+            IAGO_CUDA(cudaMemcpyAsync(final_p2 + g0, d + o_f2, 8 * N, D2H, s));
+            IAGO_CUDA(cudaMemcpyAsync(result + g0, d + o_res, N, D2H, s));
+            if (n_moves) IAGO_CUDA(cudaMemcpyAsync(n_moves + g0, d + o_nm, 4 * N, D2H, s));
+            if (move_log) IAGO_CUDA(cudaMemcpyAsync(move_log + 64 * g0, d + o_log, 64 * N, D2H, s));
+            IAGO_CUDA(cudaMemcpyAsync(h + o_cnt, d + o_cnt, 16, D2H, s));
+        } else {
+            IAGO_CUDA(cudaMemcpyAsync(h + o_f1, d + o_f1, (move_log ? o_log + 64 * N : o_res + N) - o_f1, D2H, s));
+        }
     }
     ctx->timed = true;
     for (int c = 0; c < chunks; c++) {
@@ -675,11 +739,13 @@ int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, con
         const size_t N = ((size_t)n - g0 < per) ? (size_t)n - g0 : per;
         const char *h = (const char *)ctx->stage.host + region * c;
         IAGO_CUDA(cudaStreamSynchronize(ctx->host_streams[c]));
-        memcpy(final_p1 + g0, h + o_f1, 8 * N);
-        memcpy(final_p2 + g0, h + o_f2, 8 * N);
-        memcpy(result + g0, h + o_res, N);
-        if (n_moves) memcpy(n_moves + g0, h + o_nm, 4 * N);
-        if (move_log) memcpy(move_log + 64 * g0, h + o_log, 64 * N);
+        if (!direct) {
+            memcpy(final_p1 + g0, h + o_f1, 8 * N);
+            memcpy(final_p2 + g0, h + o_f2, 8 * N);
+            memcpy(result + g0, h + o_res, N);
+            if (n_moves) memcpy(n_moves + g0, h + o_nm, 4 * N);
+            if (move_log) memcpy(move_log + 64 * g0, h + o_log, 64 * N);
+        }
         if (counters_host) {
             uint64_t cnt[2];
             memcpy(cnt, h + o_cnt, 16);

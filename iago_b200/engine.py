@@ -326,8 +326,26 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------ host API (numpy arrays)
+    @staticmethod
+    def pinned(shape, dtype):
+        """numpy array on page-locked, device-mapped host memory (a torch pin_memory tensor keeps it alive).  When every buffer
+        of a rollout_host call is such an array the library skips its staging copy (include/iago_b200.h, iago_rollout_host)."""
+        torch = _torch()
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+        t = torch.empty(max(nbytes, 1), dtype=torch.uint8, pin_memory=True)
+        return t.numpy()[:nbytes].view(dtype).reshape(shape)
+
+    def rollout_host_buffers(self, n, want_moves=False, pinned=True):
+        """(p1, p2, color, out) for rollout_host, page-locked by default."""
+        mk = self.pinned if pinned else (lambda shape, dtype: np.empty(shape, dtype))
+        out = dict(result=mk(n, np.int8), final_p1=mk(n, np.uint64), final_p2=mk(n, np.uint64), n_moves=mk(n, np.int32),
+                   moves=mk((n, 64), np.int8) if want_moves else None, counters=np.zeros(2, np.uint64))
+        return mk(n, np.uint64), mk(n, np.uint64), mk(n, np.uint8), out
+
     def rollout_host(self, p1, p2, color, rng: Optional[Rng] = None, want_moves=False, out=None):
-        """Same as rollout() with HOST buffers: H2D + kernel + D2H inside the C call (synchronous)."""
+        """Same as rollout() with HOST buffers: H2D + kernel + D2H inside the C call (synchronous).  Pageable arrays go through
+        the context's pinned staging buffer; arrays from pinned() / rollout_host_buffers() are used in place."""
         rng = rng or Rng()
         p1 = np.ascontiguousarray(p1, np.uint64).reshape(-1)
         n = p1.shape[0]

@@ -104,8 +104,11 @@ IAGO_API int iago_rollout(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2,
                  const iago_rng *rng, int8_t *result, uint64_t *final_p1, uint64_t *final_p2,
                  int32_t *n_moves, int8_t *move_log, uint64_t *counters, void *stream);
 
-/* Same, HOST buffers in and out (pinned staging inside the context); synchronous.  This is the call the
- * Python facade `Simulate` / `simulate_batch` makes and the one bench.py's e2e figure times. */
+/* Same, HOST buffers in and out; synchronous.  This is the call the Python facade `Simulate` / `simulate_batch` makes and the
+ * one bench.py's e2e figure times.  Pageable buffers are packed into pinned staging inside the context and pipelined in four
+ * chunks (H2D / kernel / D2H overlap).  When EVERY buffer of the call is page-locked (cudaHostAlloc, cudaHostRegister, torch
+ * pin_memory) the library uses them in place: with Philox uniforms one launch reads and writes the device-mapped buffers
+ * itself (17 B in, 21 B out per game across PCIe), with a replay stream the async copies go straight from / to them. */
 IAGO_API int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
                       const iago_rng *rng, int8_t *result, uint64_t *final_p1, uint64_t *final_p2,
                       int32_t *n_moves, int8_t *move_log, uint64_t *counters_host);

@@ -215,3 +215,36 @@ def test_fallback_sampler_and_host_chunking(engine, cref, rollout_weights):
         ref = cref.simulate_batch(st, 1, W, b, mode=cref.RNG_PHILOX, seed=9, game_id0=12345, threads=0)
         assert (out["moves"] == ref["moves"]).all() and (out["result"] == ref["results"]).all(), n
         assert int(out["counters"][0]) == int(ref["n_moves"].sum()) and int(out["counters"][1]) == int(ref["n_turns"].sum()), n
+
+
+def test_host_call_on_pinned_buffers(engine, cref, rollout_weights):
+    """iago_rollout_host uses page-locked caller buffers in place: Philox games run as one launch that reads / writes the mapped
+    buffers itself, replay streams go through direct async copies (two chunks from 16,384 games).  Both give the oracle's games,
+    the same as the pageable (staged) path, with and without the optional outputs."""
+    from iago_b200 import Rng, boards
+    W, b = rollout_weights
+    for n in (1, 63, 16385, 40000):
+        p1, p2, col, out = engine.rollout_host_buffers(n, want_moves=True)
+        p1[:], p2[:], col[:] = boards.START_P1, boards.START_P2, 1
+        out["moves"][:] = 77
+        engine.rollout_host(p1, p2, col, rng=Rng.philox(seed=11, game_id0=5), out=out)
+        st = np.tile(boards.start_state().reshape(1, 64), (n, 1))
+        ref = cref.simulate_batch(st, 1, W, b, mode=cref.RNG_PHILOX, seed=11, game_id0=5, threads=0)
+        r1, r2 = cref.to_bitboards(ref["final"])
+        assert (out["moves"] == ref["moves"]).all() and (out["result"] == ref["results"]).all(), n
+        assert (out["final_p1"] == r1).all() and (out["final_p2"] == r2).all() and (out["n_moves"] == ref["n_moves"]).all(), n
+        assert int(out["counters"][0]) == int(ref["n_moves"].sum()) and int(out["counters"][1]) == int(ref["n_turns"].sum()), n
+        # no optional outputs
+        slim = dict(out, n_moves=None, moves=None, result=engine.pinned(n, np.int8), counters=np.zeros(2, np.uint64))
+        engine.rollout_host(p1, p2, col, rng=Rng.philox(seed=11, game_id0=5), out=slim)
+        assert (slim["result"] == ref["results"]).all() and int(slim["counters"][0]) == int(ref["n_moves"].sum())
+        # replayed moves from a pinned log: the direct-copy path
+        forced = engine.pinned((n, 64), np.int8)
+        forced[:] = ref["moves"]
+        out2 = engine.rollout_host_buffers(n, want_moves=True)[3]
+        engine.rollout_host(p1, p2, col, rng=Rng.replay_moves(forced), out=out2)
+        assert (out2["moves"] == ref["moves"]).all() and (out2["final_p1"] == r1).all() and (out2["result"] == ref["results"]).all(), n
+        # a pageable buffer among pinned ones falls back to staging
+        out3 = dict(out2, result=np.empty(n, np.int8))
+        engine.rollout_host(p1, p2, col, rng=Rng.philox(seed=11, game_id0=5), out=out3)
+        assert (out3["result"] == ref["results"]).all() and (out3["moves"] == ref["moves"]).all(), n

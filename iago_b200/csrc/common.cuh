@@ -19,6 +19,10 @@ struct RolloutWeights {
     uint32_t colmask[8]; // 3x3 window mask for column j: 0x070707 without the wrapped column at j = 0 / j = 7
     double elut[2][512]; // elut[c][index] = canon_exp(lut[c][index])                  (fast sampler: e = elut0 * elut1 * ebias)
     double ebias[64];    // ebias[k]       = canon_exp(bias[k])
+    // the same tables for the board turned by 180 degrees (cell k -> 63 - k, tap t -> 8 - t, i.e. the 9-bit index reversed): the
+    // lane of a rollout pair that owns board rows 4-7 plays the turned game (rollout.cu, rollout_pair_kernel)
+    double elut_r[2][512];
+    double ebias_r[64];
 };
 
 struct Staging {

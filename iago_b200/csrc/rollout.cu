@@ -167,49 +167,38 @@ __device__ __forceinline__ double weight_at(const PolicySmemD &w, const Plane3 &
     return __dmul_rn(__dmul_rn(e0, e1), w.tb[k]);
 }
 
-__device__ __forceinline__ int sample_move_fast(const PolicySmemD &w, u64 own, u64 opp, u64 legal, u64 m53, double *sa, uint8_t *sc) {
+// One thread, whole board (rollout_sample_kernel, and the rollout kernel of last resort): the two-sided cdf of the canonical rule —
+// A = running sum over the legal cells 0..31 ascending, D = over the legal cells 63..32 descending (see the header of this file).
+__device__ __noinline__ int sample_move_fast(const PolicySmemD &w, u64 own, u64 opp, u64 legal, u64 m53, double *sa, uint8_t *sc) {
     const int n = __popcll(legal);
     if (n == 1) return __ffsll((long long)legal) - 1;
     const Plane3 pm = plane3(own), po = plane3(opp);
     const double u = __dmul_rn((double)(long long)m53, 1.1102230246251565e-16);  // m53 / 2^53, exact
-    if (n <= kMaxLegal) {
+    const uint32_t llo = (uint32_t)legal, lhi = (uint32_t)(legal >> 32);
+    const int nl = __popc(llo), nh = __popc(lhi);
+    double lo = 0.0, hi = 0.0;
+    for (uint32_t m = llo; m; m &= m - 1) lo = __dadd_rn(lo, weight_at(w, pm, po, __ffs((int)m) - 1));
+    for (uint32_t m = lhi; m; m &= ~(0x80000000u >> __clz((int)m))) hi = __dadd_rn(hi, weight_at(w, pm, po, 63 - __clz((int)m)));
+    const double total = __dadd_rn(lo, hi), T = __dmul_rn(u, total);
+    (void)sa; (void)sc;
+    if (T < lo || nh == 0) {
         double cum = 0.0;
-        uint32_t lo = (uint32_t)legal, hi = (uint32_t)(legal >> 32);
-        for (int i = 0; i < n; i++) {
-            // lowest set bit of (hi:lo) with 32-bit operations; `up` also selects the words of the pre-shifted planes
-            const bool up = lo == 0;
-            const uint32_t wd = up ? hi : lo;
-            const int sh = __ffs((int)wd) - 1, k = sh + (up ? 32 : 0);
-            const uint32_t rest = wd & (wd - 1);
-            lo = up ? 0u : rest;
-            hi = up ? rest : hi;
-            const uint32_t cm = w.colmask[sh & 7];
-            const uint32_t t0 = __funnelshift_r(up ? po.w1 : po.w0, up ? po.w2 : po.w1, (uint32_t)sh) & cm;
-            const uint32_t t1 = __funnelshift_r(up ? pm.w1 : pm.w0, up ? pm.w2 : pm.w1, (uint32_t)sh) & cm;
-            const double e0 = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(w.t0) + (((t0 * 0x400801u) >> 13) & 0xFF8u));
-            const double e1 = *reinterpret_cast<const double *>(reinterpret_cast<const char *>(w.t1) + (((t1 * 0x400801u) >> 13) & 0xFF8u));
-            cum = __dadd_rn(cum, __dmul_rn(__dmul_rn(e0, e1), w.tb[k]));
-            sa[i * kBlock] = cum;
-            sc[i * kBlock] = (uint8_t)k;
+        int last = 0;
+        for (uint32_t m = llo; m; m &= m - 1) {
+            last = __ffs((int)m) - 1;
+            cum = __dadd_rn(cum, weight_at(w, pm, po, last));
+            if (cum > T) return last;
         }
-        const double T = __dmul_rn(u, cum);
-        int idx = 0, end = n;                  // number of cum_i <= T: the running sums are non-decreasing, so bisect
-        while (idx < end) {
-            const int mid = (idx + end) >> 1;
-            if (sa[mid * kBlock] <= T) idx = mid + 1; else end = mid;
-        }
-        idx = min(idx, n - 1);
-        return (int)sc[idx * kBlock];
+        return last;
     }
-    double total = 0.0;
-    for (u64 m = legal; m; m &= m - 1) total = __dadd_rn(total, weight_at(w, pm, po, __ffsll((long long)m) - 1));
-    const double T = __dmul_rn(u, total);
+    (void)nl;
+    const double R = __dsub_rn(total, T);
     double cum = 0.0;
-    int last = 0;
-    for (u64 m = legal; m; m &= m - 1) {
-        last = __ffsll((long long)m) - 1;
+    int last = 63;
+    for (uint32_t m = lhi; m; m &= ~(0x80000000u >> __clz((int)m))) {
+        last = 63 - __clz((int)m);
         cum = __dadd_rn(cum, weight_at(w, pm, po, last));
-        if (cum > T) return last;
+        if (!(cum < R)) return last;
     }
     return last;
 }
@@ -321,6 +310,238 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const Ro
     }
     if (a.counters) {
         unsigned p = (unsigned)placed, t = (unsigned)turns;
+        p = __reduce_add_sync(0xFFFFFFFFu, p);
+        t = __reduce_add_sync(0xFFFFFFFFu, t);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd(a.counters + 0, (u64)p);
+            atomicAdd(a.counters + 1, (u64)t);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- the paired rollout kernel (FAST weights)
+//
+// TWO lanes own one game.  Lane h = 0 holds the board as it is, lane h = 1 holds it turned by 180 degrees (bit k -> 63 - k, one
+// BREV per word).  Othello's rules do not change under that turn, and it maps the four "right shift" flood directions onto the
+// four "left shift" ones — so both lanes run the SAME instructions: each floods only the directions +1, +7, +8, +9 of its own
+// frame (half of movegen, half of the flips) and handles the legal cells 0..31 of its own frame (board rows 0-3 in lane 0, rows
+// 7-4 in lane 1) with policy tables built for its frame (elut / elut_r).  Per turn the pair exchanges through shuffles: the half
+// move sets, the half flip sets (each 2 x 32 bits + BREV), the two half sums of the softmax numerators and the candidate cell.
+// Against one thread per game this doubles the warps per SM (65,536 games = 27.7 warps per SM instead of 13.8), removes the
+// word selects from the per-cell loop and shortens the divergent loop from max(n) over 32 games to max(n_half) over 32 halves.
+// One CTA per SM: the 17 KB of tables are held once per SM instead of once per small CTA, which leaves room for 16 scratch slots
+// per lane and the flip line masks.  65,536 games = 4,096 warps = 147 CTAs of 28 warps; small batches use smaller CTAs (host side).
+constexpr int kPairMaxWarps = 28;
+constexpr int kPairSlots = 16;    // running sums kept per lane; a half board with more legal cells (never seen in play) recomputes
+
+struct PairTables {
+    double tab[2][1088];          // [frame][E0 512 | E1 512 | EB 64]
+    u64 line[4][64];              // line[d][k]: the cells beyond k along direction +1, +7, +8, +9 up to the board edge
+    uint32_t colmask[8];
+    uint32_t pad[8];
+};
+struct PairScratch {              // per warp
+    double cum[kPairSlots][32];
+    uint8_t cell[kPairSlots][32];
+};
+static size_t pair_smem_bytes(int warps) { return sizeof(PairTables) + (size_t)warps * sizeof(PairScratch); }
+
+__device__ __forceinline__ u64 rev64(u64 x) { return ((u64)__brev((uint32_t)x) << 32) | (u64)__brev((uint32_t)(x >> 32)); }
+__device__ __forceinline__ u64 pair_xchg(unsigned mask, u64 x) {   // the partner lane's x, turned into this lane's frame
+    const uint32_t lo = __shfl_xor_sync(mask, (uint32_t)x, 1), hi = __shfl_xor_sync(mask, (uint32_t)(x >> 32), 1);
+    return ((u64)__brev(lo) << 32) | (u64)__brev(hi);
+}
+// Moves reached by walking towards higher bits.  Along +1 the walk is an addition: a carry injected at the first opponent stone
+// east of an own stone runs through the run and leaves a 1 on the cell behind it (edge columns are not in `mo`, so a carry never
+// leaves its row); the other three directions flood.  Cells that are not empty are removed by the caller.
+__device__ __forceinline__ u64 half_moves(u64 own, u64 opp) {
+    const u64 mo = opp & kInnerCols;
+    const u64 east = (mo + ((own << 1) & mo)) & ~mo;
+    return east | moves_up<8>(own, opp) | moves_up<7>(own, mo) | moves_up<9>(own, mo);
+}
+// Stones bracketed by the move `mv` = bit k along the four directions towards higher bits, by carry propagation: with every bit
+// outside the line L = line[d][k] set, adding mv ripples from k through the opponent run on the line and stops on the first line
+// cell that holds no opponent stone; if that cell is own, everything on the line below it is flipped.
+__device__ __forceinline__ u64 half_flips(const u64 (*line)[64], int k, u64 mv, u64 own, u64 opp) {
+    u64 f = 0;
+#pragma unroll
+    for (int d = 0; d < 4; d++) {
+        const u64 L = line[d][k];
+        const u64 out = ((opp | ~L) + mv) & L & own;
+        f |= (out - (u64)(out != 0)) & L;
+    }
+    return f;
+}
+
+struct PairPlanes {
+    uint32_t o0, o1, m0, m1;   // opponent / mover planes << 9, words 0 and 1: all a window starting at a cell below 32 can reach
+};
+__device__ __forceinline__ double pair_weight(const char *tab, const uint32_t *colmask, const PairPlanes &p, int sh) {
+    const uint32_t cm = colmask[sh & 7];
+    const uint32_t t0 = __funnelshift_r(p.o0, p.o1, (uint32_t)sh) & cm;
+    const uint32_t t1 = __funnelshift_r(p.m0, p.m1, (uint32_t)sh) & cm;
+    const double e0 = *reinterpret_cast<const double *>(tab + (((t0 * 0x400801u) >> 13) & 0xFF8u));
+    const double e1 = *reinterpret_cast<const double *>(tab + 4096 + (((t1 * 0x400801u) >> 13) & 0xFF8u));
+    const double eb = *reinterpret_cast<const double *>(tab + 8192 + sh * 8);
+    return __dmul_rn(__dmul_rn(e0, e1), eb);
+}
+// More legal cells in this half than scratch slots: nothing was stored, walk again.  First cell (own-frame ascending) whose
+// running sum fails `pred`, the last cell when none does.
+__device__ __noinline__ int pair_pick_slow(const char *tab, const uint32_t *colmask, PairPlanes p, uint32_t wd, int limit, double thr, int h) {
+    double cum = 0.0;
+    int last = 0, j = 0;
+    for (; wd; wd &= wd - 1, j++) {
+        last = __ffs((int)wd) - 1;
+        cum = __dadd_rn(cum, pair_weight(tab, colmask, p, last));
+        const bool pred = h ? (cum < thr) : (cum <= thr);
+        if (!(j < limit && pred)) break;
+    }
+    return last;
+}
+
+template <int MODE, bool LOG>
+__global__ void __launch_bounds__(kPairMaxWarps * 32, 1) rollout_pair_kernel(RolloutArgs a, const RolloutWeights *__restrict__ gw) {
+    extern __shared__ __align__(16) unsigned char pair_smem[];
+    PairTables &sm = *reinterpret_cast<PairTables *>(pair_smem);
+    PairScratch &scr = reinterpret_cast<PairScratch *>(pair_smem + sizeof(PairTables))[threadIdx.x >> 5];
+    if (MODE != IAGO_RNG_FORCED) {
+        const double *e = &gw->elut[0][0], *er = &gw->elut_r[0][0];   // elut[2][512] | ebias[64] and elut_r | ebias_r: contiguous
+        for (int i = threadIdx.x; i < 1088; i += blockDim.x) {
+            sm.tab[0][i] = e[i];
+            sm.tab[1][i] = er[i];
+        }
+        if (threadIdx.x < 8) sm.colmask[threadIdx.x] = gw->colmask[threadIdx.x];
+    }
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
+        const int d = i >> 6, k = i & 63, r = k >> 3, c = k & 7;
+        const int steps = d == 0 ? 7 - c : d == 1 ? min(7 - r, c) : d == 2 ? 7 - r : min(7 - r, 7 - c);
+        const int S = d == 0 ? 1 : d + 6;
+        u64 L = 0;
+        for (int t = 1; t <= steps; t++) L |= 1ULL << (k + t * S);
+        sm.line[d][k] = L;
+    }
+    __syncthreads();
+
+    const int h = threadIdx.x & 1;
+    const unsigned pmask = 3u << (threadIdx.x & 30);
+    const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
+    int placed = 0, turns = 0;
+    if (g < a.n) {   // the same for both lanes of a pair, as is every branch below
+        const int color = a.color[g];
+        const u64 gid = a.game_ids ? a.game_ids[g] : a.game_id0 + (u64)g;
+        u64 own = (color == 1) ? a.p1[g] : a.p2[g];
+        u64 opp = (color == 1) ? a.p2[g] : a.p1[g];
+        if (h) { own = rev64(own); opp = rev64(opp); }
+        int stone_num = __popcll(own | opp);  // 64 - sum(state == 0), mcts_self_play.py:15
+        bool pass_flg = false;
+        const char *tab = reinterpret_cast<const char *>(sm.tab[h]);
+        double *sa = &scr.cum[0][threadIdx.x & 31];
+        uint8_t *sc = &scr.cell[0][threadIdx.x & 31];
+        uint32_t rnd[4] = {0, 0, 0, 0};  // the Philox block serving draws 4*(placed >> 2) .. + 3
+        while (stone_num < 64) {  // mcts_self_play.py:26 — the end test runs once per PAIR of turns
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+                const u64 hm = half_moves(own, opp);
+                const u64 legal = (hm | pair_xchg(pmask, hm)) & ~(own | opp);
+                turns++;
+                if (legal) {
+                    int k;   // the move, in this lane's frame
+                    if (MODE == IAGO_RNG_FORCED) {
+                        k = (placed < a.f_stride) ? a.forced[g * a.f_stride + placed] : -1;
+                        if (k >= 0 && k <= 63 && h) k = 63 - k;
+                    } else {
+                        u64 m53;
+                        if (MODE == IAGO_RNG_UNIFORMS)
+                            m53 = __double2ull_rz(a.uniforms[g * a.u_stride + placed] * 9007199254740992.0);
+                        else {
+                            if ((placed & 3) == 0) philox_block(a.seed, gid, (uint32_t)placed >> 2, a.stream_id, rnd);
+                            const uint32_t wd = (placed & 2) ? ((placed & 1) ? rnd[3] : rnd[2]) : ((placed & 1) ? rnd[1] : rnd[0]);
+                            m53 = (u64)wd << 21;
+                        }
+                        const double u = __dmul_rn((double)(long long)m53, 1.1102230246251565e-16);  // m53 / 2^53, exact
+                        // this lane's half of the softmax numerators: legal cells 0..31 of its frame, ascending
+                        const uint32_t lw = (uint32_t)legal;
+                        const int n = __popc(lw);
+                        PairPlanes pl;
+                        pl.o0 = (uint32_t)opp << 9;
+                        pl.o1 = __funnelshift_l((uint32_t)opp, (uint32_t)(opp >> 32), 9);
+                        pl.m0 = (uint32_t)own << 9;
+                        pl.m1 = __funnelshift_l((uint32_t)own, (uint32_t)(own >> 32), 9);
+                        const bool stored = n <= kPairSlots;
+                        double cum = 0.0;
+                        if (stored) {
+                            uint32_t wd = lw;
+                            for (int i = 0; i < n; i++) {
+                                const int sh = __ffs((int)wd) - 1;
+                                wd &= wd - 1;
+                                cum = __dadd_rn(cum, pair_weight(tab, sm.colmask, pl, sh));
+                                sa[i * 32] = cum;
+                                sc[i * 32] = (uint8_t)sh;
+                            }
+                        } else {
+                            for (uint32_t wd = lw; wd; wd &= wd - 1) cum = __dadd_rn(cum, pair_weight(tab, sm.colmask, pl, __ffs((int)wd) - 1));
+                        }
+                        // A_last (lane 0) and D_last (lane 1) -> total, T, and which half holds the answer
+                        const double oth = __hiloint2double(__shfl_xor_sync(pmask, __double2hiint(cum), 1),
+                                                            __shfl_xor_sync(pmask, __double2loint(cum), 1));
+                        const double lo_t = h ? oth : cum, hi_t = h ? cum : oth;
+                        const double total = __dadd_rn(lo_t, hi_t), T = __dmul_rn(u, total);
+                        const bool in_hi = !(T < lo_t) && hi_t > 0.0;
+                        // lane 0: number of A_i <= T (at most n - 1); lane 1: number of D_j < total - T among j <= n - 2
+                        const double thr = h ? __dsub_rn(total, T) : T;
+                        int c;
+                        if (stored) {
+                            int idx = 0, end = n - h;
+                            while (idx < end) {
+                                const int mid = (idx + end) >> 1;
+                                const double v = sa[mid * 32];
+                                if (h ? (v < thr) : (v <= thr)) idx = mid + 1; else end = mid;
+                            }
+                            idx = max(min(idx, n - 1), 0);
+                            c = (int)sc[idx * 32];
+                        } else {
+                            c = pair_pick_slow(tab, sm.colmask, pl, lw, n - h, thr, h);
+                        }
+                        const int ct = h ? 63 - c : c;   // this lane's candidate as a cell of the real board
+                        const int octv = __shfl_xor_sync(pmask, ct, 1);
+                        const int kt = (in_hi == (h != 0)) ? ct : octv;
+                        k = h ? 63 - kt : kt;
+                    }
+                    if (MODE == IAGO_RNG_FORCED && (k < 0 || k > 63)) {
+                        stone_num = 64;  // replay stream exhausted: stop this game where it stands
+                    } else {
+                        const u64 mv = 1ULL << k;
+                        own |= mv;
+                        opp &= ~mv;
+                        const u64 hf = half_flips(sm.line, k, mv, own, opp);
+                        const u64 f = hf | pair_xchg(pmask, hf);
+                        own |= f;
+                        opp &= ~f;
+                        if (LOG && !h) a.move_log[g * 64 + placed] = (int8_t)k;
+                        placed++;
+                        pass_flg = false;
+                        stone_num++;
+                    }
+                } else {
+                    if (pass_flg) stone_num = 64;  // two consecutive passes end the game
+                    pass_flg = true;
+                }
+                const u64 t = own; own = opp; opp = t;
+            }
+        }
+        if (!h) {
+            // an even number of swaps happened: own = stones of `color` again
+            const int me = __popcll(own), op = __popcll(opp);
+            a.result[g] = (int8_t)((me > op) - (me < op));
+            a.final_p1[g] = (color == 1) ? own : opp;
+            a.final_p2[g] = (color == 1) ? opp : own;
+            if (a.n_moves) a.n_moves[g] = placed;
+            if (LOG)
+                for (int i = placed; i < 64; i++) a.move_log[g * 64 + i] = -1;
+        }
+    }
+    if (a.counters) {
+        unsigned p = h ? 0u : (unsigned)placed, t = h ? 0u : (unsigned)turns;
         p = __reduce_add_sync(0xFFFFFFFFu, p);
         t = __reduce_add_sync(0xFFFFFFFFu, t);
         if ((threadIdx.x & 31) == 0) {
@@ -448,6 +669,13 @@ static bool build_rollout_weights(const float *W, const float *b, RolloutWeights
         if (fabsf(b[k]) > bmax) bmax = fabsf(b[k]);
         if (!(fabsf(b[k]) <= 300.0f)) finite = 0;
     }
+    for (int c = 0; c < 2; c++)
+        for (int idx = 0; idx < 512; idx++) {
+            int r = 0;
+            for (int bit = 0; bit < 9; bit++) r |= ((idx >> bit) & 1) << (8 - bit);
+            out->elut_r[c][idx] = out->elut[c][r];
+        }
+    for (int k = 0; k < 64; k++) out->ebias_r[k] = out->ebias[63 - k];
     for (int j = 0; j < 8; j++) out->colmask[j] = 0x070707u & ~(j == 0 ? 0x010101u : 0u) & ~(j == 7 ? 0x040404u : 0u);
     const float span = amax[0] + amax[1] + bmax;
     return finite && span <= 300.0f;   // NaN / inf weights take the SAFE path
@@ -455,6 +683,33 @@ static bool build_rollout_weights(const float *W, const float *b, RolloutWeights
 
 template <int MODE, bool FAST>
 static void launch_rollout(const RolloutArgs &a, const RolloutWeights *w, cudaStream_t s) {
+#ifndef IAGO_ROLLOUT_SINGLE
+    if (FAST) {   // two lanes per game; CTAs as large as it takes to cover the batch with one CTA per SM, at most 28 warps
+        static int sms = 0;
+        static bool attr_set[2] = {false, false};   // per instantiation and LOG variant; the attribute is per function and sticky
+        if (!sms) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+            if (sms <= 0) sms = 148;
+        }
+        const long long warps = (2 * a.n + 31) / 32;
+        long long wpc = (warps + sms - 1) / sms;
+        wpc = wpc < 2 ? 2 : wpc > kPairMaxWarps ? kPairMaxWarps : wpc;
+        const unsigned grid = (unsigned)((warps + wpc - 1) / wpc);
+        const size_t smem = pair_smem_bytes(kPairMaxWarps);
+        if (a.move_log) {
+            if (!attr_set[1]) cudaFuncSetAttribute(rollout_pair_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set[1] = true;
+            rollout_pair_kernel<MODE, true><<<grid, (unsigned)wpc * 32, pair_smem_bytes((int)wpc), s>>>(a, w);
+        } else {
+            if (!attr_set[0]) cudaFuncSetAttribute(rollout_pair_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            attr_set[0] = true;
+            rollout_pair_kernel<MODE, false><<<grid, (unsigned)wpc * 32, pair_smem_bytes((int)wpc), s>>>(a, w);
+        }
+        return;
+    }
+#endif
     const unsigned grid = (unsigned)((a.n + kBlock - 1) / kBlock);
     if (a.move_log)
         rollout_kernel<MODE, true, FAST><<<grid, kBlock, 0, s>>>(a, w);

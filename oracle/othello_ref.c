@@ -29,9 +29,13 @@
  *     w[k]   = (E0 * E1) * EB in double,  E_c = canon_exp((double)S_c), EB = canon_exp((double)b[k])
  *              — the softmax numerator as a product of exponentials; the reference's max subtraction, denominator
  *              and fp32 division cancel in p/sum(p), and its float64 cdf is float64 here too
- *     choice = double running sum over the legal cells ascending, first legal k with cum_k > u * total, u = m53 / 2^53
- *              == searchsorted(cumsum(p)/cumsum(p)[-1], u, 'right') of np.random.choice, up to the rounding error of the
- *              reference's own fp32 softmax (~1e-9 in cdf units)
+ *     choice = first legal k (ascending) whose cdf exceeds T = u * total, u = m53 / 2^53, with a two-sided double cdf:
+ *              A_k = running sum over the legal cells 0..31 ascending, D_k = running sum over the legal cells 63..32
+ *              descending, total = A_last + D_last; k < 32 (taken when T < A_last): first k with A_k > T; k >= 32: first k
+ *              with D_(legal cells above k) < total - T.  In exact arithmetic this IS
+ *              searchsorted(cumsum(p)/cumsum(p)[-1], u, 'right') of np.random.choice; in double it differs from the
+ *              reference's cdf by ~1e-16, far below the rounding error of the reference's own fp32 softmax (~1e-9 in cdf
+ *              units).  (Two-sided because the kernel gives each half of the board to its own lane.)
  *     canon_exp = Cody-Waite reduction + degree-13 Taylor in double, fixed operation order (no libm dependence)
  *   SAFE  otherwise:
  *     e[k]   = exp32(logit[k] - max over LEGAL k)   only at legal cells
@@ -286,16 +290,34 @@ static int sample_action(const float *state, int color, const int *actions, int 
                          const float *W, const float *b, const policy_tables *t, uint64_t m53) {
     if (n == 1) return actions[0];
     if (t->fast) {
-        /* only the legal cells survive the mask (mcts_self_play.py:103-105) */
-        double cum[64], total = 0.0;
-        for (int a = 0; a < n; a++) {
-            total = total + rollout_weight_at(state, color, t, actions[a] / 8, actions[a] % 8);
-            cum[a] = total;
-        }
+        /* only the legal cells survive the mask (mcts_self_play.py:103-105).  Two-sided cdf: the cells of board rows 0-3 are
+         * summed ascending (A), those of rows 4-7 descending (D); cdf(k) = A_k for k < 32 and total - D_(cells above k) else. */
+        double A[32], D[32], lo = 0.0, hi = 0.0;
+        int cl[32], ch[32], nl = 0, nh = 0;
+        for (int a = 0; a < n; a++)
+            if (actions[a] < 32) {
+                lo = lo + rollout_weight_at(state, color, t, actions[a] / 8, actions[a] % 8);
+                A[nl] = lo;
+                cl[nl++] = actions[a];
+            }
+        for (int a = n - 1; a >= 0; a--)
+            if (actions[a] >= 32) {
+                hi = hi + rollout_weight_at(state, color, t, actions[a] / 8, actions[a] % 8);
+                D[nh] = hi;
+                ch[nh++] = actions[a];
+            }
         const double u = (double)(int64_t)m53 * 1.1102230246251565e-16; /* m53 / 2^53, exact */
+        const double total = lo + hi;
         const double T = u * total;
-        for (int a = 0; a < n; a++) if (cum[a] > T) return actions[a];
-        return actions[n - 1];
+        if (T < lo || nh == 0) {            /* first k with A_k > T */
+            int idx = 0;
+            for (int i = 0; i < nl; i++) idx += (A[i] <= T);
+            return cl[idx < nl - 1 ? idx : nl - 1];
+        }
+        const double R = total - T;          /* first k (ascending) with total - D_(above k) > T  <=>  D_(above k) < R */
+        int idx = 0;
+        for (int j = 0; j + 1 < nh; j++) idx += (D[j] < R);
+        return ch[idx];
     }
     float logits[64];
     for (int a = 0; a < n; a++) logits[actions[a]] = rollout_logit_at(state, color, W, b, actions[a] / 8, actions[a] % 8);

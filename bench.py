@@ -33,9 +33,10 @@ sys.path.insert(0, ROOT)
 
 GAMES_PER_STEP = 65536
 OPS_PER_PLY = 676          # int32 ALU lane-ops per ply: movegen 314 + flip 352 + ~10 (SURVEY.md §8d, step-by-step 6-step flood)
-OPS_PER_PLY_IMPL = 548     # the same rules with the parallel-prefix flood of bitboard.cuh: movegen 250 + flip 288 + ~10
+OPS_PER_PLY_IMPL = 308     # ALU-pipe instructions per ply the paired kernel really issues for the rules (2 lanes x 154, counted in the SASS
+                           # of rollout_pair_kernel<FORCED>: carry-propagation flips / east moves, three parallel-prefix floods; + 92 IMAD on the FMA pipe)
 BYTES_PER_GAME = 17 + 21   # p1,p2,colour in; final p1,p2,n_moves,result out
-NCU_DRAM_BYTES_PER_LAUNCH = 1146112   # profiles/r01_ncu_rollout_v3_summary.csv (dram__bytes_read.sum; write 0), 65,536-game launch
+NCU_DRAM_BYTES_PER_LAUNCH = 1152256   # profiles/r01_ncu_rollout_v4_summary.csv (dram__bytes_read.sum; write 0), 65,536-game launch
 METRIC = "rollout_plies_per_s"
 
 
@@ -363,23 +364,25 @@ def run_ours(args, rank, world, local_rank):
                                                 "H2D / kernel / D2H pipeline", "scope": "rank 0"}},
             "gpu_launches": args.steps * world,
             "clocks": clk.summary(),
-            "roofline": {"bound": "alu", "kernel": "rollout_kernel<PHILOX>", "achieved": achieved / 1e12,
+            "roofline": {"bound": "alu", "kernel": "rollout_pair_kernel<PHILOX> (two lanes per game)", "achieved": achieved / 1e12,
                          "peak": int_peak / 1e12, "unit": "Tint32op/s", "frac": achieved / int_peak,
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == GAMES_PER_STEP else None,
                          "ops_per_ply_as_implemented": OPS_PER_PLY_IMPL,
                          "frac_as_implemented": OPS_PER_PLY_IMPL * plies_per_launch / kernel_s / int_peak,
                          "note": "issue-bound path: 676 algorithmic int32 lane-ops/ply (SURVEY 8d: 6-step flood formulation) x plies per launch / mean launch "
                                  "time; peak = SHF+LOP3 micro-kernel measured in this run (iago_measure_int_peak); traffic = "
-                                 "dram__bytes_read+write per launch from the ncu --set full capture in profiles/r01_ncu_rollout_v3_summary.csv "
+                                 "dram__bytes_read+write per launch from the ncu --set full capture in profiles/r01_ncu_rollout_v4_summary.csv "
                                  "(algorithmic bytes per launch: 38 B x 65,536 games = 2.49 MB; outputs stay in L2 during the capture)"},
-            "roofline_movegen": {"bound": "alu", "kernel": "rollout_kernel<FORCED> (legal_moves + flips + pass/terminal/score only, moves "
+            "roofline_movegen": {"bound": "alu", "kernel": "rollout_pair_kernel<FORCED> (legal_moves + flips + pass/terminal/score only, moves "
                                  "replayed from a 64 B/game log)", "plies_per_s": mg_plies / t_mg,
                                  "achieved": OPS_PER_PLY * mg_plies / t_mg / 1e12, "peak": int_peak / 1e12, "unit": "Tint32op/s",
                                  "frac": OPS_PER_PLY * mg_plies / t_mg / int_peak, "traffic": None, "scope": "rank 0",
                                  "ops_per_ply_as_implemented": OPS_PER_PLY_IMPL,
                                  "frac_as_implemented": OPS_PER_PLY_IMPL * mg_plies / t_mg / int_peak,
-                                 "note": "the kernel floods with a parallel-prefix (Kogge-Stone) form that needs ~548 int32 lane-ops per ply "
-                                         "instead of the 676 of the step-by-step form SURVEY 8d counts, so the fraction on the 676 count can exceed 1"},
+                                 "note": "the kernel finds flips and east moves by carry propagation and floods the other directions in parallel-prefix "
+                                         "form: 308 ALU-pipe instructions per ply (+ 92 IMAD on the FMA pipe) instead of the 676 of the step-by-step "
+                                         "form SURVEY 8d counts, so the fraction on the 676 count exceeds 1; frac_as_implemented is the ALU-pipe "
+                                         "utilisation by the instructions really issued"},
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                              "frac": hbm_ach / hbm_peak, "traffic": None,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
@@ -427,19 +430,21 @@ def section_selfplay(eng, args, rank, world, dev, dist, barrier):
     n = args.selfplay_games
     eng.load_net(0, model_path("sl_model.npz"))
     reps = max(1, args.selfplay_steps)
-    eng.selfplay(0, 0, min(n, 2048), greedy=True, rng=Rng.philox(seed=1, stream_id=1))  # warm-up
+    eng.selfplay(0, 0, n, greedy=True, rng=Rng.philox(seed=1, stream_id=1))  # warm-up at full size (workspaces, clocks)
     barrier()
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
     fwd = pairs = 0
     res = None
-    for i in range(reps):
-        ev[i][0].record()
-        res = eng.selfplay(0, 0, n, greedy=True, rng=Rng.philox(seed=args.seed, game_id0=(i * world + rank) * n, stream_id=1))
-        ev[i][1].record()
-        fwd += res["stats"]["forwards"]
-        pairs += res["stats"]["turn_pairs"]
-    barrier()
-    t = sum(a.elapsed_time(b) for a, b in ev) / 1e3
+    with ClockSampler(dev.index or 0) as clk:
+        for i in range(reps):
+            ev[i][0].record()
+            res = eng.selfplay(0, 0, n, greedy=True, rng=Rng.philox(seed=args.seed, game_id0=(i * world + rank) * n, stream_id=1))
+            ev[i][1].record()
+            fwd += res["stats"]["forwards"]
+            pairs += res["stats"]["turn_pairs"]
+        barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    t = sum(step_ms) / 1e3
     wins = torch.stack([(res["result"] == 1).sum(), (res["result"] == 0).sum(), (res["result"] == -1).sum()]).to(torch.int64)
     tt = torch.tensor([t], dtype=torch.float64, device=dev)
     cc = torch.tensor([reps * n, fwd * n], dtype=torch.int64, device=dev)
@@ -455,6 +460,7 @@ def section_selfplay(eng, args, rank, world, dev, dist, barrier):
            "config": {"workload": "SL-policy greedy self-play, lockstep batch per GPU, sl_model.npz vs sl_model.npz "
                                   "(BASELINE configs[2])", "games_per_step_per_gpu": n, "steps": reps, "precision": "fp16 hi/lo split, 3 MMAs"},
            "positions_per_s": positions / t, "trunk_forwards_per_game": fwd / reps,
+           "step_ms_rank0": [round(x, 2) for x in step_ms], "clocks": clk.summary(),
            "last_step_w_d_l": wins.tolist(),
            "roofline": {"bound": "tensor", "kernel": "trunk_kernel", "achieved": ach, "peak": peak * world, "unit": "TFLOP/s",
                         "frac": ach / (peak * world), "traffic": None, "peak_source": src,

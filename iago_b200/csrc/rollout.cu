@@ -334,17 +334,20 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const Ro
 constexpr int kPairMaxWarps = 28;
 constexpr int kPairSlots = 16;    // running sums kept per lane; a half board with more legal cells (never seen in play) recomputes
 
-struct PairTables {
-    double tab[2][1088];          // [frame][E0 512 | E1 512 | EB 64]
+struct __align__(16) PairCell {   // what the per-cell loop needs about cell c of a frame, one 16-byte load
+    double eb;                    // exp(bias) of the cell
+    uint32_t cm, pad;             // 3x3 window mask of its column
+};
+struct PairTables {               // placed on an 8 KB boundary of the shared window: a table address is (index & 0xFF8) | base
+    double e[2][2][512];          // [frame][plane][pattern]: exp of the tap sum, frame 1 = the turned board
+    PairCell cell[2][32];
     u64 line[4][64];              // line[d][k]: the cells beyond k along direction +1, +7, +8, +9 up to the board edge
-    uint32_t colmask[8];
-    uint32_t pad[8];
 };
 struct PairScratch {              // per warp
     double cum[kPairSlots][32];
     uint8_t cell[kPairSlots][32];
 };
-static size_t pair_smem_bytes(int warps) { return sizeof(PairTables) + (size_t)warps * sizeof(PairScratch); }
+static size_t pair_smem_bytes(int warps) { return 8192 + sizeof(PairTables) + (size_t)warps * sizeof(PairScratch); }
 
 __device__ __forceinline__ u64 rev64(u64 x) { return ((u64)__brev((uint32_t)x) << 32) | (u64)__brev((uint32_t)(x >> 32)); }
 __device__ __forceinline__ u64 pair_xchg(unsigned mask, u64 x) {   // the partner lane's x, turned into this lane's frame
@@ -376,23 +379,35 @@ __device__ __forceinline__ u64 half_flips(const u64 (*line)[64], int k, u64 mv, 
 struct PairPlanes {
     uint32_t o0, o1, m0, m1;   // opponent / mover planes << 9, words 0 and 1: all a window starting at a cell below 32 can reach
 };
-__device__ __forceinline__ double pair_weight(const char *tab, const uint32_t *colmask, const PairPlanes &p, int sh) {
-    const uint32_t cm = colmask[sh & 7];
-    const uint32_t t0 = __funnelshift_r(p.o0, p.o1, (uint32_t)sh) & cm;
-    const uint32_t t1 = __funnelshift_r(p.m0, p.m1, (uint32_t)sh) & cm;
-    const double e0 = *reinterpret_cast<const double *>(tab + (((t0 * 0x400801u) >> 13) & 0xFF8u));
-    const double e1 = *reinterpret_cast<const double *>(tab + 4096 + (((t1 * 0x400801u) >> 13) & 0xFF8u));
-    const double eb = *reinterpret_cast<const double *>(tab + 8192 + sh * 8);
-    return __dmul_rn(__dmul_rn(e0, e1), eb);
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
+}
+// e_base = shared-window address of e[frame][0] (8 KB aligned), cells = cell[frame]
+__device__ __forceinline__ double pair_weight(uint32_t e_base, const PairCell *cells, const PairPlanes &p, int sh) {
+#ifndef IAGO_PAIR_SPLIT_CELL
+    const uint4 raw = *reinterpret_cast<const uint4 *>(cells + sh);   // one 16-byte load: eb (x, y), cm (z)
+#else
+    uint4 raw;
+    raw.z = cells[sh].cm;
+    const double ebv = cells[sh].eb;
+    raw.x = (uint32_t)__double2loint(ebv); raw.y = (uint32_t)__double2hiint(ebv);
+#endif
+    const uint32_t t0 = __funnelshift_r(p.o0, p.o1, (uint32_t)sh) & raw.z;
+    const uint32_t t1 = __funnelshift_r(p.m0, p.m1, (uint32_t)sh) & raw.z;
+    const double e0 = lds_f64((((t0 * 0x400801u) >> 13) & 0xFF8u) | e_base);
+    const double e1 = lds_f64((((t1 * 0x400801u) >> 13) & 0xFF8u) | (e_base + 0x1000u));
+    return __dmul_rn(__dmul_rn(e0, e1), __hiloint2double((int)raw.y, (int)raw.x));
 }
 // More legal cells in this half than scratch slots: nothing was stored, walk again.  First cell (own-frame ascending) whose
 // running sum fails `pred`, the last cell when none does.
-__device__ __noinline__ int pair_pick_slow(const char *tab, const uint32_t *colmask, PairPlanes p, uint32_t wd, int limit, double thr, int h) {
+__device__ __noinline__ int pair_pick_slow(uint32_t e_base, const PairCell *cells, PairPlanes p, uint32_t wd, int limit, double thr, int h) {
     double cum = 0.0;
     int last = 0, j = 0;
     for (; wd; wd &= wd - 1, j++) {
         last = __ffs((int)wd) - 1;
-        cum = __dadd_rn(cum, pair_weight(tab, colmask, p, last));
+        cum = __dadd_rn(cum, pair_weight(e_base, cells, p, last));
         const bool pred = h ? (cum < thr) : (cum <= thr);
         if (!(j < limit && pred)) break;
     }
@@ -401,16 +416,23 @@ __device__ __noinline__ int pair_pick_slow(const char *tab, const uint32_t *colm
 
 template <int MODE, bool LOG>
 __global__ void __launch_bounds__(kPairMaxWarps * 32, 1) rollout_pair_kernel(RolloutArgs a, const RolloutWeights *__restrict__ gw) {
-    extern __shared__ __align__(16) unsigned char pair_smem[];
+    extern __shared__ __align__(16) unsigned char pair_smem_raw[];
+    unsigned char *pair_smem = pair_smem_raw + ((0x2000u - ((uint32_t)__cvta_generic_to_shared(pair_smem_raw) & 0x1FFFu)) & 0x1FFFu);
     PairTables &sm = *reinterpret_cast<PairTables *>(pair_smem);
     PairScratch &scr = reinterpret_cast<PairScratch *>(pair_smem + sizeof(PairTables))[threadIdx.x >> 5];
     if (MODE != IAGO_RNG_FORCED) {
-        const double *e = &gw->elut[0][0], *er = &gw->elut_r[0][0];   // elut[2][512] | ebias[64] and elut_r | ebias_r: contiguous
-        for (int i = threadIdx.x; i < 1088; i += blockDim.x) {
-            sm.tab[0][i] = e[i];
-            sm.tab[1][i] = er[i];
+        for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
+            (&sm.e[0][0][0])[i] = (&gw->elut[0][0])[i];
+            (&sm.e[1][0][0])[i] = (&gw->elut_r[0][0])[i];
         }
-        if (threadIdx.x < 8) sm.colmask[threadIdx.x] = gw->colmask[threadIdx.x];
+        if (threadIdx.x < 64) {
+            const int f = threadIdx.x >> 5, c = threadIdx.x & 31;
+            PairCell ci;
+            ci.eb = f ? gw->ebias_r[c] : gw->ebias[c];
+            ci.cm = gw->colmask[c & 7];
+            ci.pad = 0;
+            sm.cell[f][c] = ci;
+        }
     }
     for (int i = threadIdx.x; i < 256; i += blockDim.x) {
         const int d = i >> 6, k = i & 63, r = k >> 3, c = k & 7;
@@ -434,7 +456,8 @@ __global__ void __launch_bounds__(kPairMaxWarps * 32, 1) rollout_pair_kernel(Rol
         if (h) { own = rev64(own); opp = rev64(opp); }
         int stone_num = __popcll(own | opp);  // 64 - sum(state == 0), mcts_self_play.py:15
         bool pass_flg = false;
-        const char *tab = reinterpret_cast<const char *>(sm.tab[h]);
+        const uint32_t e_base = (uint32_t)__cvta_generic_to_shared(&sm.e[h][0][0]);
+        const PairCell *cells = sm.cell[h];
         double *sa = &scr.cum[0][threadIdx.x & 31];
         uint8_t *sc = &scr.cell[0][threadIdx.x & 31];
         uint32_t rnd[4] = {0, 0, 0, 0};  // the Philox block serving draws 4*(placed >> 2) .. + 3
@@ -454,8 +477,15 @@ __global__ void __launch_bounds__(kPairMaxWarps * 32, 1) rollout_pair_kernel(Rol
                         if (MODE == IAGO_RNG_UNIFORMS)
                             m53 = __double2ull_rz(a.uniforms[g * a.u_stride + placed] * 9007199254740992.0);
                         else {
+#ifndef IAGO_PAIR_NO_COOP_PHILOX
+                            // lane h holds Philox block 2 * (placed >> 3) + h: the ten rounds run once per EIGHT stones of a game
+                            if ((placed & 7) == 0) philox_block(a.seed, gid, (((uint32_t)placed >> 3) << 1) + h, a.stream_id, rnd);
+                            const uint32_t mine = (placed & 2) ? ((placed & 1) ? rnd[3] : rnd[2]) : ((placed & 1) ? rnd[1] : rnd[0]);
+                            const uint32_t wd = __shfl_sync(pmask, mine, (threadIdx.x & 30) + ((placed >> 2) & 1));
+#else
                             if ((placed & 3) == 0) philox_block(a.seed, gid, (uint32_t)placed >> 2, a.stream_id, rnd);
                             const uint32_t wd = (placed & 2) ? ((placed & 1) ? rnd[3] : rnd[2]) : ((placed & 1) ? rnd[1] : rnd[0]);
+#endif
                             m53 = (u64)wd << 21;
                         }
                         const double u = __dmul_rn((double)(long long)m53, 1.1102230246251565e-16);  // m53 / 2^53, exact
@@ -474,12 +504,12 @@ __global__ void __launch_bounds__(kPairMaxWarps * 32, 1) rollout_pair_kernel(Rol
                             for (int i = 0; i < n; i++) {
                                 const int sh = __ffs((int)wd) - 1;
                                 wd &= wd - 1;
-                                cum = __dadd_rn(cum, pair_weight(tab, sm.colmask, pl, sh));
+                                cum = __dadd_rn(cum, pair_weight(e_base, cells, pl, sh));
                                 sa[i * 32] = cum;
                                 sc[i * 32] = (uint8_t)sh;
                             }
                         } else {
-                            for (uint32_t wd = lw; wd; wd &= wd - 1) cum = __dadd_rn(cum, pair_weight(tab, sm.colmask, pl, __ffs((int)wd) - 1));
+                            for (uint32_t wd = lw; wd; wd &= wd - 1) cum = __dadd_rn(cum, pair_weight(e_base, cells, pl, __ffs((int)wd) - 1));
                         }
                         // A_last (lane 0) and D_last (lane 1) -> total, T, and which half holds the answer
                         const double oth = __hiloint2double(__shfl_xor_sync(pmask, __double2hiint(cum), 1),
@@ -500,7 +530,7 @@ __global__ void __launch_bounds__(kPairMaxWarps * 32, 1) rollout_pair_kernel(Rol
                             idx = max(min(idx, n - 1), 0);
                             c = (int)sc[idx * 32];
                         } else {
-                            c = pair_pick_slow(tab, sm.colmask, pl, lw, n - h, thr, h);
+                            c = pair_pick_slow(e_base, cells, pl, lw, n - h, thr, h);
                         }
                         const int ct = h ? 63 - c : c;   // this lane's candidate as a cell of the real board
                         const int octv = __shfl_xor_sync(pmask, ct, 1);

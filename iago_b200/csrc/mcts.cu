@@ -275,6 +275,225 @@ __global__ void __launch_bounds__(32) mcts_select_kernel(MctsDev d, MctsParams p
     if (lane == 0) d.n_nodes[t] = n_nodes;
 }
 
+// ---------------------------------------------------------------- pipelined select
+// The same descents in the same order, as a software pipeline: kPipeWarps warps per tree, warp w runs the tree's active descents
+// w, w + W, w + 2W, ... .  Descent a may work on stage k (stage 0 = root bookkeeping, stage L + 1 = choosing a child at depth L)
+// only after descent a - 1 has finished stage k or ended above it, and may do its leaf work (expansion, request lists, node
+// allocation) only after descent a - 1 has ended.  By induction every descent then sees exactly the virtual visits, expansions and
+// node indices it would see if the descents ran one after the other, so the tree is bit-identical to mcts_select_kernel's — but a
+// level of the tree costs one load round per descent in flight instead of one per descent.
+// Progress flags live in shared memory (prog[a] = stages finished, INT_MAX = ended); node data written by one warp is published to
+// the other warps of the CTA by __threadfence_block before the flag is raised and read after a fence behind the flag (release /
+// acquire at CTA scope; all warps of a tree share one SM and its L1).  In pass 2 stages count from the node a descent was parked
+// on: only descents parked on the same node meet in the tree (a pending node has no visible children, so no parked node lies
+// below another), those start at the same depth, and the wait chain is transitive.
+constexpr int kPipeWarps = 8;
+constexpr int kPipeMaxB = 1024;
+
+__device__ __forceinline__ void pipe_wait(const volatile int *prog, int a, int need) {   // until descent a - 1 has progress >= need
+    if (a == 0) return;
+    while (prog[a - 1] < need) __nanosleep(20);
+    __threadfence_block();
+}
+__device__ __forceinline__ void pipe_signal(volatile int *prog, int a, int value, int lane) {
+    __syncwarp();
+    __threadfence_block();
+    if (lane == 0) prog[a] = value;
+}
+
+__global__ void __launch_bounds__(kPipeWarps * 32) mcts_select_pipe_kernel(MctsDev d, MctsParams p, int pass) {
+    __shared__ volatile int prog[kPipeMaxB];
+    __shared__ short active[kPipeMaxB];
+    __shared__ int n_active;
+    __shared__ volatile int s_n_nodes;
+    const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    MctsNode *nodes = d.nodes + (size_t)t * d.cap;
+    const long long done = d.done[t];
+    if (threadIdx.x == 0) {   // the descents that run in this pass, in slot order (a few hundred at most)
+        int c = 0;
+        for (int s = 0; s < p.B; s++) {
+            const bool on = pass == 1 ? (done + s < p.target) : (d.status[t * p.B + s] == S_PARKED);
+            if (on) active[c++] = (short)s;
+        }
+        n_active = c;
+        s_n_nodes = d.n_nodes[t];
+    }
+    for (int i = threadIdx.x; i < p.B; i += blockDim.x) {
+        prog[i] = 0;
+        if (pass == 1 && done + i >= p.target && i < p.B) {   // idle slot: an empty board, the rollout ends at once
+            const int slot = t * p.B + i;
+            d.status[slot] = S_INACTIVE;
+            d.leaf_p1[slot] = 0; d.leaf_p2[slot] = 0; d.leaf_color[slot] = 1;
+            d.game_ids[slot] = 0;
+        }
+    }
+    __syncthreads();
+    const int na = n_active;
+    for (int a = warp; a < na; a += kPipeWarps) {
+        const int s = active[a], slot = t * p.B + s;
+        int node, color, stage = 0;
+        u64 own, opp;
+        int nch, flags, n_here, vn_here, fc;
+        pipe_wait(prog, a, 1);
+        if (pass == 1) {
+            node = 0;
+            color = d.root_color[t];
+            own = color == 1 ? d.root_p1[t] : d.root_p2[t];
+            opp = color == 1 ? d.root_p2[t] : d.root_p1[t];
+            const uint4 w1 = reinterpret_cast<const uint4 *>(nodes)[1], w2 = reinterpret_cast<const uint4 *>(nodes)[2];
+            n_here = (int)w1.w; vn_here = (int)w2.x + 1; fc = (int)w2.z;
+            nch = (w2.w >> 8) & 0xFF; flags = (w2.w >> 16) & 0xFF;
+            if (lane == 0) {
+                nodes[0].vn = vn_here;
+                d.game_ids[slot] = (d.tree_gid[t] << 32) | (u64)(uint32_t)(done + s);
+            }
+        } else {
+            node = d.leaf_node[slot];
+            color = d.leaf_color[slot];
+            own = color == 1 ? d.leaf_p1[slot] : d.leaf_p2[slot];
+            opp = color == 1 ? d.leaf_p2[slot] : d.leaf_p1[slot];
+            const uint4 w1 = reinterpret_cast<const uint4 *>(nodes + node)[1], w2 = reinterpret_cast<const uint4 *>(nodes + node)[2];
+            n_here = (int)w1.w; vn_here = (int)w2.x; fc = (int)w2.z;
+            nch = (w2.w >> 8) & 0xFF; flags = (w2.w >> 16) & 0xFF;
+        }
+        stage = 1;
+        pipe_signal(prog, a, stage, lane);
+        bool exclusive = false;   // true once descent a - 1 has ended: nothing this descent reads can change any more
+        for (;;) {
+            if (nch == 0) {
+                if (!exclusive) {
+                    pipe_wait(prog, a, 0x7FFFFFFF);
+                    exclusive = true;
+                    // an earlier descent may have expanded or parked this node after its header was read: read it again
+                    const uint4 w1 = reinterpret_cast<const uint4 *>(nodes + node)[1], w2 = reinterpret_cast<const uint4 *>(nodes + node)[2];
+                    n_here = (int)w1.w; fc = (int)w2.z;
+                    nch = (w2.w >> 8) & 0xFF; flags = (w2.w >> 16) & 0xFF;
+                    if (nch != 0) continue;
+                }
+                int n_nodes = s_n_nodes;
+                bool park = (flags & F_PENDING) != 0;
+                if (!park && n_here >= p.n_thr) {  // MCTS.py:108-121 expand
+                    const u64 legal = legal_moves(own, opp);
+                    const int k = __popcll(legal), c = k > 0 ? k : 1;
+                    if (n_nodes + c <= d.cap) {
+                        const int base = n_nodes;
+                        n_nodes += c;
+                        for (int i = lane; i < c; i += 32) {
+                            MctsNode ch;
+                            ch.P = k <= 1 ? 1.1 : 0.0;   // Node(node, 1): the literal 1 + 0.1 in float64 (MCTS.py:114,117)
+                            ch.Q = 0.0; ch.W = 0; ch.v = 0.0f; ch.n = 0; ch.vn = 0; ch.parent = node; ch.first_child = -1;
+                            ch.action = (int8_t)(k == 0 ? -1 : nth_set_bit(legal, i));
+                            ch.nch = 0; ch.flags = k <= 1 ? F_P_F64 : 0; ch.nch_pending = 0;
+                            nodes[base + i] = ch;
+                        }
+                        __syncwarp();
+                        if (lane == 0) s_n_nodes = n_nodes;
+                        if (k <= 1) {
+                            if (lane == 0) { nodes[node].first_child = base; nodes[node].nch = (uint8_t)c; }
+                            __syncwarp();
+                            __threadfence_block();
+                            fc = base;
+                            nch = c;
+                            continue;  // the playout goes on through the only child (MCTS.py:121)
+                        }
+                        if (lane == 0) {
+                            nodes[node].first_child = base;
+                            nodes[node].nch_pending = (uint8_t)c;
+                            nodes[node].flags = (uint8_t)(flags | F_PENDING);
+                            const int j = atomicAdd(d.counts + 0, 1);
+                            d.pol_p1[j] = color == 1 ? own : opp;
+                            d.pol_p2[j] = color == 1 ? opp : own;
+                            d.pol_color[j] = (uint8_t)color;
+                            d.pol_node[j] = t * d.cap + node;
+                        }
+                        park = true;
+                    } else if (lane == 0) {
+                        atomicAdd(d.counts + 2, 1);  // pool full: evaluate instead of expanding (reported to the host)
+                    }
+                }
+                if (lane == 0) {
+                    d.leaf_node[slot] = node;
+                    d.leaf_p1[slot] = color == 1 ? own : opp;
+                    d.leaf_p2[slot] = color == 1 ? opp : own;
+                    d.leaf_color[slot] = (uint8_t)color;
+                    if (park) {
+                        d.status[slot] = S_PARKED;
+                        if (pass == 2) atomicAdd(d.counts + 3, 1);
+                    } else {
+                        d.status[slot] = S_EVAL;
+                        if (p.need_v) {
+                            const uint8_t fl = nodes[node].flags;
+                            const bool have = p.cache_v && (fl & (F_V_VALID | F_V_CLAIMED));
+                            if (!have) {
+                                if (p.cache_v) nodes[node].flags = (uint8_t)(fl | F_V_CLAIMED);
+                                const int j = atomicAdd(d.counts + 1, 1);
+                                d.val_p1[j] = color == 1 ? own : opp;
+                                d.val_p2[j] = color == 1 ? opp : own;
+                                d.val_color[j] = (uint8_t)color;
+                                d.val_node[j] = t * d.cap + node;
+                                d.val_slot[j] = slot;
+                            }
+                        }
+                    }
+                }
+                break;
+            }
+            // ---- select (MCTS.py:39-49): arg-max over children of Q + u, first maximum wins
+            if (!exclusive) pipe_wait(prog, a, stage + 1);
+            const double n_parent = (double)(n_here + vn_here - 1);  // without this descent's own virtual visit
+            const double sq = __dsqrt_rn(n_parent);
+            double best = -1.0e300;
+            int best_i = 1 << 30;
+            int b_n = 0, b_vn = 0, b_fc = -1, b_meta = 0;
+            for (int i = lane; i < nch; i += 32) {
+                const uint4 *raw = reinterpret_cast<const uint4 *>(nodes + fc + i);
+                const uint4 w0 = raw[0], w1 = raw[1], w2 = raw[2];   // P Q | W v n | vn parent first_child meta
+                const double cP = __hiloint2double((int)w0.y, (int)w0.x);
+                const long long cW = (long long)(((u64)w1.y << 32) | (u64)w1.x);
+                const int cn = (int)w1.w, cvn = (int)w2.x, cflags = (int)((w2.w >> 16) & 0xFFu);
+                const double cp = (cflags & F_P_F64) ? __dmul_rn(p.c_puct, cP) : (double)__fmul_rn((float)p.c_puct, (float)cP);
+                const int tot = cn + cvn;
+                const double q = tot > 0 ? __ddiv_rn(__dsub_rn((double)cW * (1.0 / kFix), __dmul_rn(p.vloss, (double)cvn)), (double)tot) : 0.0;
+                const double den = __dadd_rn(0.01, (double)tot);
+                const double u = __ddiv_rn(__dmul_rn(cp, sq), den);
+                const double val = __dadd_rn(q, u);
+                if (val > best) {  // ascending i: the first maximum stays
+                    best = val; best_i = i;
+                    b_n = cn; b_vn = cvn; b_fc = (int)w2.z; b_meta = (int)w2.w;
+                }
+            }
+            int win = lane;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ov = shfl_down_d(best, o);
+                const int oi = __shfl_down_sync(0xFFFFFFFFu, best_i, o);
+                const int ow = __shfl_down_sync(0xFFFFFFFFu, win, o);
+                if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; win = ow; }
+            }
+            win = __shfl_sync(0xFFFFFFFFu, win, 0);
+            best_i = __shfl_sync(0xFFFFFFFFu, best_i, 0);
+            const int child = fc + best_i;
+            n_here = __shfl_sync(0xFFFFFFFFu, b_n, win);
+            vn_here = __shfl_sync(0xFFFFFFFFu, b_vn, win) + 1;   // with this descent's own virtual visit, stored below
+            fc = __shfl_sync(0xFFFFFFFFu, b_fc, win);
+            const int meta = __shfl_sync(0xFFFFFFFFu, b_meta, win);
+            const int act = (int)(int8_t)(meta & 0xFF);
+            nch = (meta >> 8) & 0xFF;
+            flags = (meta >> 16) & 0xFF;
+            if (lane == 0) nodes[child].vn = vn_here;
+            stage++;
+            if (!exclusive) pipe_signal(prog, a, stage, lane);
+            if (act >= 0) place(1ULL << act, own, opp);   // action -1 = pass = no-op (game.py:181-182)
+            { const u64 tmp = own; own = opp; opp = tmp; }
+            color = 3 - color;
+            node = child;
+        }
+        pipe_signal(prog, a, 0x7FFFFFFF, lane);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) d.n_nodes[t] = s_n_nodes;
+}
+
 // priors: child P = float32(prob[action] + 0.1) (MCTS.py:93-99, :18-19); the children become visible.
 __global__ void mcts_expand_kernel(MctsDev d) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -616,12 +835,15 @@ int iago_mcts_search(iago_mcts *m, const iago_mcts_params *pp, void *stream) {
     IAGO_CUDA(cudaMemsetAsync(d.counts, 0, 8 * sizeof(int), s));
     for (int w = 0; w < waves; w++) {
         IAGO_CUDA(cudaMemsetAsync(d.counts, 0, 2 * sizeof(int), s));
-        mcts_select_kernel<<<m->T, 32, 0, s>>>(d, p, 1);
+        const bool pipe = !p.exact && p.B >= 8 && p.B <= kPipeMaxB;   // descents of a tree as a software pipeline over 8 warps
+        if (pipe) mcts_select_pipe_kernel<<<m->T, kPipeWarps * 32, 0, s>>>(d, p, 1);
+        else mcts_select_kernel<<<m->T, 32, 0, s>>>(d, p, 1);
         IAGO_CUDA(cudaGetLastError());
         int rc = trunk_launch(ctx, pp->slot_policy, 0, (const uint64_t *)d.pol_p1, (const uint64_t *)d.pol_p2, d.pol_color, S, d.probs, 1, pp->precision, s, d.counts + 0);
         if (rc) return rc;
         mcts_expand_kernel<<<(unsigned)((S + 127) / 128), 128, 0, s>>>(d);
-        mcts_select_kernel<<<m->T, 32, 0, s>>>(d, p, 2);
+        if (pipe) mcts_select_pipe_kernel<<<m->T, kPipeWarps * 32, 0, s>>>(d, p, 2);
+        else mcts_select_kernel<<<m->T, 32, 0, s>>>(d, p, 2);
         IAGO_CUDA(cudaGetLastError());
         if (run_v) {
             rc = trunk_launch(ctx, pp->slot_value, 1, (const uint64_t *)d.val_p1, (const uint64_t *)d.val_p2, d.val_color, S, d.vals, 0, pp->precision, s, d.counts + 1);

@@ -106,6 +106,53 @@ def test_arbitrary_boards_sample_vs_oracle(engine, cref, rollout_weights):
     assert max(counts) >= 34 and sum(c > 32 for c in counts) >= 3  # the recompute path was exercised
 
 
+def test_arbitrary_boards_full_rollouts_vs_oracle(engine, cref, rollout_weights):
+    """Whole rollouts from arbitrary (unreachable) boards in all three rng modes.  The paired kernel keeps 16 running sums per
+    lane; the hill-climbed boards have more than 16 legal cells in one half of the board, so the first turn of those games takes
+    its recompute path, and random dense boards exercise extreme u values at the seams of the two-sided cdf."""
+    from iago_b200 import Rng
+    W, b = rollout_weights
+    rng = np.random.default_rng(11)
+    n = 4000
+    st = np.zeros((n, 64), np.float32)
+    many = np.array([[int(ch) for ch in s] for s in MANY_MOVES], np.float32)
+    for i in range(n):
+        if i % 4 == 0:
+            st[i] = many[(i // 4) % 3]
+            if i >= 12:
+                idx = rng.integers(0, 64, 2)
+                st[i, idx] = rng.integers(0, 3, 2)
+            if (i // 4) % 2:
+                st[i] = st[i][::-1]   # the same board turned by 180 degrees: the crowded half changes lanes
+        else:
+            fill = rng.random()
+            r = rng.random(64)
+            st[i] = np.where(r < fill * 0.5, 1, np.where(r < fill, 2, 0))
+    col = rng.integers(1, 3, n).astype(np.uint8)
+    col[::4] = 1
+    half_counts = []
+    for i in range(0, n, 4):
+        acts = cref.legal_actions(st[i], int(col[i]))
+        half_counts.append(max(sum(a < 32 for a in acts), sum(a >= 32 for a in acts)))
+    assert sum(c > 16 for c in half_counts) >= 6
+    p1, p2 = bb(st)
+    ref = cref.simulate_batch(st, col.astype(np.int32), W, b, mode=cref.RNG_PHILOX, seed=77, game_id0=3, threads=0)
+    out = engine.rollout_host(p1, p2, col, rng=Rng.philox(seed=77, game_id0=3), want_moves=True)
+    assert (out["moves"] == ref["moves"]).all() and (out["result"] == ref["results"]).all()
+    r1, r2 = bb(ref["final"])
+    assert (out["final_p1"] == r1).all() and (out["final_p2"] == r2).all()
+    # replayed uniforms, with the extreme values in every position of the stream
+    u = rng.random((n, 64))
+    u[:, ::7] = np.array([0.0, 1 - 2.0**-53, 0.5, 2.0**-53, 0.999999, 1e-9, 0.25, 0.75, 0.125, 0.875])[rng.integers(0, 10, (n, 10))]
+    ref = cref.simulate_batch(st, col.astype(np.int32), W, b, mode=cref.RNG_UNIFORMS, uniforms=u, threads=0)
+    out = engine.rollout_host(p1, p2, col, rng=Rng.replay_uniforms(u), want_moves=True)
+    assert (out["moves"] == ref["moves"]).all() and (out["result"] == ref["results"]).all()
+    # and the moves replayed
+    out2 = engine.rollout_host(p1, p2, col, rng=Rng.replay_moves(ref["moves"]), want_moves=True)
+    r1, r2 = bb(ref["final"])
+    assert (out2["moves"] == ref["moves"]).all() and (out2["final_p1"] == r1).all() and (out2["final_p2"] == r2).all()
+
+
 def test_logits_vs_oracle_and_reference(engine, cref, rollout_weights, golden_nets):
     W, b = rollout_weights
     g = golden_nets

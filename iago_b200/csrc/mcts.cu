@@ -287,12 +287,15 @@ __global__ void __launch_bounds__(32) mcts_select_kernel(MctsDev d, MctsParams p
 // acquire at CTA scope; all warps of a tree share one SM and its L1).  In pass 2 stages count from the node a descent was parked
 // on: only descents parked on the same node meet in the tree (a pending node has no visible children, so no parked node lies
 // below another), those start at the same depth, and the wait chain is transitive.
-constexpr int kPipeWarps = 8;
+#ifndef IAGO_PIPE_WARPS
+#define IAGO_PIPE_WARPS 8
+#endif
+constexpr int kPipeWarps = IAGO_PIPE_WARPS;
 constexpr int kPipeMaxB = 1024;
 
 __device__ __forceinline__ void pipe_wait(const volatile int *prog, int a, int need) {   // until descent a - 1 has progress >= need
     if (a == 0) return;
-    while (prog[a - 1] < need) __nanosleep(20);
+    while (prog[a - 1] < need) __nanosleep(20);   // (a pure spin measured the same)
     __threadfence_block();
 }
 __device__ __forceinline__ void pipe_signal(volatile int *prog, int a, int value, int lane) {
@@ -703,6 +706,8 @@ struct iago_mcts {
     int32_t *d_stats = nullptr;  // visits [T][65] | q [T][65] | best [T]
     int last_exact = 1;
     long long overflows = 0;
+    cudaStream_t side = nullptr;            // the lockstep rollouts of a wave run here, beside the value-net launch
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
 };
 
 template <class T_>
@@ -761,6 +766,9 @@ int iago_mcts_destroy(iago_mcts *m) {
     cudaFree(m->d_forced_v);
     cudaFree(m->d_forced_z);
     if (m->h_counts) cudaFreeHost(m->h_counts);
+    if (m->side) cudaStreamDestroy(m->side);
+    if (m->ev_fork) cudaEventDestroy(m->ev_fork);
+    if (m->ev_join) cudaEventDestroy(m->ev_join);
     delete m;
     return IAGO_OK;
 }
@@ -845,16 +853,29 @@ int iago_mcts_search(iago_mcts *m, const iago_mcts_params *pp, void *stream) {
         if (pipe) mcts_select_pipe_kernel<<<m->T, kPipeWarps * 32, 0, s>>>(d, p, 2);
         else mcts_select_kernel<<<m->T, 32, 0, s>>>(d, p, 2);
         IAGO_CUDA(cudaGetLastError());
+        // value net and rollouts read the same leaves and write different outputs: the rollouts go to a second stream
+        const bool fork = run_v && run_z;
+        if (fork) {
+            if (!m->side) {
+                IAGO_CUDA(cudaStreamCreateWithFlags(&m->side, cudaStreamNonBlocking));
+                IAGO_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
+                IAGO_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
+            }
+            IAGO_CUDA(cudaEventRecord(m->ev_fork, s));
+            IAGO_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
+        }
+        if (run_z) {
+            rc = rollout_launch_ids(ctx, (const uint64_t *)d.leaf_p1, (const uint64_t *)d.leaf_p2, d.leaf_color, S, pp->seed, 2u,
+                                    (const uint64_t *)d.game_ids, d.z, nullptr, nullptr, fork ? m->side : s);
+            if (rc) return rc;
+            if (fork) IAGO_CUDA(cudaEventRecord(m->ev_join, m->side));
+        }
         if (run_v) {
             rc = trunk_launch(ctx, pp->slot_value, 1, (const uint64_t *)d.val_p1, (const uint64_t *)d.val_p2, d.val_color, S, d.vals, 0, pp->precision, s, d.counts + 1);
             if (rc) return rc;
             mcts_scatter_value_kernel<<<(unsigned)((S + 127) / 128), 128, 0, s>>>(d, p.cache_v);
         }
-        if (run_z) {
-            rc = rollout_launch_ids(ctx, (const uint64_t *)d.leaf_p1, (const uint64_t *)d.leaf_p2, d.leaf_color, S, pp->seed, 2u,
-                                    (const uint64_t *)d.game_ids, d.z, (uint64_t *)d.val_p1, (uint64_t *)d.val_p2, s);
-            if (rc) return rc;
-        }
+        if (fork) IAGO_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));
         if (p.exact) {
             mcts_backup_exact_kernel<<<(m->T + 63) / 64, 64, 0, s>>>(d, p);
         } else {

@@ -302,8 +302,10 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const Ro
         // an even number of swaps happened: own = stones of `color` again
         const int me = __popcll(own), op = __popcll(opp);
         a.result[g] = (int8_t)((me > op) - (me < op));
-        a.final_p1[g] = (color == 1) ? own : opp;
-        a.final_p2[g] = (color == 1) ? opp : own;
+        if (a.final_p1) {
+            a.final_p1[g] = (color == 1) ? own : opp;
+            a.final_p2[g] = (color == 1) ? opp : own;
+        }
         if (a.n_moves) a.n_moves[g] = placed;
         if (LOG)
             for (int i = placed; i < 64; i++) a.move_log[g * 64 + i] = -1;
@@ -563,8 +565,10 @@ __global__ void __launch_bounds__(kPairMaxWarps * 32, 1) rollout_pair_kernel(Rol
             // an even number of swaps happened: own = stones of `color` again
             const int me = __popcll(own), op = __popcll(opp);
             a.result[g] = (int8_t)((me > op) - (me < op));
-            a.final_p1[g] = (color == 1) ? own : opp;
-            a.final_p2[g] = (color == 1) ? opp : own;
+            if (a.final_p1) {   // nullable for callers that only want the result (mcts.cu)
+                a.final_p1[g] = (color == 1) ? own : opp;
+                a.final_p2[g] = (color == 1) ? opp : own;
+            }
             if (a.n_moves) a.n_moves[g] = placed;
             if (LOG)
                 for (int i = placed; i < 64; i++) a.move_log[g * 64 + i] = -1;

@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
         }
     } else if ((tid & 31) == 0) {
         // ================= MMA issuer =================
-        const uint32_t idesc = instr_desc(128, N);   // fp16 operands, fp32 accumulate
+        const uint32_t idesc = instr_desc(128, N), idesc256 = instr_desc(128, 256);   // fp16 operands, fp32 accumulate
         const uint64_t hi_a = ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46);   // SBO = 1,024 B between o groups
         const uint64_t hi_b = ((uint64_t)(1280 >> 4) << 32) | (1ULL << 46);   // SBO = 1,280 B between c groups (10 padded rows)
         const uint32_t lbo_word = (uint32_t)(128 >> 4) << 16;                 // LBO = 128 B between K-adjacent core matrices (board rows)
@@ -383,14 +383,31 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
             const uint32_t st = sbase + stage * kWgStage;
-#pragma unroll
-            for (int kx = 0; kx < 3; kx++) {
+            if (N == 128) {
+                // The X copies for kx = 0 and kx = 1 are adjacent in units of the c-group stride (16 groups x 1,280 B = one copy), so
+                // one N = 256 MMA serves both taps and reads the dY tile once for the two of them; accumulator columns 0-255 are
+                // exactly taps kx = 0 | kx = 1.  (Shared-memory throughput is what bounds this kernel: 32 KB less per position.)
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {   // board rows (2 ks, 2 ks + 1) of dY against padded rows (2 ks + ky, 2 ks + ky + 1) of X
                     const uint32_t aw = ((st + ks * 256) >> 4) | lbo_word, alw = ((st + kWgATile + ks * 256) >> 4) | lbo_word;
-                    const uint32_t bw = ((st + kWgXBase + kx * kWgXCopy + (2 * ks + ky) * 128) >> 4) | lbo_word;
-                    umma_f16(tmem + kx * 128, hi_a | aw, hi_b | bw, idesc, (ip > 0 || ks > 0) ? 1u : 0u);
-                    umma_f16(tmem + kx * 128, hi_a | alw, hi_b | bw, idesc, 1u);
+                    const uint32_t bw01 = ((st + kWgXBase + (2 * ks + ky) * 128) >> 4) | lbo_word;
+                    const uint32_t bw2 = ((st + kWgXBase + 2 * kWgXCopy + (2 * ks + ky) * 128) >> 4) | lbo_word;
+                    const uint32_t acc = (ip > 0 || ks > 0) ? 1u : 0u;
+                    umma_f16(tmem, hi_a | aw, hi_b | bw01, idesc256, acc);
+                    umma_f16(tmem, hi_a | alw, hi_b | bw01, idesc256, 1u);
+                    umma_f16(tmem + 256, hi_a | aw, hi_b | bw2, idesc, acc);
+                    umma_f16(tmem + 256, hi_a | alw, hi_b | bw2, idesc, 1u);
+                }
+            } else {
+#pragma unroll
+                for (int kx = 0; kx < 3; kx++) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) {
+                        const uint32_t aw = ((st + ks * 256) >> 4) | lbo_word, alw = ((st + kWgATile + ks * 256) >> 4) | lbo_word;
+                        const uint32_t bw = ((st + kWgXBase + kx * kWgXCopy + (2 * ks + ky) * 128) >> 4) | lbo_word;
+                        umma_f16(tmem + kx * 128, hi_a | aw, hi_b | bw, idesc, (ip > 0 || ks > 0) ? 1u : 0u);
+                        umma_f16(tmem + kx * 128, hi_a | alw, hi_b | bw, idesc, 1u);
+                    }
                 }
             }
             umma_commit(bar_empty + 8 * stage);

@@ -148,3 +148,41 @@ def test_canon_exp_and_sampler_choice(cref, rollout_weights):
     W, b = rollout_weights
     assert cref.policy_is_fast(W, b)
     assert not cref.policy_is_fast(W * 40, b) and not cref.policy_is_fast(W * np.float32("nan"), b)
+
+
+def test_two_sided_cdf_is_numpy_choice(cref, rollout_weights):
+    """The canonical sampling rule (running sums over the legal cells 0..31 ascending and 63..32 descending, see the header of
+    oracle/othello_ref.c) is, in exact arithmetic, np.random.choice's searchsorted(cdf, u, 'right') over the masked, renormalised
+    softmax (mcts_self_play.py:100-110).  Checked against a float64 numpy restatement of that line on random boards, built from the
+    fp32 logits: the picks agree everywhere except where u sits within 2e-6 of a cdf edge (rounding the logit sum to fp32, which the
+    canonical weights E0 * E1 * EB do not do, moves an edge by up to ~1e-7 * |logit|; probes 1e-5 either side of the edges are included)."""
+    W, b = rollout_weights
+    rng = np.random.default_rng(5)
+    checked = near = 0
+    for trial in range(4000):
+        fill = rng.random()
+        r = rng.random(64)
+        st = np.where(r < fill * 0.5, 1, np.where(r < fill, 2, 0)).astype(np.float32)
+        color = int(rng.integers(1, 3))
+        acts = cref.legal_actions(st, color)
+        if len(acts) < 2:
+            continue
+        logits = np.asarray(cref.rollout_logits(st, color, W, b), np.float64).reshape(64)
+        p = np.exp(logits - logits.max())
+        mask = np.zeros(64)
+        mask[acts] = 1.0
+        p = p * mask
+        cdf = np.cumsum(p)
+        cdf /= cdf[-1]
+        us = np.concatenate([rng.random(6), [0.0, 1 - 2.0**-53], cdf[acts[:-1]][:3] + 1e-5, cdf[acts[:-1]][:3] - 1e-5])
+        for u in us:
+            if not 0.0 <= u < 1.0:
+                continue
+            want = int(np.searchsorted(cdf, u, side="right"))
+            got = cref.rollout_sample(st, color, W, b, float(u))
+            if np.min(np.abs(cdf[acts] - u)) < 2e-6:
+                near += 1
+                continue
+            checked += 1
+            assert got == want, (trial, u, got, want)
+    assert checked > 30000 and near < checked // 5   # (edges of cells with probability below 1e-5 crowd each other)

@@ -111,7 +111,7 @@ def cpu_port_throughput(n_games, threads=0, seed=777):
     return plies / dt, int(r["threads"]), plies, dt
 
 
-def python_reference_throughput(n_games=12):
+def python_reference_throughput(n_games=12, procs=1):
     """The UNMODIFIED reference Simulate (baseline/_ref copies) under the chainer stand-in, one process, one core."""
     ref = os.path.join(ROOT, "baseline", "_ref")
     if not os.path.isfile(os.path.join(ref, "mcts_self_play.py")):
@@ -135,8 +135,17 @@ print(json.dumps({{"plies_per_s": plies / dt, "games": {n_games}, "seconds": dt}
 """
     env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1")
     try:
-        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
-        return json.loads(res.stdout.strip().splitlines()[-1])
+        if procs <= 1:
+            res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, env=env)
+            return json.loads(res.stdout.strip().splitlines()[-1])
+        # the same script fanned out over all host cores, one process per core (the reference itself is single-process);
+        # rate = plies of all processes / the longest process's own timed region (interpreter start-up excluded, as above)
+        ps = [subprocess.Popen([sys.executable, "-c", code.replace("np.random.seed(1)", f"np.random.seed({1 + i})")],
+                               stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env) for i in range(procs)]
+        outs = [json.loads(p_.communicate(timeout=600)[0].strip().splitlines()[-1]) for p_ in ps]
+        secs = max(o["seconds"] for o in outs)
+        plies = sum(o["plies_per_s"] * o["seconds"] for o in outs)
+        return {"plies_per_s": plies / secs, "games": n_games * procs, "seconds": secs, "cores": procs}
     except Exception as e:
         return {"error": repr(e)[:200]}
 
@@ -202,6 +211,10 @@ def cpu_baseline_block(budget_s=12.0):
     if py:
         out["python_reference"] = dict(py, cores=1, note="unmodified reference mcts_self_play.Simulate under the numpy "
                                        "chainer stand-in (Chainer itself is not installable)")
+        cores = os.cpu_count() or 1
+        if cores > 1 and "error" not in py:
+            out["python_reference_all_cores"] = dict(python_reference_throughput(12, procs=cores),
+                                                     note="the same, one process per host core running side by side")
     return out
 
 

@@ -30,6 +30,7 @@
 //     (numpy scalar rules: P is float32 unless it is the literal 1.1; Q is float32 when lambda < 1, float64 when
 //     lambda >= 1; U is float64), which is what the parity tests pin against the reference's own trees.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -707,7 +708,7 @@ struct iago_mcts {
     int last_exact = 1;
     long long overflows = 0;
     cudaStream_t side = nullptr;            // the lockstep rollouts of a wave run here, beside the value-net launch
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_in = nullptr;
 };
 
 template <class T_>
@@ -769,6 +770,7 @@ int iago_mcts_destroy(iago_mcts *m) {
     if (m->side) cudaStreamDestroy(m->side);
     if (m->ev_fork) cudaEventDestroy(m->ev_fork);
     if (m->ev_join) cudaEventDestroy(m->ev_join);
+    if (m->ev_in) cudaEventDestroy(m->ev_in);
     delete m;
     return IAGO_OK;
 }
@@ -840,18 +842,21 @@ int iago_mcts_search(iago_mcts *m, const iago_mcts_params *pp, void *stream) {
     const long long S = (long long)T * p.B;
     const int waves = (int)((pp->n_playouts + p.B - 1) / p.B);
     const bool run_v = p.need_v && !d.forced_v, run_z = p.need_z && !d.forced_z;
-    IAGO_CUDA(cudaMemsetAsync(d.counts, 0, 8 * sizeof(int), s));
-    for (int w = 0; w < waves; w++) {
-        IAGO_CUDA(cudaMemsetAsync(d.counts, 0, 2 * sizeof(int), s));
+    // One wave = the kernel sequence of the file header.  Everything a wave needs lives on the device (request counts, playout
+    // counters), so the waves of a search are identical launches: the first one runs directly, the second is captured into a CUDA
+    // graph and replayed for the rest — a single-tree search is bound by dependent launches, not by work.  The legacy default stream
+    // cannot be captured, so the search runs on the context's own stream, ordered behind the caller's stream by an event.
+    auto wave = [&](cudaStream_t ws) -> int {
+        IAGO_CUDA(cudaMemsetAsync(d.counts, 0, 2 * sizeof(int), ws));
         const bool pipe = !p.exact && p.B >= 8 && p.B <= kPipeMaxB;   // descents of a tree as a software pipeline over 8 warps
-        if (pipe) mcts_select_pipe_kernel<<<m->T, kPipeWarps * 32, 0, s>>>(d, p, 1);
-        else mcts_select_kernel<<<m->T, 32, 0, s>>>(d, p, 1);
+        if (pipe) mcts_select_pipe_kernel<<<m->T, kPipeWarps * 32, 0, ws>>>(d, p, 1);
+        else mcts_select_kernel<<<m->T, 32, 0, ws>>>(d, p, 1);
         IAGO_CUDA(cudaGetLastError());
-        int rc = trunk_launch(ctx, pp->slot_policy, 0, (const uint64_t *)d.pol_p1, (const uint64_t *)d.pol_p2, d.pol_color, S, d.probs, 1, pp->precision, s, d.counts + 0);
+        int rc = trunk_launch(ctx, pp->slot_policy, 0, (const uint64_t *)d.pol_p1, (const uint64_t *)d.pol_p2, d.pol_color, S, d.probs, 1, pp->precision, ws, d.counts + 0);
         if (rc) return rc;
-        mcts_expand_kernel<<<(unsigned)((S + 127) / 128), 128, 0, s>>>(d);
-        if (pipe) mcts_select_pipe_kernel<<<m->T, kPipeWarps * 32, 0, s>>>(d, p, 2);
-        else mcts_select_kernel<<<m->T, 32, 0, s>>>(d, p, 2);
+        mcts_expand_kernel<<<(unsigned)((S + 127) / 128), 128, 0, ws>>>(d);
+        if (pipe) mcts_select_pipe_kernel<<<m->T, kPipeWarps * 32, 0, ws>>>(d, p, 2);
+        else mcts_select_kernel<<<m->T, 32, 0, ws>>>(d, p, 2);
         IAGO_CUDA(cudaGetLastError());
         // value net and rollouts read the same leaves and write different outputs: the rollouts go to a second stream
         const bool fork = run_v && run_z;
@@ -861,31 +866,65 @@ int iago_mcts_search(iago_mcts *m, const iago_mcts_params *pp, void *stream) {
                 IAGO_CUDA(cudaEventCreateWithFlags(&m->ev_fork, cudaEventDisableTiming));
                 IAGO_CUDA(cudaEventCreateWithFlags(&m->ev_join, cudaEventDisableTiming));
             }
-            IAGO_CUDA(cudaEventRecord(m->ev_fork, s));
+            IAGO_CUDA(cudaEventRecord(m->ev_fork, ws));
             IAGO_CUDA(cudaStreamWaitEvent(m->side, m->ev_fork, 0));
         }
         if (run_z) {
             rc = rollout_launch_ids(ctx, (const uint64_t *)d.leaf_p1, (const uint64_t *)d.leaf_p2, d.leaf_color, S, pp->seed, 2u,
-                                    (const uint64_t *)d.game_ids, d.z, nullptr, nullptr, fork ? m->side : s);
+                                    (const uint64_t *)d.game_ids, d.z, nullptr, nullptr, fork ? m->side : ws);
             if (rc) return rc;
             if (fork) IAGO_CUDA(cudaEventRecord(m->ev_join, m->side));
         }
         if (run_v) {
-            rc = trunk_launch(ctx, pp->slot_value, 1, (const uint64_t *)d.val_p1, (const uint64_t *)d.val_p2, d.val_color, S, d.vals, 0, pp->precision, s, d.counts + 1);
+            rc = trunk_launch(ctx, pp->slot_value, 1, (const uint64_t *)d.val_p1, (const uint64_t *)d.val_p2, d.val_color, S, d.vals, 0, pp->precision, ws, d.counts + 1);
             if (rc) return rc;
-            mcts_scatter_value_kernel<<<(unsigned)((S + 127) / 128), 128, 0, s>>>(d, p.cache_v);
+            mcts_scatter_value_kernel<<<(unsigned)((S + 127) / 128), 128, 0, ws>>>(d, p.cache_v);
         }
-        if (fork) IAGO_CUDA(cudaStreamWaitEvent(s, m->ev_join, 0));
+        if (fork) IAGO_CUDA(cudaStreamWaitEvent(ws, m->ev_join, 0));
         if (p.exact) {
-            mcts_backup_exact_kernel<<<(m->T + 63) / 64, 64, 0, s>>>(d, p);
+            mcts_backup_exact_kernel<<<(m->T + 63) / 64, 64, 0, ws>>>(d, p);
         } else {
-            mcts_backup_atomic_kernel<<<(unsigned)((S + 127) / 128), 128, 0, s>>>(d, p);
-            mcts_advance_done_kernel<<<(m->T + 127) / 128, 128, 0, s>>>(d, p);
+            mcts_backup_atomic_kernel<<<(unsigned)((S + 127) / 128), 128, 0, ws>>>(d, p);
+            mcts_advance_done_kernel<<<(m->T + 127) / 128, 128, 0, ws>>>(d, p);
         }
         IAGO_CUDA(cudaGetLastError());
+        return IAGO_OK;
+    };
+    cudaStream_t ws = s;
+    const bool use_graph = waves > 2 && !getenv("IAGO_MCTS_NO_GRAPH");
+    if (use_graph && ctx->stream != s) {
+        if (!m->ev_in) IAGO_CUDA(cudaEventCreateWithFlags(&m->ev_in, cudaEventDisableTiming));
+        IAGO_CUDA(cudaEventRecord(m->ev_in, s));
+        ws = ctx->stream;
+        IAGO_CUDA(cudaStreamWaitEvent(ws, m->ev_in, 0));
     }
-    IAGO_CUDA(cudaMemcpyAsync(m->h_counts, d.counts, 8 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    IAGO_CUDA(cudaStreamSynchronize(s));
+    IAGO_CUDA(cudaMemsetAsync(d.counts, 0, 8 * sizeof(int), ws));
+    int w0 = 0;
+    if (use_graph) {
+        int rc = wave(ws);   // also sets function attributes and creates the side stream: nothing of that kind happens under capture
+        if (rc) return rc;
+        w0 = 1;
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        if (cudaStreamBeginCapture(ws, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            rc = wave(ws);
+            const cudaError_t e = cudaStreamEndCapture(ws, &graph);
+            if (rc == IAGO_OK && e == cudaSuccess && graph && cudaGraphInstantiate(&exec, graph, 0) == cudaSuccess) {
+                for (; w0 < waves; w0++) {
+                    if (cudaGraphLaunch(exec, ws) != cudaSuccess) break;
+                }
+            }
+            if (exec) cudaGraphExecDestroy(exec);
+            if (graph) cudaGraphDestroy(graph);
+        }
+        cudaGetLastError();   // a failed capture falls back to direct launches for the remaining waves
+    }
+    for (; w0 < waves; w0++) {
+        int rc = wave(ws);
+        if (rc) return rc;
+    }
+    IAGO_CUDA(cudaMemcpyAsync(m->h_counts, d.counts, 8 * sizeof(int), cudaMemcpyDeviceToHost, ws));
+    IAGO_CUDA(cudaStreamSynchronize(ws));
     m->overflows = m->h_counts[2];
     return IAGO_OK;
 }

@@ -620,11 +620,16 @@ int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, con
     TrunkArgs a{(const u64 *)p1, (const u64 *)p2, color, n, out, out_kind, precision, s.d_blob, s.d_bias, s.d_head, n_dev, {}, nullptr, {}};
     for (int l = 0; l < 8; l++) a.dump[l] = dump ? dump[l] : nullptr;
     cudaStream_t cs = (cudaStream_t)stream;
-    IAGO_CUDA(cudaEventRecord(ctx->ev0, cs));
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(cs, &cap);
+    const bool timed = cap == cudaStreamCaptureStatusNone;   // the timing events of iago_last_kernel_ms stay out of captured graphs (mcts.cu)
+    if (timed) IAGO_CUDA(cudaEventRecord(ctx->ev0, cs));
     trunk_kernel<0><<<grid, kThreads, kSmemBytes, cs>>>(a, s.d_desc);
     IAGO_CUDA(cudaGetLastError());
-    IAGO_CUDA(cudaEventRecord(ctx->ev1, cs));
-    ctx->timed = true;
+    if (timed) {
+        IAGO_CUDA(cudaEventRecord(ctx->ev1, cs));
+        ctx->timed = true;
+    }
     return IAGO_OK;
 }
 

@@ -795,7 +795,7 @@ int iago_mcts_search(iago_mcts *m, const iago_mcts_params *pp, void *stream) {
     IAGO_REQUIRE(m && pp, "NULL argument");
     IAGO_REQUIRE(pp->leaf_batch >= 1 && pp->leaf_batch <= m->Bmax, "leaf_batch out of range (1..max_leaf_batch)");
     IAGO_REQUIRE(pp->n_playouts >= 0 && pp->n_thr >= 1, "n_playouts >= 0 and n_thr >= 1 required");
-    IAGO_REQUIRE(pp->precision == 1 || pp->precision == 3, "precision must be 1 or 3");
+    IAGO_REQUIRE(pp->precision >= 1 && pp->precision <= 3, "precision must be 1, 2 or 3");
     iago_ctx *ctx = m->ctx;
     DeviceGuard guard(ctx->device);
     cudaStream_t s = (cudaStream_t)stream;

@@ -21,11 +21,16 @@
 //   * Precision: fp16 operands, fp32 accumulate.  precision=3 splits both operands into hi + lo fp16 parts and
 //     issues three MMAs per step (hi*hi + lo*hi + hi*lo), which recovers ~fp32 accuracy (max-abs logit error
 //     ~1e-4 on sl_model.npz); precision=1 is the single-pass fp16 path (max-abs ~0.1).  SURVEY.md §0.5.
+//     precision=2 keeps hi*hi in fp16 and computes the two cross terms, which are 2^-11 of the product, in FP8 (E4M3, kind::f8f6f4,
+//     twice the fp16 rate): cross = fp8(a_lo * 2^11) * fp8(w_hi * sw) + fp8(a_hi) * fp8(w_lo * 2^11 * sw) into a second TMEM
+//     accumulator that the epilogue folds in with the factor 1 / (2^11 * sw) (sw = a power of two per layer from max|w|).  Two MMA
+//     units per K step instead of three; max-abs logit error ~3e-3 on sl_model.npz (north-star bar 1e-2), arg-max unchanged.
 //   * Heads: policy = per-row dot with conv9 (fp32, CUDA cores) in the layer-8 epilogue (+bias10, optional
 //     softmax); value = block9 as a ninth MMA layer with N padded to 16, then relu and the collapsed
 //     fc11*fc10 64-vector.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <cuda_fp8.h>
 #include <string.h>
 
 #include <vector>
@@ -35,6 +40,14 @@
 #include "tc.cuh"
 
 namespace iago {
+
+#ifdef IAGO_TRUNK_TRACE
+// debug build only (tools/trace_trunk.py): SM clock at the pipeline's hand-over points of CTA 0, first tiles
+__device__ unsigned long long g_trace[4096];
+#define TRACE(tile_, l_, ev_) do { if (blockIdx.x == 0 && (tile_) < 4 * (long long)gridDim.x) g_trace[(((tile_) / gridDim.x) * 9 + (l_)) * 8 + (ev_)] = clock64(); } while (0)
+#else
+#define TRACE(tile_, l_, ev_) do { } while (0)
+#endif
 
 // ---------------------------------------------------------------- geometry
 constexpr int kTileRows = 128;                    // M of the MMA = 2 boards
@@ -47,7 +60,9 @@ constexpr int kStages = 3;
 constexpr int kMaxLayers = 9;
 constexpr int kEpiThreads = 256;                  // warps 0-7
 constexpr int kThreads = 320;                     // + warp 8 producer, warp 9 MMA issuer
-constexpr int kTmemCols = 256;                    // two 128-column fp32 accumulators
+constexpr int kTmemCols = 512;                    // two 128-column fp32 accumulators + two for the FP8 cross terms (precision 2)
+constexpr int kCrossCol = 256;                    // first TMEM column of the cross-term accumulators
+constexpr int kA8Bytes = 8 * kGroupBytes;         // an FP8 activation tile: 8 groups of 16 channels = 25,600 B; A8 | AL8 share OFF_ALO
 
 constexpr int OFF_AHI = 0;
 constexpr int OFF_ALO = OFF_AHI + kActBytes;
@@ -67,6 +82,7 @@ struct LayerDesc {
     int lo_off;      // byte offset of the lo block inside a unit
     int b_lbo;       // B operand: bytes between K-adjacent core matrices (= n * 16)
     int chunks;      // 64-channel chunks per tap (1 or 2); 0 for the explicit layer 1
+    float cscale;    // precision 2: factor that folds the FP8 cross-term accumulator into the output, 1 / (2^11 * sw)
 };
 
 struct NetDesc {
@@ -82,7 +98,7 @@ struct TrunkArgs {
     long long n;          // positions
     float *out;           // policy: [n][64]; value: [n]
     int out_kind;         // policy: 0 = logits, 1 = softmax probabilities
-    int precision;        // 1 = fp16 single pass, 3 = hi/lo split (3 MMAs)
+    int precision;        // 1 = fp16 single pass, 3 = hi/lo split (3 MMAs), 2 = fp16 + FP8 cross terms (blob = the slot's second blob)
     const uint8_t *blob;  // packed weight units
     const float *bias;    // [n_layers][128]
     const float *head;    // policy: w9[128], b10[64]; value: b9 at [0], wfc[64] at [128..192)
@@ -120,6 +136,34 @@ __device__ __forceinline__ void store_act32(uint8_t *smem, const float (&x)[32],
         const uint32_t off = group0_off + (uint32_t)q * kGroupBytes;
         *reinterpret_cast<uint4 *>(smem + OFF_AHI + off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
         if (split) *reinterpret_cast<uint4 *>(smem + OFF_ALO + off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+    }
+}
+
+// precision 2: 32 values of this thread's tile row -> fp16 hi parts (4 groups of 8 channels) and two FP8 tiles (2 groups of 16
+// channels each): A8 = e4m3(hi), AL8 = e4m3((x - hi) * 2^11).
+__device__ __forceinline__ void store_act32_p2(uint8_t *smem, const float (&x)[32], int col0, uint32_t row_off) {
+    uint32_t h8[8], l8[8];   // 32 FP8 values each
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        uint32_t hw[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float f0 = x[q * 8 + 2 * e], f1 = x[q * 8 + 2 * e + 1];
+            const __half2 h = __floats2half2_rn(f0, f1);
+            const float2 hf = __half22float2(h);
+            hw[e] = *reinterpret_cast<const uint32_t *>(&h);
+            const uint32_t a8 = __nv_cvt_float2_to_fp8x2(hf, __NV_SATFINITE, __NV_E4M3);
+            const uint32_t b8 = __nv_cvt_float2_to_fp8x2(make_float2((f0 - hf.x) * 2048.0f, (f1 - hf.y) * 2048.0f), __NV_SATFINITE, __NV_E4M3);
+            const int w = q * 2 + (e >> 1), sh = (e & 1) * 16;
+            if (sh == 0) { h8[w] = a8; l8[w] = b8; } else { h8[w] |= a8 << 16; l8[w] |= b8 << 16; }
+        }
+        *reinterpret_cast<uint4 *>(smem + OFF_AHI + (uint32_t)((col0 >> 3) + q) * kGroupBytes + row_off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const uint32_t off = (uint32_t)((col0 >> 4) + q) * kGroupBytes + row_off;
+        *reinterpret_cast<uint4 *>(smem + OFF_ALO + off) = make_uint4(h8[4 * q], h8[4 * q + 1], h8[4 * q + 2], h8[4 * q + 3]);
+        *reinterpret_cast<uint4 *>(smem + OFF_ALO + kA8Bytes + off) = make_uint4(l8[4 * q], l8[4 * q + 1], l8[4 * q + 2], l8[4 * q + 3]);
     }
 }
 
@@ -183,6 +227,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
     const long long n_tiles = (n_pos + 1) / 2;
     const int L = net.n_layers;
     const bool split = a.precision >= 3;
+    const bool p2 = MODE == 0 && a.precision == 2;   // fp16 main product + FP8 cross terms in the second accumulator
 
     if (warp == 8) {
         // ================= producer: stream weight units L2 -> smem ring =================
@@ -192,7 +237,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                 for (int l = 0; l < L; l++) {
                     const LayerDesc ld = net.layer[l];
                     const uint8_t *src = a.blob + net.unit_base[l];
-                    const uint32_t bytes = split ? (uint32_t)ld.unit_bytes : (uint32_t)ld.lo_off;  // single pass needs hi only
+                    const uint32_t bytes = (split || p2) ? (uint32_t)ld.unit_bytes : (uint32_t)ld.lo_off;  // single pass needs hi only
                     for (int u = 0; u < ld.n_units; u++) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         mbar_expect_tx(bar_full + 8 * stage, bytes);
@@ -216,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                     const uint32_t d_tmem = tmem + (uint32_t)(l & 1) * 128u;
                     const uint32_t b_step = (uint32_t)(2 * ld.b_lbo) >> 4;              // descriptor units (16 B) per K=16 step
                     const uint32_t b_lo_word = ((uint32_t)(ld.b_lbo >> 4) << 16);
-                    uint32_t acc = 0;
+                    uint32_t acc = 0, acc_x = 0;
                     if (MODE == 0 && ld.chunks == 0) {
                         // layer 1: explicit im2col tile [4][128][16 B], LBO = 2048, SBO = 128
                         mbar_wait(bar_a1, a1_phase);
@@ -230,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                         for (int ks = 0; ks < ld.ksteps; ks++) {
                             umma_f16(d_tmem, a1_hi | aw, desc_hi_b | bw, idesc, acc);
                             acc = 1;
-                            if (split) umma_f16(d_tmem, a1_hi | aw, desc_hi_b | blw, idesc, 1);  // inputs are exactly 0/1: no lo part
+                            if (split || p2) umma_f16(d_tmem, a1_hi | aw, desc_hi_b | blw, idesc, 1);  // inputs are exactly 0/1: no lo part
                             aw += (2 * kTileRows * 16) >> 4; bw += b_step; blw += b_step;
                         }
                         umma_commit(bar_empty + 8 * stage);
@@ -241,6 +286,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                             mbar_wait(bar_act + 8 * chunk, act_phase[chunk]);  // these 64 input channels are written
                             act_phase[chunk] ^= 1;
                             tc_fence_after();
+                            TRACE(tile, l, chunk);
                             const uint32_t a_chunk = (uint32_t)chunk * 8 * kGroupBytes;
 #pragma unroll 1
                             for (int tap = 0; tap < 9; tap++) {
@@ -261,12 +307,27 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                                     }
                                     ahw += (2 * kGroupBytes) >> 4; alw += (2 * kGroupBytes) >> 4; bw += b_step; blw += b_step;
                                 }
+                                if (p2) {
+                                    // FP8 tiles: 16 channels per 16-byte row, so a 64-channel chunk is 4 groups and one K = 32 MMA spans two
+                                    // of them — the same descriptor stepping as fp16.  Weights: W8 = e4m3(w_hi * sw) at lo_off, WL8 after it.
+                                    const uint32_t off8 = (uint32_t)chunk * 4 * kGroupBytes + (uint32_t)(ky * 20 + kx) * 16;
+                                    uint32_t a8w = ((sbase + OFF_ALO + off8) >> 4) | a_lo_word, al8w = ((sbase + OFF_ALO + kA8Bytes + off8) >> 4) | a_lo_word;
+                                    uint32_t w8w = ((bst + ld.lo_off) >> 4) | b_lo_word, wl8w = ((bst + ld.lo_off + (ld.lo_off >> 1)) >> 4) | b_lo_word;
+#pragma unroll
+                                    for (int ks = 0; ks < 2; ks++) {
+                                        umma_f8(d_tmem + kCrossCol, desc_hi_a | al8w, desc_hi_b | w8w, idesc, acc_x);
+                                        acc_x = 1;
+                                        umma_f8(d_tmem + kCrossCol, desc_hi_a | a8w, desc_hi_b | wl8w, idesc, 1);
+                                        a8w += (2 * kGroupBytes) >> 4; al8w += (2 * kGroupBytes) >> 4; w8w += b_step; wl8w += b_step;
+                                    }
+                                }
                                 umma_commit(bar_empty + 8 * stage);  // frees the weight stage when these MMAs retire
                                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
                         }
                     }
                     umma_commit(bar_acc + 8 * (l & 1));  // accumulator of this layer complete
+                    TRACE(tile, l, 2);
                 }
             }
         }
@@ -339,6 +400,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                 mbar_wait(bar_acc + 8 * (l & 1), acc_phase[l & 1]);
                 acc_phase[l & 1] ^= 1;
                 tc_fence_after();
+                if (tid == 0) TRACE(tile, l, 3);
                 const uint32_t t_addr = lane_addr + (uint32_t)(l & 1) * 128u;
                 const bool policy_head = (l == 7 && net.kind == 0);
                 const bool writes_act = (l + 1 < L);
@@ -378,8 +440,16 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                         tmem_ld32(t_addr + col0, v);
                         tmem_wait_ld();
                         float x[32];
+                        if (p2 && l > 0) {   // fold the FP8 cross-term accumulator in (layer 1 has none: its inputs are exactly 0 / 1)
+                            uint32_t vx[32];
+                            tmem_ld32(t_addr + kCrossCol + col0, vx);
+                            tmem_wait_ld();
 #pragma unroll
-                        for (int j = 0; j < 32; j++) x[j] = fmaxf(__uint_as_float(v[j]) + sbias[l * 128 + col0 + j], 0.0f);
+                            for (int j = 0; j < 32; j++) x[j] = fmaxf(fmaf(__uint_as_float(vx[j]), ld.cscale, __uint_as_float(v[j])) + sbias[l * 128 + col0 + j], 0.0f);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; j++) x[j] = fmaxf(__uint_as_float(v[j]) + sbias[l * 128 + col0 + j], 0.0f);
+                        }
                         if (policy_head) {
 #pragma unroll
                             for (int j = 0; j < 32; j++) dot = fmaf(x[j], shead[col0 + j], dot);
@@ -390,10 +460,12 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                             for (int j = 0; j < 32; j++) dst[(size_t)j * 64] = x[j];
                         }
                         if (writes_act) {
-                            store_act32<false>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
+                            if (p2) store_act32_p2(smem, x, col0, row_off);
+                            else store_act32<false>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
                             fence_async_smem();
                             tc_fence_before();
                             mbar_arrive(bar_act + 8 * ps);  // input channels [64*ps, 64*ps+64) of the next layer are in place
+                            if (tid == 0) TRACE(tile, l, 4 + ps);
                         }
                     }
                     if (policy_head) {
@@ -420,10 +492,11 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                 } else {
                     // value head: relu(block9 + b9) . (fc11 * fc10)  (network.py:92-95, dropout off)
                     if (half == 0) {
-                        uint32_t v;
+                        uint32_t v, vx = 0;
                         tmem_ld1(t_addr, v);
+                        if (p2) tmem_ld1(t_addr + kCrossCol, vx);
                         tmem_wait_ld();
-                        const float h = fmaxf(__uint_as_float(v) + shead[0], 0.0f);
+                        const float h = fmaxf(fmaf(__uint_as_float(vx), p2 ? ld.cscale : 0.0f, __uint_as_float(v)) + shead[0], 0.0f);
                         scratch[b * 64 + cell] = h * shead[128 + cell];
                         asm volatile("bar.sync 2, 128;" ::: "memory");
                         if (warp < 2) {
@@ -454,6 +527,7 @@ struct NetSlot {
     NetDesc desc;
     NetDesc *d_desc = nullptr;
     uint8_t *d_blob = nullptr;
+    uint8_t *d_blob2 = nullptr;   // precision 2: fp16 hi block | W8 | WL8 per unit (nullptr after a device-side refresh: precision 2 then runs as 3)
     float *d_bias = nullptr;
     float *d_head = nullptr;
 };
@@ -480,6 +554,7 @@ void trunk_destroy(iago_ctx *ctx) {
     for (auto &s : st->slot) {
         cudaFree(s.d_desc);
         cudaFree(s.d_blob);
+        cudaFree(s.d_blob2);
         cudaFree(s.d_bias);
         cudaFree(s.d_head);
     }
@@ -508,9 +583,45 @@ static void pack_unit(std::vector<uint8_t> &blob, int kgroups, int n_pad, F get)
             for (int e = 0; e < 8; e++) split_half(get(n, kg * 8 + e), hi[((size_t)kg * n_pad + n) * 8 + e], lo[((size_t)kg * n_pad + n) * 8 + e]);
 }
 
+// Precision-2 unit: the same fp16 hi block, then W8 = e4m3(w_hi * sw) and WL8 = e4m3(w_lo * 2^11 * sw), both [kgroups / 2][n_pad][16]
+// (16 reduction indices per 16-byte row), each half the size of the hi block.  w_hi / w_lo are the fp16 parts of pack_unit.
+template <class F>
+static void pack_unit_p2(std::vector<uint8_t> &blob, int kgroups, int n_pad, float sw, F get) {
+    const size_t half_elems = (size_t)kgroups * n_pad * 8;
+    const size_t base = blob.size();
+    blob.resize(base + half_elems * 4);
+    uint16_t *hi = reinterpret_cast<uint16_t *>(blob.data() + base);
+    uint8_t *w8 = blob.data() + base + half_elems * 2, *wl8 = w8 + half_elems;
+    for (int kg = 0; kg < kgroups; kg++)
+        for (int n = 0; n < n_pad; n++)
+            for (int e = 0; e < 8; e++) {
+                uint16_t h, l;
+                split_half(get(n, kg * 8 + e), h, l);
+                hi[((size_t)kg * n_pad + n) * 8 + e] = h;
+                const int k = kg * 8 + e;
+                const size_t o8 = ((size_t)(k >> 4) * n_pad + n) * 16 + (k & 15);
+                w8[o8] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(__ushort_as_half(h)) * sw, __NV_SATFINITE, __NV_E4M3);
+                wl8[o8] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(__ushort_as_half(l)) * 2048.0f * sw, __NV_SATFINITE, __NV_E4M3);
+            }
+}
+
+// sw: the power of two that brings the layer's largest |weight| into [128, 256) (E4M3 tops out at 448)
+static float fp8_weight_scale(const float *w, size_t count) {
+    float mx = 0.0f;
+    for (size_t i = 0; i < count; i++) mx = fmaxf(mx, fabsf(w[i]));
+    if (!(mx > 0.0f) || !isfinite(mx)) return 1.0f;
+    return ldexpf(1.0f, 7 - ilogbf(mx));
+}
+
 }  // namespace iago
 
 using namespace iago;
+
+#ifdef IAGO_TRUNK_TRACE
+extern "C" __attribute__((visibility("default"))) int iago_debug_trace(unsigned long long *out, int n) {
+    return (int)cudaMemcpyFromSymbol(out, g_trace, (size_t)n * 8);
+}
+#endif
 
 extern "C" {
 
@@ -532,7 +643,7 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
     memset(&d, 0, sizeof d);
     d.kind = kind;
     d.n_layers = kind == 0 ? 8 : 9;
-    std::vector<uint8_t> blob;
+    std::vector<uint8_t> blob, blob2;
     std::vector<float> bias((size_t)kMaxLayers * 128, 0.0f), head(256, 0.0f);
     const float *p = params;
     for (int l = 0; l < 8; l++) {
@@ -547,12 +658,18 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
             // explicit im2col: k = tap*2 + channel, K padded 18 -> 32
             ld.n_units = 1; ld.ksteps = 2; ld.chunks = 0;
             pack_unit(blob, 4, ld.n, [&](int n, int k) { return k < 18 ? W[((size_t)n * 2 + (k & 1)) * 9 + (k >> 1)] : 0.0f; });
+            pack_unit(blob2, 4, ld.n, [&](int n, int k) { return k < 18 ? W[((size_t)n * 2 + (k & 1)) * 9 + (k >> 1)] : 0.0f; });  // layer 1: fp16 hi / lo in both blobs
+            ld.cscale = 0.0f;
             ld.lo_off = 4 * ld.n * 16;
         } else {
             ld.chunks = cin[l] / 64; ld.n_units = 9 * ld.chunks; ld.ksteps = 4;
+            const float sw = fp8_weight_scale(W, (size_t)cout[l] * cin[l] * 9);
+            ld.cscale = 1.0f / (2048.0f * sw);
             for (int ch = 0; ch < ld.chunks; ch++)  // chunk-major: all taps of input channels 0..63 first
-                for (int tap = 0; tap < 9; tap++)
+                for (int tap = 0; tap < 9; tap++) {
                     pack_unit(blob, 8, ld.n, [&](int n, int k) { return W[((size_t)n * cin[l] + ch * 64 + k) * 9 + tap]; });
+                    pack_unit_p2(blob2, 8, ld.n, sw, [&](int n, int k) { return W[((size_t)n * cin[l] + ch * 64 + k) * 9 + tap]; });
+                }
             ld.lo_off = 8 * ld.n * 16;
         }
         ld.unit_bytes = 2 * ld.lo_off;
@@ -565,9 +682,13 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
         LayerDesc &ld = d.layer[8];
         d.unit_base[8] = (long long)blob.size();
         ld.n = 16; ld.b_lbo = 16 * 16; ld.chunks = 2; ld.n_units = 18; ld.ksteps = 4;
+        const float sw9 = fp8_weight_scale(W9, 1152);
+        ld.cscale = 1.0f / (2048.0f * sw9);
         for (int ch = 0; ch < 2; ch++)
-            for (int tap = 0; tap < 9; tap++)
+            for (int tap = 0; tap < 9; tap++) {
                 pack_unit(blob, 8, 16, [&](int n, int k) { return n == 0 ? W9[(size_t)(ch * 64 + k) * 9 + tap] : 0.0f; });
+                pack_unit_p2(blob2, 8, 16, sw9, [&](int n, int k) { return n == 0 ? W9[(size_t)(ch * 64 + k) * 9 + tap] : 0.0f; });
+            }
         ld.lo_off = 8 * 16 * 16;
         ld.unit_bytes = 2 * ld.lo_off;
         head[0] = b9[0];
@@ -578,10 +699,16 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
             head[128 + j] = (float)acc;
         }
     }
-    cudaFree(s.d_desc); cudaFree(s.d_blob); cudaFree(s.d_bias); cudaFree(s.d_head);
+    if (blob2.size() != blob.size()) {
+        set_error("iago_load_net: internal error, the two weight blobs differ in size");
+        return IAGO_E_STATE;
+    }
+    cudaFree(s.d_desc); cudaFree(s.d_blob); cudaFree(s.d_blob2); cudaFree(s.d_bias); cudaFree(s.d_head);
     s = NetSlot();
     IAGO_CUDA(cudaMalloc(&s.d_desc, sizeof(NetDesc)));
     IAGO_CUDA(cudaMalloc(&s.d_blob, blob.size()));
+    IAGO_CUDA(cudaMalloc(&s.d_blob2, blob2.size()));
+    IAGO_CUDA(cudaMemcpy(s.d_blob2, blob2.data(), blob2.size(), cudaMemcpyHostToDevice));
     IAGO_CUDA(cudaMalloc(&s.d_bias, bias.size() * 4));
     IAGO_CUDA(cudaMalloc(&s.d_head, head.size() * 4));
     IAGO_CUDA(cudaMemcpy(s.d_desc, &d, sizeof d, cudaMemcpyHostToDevice));
@@ -601,7 +728,7 @@ int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, con
     IAGO_REQUIRE(ctx && p1 && p2 && color && out, "NULL argument");
     IAGO_REQUIRE(slot >= 0 && slot < 8, "slot out of range (0..7)");
     IAGO_REQUIRE(n >= 0, "n < 0");
-    IAGO_REQUIRE(precision == 1 || precision == 3, "precision must be 1 (fp16) or 3 (hi/lo split)");
+    IAGO_REQUIRE(precision >= 1 && precision <= 3, "precision must be 1 (fp16), 2 (fp16 + FP8 cross terms) or 3 (fp16 hi/lo split)");
     TrunkState *st = state(ctx);
     NetSlot &s = st->slot[slot];
     if (!s.loaded || s.desc.kind != want_kind) {
@@ -617,7 +744,8 @@ int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, con
     }
     const long long tiles = (n + 1) / 2;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    TrunkArgs a{(const u64 *)p1, (const u64 *)p2, color, n, out, out_kind, precision, s.d_blob, s.d_bias, s.d_head, n_dev, {}, nullptr, {}};
+    if (precision == 2 && (!s.d_blob2 || dump)) precision = 3;   // a slot refreshed from device parameters has no FP8 blob; the trainer's forward keeps full accuracy
+    TrunkArgs a{(const u64 *)p1, (const u64 *)p2, color, n, out, out_kind, precision, precision == 2 ? s.d_blob2 : s.d_blob, s.d_bias, s.d_head, n_dev, {}, nullptr, {}};
     for (int l = 0; l < 8; l++) a.dump[l] = dump ? dump[l] : nullptr;
     cudaStream_t cs = (cudaStream_t)stream;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
@@ -708,6 +836,10 @@ int trunk_refresh_slot(iago_ctx *ctx, int slot, int kind, const float *d_params,
     }
     const int cin[8] = {2, 64, 128, 128, 128, 128, 128, 128}, cout[8] = {64, 128, 128, 128, 128, 128, 128, 128};
     cudaStream_t cs = (cudaStream_t)stream;
+    if (s.d_blob2) {   // the FP8 blob is only built by iago_load_net (it needs a per-layer max |w|): precision 2 runs as 3 on this slot from now on
+        cudaFree(s.d_blob2);
+        s.d_blob2 = nullptr;
+    }
     size_t off = 0;
     for (int l = 0; l < 8; l++) {
         const int total = (l == 0 ? 4 * cout[l] * 8 : 9 * (cin[l] / 64) * 8 * cout[l] * 8);

@@ -137,7 +137,9 @@ IAGO_API int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *param
 
 /* SLPolicy.__call__ on make_state_var(state, color) for n positions given as bitboards.
  * out [n][64]: out_kind 0 = pre-softmax logits, 1 = softmax probabilities (what the reference returns).
- * precision 3 = error-compensated fp16 hi/lo split (3 MMAs, ~fp32 accuracy), 1 = single-pass fp16. */
+ * precision 3 = error-compensated fp16 hi/lo split (3 MMAs, ~fp32 accuracy, max-abs logit error ~1e-4), 1 = single-pass fp16 (~0.1),
+ * 2 = fp16 main product + the two cross terms in FP8 / E4M3 on a second accumulator (2 MMA units, ~3e-3; north-star bar 1e-2;
+ * slots refreshed by a trainer run it as 3). */
 IAGO_API int iago_policy_forward(iago_ctx *ctx, int slot, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
                                  int64_t n, float *out, int out_kind, int precision, void *stream);
 
@@ -213,7 +215,7 @@ typedef struct iago_mcts_params {
     int32_t n_playouts;    /* playouts per tree in this call (the reference runs until time_limit, MCTS.py:139) */
     int32_t slot_policy;   /* net slots loaded with iago_load_net ('./models/sl_model.npz', value_model.npz)    */
     int32_t slot_value;
-    int32_t precision;     /* 1 or 3, as for iago_policy_forward                                               */
+    int32_t precision;     /* 1, 2 or 3, as for iago_policy_forward                                              */
     int32_t cache_value;   /* 1 = keep Value(position) in the node instead of re-running it (same outputs)     */
     int32_t reserved;
     uint64_t seed;         /* Philox key of the rollouts: game id = (tree id << 32) | playout index, stream 2  */

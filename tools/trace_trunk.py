@@ -1,0 +1,25 @@
+"""Debug: per-layer hand-over times of the trunk pipeline (needs a library built with -DIAGO_TRUNK_TRACE)."""
+import os, sys, ctypes as C
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+import iago_b200
+from iago_b200 import boards
+eng = iago_b200.Engine(0)
+mdir = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref", "models")
+eng.load_net(0, os.path.join(mdir, "sl_model.npz"))
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
+dev = torch.device("cuda", 0)
+p1 = torch.full((n,), boards.START_P1, dtype=torch.int64, device=dev); p2 = torch.full((n,), boards.START_P2, dtype=torch.int64, device=dev)
+col = torch.ones(n, dtype=torch.uint8, device=dev)
+for prec in (3, 1, 2):
+    eng.policy_forward(0, p1, p2, col, precision=prec); torch.cuda.synchronize()
+    eng.policy_forward(0, p1, p2, col, precision=prec); torch.cuda.synchronize()
+    buf = np.zeros(4096, np.uint64)
+    eng.lib.iago_debug_trace(C.c_void_p(buf.ctypes.data), 4096)
+    t = buf.reshape(-1, 8)[:4 * 9].reshape(4, 9, 8).astype(np.int64)
+    t0 = t[1, 0, 0]
+    print(f"precision {prec}: cycles relative to tile 1 layer 0 (events: chunk0 go, chunk1 go, commit issued | acc ready, pass0 done, pass1 done)")
+    for tile in (1, 2):
+        for l in range(8):
+            e = t[tile, l] - t0
+            print(f"  tile {tile} layer {l}: issuer {e[0]:7d} {e[1]:7d} {e[2]:7d} | epilogue {e[3]:7d} {e[4]:7d} {e[5]:7d}   layer span {t[tile, l, 3] - (t[tile, l - 1, 3] if l else t[tile - 1, 7, 3]):6d}")

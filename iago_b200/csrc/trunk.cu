@@ -45,8 +45,13 @@ namespace iago {
 // debug build only (tools/trace_trunk.py): SM clock at the pipeline's hand-over points of CTA 0, first tiles
 __device__ unsigned long long g_trace[4096];
 #define TRACE(tile_, l_, ev_) do { if (blockIdx.x == 0 && (tile_) < 4 * (long long)gridDim.x) g_trace[(((tile_) / gridDim.x) * 9 + (l_)) * 8 + (ev_)] = clock64(); } while (0)
+#define TRACEM(tile_, l_, u_, i_) do { if (blockIdx.x == 0 && (tile_) == (long long)gridDim.x && (l_) == 2 && (u_) == 5) g_trace[3072 + (i_)] = clock64(); } while (0)
+#define TRACEU(tile_, l_, u_, ev_) do { if (blockIdx.x == 0 && (tile_) == (long long)gridDim.x && (l_) == 2) g_trace[2048 + (u_) * 4 + (ev_)] = clock64(); } while (0)
 #else
 #define TRACE(tile_, l_, ev_) do { } while (0)
+#define TRACEM(tile_, l_, u_, i_) do { if (blockIdx.x == 0 && (tile_) == (long long)gridDim.x && (l_) == 2 && (u_) == 5) g_trace[3072 + (i_)] = clock64(); } while (0)
+#define TRACEU(tile_, l_, u_, ev_) do { } while (0)
+#define TRACEM(tile_, l_, u_, i_) do { } while (0)
 #endif
 
 // ---------------------------------------------------------------- geometry
@@ -56,7 +61,7 @@ constexpr int kRowPitch = 10 * 16;                // 160 B between consecutive 8
 constexpr int kActBytes = 16 * kGroupBytes;       // 128 channels: 51,200 B per precision part
 constexpr int kA1Bytes = 4 * kTileRows * 16;      // layer-1 explicit im2col tile, K = 32: 8,192 B
 constexpr int kStageBytes = 32768;                // one weight unit: hi [8][128][8] + lo
-constexpr int kStages = 3;
+constexpr int kStages = 3;                        // (a fourth stage was measured: no change — the issuer, not the ring, paces a layer)
 constexpr int kMaxLayers = 9;
 constexpr int kEpiThreads = 256;                  // warps 0-7
 constexpr int kThreads = 320;                     // + warp 8 producer, warp 9 MMA issuer
@@ -240,8 +245,10 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                     const uint32_t bytes = (split || p2) ? (uint32_t)ld.unit_bytes : (uint32_t)ld.lo_off;  // single pass needs hi only
                     for (int u = 0; u < ld.n_units; u++) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+                        TRACEU(tile, l, u, 0);
                         mbar_expect_tx(bar_full + 8 * stage, bytes);
                         bulk_g2s(sbase + OFF_STAGE + stage * kStageBytes, src, bytes, bar_full + 8 * stage);
+                        TRACEU(tile, l, u, 1);
                         src += ld.unit_bytes;
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
@@ -294,16 +301,21 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                                 const uint32_t off = a_chunk + (uint32_t)(ky * 20 + kx) * 16;
                                 mbar_wait(bar_full + 8 * stage, phase);
                                 tc_fence_after();
+                                TRACEU(tile, l, chunk * 9 + tap, 2);
                                 const uint32_t bst = sbase + OFF_STAGE + stage * kStageBytes;
                                 uint32_t ahw = ((sbase + OFF_AHI + off) >> 4) | a_lo_word, alw = ((sbase + OFF_ALO + off) >> 4) | a_lo_word;
                                 uint32_t bw = (bst >> 4) | b_lo_word, blw = ((bst + ld.lo_off) >> 4) | b_lo_word;
 #pragma unroll
                                 for (int ks = 0; ks < 4; ks++) {
+                                    TRACEM(tile, l, chunk * 9 + tap, ks * 4);
                                     umma_f16(d_tmem, desc_hi_a | ahw, desc_hi_b | bw, idesc, acc);
+                                    TRACEM(tile, l, chunk * 9 + tap, ks * 4 + 1);
                                     acc = 1;
                                     if (split) {
                                         umma_f16(d_tmem, desc_hi_a | ahw, desc_hi_b | blw, idesc, 1);
+                                        TRACEM(tile, l, chunk * 9 + tap, ks * 4 + 2);
                                         umma_f16(d_tmem, desc_hi_a | alw, desc_hi_b | bw, idesc, 1);
+                                        TRACEM(tile, l, chunk * 9 + tap, ks * 4 + 3);
                                     }
                                     ahw += (2 * kGroupBytes) >> 4; alw += (2 * kGroupBytes) >> 4; bw += b_step; blw += b_step;
                                 }
@@ -321,7 +333,10 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                                         a8w += (2 * kGroupBytes) >> 4; al8w += (2 * kGroupBytes) >> 4; w8w += b_step; wl8w += b_step;
                                     }
                                 }
+                                TRACEM(tile, l, chunk * 9 + tap, 16);
                                 umma_commit(bar_empty + 8 * stage);  // frees the weight stage when these MMAs retire
+                                TRACEM(tile, l, chunk * 9 + tap, 17);
+                                TRACEU(tile, l, chunk * 9 + tap, 3);
                                 if (++stage == kStages) { stage = 0; phase ^= 1; }
                             }
                         }

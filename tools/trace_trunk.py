@@ -11,15 +11,22 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 dev = torch.device("cuda", 0)
 p1 = torch.full((n,), boards.START_P1, dtype=torch.int64, device=dev); p2 = torch.full((n,), boards.START_P2, dtype=torch.int64, device=dev)
 col = torch.ones(n, dtype=torch.uint8, device=dev)
-for prec in (3, 1, 2):
+for prec in (3, 1):
     eng.policy_forward(0, p1, p2, col, precision=prec); torch.cuda.synchronize()
     eng.policy_forward(0, p1, p2, col, precision=prec); torch.cuda.synchronize()
     buf = np.zeros(4096, np.uint64)
     eng.lib.iago_debug_trace(C.c_void_p(buf.ctypes.data), 4096)
     t = buf.reshape(-1, 8)[:4 * 9].reshape(4, 9, 8).astype(np.int64)
+    u = buf[2048:2048 + 72].reshape(18, 4).astype(np.int64)
+    base = u[0, 2]
+    print(f"precision {prec}: units of tile 1 layer 2 (cycles from the issuer's first 'full'): producer empty-ready, tma issued | issuer full-ready, commit issued")
+    for i in range(18):
+        print(f"   unit {i:2d}: producer {u[i, 0] - base:7d} {u[i, 1] - base:7d} | issuer {u[i, 2] - base:7d} {u[i, 3] - base:7d}   (issue span {u[i, 3] - u[i, 2]:5d}, full-to-full {u[i, 2] - u[i - 1, 2] if i else 0:5d})")
+    mm = buf[3072:3072 + 18].astype(np.int64)
+    print("   unit 5 issue timeline (cycles from full-ready):", [int(x - u[5, 2]) if x else None for x in mm])
     t0 = t[1, 0, 0]
     print(f"precision {prec}: cycles relative to tile 1 layer 0 (events: chunk0 go, chunk1 go, commit issued | acc ready, pass0 done, pass1 done)")
-    for tile in (1, 2):
-        for l in range(8):
+    for tile in (1,):
+        for l in range(0):
             e = t[tile, l] - t0
             print(f"  tile {tile} layer {l}: issuer {e[0]:7d} {e[1]:7d} {e[2]:7d} | epilogue {e[3]:7d} {e[4]:7d} {e[5]:7d}   layer span {t[tile, l, 3] - (t[tile, l - 1, 3] if l else t[tile - 1, 7, 3]):6d}")

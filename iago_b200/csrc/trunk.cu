@@ -288,58 +288,73 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                         umma_commit(bar_empty + 8 * stage);
                         if (++stage == kStages) { stage = 0; phase ^= 1; }
                     } else {
+                        // The units of the layer as one software-pipelined stream: the wait for the NEXT unit's weights (and, at a chunk
+                        // boundary, for the next 64 input channels) is taken while this unit's last MMA group is still to be issued and
+                        // the earlier ones are queued, and the commit that frees a ring stage is issued after the first MMA of the
+                        // following unit — so the tensor pipe sees no gap between units (≈ 165 cycles per unit before).
                         const uint32_t a_lo_word = ((uint32_t)(kGroupBytes >> 4) << 16);
-                        for (int chunk = 0; chunk < ld.chunks; chunk++) {
-                            mbar_wait(bar_act + 8 * chunk, act_phase[chunk]);  // these 64 input channels are written
-                            act_phase[chunk] ^= 1;
-                            tc_fence_after();
-                            TRACE(tile, l, chunk);
-                            const uint32_t a_chunk = (uint32_t)chunk * 8 * kGroupBytes;
+                        const int n_units = 9 * ld.chunks;
+                        mbar_wait(bar_act, act_phase[0]);  // input channels 0..63 are written
+                        act_phase[0] ^= 1;
+                        tc_fence_after();
+                        TRACE(tile, l, 0);
+                        mbar_wait(bar_full + 8 * stage, phase);
+                        tc_fence_after();
+                        int pending = -1;   // ring stage whose commit is still to be issued
 #pragma unroll 1
-                            for (int tap = 0; tap < 9; tap++) {
-                                const int ky = tap / 3, kx = tap - ky * 3;  // (dy,dx) = (ky-1,kx-1); the halo sits at padded index 0
-                                const uint32_t off = a_chunk + (uint32_t)(ky * 20 + kx) * 16;
-                                mbar_wait(bar_full + 8 * stage, phase);
-                                tc_fence_after();
-                                TRACEU(tile, l, chunk * 9 + tap, 2);
-                                const uint32_t bst = sbase + OFF_STAGE + stage * kStageBytes;
-                                uint32_t ahw = ((sbase + OFF_AHI + off) >> 4) | a_lo_word, alw = ((sbase + OFF_ALO + off) >> 4) | a_lo_word;
-                                uint32_t bw = (bst >> 4) | b_lo_word, blw = ((bst + ld.lo_off) >> 4) | b_lo_word;
-#pragma unroll
-                                for (int ks = 0; ks < 4; ks++) {
-                                    TRACEM(tile, l, chunk * 9 + tap, ks * 4);
-                                    umma_f16(d_tmem, desc_hi_a | ahw, desc_hi_b | bw, idesc, acc);
-                                    TRACEM(tile, l, chunk * 9 + tap, ks * 4 + 1);
-                                    acc = 1;
-                                    if (split) {
-                                        umma_f16(d_tmem, desc_hi_a | ahw, desc_hi_b | blw, idesc, 1);
-                                        TRACEM(tile, l, chunk * 9 + tap, ks * 4 + 2);
-                                        umma_f16(d_tmem, desc_hi_a | alw, desc_hi_b | bw, idesc, 1);
-                                        TRACEM(tile, l, chunk * 9 + tap, ks * 4 + 3);
+                        for (int u = 0; u < n_units; u++) {
+                            const int chunk = u >= 9 ? 1 : 0, tap = u - chunk * 9;
+                            const int ky = tap / 3, kx = tap - ky * 3;  // (dy,dx) = (ky-1,kx-1); the halo sits at padded index 0
+                            const uint32_t off = (uint32_t)chunk * 8 * kGroupBytes + (uint32_t)(ky * 20 + kx) * 16;
+                            TRACEU(tile, l, u, 2);
+                            const uint32_t bst = sbase + OFF_STAGE + stage * kStageBytes;
+                            uint32_t ahw = ((sbase + OFF_AHI + off) >> 4) | a_lo_word, alw = ((sbase + OFF_ALO + off) >> 4) | a_lo_word;
+                            uint32_t bw = (bst >> 4) | b_lo_word, blw = ((bst + ld.lo_off) >> 4) | b_lo_word;
+                            uint32_t nstage = stage + 1, nphase = phase;
+                            if (nstage == kStages) { nstage = 0; nphase ^= 1; }
+                            auto look_ahead = [&]() {
+                                if (u + 1 < n_units) {
+                                    if (tap == 8) {   // the next unit starts the second chunk
+                                        mbar_wait(bar_act + 8, act_phase[1]);
+                                        act_phase[1] ^= 1;
+                                        TRACE(tile, l, 1);
                                     }
-                                    ahw += (2 * kGroupBytes) >> 4; alw += (2 * kGroupBytes) >> 4; bw += b_step; blw += b_step;
+                                    mbar_wait(bar_full + 8 * nstage, nphase);
+                                    tc_fence_after();
                                 }
-                                if (p2) {
-                                    // FP8 tiles: 16 channels per 16-byte row, so a 64-channel chunk is 4 groups and one K = 32 MMA spans two
-                                    // of them — the same descriptor stepping as fp16.  Weights: W8 = e4m3(w_hi * sw) at lo_off, WL8 after it.
-                                    const uint32_t off8 = (uint32_t)chunk * 4 * kGroupBytes + (uint32_t)(ky * 20 + kx) * 16;
-                                    uint32_t a8w = ((sbase + OFF_ALO + off8) >> 4) | a_lo_word, al8w = ((sbase + OFF_ALO + kA8Bytes + off8) >> 4) | a_lo_word;
-                                    uint32_t w8w = ((bst + ld.lo_off) >> 4) | b_lo_word, wl8w = ((bst + ld.lo_off + (ld.lo_off >> 1)) >> 4) | b_lo_word;
+                            };
 #pragma unroll
-                                    for (int ks = 0; ks < 2; ks++) {
-                                        umma_f8(d_tmem + kCrossCol, desc_hi_a | al8w, desc_hi_b | w8w, idesc, acc_x);
-                                        acc_x = 1;
-                                        umma_f8(d_tmem + kCrossCol, desc_hi_a | a8w, desc_hi_b | wl8w, idesc, 1);
-                                        a8w += (2 * kGroupBytes) >> 4; al8w += (2 * kGroupBytes) >> 4; w8w += b_step; wl8w += b_step;
-                                    }
+                            for (int ks = 0; ks < 4; ks++) {
+                                if (ks == 3 && !p2) look_ahead();
+                                umma_f16(d_tmem, desc_hi_a | ahw, desc_hi_b | bw, idesc, acc);
+                                acc = 1;
+                                if (split) {
+                                    umma_f16(d_tmem, desc_hi_a | ahw, desc_hi_b | blw, idesc, 1);
+                                    umma_f16(d_tmem, desc_hi_a | alw, desc_hi_b | bw, idesc, 1);
                                 }
-                                TRACEM(tile, l, chunk * 9 + tap, 16);
-                                umma_commit(bar_empty + 8 * stage);  // frees the weight stage when these MMAs retire
-                                TRACEM(tile, l, chunk * 9 + tap, 17);
-                                TRACEU(tile, l, chunk * 9 + tap, 3);
-                                if (++stage == kStages) { stage = 0; phase ^= 1; }
+                                if (ks == 0 && pending >= 0) umma_commit(bar_empty + 8 * pending);  // the previous unit's stage (covers this MMA too: harmless)
+                                ahw += (2 * kGroupBytes) >> 4; alw += (2 * kGroupBytes) >> 4; bw += b_step; blw += b_step;
                             }
+                            if (p2) {
+                                // FP8 tiles: 16 channels per 16-byte row, so a 64-channel chunk is 4 groups and one K = 32 MMA spans two
+                                // of them — the same descriptor stepping as fp16.  Weights: W8 = e4m3(w_hi * sw) at lo_off, WL8 after it.
+                                const uint32_t off8 = (uint32_t)chunk * 4 * kGroupBytes + (uint32_t)(ky * 20 + kx) * 16;
+                                uint32_t a8w = ((sbase + OFF_ALO + off8) >> 4) | a_lo_word, al8w = ((sbase + OFF_ALO + kA8Bytes + off8) >> 4) | a_lo_word;
+                                uint32_t w8w = ((bst + ld.lo_off) >> 4) | b_lo_word, wl8w = ((bst + ld.lo_off + (ld.lo_off >> 1)) >> 4) | b_lo_word;
+#pragma unroll
+                                for (int ks = 0; ks < 2; ks++) {
+                                    if (ks == 1) look_ahead();
+                                    umma_f8(d_tmem + kCrossCol, desc_hi_a | al8w, desc_hi_b | w8w, idesc, acc_x);
+                                    acc_x = 1;
+                                    umma_f8(d_tmem + kCrossCol, desc_hi_a | a8w, desc_hi_b | wl8w, idesc, 1);
+                                    a8w += (2 * kGroupBytes) >> 4; al8w += (2 * kGroupBytes) >> 4; w8w += b_step; wl8w += b_step;
+                                }
+                            }
+                            TRACEU(tile, l, u, 3);
+                            pending = (int)stage;
+                            stage = nstage; phase = nphase;
                         }
+                        umma_commit(bar_empty + 8 * pending);  // frees the last weight stage of the layer when its MMAs retire
                     }
                     umma_commit(bar_acc + 8 * (l & 1));  // accumulator of this layer complete
                     TRACE(tile, l, 2);

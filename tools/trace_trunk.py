@@ -11,7 +11,7 @@ n = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 dev = torch.device("cuda", 0)
 p1 = torch.full((n,), boards.START_P1, dtype=torch.int64, device=dev); p2 = torch.full((n,), boards.START_P2, dtype=torch.int64, device=dev)
 col = torch.ones(n, dtype=torch.uint8, device=dev)
-for prec in (3, 1):
+for prec in (3, 1, 2):
     eng.policy_forward(0, p1, p2, col, precision=prec); torch.cuda.synchronize()
     eng.policy_forward(0, p1, p2, col, precision=prec); torch.cuda.synchronize()
     buf = np.zeros(4096, np.uint64)

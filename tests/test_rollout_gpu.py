@@ -291,6 +291,14 @@ def test_host_call_on_pinned_buffers(engine, cref, rollout_weights):
         out2 = engine.rollout_host_buffers(n, want_moves=True)[3]
         engine.rollout_host(p1, p2, col, rng=Rng.replay_moves(forced), out=out2)
         assert (out2["moves"] == ref["moves"]).all() and (out2["final_p1"] == r1).all() and (out2["result"] == ref["results"]).all(), n
+        # replayed uniforms from a pinned array (direct copies again), drawn so that the games differ from the Philox ones
+        if n <= 16385:
+            u = engine.pinned((n, 64), np.float64)
+            u[:] = np.random.default_rng(n).random((n, 64))
+            refu = cref.simulate_batch(st, 1, W, b, mode=cref.RNG_UNIFORMS, uniforms=u, threads=0)
+            out4 = engine.rollout_host_buffers(n, want_moves=True)[3]
+            engine.rollout_host(p1, p2, col, rng=Rng.replay_uniforms(u), out=out4)
+            assert (out4["moves"] == refu["moves"]).all() and (out4["result"] == refu["results"]).all(), n
         # a pageable buffer among pinned ones falls back to staging
         out3 = dict(out2, result=np.empty(n, np.int8))
         engine.rollout_host(p1, p2, col, rng=Rng.philox(seed=11, game_id0=5), out=out3)

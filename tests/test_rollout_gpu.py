@@ -153,6 +153,29 @@ def test_arbitrary_boards_full_rollouts_vs_oracle(engine, cref, rollout_weights)
     assert (out2["moves"] == ref["moves"]).all() and (out2["final_p1"] == r1).all() and (out2["final_p2"] == r2).all()
 
 
+def test_arbitrary_placements_vs_oracle(engine, cref):
+    """place_stone has no legality check (game.py:179-207): the replayed move is placed whatever it is — on an occupied cell, with
+    nothing to flip, next to an edge.  20,000 random boards x random cells, both colours: the kernel's carry-propagation flips (four
+    directions per lane, the second lane on the turned board) against the oracle's ray walks, board for board."""
+    from iago_b200 import Rng
+    rng = np.random.default_rng(23)
+    n = 20000
+    fill = rng.random((n, 1))
+    r = rng.random((n, 64))
+    st = np.where(r < fill * 0.5, 1, np.where(r < fill, 2, 0)).astype(np.float32)
+    col = rng.integers(1, 3, n).astype(np.uint8)
+    forced = rng.integers(0, 64, (n, 64)).astype(np.int8)
+    W, b = np.zeros((1, 2, 3, 3), np.float32), np.zeros(64, np.float32)   # unused in FORCED mode
+    ref = cref.simulate_batch(st, col.astype(np.int32), W, b, mode=cref.RNG_FORCED, forced=forced, threads=0)
+    p1, p2 = bb(st)
+    out = engine.rollout_host(p1, p2, col, rng=Rng.replay_moves(forced), want_moves=True)
+    r1, r2 = bb(ref["final"])
+    assert (out["n_moves"] == ref["n_moves"]).all()
+    assert (out["final_p1"] == r1).all() and (out["final_p2"] == r2).all()
+    assert (out["result"] == ref["results"]).all() and (out["moves"] == ref["moves"]).all()
+    assert ref["n_moves"].sum() > 5 * n     # the games really placed stones
+
+
 def test_logits_vs_oracle_and_reference(engine, cref, rollout_weights, golden_nets):
     W, b = rollout_weights
     g = golden_nets

@@ -56,3 +56,16 @@ def mean_gradient_(flat, n_params, group=None):
     all_reduce_sum_(flat, group)
     num, count = flat[n_params:n_params + 2].tolist()
     return (num / count if count > 0 else 0.0), count
+
+
+def root_parallel_moves(visits, group=None):
+    """One game searched on several GPUs at once (the optional exchange for a single tree): every rank searches the
+    same root with its own global tree id — the rollouts draw from different Philox streams — and the root visit counts
+    [n_trees, 65] (index 64 = the pass child) are summed over the ranks.  Returns (summed visits, best action per tree) with the
+    reference's tie rule (MCTS.py:147: the first maximum, i.e. the lowest action; pass = -1 only when it is the only child)."""
+    v = torch.as_tensor(visits).to(torch.int64).clone()
+    all_reduce_sum_(v, group)
+    best = torch.argmax(v[:, :64], dim=1)
+    only_pass = (v[:, :64].sum(dim=1) == 0) & (v[:, 64] > 0)
+    best = torch.where(only_pass, torch.full_like(best, -1), best)
+    return v, best

@@ -42,7 +42,13 @@ def _worker(rank, world_size, port, out):
     lo, hi = parallel.shard_range(1001, rank, world_size)
     counters = parallel.reduce_counters(dict(wins=rank + 1, games=hi - lo, plies=10 * (rank + 1)))
     t = parallel.all_reduce_max_(torch.tensor([float(rank)]))
-    out[rank] = dict(res=res, counters=counters, tmax=float(t[0]), shard=(lo, hi))
+    # root-parallel search of one game: each rank's visit counts, summed; lowest action wins ties; a lone pass child gives -1
+    visits = np.zeros((3, 65), np.int32)
+    visits[0, [19, 26, 37]] = [5 + rank, 7 - rank, 3]        # sums: 11, 13, 6 -> 26
+    visits[1, [10, 20]] = [4 + rank, 5 - rank]                 # sums: 9, 9 -> tie -> 10
+    visits[2, 64] = 8                                          # only the pass child
+    vsum, best = parallel.root_parallel_moves(visits)
+    out[rank] = dict(res=res, counters=counters, tmax=float(t[0]), shard=(lo, hi), vsum=vsum.numpy(), best=best.tolist())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -65,6 +71,9 @@ def test_two_rank_sharding_and_collectives():
     assert out[0]["counters"] == out[1]["counters"] == dict(wins=3, games=1001, plies=30)
     assert out[0]["tmax"] == out[1]["tmax"] == 1.0
     assert out[0]["shard"] == (0, 501) and out[1]["shard"] == (501, 1001)
+    for r in range(world_size):
+        assert out[r]["best"] == [26, 10, -1]
+        assert out[r]["vsum"][0, [19, 26, 37]].tolist() == [11, 13, 6] and int(out[r]["vsum"][2, 64]) == 16
 
 
 def test_id_sharding_is_a_partition():

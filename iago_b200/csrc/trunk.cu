@@ -259,6 +259,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
         // ================= MMA issuer: one thread =================
         if ((tid & 31) == 0) {
             uint32_t stage = 0, phase = 0, act_phase[2] = {0, 0}, a1_phase = 0;
+            const uint32_t hiA = (uint32_t)(kRowPitch >> 4) | (1u << 14), hiB = (uint32_t)(128 >> 4) | (1u << 14);   // high words: SBO + version
             const uint64_t desc_hi_a = ((uint64_t)(kRowPitch >> 4) << 32) | (1ULL << 46);  // SBO + version; LBO/start in the low word
             const uint64_t desc_hi_b = ((uint64_t)(128 >> 4) << 32) | (1ULL << 46);
             for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
@@ -308,8 +309,8 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                             const uint32_t off = (uint32_t)chunk * 8 * kGroupBytes + (uint32_t)(ky * 20 + kx) * 16;
                             TRACEU(tile, l, u, 2);
                             const uint32_t bst = sbase + OFF_STAGE + stage * kStageBytes;
-                            uint32_t ahw = ((sbase + OFF_AHI + off) >> 4) | a_lo_word, alw = ((sbase + OFF_ALO + off) >> 4) | a_lo_word;
-                            uint32_t bw = (bst >> 4) | b_lo_word, blw = ((bst + ld.lo_off) >> 4) | b_lo_word;
+                            const uint32_t ahw = ((sbase + OFF_AHI + off) >> 4) | a_lo_word, alw = ((sbase + OFF_ALO + off) >> 4) | a_lo_word;
+                            const uint32_t bw = (bst >> 4) | b_lo_word, blw = ((bst + ld.lo_off) >> 4) | b_lo_word;
                             uint32_t nstage = stage + 1, nphase = phase;
                             if (nstage == kStages) { nstage = 0; nphase ^= 1; }
                             auto look_ahead = [&]() {
@@ -323,33 +324,55 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                                     tc_fence_after();
                                 }
                             };
+                            // Straight-line issue per precision mode: the four descriptor low words of the unit are computed once, every
+                            // MMA's descriptor is (low word + a constant, constant high word) — a micro-benchmark (tools/micro/umma_rate.cu)
+                            // shows the tensor pipe takes one 128x128x16 MMA per 64 cycles when the issuing thread is this lean, and 97-170
+                            // when it recomputes descriptors and branches between MMAs, which is what paced this kernel before.
+                            constexpr uint32_t dA = (2 * kGroupBytes) >> 4;
+                            const bool commit_prev = pending >= 0;
+                            const uint32_t prev_bar = bar_empty + 8 * (uint32_t)(pending < 0 ? 0 : pending);
+                            if (split) {
 #pragma unroll
-                            for (int ks = 0; ks < 4; ks++) {
-                                if (ks == 3 && !p2) look_ahead();
-                                umma_f16(d_tmem, desc_hi_a | ahw, desc_hi_b | bw, idesc, acc);
-                                acc = 1;
-                                if (split) {
-                                    umma_f16(d_tmem, desc_hi_a | ahw, desc_hi_b | blw, idesc, 1);
-                                    umma_f16(d_tmem, desc_hi_a | alw, desc_hi_b | bw, idesc, 1);
+                                for (int ks = 0; ks < 4; ks++) {
+                                    if (ks == 3) look_ahead();
+                                    const uint64_t da = pack64(ahw + ks * dA, hiA), dal = pack64(alw + ks * dA, hiA);
+                                    const uint64_t db = pack64(bw + ks * b_step, hiB), dbl = pack64(blw + ks * b_step, hiB);
+                                    if (ks == 0) umma_f16(d_tmem, da, db, idesc, acc); else umma_f16(d_tmem, da, db, idesc, 1);
+                                    umma_f16(d_tmem, da, dbl, idesc, 1);
+                                    umma_f16(d_tmem, dal, db, idesc, 1);
+                                    if (ks == 0 && commit_prev) umma_commit(prev_bar);  // the previous unit's stage (covers these MMAs too: harmless)
                                 }
-                                if (ks == 0 && pending >= 0) umma_commit(bar_empty + 8 * pending);  // the previous unit's stage (covers this MMA too: harmless)
-                                ahw += (2 * kGroupBytes) >> 4; alw += (2 * kGroupBytes) >> 4; bw += b_step; blw += b_step;
-                            }
-                            if (p2) {
+                            } else if (p2) {
                                 // FP8 tiles: 16 channels per 16-byte row, so a 64-channel chunk is 4 groups and one K = 32 MMA spans two
                                 // of them — the same descriptor stepping as fp16.  Weights: W8 = e4m3(w_hi * sw) at lo_off, WL8 after it.
                                 const uint32_t off8 = (uint32_t)chunk * 4 * kGroupBytes + (uint32_t)(ky * 20 + kx) * 16;
-                                uint32_t a8w = ((sbase + OFF_ALO + off8) >> 4) | a_lo_word, al8w = ((sbase + OFF_ALO + kA8Bytes + off8) >> 4) | a_lo_word;
-                                uint32_t w8w = ((bst + ld.lo_off) >> 4) | b_lo_word, wl8w = ((bst + ld.lo_off + (ld.lo_off >> 1)) >> 4) | b_lo_word;
+                                const uint32_t a8w = ((sbase + OFF_ALO + off8) >> 4) | a_lo_word, al8w = ((sbase + OFF_ALO + kA8Bytes + off8) >> 4) | a_lo_word;
+                                const uint32_t wl8w = ((bst + ld.lo_off + (ld.lo_off >> 1)) >> 4) | b_lo_word;   // (W8 sits at blw)
+#pragma unroll
+                                for (int ks = 0; ks < 4; ks++) {
+                                    const uint64_t da = pack64(ahw + ks * dA, hiA), db = pack64(bw + ks * b_step, hiB);
+                                    if (ks == 0) umma_f16(d_tmem, da, db, idesc, acc); else umma_f16(d_tmem, da, db, idesc, 1);
+                                    if (ks == 0 && commit_prev) umma_commit(prev_bar);
+                                }
 #pragma unroll
                                 for (int ks = 0; ks < 2; ks++) {
                                     if (ks == 1) look_ahead();
-                                    umma_f8(d_tmem + kCrossCol, desc_hi_a | al8w, desc_hi_b | w8w, idesc, acc_x);
-                                    acc_x = 1;
-                                    umma_f8(d_tmem + kCrossCol, desc_hi_a | a8w, desc_hi_b | wl8w, idesc, 1);
-                                    a8w += (2 * kGroupBytes) >> 4; al8w += (2 * kGroupBytes) >> 4; w8w += b_step; wl8w += b_step;
+                                    const uint64_t da8 = pack64(a8w + ks * dA, hiA), dal8 = pack64(al8w + ks * dA, hiA);
+                                    const uint64_t dw8 = pack64(blw + ks * b_step, hiB), dwl8 = pack64(wl8w + ks * b_step, hiB);
+                                    if (ks == 0) umma_f8(d_tmem + kCrossCol, dal8, dw8, idesc, acc_x); else umma_f8(d_tmem + kCrossCol, dal8, dw8, idesc, 1);
+                                    umma_f8(d_tmem + kCrossCol, da8, dwl8, idesc, 1);
+                                }
+                                acc_x = 1;
+                            } else {
+#pragma unroll
+                                for (int ks = 0; ks < 4; ks++) {
+                                    if (ks == 3) look_ahead();
+                                    const uint64_t da = pack64(ahw + ks * dA, hiA), db = pack64(bw + ks * b_step, hiB);
+                                    if (ks == 0) umma_f16(d_tmem, da, db, idesc, acc); else umma_f16(d_tmem, da, db, idesc, 1);
+                                    if (ks == 0 && commit_prev) umma_commit(prev_bar);
                                 }
                             }
+                            acc = 1;
                             TRACEU(tile, l, u, 3);
                             pending = (int)stage;
                             stage = nstage; phase = nphase;

@@ -63,6 +63,37 @@ __global__ void __launch_bounds__(64, 1) rate_kernel(int pattern, int steps, lon
                     }
                 }
                 n_mma = 12LL * steps;
+            } else if (pattern == 10) {  // FP8 (kind::f8f6f4, K = 32) MMAs straight, fixed descriptors
+#pragma unroll 1
+                for (int s = 0; s < steps; s++) {
+#pragma unroll
+                    for (int j = 0; j < 12; j++) umma_f8(tmem, da0, db0, idesc, 1);
+                }
+                n_mma = 12LL * steps;
+            } else if (pattern == 11) {  // precision 2's unit: 4 fp16 MMAs then 4 FP8 MMAs into a second accumulator
+#pragma unroll 1
+                for (int s = 0; s < steps; s++) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) umma_f16(tmem, da[ks], db[ks], idesc, 1);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ks++) {
+                        umma_f8(tmem + 256, dal[ks], dbl[ks], idesc, 1);
+                        umma_f8(tmem + 256, da[ks], dbl[ks + 2], idesc, 1);
+                    }
+                }
+                n_mma = 8LL * steps;
+            } else if (pattern == 12) {  // the same 8 MMAs, all kind::f16 (what a kind switch costs)
+#pragma unroll 1
+                for (int s = 0; s < steps; s++) {
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++) umma_f16(tmem, da[ks], db[ks], idesc, 1);
+#pragma unroll
+                    for (int ks = 0; ks < 2; ks++) {
+                        umma_f16(tmem + 256, dal[ks], dbl[ks], idesc, 1);
+                        umma_f16(tmem + 256, da[ks], dbl[ks + 2], idesc, 1);
+                    }
+                }
+                n_mma = 8LL * steps;
             } else {                     // precision 1's unit: 4 K steps x 1 MMA, precomputed
 #pragma unroll 1
                 for (int s = 0; s < steps; s++) {
@@ -108,9 +139,9 @@ int main() {
     long long *d_out, h[3];
     cudaMalloc(&d_out, 24);
     cudaFuncSetAttribute(rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kARegion + kBRegion);
-    const char *names[] = {"same A/B slice every MMA", "K advances every MMA (p1)", "3 MMAs per K step (p3)", "scattered slices", "K advances, 2 accumulators", "N=256 + N=128 per K step", "tight loop, 1 MMA per trip", "12 MMAs straight, fixed desc", "unit of 4x3 MMAs, precomputed", "unit of 4x1 MMAs, precomputed"};
+    const char *names[] = {"same A/B slice every MMA", "K advances every MMA (p1)", "3 MMAs per K step (p3)", "scattered slices", "K advances, 2 accumulators", "N=256 + N=128 per K step", "tight loop, 1 MMA per trip", "12 MMAs straight, fixed desc", "unit of 4x3 MMAs, precomputed", "unit of 4x1 MMAs, precomputed", "12 FP8 K=32 MMAs straight", "p2 unit: 4 f16 + 4 f8", "same 8 MMAs all f16"};
     for (int grid : {1})
-        for (int p = 0; p < 10; p++) {
+        for (int p = 6; p < 13; p++) {
             rate_kernel<<<grid, 64, kARegion + kBRegion>>>(p, 64, d_out);
             rate_kernel<<<grid, 64, kARegion + kBRegion>>>(p, 4096, d_out);
             cudaError_t e = cudaDeviceSynchronize();

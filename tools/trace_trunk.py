@@ -23,10 +23,9 @@ for prec in (3, 1, 2):
     for i in range(18):
         print(f"   unit {i:2d}: producer {u[i, 0] - base:7d} {u[i, 1] - base:7d} | issuer {u[i, 2] - base:7d} {u[i, 3] - base:7d}   (issue span {u[i, 3] - u[i, 2]:5d}, full-to-full {u[i, 2] - u[i - 1, 2] if i else 0:5d})")
     mm = buf[3072:3072 + 18].astype(np.int64)
-    print("   unit 5 issue timeline (cycles from full-ready):", [int(x - u[5, 2]) if x else None for x in mm])
     t0 = t[1, 0, 0]
     print(f"precision {prec}: cycles relative to tile 1 layer 0 (events: chunk0 go, chunk1 go, commit issued | acc ready, pass0 done, pass1 done)")
     for tile in (1,):
-        for l in range(0):
+        for l in range(8):
             e = t[tile, l] - t0
             print(f"  tile {tile} layer {l}: issuer {e[0]:7d} {e[1]:7d} {e[2]:7d} | epilogue {e[3]:7d} {e[4]:7d} {e[5]:7d}   layer span {t[tile, l, 3] - (t[tile, l - 1, 3] if l else t[tile - 1, 7, 3]):6d}")

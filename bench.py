@@ -458,6 +458,18 @@ def section_selfplay(eng, args, rank, world, dev, dist, barrier):
         barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     t = sum(step_ms) / 1e3
+    # the same step with the nets in precision 2 (fp16 main product + FP8 cross terms: 3e-3 max-abs logit error, arg-max unchanged)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.selfplay(0, 0, n, greedy=True, precision=2, rng=Rng.philox(seed=1, stream_id=1))
+    barrier()
+    e0.record()
+    res2 = eng.selfplay(0, 0, n, greedy=True, precision=2, rng=Rng.philox(seed=args.seed, game_id0=rank * n, stream_id=1))
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    same_games = bool((res2["final_p1"] == res["final_p1"]).all() and (res2["final_p2"] == res["final_p2"]).all())   # greedy play: no draws involved
     wins = torch.stack([(res["result"] == 1).sum(), (res["result"] == 0).sum(), (res["result"] == -1).sum()]).to(torch.int64)
     tt = torch.tensor([t], dtype=torch.float64, device=dev)
     cc = torch.tensor([reps * n, fwd * n], dtype=torch.int64, device=dev)
@@ -474,6 +486,9 @@ def section_selfplay(eng, args, rank, world, dev, dist, barrier):
                                   "(BASELINE configs[2])", "games_per_step_per_gpu": n, "steps": reps, "precision": "fp16 hi/lo split, 3 MMAs"},
            "positions_per_s": positions / t, "trunk_forwards_per_game": fwd / reps,
            "step_ms_rank0": [round(x, 2) for x in step_ms], "clocks": clk.summary(),
+           "precision2": {"value": n * world / float(t2[0]), "unit": "games/s", "ms_per_step": 1e3 * float(t2[0]),
+                          "note": "nets in precision 2 (fp16 main product + FP8 cross terms; 3e-3 max-abs logit error on the fixtures, "
+                                  "arg-max unchanged; north-star bar 1e-2)", "same_final_boards_as_precision3": same_games},
            "last_step_w_d_l": wins.tolist(),
            "roofline": {"bound": "tensor", "kernel": "trunk_kernel", "achieved": ach, "peak": peak * world, "unit": "TFLOP/s",
                         "frac": ach / (peak * world), "traffic": None, "peak_source": src,
@@ -497,8 +512,8 @@ def section_mcts(eng, args, rank, world, dev, dist, barrier):
     pool = SearchPool(T, max_nodes=32768, max_leaf_batch=B, tree_id0=rank * T, engine=eng)
     p1, p2 = (1 << 19) | (1 << 27) | (1 << 28) | (1 << 35), 1 << 36   # the opening after colour 1 plays 19
     out = {}
-    for cache in (True, False):
-        kw = dict(slot_policy=0, slot_value=1, lmbda=0.5, c_puct=1, n_thr=15, leaf_batch=B, virtual_loss=1.0, precision=3,
+    for cache, prec in ((True, 3), (False, 3), (True, 2)):
+        kw = dict(slot_policy=0, slot_value=1, lmbda=0.5, c_puct=1, n_thr=15, leaf_batch=B, virtual_loss=1.0, precision=prec,
                   cache_value=cache, seed=args.seed)
         pool.set_roots(p1, p2, 2, reset_tree=True)
         pool.search(2 * B, **kw)   # warm-up waves
@@ -514,14 +529,17 @@ def section_mcts(eng, args, rank, world, dev, dist, barrier):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t = float(tt[0])
         visits, q, best = pool.root_stats()
-        out["cached" if cache else "uncached"] = {"value": T * N * world / t, "ms_per_move": 1e3 * t, "best_move_tree0": int(best[0]),
-                                                  "pool_overflows": pool.overflows()}
+        out["precision2" if prec == 2 else "cached" if cache else "uncached"] = {
+            "value": T * N * world / t, "ms_per_move": 1e3 * t, "best_move_tree0": int(best[0]), "pool_overflows": pool.overflows()}
     peak, src = bf16_peak()
     unc = out["uncached"]["value"]
     res = {"metric": "mcts_playouts_per_s", "value": out["cached"]["value"], "unit": "playouts/s",
            "config": {"workload": "PV-MCTS, sl/value/rollout nets, lmbda 0.5, c_puct 1, n_thr 15, leaf batch 256, virtual loss 1, root = "
                                   "opening after move 19, one move (BASELINE configs[3])", "trees_per_gpu": T, "playouts_per_move": N},
            "value_cache_on": out["cached"], "value_cache_off": out["uncached"],
+           "precision2": dict(out["precision2"], note="the same search (value cache on) with the nets in precision 2: fp16 main product + FP8 "
+                              "cross terms, max-abs logit error 3e-3 on the fixtures against 1e-4 for the default precision 3 "
+                              "(north-star bar 1e-2), arg-max unchanged"),
            "roofline": {"bound": "tensor", "kernel": "trunk_kernel (value net, cache off: one forward per playout)",
                         "achieved": unc * VALUE_FLOP / 1e12, "peak": peak * world, "unit": "TFLOP/s",
                         "frac": unc * VALUE_FLOP / 1e12 / (peak * world), "traffic": None, "peak_source": src,

@@ -1,23 +1,27 @@
-// rollout.cu — K1+K2: the lockstep rollout kernel and the batched rules entry points.
+// rollout.cu — K1+K2: the lockstep rollout kernels and the batched rules entry points.
 //
-// One thread owns one game: its board lives in four 32-bit registers (two 64-bit bitboards, mover's view),
-// plus stone_num / pass_flg / counters.  A turn is
-//   legal_moves (shift-and-mask, bitboard.cuh)                    <- GameFunctions.legal_actions
-//   rollout policy at the legal cells only: two 512-entry LUT reads (9-bit 3x3 neighbourhood of each
-//   plane) + bias, shared memory                                  <- RolloutPolicy.__call__ network.py:59-64
-//   exp32 (bit-exact with the oracle), fixed-point inverse cdf against one Philox / replayed uniform
-//                                                                  <- Simulate.get_action mcts_self_play.py:100-110
-//   flips + board update                                           <- place_stone
+// Main path (every weight set that passes the FAST test below): rollout_pair_kernel — TWO lanes own one game, lane 1 on the board
+// turned by 180 degrees, so both run the same four flood directions and each owns the legal cells of one half of the board; see the
+// comment above that kernel.  rollout_kernel (one thread per game, the first version of this file) remains for weight sets that
+// need the SAFE sampler, and rollout_sample_kernel serves single draws.  A turn is
+//   legal moves (shift-and-mask floods / carry propagation, bitboard.cuh)      <- GameFunctions.legal_actions
+//   rollout policy at the legal cells only: two 512-entry table reads (9-bit 3x3 neighbourhood of each plane) and the cell's
+//   bias term from shared memory                                                  <- RolloutPolicy.__call__ network.py:59-64
+//   inverse cdf against one Philox / replayed uniform                            <- Simulate.get_action mcts_self_play.py:100-110
+//   flips + board update                                                         <- place_stone
 //   pass / terminal bookkeeping exactly as Simulate.turn / __call__ (mcts_self_play.py:25-29,124-134)
-// and the game ends with judge (mcts_self_play.py:113-121).  Nothing goes to global memory during the game
-// except the optional move log; algorithmic HBM traffic is 17 B in + 17-21 B out per game.
+// and the game ends with judge (mcts_self_play.py:113-121).  Nothing goes to global memory during the game except the optional
+// move log; algorithmic HBM traffic is 17 B in + 17-21 B out per game.
 //
 // Canonical rollout arithmetic (identical, bit for bit, in oracle/othello_ref.c).  S_c = sum of the set taps of plane c in
 // ascending tap order, logit = (S0 + S1) + bias[k].
 //   FAST (max|S0| + max|S1| + max|bias| <= 300, i.e. any finite sanely trained rollout net; decided when the weights are loaded):
-//     e_k = (E0 * E1) * EB in double with E_c = canon_exp(S_c), EB = canon_exp(bias[k]) from look-up tables — the softmax
-//     numerator as a product of exponentials, no exp and no max pass in the kernel; cum_k = double running sum over the legal
-//     cells ascending (the reference's cdf is float64 too); pick the first legal k with cum_k > u * total, u = m53 / 2^53.
+//     w_k = (E0 * E1) * EB in double with E_c = canon_exp(S_c), EB = canon_exp(bias[k]) from look-up tables — the softmax
+//     numerator as a product of exponentials, no exp and no max pass in the kernel.  Two-sided cdf: A_i = double running sum over
+//     the legal cells 0..31 ascending, D_j = over the legal cells 63..32 DESCENDING, total = A_last + D_last, T = u * total with
+//     u = m53 / 2^53; if T < A_last (or no legal cell lies above 31) the move is the first cell with A_i > T, otherwise the cell at
+//     position #{j <= n_hi - 2 : D_j < total - T} of the descending list.  In exact arithmetic this is np.random.choice's
+//     searchsorted(cdf, u, 'right').
 //   SAFE (any other weights): e = exp32(logit - max_legal); q = floor(e * 2^26) (uint32); pick the first legal k with
 //     cum_q > floor((m53 >> 21) * total / 2^32).
 #include <math.h>

@@ -13,16 +13,19 @@
 //     contiguous block in ascending action order (= the reference's dict insertion order, so "first maximum" is the
 //     same child).  Boards are not stored: a descent replays the moves on a bitboard pair in registers.
 //   * One wave = up to B playouts per tree:
-//       select (pass 1)  one warp per tree walks its B descents one after the other (so every descent sees the
-//                        virtual visits of the ones before it: deterministic), lanes score the children in parallel
-//                        in fp64; a leaf that must be expanded and needs priors is parked and queued
+//       select (pass 1)  the B descents of a tree run in a fixed order, each seeing the virtual visits of the ones before it
+//                        (deterministic) — executed as a software pipeline over 8 warps per tree that preserves exactly that
+//                        order (mcts_select_pipe_kernel; mcts_select_kernel is the one-warp form, used for B < 8 and the
+//                        exact mode); lanes score the children in parallel in fp64; a leaf that must be expanded and needs
+//                        priors is parked and queued
 //       policy           ONE fused trunk launch over every queued position of every tree (trunk.cu, count on device)
 //       expand           priors written, children become visible
 //       select (pass 2)  the parked descents continue into the fresh children
 //       value            ONE trunk launch over the leaves whose value is not cached yet (Value is a pure function of
 //                        the position; the reference re-runs it up to n_thr times on the same leaf)
 //       rollout          ONE lockstep rollout launch over all T*B leaves (rollout.cu), Philox keyed by
-//                        (global tree id, playout index)
+//                        (global tree id, playout index); it runs on a second stream beside the value launch
+//     and the waves of a search after the first replay a captured CUDA graph (iago_mcts_search)
 //       backup           exact mode (B = 1): the reference's float32 / float64 running mean, applied in order;
 //                        batched mode: atomicAdd on n and on a 2^-40 fixed-point value sum (order-free, so the
 //                        result does not depend on scheduling), virtual visits removed

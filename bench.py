@@ -16,6 +16,9 @@ Printed JSON (one line, rank 0):
   cpu_baseline   the CPU oracle port (oracle/othello_ref.c, pthreads over all cores) on a bounded sample,
              plus the unmodified Python reference under the chainer stand-in when baseline/_ref is present
   --impl reference   times the CPU port alone (the reference is pure Python and cannot be "compiled")
+  selfplay / mcts / reinforce / valuegen   the other BASELINE configs as extra sections of the same line (games/s, playouts/s,
+             records/s, each with its roofline fraction and the reference's CPU figure); `precision2` inside selfplay / mcts is
+             the same workload with the nets' opt-in fp16 + FP8-cross-term mode
 """
 import argparse
 import json

@@ -49,7 +49,6 @@ __device__ unsigned long long g_trace[4096];
 #define TRACEU(tile_, l_, u_, ev_) do { if (blockIdx.x == 0 && (tile_) == (long long)gridDim.x && (l_) == 2) g_trace[2048 + (u_) * 4 + (ev_)] = clock64(); } while (0)
 #else
 #define TRACE(tile_, l_, ev_) do { } while (0)
-#define TRACEM(tile_, l_, u_, i_) do { if (blockIdx.x == 0 && (tile_) == (long long)gridDim.x && (l_) == 2 && (u_) == 5) g_trace[3072 + (i_)] = clock64(); } while (0)
 #define TRACEU(tile_, l_, u_, ev_) do { } while (0)
 #define TRACEM(tile_, l_, u_, i_) do { } while (0)
 #endif

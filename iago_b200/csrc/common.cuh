@@ -93,14 +93,13 @@ int rollout_launch_ids(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, co
 bool trunk_slot_holds(iago_ctx *ctx, int slot, int kind);
 void valuegen_destroy(iago_ctx *ctx);
 // trunk.cu, backward data-gradient chain of the SLPolicy trunk on the tensor cores (used by reinforce.cu):
-//   pack: W[l] (l = 1..7, device fp32 [128][cin_l][3][3]) -> bf16 hi/lo weight units in `blob` + the chain descriptor in `desc_dev`
+//   pack: W[l] (l = 1..7, device fp32 [128][cin_l][3][3]) -> bf16 hi/lo weight units in `blob`
 //   launch: dy_in = gradient w.r.t. block 8's output [n][128][64]; chain layer i (i = 0..6) writes the gradient w.r.t. the output
 //   of block 7-i to dx_out[i] ([n][cin][64], cin = 64 for i = 6), gated by mask[i] > 0 (that block's forward output).
 // trunk.cu: rewrite the weight blob of an already loaded slot of the same kind from DEVICE fp32 parameters (iago_load_net order).
 int trunk_refresh_slot(iago_ctx *ctx, int slot, int kind, const float *d_params, void *stream);
 size_t trunk_backward_blob_bytes();
-size_t trunk_desc_bytes();
-int trunk_backward_pack(iago_ctx *ctx, const float *const *W, uint8_t *blob, void *desc_dev, void *stream);
-int trunk_backward_launch(iago_ctx *ctx, const void *desc_dev, const uint8_t *blob, const float *dy_in, const float *const *mask,
+int trunk_backward_pack(iago_ctx *ctx, const float *const *W, uint8_t *blob, void *stream);
+int trunk_backward_launch(iago_ctx *ctx, const uint8_t *blob, const float *dy_in, const float *const *mask,
                           float *const *dx_out, int64_t n, int precision, void *stream);
 }  // namespace iago

@@ -888,7 +888,6 @@ struct iago_trainer {
     float *act[9] = {};               // act[0] = input planes, act[l] = output of block l
     float *dyb[8] = {};               // dyb[l]: gradient w.r.t. the pre-activation output of block l+1, [max_pos][cout_l][64]
     uint8_t *bwd_blob = nullptr;      // bf16 hi/lo weight units of the data-gradient chain (trunk.cu, backward mode)
-    void *bwd_desc = nullptr;
     int bwd_precision = 3;
     float *dlogit = nullptr, *loss_terms = nullptr, *partial = nullptr, *bias_partial = nullptr;
     unsigned *dymax = nullptr;        // [8] bit pattern of max |dY| per layer (bias_grad_kernel)
@@ -961,7 +960,6 @@ int iago_trainer_create(iago_ctx *ctx, int kind, const float *params, int64_t n_
     for (int l = 0; l < 8; l++) A(t->act[l + 1], M * kCout[l] * 64);
     for (int l = 0; l < 8; l++) A(t->dyb[l], M * kCout[l] * 64);
     A(t->bwd_blob, trunk_backward_blob_bytes());
-    { uint8_t *d = nullptr; A(d, trunk_desc_bytes()); t->bwd_desc = d; }
     A(t->dlogit, M * 64); A(t->loss_terms, M); A(t->ones, M); A(t->logits_scratch, M * 64);
     if (kind == 1) {
         A(t->h9, M * 64); A(t->du, M * 128); A(t->zbuf, M * 128); A(t->dpre9, M * 64); A(t->dv, M); A(t->vpred, M);
@@ -1035,9 +1033,9 @@ static int backward_trunk(iago_trainer *t, int64_t m, float *grad, int accumulat
             mask[i] = t->act[7 - i];
             dx[i] = t->dyb[6 - i];
         }
-        int rc = trunk_backward_pack(t->ctx, W, t->bwd_blob, t->bwd_desc, stream);
+        int rc = trunk_backward_pack(t->ctx, W, t->bwd_blob, stream);
         if (rc) return rc;
-        rc = trunk_backward_launch(t->ctx, t->bwd_desc, t->bwd_blob, t->dyb[7], mask, dx, m, t->bwd_precision, stream);
+        rc = trunk_backward_launch(t->ctx, t->bwd_blob, t->dyb[7], mask, dx, m, t->bwd_precision, stream);
         if (rc) return rc;
     }
     for (int l = 7; l >= 0; l--) {

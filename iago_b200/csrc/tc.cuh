@@ -42,6 +42,13 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// One lane of a fully converged warp (the same lane every time for the same mask: tcgen05.commit tracks the MMAs of the thread
+// that issued them).  Code that wraps only the TMA / tcgen05 instructions in `if (elect_one())` keeps the surrounding loop warp-uniform.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xFFFFFFFF;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -88,6 +95,80 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t &v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---------------------------------------------------------------- CTA pairs (cta_group::2): two CTAs of a cluster share one MMA
+// (tools/micro/umma2_check.cu is the known-answer test of everything below: M = 256 = 128 rows of A per CTA, each CTA holds HALF of
+// B's N columns — rank 0 the lower half —, both CTAs' TMA loads complete their bytes on the leader's mbarrier, commits are multicast.)
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// wait with acquire at cluster scope: the arrivals / transaction bytes may come from the peer CTA
+__device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, 0x989680;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    if (mbar_try_cluster(bar, parity)) return;
+    uint32_t spins = 0;
+    while (!mbar_try_cluster(bar, parity)) {
+        if (++spins > 2000u) __trap();
+    }
+}
+template <int CG>
+__device__ __forceinline__ void mbar_wait_cg(uint32_t bar, uint32_t parity) {
+    if (CG == 2) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+}
+__device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+template <int CG>
+__device__ __forceinline__ void umma_f16_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if (CG == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    else
+        umma_f16(tmem_d, adesc, bdesc, idesc, acc);
+}
+template <int CG>
+__device__ __forceinline__ void umma_f8_cg(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    if (CG == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+    else
+        umma_f8(tmem_d, adesc, bdesc, idesc, acc);
+}
+// commit: for a pair the arrival is multicast to the barrier at the same offset in both CTAs
+template <int CG>
+__device__ __forceinline__ void umma_commit_cg(uint32_t bar) {
+    if (CG == 2)
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"((uint16_t)3) : "memory");
+    else
+        umma_commit(bar);
+}
+// 2-D tensor-map TMA load of this CTA's part of a pair's tile; the bytes complete on the LEADER's barrier (peer bit of the address cleared)
+__device__ __forceinline__ void tma2d_pair(uint32_t dst, const void *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(dst), "l"(map),
+                 "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu)
+                 : "memory");
+}
 
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14),
 // LBO>>4 [16,30) = bytes between K-adjacent core matrices, SBO>>4 [32,46) = bytes between M/N-adjacent core

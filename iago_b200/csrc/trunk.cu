@@ -28,9 +28,11 @@
 //   * Heads: policy = per-row dot with conv9 (fp32, CUDA cores) in the layer-8 epilogue (+bias10, optional
 //     softmax); value = block9 as a ninth MMA layer with N padded to 16, then relu and the collapsed
 //     fc11*fc10 64-vector.
+#include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_fp8.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <vector>
@@ -44,9 +46,9 @@ namespace iago {
 #ifdef IAGO_TRUNK_TRACE
 // debug build only (tools/trace_trunk.py): SM clock at the pipeline's hand-over points of CTA 0, first tiles
 __device__ unsigned long long g_trace[4096];
-#define TRACE(tile_, l_, ev_) do { if (blockIdx.x == 0 && (tile_) < 4 * (long long)gridDim.x) g_trace[(((tile_) / gridDim.x) * 9 + (l_)) * 8 + (ev_)] = clock64(); } while (0)
-#define TRACEM(tile_, l_, u_, i_) do { if (blockIdx.x == 0 && (tile_) == (long long)gridDim.x && (l_) == 2 && (u_) == 5) g_trace[3072 + (i_)] = clock64(); } while (0)
-#define TRACEU(tile_, l_, u_, ev_) do { if (blockIdx.x == 0 && (tile_) == (long long)gridDim.x && (l_) == 2) g_trace[2048 + (u_) * 4 + (ev_)] = clock64(); } while (0)
+#define TRACE(tile_, l_, ev_) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile_) < 4 * (long long)gridDim.x) g_trace[(((tile_) / gridDim.x) * 9 + (l_)) * 8 + (ev_)] = clock64(); } while (0)
+#define TRACEM(tile_, l_, u_, i_) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile_) == (long long)gridDim.x && (l_) == 2 && (u_) == 5) g_trace[3072 + (i_)] = clock64(); } while (0)
+#define TRACEU(tile_, l_, u_, ev_) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile_) == (long long)gridDim.x && (l_) == 2) g_trace[2048 + (u_) * 8 + (ev_)] = clock64(); } while (0)
 #else
 #define TRACE(tile_, l_, ev_) do { } while (0)
 #define TRACEU(tile_, l_, u_, ev_) do { } while (0)
@@ -60,10 +62,16 @@ constexpr int kRowPitch = 10 * 16;                // 160 B between consecutive 8
 constexpr int kActBytes = 16 * kGroupBytes;       // 128 channels: 51,200 B per precision part
 constexpr int kA1Bytes = 4 * kTileRows * 16;      // layer-1 explicit im2col tile, K = 32: 8,192 B
 constexpr int kStageBytes = 32768;                // one weight unit: hi [8][128][8] + lo
-constexpr int kStages = 3;                        // (a fourth stage was measured: no change — the issuer, not the ring, paces a layer)
+constexpr int kStages = 3;                        // one producer warp (9, 10, 11) per ring stage
+static_assert(kStages == 3, "the producer warps are numbered by ring stage");
+// 2-D tensor maps (256-byte rows) over a pair-layout weight blob, one per half-unit size: 64 rows (16 KB: the 128-channel layers),
+// 16 rows (4 KB: layer 1), 8 rows (2 KB: the value head's block9)
+struct alignas(64) TrunkMaps {
+    CUtensorMap m[3];
+};
 constexpr int kMaxLayers = 9;
 constexpr int kEpiThreads = 256;                  // warps 0-7
-constexpr int kThreads = 320;                     // + warp 8 producer, warp 9 MMA issuer
+constexpr int kThreads = 384;                     // + warp 8 MMA issuer, warps 9-11 weight producers (one per ring stage)
 constexpr int kTmemCols = 512;                    // two 128-column fp32 accumulators + two for the FP8 cross terms (precision 2)
 constexpr int kCrossCol = 256;                    // first TMEM column of the cross-term accumulators
 constexpr int kA8Bytes = 8 * kGroupBytes;         // an FP8 activation tile: 8 groups of 16 channels = 25,600 B; A8 | AL8 share OFF_ALO
@@ -76,7 +84,8 @@ constexpr int OFF_BIAS = OFF_STAGE + kStages * kStageBytes;   // float [9][128]
 constexpr int OFF_HEAD = OFF_BIAS + kMaxLayers * 128 * 4;      // float w9[128], b10[64], wfc[64]
 constexpr int OFF_SCRATCH = OFF_HEAD + 256 * 4;                // float [2][128] partial dots + [2][64] logits
 constexpr int OFF_BAR = OFF_SCRATCH + 384 * 4;                 // mbarriers + tmem pointer
-constexpr int kSmemBytes = OFF_BAR + 128;
+constexpr int kSmemBytes = OFF_BAR + 256;
+constexpr int kMaxStages = 6;                      // barrier slots: a CTA pair runs 6 stages of 16 KB (its half of a unit), a single CTA 3 of 32 KB
 
 struct LayerDesc {
     int n_units;     // weight units (tap x 64-channel chunk), consumed in order
@@ -171,8 +180,13 @@ __device__ __forceinline__ void store_act32_p2(uint8_t *smem, const float (&x)[3
     }
 }
 
+template <int CG>
+__device__ __forceinline__ void arrive_leader(uint32_t bar) {
+    if (CG == 2) mbar_arrive_cluster(bar); else mbar_arrive(bar);
+}
+
 // Thread layout: warps 0-7 epilogue (warp w reads TMEM lanes 32*(w%4)..; warps 0-3 take columns [0,32)+[64,96),
-// warps 4-7 take [32,64)+[96,128)), warp 8 = weight producer, warp 9 = MMA issuer.
+// warps 4-7 take [32,64)+[96,128)), warp 8 = MMA issuer (also allocates TMEM), warps 9-11 = weight producers.
 //
 // Pipeline per tile (DESIGN.md "trunk pipeline"): the accumulator is double-buffered in TMEM (layer l uses buffer
 // l&1) and weight units are ordered chunk-major, so the MMAs of layer l+1 on input channels 0..63 start as soon as
@@ -182,20 +196,35 @@ __device__ __forceinline__ void store_act32_p2(uint8_t *smem, const float (&x)[3
 // chain layer i is the transposed, tap-flipped conv of block 8-i in bf16 hi/lo; the tile entering the chain is read from
 // HBM (dy_in), every layer's output is gated by the sign of the forward activation (mask[i]) and written to HBM (dump[i])
 // for the weight-gradient kernel as well as to the activation tile for the next chain layer.
-template <int MODE>
-__global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const NetDesc *__restrict__ gnet) {
+//
+// CG = 2: two CTAs of a cluster (one TPC) work as a pair on 4 boards: every MMA is cta_group::2 with M = 256 (128 rows of A = 2 boards per
+// CTA) and each CTA holds only ITS HALF of a weight unit's output channels (rank 0: 0..N/2-1), loaded by 2-D tensor-map TMA whose bytes
+// complete on the leader's "full" barrier.  The same 96 KB ring is then SIX units deep instead of three and each SM ingests half the
+// weight bytes — the L2 -> shared-memory latency of a unit (≈ 1,000 cycles end to end) is what paced precision 2 with a 3-deep ring.
+// The leader's warp 8 issues for the pair; commits are multicast to both CTAs; the epilogue threads of both CTAs arrive on the leader's
+// "activations written" barriers (tools/micro/umma2_check.cu is the known-answer test of these mechanisms).  Forward only.
+template <int MODE, int CG>
+__global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constant__ TrunkArgs a, const __grid_constant__ NetDesc net,
+                                                            const __grid_constant__ TrunkMaps maps) {
+    static_assert(CG == 1 || (CG == 2 && MODE == 0), "the CTA-pair path is the forward kernel only");
     extern __shared__ __align__(1024) uint8_t smem[];
-    __shared__ NetDesc net;
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x;
+    const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;          // 0 = leader
+    constexpr int kRing = CG == 2 ? 6 : kStages;                      // ring stages
+    constexpr int kRingBytes = kStageBytes / CG;                      // bytes per stage
+    // The producer and issuer warps run their loops with all 32 lanes (warp-uniform control flow, one lane elected for the TMA / tcgen05
+    // instructions): the compiler then keeps descriptors and barrier addresses in uniform registers.  With the role branch on a single
+    // lane ((tid & 31) == 0) every UTCHMMA was wrapped in an R2UR + ELECT + BRA.U.ANY waterfall and the issuing thread, not the tensor
+    // pipe, paced the layer (700 cycles per precision-2 unit against 512 of MMA time).  The shuffle makes `warp` provably uniform.
+    const int warp = __shfl_sync(0xFFFFFFFFu, tid >> 5, 0);
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar_full = sbase + OFF_BAR, bar_empty = bar_full + 8 * kStages;
-    const uint32_t bar_acc = bar_empty + 8 * kStages;  // [2] accumulator buffer complete
+    const uint32_t bar_full = sbase + OFF_BAR, bar_empty = bar_full + 8 * kMaxStages;
+    const uint32_t bar_acc = bar_empty + 8 * kMaxStages;  // [2] accumulator buffer complete
     const uint32_t bar_act = bar_acc + 16;              // [2] input channels 0..63 / 64..127 of the next layer written
     const uint32_t bar_a1 = bar_act + 16;               // layer-1 im2col tile written, TMEM buffer 0 drained
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 * (2 * kStages + 5));
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 * (2 * kMaxStages + 5));
 
     // ---- one-time setup
-    for (int i = tid; i < (int)(sizeof(NetDesc) / 4); i += kThreads) reinterpret_cast<int *>(&net)[i] = reinterpret_cast<const int *>(gnet)[i];
     for (int i = tid; i < (OFF_A1 + kA1Bytes) / 16; i += kThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
     __syncthreads();
     if (MODE == 0) {
@@ -205,183 +234,222 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
         for (int i = tid; i < 256; i += kThreads) sh[i] = a.head[i];
     }
     if (tid == 0) {
-        for (int s = 0; s < kStages; s++) {
+        for (int s = 0; s < kRing; s++) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
         mbar_init(bar_acc + 8, 1);
-        mbar_init(bar_act, kEpiThreads);
-        mbar_init(bar_act + 8, kEpiThreads);
-        mbar_init(bar_a1, kEpiThreads);
+        // one arrival per epilogue warp (each thread fences its own writes, the warp synchronises, lane 0 arrives); pair: the warps of
+        // both CTAs arrive on the leader's barriers
+        mbar_init(bar_act, CG * (kEpiThreads / 32));
+        mbar_init(bar_act + 8, CG * (kEpiThreads / 32));
+        mbar_init(bar_a1, CG * (kEpiThreads / 32));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 8) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CG == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     fence_async_smem();
     tc_fence_before();
-    __syncthreads();
+    if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: the peer's barriers are initialised before anything arrives on them
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
     long long n_pos = a.n;
-    if (a.n_dev) n_pos = min(n_pos, (long long)*a.n_dev);
-    const long long n_tiles = (n_pos + 1) / 2;
+    if (a.n_dev) n_pos = min(n_pos, (long long)__shfl_sync(0xFFFFFFFFu, *a.n_dev, 0));   // (the shuffle tells the compiler the bound is warp-uniform)
+    const long long n_tiles = (n_pos + 2 * CG - 1) / (2 * CG);   // a tile = 2 boards per CTA (4 per pair)
+    const long long tile0 = blockIdx.x / CG, tile_step = gridDim.x / CG;   // CTAs 2i, 2i+1 form cluster i
     const int L = net.n_layers;
     const bool split = a.precision >= 3;
     const bool p2 = MODE == 0 && a.precision == 2;   // fp16 main product + FP8 cross terms in the second accumulator
 
-    if (warp == 8) {
-        // ================= producer: stream weight units L2 -> smem ring =================
-        if ((tid & 31) == 0) {
-            uint32_t stage = 0, phase = 0;
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int l = 0; l < L; l++) {
-                    const LayerDesc ld = net.layer[l];
-                    const uint8_t *src = a.blob + net.unit_base[l];
-                    const uint32_t bytes = (split || p2) ? (uint32_t)ld.unit_bytes : (uint32_t)ld.lo_off;  // single pass needs hi only
-                    for (int u = 0; u < ld.n_units; u++) {
+    if (warp >= 9) {
+        // ================= producers: stream weight units L2 -> smem ring, one warp per ring stage =================
+        // A thread's wait-empty / expect_tx / cp.async.bulk round takes ≈ 0.3 µs whatever the copy size, and the rounds of ONE thread do
+        // not overlap (tools/micro/tma_stream.cu: 74-100 GB/s per SM with one producer thread at any ring depth, 145 with two, 215 with
+        // three) — so a single producer paced precision 1 / 2 at one unit per 0.3 µs.  Producer w owns ring stage w: it copies the units
+        // g = w, w + 3, ... of the kernel-wide unit sequence (all 32 lanes run the loop, one elected lane issues).
+        // Pair: producer w copies the units g = w, w + 3, ... into ring stage g mod 6 — this CTA's half of the unit, by tensor-map TMA.
+        const uint32_t my_turn = (uint32_t)(warp - 9);
+        uint32_t stage = 0, phase = 0, turn = 0;
+        for (long long tile = tile0; tile < n_tiles; tile += tile_step) {
+            for (int l = 0; l < L; l++) {
+                const uint8_t *src = a.blob + net.unit_base[l];
+                const uint32_t unit_bytes = (uint32_t)net.layer[l].unit_bytes;
+                const uint32_t bytes = (split || p2 || CG == 2) ? unit_bytes : (uint32_t)net.layer[l].lo_off;  // single pass needs hi only
+                const int nu = net.layer[l].n_units;
+                // pair: row (256 B) of this CTA's half of the layer's first unit, and the tensor map whose box is one half-unit
+                int row = (int)((net.unit_base[l] + (long long)rank * (unit_bytes / 2)) >> 8);
+                const void *map = &maps.m[net.layer[l].chunks == 0 ? 1 : net.layer[l].n == 16 ? 2 : 0];
+                for (int u = 0; u < nu; u++) {
+                    if (turn == my_turn) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                         TRACEU(tile, l, u, 0);
-                        mbar_expect_tx(bar_full + 8 * stage, bytes);
-                        bulk_g2s(sbase + OFF_STAGE + stage * kStageBytes, src, bytes, bar_full + 8 * stage);
+                        if (elect_one()) {
+                            if (CG == 2) {
+                                if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, bytes);   // both halves complete on the leader's barrier
+                                tma2d_pair(sbase + OFF_STAGE + stage * kRingBytes, map, 0, row, bar_full + 8 * stage);
+                            } else {
+                                mbar_expect_tx(bar_full + 8 * stage, bytes);
+                                bulk_g2s(sbase + OFF_STAGE + stage * kRingBytes, src, bytes, bar_full + 8 * stage);
+                            }
+                        }
                         TRACEU(tile, l, u, 1);
-                        src += ld.unit_bytes;
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
                     }
+                    src += unit_bytes;
+                    row += (int)(unit_bytes >> 8);
+                    if (++turn == 3) turn = 0;
+                    if (++stage == kRing) { stage = 0; phase ^= 1; }
                 }
             }
         }
-    } else if (warp == 9) {
-        // ================= MMA issuer: one thread =================
-        if ((tid & 31) == 0) {
-            uint32_t stage = 0, phase = 0, act_phase[2] = {0, 0}, a1_phase = 0;
-            const uint32_t hiA = (uint32_t)(kRowPitch >> 4) | (1u << 14), hiB = (uint32_t)(128 >> 4) | (1u << 14);   // high words: SBO + version
-            const uint64_t desc_hi_a = ((uint64_t)(kRowPitch >> 4) << 32) | (1ULL << 46);  // SBO + version; LBO/start in the low word
-            const uint64_t desc_hi_b = ((uint64_t)(128 >> 4) << 32) | (1ULL << 46);
-            for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                for (int l = 0; l < L; l++) {
-                    const LayerDesc ld = net.layer[l];
-                    const uint32_t idesc = MODE == 0 ? instr_desc(kTileRows, ld.n) : instr_desc_bf16(kTileRows, ld.n);
-                    const uint32_t d_tmem = tmem + (uint32_t)(l & 1) * 128u;
-                    const uint32_t b_step = (uint32_t)(2 * ld.b_lbo) >> 4;              // descriptor units (16 B) per K=16 step
-                    const uint32_t b_lo_word = ((uint32_t)(ld.b_lbo >> 4) << 16);
-                    uint32_t acc = 0, acc_x = 0;
-                    if (MODE == 0 && ld.chunks == 0) {
-                        // layer 1: explicit im2col tile [4][128][16 B], LBO = 2048, SBO = 128
-                        mbar_wait(bar_a1, a1_phase);
-                        a1_phase ^= 1;
-                        mbar_wait(bar_full + 8 * stage, phase);
-                        tc_fence_after();
-                        const uint32_t bst = sbase + OFF_STAGE + stage * kStageBytes;
-                        const uint64_t a1_hi = ((uint64_t)(128 >> 4) << 32) | (1ULL << 46);
-                        uint32_t aw = ((sbase + OFF_A1) >> 4) | ((uint32_t)((kTileRows * 16) >> 4) << 16);
-                        uint32_t bw = (bst >> 4) | b_lo_word, blw = ((bst + ld.lo_off) >> 4) | b_lo_word;
-                        for (int ks = 0; ks < ld.ksteps; ks++) {
-                            umma_f16(d_tmem, a1_hi | aw, desc_hi_b | bw, idesc, acc);
-                            acc = 1;
-                            if (split || p2) umma_f16(d_tmem, a1_hi | aw, desc_hi_b | blw, idesc, 1);  // inputs are exactly 0/1: no lo part
-                            aw += (2 * kTileRows * 16) >> 4; bw += b_step; blw += b_step;
+    } else if (warp == 8) {
+        // ================= MMA issuer (pair: the leader's warp issues for both CTAs, the peer's warp 8 has nothing to do)
+        // the whole warp runs the loop, one elected lane issues the MMAs and commits
+        if (rank == 0) {
+        uint32_t stage = 0, phase = 0, act_phase0 = 0, act_phase1 = 0, a1_phase = 0;
+        const uint32_t hiA = (uint32_t)(kRowPitch >> 4) | (1u << 14), hiB = (uint32_t)(128 >> 4) | (1u << 14);   // high words: SBO + version
+        for (long long tile = tile0; tile < n_tiles; tile += tile_step) {
+            for (int l = 0; l < L; l++) {
+                const int ld_n = net.layer[l].n, ld_chunks = net.layer[l].chunks;
+                const int ld_lo_off = net.layer[l].lo_off / CG, ld_b_lbo = net.layer[l].b_lbo / CG;   // pair: this CTA's half of the unit's N
+                const uint32_t idesc = MODE == 0 ? instr_desc(kTileRows * CG, ld_n) : instr_desc_bf16(kTileRows * CG, ld_n);
+                const uint32_t d_tmem = tmem + (uint32_t)(l & 1) * 128u;
+                const uint32_t b_step = (uint32_t)(2 * ld_b_lbo) >> 4;              // descriptor units (16 B) per K=16 step
+                const uint32_t b_lo_word = ((uint32_t)(ld_b_lbo >> 4) << 16);
+                if (MODE == 0 && ld_chunks == 0) {
+                    // layer 1: explicit im2col tile [4][128][16 B], LBO = 2048, SBO = 128; K = 32 = two steps
+                    mbar_wait_cg<CG>(bar_a1, a1_phase);
+                    a1_phase ^= 1;
+                    mbar_wait_cg<CG>(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t bst = sbase + OFF_STAGE + stage * kRingBytes;
+                    const uint32_t a1_hiw = (uint32_t)(128 >> 4) | (1u << 14);
+                    const uint32_t aw = ((sbase + OFF_A1) >> 4) | ((uint32_t)((kTileRows * 16) >> 4) << 16);
+                    const uint32_t bw = (bst >> 4) | b_lo_word, blw = ((bst + ld_lo_off) >> 4) | b_lo_word;
+                    constexpr uint32_t dA1 = (2 * kTileRows * 16) >> 4;
+                    if (elect_one()) {
+#pragma unroll
+                        for (int ks = 0; ks < 2; ks++) {
+                            const uint64_t da = pack64(aw + ks * dA1, a1_hiw);
+                            if (ks == 0) umma_f16_cg<CG>(d_tmem, da, pack64(bw, hiB), idesc, 0); else umma_f16_cg<CG>(d_tmem, da, pack64(bw + b_step, hiB), idesc, 1);
+                            if (split || p2) umma_f16_cg<CG>(d_tmem, da, pack64(blw + ks * b_step, hiB), idesc, 1);  // inputs are exactly 0/1: no lo part
                         }
-                        umma_commit(bar_empty + 8 * stage);
-                        if (++stage == kStages) { stage = 0; phase ^= 1; }
-                    } else {
-                        // The units of the layer as one software-pipelined stream: the wait for the NEXT unit's weights (and, at a chunk
-                        // boundary, for the next 64 input channels) is taken while this unit's last MMA group is still to be issued and
-                        // the earlier ones are queued, and the commit that frees a ring stage is issued after the first MMA of the
-                        // following unit — so the tensor pipe sees no gap between units (≈ 165 cycles per unit before).
-                        const uint32_t a_lo_word = ((uint32_t)(kGroupBytes >> 4) << 16);
-                        const int n_units = 9 * ld.chunks;
-                        mbar_wait(bar_act, act_phase[0]);  // input channels 0..63 are written
-                        act_phase[0] ^= 1;
-                        tc_fence_after();
-                        TRACE(tile, l, 0);
-                        mbar_wait(bar_full + 8 * stage, phase);
-                        tc_fence_after();
-                        int pending = -1;   // ring stage whose commit is still to be issued
+                        umma_commit_cg<CG>(bar_empty + 8 * stage);
+                    }
+                    if (++stage == kRing) { stage = 0; phase ^= 1; }
+                } else {
+                    // The units of the layer as one software-pipelined stream: the wait for the NEXT unit's weights (and, at a chunk
+                    // boundary, for the next 64 input channels) is taken while this unit's last MMA group is still to be issued and
+                    // the earlier ones are queued, and the commit that frees a ring stage is issued after the first MMA of the
+                    // following unit — so the tensor pipe sees no gap between units.
+                    const uint32_t a_lo_word = ((uint32_t)(kGroupBytes >> 4) << 16);
+                    mbar_wait_cg<CG>(bar_act, act_phase0);  // input channels 0..63 are written
+                    act_phase0 ^= 1;
+                    tc_fence_after();
+                    TRACE(tile, l, 0);
+                    mbar_wait_cg<CG>(bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    uint32_t prev_bar = 0;   // ring stage barrier whose commit is still to be issued (0 = none)
+                    uint32_t acc = 0;
+                    // Straight-line issue per unit: every MMA's descriptor is (a uniform-register low word + a constant, constant high word), and
+                    // a unit is ONE elected region: first MMA group, the
+                    // deferred commit of the previous unit's ring stage, the look-ahead waits (taken by the issuing lane itself while those
+                    // MMAs are queued), last MMA group.  (Two elected regions per unit with the waits between them cost ≈ 110 cycles more.)
+                    constexpr uint32_t dA = (2 * kGroupBytes) >> 4;
+                    for (int chunk = 0; chunk < ld_chunks; chunk++) {
+                        const uint32_t a_hi_base = sbase + OFF_AHI + (uint32_t)chunk * 8 * kGroupBytes, a_lo_base = sbase + OFF_ALO + (uint32_t)chunk * 8 * kGroupBytes;
+                        const uint32_t a8_base = sbase + OFF_ALO + (uint32_t)chunk * 4 * kGroupBytes;   // FP8 tiles: 16 channels per group
+                        const bool last_chunk = chunk + 1 == ld_chunks;
 #pragma unroll 1
-                        for (int u = 0; u < n_units; u++) {
-                            const int chunk = u >= 9 ? 1 : 0, tap = u - chunk * 9;
+                        for (int tap = 0; tap < 9; tap++) {   // (unrolling the taps made the issuer's loop ≈ 40 KB of code and 10-25 % slower: instruction fetch)
                             const int ky = tap / 3, kx = tap - ky * 3;  // (dy,dx) = (ky-1,kx-1); the halo sits at padded index 0
-                            const uint32_t off = (uint32_t)chunk * 8 * kGroupBytes + (uint32_t)(ky * 20 + kx) * 16;
+                            const uint32_t off = (uint32_t)(ky * 20 + kx) * 16;
+                            const int u = chunk * 9 + tap;
+                            (void)u;
                             TRACEU(tile, l, u, 2);
-                            const uint32_t bst = sbase + OFF_STAGE + stage * kStageBytes;
-                            const uint32_t ahw = ((sbase + OFF_AHI + off) >> 4) | a_lo_word, alw = ((sbase + OFF_ALO + off) >> 4) | a_lo_word;
-                            const uint32_t bw = (bst >> 4) | b_lo_word, blw = ((bst + ld.lo_off) >> 4) | b_lo_word;
+                            const uint32_t bst = sbase + OFF_STAGE + stage * kRingBytes;
+                            const uint32_t ahw = ((a_hi_base + off) >> 4) | a_lo_word, alw = ((a_lo_base + off) >> 4) | a_lo_word;
+                            const uint32_t a8w = ((a8_base + off) >> 4) | a_lo_word, al8w = ((a8_base + kA8Bytes + off) >> 4) | a_lo_word;
+                            const uint32_t bw = (bst >> 4) | b_lo_word, blw = ((bst + ld_lo_off) >> 4) | b_lo_word;
+                            const uint32_t wl8w = ((bst + ld_lo_off + (ld_lo_off >> 1)) >> 4) | b_lo_word;   // precision 2: W8 sits at blw, WL8 after it
                             uint32_t nstage = stage + 1, nphase = phase;
-                            if (nstage == kStages) { nstage = 0; nphase ^= 1; }
-                            auto look_ahead = [&]() {
-                                if (u + 1 < n_units) {
-                                    if (tap == 8) {   // the next unit starts the second chunk
-                                        mbar_wait(bar_act + 8, act_phase[1]);
-                                        act_phase[1] ^= 1;
-                                        TRACE(tile, l, 1);
+                            if (nstage == kRing) { nstage = 0; nphase ^= 1; }
+                            const bool more = !(tap == 8 && last_chunk);
+                            if (elect_one()) {
+                                // ---- first MMA group
+                                if (split) {
+#pragma unroll
+                                    for (int ks = 0; ks < 3; ks++) {
+                                        const uint64_t da = pack64(ahw + ks * dA, hiA), dal = pack64(alw + ks * dA, hiA);
+                                        const uint64_t db = pack64(bw + ks * b_step, hiB), dbl = pack64(blw + ks * b_step, hiB);
+                                        if (ks == 0) umma_f16_cg<CG>(d_tmem, da, db, idesc, acc); else umma_f16_cg<CG>(d_tmem, da, db, idesc, 1);
+                                        umma_f16_cg<CG>(d_tmem, da, dbl, idesc, 1);
+                                        umma_f16_cg<CG>(d_tmem, dal, db, idesc, 1);
+                                        if (ks == 0 && prev_bar) umma_commit_cg<CG>(prev_bar);  // the previous unit's stage (covers these MMAs too: harmless)
                                     }
-                                    mbar_wait(bar_full + 8 * nstage, nphase);
+                                } else if (p2) {
+                                    // FP8 tiles: 16 channels per 16-byte row, so a 64-channel chunk is 4 groups and one K = 32 MMA spans two of them —
+                                    // the same descriptor stepping as fp16
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ks++) {
+                                        const uint64_t da = pack64(ahw + ks * dA, hiA), db = pack64(bw + ks * b_step, hiB);
+                                        if (ks == 0) umma_f16_cg<CG>(d_tmem, da, db, idesc, acc); else umma_f16_cg<CG>(d_tmem, da, db, idesc, 1);
+                                        if (ks == 0 && prev_bar) umma_commit_cg<CG>(prev_bar);
+                                    }
+                                    umma_f8_cg<CG>(d_tmem + kCrossCol, pack64(al8w, hiA), pack64(blw, hiB), idesc, acc);
+                                    umma_f8_cg<CG>(d_tmem + kCrossCol, pack64(a8w, hiA), pack64(wl8w, hiB), idesc, 1);
+                                } else {
+#pragma unroll
+                                    for (int ks = 0; ks < 3; ks++) {
+                                        const uint64_t da = pack64(ahw + ks * dA, hiA), db = pack64(bw + ks * b_step, hiB);
+                                        if (ks == 0) umma_f16_cg<CG>(d_tmem, da, db, idesc, acc); else umma_f16_cg<CG>(d_tmem, da, db, idesc, 1);
+                                        if (ks == 0 && prev_bar) umma_commit_cg<CG>(prev_bar);
+                                    }
+                                }
+                                // ---- look-ahead: the next unit's weights (and, at the chunk boundary, the next 64 input channels)
+                                if (more) {
+                                    if (tap == 8) mbar_wait_cg<CG>(bar_act + 8, act_phase1);
+                                    mbar_wait_cg<CG>(bar_full + 8 * nstage, nphase);
                                     tc_fence_after();
                                 }
-                            };
-                            // Straight-line issue per precision mode: the four descriptor low words of the unit are computed once, every
-                            // MMA's descriptor is (low word + a constant, constant high word) — a micro-benchmark (tools/micro/umma_rate.cu)
-                            // shows the tensor pipe takes one 128x128x16 MMA per 64 cycles when the issuing thread is this lean, and 97-170
-                            // when it recomputes descriptors and branches between MMAs, which is what paced this kernel before.
-                            constexpr uint32_t dA = (2 * kGroupBytes) >> 4;
-                            const bool commit_prev = pending >= 0;
-                            const uint32_t prev_bar = bar_empty + 8 * (uint32_t)(pending < 0 ? 0 : pending);
-                            if (split) {
-#pragma unroll
-                                for (int ks = 0; ks < 4; ks++) {
-                                    if (ks == 3) look_ahead();
-                                    const uint64_t da = pack64(ahw + ks * dA, hiA), dal = pack64(alw + ks * dA, hiA);
-                                    const uint64_t db = pack64(bw + ks * b_step, hiB), dbl = pack64(blw + ks * b_step, hiB);
-                                    if (ks == 0) umma_f16(d_tmem, da, db, idesc, acc); else umma_f16(d_tmem, da, db, idesc, 1);
-                                    umma_f16(d_tmem, da, dbl, idesc, 1);
-                                    umma_f16(d_tmem, dal, db, idesc, 1);
-                                    if (ks == 0 && commit_prev) umma_commit(prev_bar);  // the previous unit's stage (covers these MMAs too: harmless)
+                                // ---- last MMA group
+                                if (split) {
+                                    const uint64_t da = pack64(ahw + 3 * dA, hiA), dal = pack64(alw + 3 * dA, hiA);
+                                    const uint64_t db = pack64(bw + 3 * b_step, hiB), dbl = pack64(blw + 3 * b_step, hiB);
+                                    umma_f16_cg<CG>(d_tmem, da, db, idesc, 1);
+                                    umma_f16_cg<CG>(d_tmem, da, dbl, idesc, 1);
+                                    umma_f16_cg<CG>(d_tmem, dal, db, idesc, 1);
+                                } else if (p2) {
+                                    umma_f8_cg<CG>(d_tmem + kCrossCol, pack64(al8w + dA, hiA), pack64(blw + b_step, hiB), idesc, 1);
+                                    umma_f8_cg<CG>(d_tmem + kCrossCol, pack64(a8w + dA, hiA), pack64(wl8w + b_step, hiB), idesc, 1);
+                                } else {
+                                    umma_f16_cg<CG>(d_tmem, pack64(ahw + 3 * dA, hiA), pack64(bw + 3 * b_step, hiB), idesc, 1);
                                 }
-                            } else if (p2) {
-                                // FP8 tiles: 16 channels per 16-byte row, so a 64-channel chunk is 4 groups and one K = 32 MMA spans two
-                                // of them — the same descriptor stepping as fp16.  Weights: W8 = e4m3(w_hi * sw) at lo_off, WL8 after it.
-                                const uint32_t off8 = (uint32_t)chunk * 4 * kGroupBytes + (uint32_t)(ky * 20 + kx) * 16;
-                                const uint32_t a8w = ((sbase + OFF_ALO + off8) >> 4) | a_lo_word, al8w = ((sbase + OFF_ALO + kA8Bytes + off8) >> 4) | a_lo_word;
-                                const uint32_t wl8w = ((bst + ld.lo_off + (ld.lo_off >> 1)) >> 4) | b_lo_word;   // (W8 sits at blw)
-#pragma unroll
-                                for (int ks = 0; ks < 4; ks++) {
-                                    const uint64_t da = pack64(ahw + ks * dA, hiA), db = pack64(bw + ks * b_step, hiB);
-                                    if (ks == 0) umma_f16(d_tmem, da, db, idesc, acc); else umma_f16(d_tmem, da, db, idesc, 1);
-                                    if (ks == 0 && commit_prev) umma_commit(prev_bar);
-                                }
-#pragma unroll
-                                for (int ks = 0; ks < 2; ks++) {
-                                    if (ks == 1) look_ahead();
-                                    const uint64_t da8 = pack64(a8w + ks * dA, hiA), dal8 = pack64(al8w + ks * dA, hiA);
-                                    const uint64_t dw8 = pack64(blw + ks * b_step, hiB), dwl8 = pack64(wl8w + ks * b_step, hiB);
-                                    if (ks == 0) umma_f8(d_tmem + kCrossCol, dal8, dw8, idesc, acc_x); else umma_f8(d_tmem + kCrossCol, dal8, dw8, idesc, 1);
-                                    umma_f8(d_tmem + kCrossCol, da8, dwl8, idesc, 1);
-                                }
-                                acc_x = 1;
-                            } else {
-#pragma unroll
-                                for (int ks = 0; ks < 4; ks++) {
-                                    if (ks == 3) look_ahead();
-                                    const uint64_t da = pack64(ahw + ks * dA, hiA), db = pack64(bw + ks * b_step, hiB);
-                                    if (ks == 0) umma_f16(d_tmem, da, db, idesc, acc); else umma_f16(d_tmem, da, db, idesc, 1);
-                                    if (ks == 0 && commit_prev) umma_commit(prev_bar);
-                                }
+                            }
+                            if (tap == 8 && more) {
+                                act_phase1 ^= 1;
+                                TRACE(tile, l, 1);
                             }
                             acc = 1;
                             TRACEU(tile, l, u, 3);
-                            pending = (int)stage;
+                            prev_bar = bar_empty + 8 * stage;
                             stage = nstage; phase = nphase;
                         }
-                        umma_commit(bar_empty + 8 * pending);  // frees the last weight stage of the layer when its MMAs retire
                     }
-                    umma_commit(bar_acc + 8 * (l & 1));  // accumulator of this layer complete
-                    TRACE(tile, l, 2);
+                    if (elect_one()) umma_commit_cg<CG>(prev_bar);  // frees the last weight stage of the layer when its MMAs retire
                 }
+                if (elect_one()) umma_commit_cg<CG>(bar_acc + 8 * (l & 1));  // accumulator of this layer complete
+                TRACE(tile, l, 2);
             }
+        }
         }
     } else {
         // ================= epilogue warps: thread pair (m, m+128) owns tile row m = TMEM lane m =================
@@ -394,8 +462,10 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
         float *scratch = reinterpret_cast<float *>(smem + OFF_SCRATCH);   // [2][128] partial dots / [2][64] logits
         const int cell = r * 8 + c;
         uint32_t acc_phase[2] = {0, 0};
-        for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-            const long long pos = tile * 2 + b;
+        // the barriers the issuer waits on are the leader's: a pair's peer CTA arrives on them through the cluster address
+        const uint32_t act_leader = CG == 2 ? mapa_rank(bar_act, 0) : bar_act, a1_leader = CG == 2 ? mapa_rank(bar_a1, 0) : bar_a1;
+        for (long long tile = tile0; tile < n_tiles; tile += tile_step) {
+            const long long pos = (tile * CG + rank) * 2 + b;
             const bool valid = pos < n_pos;
             if (MODE == 1) {
                 // ---- chain entry: the gradient tile [128 channels][cell] of this row's position -> bf16 hi/lo activation tile
@@ -409,7 +479,8 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                     store_act32<true>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
                     fence_async_smem();
                     tc_fence_before();
-                    mbar_arrive(bar_act + 8 * ps);
+                    __syncwarp();
+                    if ((tid & 31) == 0) arrive_leader<CG>(act_leader + 8 * ps);
                 }
             } else {
             // ---- layer-1 input: explicit im2col of the two bit planes, k = tap*2 + channel (0 = opponent, 1 = mover)
@@ -444,7 +515,8 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                 }
                 fence_async_smem();
                 tc_fence_before();
-                mbar_arrive(bar_a1);
+                __syncwarp();
+                if ((tid & 31) == 0) arrive_leader<CG>(a1_leader);
             }
 
             for (int l = 0; l < L; l++) {
@@ -480,7 +552,8 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                             store_act32<true>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
                             fence_async_smem();
                             tc_fence_before();
-                            mbar_arrive(bar_act + 8 * ps);
+                            __syncwarp();
+                            if ((tid & 31) == 0) arrive_leader<CG>(act_leader + 8 * ps);
                         }
                     }
                 } else if (l < 8) {
@@ -516,7 +589,8 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                             else store_act32<false>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
                             fence_async_smem();
                             tc_fence_before();
-                            mbar_arrive(bar_act + 8 * ps);  // input channels [64*ps, 64*ps+64) of the next layer are in place
+                            __syncwarp();
+                            if ((tid & 31) == 0) arrive_leader<CG>(act_leader + 8 * ps);  // input channels [64*ps, 64*ps+64) of the next layer are in place
                             if (tid == 0) TRACE(tile, l, 4 + ps);
                         }
                     }
@@ -555,7 +629,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
                             float s = scratch[warp * 64 + (tid & 31)] + scratch[warp * 64 + 32 + (tid & 31)];
 #pragma unroll
                             for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, o);
-                            const long long p = tile * 2 + warp;
+                            const long long p = (tile * CG + rank) * 2 + warp;
                             if ((tid & 31) == 0 && p < n_pos) a.out[p] = s;
                         }
                         asm volatile("bar.sync 2, 128;" ::: "memory");
@@ -568,8 +642,11 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
 
     // ---- teardown
     tc_fence_before();
-    __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: no CTA leaves (or frees TMEM) while the other may still be addressed
+    if (warp == 8) {
+        if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
+    }
 }
 
 // ---------------------------------------------------------------- host side: packing + launch
@@ -577,15 +654,18 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(TrunkArgs a, const N
 struct NetSlot {
     bool loaded = false;
     NetDesc desc;
-    NetDesc *d_desc = nullptr;
     uint8_t *d_blob = nullptr;
     uint8_t *d_blob2 = nullptr;   // precision 2: fp16 hi block | W8 | WL8 per unit (nullptr after a device-side refresh: precision 2 then runs as 3)
+    // CTA-pair layout of the same two blobs (every unit as [rank 0's half of the output channels | rank 1's half]) and their tensor maps;
+    // nullptr after a device-side refresh: the slot then runs on the single-CTA kernel
+    uint8_t *d_pair = nullptr, *d_pair2 = nullptr;
+    TrunkMaps maps, maps2;
     float *d_bias = nullptr;
     float *d_head = nullptr;
 };
 
 struct TrunkState {
-    NetSlot slot[8];
+    NetSlot slot[IAGO_NET_SLOTS];
     bool attr_set = false;
 };
 
@@ -595,7 +675,7 @@ static TrunkState *state(iago_ctx *ctx) {
 }
 
 bool trunk_slot_holds(iago_ctx *ctx, int slot, int kind) {
-    if (slot < 0 || slot >= 8 || !ctx->trunk) return false;
+    if (slot < 0 || slot >= IAGO_NET_SLOTS || !ctx->trunk) return false;
     const NetSlot &s = static_cast<TrunkState *>(ctx->trunk)->slot[slot];
     return s.loaded && s.desc.kind == kind;
 }
@@ -604,9 +684,10 @@ void trunk_destroy(iago_ctx *ctx) {
     if (!ctx->trunk) return;
     TrunkState *st = static_cast<TrunkState *>(ctx->trunk);
     for (auto &s : st->slot) {
-        cudaFree(s.d_desc);
         cudaFree(s.d_blob);
         cudaFree(s.d_blob2);
+        cudaFree(s.d_pair);
+        cudaFree(s.d_pair2);
         cudaFree(s.d_bias);
         cudaFree(s.d_head);
     }
@@ -657,6 +738,43 @@ static void pack_unit_p2(std::vector<uint8_t> &blob, int kgroups, int n_pad, flo
             }
 }
 
+// Pair layout: the unit as two halves of its output channels, each a complete (hi | lo) or (hi | W8 | WL8) unit of n_pad / 2 columns.
+template <class F>
+static void pack_unit_pair(std::vector<uint8_t> &blob, int kgroups, int n_pad, F get) {
+    for (int h = 0; h < 2; h++) pack_unit(blob, kgroups, n_pad / 2, [&](int n, int k) { return get(h * (n_pad / 2) + n, k); });
+}
+template <class F>
+static void pack_unit_p2_pair(std::vector<uint8_t> &blob, int kgroups, int n_pad, float sw, F get) {
+    for (int h = 0; h < 2; h++) pack_unit_p2(blob, kgroups, n_pad / 2, sw, [&](int n, int k) { return get(h * (n_pad / 2) + n, k); });
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Tensor maps over a pair-layout blob seen as rows of 256 bytes; box = one half-unit (64, 16 or 8 rows).
+static int make_maps(uint8_t *d_blob, size_t bytes, TrunkMaps &out) {
+    static EncodeTiledFn encode = nullptr;
+    if (!encode) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", (void **)&encode, cudaEnableDefault, &q) != cudaSuccess || !encode) {
+            set_error("cuTensorMapEncodeTiled is not available from this driver");
+            return IAGO_E_CUDA;
+        }
+    }
+    const cuuint32_t rows[3] = {64, 16, 8};
+    for (int i = 0; i < 3; i++) {
+        const cuuint64_t gdim[2] = {256, (cuuint64_t)(bytes / 256)}, gstride[1] = {256};
+        const cuuint32_t box[2] = {256, rows[i]}, estr[2] = {1, 1};
+        const CUresult r = encode(&out.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d_blob, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                  CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled failed (%d)", (int)r);
+            return IAGO_E_CUDA;
+        }
+    }
+    return IAGO_OK;
+}
+
 // sw: the power of two that brings the layer's largest |weight| into [128, 256) (E4M3 tops out at 448)
 static float fp8_weight_scale(const float *w, size_t count) {
     float mx = 0.0f;
@@ -679,7 +797,7 @@ extern "C" {
 
 int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_t n_floats) {
     IAGO_REQUIRE(ctx && params, "NULL argument");
-    IAGO_REQUIRE(slot >= 0 && slot < 8, "slot out of range (0..7)");
+    IAGO_REQUIRE(slot >= 0 && slot < IAGO_NET_SLOTS, "slot out of range (0..IAGO_NET_SLOTS-1)");
     IAGO_REQUIRE(kind == 0 || kind == 1, "kind must be 0 (SL policy) or 1 (value)");
     const int cin[8] = {2, 64, 128, 128, 128, 128, 128, 128}, cout[8] = {64, 128, 128, 128, 128, 128, 128, 128};
     int64_t need = 0;
@@ -695,7 +813,7 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
     memset(&d, 0, sizeof d);
     d.kind = kind;
     d.n_layers = kind == 0 ? 8 : 9;
-    std::vector<uint8_t> blob, blob2;
+    std::vector<uint8_t> blob, blob2, pair, pair2;
     std::vector<float> bias((size_t)kMaxLayers * 128, 0.0f), head(256, 0.0f);
     const float *p = params;
     for (int l = 0; l < 8; l++) {
@@ -709,8 +827,11 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
         if (l == 0) {
             // explicit im2col: k = tap*2 + channel, K padded 18 -> 32
             ld.n_units = 1; ld.ksteps = 2; ld.chunks = 0;
-            pack_unit(blob, 4, ld.n, [&](int n, int k) { return k < 18 ? W[((size_t)n * 2 + (k & 1)) * 9 + (k >> 1)] : 0.0f; });
-            pack_unit(blob2, 4, ld.n, [&](int n, int k) { return k < 18 ? W[((size_t)n * 2 + (k & 1)) * 9 + (k >> 1)] : 0.0f; });  // layer 1: fp16 hi / lo in both blobs
+            auto w1 = [&](int n, int k) { return k < 18 ? W[((size_t)n * 2 + (k & 1)) * 9 + (k >> 1)] : 0.0f; };
+            pack_unit(blob, 4, ld.n, w1);
+            pack_unit(blob2, 4, ld.n, w1);  // layer 1: fp16 hi / lo in both blobs
+            pack_unit_pair(pair, 4, ld.n, w1);
+            pack_unit_pair(pair2, 4, ld.n, w1);
             ld.cscale = 0.0f;
             ld.lo_off = 4 * ld.n * 16;
         } else {
@@ -719,8 +840,11 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
             ld.cscale = 1.0f / (2048.0f * sw);
             for (int ch = 0; ch < ld.chunks; ch++)  // chunk-major: all taps of input channels 0..63 first
                 for (int tap = 0; tap < 9; tap++) {
-                    pack_unit(blob, 8, ld.n, [&](int n, int k) { return W[((size_t)n * cin[l] + ch * 64 + k) * 9 + tap]; });
-                    pack_unit_p2(blob2, 8, ld.n, sw, [&](int n, int k) { return W[((size_t)n * cin[l] + ch * 64 + k) * 9 + tap]; });
+                    auto wl = [&](int n, int k) { return W[((size_t)n * cin[l] + ch * 64 + k) * 9 + tap]; };
+                    pack_unit(blob, 8, ld.n, wl);
+                    pack_unit_p2(blob2, 8, ld.n, sw, wl);
+                    pack_unit_pair(pair, 8, ld.n, wl);
+                    pack_unit_p2_pair(pair2, 8, ld.n, sw, wl);
                 }
             ld.lo_off = 8 * ld.n * 16;
         }
@@ -738,8 +862,11 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
         ld.cscale = 1.0f / (2048.0f * sw9);
         for (int ch = 0; ch < 2; ch++)
             for (int tap = 0; tap < 9; tap++) {
-                pack_unit(blob, 8, 16, [&](int n, int k) { return n == 0 ? W9[(size_t)(ch * 64 + k) * 9 + tap] : 0.0f; });
-                pack_unit_p2(blob2, 8, 16, sw9, [&](int n, int k) { return n == 0 ? W9[(size_t)(ch * 64 + k) * 9 + tap] : 0.0f; });
+                auto w9 = [&](int n, int k) { return n == 0 ? W9[(size_t)(ch * 64 + k) * 9 + tap] : 0.0f; };
+                pack_unit(blob, 8, 16, w9);
+                pack_unit_p2(blob2, 8, 16, sw9, w9);
+                pack_unit_pair(pair, 8, 16, w9);
+                pack_unit_p2_pair(pair2, 8, 16, sw9, w9);
             }
         ld.lo_off = 8 * 16 * 16;
         ld.unit_bytes = 2 * ld.lo_off;
@@ -751,19 +878,23 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
             head[128 + j] = (float)acc;
         }
     }
-    if (blob2.size() != blob.size()) {
+    if (blob2.size() != blob.size() || pair.size() != blob.size() || pair2.size() != blob.size()) {
         set_error("iago_load_net: internal error, the two weight blobs differ in size");
         return IAGO_E_STATE;
     }
-    cudaFree(s.d_desc); cudaFree(s.d_blob); cudaFree(s.d_blob2); cudaFree(s.d_bias); cudaFree(s.d_head);
+    cudaFree(s.d_blob); cudaFree(s.d_blob2); cudaFree(s.d_pair); cudaFree(s.d_pair2); cudaFree(s.d_bias); cudaFree(s.d_head);
     s = NetSlot();
-    IAGO_CUDA(cudaMalloc(&s.d_desc, sizeof(NetDesc)));
+    IAGO_CUDA(cudaMalloc(&s.d_pair, pair.size()));
+    IAGO_CUDA(cudaMalloc(&s.d_pair2, pair2.size()));
+    IAGO_CUDA(cudaMemcpy(s.d_pair, pair.data(), pair.size(), cudaMemcpyHostToDevice));
+    IAGO_CUDA(cudaMemcpy(s.d_pair2, pair2.data(), pair2.size(), cudaMemcpyHostToDevice));
+    if (int rc = make_maps(s.d_pair, pair.size(), s.maps)) return rc;
+    if (int rc = make_maps(s.d_pair2, pair2.size(), s.maps2)) return rc;
     IAGO_CUDA(cudaMalloc(&s.d_blob, blob.size()));
     IAGO_CUDA(cudaMalloc(&s.d_blob2, blob2.size()));
     IAGO_CUDA(cudaMemcpy(s.d_blob2, blob2.data(), blob2.size(), cudaMemcpyHostToDevice));
     IAGO_CUDA(cudaMalloc(&s.d_bias, bias.size() * 4));
     IAGO_CUDA(cudaMalloc(&s.d_head, head.size() * 4));
-    IAGO_CUDA(cudaMemcpy(s.d_desc, &d, sizeof d, cudaMemcpyHostToDevice));
     IAGO_CUDA(cudaMemcpy(s.d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice));
     IAGO_CUDA(cudaMemcpy(s.d_bias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
     IAGO_CUDA(cudaMemcpy(s.d_head, head.data(), head.size() * 4, cudaMemcpyHostToDevice));
@@ -775,10 +906,19 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
 }  // extern "C"
 
 namespace iago {
+static int set_trunk_attrs(TrunkState *st) {
+    if (st->attr_set) return IAGO_OK;
+    IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    st->attr_set = true;
+    return IAGO_OK;
+}
+
 int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
                  int64_t n, float *out, int out_kind, int precision, void *stream, const int *n_dev, float *const *dump) {
     IAGO_REQUIRE(ctx && p1 && p2 && color && out, "NULL argument");
-    IAGO_REQUIRE(slot >= 0 && slot < 8, "slot out of range (0..7)");
+    IAGO_REQUIRE(slot >= 0 && slot < IAGO_NET_SLOTS, "slot out of range (0..IAGO_NET_SLOTS-1)");
     IAGO_REQUIRE(n >= 0, "n < 0");
     IAGO_REQUIRE(precision >= 1 && precision <= 3, "precision must be 1 (fp16), 2 (fp16 + FP8 cross terms) or 3 (fp16 hi/lo split)");
     TrunkState *st = state(ctx);
@@ -789,22 +929,38 @@ int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, con
     }
     if (n == 0) return IAGO_OK;
     DeviceGuard guard(ctx->device);
-    if (!st->attr_set) {
-        IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        st->attr_set = true;
-    }
-    const long long tiles = (n + 1) / 2;
-    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    if (int rc = set_trunk_attrs(st)) return rc;
+    // CTA pairs (4 boards per cluster) whenever the slot has the pair-layout blobs and no activations are dumped; IAGO_TRUNK_CG1=1 forces
+    // the single-CTA kernel (A/B measurements)
+    static const bool force_cg1 = getenv("IAGO_TRUNK_CG1") != nullptr;
+    const bool pairs = s.d_pair && !dump && !force_cg1;
+    const long long tiles = pairs ? (n + 3) / 4 : (n + 1) / 2;
+    const long long max_groups = pairs ? ctx->sm_count / 2 : ctx->sm_count;
+    const int grid = (int)(tiles < max_groups ? tiles : max_groups) * (pairs ? 2 : 1);
     if (precision == 2 && (!s.d_blob2 || dump)) precision = 3;   // a slot refreshed from device parameters has no FP8 blob; the trainer's forward keeps full accuracy
     TrunkArgs a{(const u64 *)p1, (const u64 *)p2, color, n, out, out_kind, precision, precision == 2 ? s.d_blob2 : s.d_blob, s.d_bias, s.d_head, n_dev, {}, nullptr, {}};
+    if (pairs) a.blob = precision == 2 ? s.d_pair2 : s.d_pair;
     for (int l = 0; l < 8; l++) a.dump[l] = dump ? dump[l] : nullptr;
     cudaStream_t cs = (cudaStream_t)stream;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(cs, &cap);
     const bool timed = cap == cudaStreamCaptureStatusNone;   // the timing events of iago_last_kernel_ms stay out of captured graphs (mcts.cu)
     if (timed) IAGO_CUDA(cudaEventRecord(ctx->ev0, cs));
-    trunk_kernel<0><<<grid, kThreads, kSmemBytes, cs>>>(a, s.d_desc);
+    if (pairs) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = kSmemBytes;
+        cfg.stream = cs;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        IAGO_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<0, 2>, a, s.desc, precision == 2 ? s.maps2 : s.maps));
+    } else {
+        trunk_kernel<0, 1><<<grid, kThreads, kSmemBytes, cs>>>(a, s.desc, TrunkMaps{});
+    }
     IAGO_CUDA(cudaGetLastError());
     if (timed) {
         IAGO_CUDA(cudaEventRecord(ctx->ev1, cs));
@@ -880,7 +1036,7 @@ __global__ void pack_value_head_kernel(const float *__restrict__ hp /* W9[1152] 
 
 int trunk_refresh_slot(iago_ctx *ctx, int slot, int kind, const float *d_params, void *stream) {
     IAGO_REQUIRE(ctx && d_params, "NULL argument");
-    IAGO_REQUIRE(slot >= 0 && slot < 8, "slot out of range (0..7)");
+    IAGO_REQUIRE(slot >= 0 && slot < IAGO_NET_SLOTS, "slot out of range (0..IAGO_NET_SLOTS-1)");
     NetSlot &s = state(ctx)->slot[slot];
     if (!s.loaded || s.desc.kind != kind) {
         set_error("net slot %d holds no network of kind %d to refresh (call iago_load_net once first)", slot, kind);
@@ -891,6 +1047,11 @@ int trunk_refresh_slot(iago_ctx *ctx, int slot, int kind, const float *d_params,
     if (s.d_blob2) {   // the FP8 blob is only built by iago_load_net (it needs a per-layer max |w|): precision 2 runs as 3 on this slot from now on
         cudaFree(s.d_blob2);
         s.d_blob2 = nullptr;
+    }
+    if (s.d_pair) {    // so are the pair-layout blobs: the slot runs on the single-CTA kernel from now on
+        cudaFree(s.d_pair);
+        cudaFree(s.d_pair2);
+        s.d_pair = s.d_pair2 = nullptr;
     }
     size_t off = 0;
     for (int l = 0; l < 8; l++) {
@@ -931,42 +1092,44 @@ __global__ void pack_dgrad_kernel(const float *__restrict__ W, uint8_t *__restri
     unit[half_elems + off] = l;
 }
 
-int trunk_backward_pack(iago_ctx *ctx, const float *const *W /* W[l], l = 1..7: [128][cin_l][3][3] on the device */, uint8_t *blob,
-                        void *desc_dev, void *stream) {
+// The chain's layer table (a function of the architecture alone; passed to the kernel by value).
+static NetDesc backward_desc() {
     NetDesc d;
     memset(&d, 0, sizeof d);
     d.n_layers = 7;
     d.kind = 2;
     size_t off = 0;
-    cudaStream_t cs = (cudaStream_t)stream;
     for (int i = 0; i < 7; i++) {
         const int l = 7 - i, cin = l == 1 ? 64 : 128;
         LayerDesc &ld = d.layer[i];
         ld.n_units = 18; ld.ksteps = 4; ld.n = cin; ld.lo_off = 8 * cin * 16; ld.unit_bytes = 2 * ld.lo_off; ld.b_lbo = cin * 16; ld.chunks = 2;
         d.unit_base[i] = (long long)off;
-        const int total = 2 * 9 * 8 * cin * 8;
-        pack_dgrad_kernel<<<(total + 255) / 256, 256, 0, cs>>>(W[l], blob + off, cin);
         off += (size_t)18 * ld.unit_bytes;
     }
+    return d;
+}
+
+int trunk_backward_pack(iago_ctx *ctx, const float *const *W /* W[l], l = 1..7: [128][cin_l][3][3] on the device */, uint8_t *blob,
+                        void *stream) {
+    const NetDesc d = backward_desc();
+    cudaStream_t cs = (cudaStream_t)stream;
+    for (int i = 0; i < 7; i++) {
+        const int l = 7 - i, cin = l == 1 ? 64 : 128;
+        const int total = 2 * 9 * 8 * cin * 8;
+        pack_dgrad_kernel<<<(total + 255) / 256, 256, 0, cs>>>(W[l], blob + d.unit_base[i], cin);
+    }
     IAGO_CUDA(cudaGetLastError());
-    if (desc_dev) IAGO_CUDA(cudaMemcpyAsync(desc_dev, &d, sizeof d, cudaMemcpyHostToDevice, cs));
     (void)ctx;
     return IAGO_OK;
 }
 
-size_t trunk_desc_bytes() { return sizeof(NetDesc); }
-
-int trunk_backward_launch(iago_ctx *ctx, const void *desc_dev, const uint8_t *blob, const float *dy_in, const float *const *mask,
+int trunk_backward_launch(iago_ctx *ctx, const uint8_t *blob, const float *dy_in, const float *const *mask,
                           float *const *dx_out, int64_t n, int precision, void *stream) {
-    IAGO_REQUIRE(ctx && desc_dev && blob && dy_in && mask && dx_out, "NULL argument");
+    IAGO_REQUIRE(ctx && blob && dy_in && mask && dx_out, "NULL argument");
     IAGO_REQUIRE(precision == 1 || precision == 3, "precision must be 1 (bf16) or 3 (bf16 hi/lo split)");
     if (n <= 0) return IAGO_OK;
     TrunkState *st = state(ctx);
-    if (!st->attr_set) {
-        IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        st->attr_set = true;
-    }
+    if (int rc = set_trunk_attrs(st)) return rc;
     const long long tiles = (n + 1) / 2;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
     TrunkArgs a{nullptr, nullptr, nullptr, n, nullptr, 0, precision, blob, nullptr, nullptr, nullptr, {}, dy_in, {}};
@@ -976,7 +1139,7 @@ int trunk_backward_launch(iago_ctx *ctx, const void *desc_dev, const uint8_t *bl
     }
     a.dump[7] = nullptr;
     a.mask[7] = nullptr;
-    trunk_kernel<1><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, static_cast<const NetDesc *>(desc_dev));
+    trunk_kernel<1, 1><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, backward_desc(), TrunkMaps{});
     IAGO_CUDA(cudaGetLastError());
     return IAGO_OK;
 }

@@ -62,6 +62,7 @@ class Engine:
         check(self.lib.iago_ctx_create(self.device, C.byref(ctx)))
         self.ctx = ctx
         self._keep = []
+        self._slot_owner = {}   # net slot -> owner tag; slots handed out by alloc_slot() (facade models, trainers)
 
     def close(self):
         if getattr(self, "ctx", None):
@@ -86,9 +87,28 @@ class Engine:
             pre = "predictor/" if "predictor/conv1/W" in z.files else ""
             self.load_rollout(z[pre + "conv1/W"], z[pre + "bias2/b"])
 
-    def load_net(self, slot, params, kind=None):
-        """SLPolicy / Value weights into a resident slot (0..7). `params`: dict in the reference's npz key layout, or a path."""
+    N_SLOTS = 32   # IAGO_NET_SLOTS of include/iago_b200.h
+
+    def alloc_slot(self, owner):
+        """A free net slot for `owner` (any hashable tag), highest numbers first so that explicit low slot numbers used by scripts
+        stay free.  Raises when all slots are taken: a model object never silently overwrites another object's weights."""
+        for s in range(self.N_SLOTS - 1, -1, -1):
+            if s not in self._slot_owner:
+                self._slot_owner[s] = owner
+                return s
+        raise _lib.IagoError(f"all {self.N_SLOTS} net slots of device {self.device} are in use; close() a model or trainer to free one")
+
+    def free_slot(self, slot, owner=None):
+        if slot in self._slot_owner and (owner is None or self._slot_owner[slot] == owner):
+            del self._slot_owner[slot]
+
+    def load_net(self, slot, params, kind=None, owner=None):
+        """SLPolicy / Value weights into a resident slot. `params`: dict in the reference's npz key layout, or a path.
+        A slot handed out by alloc_slot() can only be (re)loaded by its owner."""
         from . import npz
+        held = self._slot_owner.get(int(slot))
+        if held is not None and held != owner:
+            raise _lib.IagoError(f"net slot {slot} belongs to {held!r}; use another slot or alloc_slot()")
         if isinstance(params, (str, bytes)) or hasattr(params, "__fspath__"):
             params = npz.read_npz(params)
         kind = npz.detect_kind(params) if kind is None else kind

@@ -15,7 +15,7 @@ import numpy as np
 from . import npz
 from .engine import default_engine
 
-_slots = itertools.count()
+_ids = itertools.count()
 _W = (np.uint64(1) << np.arange(64, dtype=np.uint64))
 
 
@@ -45,17 +45,29 @@ class _TrunkNet:
 
     def __init__(self, device=0, precision=3):
         self.device, self.precision = device, precision
-        self.slot = next(_slots) % 8
+        self._tag = f"{type(self).__name__}#{next(_ids)}"
+        self.slot = default_engine(device).alloc_slot(self._tag)   # owned until close() / garbage collection; raises when none is free
         self.params = None
+
+    def close(self):
+        if getattr(self, "slot", None) is not None:
+            default_engine(self.device).free_slot(self.slot, self._tag)
+            self.slot = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def load(self, path):
         self.params = npz.read_npz(path)
-        default_engine(self.device).load_net(self.slot, self.params, self.kind)
+        default_engine(self.device).load_net(self.slot, self.params, self.kind, owner=self._tag)
         return self
 
     def load_params(self, params):
         self.params = {k: np.asarray(v, np.float32) for k, v in params.items()}
-        default_engine(self.device).load_net(self.slot, self.params, self.kind)
+        default_engine(self.device).load_net(self.slot, self.params, self.kind, owner=self._tag)
         return self
 
 

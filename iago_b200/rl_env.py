@@ -12,7 +12,10 @@ sampling step runs on the GPU (iago_env_step, iago_legal_actions, iago_place_sto
 Randomness: the reference draws the opponent's moves from the global np.random (one uniform per attempt, re-drawn until
 legal, rl_env.py:167-171) and the learner's illegal-move fallback from Python's `random` (rl_env.py:46-48).  Here both come
 from one explicit stream per environment (Philox keyed by seed / env id, or `uniforms=` to replay np.random's draws);
-the fallback takes positions[floor(u * len)].
+the fallback takes positions[floor(u * len)].  Like the reference's global generators, the stream keeps advancing across
+episodes: reset() does NOT rewind `draws` (a gym-style loop that resets per episode would otherwise face the same opponent
+draws every episode); in replay mode (`uniforms=`) the supplied stream is likewise consumed across resets and must be long
+enough for all episodes (the kernel bound-checks it).  `reseed(seed, env_id0)` starts a fresh stream explicitly.
 """
 import itertools
 
@@ -42,7 +45,15 @@ class VecGameEnv:
         self.eng = default_engine(device)
         self.model2 = _net(model2)
         self.seed, self.env_id0, self._uniforms = seed, env_id0, uniforms
+        self.draws = torch.zeros(self.n, dtype=torch.int32, device=torch.device("cuda", device))   # position in each environment's stream
         self.reset()
+
+    def reseed(self, seed, env_id0=None):
+        """A fresh Philox stream (draw index back to 0)."""
+        self.seed = seed
+        if env_id0 is not None:
+            self.env_id0 = env_id0
+        self.draws.zero_()
 
     def _rng(self):
         if self._uniforms is not None:
@@ -59,8 +70,7 @@ class VecGameEnv:
         self.p2 = torch.full((self.n,), boards.START_P2, dtype=torch.int64, device=dev)
         self.stone_num = torch.full((self.n,), 4, dtype=torch.int32, device=dev)
         self.pass_flg = torch.zeros(self.n, dtype=torch.uint8, device=dev)
-        self.draws = torch.zeros(self.n, dtype=torch.int32, device=dev)
-        return self.p1, self.p2
+        return self.p1, self.p2   # `draws` is deliberately left alone: the random stream continues (rl_env.py draws from the global np.random)
 
     def step(self, actions):
         a = torch.as_tensor(actions, dtype=torch.int8).to(self.p1.device).contiguous()

@@ -22,9 +22,13 @@ N_PARAMS = npz.N_PARAMS[npz.KIND_VALUE]
 
 class ValueTrainer:
     def __init__(self, params=None, alpha=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=5e-4, max_positions=MINIBATCH, device=0,
-                 slot=7, precision=3, group=None, tensor_cores=True, dropout=0.4, seed=0):
+                 slot=None, precision=3, group=None, tensor_cores=True, dropout=0.4, seed=0):
         self.eng = default_engine(device)
         self.lib = self.eng.lib
+        self._tag = f"ValueTrainer@{id(self):x}"
+        self._own_slot = slot is None   # None: a free slot from the engine's allocator (released by close()); a number: the caller's slot
+        if slot is None:
+            slot = self.eng.alloc_slot(self._tag)
         self.device, self.slot, self.precision, self.group = device, slot, precision, group
         self.hp = dict(alpha=alpha, beta1=beta1, beta2=beta2, eps=eps, weight_decay=weight_decay)
         self.dropout, self.seed, self.records = float(dropout), int(seed), 0
@@ -44,6 +48,9 @@ class ValueTrainer:
         if getattr(self, "h", None):
             self.lib.iago_reinforce_destroy(self.h)
             self.h = None
+        if getattr(self, "_own_slot", False) and getattr(self, "slot", None) is not None:
+            self.eng.free_slot(self.slot, self._tag)
+            self.slot = None
 
     def __del__(self):
         try:

@@ -50,6 +50,9 @@ enum {
 
 typedef struct iago_ctx iago_ctx;
 
+/* Resident SLPolicy / Value weight sets per context (net "slots"). */
+#define IAGO_NET_SLOTS 32
+
 /* How a game draws its moves.  Exactly one uniform is consumed per stone placed and none per pass
  * (mcts_self_play.py:100-110 -> np.random.choice -> one random_sample()). */
 enum {
@@ -132,7 +135,8 @@ IAGO_API int iago_rollout_logits(iago_ctx *ctx, const uint64_t *p1, const uint64
  *   block3..8/conv/W [128][128][3][3], b [128],
  *   kind 0 (SLPolicy, 960,768 floats): conv9/W [1][128][1][1], bias10/b [64]
  *   kind 1 (Value,    970,049 floats): block9/conv/W [1][128][3][3], block9/conv/b [1], fc10/W [128][64], fc11/W [1][128]
- * The fp16 hi/lo split and the tensor-core operand layout are produced inside.  slot in 0..7. */
+ * The fp16 hi/lo split and the tensor-core operand layout are produced inside.  slot in 0..IAGO_NET_SLOTS-1
+ * (a loaded slot holds about 15 MB of device memory: four operand layouts of the 3.8 MB weight set). */
 IAGO_API int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_t n_floats);
 
 /* SLPolicy.__call__ on make_state_var(state, color) for n positions given as bitboards.

@@ -17,11 +17,11 @@ for prec in (3, 1, 2):
     buf = np.zeros(4096, np.uint64)
     eng.lib.iago_debug_trace(C.c_void_p(buf.ctypes.data), 4096)
     t = buf.reshape(-1, 8)[:4 * 9].reshape(4, 9, 8).astype(np.int64)
-    u = buf[2048:2048 + 72].reshape(18, 4).astype(np.int64)
+    u = buf[2048:2048 + 144].reshape(18, 8).astype(np.int64)
     base = u[0, 2]
     print(f"precision {prec}: units of tile 1 layer 2 (cycles from the issuer's first 'full'): producer empty-ready, tma issued | issuer full-ready, commit issued")
     for i in range(18):
-        print(f"   unit {i:2d}: producer {u[i, 0] - base:7d} {u[i, 1] - base:7d} | issuer {u[i, 2] - base:7d} {u[i, 3] - base:7d}   (issue span {u[i, 3] - u[i, 2]:5d}, full-to-full {u[i, 2] - u[i - 1, 2] if i else 0:5d})")
+        print(f"   unit {i:2d}: producer {u[i, 0] - base:7d} {u[i, 1] - base:7d} | issuer {u[i, 2] - base:7d} {u[i, 3] - base:7d}   (issue span {u[i, 3] - u[i, 2]:5d} = first MMA group {u[i, 4] - u[i, 2]:4d} + look-ahead waits {u[i, 5] - u[i, 4]:4d} + last group {u[i, 3] - u[i, 5]:4d}; unit-to-unit {u[i, 2] - u[i - 1, 2] if i else 0:5d})")
     mm = buf[3072:3072 + 18].astype(np.int64)
     t0 = t[1, 0, 0]
     print(f"precision {prec}: cycles relative to tile 1 layer 0 (events: chunk0 go, chunk1 go, commit issued | acc ready, pass0 done, pass1 done)")

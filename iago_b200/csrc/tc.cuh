@@ -91,6 +91,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t &v) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr) : "memory");
 }
@@ -114,8 +123,11 @@ __device__ __forceinline__ uint32_t mapa_rank(uint32_t addr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
     return r;
 }
+// (the form CUTLASS's ClusterBarrier::arrive(cta_id) uses: default semantics.  An explicit .release.cluster costs ≈ 1,200 cycles per arrival
+// here — it drains the thread's writes to cluster scope — and is not needed: what the peer's epilogue threads wrote is read by the
+// tensor core through the async proxy, which fence.proxy.async has already been told about.)
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 // wait with acquire at cluster scope: the arrivals / transaction bytes may come from the peer CTA
 __device__ __forceinline__ bool mbar_try_cluster(uint32_t bar, uint32_t parity) {
@@ -136,9 +148,17 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         if (++spins > 2000u) __trap();
     }
 }
+// Non-blocking phase test: the result is needed only where it is consumed, so the barrier unit's round trip (≈ 100 cycles even for a
+// completed phase) overlaps whatever is issued in between.
+template <int CG>
+__device__ __forceinline__ uint32_t mbar_test_cg(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    return done;
+}
 template <int CG>
 __device__ __forceinline__ void mbar_wait_cg(uint32_t bar, uint32_t parity) {
-    if (CG == 2) mbar_wait_cluster(bar, parity); else mbar_wait(bar, parity);
+    mbar_wait(bar, parity);   // (CUTLASS's ClusterBarrier::wait is the same plain try_wait for 2-SM kernels; the .acquire.cluster form is slower)
 }
 __device__ __forceinline__ void fence_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 template <int CG>

@@ -48,10 +48,12 @@ namespace iago {
 __device__ unsigned long long g_trace[4096];
 #define TRACE(tile_, l_, ev_) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile_) < 4 * (long long)gridDim.x) g_trace[(((tile_) / gridDim.x) * 9 + (l_)) * 8 + (ev_)] = clock64(); } while (0)
 #define TRACEM(tile_, l_, u_, i_) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile_) == (long long)gridDim.x && (l_) == 2 && (u_) == 5) g_trace[3072 + (i_)] = clock64(); } while (0)
+#define TRACEE(tile_, l_, k_) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (tile_) == (long long)gridDim.x) g_trace[3072 + (l_) * 8 + (k_)] = clock64(); } while (0)
 #define TRACEU(tile_, l_, u_, ev_) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile_) == (long long)gridDim.x && (l_) == 2) g_trace[2048 + (u_) * 8 + (ev_)] = clock64(); } while (0)
 #else
 #define TRACE(tile_, l_, ev_) do { } while (0)
 #define TRACEU(tile_, l_, u_, ev_) do { } while (0)
+#define TRACEE(tile_, l_, k_) do { } while (0)
 #define TRACEM(tile_, l_, u_, i_) do { } while (0)
 #endif
 
@@ -70,8 +72,9 @@ struct alignas(64) TrunkMaps {
     CUtensorMap m[3];
 };
 constexpr int kMaxLayers = 9;
-constexpr int kEpiThreads = 256;                  // warps 0-7
-constexpr int kThreads = 384;                     // + warp 8 MMA issuer, warps 9-11 weight producers (one per ring stage)
+constexpr int kEpiThreads = 512;                  // warps 0-15: four threads per tile row, 16 of a pass's 64 output channels each
+constexpr int kIssuerWarp = kEpiThreads / 32;     // warp 16
+constexpr int kThreads = kEpiThreads + 128;        // + warp 16 MMA issuer, warps 17-19 weight producers
 constexpr int kTmemCols = 512;                    // two 128-column fp32 accumulators + two for the FP8 cross terms (precision 2)
 constexpr int kCrossCol = 256;                    // first TMEM column of the cross-term accumulators
 constexpr int kA8Bytes = 8 * kGroupBytes;         // an FP8 activation tile: 8 groups of 16 channels = 25,600 B; A8 | AL8 share OFF_ALO
@@ -82,8 +85,8 @@ constexpr int OFF_A1 = OFF_ALO + kActBytes;
 constexpr int OFF_STAGE = OFF_A1 + kA1Bytes;
 constexpr int OFF_BIAS = OFF_STAGE + kStages * kStageBytes;   // float [9][128]
 constexpr int OFF_HEAD = OFF_BIAS + kMaxLayers * 128 * 4;      // float w9[128], b10[64], wfc[64]
-constexpr int OFF_SCRATCH = OFF_HEAD + 256 * 4;                // float [2][128] partial dots + [2][64] logits
-constexpr int OFF_BAR = OFF_SCRATCH + 384 * 4;                 // mbarriers + tmem pointer
+constexpr int OFF_SCRATCH = OFF_HEAD + 256 * 4;                // float [4][128] partial dots + [2][64] logits
+constexpr int OFF_BAR = OFF_SCRATCH + 768 * 4;                 // mbarriers + tmem pointer
 constexpr int kSmemBytes = OFF_BAR + 256;
 constexpr int kMaxStages = 6;                      // barrier slots: a CTA pair runs 6 stages of 16 KB (its half of a unit), a single CTA 3 of 32 KB
 
@@ -122,12 +125,12 @@ struct TrunkArgs {
     const float *mask[8]; // mask[i]: [n][N_i][64] forward activation whose sign gates the output of chain layer i (ReLU backward)
 };
 
-// hi/lo split (fp16 in the forward, bf16 in the backward chain: gradients need the exponent range) of 32 values of this
-// thread's tile row, written as 4 channel groups of the activation tile.
+// hi/lo split (fp16 in the forward, bf16 in the backward chain: gradients need the exponent range) of 16 values of this
+// thread's tile row, written as 2 channel groups of the activation tile.
 template <bool BF16>
-__device__ __forceinline__ void store_act32(uint8_t *smem, const float (&x)[32], uint32_t group0_off, bool split) {
+__device__ __forceinline__ void store_act16(uint8_t *smem, const float (&x)[16], uint32_t group0_off, bool split) {
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < 2; q++) {
         uint32_t hw[4], lw[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
@@ -152,12 +155,12 @@ __device__ __forceinline__ void store_act32(uint8_t *smem, const float (&x)[32],
     }
 }
 
-// precision 2: 32 values of this thread's tile row -> fp16 hi parts (4 groups of 8 channels) and two FP8 tiles (2 groups of 16
-// channels each): A8 = e4m3(hi), AL8 = e4m3((x - hi) * 2^11).
-__device__ __forceinline__ void store_act32_p2(uint8_t *smem, const float (&x)[32], int col0, uint32_t row_off) {
-    uint32_t h8[8], l8[8];   // 32 FP8 values each
+// precision 2: 16 values of this thread's tile row -> fp16 hi parts (2 groups of 8 channels) and one 16-channel row of each FP8
+// tile: A8 = e4m3(hi), AL8 = e4m3((x - hi) * 2^11).
+__device__ __forceinline__ void store_act16_p2(uint8_t *smem, const float (&x)[16], int col0, uint32_t row_off) {
+    uint32_t h8[4], l8[4];   // 16 FP8 values each
 #pragma unroll
-    for (int q = 0; q < 4; q++) {
+    for (int q = 0; q < 2; q++) {
         uint32_t hw[4];
 #pragma unroll
         for (int e = 0; e < 4; e++) {
@@ -172,12 +175,9 @@ __device__ __forceinline__ void store_act32_p2(uint8_t *smem, const float (&x)[3
         }
         *reinterpret_cast<uint4 *>(smem + OFF_AHI + (uint32_t)((col0 >> 3) + q) * kGroupBytes + row_off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
     }
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const uint32_t off = (uint32_t)((col0 >> 4) + q) * kGroupBytes + row_off;
-        *reinterpret_cast<uint4 *>(smem + OFF_ALO + off) = make_uint4(h8[4 * q], h8[4 * q + 1], h8[4 * q + 2], h8[4 * q + 3]);
-        *reinterpret_cast<uint4 *>(smem + OFF_ALO + kA8Bytes + off) = make_uint4(l8[4 * q], l8[4 * q + 1], l8[4 * q + 2], l8[4 * q + 3]);
-    }
+    const uint32_t off = (uint32_t)(col0 >> 4) * kGroupBytes + row_off;
+    *reinterpret_cast<uint4 *>(smem + OFF_ALO + off) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
+    *reinterpret_cast<uint4 *>(smem + OFF_ALO + kA8Bytes + off) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
 }
 
 template <int CG>
@@ -185,8 +185,8 @@ __device__ __forceinline__ void arrive_leader(uint32_t bar) {
     if (CG == 2) mbar_arrive_cluster(bar); else mbar_arrive(bar);
 }
 
-// Thread layout: warps 0-7 epilogue (warp w reads TMEM lanes 32*(w%4)..; warps 0-3 take columns [0,32)+[64,96),
-// warps 4-7 take [32,64)+[96,128)), warp 8 = MMA issuer (also allocates TMEM), warps 9-11 = weight producers.
+// Thread layout: warps 0-15 epilogue (warp w reads TMEM lanes 32*(w%4)..; quarter q = w / 4 takes columns [16q, 16q+16) of each
+// 64-column pass), warp 16 = MMA issuer (also allocates TMEM), warps 17-19 = weight producers.
 //
 // Pipeline per tile (DESIGN.md "trunk pipeline"): the accumulator is double-buffered in TMEM (layer l uses buffer
 // l&1) and weight units are ordered chunk-major, so the MMAs of layer l+1 on input channels 0..63 start as soon as
@@ -247,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
         mbar_init(bar_a1, CG * (kEpiThreads / 32));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == kIssuerWarp) {
         if (CG == 2) {
             asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(kTmemCols) : "memory");
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
@@ -270,14 +270,14 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
     const bool split = a.precision >= 3;
     const bool p2 = MODE == 0 && a.precision == 2;   // fp16 main product + FP8 cross terms in the second accumulator
 
-    if (warp >= 9) {
+    if (warp > kIssuerWarp) {
         // ================= producers: stream weight units L2 -> smem ring, one warp per ring stage =================
         // A thread's wait-empty / expect_tx / cp.async.bulk round takes ≈ 0.3 µs whatever the copy size, and the rounds of ONE thread do
         // not overlap (tools/micro/tma_stream.cu: 74-100 GB/s per SM with one producer thread at any ring depth, 145 with two, 215 with
         // three) — so a single producer paced precision 1 / 2 at one unit per 0.3 µs.  Producer w owns ring stage w: it copies the units
         // g = w, w + 3, ... of the kernel-wide unit sequence (all 32 lanes run the loop, one elected lane issues).
         // Pair: producer w copies the units g = w, w + 3, ... into ring stage g mod 6 — this CTA's half of the unit, by tensor-map TMA.
-        const uint32_t my_turn = (uint32_t)(warp - 9);
+        const uint32_t my_turn = (uint32_t)(warp - kIssuerWarp - 1);
         uint32_t stage = 0, phase = 0, turn = 0;
         for (long long tile = tile0; tile < n_tiles; tile += tile_step) {
             for (int l = 0; l < L; l++) {
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                 }
             }
         }
-    } else if (warp == 8) {
+    } else if (warp == kIssuerWarp) {
         // ================= MMA issuer (pair: the leader's warp issues for both CTAs, the peer's warp 8 has nothing to do)
         // the whole warp runs the loop, one elected lane issues the MMAs and commits
         if (rank == 0) {
@@ -360,9 +360,9 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                     uint32_t prev_bar = 0;   // ring stage barrier whose commit is still to be issued (0 = none)
                     uint32_t acc = 0;
                     // Straight-line issue per unit: every MMA's descriptor is (a uniform-register low word + a constant, constant high word), and
-                    // a unit is ONE elected region: first MMA group, the
-                    // deferred commit of the previous unit's ring stage, the look-ahead waits (taken by the issuing lane itself while those
-                    // MMAs are queued), last MMA group.  (Two elected regions per unit with the waits between them cost ≈ 110 cycles more.)
+                    // a unit is ONE elected region: a non-blocking test of the next unit's "full" barrier, the MMAs (with the deferred commit of the
+                    // previous unit's ring stage after the first one) up to the last group, then the test's answer — a blocking wait only if the weights
+                    // have not landed —, then the last MMA group.  (Two elected regions per unit with blocking waits between them cost ≈ 110 + 100 cycles more per unit.)
                     constexpr uint32_t dA = (2 * kGroupBytes) >> 4;
                     for (int chunk = 0; chunk < ld_chunks; chunk++) {
                         const uint32_t a_hi_base = sbase + OFF_AHI + (uint32_t)chunk * 8 * kGroupBytes, a_lo_base = sbase + OFF_ALO + (uint32_t)chunk * 8 * kGroupBytes;
@@ -384,6 +384,8 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                             if (nstage == kRing) { nstage = 0; nphase ^= 1; }
                             const bool more = !(tap == 8 && last_chunk);
                             if (elect_one()) {
+                                // the next unit's weights: test now, look at the answer after this unit's MMAs are issued
+                                const uint32_t next_ready = (CG == 2 && more) ? mbar_test_cg<CG>(bar_full + 8 * nstage, nphase) : 0u;   // (single CTA, 3-deep ring: the copy has rarely landed this early and the extra test measured 8 % slower)
                                 // ---- first MMA group
                                 if (split) {
 #pragma unroll
@@ -414,10 +416,12 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                                         if (ks == 0 && prev_bar) umma_commit_cg<CG>(prev_bar);
                                     }
                                 }
-                                // ---- look-ahead: the next unit's weights (and, at the chunk boundary, the next 64 input channels)
+                                // ---- the waits, while the MMAs above are queued: at the chunk boundary the next 64 input channels; the next unit's
+                                // weights only if the early test failed.  The last MMA group is issued after them: it keeps the tensor pipe busy while
+                                // this thread goes round the loop (checking after ALL the unit's MMAs measured 10 % slower with the 3-deep ring).
                                 if (more) {
                                     if (tap == 8) mbar_wait_cg<CG>(bar_act + 8, act_phase1);
-                                    mbar_wait_cg<CG>(bar_full + 8 * nstage, nphase);
+                                    if (!next_ready) mbar_wait_cg<CG>(bar_full + 8 * nstage, nphase);
                                     tc_fence_after();
                                 }
                                 // ---- last MMA group
@@ -453,13 +457,13 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
         }
     } else {
         // ================= epilogue warps: thread pair (m, m+128) owns tile row m = TMEM lane m =================
-        const int m = tid & 127, half = tid >> 7;  // half 0: columns [0,32)+[64,96); half 1: [32,64)+[96,128)
+        const int m = tid & 127, qt = tid >> 7;    // quarter qt: columns [16 qt, 16 qt + 16) of each 64-column pass
         const int g = m >> 3, c = m & 7, r = g >> 1, b = g & 1;
         const uint32_t row_off = (uint32_t)(((r + 1) * 2 + b) * 10 + (c + 1)) * 16;  // interior cell of the padded tile
         const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
         const float *sbias = reinterpret_cast<const float *>(smem + OFF_BIAS);
         const float *shead = reinterpret_cast<const float *>(smem + OFF_HEAD);
-        float *scratch = reinterpret_cast<float *>(smem + OFF_SCRATCH);   // [2][128] partial dots / [2][64] logits
+        float *scratch = reinterpret_cast<float *>(smem + OFF_SCRATCH);   // [4][128] partial dots / [2][64] logits
         const int cell = r * 8 + c;
         uint32_t acc_phase[2] = {0, 0};
         // the barriers the issuer waits on are the leader's: a pair's peer CTA arrives on them through the cluster address
@@ -472,11 +476,11 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                 const float *src = a.dy_in + (size_t)pos * 128 * 64 + cell;
 #pragma unroll 1
                 for (int ps = 0; ps < 2; ps++) {
-                    const int col0 = ps * 64 + half * 32;
-                    float x[32];
+                    const int col0 = ps * 64 + qt * 16;
+                    float x[16];
 #pragma unroll
-                    for (int j = 0; j < 32; j++) x[j] = valid ? __ldg(src + (size_t)(col0 + j) * 64) : 0.0f;
-                    store_act32<true>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
+                    for (int j = 0; j < 16; j++) x[j] = valid ? __ldg(src + (size_t)(col0 + j) * 64) : 0.0f;
+                    store_act16<true>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
                     fence_async_smem();
                     tc_fence_before();
                     __syncwarp();
@@ -484,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                 }
             } else {
             // ---- layer-1 input: explicit im2col of the two bit planes, k = tap*2 + channel (0 = opponent, 1 = mover)
-                if (half == 0) {
+                if (qt == 0) {
                     u64 own = 0, opp = 0;
                     if (valid) {
                         const bool first = a.color[pos] == 1;
@@ -534,22 +538,22 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                     float *dst = a.dump[l] + ((size_t)pos * ld.n) * 64 + cell;
 #pragma unroll 1
                     for (int ps = 0; ps < passes; ps++) {
-                        const int col0 = ps * 64 + half * 32;
-                        float g[32];
+                        const int col0 = ps * 64 + qt * 16;
+                        float g[16];
 #pragma unroll
-                        for (int j = 0; j < 32; j++) g[j] = valid ? __ldg(mk + (size_t)(col0 + j) * 64) : 0.0f;   // in flight during the TMEM read
-                        uint32_t v[32];
-                        tmem_ld32(t_addr + col0, v);
+                        for (int j = 0; j < 16; j++) g[j] = valid ? __ldg(mk + (size_t)(col0 + j) * 64) : 0.0f;   // in flight during the TMEM read
+                        uint32_t v[16];
+                        tmem_ld16(t_addr + col0, v);
                         tmem_wait_ld();
-                        float x[32];
+                        float x[16];
 #pragma unroll
-                        for (int j = 0; j < 32; j++) x[j] = g[j] > 0.0f ? __uint_as_float(v[j]) : 0.0f;
+                        for (int j = 0; j < 16; j++) x[j] = g[j] > 0.0f ? __uint_as_float(v[j]) : 0.0f;
                         if (valid) {
 #pragma unroll
-                            for (int j = 0; j < 32; j++) dst[(size_t)(col0 + j) * 64] = x[j];
+                            for (int j = 0; j < 16; j++) dst[(size_t)(col0 + j) * 64] = x[j];
                         }
                         if (writes_act) {
-                            store_act32<true>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
+                            store_act16<true>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
                             fence_async_smem();
                             tc_fence_before();
                             __syncwarp();
@@ -560,50 +564,55 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                     float dot = 0.0f;
                     const int passes = ld.n / 64;  // 1 for the 64-channel layer, else 2
                     for (int ps = 0; ps < passes; ps++) {
-                        const int col0 = ps * 64 + half * 32;
-                        uint32_t v[32];
-                        tmem_ld32(t_addr + col0, v);
-                        tmem_wait_ld();
-                        float x[32];
+                        const int col0 = ps * 64 + qt * 16;
+                        uint32_t v[16];
+                        if (ps == 0) TRACEE(tile, l, 0);
+                        tmem_ld16(t_addr + col0, v);
+                        float x[16];
                         if (p2 && l > 0) {   // fold the FP8 cross-term accumulator in (layer 1 has none: its inputs are exactly 0 / 1)
-                            uint32_t vx[32];
-                            tmem_ld32(t_addr + kCrossCol + col0, vx);
+                            uint32_t vx[16];
+                            tmem_ld16(t_addr + kCrossCol + col0, vx);
                             tmem_wait_ld();
 #pragma unroll
-                            for (int j = 0; j < 32; j++) x[j] = fmaxf(fmaf(__uint_as_float(vx[j]), ld.cscale, __uint_as_float(v[j])) + sbias[l * 128 + col0 + j], 0.0f);
+                            for (int j = 0; j < 16; j++) x[j] = fmaxf(fmaf(__uint_as_float(vx[j]), ld.cscale, __uint_as_float(v[j])) + sbias[l * 128 + col0 + j], 0.0f);
                         } else {
+                            tmem_wait_ld();
 #pragma unroll
-                            for (int j = 0; j < 32; j++) x[j] = fmaxf(__uint_as_float(v[j]) + sbias[l * 128 + col0 + j], 0.0f);
+                            for (int j = 0; j < 16; j++) x[j] = fmaxf(__uint_as_float(v[j]) + sbias[l * 128 + col0 + j], 0.0f);
                         }
+                        if (ps == 0) TRACEE(tile, l, 1);
                         if (policy_head) {
 #pragma unroll
-                            for (int j = 0; j < 32; j++) dot = fmaf(x[j], shead[col0 + j], dot);
+                            for (int j = 0; j < 16; j++) dot = fmaf(x[j], shead[col0 + j], dot);
                         }
                         if (a.dump[l] != nullptr && valid) {
                             float *dst = a.dump[l] + ((size_t)pos * ld.n + col0) * 64 + cell;
 #pragma unroll
-                            for (int j = 0; j < 32; j++) dst[(size_t)j * 64] = x[j];
+                            for (int j = 0; j < 16; j++) dst[(size_t)j * 64] = x[j];
                         }
                         if (writes_act) {
-                            if (p2) store_act32_p2(smem, x, col0, row_off);
-                            else store_act32<false>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
+                            if (p2) store_act16_p2(smem, x, col0, row_off);
+                            else store_act16<false>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
+                            if (ps == 0) TRACEE(tile, l, 2);
                             fence_async_smem();
+                            if (ps == 0) TRACEE(tile, l, 3);
                             tc_fence_before();
                             __syncwarp();
                             if ((tid & 31) == 0) arrive_leader<CG>(act_leader + 8 * ps);  // input channels [64*ps, 64*ps+64) of the next layer are in place
+                            if (ps == 0) TRACEE(tile, l, 4);
                             if (tid == 0) TRACE(tile, l, 4 + ps);
                         }
                     }
                     if (policy_head) {
-                        // policy head: conv9 (1x1, no bias) + bias10[cell] (network.py:44-46); the row's two threads hold half each
-                        scratch[half * 128 + m] = dot;
-                        asm volatile("bar.sync 1, 256;" ::: "memory");
-                        if (half == 0) {
-                            const float logit = scratch[m] + scratch[128 + m] + shead[128 + cell];
+                        // policy head: conv9 (1x1, no bias) + bias10[cell] (network.py:44-46); the row's four threads hold a quarter each
+                        scratch[qt * 128 + m] = dot;
+                        asm volatile("bar.sync 1, 512;" ::: "memory");
+                        if (qt == 0) {
+                            const float logit = ((scratch[m] + scratch[128 + m]) + (scratch[256 + m] + scratch[384 + m])) + shead[128 + cell];
                             if (a.out_kind == 0) {
                                 if (valid) a.out[pos * 64 + cell] = logit;
                             } else {
-                                float *lg = scratch + 256;
+                                float *lg = scratch + 512;
                                 lg[b * 64 + cell] = logit;
                                 asm volatile("bar.sync 2, 128;" ::: "memory");
                                 float mx = -3.0e38f;
@@ -613,11 +622,11 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                                 if (valid) a.out[pos * 64 + cell] = __expf(logit - mx) / sum;
                             }
                         }
-                        asm volatile("bar.sync 1, 256;" ::: "memory");  // scratch is reused by the next tile
+                        asm volatile("bar.sync 1, 512;" ::: "memory");  // scratch is reused by the next tile
                     }
                 } else {
                     // value head: relu(block9 + b9) . (fc11 * fc10)  (network.py:92-95, dropout off)
-                    if (half == 0) {
+                    if (qt == 0) {
                         uint32_t v, vx = 0;
                         tmem_ld1(t_addr, v);
                         if (p2) tmem_ld1(t_addr + kCrossCol, vx);
@@ -643,7 +652,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
     // ---- teardown
     tc_fence_before();
     if (CG == 2) cluster_sync_all(); else __syncthreads();   // pair: no CTA leaves (or frees TMEM) while the other may still be addressed
-    if (warp == 8) {
+    if (warp == kIssuerWarp) {
         if (CG == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
         else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(kTmemCols) : "memory");
     }

@@ -21,11 +21,16 @@ for prec in (3, 1, 2):
     base = u[0, 2]
     print(f"precision {prec}: units of tile 1 layer 2 (cycles from the issuer's first 'full'): producer empty-ready, tma issued | issuer full-ready, commit issued")
     for i in range(18):
-        print(f"   unit {i:2d}: producer {u[i, 0] - base:7d} {u[i, 1] - base:7d} | issuer {u[i, 2] - base:7d} {u[i, 3] - base:7d}   (issue span {u[i, 3] - u[i, 2]:5d} = first MMA group {u[i, 4] - u[i, 2]:4d} + look-ahead waits {u[i, 5] - u[i, 4]:4d} + last group {u[i, 3] - u[i, 5]:4d}; unit-to-unit {u[i, 2] - u[i - 1, 2] if i else 0:5d})")
-    mm = buf[3072:3072 + 18].astype(np.int64)
+        print(f"   unit {i:2d}: producer {u[i, 0] - base:7d} {u[i, 1] - base:7d} | issuer {u[i, 2] - base:7d} {u[i, 3] - base:7d}   (issue span {u[i, 3] - u[i, 2]:5d}; unit-to-unit {u[i, 2] - u[i - 1, 2] if i else 0:5d})")
+    ee = buf[3072:3072 + 72].reshape(9, 8).astype(np.int64)
     t0 = t[1, 0, 0]
     print(f"precision {prec}: cycles relative to tile 1 layer 0 (events: chunk0 go, chunk1 go, commit issued | acc ready, pass0 done, pass1 done)")
     for tile in (1,):
         for l in range(8):
             e = t[tile, l] - t0
-            print(f"  tile {tile} layer {l}: issuer {e[0]:7d} {e[1]:7d} {e[2]:7d} | epilogue {e[3]:7d} {e[4]:7d} {e[5]:7d}   layer span {t[tile, l, 3] - (t[tile, l - 1, 3] if l else t[tile - 1, 7, 3]):6d}")
+            prev = t[tile, l - 1] if l else t[tile - 1, 7]
+            print(f"  tile {tile} layer {l}: issuer chunk0-go {e[0]:7d} chunk1-go {e[1]:7d} last-commit {e[2]:7d} | epilogue acc-ready {e[3]:7d} pass0-done {e[4]:7d} pass1-done {e[5]:7d} | "
+                  f"layer span {t[tile, l, 3] - prev[3]:6d}  issuing {t[tile, l, 2] - t[tile, l, 0]:6d}  drain {t[tile, l, 3] - t[tile, l, 2]:4d}  prev-acc-ready -> this chunk0-go {t[tile, l, 0] - prev[3]:5d}")
+    for l in range(1, 7):
+        e = ee[l]
+        print(f"  epilogue thread 0, tile 1 layer {l} pass 0: acc-ready -> start {e[0] - t[1, l, 3]:5d} | tmem loads + math {e[1] - e[0]:5d} | convert + st.shared {e[2] - e[1]:5d} | fence.proxy.async {e[3] - e[2]:5d} | syncwarp + arrive {e[4] - e[3]:5d}")

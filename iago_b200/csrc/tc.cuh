@@ -105,6 +105,41 @@ __device__ __forceinline__ void tmem_ld1(uint32_t taddr, uint32_t &v) {
 }
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---------------------------------------------------------------- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 / FMUL2) and conversions
+__device__ __forceinline__ uint64_t f32x2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f32x2_unpack(uint64_t v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// two fp16 values (one 32-bit register) -> two E4M3 bytes
+__device__ __forceinline__ uint32_t e4m3x2_from_half2(uint32_t h2) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
+    return r;
+}
+// two fp32 values -> two E4M3 bytes (`hi` lands in the upper byte)
+__device__ __forceinline__ uint32_t e4m3x2_from_floats(float lo, float hi) {
+    uint16_t r;
+    asm("cvt.rn.satfinite.e4m3x2.f32 %0, %1, %2;" : "=h"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+
 // ---------------------------------------------------------------- CTA pairs (cta_group::2): two CTAs of a cluster share one MMA
 // (tools/micro/umma2_check.cu is the known-answer test of everything below: M = 256 = 128 rows of A per CTA, each CTA holds HALF of
 // B's N columns — rank 0 the lower half —, both CTAs' TMA loads complete their bytes on the leader's mbarrier, commits are multicast.)

@@ -46,15 +46,13 @@ namespace iago {
 #ifdef IAGO_TRUNK_TRACE
 // debug build only (tools/trace_trunk.py): SM clock at the pipeline's hand-over points of CTA 0, first tiles
 __device__ unsigned long long g_trace[4096];
-#define TRACE(tile_, l_, ev_) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile_) < 4 * (long long)gridDim.x) g_trace[(((tile_) / gridDim.x) * 9 + (l_)) * 8 + (ev_)] = clock64(); } while (0)
-#define TRACEM(tile_, l_, u_, i_) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile_) == (long long)gridDim.x && (l_) == 2 && (u_) == 5) g_trace[3072 + (i_)] = clock64(); } while (0)
-#define TRACEE(tile_, l_, k_) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (tile_) == (long long)gridDim.x) g_trace[3072 + (l_) * 8 + (k_)] = clock64(); } while (0)
-#define TRACEU(tile_, l_, u_, ev_) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (tile_) == (long long)gridDim.x && (l_) == 2) g_trace[2048 + (u_) * 8 + (ev_)] = clock64(); } while (0)
+#define TRACE(it_, l_, ev_) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (it_) < 4) g_trace[((it_) * 9 + (l_)) * 8 + (ev_)] = clock64(); } while (0)
+#define TRACEE(it_, l_, k_) do { if (blockIdx.x == 0 && threadIdx.x == 0 && (it_) == 1) g_trace[3072 + (l_) * 8 + (k_)] = clock64(); } while (0)
+#define TRACEU(it_, l_, u_, ev_) do { if (blockIdx.x == 0 && (threadIdx.x & 31) == 0 && (it_) == 1 && (l_) == 2) g_trace[2048 + (u_) * 8 + (ev_)] = clock64(); } while (0)
 #else
 #define TRACE(tile_, l_, ev_) do { } while (0)
 #define TRACEU(tile_, l_, u_, ev_) do { } while (0)
 #define TRACEE(tile_, l_, k_) do { } while (0)
-#define TRACEM(tile_, l_, u_, i_) do { } while (0)
 #endif
 
 // ---------------------------------------------------------------- geometry
@@ -98,7 +96,7 @@ struct LayerDesc {
     int lo_off;      // byte offset of the lo block inside a unit
     int b_lbo;       // B operand: bytes between K-adjacent core matrices (= n * 16)
     int chunks;      // 64-channel chunks per tap (1 or 2); 0 for the explicit layer 1
-    float cscale;    // precision 2: factor that folds the FP8 cross-term accumulator into the output, 1 / (2^11 * sw)
+    float cscale;    // precision 2: 1 / (2^11 * sw) as computed at load time (the kernel reads the slot's device copy, TrunkArgs::cscale)
 };
 
 struct NetDesc {
@@ -119,6 +117,7 @@ struct TrunkArgs {
     const float *bias;    // [n_layers][128]
     const float *head;    // policy: w9[128], b10[64]; value: b9 at [0], wfc[64] at [128..192)
     const int *n_dev;     // nullable: the live position count is min(n, *n_dev) (request lists built on the device, mcts.cu)
+    const float *cscale;  // [n_layers] precision 2: factor that folds the FP8 cross-term accumulator in, 1 / (2^11 * sw_l) (device: a slot refresh rewrites it)
     float *dump[8];       // nullable each: post-ReLU output of block l+1 as fp32 [n][channels][64] (kept for the backward pass, reinforce.cu)
     // backward mode only (trunk_kernel<1>, the data-gradient chain of reinforce.cu):
     const float *dy_in;   // [n][128][64] gradient w.r.t. the output of block 8, entering the chain
@@ -155,26 +154,27 @@ __device__ __forceinline__ void store_act16(uint8_t *smem, const float (&x)[16],
     }
 }
 
-// precision 2: 16 values of this thread's tile row -> fp16 hi parts (2 groups of 8 channels) and one 16-channel row of each FP8
-// tile: A8 = e4m3(hi), AL8 = e4m3((x - hi) * 2^11).
-__device__ __forceinline__ void store_act16_p2(uint8_t *smem, const float (&x)[16], int col0, uint32_t row_off) {
-    uint32_t h8[4], l8[4];   // 16 FP8 values each
+// precision 2: 16 values of this thread's tile row (as 8 packed pairs) -> fp16 hi parts (2 groups of 8 channels) and one 16-channel row
+// of each FP8 tile: A8 = e4m3(hi), AL8 = e4m3((x - hi) * 2^11).  Packed fp32x2 arithmetic and the fp16x2 -> e4m3x2 conversion keep this at
+// 7 instructions per pair (the pass is issue-bound: it is what a layer boundary waits for).
+__device__ __forceinline__ void store_act16_p2(uint8_t *smem, const uint64_t (&x2)[8], int col0, uint32_t row_off) {
+    uint32_t hw[8], h8[4], l8[4];
+    const uint64_t k2048 = f32x2(2048.0f, 2048.0f), kneg = f32x2(-1.0f, -1.0f);
 #pragma unroll
-    for (int q = 0; q < 2; q++) {
-        uint32_t hw[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const float f0 = x[q * 8 + 2 * e], f1 = x[q * 8 + 2 * e + 1];
-            const __half2 h = __floats2half2_rn(f0, f1);
-            const float2 hf = __half22float2(h);
-            hw[e] = *reinterpret_cast<const uint32_t *>(&h);
-            const uint32_t a8 = __nv_cvt_float2_to_fp8x2(hf, __NV_SATFINITE, __NV_E4M3);
-            const uint32_t b8 = __nv_cvt_float2_to_fp8x2(make_float2((f0 - hf.x) * 2048.0f, (f1 - hf.y) * 2048.0f), __NV_SATFINITE, __NV_E4M3);
-            const int w = q * 2 + (e >> 1), sh = (e & 1) * 16;
-            if (sh == 0) { h8[w] = a8; l8[w] = b8; } else { h8[w] |= a8 << 16; l8[w] |= b8 << 16; }
-        }
-        *reinterpret_cast<uint4 *>(smem + OFF_AHI + (uint32_t)((col0 >> 3) + q) * kGroupBytes + row_off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    for (int e = 0; e < 8; e++) {
+        float f0, f1;
+        f32x2_unpack(x2[e], f0, f1);
+        const __half2 h = __floats2half2_rn(f0, f1);
+        hw[e] = *reinterpret_cast<const uint32_t *>(&h);
+        const float2 hf = __half22float2(h);
+        const uint64_t lo = mul2(fma2(f32x2(hf.x, hf.y), kneg, x2[e]), k2048);   // (x - hi) * 2^11, exact until the FP8 rounding
+        float l0, l1;
+        f32x2_unpack(lo, l0, l1);
+        const uint32_t a8 = e4m3x2_from_half2(hw[e]), b8 = e4m3x2_from_floats(l0, l1);
+        if ((e & 1) == 0) { h8[e >> 1] = a8; l8[e >> 1] = b8; } else { h8[e >> 1] |= a8 << 16; l8[e >> 1] |= b8 << 16; }
     }
+    *reinterpret_cast<uint4 *>(smem + OFF_AHI + (uint32_t)(col0 >> 3) * kGroupBytes + row_off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4 *>(smem + OFF_AHI + (uint32_t)((col0 >> 3) + 1) * kGroupBytes + row_off) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
     const uint32_t off = (uint32_t)(col0 >> 4) * kGroupBytes + row_off;
     *reinterpret_cast<uint4 *>(smem + OFF_ALO + off) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
     *reinterpret_cast<uint4 *>(smem + OFF_ALO + kA8Bytes + off) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
         // Pair: producer w copies the units g = w, w + 3, ... into ring stage g mod 6 — this CTA's half of the unit, by tensor-map TMA.
         const uint32_t my_turn = (uint32_t)(warp - kIssuerWarp - 1);
         uint32_t stage = 0, phase = 0, turn = 0;
-        for (long long tile = tile0; tile < n_tiles; tile += tile_step) {
+        for (long long tile = tile0, it = 0; tile < n_tiles; tile += tile_step, it++) {
             for (int l = 0; l < L; l++) {
                 const uint8_t *src = a.blob + net.unit_base[l];
                 const uint32_t unit_bytes = (uint32_t)net.layer[l].unit_bytes;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                 for (int u = 0; u < nu; u++) {
                     if (turn == my_turn) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                        TRACEU(tile, l, u, 0);
+                        TRACEU(it, l, u, 0);
                         if (elect_one()) {
                             if (CG == 2) {
                                 if (rank == 0) mbar_expect_tx(bar_full + 8 * stage, bytes);   // both halves complete on the leader's barrier
@@ -301,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                                 bulk_g2s(sbase + OFF_STAGE + stage * kRingBytes, src, bytes, bar_full + 8 * stage);
                             }
                         }
-                        TRACEU(tile, l, u, 1);
+                        TRACEU(it, l, u, 1);
                     }
                     src += unit_bytes;
                     row += (int)(unit_bytes >> 8);
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
         if (rank == 0) {
         uint32_t stage = 0, phase = 0, act_phase0 = 0, act_phase1 = 0, a1_phase = 0;
         const uint32_t hiA = (uint32_t)(kRowPitch >> 4) | (1u << 14), hiB = (uint32_t)(128 >> 4) | (1u << 14);   // high words: SBO + version
-        for (long long tile = tile0; tile < n_tiles; tile += tile_step) {
+        for (long long tile = tile0, it = 0; tile < n_tiles; tile += tile_step, it++) {
             for (int l = 0; l < L; l++) {
                 const int ld_n = net.layer[l].n, ld_chunks = net.layer[l].chunks;
                 const int ld_lo_off = net.layer[l].lo_off / CG, ld_b_lbo = net.layer[l].b_lbo / CG;   // pair: this CTA's half of the unit's N
@@ -354,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                     mbar_wait_cg<CG>(bar_act, act_phase0);  // input channels 0..63 are written
                     act_phase0 ^= 1;
                     tc_fence_after();
-                    TRACE(tile, l, 0);
+                    TRACE(it, l, 0);
                     mbar_wait_cg<CG>(bar_full + 8 * stage, phase);
                     tc_fence_after();
                     uint32_t prev_bar = 0;   // ring stage barrier whose commit is still to be issued (0 = none)
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                             const uint32_t off = (uint32_t)(ky * 20 + kx) * 16;
                             const int u = chunk * 9 + tap;
                             (void)u;
-                            TRACEU(tile, l, u, 2);
+                            TRACEU(it, l, u, 2);
                             const uint32_t bst = sbase + OFF_STAGE + stage * kRingBytes;
                             const uint32_t ahw = ((a_hi_base + off) >> 4) | a_lo_word, alw = ((a_lo_base + off) >> 4) | a_lo_word;
                             const uint32_t a8w = ((a8_base + off) >> 4) | a_lo_word, al8w = ((a8_base + kA8Bytes + off) >> 4) | a_lo_word;
@@ -440,10 +440,10 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                             }
                             if (tap == 8 && more) {
                                 act_phase1 ^= 1;
-                                TRACE(tile, l, 1);
+                                TRACE(it, l, 1);
                             }
                             acc = 1;
-                            TRACEU(tile, l, u, 3);
+                            TRACEU(it, l, u, 3);
                             prev_bar = bar_empty + 8 * stage;
                             stage = nstage; phase = nphase;
                         }
@@ -451,7 +451,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                     if (elect_one()) umma_commit_cg<CG>(prev_bar);  // frees the last weight stage of the layer when its MMAs retire
                 }
                 if (elect_one()) umma_commit_cg<CG>(bar_acc + 8 * (l & 1));  // accumulator of this layer complete
-                TRACE(tile, l, 2);
+                TRACE(it, l, 2);
             }
         }
         }
@@ -465,10 +465,10 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
         const float *shead = reinterpret_cast<const float *>(smem + OFF_HEAD);
         float *scratch = reinterpret_cast<float *>(smem + OFF_SCRATCH);   // [4][128] partial dots / [2][64] logits
         const int cell = r * 8 + c;
-        uint32_t acc_phase[2] = {0, 0};
+        uint32_t acc_phase = 0;   // bit b: parity of accumulator buffer b's barrier
         // the barriers the issuer waits on are the leader's: a pair's peer CTA arrives on them through the cluster address
         const uint32_t act_leader = CG == 2 ? mapa_rank(bar_act, 0) : bar_act, a1_leader = CG == 2 ? mapa_rank(bar_a1, 0) : bar_a1;
-        for (long long tile = tile0; tile < n_tiles; tile += tile_step) {
+        for (long long tile = tile0, it = 0; tile < n_tiles; tile += tile_step, it++) {
             const long long pos = (tile * CG + rank) * 2 + b;
             const bool valid = pos < n_pos;
             if (MODE == 1) {
@@ -524,11 +524,17 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
             }
 
             for (int l = 0; l < L; l++) {
-                const LayerDesc ld = net.layer[l];
-                mbar_wait(bar_acc + 8 * (l & 1), acc_phase[l & 1]);
-                acc_phase[l & 1] ^= 1;
+                // the layer's constants are fetched BEFORE the wait (indexed constant loads: ≈ 500 cycles after it otherwise, on the path the
+                // next layer's first MMA waits for)
+                LayerDesc ld;
+                ld.n = net.layer[l].n;
+                ld.cscale = (MODE == 0 && a.cscale) ? __ldg(a.cscale + l) : 0.0f;
+                float *const dump_l = MODE == 0 ? a.dump[l] : nullptr;
+                asm volatile("" ::"r"(ld.n), "f"(ld.cscale), "l"(dump_l));
+                mbar_wait(bar_acc + 8 * (l & 1), (acc_phase >> (l & 1)) & 1u);
+                acc_phase ^= 1u << (l & 1);
                 tc_fence_after();
-                if (tid == 0) TRACE(tile, l, 3);
+                if (tid == 0) TRACE(it, l, 3);
                 const uint32_t t_addr = lane_addr + (uint32_t)(l & 1) * 128u;
                 const bool policy_head = (l == 7 && net.kind == 0);
                 const bool writes_act = (l + 1 < L);
@@ -566,41 +572,55 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                     for (int ps = 0; ps < passes; ps++) {
                         const int col0 = ps * 64 + qt * 16;
                         uint32_t v[16];
-                        if (ps == 0) TRACEE(tile, l, 0);
+                        if (ps == 0) TRACEE(it, l, 0);
                         tmem_ld16(t_addr + col0, v);
                         float x[16];
                         if (p2 && l > 0) {   // fold the FP8 cross-term accumulator in (layer 1 has none: its inputs are exactly 0 / 1)
                             uint32_t vx[16];
                             tmem_ld16(t_addr + kCrossCol + col0, vx);
                             tmem_wait_ld();
+                            const uint64_t cs2 = f32x2(ld.cscale, ld.cscale);
+                            const float2 *b2 = reinterpret_cast<const float2 *>(sbias + l * 128 + col0);
 #pragma unroll
-                            for (int j = 0; j < 16; j++) x[j] = fmaxf(fmaf(__uint_as_float(vx[j]), ld.cscale, __uint_as_float(v[j])) + sbias[l * 128 + col0 + j], 0.0f);
+                            for (int j = 0; j < 8; j++) {
+                                const float2 bb = b2[j];
+                                const uint64_t y = add2(fma2(f32x2(__uint_as_float(vx[2 * j]), __uint_as_float(vx[2 * j + 1])), cs2,
+                                                             f32x2(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]))), f32x2(bb.x, bb.y));
+                                float y0, y1;
+                                f32x2_unpack(y, y0, y1);
+                                x[2 * j] = fmaxf(y0, 0.0f);
+                                x[2 * j + 1] = fmaxf(y1, 0.0f);
+                            }
                         } else {
                             tmem_wait_ld();
 #pragma unroll
                             for (int j = 0; j < 16; j++) x[j] = fmaxf(__uint_as_float(v[j]) + sbias[l * 128 + col0 + j], 0.0f);
                         }
-                        if (ps == 0) TRACEE(tile, l, 1);
+                        if (ps == 0) TRACEE(it, l, 1);
                         if (policy_head) {
 #pragma unroll
                             for (int j = 0; j < 16; j++) dot = fmaf(x[j], shead[col0 + j], dot);
                         }
-                        if (a.dump[l] != nullptr && valid) {
-                            float *dst = a.dump[l] + ((size_t)pos * ld.n + col0) * 64 + cell;
+                        if (dump_l != nullptr && valid) {
+                            float *dst = dump_l + ((size_t)pos * ld.n + col0) * 64 + cell;
 #pragma unroll
                             for (int j = 0; j < 16; j++) dst[(size_t)j * 64] = x[j];
                         }
                         if (writes_act) {
-                            if (p2) store_act16_p2(smem, x, col0, row_off);
-                            else store_act16<false>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
-                            if (ps == 0) TRACEE(tile, l, 2);
+                            if (p2) {
+                                uint64_t x2[8];
+#pragma unroll
+                                for (int j = 0; j < 8; j++) x2[j] = f32x2(x[2 * j], x[2 * j + 1]);
+                                store_act16_p2(smem, x2, col0, row_off);
+                            } else store_act16<false>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
+                            if (ps == 0) TRACEE(it, l, 2);
                             fence_async_smem();
-                            if (ps == 0) TRACEE(tile, l, 3);
+                            if (ps == 0) TRACEE(it, l, 3);
                             tc_fence_before();
                             __syncwarp();
                             if ((tid & 31) == 0) arrive_leader<CG>(act_leader + 8 * ps);  // input channels [64*ps, 64*ps+64) of the next layer are in place
-                            if (ps == 0) TRACEE(tile, l, 4);
-                            if (tid == 0) TRACE(tile, l, 4 + ps);
+                            if (ps == 0) TRACEE(it, l, 4);
+                            if (tid == 0) TRACE(it, l, 4 + ps);
                         }
                     }
                     if (policy_head) {
@@ -669,6 +689,7 @@ struct NetSlot {
     // nullptr after a device-side refresh: the slot then runs on the single-CTA kernel
     uint8_t *d_pair = nullptr, *d_pair2 = nullptr;
     TrunkMaps maps, maps2;
+    float *d_cscale = nullptr;    // [kMaxLayers]
     float *d_bias = nullptr;
     float *d_head = nullptr;
 };
@@ -676,11 +697,20 @@ struct NetSlot {
 struct TrunkState {
     NetSlot slot[IAGO_NET_SLOTS];
     bool attr_set = false;
+    float *d_sw = nullptr;   // [kMaxLayers] scratch of trunk_refresh_slot: the FP8 weight scale per layer
 };
 
 static TrunkState *state(iago_ctx *ctx) {
     if (!ctx->trunk) ctx->trunk = new TrunkState();
     return static_cast<TrunkState *>(ctx->trunk);
+}
+static float *st_scratch(iago_ctx *ctx) {
+    TrunkState *st = state(ctx);
+    if (!st->d_sw && cudaMalloc(&st->d_sw, kMaxLayers * sizeof(float)) != cudaSuccess) {
+        set_error("cudaMalloc failed for the weight-scale scratch");
+        return nullptr;
+    }
+    return st->d_sw;
 }
 
 bool trunk_slot_holds(iago_ctx *ctx, int slot, int kind) {
@@ -692,11 +722,13 @@ bool trunk_slot_holds(iago_ctx *ctx, int slot, int kind) {
 void trunk_destroy(iago_ctx *ctx) {
     if (!ctx->trunk) return;
     TrunkState *st = static_cast<TrunkState *>(ctx->trunk);
+    cudaFree(st->d_sw);
     for (auto &s : st->slot) {
         cudaFree(s.d_blob);
         cudaFree(s.d_blob2);
         cudaFree(s.d_pair);
         cudaFree(s.d_pair2);
+        cudaFree(s.d_cscale);
         cudaFree(s.d_bias);
         cudaFree(s.d_head);
     }
@@ -891,8 +923,14 @@ int iago_load_net(iago_ctx *ctx, int slot, int kind, const float *params, int64_
         set_error("iago_load_net: internal error, the two weight blobs differ in size");
         return IAGO_E_STATE;
     }
-    cudaFree(s.d_blob); cudaFree(s.d_blob2); cudaFree(s.d_pair); cudaFree(s.d_pair2); cudaFree(s.d_bias); cudaFree(s.d_head);
+    cudaFree(s.d_blob); cudaFree(s.d_blob2); cudaFree(s.d_pair); cudaFree(s.d_pair2); cudaFree(s.d_cscale); cudaFree(s.d_bias); cudaFree(s.d_head);
     s = NetSlot();
+    {
+        float cs[kMaxLayers];
+        for (int l = 0; l < kMaxLayers; l++) cs[l] = d.layer[l].cscale;
+        IAGO_CUDA(cudaMalloc(&s.d_cscale, sizeof cs));
+        IAGO_CUDA(cudaMemcpy(s.d_cscale, cs, sizeof cs, cudaMemcpyHostToDevice));
+    }
     IAGO_CUDA(cudaMalloc(&s.d_pair, pair.size()));
     IAGO_CUDA(cudaMalloc(&s.d_pair2, pair2.size()));
     IAGO_CUDA(cudaMemcpy(s.d_pair, pair.data(), pair.size(), cudaMemcpyHostToDevice));
@@ -946,8 +984,8 @@ int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, con
     const long long tiles = pairs ? (n + 3) / 4 : (n + 1) / 2;
     const long long max_groups = pairs ? ctx->sm_count / 2 : ctx->sm_count;
     const int grid = (int)(tiles < max_groups ? tiles : max_groups) * (pairs ? 2 : 1);
-    if (precision == 2 && (!s.d_blob2 || dump)) precision = 3;   // a slot refreshed from device parameters has no FP8 blob; the trainer's forward keeps full accuracy
-    TrunkArgs a{(const u64 *)p1, (const u64 *)p2, color, n, out, out_kind, precision, precision == 2 ? s.d_blob2 : s.d_blob, s.d_bias, s.d_head, n_dev, {}, nullptr, {}};
+    if (precision == 2 && dump) precision = 3;   // the trainer's forward (activations dumped for the backward pass) keeps full accuracy
+    TrunkArgs a{(const u64 *)p1, (const u64 *)p2, color, n, out, out_kind, precision, precision == 2 ? s.d_blob2 : s.d_blob, s.d_bias, s.d_head, n_dev, s.d_cscale, {}, nullptr, {}};
     if (pairs) a.blob = precision == 2 ? s.d_pair2 : s.d_pair;
     for (int l = 0; l < 8; l++) a.dump[l] = dump ? dump[l] : nullptr;
     cudaStream_t cs = (cudaStream_t)stream;
@@ -981,27 +1019,93 @@ int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, con
 // ---------------------------------------------------------------- refresh a policy slot from DEVICE parameters
 // The same blob iago_load_net builds on the host (same roundings, bit-identical), written by kernels: the REINFORCE
 // trainer refreshes its playing slot after every Adam step without a device -> host -> device round trip.
-__global__ void pack_forward_kernel(const float *__restrict__ W, uint8_t *__restrict__ units, int cin, int cout, int first) {
+// One thread per weight element of a layer: the element's fp16 hi / lo parts and FP8 forms go to their places in the four operand
+// layouts (single-CTA and pair, precision 3 and precision 2).  mode 0 = a trunk layer (chunk-major units of 64 input channels),
+// 1 = layer 1 (explicit im2col, K = 18 padded to 32; fp16 hi / lo in every blob), 2 = the value head's block9 (N padded to 16).
+__global__ void pack_all_kernel(const float *__restrict__ W, int cin, int n_pad, int mode, const float *__restrict__ sw_ptr,
+                                uint8_t *__restrict__ blob, uint8_t *__restrict__ blob2, uint8_t *__restrict__ pair, uint8_t *__restrict__ pair2) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    const int kgroups = first ? 4 : 8, n_units = first ? 1 : 9 * (cin / 64);
-    const int total = n_units * kgroups * cout * 8;
-    if (idx >= total) return;
-    const int e = idx & 7, n = (idx >> 3) % cout, kg = ((idx >> 3) / cout) % kgroups, ut = (idx >> 3) / cout / kgroups;
+    const int kgroups = mode == 1 ? 4 : 8, n_units = mode == 1 ? 1 : 9 * (cin / 64);
+    if (idx >= n_units * kgroups * n_pad * 8) return;
+    const int e = idx & 7, n = (idx >> 3) % n_pad, kg = ((idx >> 3) / n_pad) % kgroups, ut = (idx >> 3) / n_pad / kgroups;
     const int k = kg * 8 + e;
     float w;
-    if (first) {
-        w = k < 18 ? W[((size_t)n * 2 + (k & 1)) * 9 + (k >> 1)] : 0.0f;       // explicit im2col: k = tap*2 + channel
+    if (mode == 1) {
+        w = k < 18 ? W[((size_t)n * 2 + (k & 1)) * 9 + (k >> 1)] : 0.0f;       // k = tap*2 + channel
     } else {
         const int ch = ut / 9, tap = ut % 9;                                   // chunk-major units
-        w = W[((size_t)n * cin + ch * 64 + k) * 9 + tap];
+        w = mode == 2 ? (n == 0 ? W[(size_t)(ch * 64 + k) * 9 + tap] : 0.0f) : W[((size_t)n * cin + ch * 64 + k) * 9 + tap];
     }
     const __half h = __float2half_rn(w);
     const __half l = __float2half_rn(w - __half2float(h));
-    const size_t half_elems = (size_t)kgroups * cout * 8;
-    __half *unit = reinterpret_cast<__half *>(units) + (size_t)ut * 2 * half_elems;
-    const size_t off = ((size_t)kg * cout + n) * 8 + e;
-    unit[off] = h;
-    unit[half_elems + off] = l;
+    const size_t half_elems = (size_t)kgroups * n_pad * 8, unit_bytes = half_elems * 4;
+    // single-CTA layouts
+    {
+        const size_t off = ((size_t)kg * n_pad + n) * 8 + e;
+        __half *u = reinterpret_cast<__half *>(blob + (size_t)ut * unit_bytes);
+        u[off] = h;
+        u[half_elems + off] = l;
+        __half *u2 = reinterpret_cast<__half *>(blob2 + (size_t)ut * unit_bytes);
+        u2[off] = h;
+        if (mode == 1) {
+            u2[half_elems + off] = l;
+        } else {
+            const float sw = *sw_ptr;
+            uint8_t *w8 = blob2 + (size_t)ut * unit_bytes + half_elems * 2, *wl8 = w8 + half_elems;
+            const size_t o8 = ((size_t)(k >> 4) * n_pad + n) * 16 + (k & 15);
+            w8[o8] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(h) * sw, __NV_SATFINITE, __NV_E4M3);
+            wl8[o8] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(l) * 2048.0f * sw, __NV_SATFINITE, __NV_E4M3);
+        }
+    }
+    // pair layouts: the unit as [rank 0's half of the output channels | rank 1's half], each a complete unit of n_pad / 2 columns
+    {
+        const int nh = n_pad / 2, hh = n / nh, nn = n % nh;
+        const size_t he2 = half_elems / 2, base = (size_t)ut * unit_bytes + (size_t)hh * (unit_bytes / 2);
+        const size_t off = ((size_t)kg * nh + nn) * 8 + e;
+        __half *u = reinterpret_cast<__half *>(pair + base);
+        u[off] = h;
+        u[he2 + off] = l;
+        __half *u2 = reinterpret_cast<__half *>(pair2 + base);
+        u2[off] = h;
+        if (mode == 1) {
+            u2[he2 + off] = l;
+        } else {
+            const float sw = *sw_ptr;
+            uint8_t *w8 = pair2 + base + he2 * 2, *wl8 = w8 + he2;
+            const size_t o8 = ((size_t)(k >> 4) * nh + nn) * 16 + (k & 15);
+            w8[o8] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(h) * sw, __NV_SATFINITE, __NV_E4M3);
+            wl8[o8] = (uint8_t)__nv_cvt_float_to_fp8(__half2float(l) * 2048.0f * sw, __NV_SATFINITE, __NV_E4M3);
+        }
+    }
+}
+
+// Per-layer FP8 weight scale (the rule of fp8_weight_scale on the host): sw = the power of two that brings max |w| into [128, 256);
+// cscale = 1 / (2^11 * sw).  One block per layer; layer 0 has no FP8 part.
+__global__ void layer_scale_kernel(const float *__restrict__ params, int kind, float *__restrict__ sw_out, float *__restrict__ cscale_out) {
+    const int cin[8] = {2, 64, 128, 128, 128, 128, 128, 128}, cout[8] = {64, 128, 128, 128, 128, 128, 128, 128};
+    const int l = blockIdx.x;
+    size_t off = 0, count = 0;
+    for (int i = 0; i < 8; i++) {
+        const size_t nw = (size_t)cout[i] * cin[i] * 9;
+        if (i == l) count = nw;
+        if (i < l || l == 8) off += nw + cout[i];
+    }
+    if (l == 8) count = kind == 1 ? 1152 : 0;
+    __shared__ float red[256];
+    float mx = 0.0f;
+    for (size_t i = threadIdx.x; i < count; i += blockDim.x) mx = fmaxf(mx, fabsf(params[off + i]));
+    red[threadIdx.x] = mx;
+    __syncthreads();
+    for (int sft = 128; sft > 0; sft >>= 1) {
+        if ((int)threadIdx.x < sft) red[threadIdx.x] = fmaxf(red[threadIdx.x], red[threadIdx.x + sft]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        mx = red[0];
+        const float sw = (!(mx > 0.0f) || !isfinite(mx)) ? 1.0f : ldexpf(1.0f, 7 - ilogbf(mx));
+        sw_out[l] = sw;
+        cscale_out[l] = (l == 0 || count == 0) ? 0.0f : 1.0f / (2048.0f * sw);
+    }
 }
 
 __global__ void pack_bias_head_kernel(const float *__restrict__ params, float *__restrict__ bias, float *__restrict__ head, int kind) {
@@ -1017,23 +1121,9 @@ __global__ void pack_bias_head_kernel(const float *__restrict__ params, float *_
         for (int i = threadIdx.x; i < 192; i += blockDim.x) head[i] = params[off + i];
 }
 
-// Value head: block9 units (N padded to 16, only output 0 is real, chunk-major like the trunk layers), b9 and the collapsed
-// fc11 * fc10 64-vector (fp64 accumulation, as iago_load_net does on the host).
-__global__ void pack_value_head_kernel(const float *__restrict__ hp /* W9[1152] | b9 | fc10[128][64] | fc11[128] */,
-                                       uint8_t *__restrict__ units, float *__restrict__ head) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over [ut 18][kg 8][n 16][e 8]
-    if (idx < 18 * 8 * 16 * 8) {
-        const int e = idx & 7, n = (idx >> 3) & 15, kg = (idx >> 7) & 7, ut = idx >> 10;
-        const int ch = ut / 9, tap = ut % 9;
-        const float w = n == 0 ? hp[(size_t)(ch * 64 + kg * 8 + e) * 9 + tap] : 0.0f;
-        const __half h = __float2half_rn(w);
-        const __half l = __float2half_rn(w - __half2float(h));
-        const size_t half_elems = 8 * 16 * 8;
-        __half *unit = reinterpret_cast<__half *>(units) + (size_t)ut * 2 * half_elems;
-        const size_t off = ((size_t)kg * 16 + n) * 8 + e;
-        unit[off] = h;
-        unit[half_elems + off] = l;
-    }
+// Value head scalars: b9 and the collapsed fc11 * fc10 64-vector (fp64 accumulation, as iago_load_net does on the host).
+__global__ void pack_value_head_kernel(const float *__restrict__ hp /* W9[1152] | b9 | fc10[128][64] | fc11[128] */, float *__restrict__ head) {
+    const int idx = threadIdx.x;
     if (idx < 64) {
         const float *fc10 = hp + 1153, *fc11 = fc10 + 128 * 64;
         double acc = 0.0;
@@ -1053,23 +1143,24 @@ int trunk_refresh_slot(iago_ctx *ctx, int slot, int kind, const float *d_params,
     }
     const int cin[8] = {2, 64, 128, 128, 128, 128, 128, 128}, cout[8] = {64, 128, 128, 128, 128, 128, 128, 128};
     cudaStream_t cs = (cudaStream_t)stream;
-    if (s.d_blob2) {   // the FP8 blob is only built by iago_load_net (it needs a per-layer max |w|): precision 2 runs as 3 on this slot from now on
-        cudaFree(s.d_blob2);
-        s.d_blob2 = nullptr;
-    }
-    if (s.d_pair) {    // so are the pair-layout blobs: the slot runs on the single-CTA kernel from now on
-        cudaFree(s.d_pair);
-        cudaFree(s.d_pair2);
-        s.d_pair = s.d_pair2 = nullptr;
-    }
+    if (!st_scratch(ctx)) return IAGO_E_CUDA;
+    float *d_sw = st_scratch(ctx);
+    layer_scale_kernel<<<kMaxLayers, 256, 0, cs>>>(d_params, kind, d_sw, s.d_cscale);
     size_t off = 0;
     for (int l = 0; l < 8; l++) {
         const int total = (l == 0 ? 4 * cout[l] * 8 : 9 * (cin[l] / 64) * 8 * cout[l] * 8);
-        pack_forward_kernel<<<(total + 255) / 256, 256, 0, cs>>>(d_params + off, s.d_blob + s.desc.unit_base[l], cin[l], cout[l], l == 0);
+        const size_t ub = (size_t)s.desc.unit_base[l];
+        pack_all_kernel<<<(total + 255) / 256, 256, 0, cs>>>(d_params + off, cin[l], cout[l], l == 0 ? 1 : 0, d_sw + l, s.d_blob + ub, s.d_blob2 + ub,
+                                                             s.d_pair + ub, s.d_pair2 + ub);
         off += (size_t)cout[l] * cin[l] * 9 + cout[l];
     }
     pack_bias_head_kernel<<<1, 128, 0, cs>>>(d_params, s.d_bias, s.d_head, kind);
-    if (kind == 1) pack_value_head_kernel<<<(18 * 8 * 16 * 8 + 255) / 256, 256, 0, cs>>>(d_params + off, s.d_blob + s.desc.unit_base[8], s.d_head);
+    if (kind == 1) {
+        const size_t ub = (size_t)s.desc.unit_base[8];
+        pack_all_kernel<<<(18 * 8 * 16 * 8 + 255) / 256, 256, 0, cs>>>(d_params + off, 128, 16, 2, d_sw + 8, s.d_blob + ub, s.d_blob2 + ub, s.d_pair + ub,
+                                                                      s.d_pair2 + ub);
+        pack_value_head_kernel<<<1, 128, 0, cs>>>(d_params + off, s.d_head);
+    }
     IAGO_CUDA(cudaGetLastError());
     return IAGO_OK;
 }
@@ -1141,7 +1232,7 @@ int trunk_backward_launch(iago_ctx *ctx, const uint8_t *blob, const float *dy_in
     if (int rc = set_trunk_attrs(st)) return rc;
     const long long tiles = (n + 1) / 2;
     const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
-    TrunkArgs a{nullptr, nullptr, nullptr, n, nullptr, 0, precision, blob, nullptr, nullptr, nullptr, {}, dy_in, {}};
+    TrunkArgs a{nullptr, nullptr, nullptr, n, nullptr, 0, precision, blob, nullptr, nullptr, nullptr, nullptr, {}, dy_in, {}};
     for (int i = 0; i < 7; i++) {
         a.dump[i] = dx_out[i];
         a.mask[i] = mask[i];

@@ -6,6 +6,7 @@ Host API    : numpy arrays in and out through the library's *_host entry points 
               D2H inside the call) — what the reference-style facade classes use.
 """
 import ctypes as C
+import os
 import dataclasses
 from typing import Optional
 
@@ -16,6 +17,16 @@ from ._lib import IagoError, IagoRng, check
 
 RNG_PHILOX, RNG_UNIFORMS, RNG_FORCED = 0, 1, 2
 STREAM_ROLLOUT, STREAM_SELFPLAY, STREAM_MCTS, STREAM_ENV, STREAM_VALUEGEN = 0, 1, 2, 3, 4
+
+
+# Inference default of the conv nets: precision 2 = fp16 main product + FP8 (E4M3) cross terms, 2 MMA units per K step; max-abs logit error
+# 3e-3 on sl_model.npz, value 5e-5, legal arg-max identical on every harvested position (tests/test_nets_gpu.py; north-star bar: 1e-2 and
+# 99.9 %).  Precision 3 (fp16 hi/lo split, 3 MMAs, ~1e-4) is what the trainers' forward passes and the bit-level parity tests use.
+DEFAULT_PRECISION = int(os.environ.get("IAGO_DEFAULT_PRECISION", "2"))
+
+
+def _prec(precision):
+    return DEFAULT_PRECISION if precision is None else int(precision)
 
 
 @dataclasses.dataclass
@@ -181,14 +192,14 @@ class Engine:
         check(self.lib.iago_rollout_logits(self.ctx, _ptr(p1), _ptr(p2), _ptr(color), _ptr(out), n, self._stream(stream)))
         return out
 
-    def policy_forward(self, slot, p1, p2, color, probs=True, precision=3, out=None, stream=None):
+    def policy_forward(self, slot, p1, p2, color, probs=True, precision=None, out=None, stream=None):
         """SLPolicy forward for n bitboard positions -> (n,64) float32 CUDA tensor (probabilities, or logits if probs=False)."""
         torch = _torch()
         n = self._check_i64(p1, p2)
         if out is None:
             out = torch.empty((n, 64), dtype=torch.float32, device=self._dev())
         check(self.lib.iago_policy_forward(self.ctx, int(slot), _ptr(p1), _ptr(p2), _ptr(color), n, _ptr(out),
-                                           1 if probs else 0, int(precision), self._stream(stream)))
+                                           1 if probs else 0, _prec(precision), self._stream(stream)))
         return out
 
     def policy_forward_acts(self, slot, p1, p2, color, precision=3, stream=None):
@@ -200,7 +211,7 @@ class Engine:
         acts = [torch.empty((n, 64 if l == 0 else 128, 8, 8), dtype=torch.float32, device=dev) for l in range(8)]
         ptrs = (C.c_void_p * 8)(*[a.data_ptr() for a in acts])
         check(self.lib.iago_policy_forward_acts(self.ctx, int(slot), _ptr(p1), _ptr(p2), _ptr(color), n, _ptr(logits),
-                                                C.cast(ptrs, C.c_void_p), int(precision), self._stream(stream)))
+                                                C.cast(ptrs, C.c_void_p), _prec(precision), self._stream(stream)))
         return logits, acts
 
     def value_forward_acts(self, slot, p1, p2, color, precision=3, stream=None):
@@ -212,17 +223,17 @@ class Engine:
         acts = [torch.empty((n, 64 if l == 0 else 128, 8, 8), dtype=torch.float32, device=dev) for l in range(8)]
         ptrs = (C.c_void_p * 8)(*[a.data_ptr() for a in acts])
         check(self.lib.iago_value_forward_acts(self.ctx, int(slot), _ptr(p1), _ptr(p2), _ptr(color), n, _ptr(values),
-                                               C.cast(ptrs, C.c_void_p), int(precision), self._stream(stream)))
+                                               C.cast(ptrs, C.c_void_p), _prec(precision), self._stream(stream)))
         return values, acts
 
-    def value_forward(self, slot, p1, p2, color, precision=3, out=None, stream=None):
+    def value_forward(self, slot, p1, p2, color, precision=None, out=None, stream=None):
         """Value forward for n bitboard positions -> (n,) float32 CUDA tensor."""
         torch = _torch()
         n = self._check_i64(p1, p2)
         if out is None:
             out = torch.empty(n, dtype=torch.float32, device=self._dev())
         check(self.lib.iago_value_forward(self.ctx, int(slot), _ptr(p1), _ptr(p2), _ptr(color), n, _ptr(out),
-                                          int(precision), self._stream(stream)))
+                                          _prec(precision), self._stream(stream)))
         return out
 
     def rollout_sample(self, p1, p2, color, rng: Optional[Rng] = None, draw=0, stream=None):
@@ -255,7 +266,7 @@ class Engine:
                                     _ptr(out.get("moves")), _ptr(counters), self._stream(stream)))
         return out
 
-    def selfplay(self, slot_learner, slot_opponent, n, init_p1=None, init_p2=None, greedy=False, precision=3,
+    def selfplay(self, slot_learner, slot_opponent, n, init_p1=None, init_p2=None, greedy=False, precision=None,
                  rng: Optional[Rng] = None, rec_cap=40, want_moves=False, stream=None):
         """n lockstep rl_self_play.Game(model1, model2)() games. Returns a dict of CUDA tensors (+ 'stats' host ints)."""
         torch = _torch()
@@ -274,14 +285,14 @@ class Engine:
         stats = (C.c_int64 * 2)()
         r, keep = self._rng_struct(rng, n, host=False)
         check(self.lib.iago_selfplay(self.ctx, int(slot_learner), int(slot_opponent), n, _ptr(init_p1), _ptr(init_p2),
-                                     1 if greedy else 0, int(precision), C.byref(r), _ptr(out["final_p1"]),
+                                     1 if greedy else 0, _prec(precision), C.byref(r), _ptr(out["final_p1"]),
                                      _ptr(out["final_p2"]), _ptr(out["result"]), _ptr(out["rec_own"]), _ptr(out["rec_opp"]),
                                      _ptr(out["rec_action"]), _ptr(out["n_rec"]), int(rec_cap), _ptr(out["moves"]),
                                      C.cast(stats, C.c_void_p), self._stream(stream)))
         out["stats"] = dict(turn_pairs=int(stats[0]), forwards=int(stats[1]))
         return out
 
-    def value_selfplay(self, slot_sl, slot_rl, stop_num, precision=3, rng: Optional[Rng] = None, stream=None):
+    def value_selfplay(self, slot_sl, slot_rl, stop_num, precision=None, rng: Optional[Rng] = None, stream=None):
         """n lockstep value_self_play.SelfPlay(stop_num[g])() games (stop_num: int32 CUDA tensor). Returns a dict of CUDA tensors:
         rec_own / rec_opp (the recorded position, mover's view), rec_color, rec_action (the random move, -1 = none), result,
         final_p1 / final_p2, draws (+ 'stats' host ints)."""
@@ -296,14 +307,14 @@ class Engine:
                    final_p1=i64(), final_p2=i64(), draws=torch.empty(n, dtype=torch.int32, device=dev))
         stats = (C.c_int64 * 2)()
         r, keep = self._rng_struct(rng, n, host=False)
-        check(self.lib.iago_value_selfplay(self.ctx, int(slot_sl), int(slot_rl), n, _ptr(stop_num), int(precision), C.byref(r),
+        check(self.lib.iago_value_selfplay(self.ctx, int(slot_sl), int(slot_rl), n, _ptr(stop_num), _prec(precision), C.byref(r),
                                            _ptr(out["rec_own"]), _ptr(out["rec_opp"]), _ptr(out["rec_color"]), _ptr(out["rec_action"]),
                                            _ptr(out["result"]), _ptr(out["final_p1"]), _ptr(out["final_p2"]), _ptr(out["draws"]),
                                            C.cast(stats, C.c_void_p), self._stream(stream)))
         out["stats"] = dict(turns=int(stats[0]), forwards=int(stats[1]))
         return out
 
-    def env_step(self, slot_opponent, p1, p2, stone_num, pass_flg, action, draws, rng: Optional[Rng] = None, precision=3,
+    def env_step(self, slot_opponent, p1, p2, stone_num, pass_flg, action, draws, rng: Optional[Rng] = None, precision=None,
                  want_errors=True, stream=None):
         """rl_env.GameEnv.step for n environments, in place on the CUDA state tensors (p1/p2 int64, stone_num/draws int32,
         pass_flg uint8); action int8. Returns (done uint8[n], opp_action int8[n], rejection-limit errors)."""
@@ -315,7 +326,7 @@ class Engine:
         opp = torch.empty(n, dtype=torch.int8, device=dev)
         err = C.c_int32(0)
         r, keep = self._rng_struct(rng, n, host=False)
-        check(self.lib.iago_env_step(self.ctx, int(slot_opponent), int(precision), n, _ptr(p1), _ptr(p2), _ptr(stone_num),
+        check(self.lib.iago_env_step(self.ctx, int(slot_opponent), _prec(precision), n, _ptr(p1), _ptr(p2), _ptr(stone_num),
                                      _ptr(pass_flg), _ptr(action), C.byref(r), _ptr(draws), _ptr(done), _ptr(opp),
                                      C.cast(C.byref(err), C.c_void_p) if want_errors else None, self._stream(stream)))
         return done, opp, int(err.value)
@@ -424,11 +435,11 @@ class Engine:
         color = np.ascontiguousarray(np.broadcast_to(np.asarray(color, np.uint8), (n,)))
         return self._to_dev(p1, np.int64), self._to_dev(p2, np.int64), self._to_dev(color, None)
 
-    def policy_forward_host(self, slot, p1, p2, color, probs=True, precision=3):
-        return self.policy_forward(slot, *self._host_boards(p1, p2, color), probs=probs, precision=precision).cpu().numpy()
+    def policy_forward_host(self, slot, p1, p2, color, probs=True, precision=None):
+        return self.policy_forward(slot, *self._host_boards(p1, p2, color), probs=probs, precision=_prec(precision)).cpu().numpy()
 
-    def value_forward_host(self, slot, p1, p2, color, precision=3):
-        return self.value_forward(slot, *self._host_boards(p1, p2, color), precision=precision).cpu().numpy()
+    def value_forward_host(self, slot, p1, p2, color, precision=None):
+        return self.value_forward(slot, *self._host_boards(p1, p2, color), precision=_prec(precision)).cpu().numpy()
 
     def rollout_logits_host(self, p1, p2, color):
         p1 = np.ascontiguousarray(p1, np.uint64).reshape(-1)

@@ -43,7 +43,7 @@ class _TrunkNet:
     kind = None
     default_file = None
 
-    def __init__(self, device=0, precision=3):
+    def __init__(self, device=0, precision=None):
         self.device, self.precision = device, precision
         self._tag = f"{type(self).__name__}#{next(_ids)}"
         self.slot = default_engine(device).alloc_slot(self._tag)   # owned until close() / garbage collection; raises when none is free

@@ -8,7 +8,7 @@ import ctypes as C
 import numpy as np
 
 from ._lib import IagoMctsParams, check
-from .engine import STREAM_MCTS, default_engine
+from .engine import STREAM_MCTS, _prec, default_engine
 
 PASS_INDEX = 64  # visits[:, 64] / q[:, 64] belong to the pass child (action -1, MCTS.py:112-114)
 
@@ -52,12 +52,12 @@ class SearchPool:
         return p1, p2, color, done
 
     def search(self, n_playouts, *, slot_policy, slot_value, lmbda=0.5, c_puct=1.0, n_thr=15, leaf_batch=1, virtual_loss=1.0,
-               precision=3, cache_value=True, seed=0, forced_v=None, forced_z=None):
+               precision=None, cache_value=True, seed=0, forced_v=None, forced_z=None):
         """n_playouts more MCTS.playout calls on every tree. forced_v / forced_z ([n_trees, stride], indexed by the playout
         number since the tree was created) replay given leaf evaluations instead of running the nets (test hook)."""
         p = IagoMctsParams(lmbda=float(lmbda), c_puct=float(c_puct), virtual_loss=float(virtual_loss), n_thr=int(n_thr),
                            leaf_batch=int(leaf_batch), n_playouts=int(n_playouts), slot_policy=int(slot_policy),
-                           slot_value=int(slot_value), precision=int(precision), cache_value=1 if cache_value else 0,
+                           slot_value=int(slot_value), precision=_prec(precision), cache_value=1 if cache_value else 0,
                            reserved=0, seed=int(seed) & (2**64 - 1), forced_v=None, forced_z=None, forced_stride=0)
         keep = []
         if forced_v is not None:

@@ -128,12 +128,23 @@ def test_facade_network_classes(engine, golden_nets):
     va = network.Value().load(model_file("value_model.npz"))
     ro = network.RolloutPolicy().load(model_file("rollout_model.npz"))
     x = g["x"][:64].astype(np.float32)
-    assert np.abs(sl(x).data - g["sl_prob"][:64]).max() <= 1e-4
-    assert np.abs(va(x).data - g["value"][:64]).max() <= 1e-4
+    # the facade default is the inference precision (2: fp16 + FP8 cross terms, logits within 1e-2 -> probabilities within 2.5e-3);
+    # precision 3 is the parity setting
+    assert np.abs(sl(x).data - g["sl_prob"][:64]).max() <= 2.5e-3
+    assert np.abs(va(x).data - g["value"][:64]).max() <= 1e-3
+    sl3 = network.SLPolicy(precision=3).load(model_file("sl_model.npz"))
+    va3 = network.Value(precision=3).load(model_file("value_model.npz"))
+    assert np.abs(sl3(x).data - g["sl_prob"][:64]).max() <= 1e-4
+    assert np.abs(va3(x).data - g["value"][:64]).max() <= 1e-4
     assert np.abs(ro(x).data - g["rollout_prob"][:64]).max() <= 1e-6
     s = g["state"][5].reshape(8, 8).astype(np.float32)
-    prob = sl(gf.make_state_var(s, int(g["color"][5]))).data.reshape(64)   # the reference's call shape (MCTS.py:95)
+    prob = sl3(gf.make_state_var(s, int(g["color"][5]))).data.reshape(64)   # the reference's call shape (MCTS.py:95)
     assert np.abs(prob - g["sl_prob"][5]).max() <= 1e-4
+    # slots are owned: the two SLPolicy objects hold different slots, and a closed model gives its slot back
+    assert len({sl.slot, va.slot, sl3.slot, va3.slot}) == 4
+    freed = sl3.slot
+    sl3.close()
+    assert network.SLPolicy().slot == freed
 
 
 def test_policy_and_value_on_harvested_positions(engine, cref, oracle_nets, rollout_weights):

@@ -17,8 +17,9 @@ Printed JSON (one line, rank 0):
              plus the unmodified Python reference under the chainer stand-in when baseline/_ref is present
   --impl reference   times the CPU port alone (the reference is pure Python and cannot be "compiled")
   selfplay / mcts / reinforce / valuegen   the other BASELINE configs as extra sections of the same line (games/s, playouts/s,
-             records/s, each with its roofline fraction and the reference's CPU figure); `precision2` inside selfplay / mcts is
-             the same workload with the nets' opt-in fp16 + FP8-cross-term mode
+             records/s, each with its roofline fraction and the reference's CPU figure); the nets run in the inference precision 2
+             (fp16 + FP8 cross terms, DESIGN.md §3), `precision3` inside selfplay / mcts is the same workload in the parity precision;
+             `selfplay.sampled` is the batch with sampled moves and switched openings (games that differ)
 """
 import argparse
 import json
@@ -39,7 +40,17 @@ OPS_PER_PLY = 676          # int32 ALU lane-ops per ply: movegen 314 + flip 352 
 OPS_PER_PLY_IMPL = 308     # ALU-pipe instructions per ply the paired kernel really issues for the rules (2 lanes x 154, counted in the SASS
                            # of rollout_pair_kernel<FORCED>: carry-propagation flips / east moves, three parallel-prefix floods; + 92 IMAD on the FMA pipe)
 BYTES_PER_GAME = 17 + 21   # p1,p2,colour in; final p1,p2,n_moves,result out
-NCU_DRAM_BYTES_PER_LAUNCH = 1152256   # profiles/r01_ncu_rollout_v4_summary.csv (dram__bytes_read.sum; write 0), 65,536-game launch
+
+
+def ncu_traffic():
+    """dram__bytes_read + write per launch of the headline kernel from the committed ncu capture (profiles/ncu_traffic.json, written by
+    profiles/ncu_summary.py with the capture's date and command); None when the file is missing or is for another launch size."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["rollout_pair_kernel"]
+        return t if t.get("games_per_launch") == GAMES_PER_STEP else None
+    except Exception:
+        return None
+
 METRIC = "rollout_plies_per_s"
 
 
@@ -224,7 +235,7 @@ def cpu_baseline_block(budget_s=12.0):
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    n = args.games or 16384
+    n = args.games or GAMES_PER_STEP   # the same 65,536-game step as the GPU arm (about 0.3 s of CPU work per step on 16 threads)
     for _ in range(args.warmup):
         cpu_port_throughput(min(n, 2048))
     plies = 0
@@ -238,8 +249,10 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "plies/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "u64 bitboards + f32 policy", "data": "synthetic",
-            "config": {"workload": f"rollout-policy self-play from the opening, rollout_model.npz, {n} games per step "
-                                   "(bounded sample of the 65,536-game config)", "games_per_step": n},
+            "config": {"workload": "65,536 lockstep rollout-policy games per GPU per step from the opening, colour 1 first, "
+                                   "rollout_model.npz, Philox4x32-10 uniforms keyed by global game id (BASELINE configs[1])",
+                       "games_per_step_per_gpu": n, "implementation": "oracle/othello_ref.c on all host threads (the reference itself is "
+                       "single-process Python: 4.9e3 plies/s, see cpu_baseline.python_reference of the GPU arm)"},
             "cpu_baseline": {"value": v, "unit": "plies/s", "cores": threads, "kind": "port",
                              "sample": f"{args.steps} steps x {n} games, oracle/othello_ref.c, {threads} pthreads"},
             "e2e": {"value": v, "unit": "plies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -382,13 +395,14 @@ def run_ours(args, rank, world, local_rank):
             "clocks": clk.summary(),
             "roofline": {"bound": "alu", "kernel": "rollout_pair_kernel<PHILOX> (two lanes per game)", "achieved": achieved / 1e12,
                          "peak": int_peak / 1e12, "unit": "Tint32op/s", "frac": achieved / int_peak,
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH if n == GAMES_PER_STEP else None,
+                         "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch") if n == GAMES_PER_STEP else None,
+                         "traffic_source": ncu_traffic(),
                          "ops_per_ply_as_implemented": OPS_PER_PLY_IMPL,
                          "frac_as_implemented": OPS_PER_PLY_IMPL * plies_per_launch / kernel_s / int_peak,
                          "note": "issue-bound path: 676 algorithmic int32 lane-ops/ply (SURVEY 8d: 6-step flood formulation) x plies per launch / mean launch "
                                  "time; peak = SHF+LOP3 micro-kernel measured in this run (iago_measure_int_peak); traffic = "
-                                 "dram__bytes_read+write per launch from the ncu --set full capture in profiles/r01_ncu_rollout_v4_summary.csv "
-                                 "(algorithmic bytes per launch: 38 B x 65,536 games = 2.49 MB; outputs stay in L2 during the capture)"},
+                                 "dram__bytes_read+write per launch read from profiles/ncu_traffic.json (the committed ncu --set full capture; "
+                                 "algorithmic bytes per launch: 38 B x 65,536 games = 2.49 MB; outputs stay in L2 during the capture)"},
             "roofline_movegen": {"bound": "alu", "kernel": "rollout_pair_kernel<FORCED> (legal_moves + flips + pass/terminal/score only, moves "
                                  "replayed from a 64 B/game log)", "plies_per_s": mg_plies / t_mg,
                                  "achieved": OPS_PER_PLY * mg_plies / t_mg / 1e12, "peak": int_peak / 1e12, "unit": "Tint32op/s",
@@ -440,63 +454,87 @@ def bf16_peak():
 
 
 def section_selfplay(eng, args, rank, world, dev, dist, barrier):
-    """BASELINE configs[2]: SL-policy greedy self-play, 16,384-game lockstep batch per GPU, sl_model.npz both sides."""
+    """BASELINE configs[2]: SL-policy greedy self-play, 16,384-game lockstep batch per GPU, sl_model.npz both sides — plus the same batch
+    with SAMPLED moves and the head/tail-switched openings of src/train_rl.py:43-46 (the greedy games are all the same game)."""
     import torch
-    from iago_b200 import Rng
+    from iago_b200 import Rng, boards
+    from iago_b200.train_rl import SWITCH_CELLS
     n = args.selfplay_games
     eng.load_net(0, model_path("sl_model.npz"))
     reps = max(1, args.selfplay_steps)
-    eng.selfplay(0, 0, n, greedy=True, rng=Rng.philox(seed=1, stream_id=1))  # warm-up at full size (workspaces, clocks)
-    barrier()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    fwd = pairs = 0
-    res = None
-    with ClockSampler(dev.index or 0) as clk:
-        for i in range(reps):
-            ev[i][0].record()
-            res = eng.selfplay(0, 0, n, greedy=True, rng=Rng.philox(seed=args.seed, game_id0=(i * world + rank) * n, stream_id=1))
-            ev[i][1].record()
-            fwd += res["stats"]["forwards"]
-            pairs += res["stats"]["turn_pairs"]
-        barrier()
-    step_ms = [a.elapsed_time(b) for a, b in ev]
-    t = sum(step_ms) / 1e3
-    # the same step with the nets in precision 2 (fp16 main product + FP8 cross terms: 3e-3 max-abs logit error, arg-max unchanged)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    eng.selfplay(0, 0, n, greedy=True, precision=2, rng=Rng.philox(seed=1, stream_id=1))
-    barrier()
-    e0.record()
-    res2 = eng.selfplay(0, 0, n, greedy=True, precision=2, rng=Rng.philox(seed=args.seed, game_id0=rank * n, stream_id=1))
-    e1.record()
-    barrier()
-    t2 = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=dev)
-    if dist is not None:
-        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
-    same_games = bool((res2["final_p1"] == res["final_p1"]).all() and (res2["final_p2"] == res["final_p2"]).all())   # greedy play: no draws involved
-    wins = torch.stack([(res["result"] == 1).sum(), (res["result"] == 0).sum(), (res["result"] == -1).sum()]).to(torch.int64)
-    tt = torch.tensor([t], dtype=torch.float64, device=dev)
-    cc = torch.tensor([reps * n, fwd * n], dtype=torch.int64, device=dev)
-    if dist is not None:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dist.all_reduce(cc, op=dist.ReduceOp.SUM)
-        dist.all_reduce(wins, op=dist.ReduceOp.SUM)   # win statistics: the only cross-GPU exchange of this workload
-    t = float(tt[0])
-    games, positions = cc.tolist()
     peak, src = bf16_peak()
+
+    def timed(greedy, precision, init=None, steps=reps):
+        """`steps` self-play steps; returns (seconds max over ranks, games, positions, last result dict, per-step ms, clocks)."""
+        kw = dict(greedy=greedy, precision=precision)
+        if init is not None:
+            kw.update(init_p1=init[0], init_p2=init[1])
+        eng.selfplay(0, 0, n, rng=Rng.philox(seed=1, stream_id=1), **kw)  # warm-up at full size (workspaces, clocks)
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        fwd = 0
+        res = None
+        with ClockSampler(dev.index or 0) as clk:
+            for i in range(steps):
+                ev[i][0].record()
+                res = eng.selfplay(0, 0, n, rng=Rng.philox(seed=args.seed, game_id0=(i * world + rank) * n, stream_id=1), **kw)
+                ev[i][1].record()
+                fwd += res["stats"]["forwards"]
+            barrier()
+        step_ms = [a.elapsed_time(b) for a, b in ev]
+        tt = torch.tensor([sum(step_ms) / 1e3], dtype=torch.float64, device=dev)
+        cc = torch.tensor([steps * n, fwd * n], dtype=torch.int64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        return float(tt[0]), int(cc[0]), int(cc[1]), res, step_ms, clk.summary(), fwd / steps
+
+    def wdl(res):
+        w = torch.stack([(res["result"] == 1).sum(), (res["result"] == 0).sum(), (res["result"] == -1).sum()]).to(torch.int64)
+        if dist is not None:
+            dist.all_reduce(w, op=dist.ReduceOp.SUM)   # win statistics: the only cross-GPU exchange of this workload
+        return w.tolist()
+
+    # (a) the headline: greedy, inference precision (2)
+    t, games, positions, res, step_ms, clocks, fpg = timed(True, None)
     ach = positions * SL_FLOP / t / 1e12
+    # (b) the same in precision 3 (the parity setting): same games?
+    t3, games3, _, res3, _, _, _ = timed(True, 3, steps=1)
+    same_games = bool((res3["final_p1"] == res["final_p1"]).all() and (res3["final_p2"] == res["final_p2"]).all()) if reps == 1 else None
+    if same_games is None:   # compare like with like: step 0 of both runs
+        r2 = eng.selfplay(0, 0, n, greedy=True, precision=None, rng=Rng.philox(seed=args.seed, game_id0=rank * n, stream_id=1))
+        same_games = bool((res3["final_p1"] == r2["final_p1"]).all() and (res3["final_p2"] == r2["final_p2"]).all())
+    # (c) sampled moves, odd games from a head/tail-switched opening: 16,384 different games of different lengths per GPU
+    p1 = torch.full((n,), boards.START_P1, dtype=torch.int64, device=dev)
+    p2 = torch.full((n,), boards.START_P2, dtype=torch.int64, device=dev)
+    cells = torch.tensor(SWITCH_CELLS, dtype=torch.int64, device=dev)[torch.randint(0, 4, (n,), device=dev, generator=torch.Generator(device=dev).manual_seed(args.seed + rank))]
+    odd = (torch.arange(n, device=dev) & 1) == 1
+    p2 = torch.where(odd, p2 | (torch.ones_like(p2) << cells), p2)   # a colour-2 stone dropped without flipping (src/train_rl.py:43-46)
+    ts, games_s, positions_s, res_s, step_ms_s, clocks_s, fpg_s = timed(False, None, init=(p1, p2))
+    n_final = torch.tensor([len(torch.unique(torch.stack([res_s["final_p1"], res_s["final_p2"]], 1), dim=0))], dtype=torch.int64, device=dev)
+    ach_s = positions_s * SL_FLOP / ts / 1e12
     out = {"metric": "selfplay_games_per_s", "value": games / t, "unit": "games/s", "ms_per_step": 1e3 * t / reps,
            "config": {"workload": "SL-policy greedy self-play, lockstep batch per GPU, sl_model.npz vs sl_model.npz "
-                                  "(BASELINE configs[2])", "games_per_step_per_gpu": n, "steps": reps, "precision": "fp16 hi/lo split, 3 MMAs"},
-           "positions_per_s": positions / t, "trunk_forwards_per_game": fwd / reps,
-           "step_ms_rank0": [round(x, 2) for x in step_ms], "clocks": clk.summary(),
-           "precision2": {"value": n * world / float(t2[0]), "unit": "games/s", "ms_per_step": 1e3 * float(t2[0]),
-                          "note": "nets in precision 2 (fp16 main product + FP8 cross terms; 3e-3 max-abs logit error on the fixtures, "
-                                  "arg-max unchanged; north-star bar 1e-2)", "same_final_boards_as_precision3": same_games},
-           "last_step_w_d_l": wins.tolist(),
+                                  "(BASELINE configs[2])", "games_per_step_per_gpu": n, "steps": reps,
+                      "precision": "2 (inference default): fp16 main product + FP8 cross terms, 2 MMA units per K step; logits within 1e-2 "
+                                   "(measured 3e-3), legal arg-max identical (tests/test_nets_gpu.py)"},
+           "positions_per_s": positions / t, "trunk_forwards_per_game": fpg,
+           "step_ms_rank0": [round(x, 2) for x in step_ms], "clocks": clocks,
+           "precision3": {"value": games3 / t3, "unit": "games/s", "ms_per_step": 1e3 * t3,
+                          "note": "the same step with the nets in precision 3 (fp16 hi/lo split, 3 MMAs per K step, ~1e-4 on the logits): the parity setting",
+                          "same_final_boards_as_default_precision": same_games},
+           "last_step_w_d_l": wdl(res),
            "roofline": {"bound": "tensor", "kernel": "trunk_kernel", "achieved": ach, "peak": peak * world, "unit": "TFLOP/s",
                         "frac": ach / (peak * world), "traffic": None, "peak_source": src,
                         "note": "algorithmic FLOP (122,847,232 per position, counted once) over the whole self-play step incl. the turn "
-                                "kernels; the hi/lo split issues 3x this many MMA FLOP"}}
+                                "kernels; precision 2 issues 2x this many MMA FLOP-equivalents"},
+           "sampled": {"value": games_s / ts, "unit": "games/s", "ms_per_step": 1e3 * ts / reps, "positions_per_s": positions_s / ts,
+                       "trunk_forwards_per_game": fpg_s, "step_ms_rank0": [round(x, 2) for x in step_ms_s], "clocks": clocks_s,
+                       "last_step_w_d_l": wdl(res_s), "distinct_final_boards_rank0_last_step": int(n_final[0]),
+                       "roofline": {"bound": "tensor", "achieved": ach_s, "peak": peak * world, "unit": "TFLOP/s", "frac": ach_s / (peak * world)},
+                       "note": "the same batch with SAMPLED moves (masked softmax, one Philox uniform per move) and every odd game started from a "
+                               "head/tail-switched opening (src/train_rl.py:43-46): games differ in content and length, finished games idle "
+                               "in their lanes until the longest one ends (what REINFORCE self-play does)"}}
     if rank == 0 and world == 1 and not args.no_cpu:
         py = python_reference_selfplay()
         if py:
@@ -515,7 +553,7 @@ def section_mcts(eng, args, rank, world, dev, dist, barrier):
     pool = SearchPool(T, max_nodes=32768, max_leaf_batch=B, tree_id0=rank * T, engine=eng)
     p1, p2 = (1 << 19) | (1 << 27) | (1 << 28) | (1 << 35), 1 << 36   # the opening after colour 1 plays 19
     out = {}
-    for cache, prec in ((True, 3), (False, 3), (True, 2)):
+    for cache, prec in ((True, None), (False, None), (True, 3)):
         kw = dict(slot_policy=0, slot_value=1, lmbda=0.5, c_puct=1, n_thr=15, leaf_batch=B, virtual_loss=1.0, precision=prec,
                   cache_value=cache, seed=args.seed)
         pool.set_roots(p1, p2, 2, reset_tree=True)
@@ -532,7 +570,7 @@ def section_mcts(eng, args, rank, world, dev, dist, barrier):
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         t = float(tt[0])
         visits, q, best = pool.root_stats()
-        out["precision2" if prec == 2 else "cached" if cache else "uncached"] = {
+        out["precision3" if prec == 3 else "cached" if cache else "uncached"] = {
             "value": T * N * world / t, "ms_per_move": 1e3 * t, "best_move_tree0": int(best[0]), "pool_overflows": pool.overflows()}
     peak, src = bf16_peak()
     unc = out["uncached"]["value"]
@@ -540,9 +578,8 @@ def section_mcts(eng, args, rank, world, dev, dist, barrier):
            "config": {"workload": "PV-MCTS, sl/value/rollout nets, lmbda 0.5, c_puct 1, n_thr 15, leaf batch 256, virtual loss 1, root = "
                                   "opening after move 19, one move (BASELINE configs[3])", "trees_per_gpu": T, "playouts_per_move": N},
            "value_cache_on": out["cached"], "value_cache_off": out["uncached"],
-           "precision2": dict(out["precision2"], note="the same search (value cache on) with the nets in precision 2: fp16 main product + FP8 "
-                              "cross terms, max-abs logit error 3e-3 on the fixtures against 1e-4 for the default precision 3 "
-                              "(north-star bar 1e-2), arg-max unchanged"),
+           "precision3": dict(out["precision3"], note="the same search (value cache on) with the nets in precision 3 (fp16 hi/lo split, ~1e-4 on the "
+                              "logits) instead of the inference default 2 (fp16 + FP8 cross terms, 3e-3; north-star bar 1e-2)"),
            "roofline": {"bound": "tensor", "kernel": "trunk_kernel (value net, cache off: one forward per playout)",
                         "achieved": unc * VALUE_FLOP / 1e12, "peak": peak * world, "unit": "TFLOP/s",
                         "frac": unc * VALUE_FLOP / 1e12 / (peak * world), "traffic": None, "peak_source": src,
@@ -558,7 +595,7 @@ def section_mcts(eng, args, rank, world, dev, dist, barrier):
     if rank == 0:
         # one tree (the reference's usage: one game, one search per move): latency of a 16,384-playout move
         one = SearchPool(1, max_nodes=65536, max_leaf_batch=B, tree_id0=10_000_000, engine=eng)
-        kw = dict(slot_policy=0, slot_value=1, lmbda=0.5, c_puct=1, n_thr=15, leaf_batch=B, virtual_loss=1.0, precision=3,
+        kw = dict(slot_policy=0, slot_value=1, lmbda=0.5, c_puct=1, n_thr=15, leaf_batch=B, virtual_loss=1.0, precision=None,
                   cache_value=True, seed=args.seed)
         one.set_roots(p1, p2, 2, reset_tree=True)
         one.search(2 * B, **kw)
@@ -656,11 +693,11 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--games", type=int, default=0, help="games per step per GPU (default 65,536; reference arm 16,384)")
+    ap.add_argument("--games", type=int, default=0, help="games per step per GPU (default 65,536 for both arms)")
     ap.add_argument("--seed", type=int, default=2026)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--reinforce-games", type=int, default=2048)
-    ap.add_argument("--reinforce-steps", type=int, default=1)
+    ap.add_argument("--reinforce-steps", type=int, default=8)
     ap.add_argument("--valuegen-games", type=int, default=16384)
     ap.add_argument("--sections", default="rollout,selfplay,mcts,reinforce,valuegen", help="extra sections to run after the headline rollout bench")
     ap.add_argument("--selfplay-games", type=int, default=16384)

@@ -184,3 +184,45 @@ def test_policy_and_value_on_harvested_positions(engine, cref, oracle_nets, roll
     verr = np.abs(v - ref_v).max()
     print(f"{len(states)} harvested positions: SL logits max-abs {err:.2e}, legal-argmax agreement {agree:.4%}; value max-abs {verr:.2e}")
     assert err <= 2e-3 and agree >= 0.999 and verr <= 2e-3
+
+
+def test_c3_50000_harvested_positions_both_precisions(engine, cref):
+    """SURVEY 8d C3 at the size it asks for: >= 50,000 positions (every position of 900 rollout games, as harvested above), SL logits
+    of sl_model.npz in precision 3 (parity setting) and 2 (inference default) and the value net, against the fp32 forward of
+    oracle/nets_torch.py (pinned to oracle/nets.py and through it to the reference's own outputs, tests/test_oracle_golden.py).
+    Bars: precision 3 max-abs <= 2e-3; precision 2 <= 1e-2 (the north-star figure); legal arg-max agreement >= 99.9 % for both."""
+    from iago_b200 import Rng, boards
+    from oracle import nets, nets_torch
+    n = 900
+    out = engine.rollout_host(np.full(n, boards.START_P1, np.uint64), np.full(n, boards.START_P2, np.uint64), np.ones(n, np.uint8),
+                              rng=Rng.philox(seed=4242), want_moves=True)
+    states, colors = [], []
+    for g in range(n):
+        st, c = boards.start_state(), 1
+        for mv in out["moves"][g]:
+            if mv < 0:
+                break
+            if not cref.legal_actions(st, c):       # the mover passed
+                c = 3 - c
+            states.append(st.copy()); colors.append(c)
+            cref.place_stone(st, int(mv), c)
+            c = 3 - c
+    states, colors = np.array(states, np.float32), np.array(colors, np.uint8)
+    assert len(states) >= 50000
+    p1, p2 = bb(states)
+    masks = engine.legal_actions_host(p1, p2, colors)
+    x = nets.planes_from_state(states, colors, np.float32)
+    engine.load_net(0, model_file("sl_model.npz"))
+    engine.load_net(1, model_file("value_model.npz"))
+    ref_logits = nets_torch.sl_logits(nets.load_params(model_file("sl_model.npz")), x)
+    ref_arg, has = legal_argmax(ref_logits, masks)
+    ref_v = nets_torch.value(nets.load_params(model_file("value_model.npz")), x)
+    for prec, bar in ((3, 2e-3), (2, 1e-2)):
+        logits = engine.policy_forward_host(0, p1, p2, colors, probs=False, precision=prec)
+        err = np.abs(logits - ref_logits).max()
+        arg, _ = legal_argmax(logits, masks)
+        agree = (arg == ref_arg)[has].mean()
+        verr = np.abs(engine.value_forward_host(1, p1, p2, colors, precision=prec) - ref_v).max()
+        print(f"{len(states)} positions, precision {prec}: SL logits max-abs {err:.2e}, legal-argmax agreement {agree:.5%} "
+              f"({int((arg != ref_arg)[has].sum())} of {int(has.sum())} differ); value max-abs {verr:.2e}")
+        assert err <= bar and agree >= 0.999 and verr <= 2e-3

@@ -186,3 +186,51 @@ def test_two_sided_cdf_is_numpy_choice(cref, rollout_weights):
             checked += 1
             assert got == want, (trial, u, got, want)
     assert checked > 30000 and near < checked // 5   # (edges of cells with probability below 1e-5 crowd each other)
+
+
+def test_torch_nets_equal_numpy_nets(golden_nets):
+    """oracle/nets_torch.py (used for the >= 50,000-position GPU comparison) against oracle/nets.py, which is pinned to the reference's
+    own outputs: same graph, fp32 conv summation order differs (<= 1e-4 on logits that span 0..130), fp64 agrees to 1e-4 as well."""
+    import os
+    import torch
+    from conftest import MODELS
+    from oracle import nets, nets_torch
+    if not os.path.isfile(os.path.join(MODELS, "sl_model.npz")):
+        pytest.skip("baseline/_ref/models not present")
+    x = golden_nets["x"][:200].astype(np.float32)
+    p = nets.load_params(os.path.join(MODELS, "sl_model.npz"))
+    ref = nets.sl_logits(p, x)
+    assert np.abs(nets_torch.sl_logits(p, x) - ref).max() <= 1e-4
+    assert np.abs(nets_torch.sl_logits(p, x, torch.float64) - ref).max() <= 1e-4
+    pv = nets.load_params(os.path.join(MODELS, "value_model.npz"))
+    assert np.abs(nets_torch.value(pv, x) - nets.value(pv, x)).max() <= 1e-5
+    # and against the reference's own forward (golden file)
+    e = np.exp(nets_torch.sl_logits(p, x).astype(np.float64)); e /= e.sum(axis=1, keepdims=True)
+    assert np.abs(e - golden_nets["sl_prob"][:200]).max() <= 1e-5
+
+
+def big_uniforms(g):
+    """The uniforms the 21,000 games of simulate_big.npz consumed: game i ran under np.random.seed(seed0 + i) (oracle/gen_golden_big.py)."""
+    seed0 = int(g["seed0"])
+    return np.stack([np.random.RandomState(seed0 + i).random_sample(64) for i in range(len(g["moves"]))])
+
+
+def test_21000_reference_games_replayed(cref, rollout_weights):
+    """simulate_big.npz: 21,000 full games of the unmodified mcts_self_play.Simulate (14,000 from the opening, 7,000 from mid-game positions
+    with either side to move) replayed by the C oracle from the np.random uniforms of each game's seed: every move, result and final
+    board identical.  This is the pin of the sampling rule (the two-sided cdf) on 1.08 M reference plies."""
+    from conftest import load_golden
+    from iago_b200 import boards
+    W, b = rollout_weights
+    g = load_golden("simulate_big")
+    n = len(g["moves"])
+    assert n >= 20000
+    start = boards.from_bitboards(g["start_p1"], g["start_p2"]).reshape(n, 64)
+    r = cref.simulate_batch(start.astype(np.float32), g["color"].astype(np.int32), W, b, mode=cref.RNG_UNIFORMS, uniforms=big_uniforms(g), threads=0)
+    assert (r["n_moves"] == g["n_moves"]).all()
+    assert (r["moves"][:, :60] == g["moves"]).all()
+    assert (r["results"] == g["result"]).all()
+    f1, f2 = cref.to_bitboards(r["final"])
+    assert (f1 == g["final_p1"]).all() and (f2 == g["final_p2"]).all()
+    # how close the recorded draws come to a cdf edge is what makes the double running sum necessary: report the count of passes / early ends
+    print(f"{n} reference games, {int(g['n_moves'].sum())} plies; {(g['n_moves'] < 60 - (np.unpackbits(g['start_p1'].view(np.uint8)).reshape(n, 64).sum(1) + np.unpackbits(g['start_p2'].view(np.uint8)).reshape(n, 64).sum(1) - 4)).sum()} games ended with empty cells")

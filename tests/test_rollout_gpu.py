@@ -24,6 +24,23 @@ def test_golden_trajectories_uniform_replay(engine, golden_simulate):
     assert int(out["counters"][0]) == int(g["n_moves"].sum())
 
 
+def test_21000_reference_games_uniform_replay(engine):
+    """simulate_big.npz: 21,000 full games of the UNMODIFIED reference Simulate (opening and mid-game starts, both colours to move),
+    replayed on the GPU from the np.random uniforms of each game's seed: 1.08 M plies, every move / result / final board identical."""
+    from conftest import load_golden
+    from iago_b200 import Rng
+    g = load_golden("simulate_big")
+    seed0, n = int(g["seed0"]), len(g["moves"])
+    assert n >= 20000
+    u = np.stack([np.random.RandomState(seed0 + i).random_sample(64) for i in range(n)])
+    out = engine.rollout_host(g["start_p1"], g["start_p2"], g["color"].astype(np.uint8), rng=Rng.replay_uniforms(u), want_moves=True)
+    assert (out["n_moves"] == g["n_moves"]).all()
+    assert (out["moves"][:, :60] == g["moves"]).all()
+    assert (out["result"] == g["result"]).all()
+    assert (out["final_p1"] == g["final_p1"]).all() and (out["final_p2"] == g["final_p2"]).all()
+    assert int(out["counters"][0]) == int(g["n_moves"].astype(np.int64).sum())
+
+
 def test_golden_forced_replay(engine, golden_simulate):
     from iago_b200 import Rng, boards
     g = golden_simulate

@@ -15,6 +15,7 @@ Files:
                 yields (RandomState(seed).random_sample), move list, final board, result
   nets.npz      SLPolicy (sl_model, rl_model), Value, RolloutPolicy outputs on harvested positions
   selfplay.npz  src/rl_self_play.Game trajectories (normal and 'head/tail switched' openings)
+  selfgame.npz  self_play.SelfGame.get_position_self calls (unbound, on a stand-in object): probabilities, choice, draws consumed
   env.npz       rl_env.GameEnv.step sequences (numpy standing in for cupy): actions, opponent answers, uniforms consumed
   mcts.npz      MCTS.playout sequences: per-playout v / z / priors and the resulting tree
 """
@@ -282,6 +283,52 @@ def gen_env(mods, out, seed0):
     out["env"] = {k: np.array(v) for k, v in rec.items()}
 
 
+def gen_selfgame(mods, harvest, out, seed0, n_calls=240):
+    """self_play.SelfGame.get_position_self (UNMODIFIED, self_play.py:8-30).  The class cannot be instantiated at the reference HEAD
+    (SelfGame() omits Game.__init__'s required argument and Game lost valid_pos / place_stone(position, color)), so the function is
+    called unbound on a stand-in object that carries exactly what it reads: `state`, `model1.predictor`, `model2.predictor`.
+    Recorded per call: the board before the call, colour, the legal list handed in, the model's probabilities for the encoded
+    input, the position returned and how many np.random uniforms the call consumed (one per attempt of its rejection loop)."""
+    import importlib
+    import types
+    net, ser, chainer = mods["network"], mods["chainer"].serializers, mods["chainer"]
+    sp = importlib.import_module("self_play")
+    gf = mods["game"].GameFunctions
+    m1 = net.SLPolicy(); ser.load_npz("./models/sl_model.npz", m1)
+    m2 = net.SLPolicy(); ser.load_npz("./models/RL/model0.npz", m2)
+    rec = dict(seed=[], state=[], color=[], legal_mask=[], probs=[], action=[], n_draws=[], uniforms=[])
+    picks = [h for h in harvest if len(h[2]) >= 1][::max(1, len(harvest) // n_calls)][:n_calls]
+    skipped = 0
+    for k, (st, c, legal) in enumerate(picks):
+        seed = seed0 + k
+        stub = types.SimpleNamespace(state=st.reshape(8, 8).astype(np.float32).copy(), model1=types.SimpleNamespace(predictor=m1),
+                                     model2=types.SimpleNamespace(predictor=m2))
+        stub.get_position_self = types.MethodType(sp.SelfGame.get_position_self, stub)   # the function recurses through self
+        positions = [[a // 8 + 1, a % 8 + 1] for a in legal]
+        # the model's view of the position (what the function feeds its predictor): colour 1 sees the swapped board
+        view = stub.state.copy()
+        if c == 1:
+            view = view * (3 - view) * (3 - view) / 2
+        X = np.stack([view == 1, view == 2], axis=0).astype(np.float32).reshape(2, 1, 8, 8).transpose(1, 0, 2, 3)
+        pr = (m1 if c == 1 else m2)(chainer.Variable(X)).data.reshape(64).astype(np.float32).copy()
+        np.random.seed(seed)
+        try:
+            pos = stub.get_position_self(c, positions)
+        except RecursionError:      # the reference's own failure mode when the net's mass sits on illegal cells (SURVEY.md 8b): not recorded
+            skipped += 1
+            continue
+        nxt = np.random.random_sample()
+        u = np.random.RandomState(seed).random_sample(4096)
+        nd = int(np.argmax(u == nxt))
+        assert u[nd] == nxt and pos in positions
+        for key, v in dict(seed=seed, state=u8(st).reshape(64), color=c, legal_mask=legal_mask(legal), probs=pr,
+                           action=(pos[0] - 1) * 8 + pos[1] - 1, n_draws=nd, uniforms=u[:64]).items():
+            rec[key].append(v)
+        assert nd <= 64
+    print("selfgame:", len(rec["seed"]), "calls recorded,", skipped, "ended in the reference's RecursionError", flush=True)
+    out["selfgame"] = {k: np.array(v) for k, v in rec.items()}
+
+
 def gen_valuegen(mods, out, seed0, n_games=24):
     """value_self_play.SelfPlay (UNMODIFIED).  The file is dead at the reference HEAD: it imports a module `SLPolicy` that no
     longer exists and loads un-prefixed archives into L.Classifier.  Stand-ins, none of which touch the game logic:
@@ -485,6 +532,8 @@ def main():
         gen_selfplay(mods, out, 777); print("selfplay done", flush=True)
     if not only or "env" in only:
         gen_env(mods, out, 4242); print("env done", flush=True)
+    if not only or "selfgame" in only:
+        gen_selfgame(mods, harvest, out, 31000); print("selfgame done", flush=True)
     if not only or "valuegen" in only:
         gen_valuegen(mods, out, 9090); print("valuegen done", flush=True)
     if not only or "load" in only:

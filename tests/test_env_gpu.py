@@ -119,3 +119,68 @@ def test_self_game_plays_to_the_end(engine, opponent):
     print("SelfGame games finished:", finished, "of 4")
     game = SelfGame(m1, opponent)
     assert callable(game.get_position_self) and callable(game.turn_self) and callable(game.judge_self) and callable(game.show_self)
+
+
+def test_self_game_sampler_equals_reference_calls(engine):
+    """a8: the 239 recorded calls of the unmodified get_position_self (tests/golden/selfgame.npz).  (i) the GPU SLPolicy (precision 3)
+    reproduces the probabilities the reference's model gave for the position (colour 1 sees the swapped board); (ii) iago_sample_unmasked,
+    fed with the reference's probabilities and the call's np.random uniforms, picks the same cell after the same number of draws."""
+    import torch
+    from conftest import load_golden
+    from iago_b200 import Rng, boards
+    g = load_golden("selfgame")
+    keep = ~((g["color"] == 1) & (g["n_draws"] > 1))   # (the reference's in-place re-swap on a colour-1 retry: tests/test_env_oracle.py)
+    g = {k: v[keep] for k, v in g.items()}
+    n = len(g["seed"])
+    assert n >= 230
+    p1, p2 = boards.to_bitboards(g["state"].reshape(n, 8, 8))
+    col = g["color"].astype(np.uint8)
+    engine.load_net(0, model_file("sl_model.npz"))
+    engine.load_net(1, model_file("RL/model0.npz"))
+    dev = torch.device("cuda", 0)
+    for c, slot in ((1, 0), (2, 1)):          # model1 = sl_model plays colour 1, model2 = RL/model0 colour 2 (gen_selfgame)
+        sel = col == c
+        pr = engine.policy_forward_host(slot, p1[sel], p2[sel], c, probs=True, precision=3)
+        assert np.abs(pr - g["probs"][sel]).max() <= 1e-4
+    own = np.where(col == 1, p1, p2)
+    opp = np.where(col == 1, p2, p1)
+    draws = torch.zeros(n, dtype=torch.int32, device=dev)
+    act = engine.sample_unmasked(torch.from_numpy(g["probs"].astype(np.float32)).to(dev), torch.from_numpy(own.view(np.int64).copy()).to(dev),
+                                 torch.from_numpy(opp.view(np.int64).copy()).to(dev), draws,
+                                 Rng.replay_uniforms(torch.from_numpy(g["uniforms"].astype(np.float64)).to(dev)))
+    assert (act.cpu().numpy() == g["action"]).all()
+    assert (draws.cpu().numpy() == g["n_draws"]).all()
+
+
+def test_self_game_equals_restated_loop(engine, opponent, cref):
+    """a8: the facade SelfGame (Philox stream) against oracle/selfgame_ref.py fed with the GPU's own probabilities and the same uniforms:
+    every move, pass, gamelog line, draw count and the final summary."""
+    from iago_b200 import boards, network
+    from iago_b200.self_play import SelfGame
+    from oracle import selfgame_ref
+    m1 = network.SLPolicy(precision=3).load(model_file("sl_model.npz"))
+    m2 = network.SLPolicy(precision=3).load(model_file("RL/model0.npz"))
+
+    def policy_func(st, c):
+        q1, q2 = boards.to_bitboards(st)
+        return engine.policy_forward_host((m1 if c == 1 else m2).slot, q1, q2, c, probs=True, precision=3)[0]
+
+    played = 0
+    for seed in (11, 12, 13, 14):
+        u = np.array([cref.philox_uniform(seed, 0, d, 3) for d in range(20000)])
+        ref = selfgame_ref.RefSelfGame(policy_func, u)
+        game = SelfGame(m1, m2, seed=seed)
+        try:
+            want = ref()
+        except IndexError:                      # the reference's RecursionError case: the product must raise it too
+            with pytest.raises(RecursionError):
+                game()
+            continue
+        got = game()
+        assert got == want and game.gamelog == ref.gamelog
+        assert int(game._draws[0]) == ref.draws and game.play_num == ref.play_num
+        r1, r2 = boards.to_bitboards(ref.state)
+        g1, g2 = boards.to_bitboards(game.state)
+        assert g1[0] == r1[0] and g2[0] == r2[0]
+        played += 1
+    assert played >= 1

@@ -33,3 +33,25 @@ def test_choice_unmasked_is_numpy_choice():
         q = p - p.min()
         a = np.random.RandomState(t).choice(64, p=q / np.sum(q))
         assert a == env_ref.choice_unmasked(p, np.random.RandomState(t).random_sample())
+
+
+def test_unmasked_sampler_equals_reference_get_position_self():
+    """tests/golden/selfgame.npz: 239 calls of the UNMODIFIED self_play.SelfGame.get_position_self (made unbound on a stand-in object,
+    oracle/gen_golden.py gen_selfgame).  The restated sampler, fed with the recorded probabilities and the np.random uniforms of the
+    call's seed, returns the same cell after the same number of draws."""
+    import numpy as np
+    from conftest import load_golden
+    from oracle.env_ref import choice_unmasked
+    g = load_golden("selfgame")
+    # Colour-1 calls that needed a retry are left out: the reference swaps self.state in place on EVERY attempt (self_play.py:9-12), so
+    # its second attempt feeds the net the un-swapped board — the latent bug the product does not reproduce (iago_b200/self_play.py).
+    quirk = (g["color"] == 1) & (g["n_draws"] > 1)
+    assert quirk.sum() <= 3 and (~quirk).sum() >= 230
+    for pr, u, mask, a, nd in zip(g["probs"][~quirk], g["uniforms"][~quirk], g["legal_mask"][~quirk], g["action"][~quirk], g["n_draws"][~quirk]):
+        k = 0
+        while True:
+            idx = choice_unmasked(pr, u[k])
+            k += 1
+            if (int(mask) >> idx) & 1:
+                break
+        assert idx == int(a) and k == int(nd)

@@ -179,3 +179,54 @@ def test_train_set_runs_and_checkpoints(engine, tmp_path):
     assert int(o["t"]) == 1 and o["block3/conv/W/m"].shape == (128, 128, 3, 3) and "bias10/b/v" in o.files
     again = network.SLPolicy().load(tmp_path / "model.npz")   # loadable like any reference archive
     assert again.params["conv9/W"].shape == (1, 128, 1, 1)
+
+
+def test_checkpoint_loads_into_the_unmodified_reference_network(engine, tmp_path):
+    """src/train_rl.py:73-79 writes snapshots with serializers.save_npz and reads them back with load_npz(path, model): a snapshot of
+    this trainer (plain and 'predictor/'-prefixed, as models/rl_model.npz is) is loaded by the chainer stand-in's serializers.load_npz
+    into the UNMODIFIED reference network.SLPolicy (baseline/_ref/network.py) in a separate interpreter, and that model's forward on
+    real positions equals the GPU forward of the trainer's playing slot."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from conftest import ROOT
+    from iago_b200 import boards, network
+    from iago_b200.train_rl import ReinforceTrainer
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isfile(os.path.join(ref_dir, "network.py")):
+        pytest.fail("baseline/_ref/network.py missing: run oracle/fetch_ref.py in the build container")
+    opp = network.SLPolicy().load(model_file("RL/model0.npz"))
+    tr = ReinforceTrainer(model_file("RL/model2.npz"), max_positions=4096, precision=3)
+    tr.train_set(opp, n_games=64, seed=3)     # one real update, so the snapshot is not a file that already existed
+    tr.save_model(tmp_path / "model.npz")
+    tr.save_model(tmp_path / "model_pred.npz", prefix="predictor/")
+    g = np.load(os.path.join(ROOT, "tests", "golden", "nets.npz"))
+    x = g["x"][:96].astype(np.float32)
+    np.save(tmp_path / "x.npy", x)
+    code = f"""
+import sys, json, numpy as np
+sys.path[:0] = [{os.path.join(ROOT, 'oracle', 'chainer_shim')!r}, {ref_dir!r}]
+import chainer
+from chainer import serializers
+import network                                   # the reference's file, unmodified
+chainer.config.train = False
+x = np.load({str(tmp_path / 'x.npy')!r})
+out = {{}}
+for name, path in (("plain", ""), ("pred", "predictor/")):
+    m = network.SLPolicy()
+    f = {str(tmp_path)!r} + ("/model.npz" if name == "plain" else "/model_pred.npz")
+    if path:
+        serializers.load_npz(f, m, path=path)
+    else:
+        serializers.load_npz(f, m)
+    np.save({str(tmp_path)!r} + "/ref_" + name + ".npy", m(chainer.Variable(x)).data)
+print("ok")
+"""
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and r.stdout.strip().endswith("ok"), r.stderr[-2000:]
+    own, opp_b = network.planes_to_bitboards(x)
+    gpu = engine.policy_forward_host(tr.slot, own, opp_b, 1, probs=True, precision=3)
+    for name in ("plain", "pred"):
+        ref = np.load(tmp_path / f"ref_{name}.npy")
+        assert ref.shape == gpu.shape and np.abs(ref - gpu).max() <= 1e-4, name

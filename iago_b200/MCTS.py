@@ -75,9 +75,11 @@ def _mirror(tree, c_puct):
 
 class MCTS:
     def __init__(self, lmbda=0.5, c_puct=1, n_thr=15, time_limit=10, *, n_playouts=None, leaf_batch=1, virtual_loss=1.0,
-                 seed=0, device=0, max_nodes=1 << 18, precision=None, cache_value=True):
+                 seed=None, device=0, max_nodes=1 << 18, precision=None, cache_value=True):
         self.lmbda, self.c_puct, self.n_thr, self.time_limit = lmbda, c_puct, n_thr, time_limit
-        self.n_playouts, self.leaf_batch, self.virtual_loss, self.seed = n_playouts, leaf_batch, virtual_loss, seed
+        from .engine import fresh_seed
+        self.n_playouts, self.leaf_batch, self.virtual_loss = n_playouts, leaf_batch, virtual_loss
+        self.seed = fresh_seed() if seed is None else seed   # None: rollouts differ from run to run, like the reference's np.random draws
         self.precision, self.cache_value = precision, cache_value
         self.policy_net, self.value_net = _load_nets(device)
         self.pool = SearchPool(1, max_nodes=max_nodes, max_leaf_batch=max(leaf_batch, 1), engine=default_engine(device))

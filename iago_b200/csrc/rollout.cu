@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const Ro
                     } else {
                         u64 m53;
                         if (MODE == IAGO_RNG_UNIFORMS)
-                            m53 = __double2ull_rz(a.uniforms[g * a.u_stride + placed] * 9007199254740992.0);
+                            m53 = __double2ull_rz((placed < a.u_stride ? a.uniforms[g * a.u_stride + placed] : 0.5) * 9007199254740992.0);   // never past a short replay stream
                         else {
                             if ((placed & 3) == 0) philox_block(a.seed, gid, (uint32_t)placed >> 2, a.stream_id, rnd);
                             const uint32_t wd = (placed & 2) ? ((placed & 1) ? rnd[3] : rnd[2]) : ((placed & 1) ? rnd[1] : rnd[0]);
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(kPairMaxWarps * 32, 1) rollout_pair_kernel(Rol
                     } else {
                         u64 m53;
                         if (MODE == IAGO_RNG_UNIFORMS)
-                            m53 = __double2ull_rz(a.uniforms[g * a.u_stride + placed] * 9007199254740992.0);
+                            m53 = __double2ull_rz((placed < a.u_stride ? a.uniforms[g * a.u_stride + placed] : 0.5) * 9007199254740992.0);   // never past a short replay stream
                         else {
 #ifndef IAGO_PAIR_NO_COOP_PHILOX
                             // lane h holds Philox block 2 * (placed >> 3) + h: the ten rounds run once per EIGHT stones of a game

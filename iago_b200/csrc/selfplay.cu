@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(128) selfplay_turn_kernel(SelfplayArgs a) {
                 for (u64 m = legal; m; m &= m - 1) total += (double)(expf(lg[__ffsll((long long)m) - 1] - mx) / sum);
                 double u;
                 if (a.rng_mode == IAGO_RNG_UNIFORMS)
-                    u = a.uniforms[g * a.u_stride + placed];
+                    u = placed < a.u_stride ? a.uniforms[g * a.u_stride + placed] : 0.5;   // (a replay stream shorter than the game: never read past it)
                 else
                     u = (double)philox_m53(a.seed, a.game_id0 + (u64)g, (uint32_t)placed, a.stream_id) * (1.0 / 9007199254740992.0);
                 const double t = u * total;

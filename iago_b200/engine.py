@@ -25,6 +25,12 @@ STREAM_ROLLOUT, STREAM_SELFPLAY, STREAM_MCTS, STREAM_ENV, STREAM_VALUEGEN = 0, 1
 DEFAULT_PRECISION = int(os.environ.get("IAGO_DEFAULT_PRECISION", "2"))
 
 
+def fresh_seed():
+    """A seed nobody chose: what `seed=None` means in the facades (the reference draws from np.random / random, which differ from run to
+    run; a fixed default would replay the same games every time)."""
+    return int.from_bytes(os.urandom(8), "little") >> 1
+
+
 def _prec(precision):
     return DEFAULT_PRECISION if precision is None else int(precision)
 

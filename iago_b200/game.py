@@ -64,7 +64,7 @@ class Game:
     both sides' moves and on passes (-1), the `stone_num > 62` shortcut of get_action_auto (game.py:97-98), gamelog format
     and save_gamelog.  Keyword extras are forwarded to iago_b200.MCTS.MCTS (n_playouts, leaf_batch, ...)."""
 
-    def __init__(self, auto, seed=0, verbose=True, **mcts_kw):
+    def __init__(self, auto, seed=None, verbose=True, **mcts_kw):
         import torch
         from datetime import datetime
         from . import network
@@ -82,7 +82,8 @@ class Game:
         self.date = datetime.now().strftime("%Y-%m-%d-%H-%M")
         self.gamelog = "IaGo \n" + self.date + "\n"
         self.mcts = MCTS(**mcts_kw)
-        self.verbose, self.seed = verbose, seed
+        from .engine import fresh_seed
+        self.verbose, self.seed = verbose, (fresh_seed() if seed is None else seed)   # None: a different game every run, as with np.random
         self._draws = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", GameFunctions.device))
 
     def show(self):

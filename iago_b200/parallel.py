@@ -69,3 +69,19 @@ def root_parallel_moves(visits, group=None):
     only_pass = (v[:, :64].sum(dim=1) == 0) & (v[:, 64] > 0)
     best = torch.where(only_pass, torch.full_like(best, -1), best)
     return v, best
+
+
+def barrier(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.barrier(group=group)
+
+
+def broadcast_object(obj, group=None, src=0):
+    """`obj` of rank `src` on every rank (host-side control decisions such as the opponent file of a REINFORCE set)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src, group=group)
+    return box[0]

@@ -59,6 +59,8 @@ class RolloutTrainer:
             pass
 
     def gradient(self, own, opp, action, accumulate=False):
+        if own.numel() == 0 and not accumulate:
+            self.grad.zero_()   # an empty shard contributes nothing
         check(self.lib.iago_rollout_trainer_grad(self.h, C.c_void_p(own.data_ptr()), C.c_void_p(opp.data_ptr()), C.c_void_p(action.data_ptr()),
                                                  own.numel(), C.c_void_p(self.grad.data_ptr()), 1 if accumulate else 0, self.eng._stream(None)))
 
@@ -156,7 +158,10 @@ def train(X_train, y_train, X_test, y_test, policy="sl", epochs=30, minibatch=MI
     n = y_train.shape[0]
     history = []
     for epoch in range(epochs):
-        rands = np.random.choice(n, n, replace=False)           # the same permutation on every rank (same np.random state)
+        # One process: the reference's own draw from the global np.random (train_policy.py:49-50 / train_value.py:38-39).  Several ranks: the
+        # permutation must be THE SAME on every rank (each takes its shard of every minibatch), so it comes from a generator seeded by
+        # (seed, epoch) — the global np.random state of different processes is not synchronised.
+        rands = np.random.choice(n, n, replace=False) if world == 1 else np.random.RandomState((seed * 1000003 + epoch) & 0x7FFFFFFF).permutation(n)
         X_train, y_train = X_train[rands], y_train[rands]
         for idx in range(0, n, minibatch):
             hi = min(idx + minibatch, n)

@@ -66,6 +66,8 @@ class ReinforceTrainer:
     # ---- gradient of SUM c*r over a batch of recorded decisions (device tensors)
     def gradient(self, own, opp, action, reward, accumulate=False, want_probs=False):
         m = own.numel()
+        if m == 0 and not accumulate:
+            self.grad.zero_()   # an empty shard (fewer records than ranks) contributes nothing: not the previous step's all-reduced vector
         probs = torch.empty((m, 64), dtype=torch.float32, device=own.device) if want_probs else None
         for lo in range(0, m, self.max_positions):
             hi = min(m, lo + self.max_positions)
@@ -103,7 +105,9 @@ class ReinforceTrainer:
         out = self.eng.selfplay(self.slot, opponent.slot, n_games, i1, i2, greedy=False, precision=self.precision,
                                 rng=Rng.philox(seed=seed, game_id0=game_id0, stream_id=STREAM_SELFPLAY))
         cap = out["rec_own"].shape[1]
-        valid = torch.arange(cap, device=dev)[None, :] < out["n_rec"].clamp(max=cap)[:, None]
+        if int(out["n_rec"].max()) > cap:
+            raise RuntimeError(f"a game recorded {int(out['n_rec'].max())} learner decisions, more than rec_cap = {cap}")
+        valid = torch.arange(cap, device=dev)[None, :] < out["n_rec"][:, None]
         reward = out["result"].to(torch.float32)[:, None].expand(-1, cap)
         return dict(own=out["rec_own"][valid].contiguous(), opp=out["rec_opp"][valid].contiguous(),
                     action=out["rec_action"][valid].contiguous(), reward=reward[valid].contiguous(),
@@ -189,8 +193,10 @@ def train(model_dir, start="model2.npz", models=1, n_games=64, alpha=1e-3, max_s
     opponent = network.SLPolicy(device=device)
     history, s = [], 0
     while sched.running() and (max_sets is None or s < max_sets):
-        pool = sorted(glob.glob(os.path.join(model_dir, "*.npz")))
-        path = pool[rng.randint(len(pool))]
+        # Rank 0 lists the pool and picks; the choice is broadcast so that every rank faces the same opponent even while rank 0 is
+        # adding snapshots to the directory (a snapshot appears atomically — os.replace below — and a barrier follows it)
+        pool = sorted(f for f in glob.glob(os.path.join(model_dir, "*.npz")) if not f.endswith(".tmp.npz"))
+        path = parallel.broadcast_object(pool[rng.randint(len(pool))], group)
         opponent.load(path)
         st = trainer.play_set(opponent, n_games, seed=seed, game_id0=parallel.game_id0(s, rank, world, n_games))
         trainer.gradient(st["own"], st["opp"], st["action"], st["reward"])
@@ -206,8 +212,13 @@ def train(model_dir, start="model2.npz", models=1, n_games=64, alpha=1e-3, max_s
                     f.write(str(rate) + ", \n")          # src/train_rl.py:69-70
             if snap is not None:
                 os.makedirs(os.path.join(model_dir, "optimizers"), exist_ok=True)
-                trainer.save_model(os.path.join(model_dir, f"model{snap}.npz"))
-                trainer.save_optimizer(os.path.join(model_dir, "optimizers", f"{snap}.npz"))
+                for writer, dst in ((trainer.save_model, os.path.join(model_dir, f"model{snap}.npz")),
+                                    (trainer.save_optimizer, os.path.join(model_dir, "optimizers", f"{snap}.npz"))):
+                    tmp = dst[:-4] + ".tmp.npz"          # never a partially written archive under its final name
+                    writer(tmp)
+                    os.replace(tmp, dst)
+        if snap is not None:
+            parallel.barrier(group)                      # the new pool member exists before any rank lists the pool again
         if on_set:
             on_set(rec)
         s += 1

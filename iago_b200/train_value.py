@@ -63,6 +63,8 @@ class ValueTrainer:
 
     def gradient(self, own, opp, target, accumulate=False, dropout=None, want_pred=False, want_mask=False, position_id0=None):
         m = own.numel()
+        if m == 0 and not accumulate:
+            self.grad.zero_()   # an empty shard contributes nothing (not the previous step's all-reduced vector)
         ratio = self.dropout if dropout is None else float(dropout)
         pred = torch.empty(m, dtype=torch.float32, device=own.device) if want_pred else None
         mask = torch.empty((m, 128), dtype=torch.uint8, device=own.device) if want_mask else None
@@ -134,7 +136,10 @@ def train(train_x, train_y, test_x, test_y, epochs=20, minibatch=MINIBATCH, mode
     n = train_y.shape[0]
     history = []
     for epoch in range(epochs):
-        rands = np.random.choice(n, n, replace=False)
+        # One process: the reference's own draw from the global np.random (train_policy.py:49-50 / train_value.py:38-39).  Several ranks: the
+        # permutation must be THE SAME on every rank (each takes its shard of every minibatch), so it comes from a generator seeded by
+        # (seed, epoch) — the global np.random state of different processes is not synchronised.
+        rands = np.random.choice(n, n, replace=False) if world == 1 else np.random.RandomState((seed * 1000003 + epoch) & 0x7FFFFFFF).permutation(n)
         train_x, train_y = train_x[rands], train_y[rands]
         for idx in range(0, n, minibatch):
             hi = min(idx + minibatch, n)

@@ -71,10 +71,15 @@ class SelfPlay:
         return out["state"][0], int(out["result"][0])
 
 
-def generate(size, path="./value_data5.txt", batch=16384, seed=0, device=0, model0=None, model1=None):
+def generate(size, path="./value_data5.txt", batch=16384, seed=None, device=0, model0=None, model1=None):
     """gen_value_data.main(): `size` games with stop_num ~ randint(4, 64), appended to `path` record by record in the
-    reference's format ("\\n" + str(state) + ", \\r", "\\n", "\\n" + str(result) + ", \\r").  Returns (states, results)."""
-    rs = np.random.RandomState(seed)
+    reference's format ("\\n" + str(state) + ", \\r", "\\n", "\\n" + str(result) + ", \\r").  Returns (states, results).
+    seed=None (default) draws a fresh seed, so that a second call appends NEW games to the file as the reference does; pass a seed to
+    reproduce a run."""
+    from .engine import fresh_seed
+    if seed is None:
+        seed = fresh_seed()
+    rs = np.random.RandomState(seed & 0x7FFFFFFF)
     states, results = [], []
     done = 0
     while done < size:

@@ -614,33 +614,52 @@ def section_mcts(eng, args, rank, world, dev, dist, barrier):
 
 def section_reinforce(eng, args, rank, world, dev, dist, barrier):
     """BASELINE configs[4]: train_rl.py-style REINFORCE self-play, rl_model.npz vs RL/model0.npz, games sharded over the ranks,
-    [gradient | loss | count] all-reduced over NCCL once per update."""
+    [gradient | loss | count] all-reduced over NCCL once per update through the library (iago_comm_allreduce_sum_f32 enqueued on the
+    stream; the Adam step reads the reduced count on the device).  Two measurements: `updates` back-to-back 2,048-game updates, and
+    the config at its full size — 1,048,576 games on 8 GPUs = 131,072 games per GPU (weak scaling: every rank plays its share)."""
     import torch
     from iago_b200 import network, parallel
     from iago_b200.train_rl import ReinforceTrainer
     n = args.reinforce_games
     opp = network.SLPolicy(device=eng.device).load(model_path("RL/model0.npz"))
-    tr = ReinforceTrainer(model_path("rl_model.npz"), alpha=1e-3, max_positions=8192, device=eng.device)
+    comm = parallel.Communicator.from_process_group(eng) if world > 1 else None
+    tr = ReinforceTrainer(model_path("rl_model.npz"), alpha=1e-3, max_positions=8192, device=eng.device, comm=comm)
     tr.train_set(opp, n_games=min(n, 256), seed=args.seed, game_id0=parallel.game_id0(0, rank, world, n))   # warm-up update
+    tr.train_set(opp, n_games=n, seed=args.seed, game_id0=parallel.game_id0(1, rank, world, n))             # and one at full size (workspaces)
     barrier()
+
+    def run(steps, first_step):
+        stats = None
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for i in range(steps):
+            stats = tr.train_set(opp, n_games=n, seed=args.seed, game_id0=parallel.game_id0(first_step + i, rank, world, n),
+                                 want_stats=(i == steps - 1))
+        b.record()
+        barrier()
+        tt = torch.tensor([a.elapsed_time(b) / 1e3], dtype=torch.float64, device=dev)
+        parallel.all_reduce_max_(tt)
+        return float(tt[0]), stats
+
     steps = max(1, args.reinforce_steps)
-    stats = []
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for i in range(steps):
-        stats.append(tr.train_set(opp, n_games=n, seed=args.seed, game_id0=parallel.game_id0(1 + i, rank, world, n)))
-    b.record()
-    barrier()
-    tt = torch.tensor([a.elapsed_time(b) / 1e3], dtype=torch.float64, device=dev)
-    parallel.all_reduce_max_(tt)
-    t = float(tt[0])
-    positions = sum(s["positions"] for s in stats)    # already global: the count rides in the all-reduced vector
-    return {"metric": "reinforce_games_per_s", "value": steps * n * world / t, "unit": "games/s", "ms_per_update": 1e3 * t / steps,
-            "config": {"workload": "REINFORCE sets: self-play (sampled, odd games head/tail switched) + gradient + all-reduce + Adam/WD, "
-                                   "rl_model.npz learner vs RL/model0.npz (BASELINE configs[4])", "games_per_update_per_gpu": n,
-                       "updates": steps, "gradient_arithmetic": "tcgen05: fp16 hi/lo forward, fused bf16 hi/lo data-gradient chain, fp16 (scaled, hi/lo dY) weight-gradient GEMMs; fp32 accumulate"},
-            "positions_per_update": positions / steps, "last": stats[-1],
-            "allreduce_bytes_per_update": (960768 + 2) * 4}
+    t, last = run(steps, 2)
+    out = {"metric": "reinforce_games_per_s", "value": steps * n * world / t, "unit": "games/s", "ms_per_update": 1e3 * t / steps,
+           "config": {"workload": "REINFORCE sets: self-play (sampled, odd games head/tail switched) + gradient + all-reduce + Adam/WD, "
+                                  "rl_model.npz learner vs RL/model0.npz (BASELINE configs[4])", "games_per_update_per_gpu": n,
+                      "updates": steps, "gradient_arithmetic": "tcgen05: fp16 hi/lo forward, fused bf16 hi/lo data-gradient chain, fp16 (scaled, hi/lo dY) weight-gradient GEMMs; fp32 accumulate",
+                      "collective": "ncclAllReduce of 960,770 floats enqueued through iago_comm_allreduce_sum_f32; count read on the device" if comm else "none (one rank)"},
+           "positions_last_update": last.get("positions"), "last": last, "allreduce_bytes_per_update": (960768 + 2) * 4}
+    if args.reinforce_1m_games > 0:
+        per_gpu = args.reinforce_1m_games // 8          # the config is 1 M games on 8 GPUs: every rank plays an eighth of it
+        big_steps = max(1, per_gpu // n)
+        t1, last1 = run(big_steps, 2 + steps)
+        out["config4_full_size"] = {"games": big_steps * n * world, "games_per_gpu": big_steps * n, "updates": big_steps, "seconds": t1,
+                                    "value": big_steps * n * world / t1, "unit": "games/s", "ms_per_update": 1e3 * t1 / big_steps, "last": last1,
+                                    "note": "BASELINE configs[4] at its per-GPU size (1,048,576 games / 8 GPUs): at --gpus 8 this is the full 1 M games"}
+    if comm is not None:
+        comm.close()
+    tr.close()
+    return out
 
 
 def section_valuegen(eng, args, rank, world, dev, dist, barrier):
@@ -698,6 +717,7 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--reinforce-games", type=int, default=2048)
     ap.add_argument("--reinforce-steps", type=int, default=8)
+    ap.add_argument("--reinforce-1m-games", type=int, default=1048576, help="total games of the configs[4] run on 8 GPUs (each rank plays an eighth); 0 = skip")
     ap.add_argument("--valuegen-games", type=int, default=16384)
     ap.add_argument("--sections", default="rollout,selfplay,mcts,reinforce,valuegen", help="extra sections to run after the headline rollout bench")
     ap.add_argument("--selfplay-games", type=int, default=16384)

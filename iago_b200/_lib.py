@@ -66,6 +66,17 @@ SIGNATURES = {
     "iago_reinforce_set_state": [_P, _P, _P, _P, C.c_int64],
     "iago_reinforce_sync_slot": [_P, C.c_int],
     "iago_reinforce_set_option": [_P, C.c_int],
+    "iago_reinforce_sync_slot_async": [_P, C.c_int, _P],
+    "iago_reinforce_adam_step_dev": [_P, _P, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, _P],
+    "iago_reinforce_openings": [_P, C.c_int64, C.c_uint64, C.c_uint64, _P, _P, _P],
+    "iago_reinforce_compact": [_P, C.c_int64, C.c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P],
+    "iago_comm_unique_id": [_P, C.c_int64],
+    "iago_comm_create": [_P, _P, C.c_int, C.c_int, C.POINTER(_P)],
+    "iago_comm_from_nccl": [_P, _P, C.c_int, C.c_int, C.POINTER(_P)],
+    "iago_comm_destroy": [_P],
+    "iago_comm_rank": [_P, C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "iago_comm_allreduce_sum_f32": [_P, _P, C.c_int64, _P],
+    "iago_comm_allreduce_sum_i64": [_P, _P, C.c_int64, _P],
     "iago_trainer_create": [_P, C.c_int, _P, C.c_int64, C.c_int, C.POINTER(_P)],
     "iago_value_grad": [_P, _P, _P, _P, C.c_int64, _P, C.c_int, C.c_double, C.c_uint64, C.c_uint64, _P, _P, _P],
     "iago_policy_eval": [_P, _P, C.c_int, _P, C.c_int64, _P, _P],

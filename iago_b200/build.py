@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-shared", "-o", SO, *objs, "-lcudart"])
+    subprocess.check_call([NVCC, "-shared", "-o", SO, *objs, "-lcudart", "-ldl"])
     return SO
 
 

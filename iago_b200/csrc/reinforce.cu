@@ -869,6 +869,23 @@ __global__ void adam_kernel(float *__restrict__ p, float *__restrict__ mo, float
     p[i] = w - lr_t * m1 / (sqrtf(v1) + eps);
 }
 
+// The same update with the divisor read on the device: count = g[n + 1] of the all-reduced vector [gradient | loss numerator | count]
+// (no host round trip between the all-reduce and the update).  A count of zero (no position on any rank) leaves the parameters alone.
+__global__ void adam_dev_kernel(float *__restrict__ p, float *__restrict__ mo, float *__restrict__ ve, const float *__restrict__ g,
+                                int n, float wd, float beta1, float beta2, float eps, float lr_t) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float count = g[n + 1];
+    if (!(count > 0.0f)) return;
+    const float w = p[i];
+    const float grad = fmaf(wd, w, g[i] * (1.0f / count));
+    const float m1 = mo[i] + (1.0f - beta1) * (grad - mo[i]);
+    const float v1 = ve[i] + (1.0f - beta2) * (grad * grad - ve[i]);
+    mo[i] = m1;
+    ve[i] = v1;
+    p[i] = w - lr_t * m1 / (sqrtf(v1) + eps);
+}
+
 __global__ void set_count_kernel(float *dst, float m, int accumulate) { *dst = accumulate ? *dst + m : m; }
 
 }  // namespace iago
@@ -1161,6 +1178,21 @@ int iago_reinforce_adam_step(iago_trainer *t, const float *grad, double count, d
     return IAGO_OK;
 }
 
+int iago_reinforce_adam_step_dev(iago_trainer *t, const float *grad, double alpha, double beta1, double beta2, double eps, double weight_decay,
+                                 void *stream) {
+    IAGO_REQUIRE(t && grad, "NULL argument");
+    DeviceGuard guard(t->ctx->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    t->t += 1;
+    t->synced_slot = -1;
+    const double fix1 = 1.0 - pow(beta1, (double)t->t), fix2 = 1.0 - pow(beta2, (double)t->t);
+    const float lr_t = (float)(alpha * sqrt(fix2) / fix1);   // Chainer AdamRule.lr
+    adam_dev_kernel<<<(t->np + 255) / 256, 256, 0, s>>>(t->params, t->adam_m, t->adam_v, grad, t->np, (float)weight_decay, (float)beta1, (float)beta2,
+                                                      (float)eps, lr_t);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
 int iago_reinforce_get_state(iago_trainer *t, float *params, float *adam_m, float *adam_v, int64_t *step) {
     IAGO_REQUIRE(t, "NULL argument");
     DeviceGuard guard(t->ctx->device);
@@ -1294,6 +1326,15 @@ int iago_reinforce_sync_slot(iago_trainer *t, int slot) {
         if (rc) return rc;
         rc = iago_load_net(t->ctx, slot, t->kind, h.data(), t->np);
     }
+    if (rc == IAGO_OK) t->synced_slot = slot;
+    return rc;
+}
+
+int iago_reinforce_sync_slot_async(iago_trainer *t, int slot, void *stream) {
+    IAGO_REQUIRE(t, "NULL argument");
+    if (!trunk_slot_holds(t->ctx, slot, t->kind)) return iago_reinforce_sync_slot(t, slot);   // first use: the slot's buffers do not exist yet
+    // the pack kernels follow the Adam step on the same stream: no host synchronisation
+    const int rc = trunk_refresh_slot(t->ctx, slot, t->kind, t->params, stream);
     if (rc == IAGO_OK) t->synced_slot = slot;
     return rc;
 }

@@ -473,3 +473,101 @@ int iago_sample_masked(iago_ctx *ctx, const float *probs, const uint64_t *own, c
 }
 
 }  // extern "C"
+
+namespace iago {
+// ---------------------------------------------------------------- REINFORCE set plumbing on the device (src/train_rl.py:41-53)
+// Openings of a set: game i starts from the standard position; every odd game gets an extra colour-2 stone on one of
+// (2,4), (3,5), (4,2), (5,3) WITHOUT flipping ("switch head and tail", src/train_rl.py:43-46).  The reference picks the cell with
+// Python's random.choice; here it is word 0 of the Philox block (seed, global game id, 0, stream 6) & 3.
+__global__ void __launch_bounds__(256) openings_kernel(long long n, u64 seed, u64 game_id0, u64 *__restrict__ p1, u64 *__restrict__ p2) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    u64 b1 = (1ULL << 28) | (1ULL << 35), b2 = (1ULL << 27) | (1ULL << 36);   // game.py:26-30: (4,3),(3,4) = 1; (3,3),(4,4) = 2
+    if (g & 1) {
+        uint32_t o[4];
+        philox_block(seed, game_id0 + (u64)g, 0, 6u, o);
+        const int cells[4] = {2 * 8 + 4, 3 * 8 + 5, 4 * 8 + 2, 5 * 8 + 3};
+        b2 |= 1ULL << cells[o[0] & 3u];
+    }
+    p1[g] = b1;
+    p2[g] = b2;
+}
+
+// The learner's recorded decisions of n games, [n][rec_cap] with n_rec[g] valid entries, flattened game by game (the order
+// src/train_rl.py:47-50 stacks them in) with the game's result as the reward of each of its records.  One CTA: per-thread counts,
+// block scan, scatter.  out_count[0] = records, out_count[1] = games won by the learner, out_count[2] = largest n_rec (> rec_cap
+// means records were lost: the caller raises).
+__global__ void __launch_bounds__(1024) compact_records_kernel(long long n, int rec_cap, const u64 *__restrict__ rec_own, const u64 *__restrict__ rec_opp,
+                                                               const int8_t *__restrict__ rec_action, const int32_t *__restrict__ n_rec,
+                                                               const int8_t *__restrict__ result, u64 *__restrict__ out_own, u64 *__restrict__ out_opp,
+                                                               int8_t *__restrict__ out_action, float *__restrict__ out_reward, int32_t *__restrict__ out_count) {
+    __shared__ int part[1024];
+    __shared__ int s_wins, s_max;
+    const int t = threadIdx.x;
+    const long long per = (n + 1023) / 1024, lo = (long long)t * per, hi = lo + per < n ? lo + per : n;
+    if (t == 0) { s_wins = 0; s_max = 0; }
+    __syncthreads();
+    int cnt = 0, wins = 0, mx = 0;
+    for (long long g = lo; g < hi; g++) {
+        const int k = n_rec[g];
+        cnt += k < rec_cap ? k : rec_cap;
+        wins += result[g] == 1;
+        mx = k > mx ? k : mx;
+    }
+    part[t] = cnt;
+    if (wins) atomicAdd(&s_wins, wins);
+    if (mx) atomicMax(&s_max, mx);
+    __syncthreads();
+    for (int off = 1; off < 1024; off <<= 1) {   // inclusive scan
+        const int v = t >= off ? part[t - off] : 0;
+        __syncthreads();
+        part[t] += v;
+        __syncthreads();
+    }
+    long long o = part[t] - cnt;
+    for (long long g = lo; g < hi; g++) {
+        const int k = n_rec[g] < rec_cap ? n_rec[g] : rec_cap;
+        const float r = (float)result[g];
+        for (int i = 0; i < k; i++, o++) {
+            out_own[o] = rec_own[g * rec_cap + i];
+            out_opp[o] = rec_opp[g * rec_cap + i];
+            out_action[o] = rec_action[g * rec_cap + i];
+            out_reward[o] = r;
+        }
+    }
+    if (t == 1023) {
+        out_count[0] = part[1023];
+        out_count[1] = s_wins;
+        out_count[2] = s_max;
+    }
+}
+
+}  // namespace iago
+
+using namespace iago;
+
+extern "C" {
+
+int iago_reinforce_openings(iago_ctx *ctx, int64_t n, uint64_t seed, uint64_t game_id0, uint64_t *p1, uint64_t *p2, void *stream) {
+    IAGO_REQUIRE(ctx && p1 && p2 && n >= 0, "NULL argument");
+    if (n == 0) return IAGO_OK;
+    DeviceGuard guard(ctx->device);
+    openings_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(n, seed, game_id0, (u64 *)p1, (u64 *)p2);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+int iago_reinforce_compact(iago_ctx *ctx, int64_t n, int rec_cap, const uint64_t *rec_own, const uint64_t *rec_opp, const int8_t *rec_action,
+                           const int32_t *n_rec, const int8_t *result, uint64_t *out_own, uint64_t *out_opp, int8_t *out_action,
+                           float *out_reward, int32_t *out_count, void *stream) {
+    IAGO_REQUIRE(ctx && rec_own && rec_opp && rec_action && n_rec && result && out_own && out_opp && out_action && out_reward && out_count,
+                 "NULL argument");
+    IAGO_REQUIRE(n >= 0 && rec_cap > 0, "n / rec_cap");
+    DeviceGuard guard(ctx->device);
+    compact_records_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(n, rec_cap, (const u64 *)rec_own, (const u64 *)rec_opp, rec_action, n_rec, result,
+                                                                (u64 *)out_own, (u64 *)out_opp, out_action, out_reward, out_count);
+    IAGO_CUDA(cudaGetLastError());
+    return IAGO_OK;
+}
+
+}  // extern "C"

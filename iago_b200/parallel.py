@@ -5,8 +5,12 @@ Games and search trees are independent units: rank r of R plays
 and every random draw is keyed by the global id, so the union of all ranks' results for a step is exactly what one process
 would produce for the same ids — results never depend on R.  The only exchanges are sum all-reduces of (a) int64 result /
 win counters at report time and (b) the fp32 vector [gradient | loss numerator | position count] once per REINFORCE update.
-torch.distributed is the plumbing (NCCL on GPUs, gloo in the CPU tests).
+On GPUs both run over NCCL through the library's own entry points (iago_comm_*: the all-reduce is enqueued on the engine's stream, the
+Adam step reads the reduced count on the device — no host round trip; `Communicator` below).  torch.distributed launches the processes
+and carries the 128-byte NCCL id; it is also the fallback transport (gloo) of the CPU tests of the host logic.
 """
+import ctypes as C
+
 import torch
 import torch.distributed as dist
 
@@ -85,3 +89,47 @@ def broadcast_object(obj, group=None, src=0):
     box = [obj]
     dist.broadcast_object_list(box, src=src, group=group)
     return box[0]
+
+
+class Communicator:
+    """An NCCL communicator owned by libiago_b200.so (include/iago_b200.h iago_comm_*).  Collectives are enqueued on the engine's
+    current stream and never synchronise the host."""
+
+    def __init__(self, engine, rank, world, unique_id):
+        from ._lib import check
+        self.eng, self.lib, self.rank, self.world = engine, engine.lib, int(rank), int(world)
+        h = C.c_void_p()
+        check(self.lib.iago_comm_create(engine.ctx, C.c_char_p(unique_id), self.rank, self.world, C.byref(h)))
+        self.h = h
+
+    @staticmethod
+    def unique_id(engine):
+        from ._lib import check
+        buf = C.create_string_buffer(128)
+        check(engine.lib.iago_comm_unique_id(buf, 128))
+        return buf.raw
+
+    @classmethod
+    def from_process_group(cls, engine, group=None):
+        """One communicator per process of an initialised torch.distributed group: rank 0 makes the id, the group carries it."""
+        rank, size = world(group)
+        uid = broadcast_object(cls.unique_id(engine) if rank == 0 else None, group)
+        return cls(engine, rank, size, uid)
+
+    def all_reduce_sum_(self, t):
+        from ._lib import check
+        assert t.is_cuda and t.is_contiguous()
+        fn = {torch.float32: self.lib.iago_comm_allreduce_sum_f32, torch.int64: self.lib.iago_comm_allreduce_sum_i64}[t.dtype]
+        check(fn(self.h, C.c_void_p(t.data_ptr()), t.numel(), self.eng._stream(None)))
+        return t
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.iago_comm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -26,7 +26,7 @@ SWITCH_CELLS = [2 * 8 + 4, 3 * 8 + 5, 4 * 8 + 2, 5 * 8 + 3]   # src/train_rl.py:
 
 class ReinforceTrainer:
     def __init__(self, params, alpha=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=5e-4, max_positions=8192,
-                 device=0, slot=None, precision=3, group=None, tensor_cores=True):
+                 device=0, slot=None, precision=3, group=None, tensor_cores=True, comm=None, rec_cap=40):
         self.eng = default_engine(device)
         self.lib = self.eng.lib
         self._tag = f"ReinforceTrainer@{id(self):x}"
@@ -43,6 +43,10 @@ class ReinforceTrainer:
         self.h, self.max_positions = h, int(max_positions)
         check(self.lib.iago_reinforce_set_option(self.h, 1 if tensor_cores else 0))
         self.grad = torch.zeros(N_PARAMS + 2, dtype=torch.float32, device=torch.device("cuda", device))
+        # `comm` (parallel.Communicator): the gradient all-reduce runs over NCCL through the library, enqueued on the stream; without it a
+        # torch.distributed group (gloo in the CPU tests) is the transport, and one process needs neither
+        self.comm, self.rec_cap = comm, int(rec_cap)
+        self._set_bufs = None        # compacted records of a set (device) + their pinned counters
         self.sync_slot()
 
     def close(self):
@@ -78,46 +82,62 @@ class ReinforceTrainer:
                                                C.c_void_p(probs[sl].data_ptr()) if want_probs else None, self.eng._stream(None)))
         return probs
 
-    def update(self):
+    def update(self, want_stats=True):
         """optimizer.update(): all-reduce [gradient | loss numerator | count] over the ranks (the only collective of the training
-        path), WeightDecay hook, Adam, refresh the playing slot. Returns (mean loss, positions)."""
-        loss, count = parallel.mean_gradient_(self.grad, N_PARAMS, self.group)
-        if count <= 0:
-            return 0.0, 0
+        path), WeightDecay hook, Adam, refresh the playing slot.  Everything is enqueued on the stream: the Adam kernel reads the
+        reduced count on the device and the slot refresh follows it.  Returns (mean loss, positions) — one 8-byte read after the
+        whole update has been enqueued — or None with want_stats=False (no host synchronisation at all)."""
+        rank, world = parallel.world(self.group)
+        if self.comm is not None:
+            self.comm.all_reduce_sum_(self.grad)
+        elif world > 1:
+            parallel.all_reduce_sum_(self.grad, self.group)      # torch.distributed transport (gloo in the CPU tests)
         hp = self.hp
-        check(self.lib.iago_reinforce_adam_step(self.h, C.c_void_p(self.grad.data_ptr()), float(count), hp["alpha"], hp["beta1"],
-                                                hp["beta2"], hp["eps"], hp["weight_decay"], self.eng._stream(None)))
-        self.sync_slot()
-        return loss, int(count)
+        stream = self.eng._stream(None)
+        check(self.lib.iago_reinforce_adam_step_dev(self.h, C.c_void_p(self.grad.data_ptr()), hp["alpha"], hp["beta1"], hp["beta2"],
+                                                    hp["eps"], hp["weight_decay"], stream))
+        check(self.lib.iago_reinforce_sync_slot_async(self.h, int(self.slot), stream))
+        if not want_stats:
+            return None
+        num, count = self.grad[N_PARAMS:N_PARAMS + 2].tolist()
+        return (num / count if count > 0 else 0.0), int(count)
 
     # ---- one set of games + one update
-    def play_set(self, opponent, n_games, seed=0, game_id0=0, switch_rng=None):
-        """2N games vs `opponent` (an SLPolicy with a resident slot). Returns flattened learner decisions on the device."""
+    def play_set(self, opponent, n_games, seed=0, game_id0=0):
+        """2N games vs `opponent` (an SLPolicy with a resident slot): openings, games and the flattening of the learner's records all
+        run on the device (iago_reinforce_openings / iago_selfplay / iago_reinforce_compact); one 12-byte read tells the host how many
+        records there are.  Returns the flattened learner decisions (device views) and the set's counters."""
         dev = self.grad.device
-        init = np.tile(boards.start_state(), (n_games, 1, 1))
-        switch_rng = switch_rng or np.random.default_rng(seed + 7919 * (game_id0 + 1))
-        for i in range(1, n_games, 2):   # "switch head and tail" on odd games
-            c = SWITCH_CELLS[int(switch_rng.integers(4))]
-            init[i, c // 8, c % 8] = 2
-        q1, q2 = boards.to_bitboards(init)
-        i1 = torch.from_numpy(q1.view(np.int64).copy()).to(dev)
-        i2 = torch.from_numpy(q2.view(np.int64).copy()).to(dev)
-        out = self.eng.selfplay(self.slot, opponent.slot, n_games, i1, i2, greedy=False, precision=self.precision,
+        stream = self.eng._stream(None)
+        cap = self.rec_cap
+        if self._set_bufs is None or self._set_bufs["n"] < n_games:
+            self._set_bufs = dict(n=n_games, i1=torch.empty(n_games, dtype=torch.int64, device=dev), i2=torch.empty(n_games, dtype=torch.int64, device=dev),
+                                  own=torch.empty(n_games * cap, dtype=torch.int64, device=dev), opp=torch.empty(n_games * cap, dtype=torch.int64, device=dev),
+                                  action=torch.empty(n_games * cap, dtype=torch.int8, device=dev), reward=torch.empty(n_games * cap, dtype=torch.float32, device=dev),
+                                  count=torch.zeros(3, dtype=torch.int32, device=dev), count_host=torch.zeros(3, dtype=torch.int32).pin_memory())
+        b = self._set_bufs
+        i1, i2 = b["i1"][:n_games], b["i2"][:n_games]
+        check(self.lib.iago_reinforce_openings(self.eng.ctx, n_games, int(seed) & (2**64 - 1), int(game_id0), C.c_void_p(i1.data_ptr()),
+                                               C.c_void_p(i2.data_ptr()), stream))
+        out = self.eng.selfplay(self.slot, opponent.slot, n_games, i1, i2, greedy=False, precision=None, rec_cap=cap,
                                 rng=Rng.philox(seed=seed, game_id0=game_id0, stream_id=STREAM_SELFPLAY))
-        cap = out["rec_own"].shape[1]
-        if int(out["n_rec"].max()) > cap:
-            raise RuntimeError(f"a game recorded {int(out['n_rec'].max())} learner decisions, more than rec_cap = {cap}")
-        valid = torch.arange(cap, device=dev)[None, :] < out["n_rec"][:, None]
-        reward = out["result"].to(torch.float32)[:, None].expand(-1, cap)
-        return dict(own=out["rec_own"][valid].contiguous(), opp=out["rec_opp"][valid].contiguous(),
-                    action=out["rec_action"][valid].contiguous(), reward=reward[valid].contiguous(),
-                    wins=int((out["result"] == 1).sum()), games=n_games)
+        p = lambda t: C.c_void_p(t.data_ptr())
+        check(self.lib.iago_reinforce_compact(self.eng.ctx, n_games, cap, p(out["rec_own"]), p(out["rec_opp"]), p(out["rec_action"]), p(out["n_rec"]),
+                                              p(out["result"]), p(b["own"]), p(b["opp"]), p(b["action"]), p(b["reward"]), p(b["count"]), stream))
+        b["count_host"].copy_(b["count"], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        m, wins, longest = (int(v) for v in b["count_host"])
+        if longest > cap:
+            raise RuntimeError(f"a game recorded {longest} learner decisions, more than rec_cap = {cap}")
+        return dict(own=b["own"][:m], opp=b["opp"][:m], action=b["action"][:m], reward=b["reward"][:m], wins=wins, games=n_games)
 
-    def train_set(self, opponent, n_games=64, seed=0, game_id0=0):
+    def train_set(self, opponent, n_games=64, seed=0, game_id0=0, want_stats=True):
         d = self.play_set(opponent, n_games, seed=seed, game_id0=game_id0)
         self.gradient(d["own"], d["opp"], d["action"], d["reward"])
-        loss, count = self.update()
-        return dict(rate=d["wins"] / d["games"], loss=loss, positions=count)
+        st = self.update(want_stats)
+        if st is None:
+            return dict(rate=d["wins"] / d["games"])
+        return dict(rate=d["wins"] / d["games"], loss=st[0], positions=st[1])
 
     # ---- checkpoints in the reference's formats (serializers.save_npz of the model and of the optimizer)
     def state(self):

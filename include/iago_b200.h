@@ -295,6 +295,38 @@ IAGO_API int iago_reinforce_set_state(iago_trainer *t, const float *params, cons
 IAGO_API int iago_reinforce_set_option(iago_trainer *t, int use_tensor_cores);
 /* Makes the trainer's current parameters the policy in net slot `slot` (what self-play then plays with). */
 IAGO_API int iago_reinforce_sync_slot(iago_trainer *t, int slot);
+/* The same, enqueued on `stream` behind the update that produced the parameters, without host synchronisation (a slot that holds no
+ * net of this kind yet falls back to the synchronous path once). */
+IAGO_API int iago_reinforce_sync_slot_async(iago_trainer *t, int slot, void *stream);
+/* iago_reinforce_adam_step with the divisor read ON THE DEVICE: count = grad[n_params + 1] of the (all-reduced) vector
+ * [gradient | loss numerator | count] — the update follows the all-reduce on the stream with no host round trip
+ * (src/train_rl.py:66 on R ranks).  count = 0 leaves the parameters unchanged. */
+IAGO_API int iago_reinforce_adam_step_dev(iago_trainer *t, const float *grad, double alpha, double beta1, double beta2, double eps,
+                                          double weight_decay, void *stream);
+/* Set plumbing of src/train_rl.py:41-53 on the device.  openings: p1 / p2 (DEVICE [n]) = the start position, odd games with the
+ * extra un-flipped colour-2 stone on one of (2,4),(3,5),(4,2),(5,3) ("switch head and tail", :43-46; the cell = Philox(seed, global
+ * game id, stream 6) & 3 where the reference uses random.choice).  compact: the learner records [n][rec_cap] of iago_selfplay
+ * flattened game by game into out_* (DEVICE, capacity n * rec_cap) with reward = the game's result; out_count (DEVICE int32[3]) =
+ * records, games won by the learner, largest n_rec (larger than rec_cap = records were lost). */
+IAGO_API int iago_reinforce_openings(iago_ctx *ctx, int64_t n, uint64_t seed, uint64_t game_id0, uint64_t *p1, uint64_t *p2, void *stream);
+IAGO_API int iago_reinforce_compact(iago_ctx *ctx, int64_t n, int rec_cap, const uint64_t *rec_own, const uint64_t *rec_opp,
+                                    const int8_t *rec_action, const int32_t *n_rec, const int8_t *result, uint64_t *out_own,
+                                    uint64_t *out_opp, int8_t *out_action, float *out_reward, int32_t *out_count, void *stream);
+
+/* ---- collectives: sum all-reduces over NCCL, enqueued on the caller's stream ----
+ * Games and trees are independent; the only exchanges are the fp32 vector [gradient | loss numerator | count] once per REINFORCE
+ * update (src/train_rl.py:55-66 on R ranks) and int64 result counters at report time.  An iago_comm wraps an ncclComm_t: adopt one
+ * the host created (iago_comm_from_nccl; the caller keeps ownership), or create one: rank 0 calls iago_comm_unique_id and sends the
+ * 128 bytes to the other ranks by any host channel, then every rank calls iago_comm_create.  NCCL is bound at run time
+ * (libnccl.so.2); without it these entry points return IAGO_E_STATE. */
+typedef struct iago_comm iago_comm;
+IAGO_API int iago_comm_unique_id(char *id, int64_t bytes);
+IAGO_API int iago_comm_create(iago_ctx *ctx, const char *id, int rank, int world, iago_comm **out);
+IAGO_API int iago_comm_from_nccl(iago_ctx *ctx, void *nccl_comm, int rank, int world, iago_comm **out);
+IAGO_API int iago_comm_destroy(iago_comm *c);
+IAGO_API int iago_comm_rank(iago_comm *c, int *rank, int *world);
+IAGO_API int iago_comm_allreduce_sum_f32(iago_comm *c, float *buf, int64_t count, void *stream);
+IAGO_API int iago_comm_allreduce_sum_i64(iago_comm *c, int64_t *buf, int64_t count, void *stream);
 
 /* ---- supervised trainers: train_policy.py:16-84 (SL policy / rollout policy), train_value.py:9-70 ----
  * The SL policy is trained with the REINFORCE entry points above (reward 1 for every record gives exactly

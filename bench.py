@@ -472,7 +472,7 @@ def section_selfplay(eng, args, rank, world, dev, dist, barrier):
         eng.selfplay(0, 0, n, rng=Rng.philox(seed=1, stream_id=1), **kw)  # warm-up at full size (workspaces, clocks)
         barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        fwd = 0
+        fwd = evaluated = 0
         res = None
         with ClockSampler(dev.index or 0) as clk:
             for i in range(steps):
@@ -480,10 +480,11 @@ def section_selfplay(eng, args, rank, world, dev, dist, barrier):
                 res = eng.selfplay(0, 0, n, rng=Rng.philox(seed=args.seed, game_id0=(i * world + rank) * n, stream_id=1), **kw)
                 ev[i][1].record()
                 fwd += res["stats"]["forwards"]
+                evaluated += res["stats"]["positions"]
             barrier()
         step_ms = [a.elapsed_time(b) for a, b in ev]
         tt = torch.tensor([sum(step_ms) / 1e3], dtype=torch.float64, device=dev)
-        cc = torch.tensor([steps * n, fwd * n], dtype=torch.int64, device=dev)
+        cc = torch.tensor([steps * n, evaluated], dtype=torch.int64, device=dev)   # positions the nets really evaluated (request lists)
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.all_reduce(cc, op=dist.ReduceOp.SUM)
@@ -592,6 +593,33 @@ def section_mcts(eng, args, rank, world, dev, dist, barrier):
             res["cpu_baseline"] = dict(py, unit="playouts/s", value=py.get("playouts_per_s"), cores=1, kind="reference",
                                        sample="unmodified MCTS.playout under the numpy chainer stand-in")
     pool.close()
+    # One game searched by ALL ranks at once (the optional exchange for a single tree): every rank runs N / world playouts
+    # on the same root under its own global tree id (its rollouts draw from different Philox streams), the root visit counts [65] are
+    # summed over the ranks (parallel.root_parallel_moves) and the move is chosen from the sum.  At one rank this is the single-tree
+    # latency figure below; the ratio to it is what root parallelism buys.
+    if world > 1:
+        from iago_b200 import parallel
+        share = N // world
+        rp = SearchPool(1, max_nodes=65536, max_leaf_batch=B, tree_id0=20_000_000 + rank, engine=eng)
+        kw = dict(slot_policy=0, slot_value=1, lmbda=0.5, c_puct=1, n_thr=15, leaf_batch=B, virtual_loss=1.0, precision=None,
+                  cache_value=True, seed=args.seed)
+        rp.set_roots(p1, p2, 2, reset_tree=True)
+        rp.search(2 * B, **kw)
+        rp.set_roots(p1, p2, 2, reset_tree=True)
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        rp.search(share, **kw)
+        v, _, _ = rp.root_stats()
+        vs, best_rp = parallel.root_parallel_moves(torch.from_numpy(v).to(dev))
+        b.record()
+        barrier()
+        tt = torch.tensor([a.elapsed_time(b) / 1e3], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        res["root_parallel"] = {"ms_per_move": 1e3 * float(tt[0]), "playouts_per_rank": share, "playouts_total": share * world,
+                                "best_move": int(best_rp[0]), "root_visits_total": int(vs[0].sum()),
+                                "note": "one tree per rank on the same root, root visit counts all-reduced (one int64[65] sum), move from the sum"}
+        rp.close()
     if rank == 0:
         # one tree (the reference's usage: one game, one search per move): latency of a 16,384-playout move
         one = SearchPool(1, max_nodes=65536, max_leaf_batch=B, tree_id0=10_000_000, engine=eng)

@@ -35,7 +35,8 @@ struct SelfplayArgs {
     long long u_stride;
     const int8_t *forced;
     long long f_stride;
-    const float *logits;  // [n][64] from the trunk for the side to move
+    const float *logits;  // [requests][64] from the trunk for the side to move
+    const int32_t *req_index;   // [n] row of `logits` that holds game g's position, -1 = no evaluation was requested (see selfplay_request_kernel)
     // records of the learner's decisions (rl_self_play.py:134-138)
     u64 *rec_own, *rec_opp;
     int8_t *rec_action;
@@ -44,6 +45,42 @@ struct SelfplayArgs {
     int8_t *move_log;     // [n][64] nullable
     int32_t *active;      // device counter: games with stone_num < 64 after this half-step
 };
+
+// The positions the side to move needs its net for: games that are still running and have a CHOICE (two or more legal moves).
+// The reference evaluates the net at batch size 1 whenever a move exists (rl_self_play.py:111-127); for a single legal move the
+// outcome does not depend on it, and a finished game or a pass never reaches get_action — so those lanes cost no trunk work here.
+// Writes the compact request list (boards + colour), the game -> row map and the list length; `evaluated` accumulates the lengths.
+__global__ void __launch_bounds__(128) selfplay_request_kernel(const u64 *__restrict__ p1, const u64 *__restrict__ p2, const int32_t *__restrict__ stone_num,
+                                                               long long n, int color, u64 *__restrict__ req_p1, u64 *__restrict__ req_p2,
+                                                               uint8_t *__restrict__ req_color, int32_t *__restrict__ req_index, int32_t *__restrict__ count,
+                                                               unsigned long long *__restrict__ evaluated) {
+    const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool want = false;
+    u64 b1 = 0, b2 = 0;
+    if (g < n && stone_num[g] < 64) {
+        b1 = p1[g]; b2 = p2[g];
+        const u64 legal = color == 1 ? legal_moves(b1, b2) : legal_moves(b2, b1);
+        want = (legal & (legal - 1)) != 0;   // at least two bits set
+    }
+    // one atomic per warp: rows of a warp's games are consecutive
+    const unsigned ballot = __ballot_sync(0xFFFFFFFFu, want);
+    int base = 0;
+    if ((threadIdx.x & 31) == 0 && ballot) {
+        base = atomicAdd(count, __popc(ballot));
+        atomicAdd(evaluated, (unsigned long long)__popc(ballot));
+    }
+    base = __shfl_sync(0xFFFFFFFFu, base, 0);
+    if (g < n) {
+        int row = -1;
+        if (want) {
+            row = base + __popc(ballot & ((1u << (threadIdx.x & 31)) - 1u));
+            req_p1[row] = b1;
+            req_p2[row] = b2;
+            req_color[row] = (uint8_t)color;
+        }
+        req_index[g] = row;
+    }
+}
 
 __global__ void __launch_bounds__(128) selfplay_turn_kernel(SelfplayArgs a) {
     const long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -59,8 +96,13 @@ __global__ void __launch_bounds__(128) selfplay_turn_kernel(SelfplayArgs a) {
         if (a.rng_mode == IAGO_RNG_FORCED) {
             k = placed < a.f_stride ? a.forced[g * a.f_stride + placed] : -1;
         } else {
-            const float *lg = a.logits + g * 64;
-            if (a.select == SEL_GREEDY) {
+            const int ri = a.req_index[g];
+            const float *lg = a.logits + (long long)(ri < 0 ? 0 : ri) * 64;
+            if (ri < 0) {
+                // one legal move: the choice does not depend on the net (arg-max over one cell; np.random.choice over one non-zero
+                // probability), so no forward was requested for this game.  The sampler still consumes its uniform: `placed` advances.
+                k = __ffsll((long long)legal) - 1;
+            } else if (a.select == SEL_GREEDY) {
                 // arg-max of the logits over legal moves, lowest index on ties (BASELINE configs[2])
                 float best = -3.0e38f;
                 for (u64 m = legal; m; m &= m - 1) {
@@ -297,7 +339,11 @@ struct SelfplayWs {
     int32_t *stone_num = nullptr, *placed = nullptr, *active = nullptr;
     uint8_t *pass_flg = nullptr, *c1 = nullptr, *c2 = nullptr;
     float *logits = nullptr;
-    int32_t *h_active = nullptr;  // pinned
+    int32_t *h_active = nullptr;  // pinned: [0] games still running, [1..2] = evaluated positions (64-bit)
+    u64 *req_p1 = nullptr, *req_p2 = nullptr;
+    uint8_t *req_color = nullptr;
+    int32_t *req_index = nullptr, *req_count = nullptr;
+    unsigned long long *evaluated = nullptr;
     int32_t *env_err = nullptr;
 };
 
@@ -306,6 +352,11 @@ static int ws_ensure(iago_ctx *ctx, long long n, SelfplayWs **out) {
     SelfplayWs *w = static_cast<SelfplayWs *>(ctx->selfplay);
     if (w->cap < n) {
         cudaFree(w->stone_num); cudaFree(w->placed); cudaFree(w->pass_flg); cudaFree(w->c1); cudaFree(w->c2); cudaFree(w->logits);
+        cudaFree(w->req_p1); cudaFree(w->req_p2); cudaFree(w->req_color); cudaFree(w->req_index);
+        IAGO_CUDA(cudaMalloc(&w->req_p1, n * 8));
+        IAGO_CUDA(cudaMalloc(&w->req_p2, n * 8));
+        IAGO_CUDA(cudaMalloc(&w->req_color, n));
+        IAGO_CUDA(cudaMalloc(&w->req_index, n * 4));
         IAGO_CUDA(cudaMalloc(&w->stone_num, n * 4));
         IAGO_CUDA(cudaMalloc(&w->placed, n * 4));
         IAGO_CUDA(cudaMalloc(&w->pass_flg, n));
@@ -316,7 +367,9 @@ static int ws_ensure(iago_ctx *ctx, long long n, SelfplayWs **out) {
     }
     if (!w->active) {
         IAGO_CUDA(cudaMalloc(&w->active, 4));
-        IAGO_CUDA(cudaMallocHost(&w->h_active, 4));
+        IAGO_CUDA(cudaMalloc(&w->req_count, 4));
+        IAGO_CUDA(cudaMalloc(&w->evaluated, 8));
+        IAGO_CUDA(cudaMallocHost(&w->h_active, 16));
     }
     *out = w;
     return IAGO_OK;
@@ -327,6 +380,7 @@ void selfplay_destroy(iago_ctx *ctx) {
     SelfplayWs *w = static_cast<SelfplayWs *>(ctx->selfplay);
     cudaFree(w->stone_num); cudaFree(w->placed); cudaFree(w->pass_flg); cudaFree(w->c1); cudaFree(w->c2); cudaFree(w->logits);
     cudaFree(w->active);
+    cudaFree(w->req_p1); cudaFree(w->req_p2); cudaFree(w->req_color); cudaFree(w->req_index); cudaFree(w->req_count); cudaFree(w->evaluated);
     cudaFree(w->env_err);
     if (w->h_active) cudaFreeHost(w->h_active);
     delete w;
@@ -361,16 +415,22 @@ int iago_selfplay(iago_ctx *ctx, int slot_learner, int slot_opponent, int64_t n,
                                                w->placed, n_rec, move_log, w->c1, w->c2, n);
     IAGO_CUDA(cudaGetLastError());
     SelfplayArgs a{p1, p2, w->stone_num, w->pass_flg, w->placed, n, 1, select, rng->mode, rng->stream_id, rng->seed,
-                   rng->game_id0, rng->uniforms, rng->u_stride, rng->forced, rng->f_stride, w->logits, (u64 *)rec_own,
+                   rng->game_id0, rng->uniforms, rng->u_stride, rng->forced, rng->f_stride, w->logits, w->req_index, (u64 *)rec_own,
                    (u64 *)rec_opp, rec_action, n_rec, rec_cap, move_log, w->active};
     const bool need_net = rng->mode != IAGO_RNG_FORCED;
     long long pairs = 0, forwards = 0;
+    IAGO_CUDA(cudaMemsetAsync(w->evaluated, 0, 8, s));
     for (;;) {
         IAGO_CUDA(cudaMemsetAsync(w->active, 0, 4, s));
         for (int color = 1; color <= 2; color++) {
             if (need_net) {
-                rc = trunk_launch(ctx, color == 1 ? slot_learner : slot_opponent, 0, final_p1, final_p2,
-                                  color == 1 ? w->c1 : w->c2, n, w->logits, 0, precision, s);
+                // the trunk runs on the games that are alive and have a choice (a device-built list with a device-side length)
+                IAGO_CUDA(cudaMemsetAsync(w->req_count, 0, 4, s));
+                selfplay_request_kernel<<<grid, 128, 0, s>>>(p1, p2, w->stone_num, n, color, w->req_p1, w->req_p2, w->req_color, w->req_index,
+                                                            w->req_count, w->evaluated);
+                IAGO_CUDA(cudaGetLastError());
+                rc = trunk_launch(ctx, color == 1 ? slot_learner : slot_opponent, 0, (const uint64_t *)w->req_p1, (const uint64_t *)w->req_p2,
+                                  w->req_color, n, w->logits, 0, precision, s, w->req_count);
                 if (rc) return rc;
                 forwards++;
             }
@@ -392,6 +452,9 @@ int iago_selfplay(iago_ctx *ctx, int slot_learner, int slot_opponent, int64_t n,
     if (stats) {
         stats[0] = pairs;
         stats[1] = forwards;
+        IAGO_CUDA(cudaMemcpyAsync(w->h_active + 2, w->evaluated, 8, cudaMemcpyDeviceToHost, s));
+        IAGO_CUDA(cudaStreamSynchronize(s));
+        stats[2] = need_net ? (int64_t)*reinterpret_cast<unsigned long long *>(w->h_active + 2) : 0;   // positions the nets evaluated
     }
     return IAGO_OK;
 }

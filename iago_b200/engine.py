@@ -288,14 +288,14 @@ class Engine:
                    rec_action=torch.full((n, rec_cap), -1, dtype=torch.int8, device=dev),
                    n_rec=torch.empty(n, dtype=torch.int32, device=dev),
                    moves=torch.empty((n, 64), dtype=torch.int8, device=dev) if want_moves else None)
-        stats = (C.c_int64 * 2)()
+        stats = (C.c_int64 * 3)()
         r, keep = self._rng_struct(rng, n, host=False)
         check(self.lib.iago_selfplay(self.ctx, int(slot_learner), int(slot_opponent), n, _ptr(init_p1), _ptr(init_p2),
                                      1 if greedy else 0, _prec(precision), C.byref(r), _ptr(out["final_p1"]),
                                      _ptr(out["final_p2"]), _ptr(out["result"]), _ptr(out["rec_own"]), _ptr(out["rec_opp"]),
                                      _ptr(out["rec_action"]), _ptr(out["n_rec"]), int(rec_cap), _ptr(out["moves"]),
                                      C.cast(stats, C.c_void_p), self._stream(stream)))
-        out["stats"] = dict(turn_pairs=int(stats[0]), forwards=int(stats[1]))
+        out["stats"] = dict(turn_pairs=int(stats[0]), forwards=int(stats[1]), positions=int(stats[2]))
         return out
 
     def value_selfplay(self, slot_sl, slot_rl, stop_num, precision=None, rng: Optional[Rng] = None, stream=None):

@@ -170,7 +170,9 @@ IAGO_API int iago_value_forward(iago_ctx *ctx, int slot, const uint64_t *p1, con
  *   rec_own/rec_opp [n][rec_cap], rec_action [n][rec_cap], n_rec [n] : the learner's pre-move positions (own =
  *                     learner's stones; the reference stores the same board with colours swapped,
  *                     rl_self_play.py:134-138) and chosen actions
- *   move_log [n][64] nullable; stats (HOST int64[2], nullable) = {turn pairs executed, trunk forwards launched}
+ *   move_log [n][64] nullable; stats (HOST int64[3], nullable) = {turn pairs executed, trunk launches, positions the nets evaluated}
+ * A trunk launch covers only the games that are still running and have a choice (>= 2 legal moves): a device-built request list with
+ * a device-side length; a single legal move is played without the net (its uniform is still consumed).
  * Synchronises the stream once per pair of turns (termination test).  All other pointers are device pointers. */
 IAGO_API int iago_selfplay(iago_ctx *ctx, int slot_learner, int slot_opponent, int64_t n, const uint64_t *init_p1,
                            const uint64_t *init_p2, int select, int precision, const iago_rng *rng, uint64_t *final_p1,

@@ -230,3 +230,21 @@ print("ok")
     for name in ("plain", "pred"):
         ref = np.load(tmp_path / f"ref_{name}.npy")
         assert ref.shape == gpu.shape and np.abs(ref - gpu).max() <= 1e-4, name
+    # The forward half of the REINFORCE loss (src/train_rl.py:55-64) on the unmodified reference network: pred = model1(x) are
+    # PROBABILITIES, c = softmax_cross_entropy(pred, y, reduce='no') applies log-softmax to them again, loss numerator = sum(c * r).
+    # The trainer's own forward + loss (vector element [N_PARAMS] of iago_reinforce_grad) must give the same number.
+    import torch
+    from iago_b200.train_rl import N_PARAMS
+    ref = np.load(tmp_path / "ref_plain.npy").astype(np.float64)
+    rs = np.random.RandomState(5)
+    y = rs.randint(0, 64, size=len(x))
+    rew = rs.choice([-1.0, 0.0, 1.0], size=len(x))
+    z = ref - ref.max(axis=1, keepdims=True)
+    c = -(z[np.arange(len(x)), y] - np.log(np.exp(z).sum(axis=1)))          # Chainer's softmax_cross_entropy(reduce='no'), restated
+    want = float((c * rew).sum())
+    dev = tr.grad.device
+    t = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dt).to(dev)
+    probs = tr.gradient(t(own.view(np.int64), torch.int64), t(opp_b.view(np.int64), torch.int64), t(y, torch.int8), t(rew, torch.float32), want_probs=True)
+    got = float(tr.grad[N_PARAMS])
+    assert np.abs(probs.cpu().numpy() - ref).max() <= 1e-4
+    assert abs(got - want) <= 1e-4 * max(1.0, abs(want)) and int(tr.grad[N_PARAMS + 1]) == len(x)

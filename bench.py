@@ -637,6 +637,22 @@ def section_mcts(eng, args, rank, world, dev, dist, barrier):
         res["single_tree"] = {"playouts_per_s": N / t1, "ms_per_move": 1e3 * t1, "best_move": int(one.root_stats()[2][0]),
                               "note": "one search tree on one GPU (latency-bound: 64 dependent waves of 256 leaves)"}
         one.close()
+        # the same move budget as 8 root-parallel trees on this GPU (MCTS(root_trees=8)): 8 dependent waves instead of 64
+        R = 8
+        rp1 = SearchPool(R, max_nodes=65536, max_leaf_batch=B, tree_id0=30_000_000, engine=eng)
+        rp1.set_roots(p1, p2, 2, reset_tree=True)
+        rp1.search(2 * B, **kw)
+        rp1.set_roots(p1, p2, 2, reset_tree=True)
+        a.record()
+        rp1.search(N // R, **kw)
+        v8 = rp1.root_stats()[0].astype(np.int64).sum(axis=0)
+        b.record()
+        torch.cuda.synchronize()
+        t8 = a.elapsed_time(b) / 1e3
+        res["single_game_root_trees_8"] = {"playouts_per_s": N / t8, "ms_per_move": 1e3 * t8, "best_move": int(np.argmax(v8[:64])),
+                                           "note": "one game, 8 independent trees of 2,048 playouts on one GPU, move from the summed root visits "
+                                                   "(opt-in MCTS(root_trees=8); not the reference's single-tree algorithm)"}
+        rp1.close()
     return res
 
 

@@ -75,14 +75,19 @@ def _mirror(tree, c_puct):
 
 class MCTS:
     def __init__(self, lmbda=0.5, c_puct=1, n_thr=15, time_limit=10, *, n_playouts=None, leaf_batch=1, virtual_loss=1.0,
-                 seed=None, device=0, max_nodes=1 << 18, precision=None, cache_value=True):
+                 seed=None, device=0, max_nodes=1 << 18, precision=None, cache_value=True, root_trees=1):
         self.lmbda, self.c_puct, self.n_thr, self.time_limit = lmbda, c_puct, n_thr, time_limit
         from .engine import fresh_seed
         self.n_playouts, self.leaf_batch, self.virtual_loss = n_playouts, leaf_batch, virtual_loss
         self.seed = fresh_seed() if seed is None else seed   # None: rollouts differ from run to run, like the reference's np.random draws
         self.precision, self.cache_value = precision, cache_value
         self.policy_net, self.value_net = _load_nets(device)
-        self.pool = SearchPool(1, max_nodes=max_nodes, max_leaf_batch=max(leaf_batch, 1), engine=default_engine(device))
+        # root_trees = R > 1: root parallelisation on one GPU — R independent trees on the same root (tree ids 0..R-1: their rollouts
+        # draw from different Philox streams), n_playouts / R playouts each in lockstep waves, the move chosen from the SUMMED root
+        # visit counts (the single-GPU form of SURVEY.md 8e's optional exchange; parallel.root_parallel_moves is the multi-GPU form).
+        # Not the reference's algorithm (one tree): opt-in.  A 16,384-playout move takes 64 dependent waves with one tree, 8 with R = 8.
+        self.root_trees = max(1, int(root_trees))
+        self.pool = SearchPool(self.root_trees, max_nodes=max_nodes, max_leaf_batch=max(leaf_batch, 1), engine=default_engine(device))
         self._fresh = True
         self.playouts = 0  # playouts run by the last get_move
 
@@ -120,21 +125,26 @@ class MCTS:
         self._fresh = False
         self.playouts = 0
         if self.n_playouts is not None:
-            self._search(int(self.n_playouts))
+            self._search(-(-int(self.n_playouts) // self.root_trees))
         else:
             start = time.time()
             chunk = max(self.leaf_batch, 1) * 16
             while time.time() - start < self.time_limit:
                 self._search(chunk)
-        _, _, best = self.pool.root_stats()
-        if best[0] == -2:
+        visits, _, best = self.pool.root_stats()
+        if (best == -2).all():
             raise ValueError("max() arg is an empty sequence")  # what MCTS.py:147 raises when the root was never expanded
-        return int(best[0])
+        if self.root_trees == 1:
+            return int(best[0])
+        v = visits.astype(np.int64).sum(axis=0)              # summed over the trees; index 64 = the pass child
+        if v[:64].sum() == 0:
+            return -1
+        return int(np.argmax(v[:64]))                        # first maximum = lowest action, the reference's tie rule (MCTS.py:147)
 
     def update_with_move(self, last_move):
         if self._fresh:
             return
-        self.pool.advance(np.array([last_move], np.int8))
+        self.pool.advance(np.full(self.root_trees, last_move, np.int8))
 
     @property
     def root(self):

@@ -1,4 +1,5 @@
-// reinforce.cu — K6: the REINFORCE update of src/train_rl.py:55-66 for the SL-size policy net, fp32 on the CUDA cores.
+// reinforce.cu — K6: the REINFORCE / supervised update of src/train_rl.py:55-66 for the SL-size nets: heads, weight gradients (tcgen05
+// GEMMs; an all-fp32 CUDA-core version of every kernel is kept as the checker, iago_reinforce_set_option(0)), bias gradients, Adam.
 //
 // Reference: x = stack([states==1, states==2]) (channel 0 = opponent, channel 1 = learner; the recorded states are
 // colour-swapped, rl_self_play.py:134-138), pred = SLPolicy(x) — already softmax PROBABILITIES (network.py:47) —

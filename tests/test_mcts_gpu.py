@@ -258,3 +258,19 @@ def test_config4_leaf_batch_256_16384_playouts(engine, nets, golden_simulate, cr
           f"move {v_dev[int(best[0])]} / {v_seq[seq.best_move()]} of {N}; total-variation distance of the root-visit distributions {tv:.3f}")
     assert int(best[0]) == seq.best_move()
     assert tv <= 0.45   # measured 0.16 (opening after 19) and 0.30 (mid-game: near-equal moves trade visits under virtual loss); the decision is the same
+
+
+def test_root_trees_option_agrees_with_one_tree(engine, cref):
+    """MCTS(root_trees=8): eight independent 2,048-playout trees on the same root, move from the summed root visits.  On the opening
+    after 19 and on a mid-game root the decision equals the one-tree search's with the same total budget."""
+    from iago_b200.MCTS import MCTS
+    state = cref.start_board()
+    cref.place_stone(state, 19, 1)
+    one = MCTS(n_playouts=16384, leaf_batch=256, seed=5)
+    many = MCTS(n_playouts=16384, leaf_batch=256, seed=5, root_trees=8)
+    a1, a8 = one.get_move(state, 2), many.get_move(state, 2)
+    assert a1 == a8 and a8 in cref.legal_actions(state, 2)
+    assert many.playouts == 2048 and one.playouts == 16384
+    many.update_with_move(a8)            # all eight trees re-root
+    cref.place_stone(state, a8, 2)
+    assert many.get_move(state, 1) in cref.legal_actions(state, 1)

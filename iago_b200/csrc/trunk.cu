@@ -155,26 +155,32 @@ __device__ __forceinline__ void store_act16(uint8_t *smem, const float (&x)[16],
 }
 
 // precision 2: 16 values of this thread's tile row (as 8 packed pairs) -> fp16 hi parts (2 groups of 8 channels) and one 16-channel row
-// of each FP8 tile: A8 = e4m3(hi), AL8 = e4m3((x - hi) * 2^11).  Packed fp32x2 arithmetic and the fp16x2 -> e4m3x2 conversion keep this at
-// 7 instructions per pair (the pass is issue-bound: it is what a layer boundary waits for).
-__device__ __forceinline__ void store_act16_p2(uint8_t *smem, const uint64_t (&x2)[8], int col0, uint32_t row_off) {
-    uint32_t hw[8], h8[4], l8[4];
-    const uint64_t k2048 = f32x2(2048.0f, 2048.0f), kneg = f32x2(-1.0f, -1.0f);
+// of each FP8 tile: A8 = e4m3(hi), AL8 = e4m3((x - hi) * 2^11).  Two steps, so that the hi tile — all the next layer's fp16 MMAs need —
+// can be published before the FP8 conversions are done.  Packed fp32x2 arithmetic and the fp16x2 -> e4m3x2 conversion keep the whole
+// at 7 instructions per pair (the pass is issue-bound: it is what a layer boundary waits for).
+__device__ __forceinline__ void store_act16_p2_hi(uint8_t *smem, const uint64_t (&x2)[8], int col0, uint32_t row_off, uint32_t (&hw)[8]) {
 #pragma unroll
     for (int e = 0; e < 8; e++) {
         float f0, f1;
         f32x2_unpack(x2[e], f0, f1);
         const __half2 h = __floats2half2_rn(f0, f1);
         hw[e] = *reinterpret_cast<const uint32_t *>(&h);
-        const float2 hf = __half22float2(h);
+    }
+    *reinterpret_cast<uint4 *>(smem + OFF_AHI + (uint32_t)(col0 >> 3) * kGroupBytes + row_off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+    *reinterpret_cast<uint4 *>(smem + OFF_AHI + (uint32_t)((col0 >> 3) + 1) * kGroupBytes + row_off) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
+}
+__device__ __forceinline__ void store_act16_p2_f8(uint8_t *smem, const uint64_t (&x2)[8], const uint32_t (&hw)[8], int col0, uint32_t row_off) {
+    uint32_t h8[4], l8[4];
+    const uint64_t k2048 = f32x2(2048.0f, 2048.0f), kneg = f32x2(-1.0f, -1.0f);
+#pragma unroll
+    for (int e = 0; e < 8; e++) {
+        const float2 hf = __half22float2(*reinterpret_cast<const __half2 *>(&hw[e]));
         const uint64_t lo = mul2(fma2(f32x2(hf.x, hf.y), kneg, x2[e]), k2048);   // (x - hi) * 2^11, exact until the FP8 rounding
         float l0, l1;
         f32x2_unpack(lo, l0, l1);
         const uint32_t a8 = e4m3x2_from_half2(hw[e]), b8 = e4m3x2_from_floats(l0, l1);
         if ((e & 1) == 0) { h8[e >> 1] = a8; l8[e >> 1] = b8; } else { h8[e >> 1] |= a8 << 16; l8[e >> 1] |= b8 << 16; }
     }
-    *reinterpret_cast<uint4 *>(smem + OFF_AHI + (uint32_t)(col0 >> 3) * kGroupBytes + row_off) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
-    *reinterpret_cast<uint4 *>(smem + OFF_AHI + (uint32_t)((col0 >> 3) + 1) * kGroupBytes + row_off) = make_uint4(hw[4], hw[5], hw[6], hw[7]);
     const uint32_t off = (uint32_t)(col0 >> 4) * kGroupBytes + row_off;
     *reinterpret_cast<uint4 *>(smem + OFF_ALO + off) = make_uint4(h8[0], h8[1], h8[2], h8[3]);
     *reinterpret_cast<uint4 *>(smem + OFF_ALO + kA8Bytes + off) = make_uint4(l8[0], l8[1], l8[2], l8[3]);
@@ -222,7 +228,8 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
     const uint32_t bar_acc = bar_empty + 8 * kMaxStages;  // [2] accumulator buffer complete
     const uint32_t bar_act = bar_acc + 16;              // [2] input channels 0..63 / 64..127 of the next layer written
     const uint32_t bar_a1 = bar_act + 16;               // layer-1 im2col tile written, TMEM buffer 0 drained
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 * (2 * kMaxStages + 5));
+    const uint32_t bar_hi = bar_a1 + 8;                 // precision 2: the fp16 hi tile of input channels 0..63 written (its FP8 tiles follow: bar_act[0])
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + OFF_BAR + 8 * (2 * kMaxStages + 6));
 
     // ---- one-time setup
     for (int i = tid; i < (OFF_A1 + kA1Bytes) / 16; i += kThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);
@@ -245,6 +252,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
         mbar_init(bar_act, CG * (kEpiThreads / 32));
         mbar_init(bar_act + 8, CG * (kEpiThreads / 32));
         mbar_init(bar_a1, CG * (kEpiThreads / 32));
+        mbar_init(bar_hi, CG * (kEpiThreads / 32));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == kIssuerWarp) {
@@ -314,7 +322,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
         // ================= MMA issuer (pair: the leader's warp issues for both CTAs, the peer's warp 8 has nothing to do)
         // the whole warp runs the loop, one elected lane issues the MMAs and commits
         if (rank == 0) {
-        uint32_t stage = 0, phase = 0, act_phase0 = 0, act_phase1 = 0, a1_phase = 0;
+        uint32_t stage = 0, phase = 0, act_phase0 = 0, act_phase1 = 0, a1_phase = 0, hi_phase = 0;
         const uint32_t hiA = (uint32_t)(kRowPitch >> 4) | (1u << 14), hiB = (uint32_t)(128 >> 4) | (1u << 14);   // high words: SBO + version
         for (long long tile = tile0, it = 0; tile < n_tiles; tile += tile_step, it++) {
             for (int l = 0; l < L; l++) {
@@ -351,14 +359,67 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                     // the earlier ones are queued, and the commit that frees a ring stage is issued after the first MMA of the
                     // following unit — so the tensor pipe sees no gap between units.
                     const uint32_t a_lo_word = ((uint32_t)(kGroupBytes >> 4) << 16);
-                    mbar_wait_cg<CG>(bar_act, act_phase0);  // input channels 0..63 are written
-                    act_phase0 ^= 1;
+                    if (p2) {
+                        mbar_wait_cg<CG>(bar_hi, hi_phase);   // the fp16 hi tile of input channels 0..63 is written
+                        hi_phase ^= 1;
+                    } else {
+                        mbar_wait_cg<CG>(bar_act, act_phase0);  // input channels 0..63 are written
+                        act_phase0 ^= 1;
+                    }
                     tc_fence_after();
                     TRACE(it, l, 0);
                     mbar_wait_cg<CG>(bar_full + 8 * stage, phase);
                     tc_fence_after();
                     uint32_t prev_bar = 0;   // ring stage barrier whose commit is still to be issued (0 = none)
                     uint32_t acc = 0;
+                    int tap_start = 0;
+                    if (p2) {
+                        // Precision 2 at a layer boundary: the epilogue publishes the fp16 hi tile of channels 0..63 BEFORE it converts them
+                        // to FP8, and the first two units are issued as  f16(u0) f16(u1) | FP8 tiles ready | f8(u0) f8(u1):  eight MMAs
+                        // (512 cycles) cover the FP8 conversion.  Each accumulator still receives its products in the usual order.
+                        const uint32_t st0 = stage;
+                        uint32_t st1 = stage + 1, ph1 = phase;
+                        if (st1 == kRing) { st1 = 0; ph1 ^= 1; }
+                        uint32_t st2 = st1 + 1, ph2 = ph1;
+                        if (st2 == kRing) { st2 = 0; ph2 ^= 1; }
+                        const uint32_t b0 = sbase + OFF_STAGE + st0 * kRingBytes, b1 = sbase + OFF_STAGE + st1 * kRingBytes;
+                        constexpr uint32_t dAq = (2 * kGroupBytes) >> 4;
+                        const uint32_t ahw0 = ((sbase + OFF_AHI) >> 4) | a_lo_word, ahw1 = ((sbase + OFF_AHI + 16) >> 4) | a_lo_word;   // taps 0, 1
+                        const uint32_t a8w0 = ((sbase + OFF_ALO) >> 4) | a_lo_word, al8w0 = ((sbase + OFF_ALO + kA8Bytes) >> 4) | a_lo_word;
+                        const uint32_t a8w1 = ((sbase + OFF_ALO + 16) >> 4) | a_lo_word, al8w1 = ((sbase + OFF_ALO + kA8Bytes + 16) >> 4) | a_lo_word;
+                        if (elect_one()) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ks++)
+                                umma_f16_cg<CG>(d_tmem, pack64(ahw0 + ks * dAq, hiA), pack64(((b0 >> 4) | b_lo_word) + ks * b_step, hiB), idesc, ks > 0);
+                            mbar_wait_cg<CG>(bar_full + 8 * st1, ph1);
+                            tc_fence_after();
+#pragma unroll
+                            for (int ks = 0; ks < 4; ks++)
+                                umma_f16_cg<CG>(d_tmem, pack64(ahw1 + ks * dAq, hiA), pack64(((b1 >> 4) | b_lo_word) + ks * b_step, hiB), idesc, 1);
+                            mbar_wait_cg<CG>(bar_act, act_phase0);   // the FP8 tiles of channels 0..63
+                            tc_fence_after();
+#pragma unroll
+                            for (int uu = 0; uu < 2; uu++) {
+                                const uint32_t bb = uu ? b1 : b0, a8w = uu ? a8w1 : a8w0, al8w = uu ? al8w1 : al8w0;
+                                const uint32_t w8 = ((bb + ld_lo_off) >> 4) | b_lo_word, wl8 = ((bb + ld_lo_off + (ld_lo_off >> 1)) >> 4) | b_lo_word;
+#pragma unroll
+                                for (int ks = 0; ks < 2; ks++) {
+                                    umma_f8_cg<CG>(d_tmem + kCrossCol, pack64(al8w + ks * dAq, hiA), pack64(w8 + ks * b_step, hiB), idesc, (uu | ks) ? 1u : 0u);
+                                    umma_f8_cg<CG>(d_tmem + kCrossCol, pack64(a8w + ks * dAq, hiA), pack64(wl8 + ks * b_step, hiB), idesc, 1);
+                                }
+                                if (uu == 0) {
+                                    umma_commit_cg<CG>(bar_empty + 8 * st0);   // unit 0's ring stage
+                                    mbar_wait_cg<CG>(bar_full + 8 * st2, ph2); // the weights of unit 2, for the loop below
+                                    tc_fence_after();
+                                }
+                            }
+                        }
+                        act_phase0 ^= 1;
+                        prev_bar = bar_empty + 8 * st1;
+                        stage = st2; phase = ph2;
+                        acc = 1;
+                        tap_start = 2;
+                    }
                     // Straight-line issue per unit: every MMA's descriptor is (a uniform-register low word + a constant, constant high word), and
                     // a unit is ONE elected region: a non-blocking test of the next unit's "full" barrier, the MMAs (with the deferred commit of the
                     // previous unit's ring stage after the first one) up to the last group, then the test's answer — a blocking wait only if the weights
@@ -369,7 +430,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                         const uint32_t a8_base = sbase + OFF_ALO + (uint32_t)chunk * 4 * kGroupBytes;   // FP8 tiles: 16 channels per group
                         const bool last_chunk = chunk + 1 == ld_chunks;
 #pragma unroll 1
-                        for (int tap = 0; tap < 9; tap++) {   // (unrolling the taps made the issuer's loop ≈ 40 KB of code and 10-25 % slower: instruction fetch)
+                        for (int tap = (chunk == 0 ? tap_start : 0); tap < 9; tap++) {   // (unrolling the taps made the issuer's loop ≈ 40 KB of code and 10-25 % slower: instruction fetch)
                             const int ky = tap / 3, kx = tap - ky * 3;  // (dy,dx) = (ky-1,kx-1); the halo sits at padded index 0
                             const uint32_t off = (uint32_t)(ky * 20 + kx) * 16;
                             const int u = chunk * 9 + tap;
@@ -468,6 +529,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
         uint32_t acc_phase = 0;   // bit b: parity of accumulator buffer b's barrier
         // the barriers the issuer waits on are the leader's: a pair's peer CTA arrives on them through the cluster address
         const uint32_t act_leader = CG == 2 ? mapa_rank(bar_act, 0) : bar_act, a1_leader = CG == 2 ? mapa_rank(bar_a1, 0) : bar_a1;
+        const uint32_t hi_leader = CG == 2 ? mapa_rank(bar_hi, 0) : bar_hi;
         for (long long tile = tile0, it = 0; tile < n_tiles; tile += tile_step, it++) {
             const long long pos = (tile * CG + rank) * 2 + b;
             const bool valid = pos < n_pos;
@@ -609,9 +671,16 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                         if (writes_act) {
                             if (p2) {
                                 uint64_t x2[8];
+                                uint32_t hw[8];
 #pragma unroll
                                 for (int j = 0; j < 8; j++) x2[j] = f32x2(x[2 * j], x[2 * j + 1]);
-                                store_act16_p2(smem, x2, col0, row_off);
+                                store_act16_p2_hi(smem, x2, col0, row_off, hw);
+                                if (ps == 0) {   // channels 0..63: the hi tile is all the next layer's first fp16 MMAs need
+                                    fence_async_smem();
+                                    __syncwarp();
+                                    if ((tid & 31) == 0) arrive_leader<CG>(hi_leader);
+                                }
+                                store_act16_p2_f8(smem, x2, hw, col0, row_off);
                             } else store_act16<false>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
                             if (ps == 0) TRACEE(it, l, 2);
                             fence_async_smem();

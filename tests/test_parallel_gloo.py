@@ -48,7 +48,17 @@ def _worker(rank, world_size, port, out):
     visits[1, [10, 20]] = [4 + rank, 5 - rank]                 # sums: 9, 9 -> tie -> 10
     visits[2, 64] = 8                                          # only the pass child
     vsum, best = parallel.root_parallel_moves(visits)
-    out[rank] = dict(res=res, counters=counters, tmax=float(t[0]), shard=(lo, hi), vsum=vsum.numpy(), best=best.tolist())
+    # host-side control decisions of the REINFORCE loop (train_rl.train): rank 0's pick reaches every rank; the barrier helper
+    choice = parallel.broadcast_object(f"model{rank + 7}.npz")
+    parallel.barrier()
+    # the supervised trainers' minibatch sharding: the epoch's permutation must be the same on every rank although the processes'
+    # global np.random states differ (train_policy.train / train_value.train, world > 1 branch)
+    np.random.seed(1234 + rank)
+    seed, epoch, n_rec = 3, 2, 1001
+    perm = np.random.RandomState((seed * 1000003 + epoch) & 0x7FFFFFFF).permutation(n_rec)
+    lo_r, hi_r = parallel.shard_range(n_rec, rank, world_size)
+    out[rank] = dict(res=res, counters=counters, tmax=float(t[0]), shard=(lo, hi), vsum=vsum.numpy(), best=best.tolist(), choice=choice,
+                     perm_head=perm[:16].tolist(), mine=perm[lo_r:hi_r].tolist())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -71,6 +81,9 @@ def test_two_rank_sharding_and_collectives():
     assert out[0]["counters"] == out[1]["counters"] == dict(wins=3, games=1001, plies=30)
     assert out[0]["tmax"] == out[1]["tmax"] == 1.0
     assert out[0]["shard"] == (0, 501) and out[1]["shard"] == (501, 1001)
+    assert out[0]["choice"] == out[1]["choice"] == "model7.npz"
+    assert out[0]["perm_head"] == out[1]["perm_head"]
+    assert sorted(out[0]["mine"] + out[1]["mine"]) == list(range(1001))      # the two shards of one epoch cover every record exactly once
     for r in range(world_size):
         assert out[r]["best"] == [26, 10, -1]
         assert out[r]["vsum"][0, [19, 26, 37]].tolist() == [11, 13, 6] and int(out[r]["vsum"][2, 64]) == 16

@@ -765,7 +765,7 @@ def main():
     ap.add_argument("--valuegen-games", type=int, default=16384)
     ap.add_argument("--sections", default="rollout,selfplay,mcts,reinforce,valuegen", help="extra sections to run after the headline rollout bench")
     ap.add_argument("--selfplay-games", type=int, default=16384)
-    ap.add_argument("--selfplay-steps", type=int, default=2)
+    ap.add_argument("--selfplay-steps", type=int, default=4)
     ap.add_argument("--mcts-trees", type=int, default=256)
     ap.add_argument("--mcts-playouts", type=int, default=16384)
     args = ap.parse_args()

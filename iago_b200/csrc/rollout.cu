@@ -344,16 +344,41 @@ struct __align__(16) PairCell {   // what the per-cell loop needs about cell c o
     double eb;                    // exp(bias) of the cell
     uint32_t cm, pad;             // 3x3 window mask of its column
 };
-struct PairTables {               // placed on an 8 KB boundary of the shared window: a table address is (index & 0xFF8) | base
-    double e[2][2][512];          // [frame][plane][pattern]: exp of the tap sum, frame 1 = the turned board
-    PairCell cell[2][32];
-    u64 line[4][64];              // line[d][k]: the cells beyond k along direction +1, +7, +8, +9 up to the board edge
-};
+// Shared-memory layout of the paired kernel.  The look-up tables are laid out in bank STRIPS so that the per-cell gathers never
+// conflict, whatever the lanes ask for:
+//   * pattern tables (64 KB at a 64 KB boundary of the shared window): row = 9-bit pattern index (128 B per row), strip = 8 bytes
+//     = one bank pair, lane l reads strip l & 15 — lanes l and l + 16 share a strip, so a 64-bit gather of a whole warp is two
+//     wavefronts, the minimum for 256 B.  A legal cell is empty, so the centre bit of its pattern (index bit 4) is 0 in both planes:
+//     plane 0 (opponent) lives in the rows with bit 4 clear and plane 1 (mover) in the rows with bit 4 set.  Strip parity = lane
+//     parity = frame (odd lanes hold the board turned by 180 degrees), so a strip holds its own frame's table.
+//     address = TB | (index << 7) | (plane << 11) | ((lane & 15) << 3): the same three instructions as a plain table.
+//   * cell records (4 KB): row = cell, strip = 16 bytes, lane l reads strip l & 7 (four lanes per strip = the four wavefronts a
+//     512 B gather needs anyway).
+//   * line masks of the flips (16 KB): row = (cell, direction pair), strip = 16 bytes = line[d], line[d + 1]; two 16-byte gathers.
+// The scratch columns of the warps fill the space below and above the pattern tables.  The host asks for the largest dynamic
+// window the device offers (one CTA per SM whatever its size); the kernel lays the pieces out around the 64 KB boundary inside
+// that window and traps if they do not fit.
 struct PairScratch {              // per warp
     double cum[kPairSlots][32];
     uint8_t cell[kPairSlots][32];
+    uint32_t rnd[4][32];          // each lane's current Philox block (kept out of the register file)
 };
-static size_t pair_smem_bytes(int warps) { return 8192 + sizeof(PairTables) + (size_t)warps * sizeof(PairScratch); }
+constexpr uint32_t kPairPatBytes = 0x10000u, kPairCellBytes = 32u * 128u, kPairLineBytes = 2u * 64u * 128u;
+struct PairLayout {               // shared-window addresses
+    uint32_t pat, cells, line, scratch;
+};
+__device__ __forceinline__ PairLayout pair_layout(uint32_t w0, uint32_t dyn_bytes, int warp, int nwarps) {
+    PairLayout L;
+    L.pat = (w0 + 0xFFFFu) & ~0xFFFFu;
+    const uint32_t S = (uint32_t)sizeof(PairScratch);
+    const uint32_t below = (L.pat - ((w0 + 15u) & ~15u)) / S;          // warps whose scratch fits below the pattern tables
+    const uint32_t above = (uint32_t)nwarps > below ? (uint32_t)nwarps - below : 0u;
+    L.scratch = (uint32_t)warp < below ? ((w0 + 15u) & ~15u) + (uint32_t)warp * S : L.pat + kPairPatBytes + ((uint32_t)warp - below) * S;
+    L.cells = (L.pat + kPairPatBytes + above * S + 127u) & ~127u;
+    L.line = L.cells + kPairCellBytes;
+    if (L.line + kPairLineBytes > w0 + dyn_bytes) __trap();            // the window is too small: fail loudly
+    return L;
+}
 
 __device__ __forceinline__ u64 rev64(u64 x) { return ((u64)__brev((uint32_t)x) << 32) | (u64)__brev((uint32_t)(x >> 32)); }
 __device__ __forceinline__ u64 pair_xchg(unsigned mask, u64 x) {   // the partner lane's x, turned into this lane's frame
@@ -371,49 +396,52 @@ __device__ __forceinline__ u64 half_moves(u64 own, u64 opp) {
 // Stones bracketed by the move `mv` = bit k along the four directions towards higher bits, by carry propagation: with every bit
 // outside the line L = line[d][k] set, adding mv ripples from k through the opponent run on the line and stops on the first line
 // cell that holds no opponent stone; if that cell is own, everything on the line below it is flipped.
-__device__ __forceinline__ u64 half_flips(const u64 (*line)[64], int k, u64 mv, u64 own, u64 opp) {
-    u64 f = 0;
-#pragma unroll
-    for (int d = 0; d < 4; d++) {
-        const u64 L = line[d][k];
-        const u64 out = ((opp | ~L) + mv) & L & own;
-        f |= (out - (u64)(out != 0)) & L;
-    }
-    return f;
+__device__ __forceinline__ u64 flip_line(u64 L, u64 mv, u64 own, u64 opp) {
+    const u64 out = ((opp | ~L) + mv) & L & own;
+    return (out - (u64)(out != 0)) & L;
+}
+// line_base = shared-window address of this lane's 16-byte strip of the line-mask table: row 2k holds line[0][k], line[1][k],
+// row 2k + 1 holds line[2][k], line[3][k] (line[d][k] = the cells beyond k along direction +1, +7, +8, +9 up to the board edge)
+__device__ __forceinline__ u64 half_flips(uint32_t line_base, int k, u64 mv, u64 own, u64 opp) {
+    uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+    const uint32_t addr = line_base + ((uint32_t)k << 8);
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a0), "=r"(a1), "=r"(a2), "=r"(a3) : "r"(addr));
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4+128];" : "=r"(b0), "=r"(b1), "=r"(b2), "=r"(b3) : "r"(addr));
+    return flip_line(((u64)a1 << 32) | a0, mv, own, opp) | flip_line(((u64)a3 << 32) | a2, mv, own, opp) |
+           flip_line(((u64)b1 << 32) | b0, mv, own, opp) | flip_line(((u64)b3 << 32) | b2, mv, own, opp);
 }
 
 struct PairPlanes {
-    uint32_t o0, o1, m0, m1;   // opponent / mover planes << 9, words 0 and 1: all a window starting at a cell below 32 can reach
+    uint32_t o0, o1, m0, m1;   // opponent / mover planes << 10, words 0 and 1: all a window starting at a cell below 32 can reach
 };
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
     double v;
     asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
     return v;
 }
-// e_base = shared-window address of e[frame][0] (8 KB aligned), cells = cell[frame]
-__device__ __forceinline__ double pair_weight(uint32_t e_base, const PairCell *cells, const PairPlanes &p, int sh) {
-#ifndef IAGO_PAIR_SPLIT_CELL
-    const uint4 raw = *reinterpret_cast<const uint4 *>(cells + sh);   // one 16-byte load: eb (x, y), cm (z)
-#else
-    uint4 raw;
-    raw.z = cells[sh].cm;
-    const double ebv = cells[sh].eb;
-    raw.x = (uint32_t)__double2loint(ebv); raw.y = (uint32_t)__double2hiint(ebv);
-#endif
-    const uint32_t t0 = __funnelshift_r(p.o0, p.o1, (uint32_t)sh) & raw.z;
-    const uint32_t t1 = __funnelshift_r(p.m0, p.m1, (uint32_t)sh) & raw.z;
-    const double e0 = lds_f64((((t0 * 0x400801u) >> 13) & 0xFF8u) | e_base);
-    const double e1 = lds_f64((((t1 * 0x400801u) >> 13) & 0xFF8u) | (e_base + 0x1000u));
-    return __dmul_rn(__dmul_rn(e0, e1), __hiloint2double((int)raw.y, (int)raw.x));
+// e_base = shared-window address of this lane's 8-byte strip of the pattern tables (64 KB aligned + strip offset), e_base1 =
+// e_base | 0x800 (the mover's rows), cell_base = of its 16-byte strip of the cell records
+// The cell is given as q = 31 - cell (the per-cell loop walks the bit-reversed legal word from the top, and q is what FLO returns):
+// the cell records are stored in that order and the planes are pre-shifted by 10, so that a LEFT funnel shift by q leaves the
+// 19-bit window that starts at the cell in the low bits (bits cell .. cell + 31 of plane << 9).
+__device__ __forceinline__ double pair_weight(uint32_t e_base, uint32_t e_base1, uint32_t cell_base, const PairPlanes &p, int q) {
+    uint32_t ebl, ebh, cm, pad;
+    asm("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(ebl), "=r"(ebh), "=r"(cm), "=r"(pad) : "r"(cell_base + ((uint32_t)q << 7)));
+    (void)pad;
+    const uint32_t t0 = __funnelshift_l(p.o0, p.o1, (uint32_t)q) & cm;
+    const uint32_t t1 = __funnelshift_l(p.m0, p.m1, (uint32_t)q) & cm;
+    const double e0 = lds_f64((((t0 * 0x400801u) >> 9) & 0xFF80u) | e_base);
+    const double e1 = lds_f64((((t1 * 0x400801u) >> 9) & 0xFF80u) | e_base1);
+    return __dmul_rn(__dmul_rn(e0, e1), __hiloint2double((int)ebh, (int)ebl));
 }
 // More legal cells in this half than scratch slots: nothing was stored, walk again.  First cell (own-frame ascending) whose
 // running sum fails `pred`, the last cell when none does.
-__device__ __noinline__ int pair_pick_slow(uint32_t e_base, const PairCell *cells, PairPlanes p, uint32_t wd, int limit, double thr, int h) {
+__device__ __noinline__ int pair_pick_slow(uint32_t e_base, uint32_t cells, PairPlanes p, uint32_t wd, int limit, double thr, int h) {
     double cum = 0.0;
     int last = 0, j = 0;
     for (; wd; wd &= wd - 1, j++) {
         last = __ffs((int)wd) - 1;
-        cum = __dadd_rn(cum, pair_weight(e_base, cells, p, last));
+        cum = __dadd_rn(cum, pair_weight(e_base, e_base | 0x800u, cells, p, 31 - last));
         const bool pred = h ? (cum < thr) : (cum <= thr);
         if (!(j < limit && pred)) break;
     }
@@ -423,160 +451,192 @@ __device__ __noinline__ int pair_pick_slow(uint32_t e_base, const PairCell *cell
 template <int MODE, bool LOG>
 __global__ void __launch_bounds__(kPairMaxWarps * 32, 1) rollout_pair_kernel(RolloutArgs a, const RolloutWeights *__restrict__ gw) {
     extern __shared__ __align__(16) unsigned char pair_smem_raw[];
-    unsigned char *pair_smem = pair_smem_raw + ((0x2000u - ((uint32_t)__cvta_generic_to_shared(pair_smem_raw) & 0x1FFFu)) & 0x1FFFu);
-    PairTables &sm = *reinterpret_cast<PairTables *>(pair_smem);
-    PairScratch &scr = reinterpret_cast<PairScratch *>(pair_smem + sizeof(PairTables))[threadIdx.x >> 5];
+    const uint32_t w0 = (uint32_t)__cvta_generic_to_shared(pair_smem_raw);
+    uint32_t dyn_bytes;
+    asm("mov.u32 %0, %%dynamic_smem_size;" : "=r"(dyn_bytes));
+    const PairLayout lay = pair_layout(w0, dyn_bytes, threadIdx.x >> 5, (blockDim.x + 31) >> 5);
     if (MODE != IAGO_RNG_FORCED) {
-        for (int i = threadIdx.x; i < 1024; i += blockDim.x) {
-            (&sm.e[0][0][0])[i] = (&gw->elut[0][0])[i];
-            (&sm.e[1][0][0])[i] = (&gw->elut_r[0][0])[i];
+        double *pat = reinterpret_cast<double *>(pair_smem_raw + (lay.pat - w0));
+        for (int i = threadIdx.x; i < 8192; i += blockDim.x) {   // entry i = row i >> 4 (pattern, bit 4 = plane), strip i & 15 (parity = frame)
+            const int row = i >> 4, plane = (row >> 4) & 1, idx = row & ~0x10;
+            pat[i] = (i & 1) ? gw->elut_r[plane][idx] : gw->elut[plane][idx];
         }
-        if (threadIdx.x < 64) {
-            const int f = threadIdx.x >> 5, c = threadIdx.x & 31;
+        PairCell *cl = reinterpret_cast<PairCell *>(pair_smem_raw + (lay.cells - w0));
+        for (int i = threadIdx.x; i < 256; i += blockDim.x) {    // entry i = row i >> 3 (cell), strip i & 7
+            const int c = 31 - (i >> 3);                         // row q holds cell 31 - q
             PairCell ci;
-            ci.eb = f ? gw->ebias_r[c] : gw->ebias[c];
+            ci.eb = (i & 1) ? gw->ebias_r[c] : gw->ebias[c];
             ci.cm = gw->colmask[c & 7];
             ci.pad = 0;
-            sm.cell[f][c] = ci;
+            cl[i] = ci;
         }
     }
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) {
-        const int d = i >> 6, k = i & 63, r = k >> 3, c = k & 7;
-        const int steps = d == 0 ? 7 - c : d == 1 ? min(7 - r, c) : d == 2 ? 7 - r : min(7 - r, 7 - c);
-        const int S = d == 0 ? 1 : d + 6;
-        u64 L = 0;
-        for (int t = 1; t <= steps; t++) L |= 1ULL << (k + t * S);
-        sm.line[d][k] = L;
+    {
+        u64 *ln = reinterpret_cast<u64 *>(pair_smem_raw + (lay.line - w0));
+        for (int i = threadIdx.x; i < 2048; i += blockDim.x) {   // entry i = row i >> 4 = 2k + (d >> 1), strip (i >> 1) & 7, word d & 1
+            const int k = i >> 5, d = ((i >> 4) & 1) * 2 + (i & 1), r = k >> 3, c = k & 7;
+            const int steps = d == 0 ? 7 - c : d == 1 ? min(7 - r, c) : d == 2 ? 7 - r : min(7 - r, 7 - c);
+            const int S = d == 0 ? 1 : d + 6;
+            u64 L = 0;
+            for (int t = 1; t <= steps; t++) L |= 1ULL << (k + t * S);
+            ln[i] = L;
+        }
     }
     __syncthreads();
 
+    // Control flow is WARP-UNIFORM from here on: every lane runs every turn until the last game of its warp has ended, games that
+    // have ended (or never existed: g >= n) and turns without a legal move go through the same instructions with an empty move
+    // (no legal cell -> no loop trip, mv = 0 -> no flips).  All shuffles therefore name the full warp — a pair mask would make the
+    // compiler guard each of them with a MATCH / vote sequence — and only the per-cell loop diverges.
+    constexpr unsigned kFull = 0xFFFFFFFFu;
     const int h = threadIdx.x & 1;
     const unsigned pmask = 3u << (threadIdx.x & 30);
     const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-    int placed = 0, turns = 0;
-    if (g < a.n) {   // the same for both lanes of a pair, as is every branch below
-        const int color = a.color[g];
-        const u64 gid = a.game_ids ? a.game_ids[g] : a.game_id0 + (u64)g;
-        u64 own = (color == 1) ? a.p1[g] : a.p2[g];
-        u64 opp = (color == 1) ? a.p2[g] : a.p1[g];
+    const bool valid = g < a.n;   // the same for both lanes of a pair, as is every predicate below
+    int placed = 0, turns = 0, color = 1, stone_num = 64;
+    u64 gid = 0, own = 0, opp = 0;
+    if (valid) {
+        color = a.color[g];
+        gid = a.game_ids ? a.game_ids[g] : a.game_id0 + (u64)g;
+        own = (color == 1) ? a.p1[g] : a.p2[g];
+        opp = (color == 1) ? a.p2[g] : a.p1[g];
         if (h) { own = rev64(own); opp = rev64(opp); }
-        int stone_num = __popcll(own | opp);  // 64 - sum(state == 0), mcts_self_play.py:15
-        bool pass_flg = false;
-        const uint32_t e_base = (uint32_t)__cvta_generic_to_shared(&sm.e[h][0][0]);
-        const PairCell *cells = sm.cell[h];
-        double *sa = &scr.cum[0][threadIdx.x & 31];
-        uint8_t *sc = &scr.cell[0][threadIdx.x & 31];
-        uint32_t rnd[4] = {0, 0, 0, 0};  // the Philox block serving draws 4*(placed >> 2) .. + 3
-        while (stone_num < 64) {  // mcts_self_play.py:26 — the end test runs once per PAIR of turns
+        stone_num = __popcll(own | opp);  // 64 - sum(state == 0), mcts_self_play.py:15
+    }
+    bool pass_flg = false;
+    const uint32_t e_base = lay.pat + ((threadIdx.x & 15) << 3);
+    uint32_t e_base1;
+    asm("or.b32 %0, %1, 0x800;" : "=r"(e_base1) : "r"(e_base));   // opaque: otherwise the OR is redone per cell
+    const uint32_t cells = lay.cells + ((threadIdx.x & 7) << 4);
+    const uint32_t line_base = lay.line + ((threadIdx.x & 7) << 4);
+    PairScratch &scr = *reinterpret_cast<PairScratch *>(pair_smem_raw + (lay.scratch - w0));
+    double *sa = &scr.cum[0][threadIdx.x & 31];
+    uint8_t *sc = &scr.cell[0][threadIdx.x & 31];
+    uint32_t *srnd = &scr.rnd[0][threadIdx.x & 31];
+    while (__any_sync(kFull, stone_num < 64)) {
+        const bool alive = stone_num < 64;  // mcts_self_play.py:26 — the end test runs once per PAIR of turns
 #pragma unroll 1
-            for (int half = 0; half < 2; half++) {
-                const u64 hm = half_moves(own, opp);
-                const u64 legal = (hm | pair_xchg(pmask, hm)) & ~(own | opp);
-                turns++;
-                if (legal) {
-                    int k;   // the move, in this lane's frame
-                    if (MODE == IAGO_RNG_FORCED) {
-                        k = (placed < a.f_stride) ? a.forced[g * a.f_stride + placed] : -1;
-                        if (k >= 0 && k <= 63 && h) k = 63 - k;
-                    } else {
-                        u64 m53;
-                        if (MODE == IAGO_RNG_UNIFORMS)
-                            m53 = __double2ull_rz((placed < a.u_stride ? a.uniforms[g * a.u_stride + placed] : 0.5) * 9007199254740992.0);   // never past a short replay stream
-                        else {
-#ifndef IAGO_PAIR_NO_COOP_PHILOX
-                            // lane h holds Philox block 2 * (placed >> 3) + h: the ten rounds run once per EIGHT stones of a game
-                            if ((placed & 7) == 0) philox_block(a.seed, gid, (((uint32_t)placed >> 3) << 1) + h, a.stream_id, rnd);
-                            const uint32_t mine = (placed & 2) ? ((placed & 1) ? rnd[3] : rnd[2]) : ((placed & 1) ? rnd[1] : rnd[0]);
-                            const uint32_t wd = __shfl_sync(pmask, mine, (threadIdx.x & 30) + ((placed >> 2) & 1));
-#else
-                            if ((placed & 3) == 0) philox_block(a.seed, gid, (uint32_t)placed >> 2, a.stream_id, rnd);
-                            const uint32_t wd = (placed & 2) ? ((placed & 1) ? rnd[3] : rnd[2]) : ((placed & 1) ? rnd[1] : rnd[0]);
-#endif
-                            m53 = (u64)wd << 21;
-                        }
-                        const double u = __dmul_rn((double)(long long)m53, 1.1102230246251565e-16);  // m53 / 2^53, exact
-                        // this lane's half of the softmax numerators: legal cells 0..31 of its frame, ascending
-                        const uint32_t lw = (uint32_t)legal;
-                        const int n = __popc(lw);
-                        PairPlanes pl;
-                        pl.o0 = (uint32_t)opp << 9;
-                        pl.o1 = __funnelshift_l((uint32_t)opp, (uint32_t)(opp >> 32), 9);
-                        pl.m0 = (uint32_t)own << 9;
-                        pl.m1 = __funnelshift_l((uint32_t)own, (uint32_t)(own >> 32), 9);
-                        const bool stored = n <= kPairSlots;
-                        double cum = 0.0;
-                        if (stored) {
-                            uint32_t wd = lw;
-                            for (int i = 0; i < n; i++) {
-                                const int sh = __ffs((int)wd) - 1;
-                                wd &= wd - 1;
-                                cum = __dadd_rn(cum, pair_weight(e_base, cells, pl, sh));
-                                sa[i * 32] = cum;
-                                sc[i * 32] = (uint8_t)sh;
-                            }
-                        } else {
-                            for (uint32_t wd = lw; wd; wd &= wd - 1) cum = __dadd_rn(cum, pair_weight(e_base, cells, pl, __ffs((int)wd) - 1));
-                        }
-                        // A_last (lane 0) and D_last (lane 1) -> total, T, and which half holds the answer
-                        const double oth = __hiloint2double(__shfl_xor_sync(pmask, __double2hiint(cum), 1),
-                                                            __shfl_xor_sync(pmask, __double2loint(cum), 1));
-                        const double lo_t = h ? oth : cum, hi_t = h ? cum : oth;
-                        const double total = __dadd_rn(lo_t, hi_t), T = __dmul_rn(u, total);
-                        const bool in_hi = !(T < lo_t) && hi_t > 0.0;
-                        // lane 0: number of A_i <= T (at most n - 1); lane 1: number of D_j < total - T among j <= n - 2
-                        const double thr = h ? __dsub_rn(total, T) : T;
-                        int c;
-                        if (stored) {
-                            int idx = 0, end = n - h;
-                            while (idx < end) {
-                                const int mid = (idx + end) >> 1;
-                                const double v = sa[mid * 32];
-                                if (h ? (v < thr) : (v <= thr)) idx = mid + 1; else end = mid;
-                            }
-                            idx = max(min(idx, n - 1), 0);
-                            c = (int)sc[idx * 32];
-                        } else {
-                            c = pair_pick_slow(e_base, cells, pl, lw, n - h, thr, h);
-                        }
-                        const int ct = h ? 63 - c : c;   // this lane's candidate as a cell of the real board
-                        const int octv = __shfl_xor_sync(pmask, ct, 1);
-                        const int kt = (in_hi == (h != 0)) ? ct : octv;
-                        k = h ? 63 - kt : kt;
+        for (int half = 0; half < 2; half++) {
+            const u64 hm = half_moves(own, opp);
+            const u64 legal = (hm | pair_xchg(kFull, hm)) & ~(own | opp);
+            bool has = alive && legal != 0;   // this game places a stone in this turn
+            turns += alive ? 1 : 0;
+            int k;   // the move, in this lane's frame
+            if (MODE == IAGO_RNG_FORCED) {
+                k = (has && placed < a.f_stride) ? a.forced[g * a.f_stride + placed] : -1;
+                if (has && (k < 0 || k > 63)) {
+                    stone_num = 64;  // replay stream exhausted: stop this game where it stands
+                    has = false;
+                }
+                if (h) k = 63 - k;
+            } else {
+                u64 m53;
+                if (MODE == IAGO_RNG_UNIFORMS)
+                    m53 = __double2ull_rz(((has && placed < a.u_stride) ? a.uniforms[g * a.u_stride + placed] : 0.5) * 9007199254740992.0);   // never past a short replay stream
+                else {
+                    // lane h computes Philox block 2 * (placed >> 3) + h: the ten rounds run once per EIGHT stones of a
+                    // game; the words wait in shared memory, draw d = word d & 3 of lane (d >> 2) & 1 of the pair
+                    if (has && (placed & 7) == 0) {
+                        uint32_t o[4];
+                        philox_block(a.seed, gid, (((uint32_t)placed >> 3) << 1) + h, a.stream_id, o);
+#pragma unroll
+                        for (int j = 0; j < 4; j++) srnd[j * 32] = o[j];
+                        __syncwarp(pmask);
                     }
-                    if (MODE == IAGO_RNG_FORCED && (k < 0 || k > 63)) {
-                        stone_num = 64;  // replay stream exhausted: stop this game where it stands
-                    } else {
-                        const u64 mv = 1ULL << k;
-                        own |= mv;
-                        opp &= ~mv;
-                        const u64 hf = half_flips(sm.line, k, mv, own, opp);
-                        const u64 f = hf | pair_xchg(pmask, hf);
-                        own |= f;
-                        opp &= ~f;
-                        if (LOG && !h) a.move_log[g * 64 + placed] = (int8_t)k;
-                        placed++;
-                        pass_flg = false;
-                        stone_num++;
+                    const uint32_t wd = srnd[(placed & 3) * 32 + ((placed >> 2) & 1) - h];
+                    m53 = (u64)wd << 21;
+                }
+                const double u = __dmul_rn((double)(long long)m53, 1.1102230246251565e-16);  // m53 / 2^53, exact
+                // this lane's half of the softmax numerators: legal cells 0..31 of its frame, ascending
+                const uint32_t lw = has ? (uint32_t)legal : 0u;
+                const int n = __popc(lw);
+                PairPlanes pl;
+                pl.o0 = (uint32_t)opp << 10;
+                pl.o1 = __funnelshift_l((uint32_t)opp, (uint32_t)(opp >> 32), 10);
+                pl.m0 = (uint32_t)own << 10;
+                pl.m1 = __funnelshift_l((uint32_t)own, (uint32_t)(own >> 32), 10);
+                const bool stored = n <= kPairSlots;
+                double cum = 0.0;
+                if (stored) {
+                    // ascending cells = descending bits of the reversed word: one FLO per cell, pointers instead of an index
+                    uint32_t wr = __brev(lw);
+                    double *sap = sa;
+                    uint8_t *scp = sc;
+#pragma unroll 1
+                    while (wr) {   // (unrolling makes the warp run the remainders of all its lanes: measured slower)
+                        uint32_t q, below;
+                        asm("bfind.u32 %0, %1;" : "=r"(q) : "r"(wr));              // top set bit: q = 31 - cell, wr != 0
+                        asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(below) : "r"(q));  // the q bits below it
+                        cum = __dadd_rn(cum, pair_weight(e_base, e_base1, cells, pl, (int)q));
+                        *sap = cum;
+                        *scp = (uint8_t)q;
+                        sap += 32;
+                        scp += 32;
+                        wr &= below;
                     }
                 } else {
-                    if (pass_flg) stone_num = 64;  // two consecutive passes end the game
-                    pass_flg = true;
+                    for (uint32_t wd = lw; wd; wd &= wd - 1) cum = __dadd_rn(cum, pair_weight(e_base, e_base1, cells, pl, 32 - __ffs((int)wd)));
                 }
-                const u64 t = own; own = opp; opp = t;
+                // A_last (lane 0) and D_last (lane 1) -> total, T, and which half holds the answer
+                const double oth = __hiloint2double(__shfl_xor_sync(kFull, __double2hiint(cum), 1),
+                                                    __shfl_xor_sync(kFull, __double2loint(cum), 1));
+                const double lo_t = h ? oth : cum, hi_t = h ? cum : oth;
+                const double total = __dadd_rn(lo_t, hi_t), T = __dmul_rn(u, total);
+                const bool in_hi = !(T < lo_t) && hi_t > 0.0;
+                // lane 0: number of A_i <= T (at most n - 1); lane 1: number of D_j < total - T among j <= n - 2
+                const double thr = h ? __dsub_rn(total, T) : T;
+                int c;
+                if (stored) {
+                    // the sums ascend, so the count is found by four fixed steps; v <= thr is v < nextup(thr) (thr >= 0)
+                    const double thr2 = __longlong_as_double(__double_as_longlong(thr) + (long long)(1 - h));
+                    const int end = n - h;
+                    int idx = 0;
+#pragma unroll
+                    for (int s = 8; s; s >>= 1) {
+                        const int t = idx + s;
+                        if (t <= end && sa[(t - 1) * 32] < thr2) idx = t;   // slot t - 1 <= 14 exists whatever n is
+                    }
+                    idx = max(min(idx, n - 1), 0);
+                    c = 31 - (int)sc[idx * 32];
+                } else {
+                    c = pair_pick_slow(e_base, cells, pl, lw, n - h, thr, h);
+                }
+                const int ct = h ? 63 - c : c;   // this lane's candidate as a cell of the real board
+                const int octv = __shfl_xor_sync(kFull, ct, 1);
+                const int kt = (in_hi == (h != 0)) ? ct : octv;
+                k = h ? 63 - kt : kt;
             }
-        }
-        if (!h) {
-            // an even number of swaps happened: own = stones of `color` again
-            const int me = __popcll(own), op = __popcll(opp);
-            a.result[g] = (int8_t)((me > op) - (me < op));
-            if (a.final_p1) {   // nullable for callers that only want the result (mcts.cu)
-                a.final_p1[g] = (color == 1) ? own : opp;
-                a.final_p2[g] = (color == 1) ? opp : own;
+            k &= 63;   // (a game without a move carries a meaningless k)
+            const u64 mv = has ? 1ULL << k : 0ULL;
+            own |= mv;
+            opp &= ~mv;
+            const u64 hf = half_flips(line_base, k, mv, own, opp);   // mv = 0: nothing is bracketed
+            const u64 f = hf | pair_xchg(kFull, hf);
+            own |= f;
+            opp &= ~f;
+            if (LOG && has && !h) a.move_log[g * 64 + placed] = (int8_t)k;
+            if (has) {
+                placed++;
+                pass_flg = false;
+                stone_num++;
+            } else if (alive && (MODE != IAGO_RNG_FORCED || legal == 0)) {
+                if (pass_flg) stone_num = 64;  // two consecutive passes end the game
+                pass_flg = true;
             }
-            if (a.n_moves) a.n_moves[g] = placed;
-            if (LOG)
-                for (int i = placed; i < 64; i++) a.move_log[g * 64 + i] = -1;
+            const u64 t = own; own = opp; opp = t;
         }
+    }
+    if (valid && !h) {
+        // an even number of swaps happened: own = stones of `color` again
+        const int me = __popcll(own), op = __popcll(opp);
+        a.result[g] = (int8_t)((me > op) - (me < op));
+        if (a.final_p1) {   // nullable for callers that only want the result (mcts.cu)
+            a.final_p1[g] = (color == 1) ? own : opp;
+            a.final_p2[g] = (color == 1) ? opp : own;
+        }
+        if (a.n_moves) a.n_moves[g] = placed;
+        if (LOG)
+            for (int i = placed; i < 64; i++) a.move_log[g * 64 + i] = -1;
     }
     if (a.counters) {
         unsigned p = h ? 0u : (unsigned)placed, t = h ? 0u : (unsigned)turns;
@@ -735,15 +795,20 @@ static void launch_rollout(const RolloutArgs &a, const RolloutWeights *w, cudaSt
         long long wpc = (warps + sms - 1) / sms;
         wpc = wpc < 2 ? 2 : wpc > kPairMaxWarps ? kPairMaxWarps : wpc;
         const unsigned grid = (unsigned)((warps + wpc - 1) / wpc);
-        const size_t smem = pair_smem_bytes(kPairMaxWarps);
+        static int smem = 0;                          // the whole opt-in window (the kernel's layout is built around its 64 KB boundary)
+        if (!smem) {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        }
         if (a.move_log) {
-            if (!attr_set[1]) cudaFuncSetAttribute(rollout_pair_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (!attr_set[1]) cudaFuncSetAttribute(rollout_pair_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             attr_set[1] = true;
-            rollout_pair_kernel<MODE, true><<<grid, (unsigned)wpc * 32, pair_smem_bytes((int)wpc), s>>>(a, w);
+            rollout_pair_kernel<MODE, true><<<grid, (unsigned)wpc * 32, (size_t)smem, s>>>(a, w);
         } else {
-            if (!attr_set[0]) cudaFuncSetAttribute(rollout_pair_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (!attr_set[0]) cudaFuncSetAttribute(rollout_pair_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             attr_set[0] = true;
-            rollout_pair_kernel<MODE, false><<<grid, (unsigned)wpc * 32, pair_smem_bytes((int)wpc), s>>>(a, w);
+            rollout_pair_kernel<MODE, false><<<grid, (unsigned)wpc * 32, (size_t)smem, s>>>(a, w);
         }
         return;
     }

@@ -37,19 +37,28 @@ sys.path.insert(0, ROOT)
 
 GAMES_PER_STEP = 65536
 OPS_PER_PLY = 676          # int32 ALU lane-ops per ply: movegen 314 + flip 352 + ~10 (SURVEY.md §8d, step-by-step 6-step flood)
-OPS_PER_PLY_IMPL = 308     # ALU-pipe instructions per ply the paired kernel really issues for the rules (2 lanes x 154, counted in the SASS
-                           # of rollout_pair_kernel<FORCED>: carry-propagation flips / east moves, three parallel-prefix floods; + 92 IMAD on the FMA pipe)
 BYTES_PER_GAME = 17 + 21   # p1,p2,colour in; final p1,p2,n_moves,result out
 
 
-def ncu_traffic():
-    """dram__bytes_read + write per launch of the headline kernel from the committed ncu capture (profiles/ncu_traffic.json, written by
-    profiles/ncu_summary.py with the capture's date and command); None when the file is missing or is for another launch size."""
+def ncu_traffic(key="rollout_pair_kernel"):
+    """Per-launch figures of the headline kernel from the committed ncu capture (profiles/ncu_traffic.json, written by
+    profiles/ncu_traffic.py with the capture's date and command): dram__bytes_read + write, and the warp instructions the ALU pipe
+    executed (`key` = rollout_pair_kernel for the Philox launch, rollout_pair_kernel_forced for the rules-only replay).  None when the
+    file is missing or is for another launch size."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["rollout_pair_kernel"]
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[key]
         return t if t.get("games_per_launch") == GAMES_PER_STEP else None
     except Exception:
         return None
+
+
+def alu_lane_ops_per_ply(key, plies_per_launch):
+    """ALU-pipe lane-operations per ply the kernel really issued in the committed capture (warp instructions x 32 / plies of one
+    launch of the same workload); None without a capture."""
+    t = ncu_traffic(key)
+    if not t or not t.get("alu_pipe_warp_inst_per_launch") or not plies_per_launch:
+        return None
+    return 32.0 * t["alu_pipe_warp_inst_per_launch"] / plies_per_launch
 
 METRIC = "rollout_plies_per_s"
 
@@ -352,6 +361,9 @@ def run_ours(args, rank, world, local_rank):
     t_mg = sum(a.elapsed_time(b) for a, b in mg_ev) / 1e3
     mg_plies = int(mg_counters[0].item())
 
+    ops_impl = alu_lane_ops_per_ply("rollout_pair_kernel", plies / args.steps) if n == GAMES_PER_STEP else None   # this rank's launches
+    ops_impl_mg = alu_lane_ops_per_ply("rollout_pair_kernel_forced", mg_plies / args.steps) if n == GAMES_PER_STEP else None
+
     if dist is not None:
         tt = torch.tensor([t_dev, t_e2e, t_wall], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -397,22 +409,25 @@ def run_ours(args, rank, world, local_rank):
                          "peak": int_peak / 1e12, "unit": "Tint32op/s", "frac": achieved / int_peak,
                          "traffic": (ncu_traffic() or {}).get("dram_bytes_per_launch") if n == GAMES_PER_STEP else None,
                          "traffic_source": ncu_traffic(),
-                         "ops_per_ply_as_implemented": OPS_PER_PLY_IMPL,
-                         "frac_as_implemented": OPS_PER_PLY_IMPL * plies_per_launch / kernel_s / int_peak,
+                         "alu_lane_ops_per_ply_issued": ops_impl,
+                         "frac_alu_pipe_issued": (ops_impl * plies_per_launch / kernel_s / int_peak) if ops_impl else None,
                          "note": "issue-bound path: 676 algorithmic int32 lane-ops/ply (SURVEY 8d: 6-step flood formulation) x plies per launch / mean launch "
                                  "time; peak = SHF+LOP3 micro-kernel measured in this run (iago_measure_int_peak); traffic = "
                                  "dram__bytes_read+write per launch read from profiles/ncu_traffic.json (the committed ncu --set full capture; "
-                                 "algorithmic bytes per launch: 38 B x 65,536 games = 2.49 MB; outputs stay in L2 during the capture)"},
+                                 "algorithmic bytes per launch: 38 B x 65,536 games = 2.49 MB; outputs stay in L2 during the capture); "
+                                 "alu_lane_ops_per_ply_issued = ALU-pipe warp instructions of that capture x 32 / plies (rules + policy + "
+                                 "sampling), frac_alu_pipe_issued = what they occupy of the ALU pipe at this run's speed"},
             "roofline_movegen": {"bound": "alu", "kernel": "rollout_pair_kernel<FORCED> (legal_moves + flips + pass/terminal/score only, moves "
                                  "replayed from a 64 B/game log)", "plies_per_s": mg_plies / t_mg,
                                  "achieved": OPS_PER_PLY * mg_plies / t_mg / 1e12, "peak": int_peak / 1e12, "unit": "Tint32op/s",
                                  "frac": OPS_PER_PLY * mg_plies / t_mg / int_peak, "traffic": None, "scope": "rank 0",
-                                 "ops_per_ply_as_implemented": OPS_PER_PLY_IMPL,
-                                 "frac_as_implemented": OPS_PER_PLY_IMPL * mg_plies / t_mg / int_peak,
+                                 "alu_lane_ops_per_ply_issued": ops_impl_mg,
+                                 "frac_alu_pipe_issued": (ops_impl_mg * mg_plies / t_mg / int_peak) if ops_impl_mg else None,
                                  "note": "the kernel finds flips and east moves by carry propagation and floods the other directions in parallel-prefix "
-                                         "form: 308 ALU-pipe instructions per ply (+ 92 IMAD on the FMA pipe) instead of the 676 of the step-by-step "
-                                         "form SURVEY 8d counts, so the fraction on the 676 count exceeds 1; frac_as_implemented is the ALU-pipe "
-                                         "utilisation by the instructions really issued"},
+                                         "form, which takes about half the ALU operations of the step-by-step form SURVEY 8d counts (676), so the "
+                                         "fraction on the 676 count exceeds 1; alu_lane_ops_per_ply_issued = ALU-pipe warp instructions of the "
+                                         "committed ncu capture of this launch x 32 / plies, frac_alu_pipe_issued = what they occupy of the ALU pipe "
+                                         "at this run's speed (the capture itself: sm__inst_executed_pipe_alu in profiles/ncu_traffic.json)"},
             "roofline_hbm": {"bound": "hbm", "achieved": hbm_ach, "peak": hbm_peak, "unit": "GB/s",
                              "frac": hbm_ach / hbm_peak, "traffic": None,
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",

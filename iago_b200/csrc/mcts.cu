@@ -297,14 +297,53 @@ __global__ void __launch_bounds__(32) mcts_select_kernel(MctsDev d, MctsParams p
 constexpr int kPipeWarps = IAGO_PIPE_WARPS;
 constexpr int kPipeMaxB = 1024;
 
+// place_stone by the whole warp: lanes 0-3 find the stones bracketed along +1, +7, +8, +9, lanes 4-7 along the opposite directions on
+// the board turned by 180 degrees (one bit reversal), each by carry propagation along its line (see half_flips in rollout.cu: with
+// every bit outside the line set, adding the move ripples through the opponent run and stops on the first line cell that holds no
+// opponent stone; if that cell is the mover's, everything on the line below it is flipped) — about 40 instructions and two REDUX.OR
+// per level of a descent where every lane used to run all eight floods.  line[d][k] = the cells beyond k along direction d.
+__device__ __forceinline__ u64 rev64(u64 x) { return ((u64)__brev((uint32_t)x) << 32) | (u64)__brev((uint32_t)(x >> 32)); }
+__device__ __forceinline__ void place_warp(const u64 *line, int act, u64 &own, u64 &opp, int lane) {
+    const u64 mv = 1ULL << act;
+    own |= mv;          // the cell becomes the mover's whatever it held (game.py:185)
+    opp &= ~mv;
+    u64 f = 0;
+    if (lane < 8) {
+        const bool r = lane >= 4;
+        const u64 o = r ? rev64(own) : own, q = r ? rev64(opp) : opp;
+        const int k = r ? 63 - act : act;
+        const u64 L = line[(lane & 3) * 64 + k];
+        const u64 out = ((q | ~L) + (1ULL << k)) & L & o;   // the bracketing stone (one bit) or 0
+        const u64 ff = out ? (out - 1) & L : 0ULL;
+        f = r ? rev64(ff) : ff;
+    }
+    const uint32_t flo = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)f), fhi = __reduce_or_sync(0xFFFFFFFFu, (uint32_t)(f >> 32));
+    f = ((u64)fhi << 32) | flo;
+    own |= f;
+    opp &= ~f;
+}
+__device__ __forceinline__ void fill_line_table(u64 *line, int tid, int nthreads) {
+    for (int i = tid; i < 256; i += nthreads) {
+        const int d = i >> 6, k = i & 63, r = k >> 3, c = k & 7;
+        const int steps = d == 0 ? 7 - c : d == 1 ? min(7 - r, c) : d == 2 ? 7 - r : min(7 - r, 7 - c);
+        const int S = d == 0 ? 1 : d + 6;
+        u64 L = 0;
+        for (int t = 1; t <= steps; t++) L |= 1ULL << (k + t * S);
+        line[i] = L;
+    }
+}
+
+__device__ __forceinline__ void pipe_fence() {
+    asm volatile("fence.acq_rel.cta;" ::: "memory");   // release before the flag is raised / acquire behind it: all the hand-over needs
+}
 __device__ __forceinline__ void pipe_wait(const volatile int *prog, int a, int need) {   // until descent a - 1 has progress >= need
     if (a == 0) return;
     while (prog[a - 1] < need) __nanosleep(20);   // (a pure spin measured the same)
-    __threadfence_block();
+    pipe_fence();
 }
 __device__ __forceinline__ void pipe_signal(volatile int *prog, int a, int value, int lane) {
     __syncwarp();
-    __threadfence_block();
+    pipe_fence();
     if (lane == 0) prog[a] = value;
 }
 
@@ -313,6 +352,14 @@ __global__ void __launch_bounds__(kPipeWarps * 32) mcts_select_pipe_kernel(MctsD
     __shared__ short active[kPipeMaxB];
     __shared__ int n_active;
     __shared__ volatile int s_n_nodes;
+    // Evaluation requests are staged per tree (the slot of the asking descent, in descent order) and copied to the global lists when
+    // the launch ends, with ONE atomicAdd per list and tree: an atomic with a return value inside the leaf work — which the descents
+    // of a tree do strictly one after the other — is an L2 round trip on the critical path of every descent.
+    __shared__ short s_pol[kPipeMaxB], s_val[kPipeMaxB];
+    __shared__ volatile int s_npol, s_nval;
+    __shared__ int s_base_pol, s_base_val;
+    __shared__ u64 s_line[256];
+    fill_line_table(s_line, threadIdx.x, blockDim.x);
     const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     MctsNode *nodes = d.nodes + (size_t)t * d.cap;
     const long long done = d.done[t];
@@ -324,6 +371,8 @@ __global__ void __launch_bounds__(kPipeWarps * 32) mcts_select_pipe_kernel(MctsD
         }
         n_active = c;
         s_n_nodes = d.n_nodes[t];
+        s_npol = 0;
+        s_nval = 0;
     }
     for (int i = threadIdx.x; i < p.B; i += blockDim.x) {
         prog[i] = 0;
@@ -407,78 +456,91 @@ __global__ void __launch_bounds__(kPipeWarps * 32) mcts_select_pipe_kernel(MctsD
                             nodes[node].first_child = base;
                             nodes[node].nch_pending = (uint8_t)c;
                             nodes[node].flags = (uint8_t)(flags | F_PENDING);
-                            const int j = atomicAdd(d.counts + 0, 1);
-                            d.pol_p1[j] = color == 1 ? own : opp;
-                            d.pol_p2[j] = color == 1 ? opp : own;
-                            d.pol_color[j] = (uint8_t)color;
-                            d.pol_node[j] = t * d.cap + node;
+                            const int j = s_npol;
+                            s_pol[j] = (short)s;
+                            s_npol = j + 1;
                         }
                         park = true;
                     } else if (lane == 0) {
                         atomicAdd(d.counts + 2, 1);  // pool full: evaluate instead of expanding (reported to the host)
                     }
                 }
+                if (lane == 0 && !park && p.need_v) {   // the value of a node is asked for once (cache_v): claimed in descent order
+                    const uint8_t fl = nodes[node].flags;
+                    const bool have = p.cache_v && (fl & (F_V_VALID | F_V_CLAIMED));
+                    if (!have) {
+                        if (p.cache_v) nodes[node].flags = (uint8_t)(fl | F_V_CLAIMED);
+                        const int j = s_nval;
+                        s_val[j] = (short)s;
+                        s_nval = j + 1;
+                    }
+                }
+                // everything a later descent may read is written: let it go on, then record the leaf for the kernels behind this one
+                pipe_signal(prog, a, 0x7FFFFFFF, lane);
                 if (lane == 0) {
                     d.leaf_node[slot] = node;
                     d.leaf_p1[slot] = color == 1 ? own : opp;
                     d.leaf_p2[slot] = color == 1 ? opp : own;
                     d.leaf_color[slot] = (uint8_t)color;
-                    if (park) {
-                        d.status[slot] = S_PARKED;
-                        if (pass == 2) atomicAdd(d.counts + 3, 1);
-                    } else {
-                        d.status[slot] = S_EVAL;
-                        if (p.need_v) {
-                            const uint8_t fl = nodes[node].flags;
-                            const bool have = p.cache_v && (fl & (F_V_VALID | F_V_CLAIMED));
-                            if (!have) {
-                                if (p.cache_v) nodes[node].flags = (uint8_t)(fl | F_V_CLAIMED);
-                                const int j = atomicAdd(d.counts + 1, 1);
-                                d.val_p1[j] = color == 1 ? own : opp;
-                                d.val_p2[j] = color == 1 ? opp : own;
-                                d.val_color[j] = (uint8_t)color;
-                                d.val_node[j] = t * d.cap + node;
-                                d.val_slot[j] = slot;
-                            }
-                        }
-                    }
+                    d.status[slot] = park ? S_PARKED : S_EVAL;
+                    if (park && pass == 2) atomicAdd(d.counts + 3, 1);
                 }
                 break;
             }
             // ---- select (MCTS.py:39-49): arg-max over children of Q + u, first maximum wins
-            if (!exclusive) pipe_wait(prog, a, stage + 1);
+            // What does not depend on the earlier descents is computed BEFORE the wait: this node's visit count was final when it
+            // was read (every earlier descent had passed it), so the square root is, and so are the priors of its children (written
+            // when the node was expanded) and with them the numerators c_puct * P * sqrt(N).  Behind the wait only the visit
+            // statistics are read (plain loads: the stores of the other warps of this CTA went through the same L1) and the two
+            // divisions remain.
             const double n_parent = (double)(n_here + vn_here - 1);  // without this descent's own virtual visit
             const double sq = __dsqrt_rn(n_parent);
+            double num0 = 0.0;                                       // the numerator of the lane's first child (the common case: nch <= 32)
+            if (lane < nch) {
+                const uint4 w0 = reinterpret_cast<const uint4 *>(nodes + fc + lane)[0];
+                const int cflags = (int)reinterpret_cast<const uint8_t *>(nodes + fc + lane)[46];
+                const double cP = __hiloint2double((int)w0.y, (int)w0.x);
+                const double cp = (cflags & F_P_F64) ? __dmul_rn(p.c_puct, cP) : (double)__fmul_rn((float)p.c_puct, (float)cP);
+                num0 = __dmul_rn(cp, sq);
+            }
+            if (!exclusive) pipe_wait(prog, a, stage + 1);
             double best = -1.0e300;
             int best_i = 1 << 30;
             int b_n = 0, b_vn = 0, b_fc = -1, b_meta = 0;
             for (int i = lane; i < nch; i += 32) {
                 const uint4 *raw = reinterpret_cast<const uint4 *>(nodes + fc + i);
-                const uint4 w0 = raw[0], w1 = raw[1], w2 = raw[2];   // P Q | W v n | vn parent first_child meta
-                const double cP = __hiloint2double((int)w0.y, (int)w0.x);
+                const uint4 w1 = raw[1], w2 = raw[2];   // W v n | vn parent first_child meta
+                double num = num0;
+                if (i >= 32) {
+                    const uint4 w0 = raw[0];
+                    const int cflags = (int)((w2.w >> 16) & 0xFFu);
+                    const double cP = __hiloint2double((int)w0.y, (int)w0.x);
+                    const double cp = (cflags & F_P_F64) ? __dmul_rn(p.c_puct, cP) : (double)__fmul_rn((float)p.c_puct, (float)cP);
+                    num = __dmul_rn(cp, sq);
+                }
                 const long long cW = (long long)(((u64)w1.y << 32) | (u64)w1.x);
-                const int cn = (int)w1.w, cvn = (int)w2.x, cflags = (int)((w2.w >> 16) & 0xFFu);
-                const double cp = (cflags & F_P_F64) ? __dmul_rn(p.c_puct, cP) : (double)__fmul_rn((float)p.c_puct, (float)cP);
+                const int cn = (int)w1.w, cvn = (int)w2.x;
                 const int tot = cn + cvn;
                 const double q = tot > 0 ? __ddiv_rn(__dsub_rn((double)cW * (1.0 / kFix), __dmul_rn(p.vloss, (double)cvn)), (double)tot) : 0.0;
                 const double den = __dadd_rn(0.01, (double)tot);
-                const double u = __ddiv_rn(__dmul_rn(cp, sq), den);
+                const double u = __ddiv_rn(num, den);
                 const double val = __dadd_rn(q, u);
                 if (val > best) {  // ascending i: the first maximum stays
                     best = val; best_i = i;
                     b_n = cn; b_vn = cvn; b_fc = (int)w2.z; b_meta = (int)w2.w;
                 }
             }
-            int win = lane;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                const double ov = shfl_down_d(best, o);
-                const int oi = __shfl_down_sync(0xFFFFFFFFu, best_i, o);
-                const int ow = __shfl_down_sync(0xFFFFFFFFu, win, o);
-                if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; win = ow; }
-            }
-            win = __shfl_sync(0xFFFFFFFFu, win, 0);
-            best_i = __shfl_sync(0xFFFFFFFFu, best_i, 0);
+            // warp arg-max on an order-preserving integer key: two 32-bit REDUX.MAX (high word, then low word among the lanes that
+            // hold the high maximum) and a REDUX.MIN of the child index among the lanes that hold the maximum — the first maximum
+            // wins, as in the scalar loop (every val is a finite double; -0.0 cannot come out of q + u with u >= +0)
+            const long long bits = __double_as_longlong(best);
+            const u64 key = (u64)bits ^ (u64)((bits >> 63) | (long long)0x8000000000000000LL);
+            const uint32_t khi = (uint32_t)(key >> 32), klo = (uint32_t)key;
+            const uint32_t mhi = __reduce_max_sync(0xFFFFFFFFu, khi);
+            const uint32_t mlo = __reduce_max_sync(0xFFFFFFFFu, khi == mhi ? klo : 0u);
+            const bool top = khi == mhi && klo == mlo;
+            best_i = (int)__reduce_min_sync(0xFFFFFFFFu, top ? (uint32_t)best_i : 0xFFFFFFFFu);
+            const int win = best_i & 31;   // child i is held by lane i & 31
             const int child = fc + best_i;
             n_here = __shfl_sync(0xFFFFFFFFu, b_n, win);
             vn_here = __shfl_sync(0xFFFFFFFFu, b_vn, win) + 1;   // with this descent's own virtual visit, stored below
@@ -490,15 +552,34 @@ __global__ void __launch_bounds__(kPipeWarps * 32) mcts_select_pipe_kernel(MctsD
             if (lane == 0) nodes[child].vn = vn_here;
             stage++;
             if (!exclusive) pipe_signal(prog, a, stage, lane);
-            if (act >= 0) place(1ULL << act, own, opp);   // action -1 = pass = no-op (game.py:181-182)
+            if (act >= 0) place_warp(s_line, act, own, opp, lane);   // action -1 = pass = no-op (game.py:181-182)
             { const u64 tmp = own; own = opp; opp = tmp; }
             color = 3 - color;
             node = child;
         }
-        pipe_signal(prog, a, 0x7FFFFFFF, lane);
     }
     __syncthreads();
-    if (threadIdx.x == 0) d.n_nodes[t] = s_n_nodes;
+    if (threadIdx.x == 0) {
+        d.n_nodes[t] = s_n_nodes;
+        s_base_pol = s_npol ? atomicAdd(d.counts + 0, s_npol) : 0;
+        s_base_val = s_nval ? atomicAdd(d.counts + 1, s_nval) : 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < s_npol; i += blockDim.x) {
+        const int slot = t * p.B + s_pol[i], j = s_base_pol + i;
+        d.pol_p1[j] = d.leaf_p1[slot];
+        d.pol_p2[j] = d.leaf_p2[slot];
+        d.pol_color[j] = d.leaf_color[slot];
+        d.pol_node[j] = t * d.cap + d.leaf_node[slot];
+    }
+    for (int i = threadIdx.x; i < s_nval; i += blockDim.x) {
+        const int slot = t * p.B + s_val[i], j = s_base_val + i;
+        d.val_p1[j] = d.leaf_p1[slot];
+        d.val_p2[j] = d.leaf_p2[slot];
+        d.val_color[j] = d.leaf_color[slot];
+        d.val_node[j] = t * d.cap + d.leaf_node[slot];
+        d.val_slot[j] = slot;
+    }
 }
 
 // priors: child P = float32(prob[action] + 0.1) (MCTS.py:93-99, :18-19); the children become visible.

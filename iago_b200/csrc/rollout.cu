@@ -397,8 +397,10 @@ __device__ __forceinline__ u64 half_moves(u64 own, u64 opp) {
 // outside the line L = line[d][k] set, adding mv ripples from k through the opponent run on the line and stops on the first line
 // cell that holds no opponent stone; if that cell is own, everything on the line below it is flipped.
 __device__ __forceinline__ u64 flip_line(u64 L, u64 mv, u64 own, u64 opp) {
-    const u64 out = ((opp | ~L) + mv) & L & own;
-    return (out - (u64)(out != 0)) & L;
+    const u64 out = ((opp | ~L) + mv) & L & own;   // the bracketing stone (one bit) or 0
+    const u64 m = out - 1;                          // the bits below it; all ones when there is none: removed by the sign word
+    const uint32_t sg = (uint32_t)((int32_t)(uint32_t)(m >> 32) >> 31);
+    return m & L & ~(((u64)sg << 32) | sg);
 }
 // line_base = shared-window address of this lane's 16-byte strip of the line-mask table: row 2k holds line[0][k], line[1][k],
 // row 2k + 1 holds line[2][k], line[3][k] (line[d][k] = the cells beyond k along direction +1, +7, +8, +9 up to the board edge)
@@ -563,7 +565,8 @@ __global__ void __launch_bounds__(kPairMaxWarps * 32, 1) rollout_pair_kernel(Rol
                     double *sap = sa;
                     uint8_t *scp = sc;
 #pragma unroll 1
-                    while (wr) {   // (unrolling makes the warp run the remainders of all its lanes: measured slower)
+                    while (wr) {   // (unrolling makes the warp run the remainders of all its lanes, and requesting the next cell's record
+                                   // one trip ahead costs more in register moves than the latency it hides: both measured slower)
                         uint32_t q, below;
                         asm("bfind.u32 %0, %1;" : "=r"(q) : "r"(wr));              // top set bit: q = 31 - cell, wr != 0
                         asm("bmsk.clamp.b32 %0, 0, %1;" : "=r"(below) : "r"(q));  // the q bits below it

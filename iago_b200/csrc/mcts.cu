@@ -296,6 +296,7 @@ __global__ void __launch_bounds__(32) mcts_select_kernel(MctsDev d, MctsParams p
 #endif
 constexpr int kPipeWarps = IAGO_PIPE_WARPS;
 constexpr int kPipeMaxB = 1024;
+constexpr float kScreenEps = 8.0e-6f;   // fp32 screen of the select scores: see mcts_select_pipe_kernel
 
 // place_stone by the whole warp: lanes 0-3 find the stones bracketed along +1, +7, +8, +9, lanes 4-7 along the opposite directions on
 // the board turned by 180 degrees (one bit reversal), each by carry propagation along its line (see half_flips in rollout.cu: with
@@ -488,59 +489,81 @@ __global__ void __launch_bounds__(kPipeWarps * 32) mcts_select_pipe_kernel(MctsD
                 break;
             }
             // ---- select (MCTS.py:39-49): arg-max over children of Q + u, first maximum wins
-            // What does not depend on the earlier descents is computed BEFORE the wait: this node's visit count was final when it
-            // was read (every earlier descent had passed it), so the square root is, and so are the priors of its children (written
-            // when the node was expanded) and with them the numerators c_puct * P * sqrt(N).  Behind the wait only the visit
-            // statistics are read (plain loads: the stores of the other warps of this CTA went through the same L1) and the two
-            // divisions remain.
-            const double n_parent = (double)(n_here + vn_here - 1);  // without this descent's own virtual visit
-            const double sq = __dsqrt_rn(n_parent);
-            double num0 = 0.0;                                       // the numerator of the lane's first child (the common case: nch <= 32)
+            // The arg-max is that of the reference's float64 scores, found in two steps.  (1) An fp32 SCREEN: every lane scores its
+            // child in single precision (a dozen 4-cycle operations instead of a float64 square root and two float64 divisions: the
+            // time a warp spends on a level is what paces the pipeline of descents); one REDUX.MAX gives the best score, and every
+            // child within kScreenEps * (2 + |best|) of it — eight times the worst-case distance between an fp32 score and its float64
+            // value — is a candidate.  (2) Only when there is more than one candidate (near-ties, or more than 32 children) the
+            // float64 scores are computed and compared exactly as before.  A single candidate IS the float64 arg-max, so the tree
+            // does not change.  What does not depend on the earlier descents (the node's visit count, the priors) is read before the wait.
+            const int n_par = n_here + vn_here - 1;   // without this descent's own virtual visit
+            const float sqf = sqrtf((float)n_par);
+            uint4 w0 = make_uint4(0, 0, 0, 0);
+            float numf = 0.0f;
             if (lane < nch) {
-                const uint4 w0 = reinterpret_cast<const uint4 *>(nodes + fc + lane)[0];
-                const int cflags = (int)reinterpret_cast<const uint8_t *>(nodes + fc + lane)[46];
-                const double cP = __hiloint2double((int)w0.y, (int)w0.x);
-                const double cp = (cflags & F_P_F64) ? __dmul_rn(p.c_puct, cP) : (double)__fmul_rn((float)p.c_puct, (float)cP);
-                num0 = __dmul_rn(cp, sq);
+                w0 = reinterpret_cast<const uint4 *>(nodes + fc + lane)[0];
+                numf = (float)p.c_puct * (float)__hiloint2double((int)w0.y, (int)w0.x) * sqf;
             }
             if (!exclusive) pipe_wait(prog, a, stage + 1);
-            double best = -1.0e300;
-            int best_i = 1 << 30;
-            int b_n = 0, b_vn = 0, b_fc = -1, b_meta = 0;
-            for (int i = lane; i < nch; i += 32) {
-                const uint4 *raw = reinterpret_cast<const uint4 *>(nodes + fc + i);
-                const uint4 w1 = raw[1], w2 = raw[2];   // W v n | vn parent first_child meta
-                double num = num0;
-                if (i >= 32) {
-                    const uint4 w0 = raw[0];
-                    const int cflags = (int)((w2.w >> 16) & 0xFFu);
-                    const double cP = __hiloint2double((int)w0.y, (int)w0.x);
-                    const double cp = (cflags & F_P_F64) ? __dmul_rn(p.c_puct, cP) : (double)__fmul_rn((float)p.c_puct, (float)cP);
-                    num = __dmul_rn(cp, sq);
-                }
+            uint4 w1 = make_uint4(0, 0, 0, 0), w2 = make_uint4(0, 0, 0, 0);   // W v n | vn parent first_child meta of the lane's first child
+            float valf = -3.0e38f;
+            if (lane < nch) {
+                const uint4 *raw = reinterpret_cast<const uint4 *>(nodes + fc + lane);
+                w1 = raw[1]; w2 = raw[2];
                 const long long cW = (long long)(((u64)w1.y << 32) | (u64)w1.x);
-                const int cn = (int)w1.w, cvn = (int)w2.x;
-                const int tot = cn + cvn;
-                const double q = tot > 0 ? __ddiv_rn(__dsub_rn((double)cW * (1.0 / kFix), __dmul_rn(p.vloss, (double)cvn)), (double)tot) : 0.0;
-                const double den = __dadd_rn(0.01, (double)tot);
-                const double u = __ddiv_rn(num, den);
-                const double val = __dadd_rn(q, u);
-                if (val > best) {  // ascending i: the first maximum stays
-                    best = val; best_i = i;
-                    b_n = cn; b_vn = cvn; b_fc = (int)w2.z; b_meta = (int)w2.w;
+                const int cvn = (int)w2.x, tot = (int)w1.w + cvn;
+                const float totf = (float)tot;
+                const float qf = tot > 0 ? __fdividef((float)cW * (float)(1.0 / kFix) - (float)p.vloss * (float)cvn, totf) : 0.0f;
+                valf = qf + __fdividef(numf, 0.01f + totf);
+            }
+            int b_n = (int)w1.w, b_vn = (int)w2.x, b_fc = (int)w2.z, b_meta = (int)w2.w;   // the best child of THIS lane
+            int best_i, win;
+            {
+                const uint32_t fb = __float_as_uint(valf);
+                const uint32_t fkey = fb ^ ((uint32_t)((int32_t)fb >> 31) | 0x80000000u);   // order-preserving
+                const uint32_t mkey = __reduce_max_sync(0xFFFFFFFFu, fkey);
+                const float mf = __uint_as_float(mkey ^ (((mkey >> 31) - 1u) | 0x80000000u));
+                const unsigned cand = __ballot_sync(0xFFFFFFFFu, valf >= mf - kScreenEps * (2.0f + fabsf(mf)));
+                win = __ffs((int)cand) - 1;
+                best_i = win;
+                if (nch > 32 || (cand & (cand - 1)) != 0) {   // warp-uniform: near-ties are settled in float64
+                    const double sq = __dsqrt_rn((double)n_par);
+                    double best = -1.0e300;
+                    best_i = 1 << 30;
+                    for (int i = lane; i < nch; i += 32) {
+                        uint4 x0 = w0, x1 = w1, x2 = w2;
+                        if (i >= 32) {
+                            const uint4 *raw = reinterpret_cast<const uint4 *>(nodes + fc + i);
+                            x0 = raw[0]; x1 = raw[1]; x2 = raw[2];
+                        }
+                        const int cflags = (int)((x2.w >> 16) & 0xFFu);
+                        const double cP = __hiloint2double((int)x0.y, (int)x0.x);
+                        const double cp = (cflags & F_P_F64) ? __dmul_rn(p.c_puct, cP) : (double)__fmul_rn((float)p.c_puct, (float)cP);
+                        const long long cW = (long long)(((u64)x1.y << 32) | (u64)x1.x);
+                        const int cn = (int)x1.w, cvn = (int)x2.x;
+                        const int tot = cn + cvn;
+                        const double q = tot > 0 ? __ddiv_rn(__dsub_rn((double)cW * (1.0 / kFix), __dmul_rn(p.vloss, (double)cvn)), (double)tot) : 0.0;
+                        const double den = __dadd_rn(0.01, (double)tot);
+                        const double u = __ddiv_rn(__dmul_rn(cp, sq), den);
+                        const double val = __dadd_rn(q, u);
+                        if (val > best) {  // ascending i: the first maximum stays
+                            best = val; best_i = i;
+                            b_n = cn; b_vn = cvn; b_fc = (int)x2.z; b_meta = (int)x2.w;
+                        }
+                    }
+                    // warp arg-max on an order-preserving integer key: two 32-bit REDUX.MAX (high word, then low word among the lanes
+                    // that hold the high maximum) and a REDUX.MIN of the child index among the lanes that hold the maximum — the first
+                    // maximum wins, as in the scalar loop (every val is a finite double; -0.0 cannot come out of q + u with u >= +0)
+                    const long long bits = __double_as_longlong(best);
+                    const u64 key = (u64)bits ^ (u64)((bits >> 63) | (long long)0x8000000000000000LL);
+                    const uint32_t khi = (uint32_t)(key >> 32), klo = (uint32_t)key;
+                    const uint32_t mhi = __reduce_max_sync(0xFFFFFFFFu, khi);
+                    const uint32_t mlo = __reduce_max_sync(0xFFFFFFFFu, khi == mhi ? klo : 0u);
+                    const bool top = khi == mhi && klo == mlo;
+                    best_i = (int)__reduce_min_sync(0xFFFFFFFFu, top ? (uint32_t)best_i : 0xFFFFFFFFu);
+                    win = best_i & 31;   // child i is held by lane i & 31
                 }
             }
-            // warp arg-max on an order-preserving integer key: two 32-bit REDUX.MAX (high word, then low word among the lanes that
-            // hold the high maximum) and a REDUX.MIN of the child index among the lanes that hold the maximum — the first maximum
-            // wins, as in the scalar loop (every val is a finite double; -0.0 cannot come out of q + u with u >= +0)
-            const long long bits = __double_as_longlong(best);
-            const u64 key = (u64)bits ^ (u64)((bits >> 63) | (long long)0x8000000000000000LL);
-            const uint32_t khi = (uint32_t)(key >> 32), klo = (uint32_t)key;
-            const uint32_t mhi = __reduce_max_sync(0xFFFFFFFFu, khi);
-            const uint32_t mlo = __reduce_max_sync(0xFFFFFFFFu, khi == mhi ? klo : 0u);
-            const bool top = khi == mhi && klo == mlo;
-            best_i = (int)__reduce_min_sync(0xFFFFFFFFu, top ? (uint32_t)best_i : 0xFFFFFFFFu);
-            const int win = best_i & 31;   // child i is held by lane i & 31
             const int child = fc + best_i;
             n_here = __shfl_sync(0xFFFFFFFFu, b_n, win);
             vn_here = __shfl_sync(0xFFFFFFFFu, b_vn, win) + 1;   // with this descent's own virtual visit, stored below

@@ -16,8 +16,9 @@
 //       select (pass 1)  the B descents of a tree run in a fixed order, each seeing the virtual visits of the ones before it
 //                        (deterministic) — executed as a software pipeline over 8 warps per tree that preserves exactly that
 //                        order (mcts_select_pipe_kernel; mcts_select_kernel is the one-warp form, used for B < 8 and the
-//                        exact mode); lanes score the children in parallel in fp64; a leaf that must be expanded and needs
-//                        priors is parked and queued
+//                        exact mode); lanes score the children in parallel (pipelined form: an fp32 screen, float64 only for
+//                        near-ties — the arg-max is the float64 one either way); a leaf that must be expanded and needs priors
+//                        is parked and queued
 //       policy           ONE fused trunk launch over every queued position of every tree (trunk.cu, count on device)
 //       expand           priors written, children become visible
 //       select (pass 2)  the parked descents continue into the fresh children

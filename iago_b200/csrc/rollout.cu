@@ -335,8 +335,8 @@ __global__ void __launch_bounds__(kBlock) rollout_kernel(RolloutArgs a, const Ro
 // move sets, the half flip sets (each 2 x 32 bits + BREV), the two half sums of the softmax numerators and the candidate cell.
 // Against one thread per game this doubles the warps per SM (65,536 games = 27.7 warps per SM instead of 13.8), removes the
 // word selects from the per-cell loop and shortens the divergent loop from max(n) over 32 games to max(n_half) over 32 halves.
-// One CTA per SM: the 17 KB of tables are held once per SM instead of once per small CTA, which leaves room for 16 scratch slots
-// per lane and the flip line masks.  65,536 games = 4,096 warps = 147 CTAs of 28 warps; small batches use smaller CTAs (host side).
+// One CTA per SM: the tables (84 KB in bank strips, see PairLayout below) are held once per SM, next to 16 scratch slots per lane.
+// 65,536 games = 4,096 warps = 147 CTAs of 28 warps; small batches use smaller CTAs (host side).
 constexpr int kPairMaxWarps = 28;
 constexpr int kPairSlots = 16;    // running sums kept per lane; a half board with more legal cells (never seen in play) recomputes
 

@@ -541,6 +541,7 @@ __global__ void __launch_bounds__(kPairMaxWarps * 32, 1) rollout_pair_kernel(Rol
                     if (has && (placed & 7) == 0) {
                         uint32_t o[4];
                         philox_block(a.seed, gid, (((uint32_t)placed >> 3) << 1) + h, a.stream_id, o);
+                        __syncwarp(pmask);   // the partner has read the last word of the block these stores replace
 #pragma unroll
                         for (int j = 0; j < 4; j++) srnd[j * 32] = o[j];
                         __syncwarp(pmask);

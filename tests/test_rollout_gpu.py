@@ -85,6 +85,36 @@ def test_midgame_both_colours_vs_oracle(engine, cref, rollout_weights, golden_ru
     assert (out["final_p1"] == r1).all() and (out["final_p2"] == r2).all()
 
 
+def test_ragged_batches_and_mixed_endgames_vs_oracle(engine, cref, rollout_weights, golden_rules):
+    """The paired kernel's control flow is warp-uniform: games that have ended (or never existed: a batch that does not fill its
+    last warp) run on with an empty move.  Batches of 1 ... 1,000 games that mix openings, positions a few stones from the end, full
+    boards and boards without a legal move for either side, all three rng modes, every trajectory against the CPU oracle."""
+    from iago_b200 import Rng, boards
+    W, b = rollout_weights
+    rs = np.random.RandomState(77)
+    st_all = golden_rules["state"].astype(np.float32)
+    filled = (st_all != 0).sum(axis=1)
+    late = st_all[filled >= 56][:300]                      # a handful of empties left: games of very different lengths in one warp
+    mid = st_all[(filled > 20) & (filled < 40)][:300]
+    special = np.stack([np.ones(64, np.float32), np.full(64, 2, np.float32), np.zeros(64, np.float32),
+                        np.concatenate([np.ones(32), np.zeros(32)]).astype(np.float32)])   # full, full, empty, no move for anyone
+    pool = np.concatenate([late, mid, special, np.tile(boards.start_state().reshape(1, 64), (50, 1)).astype(np.float32)])
+    for n in (1, 2, 3, 15, 16, 17, 31, 33, 257, 1000):
+        st = pool[rs.randint(0, len(pool), size=n)]
+        col = rs.randint(1, 3, size=n).astype(np.uint8)
+        p1, p2 = bb(st)
+        out = engine.rollout_host(p1, p2, col, rng=Rng.philox(seed=n, game_id0=5 * n), want_moves=True)
+        ref = cref.simulate_batch(st, col.astype(np.int32), W, b, mode=cref.RNG_PHILOX, seed=n, game_id0=5 * n, threads=0)
+        assert (out["moves"] == ref["moves"]).all() and (out["result"] == ref["results"]).all(), n
+        assert (out["n_moves"] == ref["n_moves"]).all(), n
+        r1, r2 = bb(ref["final"])
+        assert (out["final_p1"] == r1).all() and (out["final_p2"] == r2).all(), n
+        assert int(out["counters"][0]) == int(ref["n_moves"].sum()) and int(out["counters"][1]) == int(ref["n_turns"].sum()), n
+        # the same games replayed from their move logs (rules-only instantiation) end on the same boards
+        rep = engine.rollout_host(p1, p2, col, rng=Rng.replay_moves(out["moves"]))
+        assert (rep["final_p1"] == r1).all() and (rep["final_p2"] == r2).all() and (rep["result"] == ref["results"]).all(), n
+
+
 MANY_MOVES = [  # hill-climbed boards with 34 / 34 / 33 legal moves for colour 1 (more than the kernel's 32 scratch slots)
     "0120100002100220021201200021011001010120021220200212000000000021",
     "0000002112020000211122200220110000002120000001101201222011100000",

@@ -468,7 +468,7 @@ __global__ void __launch_bounds__(kPipeWarps * 32) mcts_select_pipe_kernel(MctsD
                     }
                 }
                 if (lane == 0 && !park && p.need_v) {   // the value of a node is asked for once (cache_v): claimed in descent order
-                    const uint8_t fl = nodes[node].flags;
+                    const uint8_t fl = (uint8_t)flags;   // read after descent a - 1 had ended (the header re-read above, or a level scored since)
                     const bool have = p.cache_v && (fl & (F_V_VALID | F_V_CLAIMED));
                     if (!have) {
                         if (p.cache_v) nodes[node].flags = (uint8_t)(fl | F_V_CLAIMED);

@@ -102,7 +102,9 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            time.sleep(0.002)
+            # a few closely spaced samples for the short regions (the headline step is ~10 ms), then 20 Hz (NVML queries take a driver
+            # lock; the long sections read device counters from the host every pair of turns)
+            time.sleep(0.002 if len(self.samples) < 8 else 0.05)
 
     def __enter__(self):
         if self.ok:
@@ -117,7 +119,7 @@ class ClockSampler:
     def summary(self):
         if not self.ok or not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "note": "no NVML samples"}
-        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+        return {"sm_mhz": statistics.median(self.samples), "sm_min_mhz": min(self.samples), "sm_max_mhz": self.max_mhz,
                 "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
@@ -433,8 +435,6 @@ def run_ours(args, rank, world, local_rank):
                              "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback",
                              "note": "38 algorithmic bytes per game; shown to document that HBM is not the limiter"},
         }
-        if world == 1 and not args.no_cpu:
-            line["cpu_baseline"] = cpu_baseline_block()
     extra = {}
     for name, fn in (("selfplay", section_selfplay), ("mcts", section_mcts), ("reinforce", section_reinforce),
                      ("valuegen", section_valuegen)):
@@ -444,6 +444,9 @@ def run_ours(args, rank, world, local_rank):
             except Exception as e:  # a failed extra section must not lose the headline line
                 extra[name] = {"error": repr(e)[:300]}
     if rank == 0:
+        # the all-core CPU leg runs last, after every GPU section has been timed
+        if world == 1 and not args.no_cpu:
+            line["cpu_baseline"] = cpu_baseline_block()
         line.update(extra)
         print(json.dumps(line), flush=True)
     if dist is not None:
@@ -484,11 +487,13 @@ def section_selfplay(eng, args, rank, world, dev, dist, barrier):
         kw = dict(greedy=greedy, precision=precision)
         if init is not None:
             kw.update(init_p1=init[0], init_p2=init[1])
-        eng.selfplay(0, 0, n, rng=Rng.philox(seed=1, stream_id=1), **kw)  # warm-up at full size (workspaces, clocks)
+        res = None
+        for w in range(3):   # warm-up at full size, holding the previous step's result like the timed loop does: both sets of result
+            res = eng.selfplay(0, 0, n, rng=Rng.philox(seed=1 + w, stream_id=1), **kw)   # tensors exist before the timing starts (with
+            # one discarded warm-up step the second timed step paid a cudaMalloc of the record buffers: 180-250 ms instead of 138)
         barrier()
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         fwd = evaluated = 0
-        res = None
         with ClockSampler(dev.index or 0) as clk:
             for i in range(steps):
                 ev[i][0].record()

@@ -280,6 +280,25 @@ __global__ void __launch_bounds__(32) mcts_select_kernel(MctsDev d, MctsParams p
     if (lane == 0) d.n_nodes[t] = n_nodes;
 }
 
+// priors: child P = float32(prob[action] + 0.1) (MCTS.py:93-99, :18-19); the children become visible.
+__device__ __forceinline__ void expand_one(const MctsDev &d, int j) {
+    MctsNode *nd = d.nodes + d.pol_node[j];
+    MctsNode *tree = d.nodes + (size_t)(d.pol_node[j] / d.cap) * d.cap;
+    const int c = nd->nch_pending, fc = nd->first_child;
+    const float *pr = d.probs + (size_t)j * 64;
+    for (int i = 0; i < c; i++) {
+        MctsNode *ch = tree + fc + i;
+        ch->P = (double)__fadd_rn(pr[ch->action], 0.1f);
+    }
+    nd->nch = (uint8_t)c;
+    nd->nch_pending = 0;
+    nd->flags &= (uint8_t)~F_PENDING;
+}
+__global__ void mcts_expand_kernel(MctsDev d) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < d.counts[0]) expand_one(d, j);
+}
+
 // ---------------------------------------------------------------- pipelined select
 // The same descents in the same order, as a software pipeline: kPipeWarps warps per tree, warp w runs the tree's active descents
 // w, w + W, w + 2W, ... .  Descent a may work on stage k (stage 0 = root bookkeeping, stage L + 1 = choosing a child at depth L)
@@ -349,7 +368,9 @@ __device__ __forceinline__ void pipe_signal(volatile int *prog, int a, int value
     if (lane == 0) prog[a] = value;
 }
 
-__global__ void __launch_bounds__(kPipeWarps * 32) mcts_select_pipe_kernel(MctsDev d, MctsParams p, int pass) {
+// expand_first (pass 2 of a search with a few trees): the priors of this tree's pending nodes are written by this launch instead of
+// a launch of their own in front of it.
+__global__ void __launch_bounds__(kPipeWarps * 32) mcts_select_pipe_kernel(MctsDev d, MctsParams p, int pass, int expand_first) {
     __shared__ volatile int prog[kPipeMaxB];
     __shared__ short active[kPipeMaxB];
     __shared__ int n_active;
@@ -365,16 +386,38 @@ __global__ void __launch_bounds__(kPipeWarps * 32) mcts_select_pipe_kernel(MctsD
     const int t = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     MctsNode *nodes = d.nodes + (size_t)t * d.cap;
     const long long done = d.done[t];
-    if (threadIdx.x == 0) {   // the descents that run in this pass, in slot order (a few hundred at most)
-        int c = 0;
-        for (int s = 0; s < p.B; s++) {
-            const bool on = pass == 1 ? (done + s < p.target) : (d.status[t * p.B + s] == S_PARKED);
-            if (on) active[c++] = (short)s;
+    if (expand_first) {
+        const int nreq = d.counts[0];
+        for (int j = threadIdx.x; j < nreq; j += blockDim.x)
+            if (d.pol_node[j] / d.cap == t) expand_one(d, j);
+        __syncthreads();   // (block-wide visibility of the children for the descents below)
+    }
+    // the descents that run in this pass, in slot order (ballot + per-warp offsets: one thread walking the B status bytes of a parked
+    // pass cost 5 us per launch)
+    {
+        __shared__ int s_wcount[kPipeWarps];
+        int base = 0;
+        for (int s0 = 0; s0 < p.B; s0 += (int)blockDim.x) {
+            const int s = s0 + (int)threadIdx.x;
+            const bool on = s < p.B && (pass == 1 ? (done + s < p.target) : (d.status[t * p.B + s] == S_PARKED));
+            const unsigned bal = __ballot_sync(0xFFFFFFFFu, on);
+            if (lane == 0) s_wcount[warp] = __popc(bal);
+            __syncthreads();
+            int off = base, tot = 0;
+            for (int w = 0; w < kPipeWarps; w++) {
+                if (w < warp) off += s_wcount[w];
+                tot += s_wcount[w];
+            }
+            if (on) active[off + __popc(bal & ((1u << lane) - 1u))] = (short)s;
+            base += tot;
+            __syncthreads();
         }
-        n_active = c;
-        s_n_nodes = d.n_nodes[t];
-        s_npol = 0;
-        s_nval = 0;
+        if (threadIdx.x == 0) {
+            n_active = base;
+            s_n_nodes = d.n_nodes[t];
+            s_npol = 0;
+            s_nval = 0;
+        }
     }
     for (int i = threadIdx.x; i < p.B; i += blockDim.x) {
         prog[i] = 0;
@@ -606,25 +649,7 @@ __global__ void __launch_bounds__(kPipeWarps * 32) mcts_select_pipe_kernel(MctsD
     }
 }
 
-// priors: child P = float32(prob[action] + 0.1) (MCTS.py:93-99, :18-19); the children become visible.
-__global__ void mcts_expand_kernel(MctsDev d) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= d.counts[0]) return;
-    MctsNode *nd = d.nodes + d.pol_node[j];
-    MctsNode *tree = d.nodes + (size_t)(d.pol_node[j] / d.cap) * d.cap;
-    const int c = nd->nch_pending, fc = nd->first_child;
-    const float *pr = d.probs + (size_t)j * 64;
-    for (int i = 0; i < c; i++) {
-        MctsNode *ch = tree + fc + i;
-        ch->P = (double)__fadd_rn(pr[ch->action], 0.1f);
-    }
-    nd->nch = (uint8_t)c;
-    nd->nch_pending = 0;
-    nd->flags &= (uint8_t)~F_PENDING;
-}
-
-__global__ void mcts_scatter_value_kernel(MctsDev d, int cache_v) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void scatter_value_one(const MctsDev &d, int cache_v, int j) {
     if (j >= d.counts[1]) return;
     const float v = d.vals[j];
     d.v_slot[d.val_slot[j]] = v;
@@ -634,6 +659,7 @@ __global__ void mcts_scatter_value_kernel(MctsDev d, int cache_v) {
         nd->flags = (uint8_t)((nd->flags & ~F_V_CLAIMED) | F_V_VALID);
     }
 }
+__global__ void mcts_scatter_value_kernel(MctsDev d, int cache_v) { scatter_value_one(d, cache_v, blockIdx.x * blockDim.x + threadIdx.x); }
 
 // leaf_value = (1 - lambda) * v + lambda * z with numpy's scalar types (MCTS.py:123-125): float32 when lambda < 1
 // (v is np.float32, Python scalars are weak), float64 when lambda >= 1 (v is the int 0).
@@ -690,8 +716,7 @@ __global__ void mcts_backup_exact_kernel(MctsDev d, MctsParams p) {
 }
 
 // batched mode: one thread per slot, order-free integer atomics.
-__global__ void mcts_backup_atomic_kernel(MctsDev d, MctsParams p) {
-    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void backup_atomic_one(const MctsDev &d, const MctsParams &p, int slot) {
     if (slot >= d.T * p.B) return;
     const int t = slot / p.B, s = slot - t * p.B;
     if (d.status[slot] == S_INACTIVE) return;
@@ -710,12 +735,21 @@ __global__ void mcts_backup_atomic_kernel(MctsDev d, MctsParams p) {
         atomicSub(&nd->vn, 1);
     }
 }
+__global__ void mcts_backup_atomic_kernel(MctsDev d, MctsParams p) { backup_atomic_one(d, p, blockIdx.x * blockDim.x + threadIdx.x); }
 
-__global__ void mcts_advance_done_kernel(MctsDev d, MctsParams p) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void advance_done_one(const MctsDev &d, const MctsParams &p, int t) {
     if (t >= d.T) return;
     const long long left = p.target - d.done[t];
     d.done[t] += left < p.B ? (left > 0 ? left : 0) : p.B;
+}
+__global__ void mcts_advance_done_kernel(MctsDev d, MctsParams p) { advance_done_one(d, p, blockIdx.x * blockDim.x + threadIdx.x); }
+
+// The end of a wave as ONE launch when all slots fit one CTA (T * B <= 1,024: a single tree, a few root-parallel trees): every
+// playout backed up, then the playout counters advanced (a search of one tree is bound by dependent launches).
+__global__ void __launch_bounds__(1024) mcts_tail_kernel(MctsDev d, MctsParams p) {
+    backup_atomic_one(d, p, threadIdx.x);
+    __syncthreads();
+    advance_done_one(d, p, threadIdx.x);
 }
 
 __global__ void mcts_init_roots_kernel(MctsDev d, const u64 *p1, const u64 *p2, const uint8_t *color, int reset_tree) {
@@ -957,13 +991,14 @@ int iago_mcts_search(iago_mcts *m, const iago_mcts_params *pp, void *stream) {
     auto wave = [&](cudaStream_t ws) -> int {
         IAGO_CUDA(cudaMemsetAsync(d.counts, 0, 2 * sizeof(int), ws));
         const bool pipe = !p.exact && p.B >= 8 && p.B <= kPipeMaxB;   // descents of a tree as a software pipeline over 8 warps
-        if (pipe) mcts_select_pipe_kernel<<<m->T, kPipeWarps * 32, 0, ws>>>(d, p, 1);
+        if (pipe) mcts_select_pipe_kernel<<<m->T, kPipeWarps * 32, 0, ws>>>(d, p, 1, 0);
         else mcts_select_kernel<<<m->T, 32, 0, ws>>>(d, p, 1);
         IAGO_CUDA(cudaGetLastError());
         int rc = trunk_launch(ctx, pp->slot_policy, 0, (const uint64_t *)d.pol_p1, (const uint64_t *)d.pol_p2, d.pol_color, S, d.probs, 1, pp->precision, ws, d.counts + 0);
         if (rc) return rc;
-        mcts_expand_kernel<<<(unsigned)((S + 127) / 128), 128, 0, ws>>>(d);
-        if (pipe) mcts_select_pipe_kernel<<<m->T, kPipeWarps * 32, 0, ws>>>(d, p, 2);
+        const bool expand_in_select = pipe && m->T <= 8;   // a few trees: every CTA can afford to look through the request list
+        if (!expand_in_select) mcts_expand_kernel<<<(unsigned)((S + 127) / 128), 128, 0, ws>>>(d);
+        if (pipe) mcts_select_pipe_kernel<<<m->T, kPipeWarps * 32, 0, ws>>>(d, p, 2, expand_in_select ? 1 : 0);
         else mcts_select_kernel<<<m->T, 32, 0, ws>>>(d, p, 2);
         IAGO_CUDA(cudaGetLastError());
         // value net and rollouts read the same leaves and write different outputs: the rollouts go to a second stream
@@ -983,13 +1018,16 @@ int iago_mcts_search(iago_mcts *m, const iago_mcts_params *pp, void *stream) {
             if (rc) return rc;
             if (fork) IAGO_CUDA(cudaEventRecord(m->ev_join, m->side));
         }
+        const bool one_cta_tail = !p.exact && S <= 1024;
         if (run_v) {
             rc = trunk_launch(ctx, pp->slot_value, 1, (const uint64_t *)d.val_p1, (const uint64_t *)d.val_p2, d.val_color, S, d.vals, 0, pp->precision, ws, d.counts + 1);
             if (rc) return rc;
             mcts_scatter_value_kernel<<<(unsigned)((S + 127) / 128), 128, 0, ws>>>(d, p.cache_v);
         }
         if (fork) IAGO_CUDA(cudaStreamWaitEvent(ws, m->ev_join, 0));
-        if (p.exact) {
+        if (one_cta_tail) {
+            mcts_tail_kernel<<<1, 1024, 0, ws>>>(d, p);
+        } else if (p.exact) {
             mcts_backup_exact_kernel<<<(m->T + 63) / 64, 64, 0, ws>>>(d, p);
         } else {
             mcts_backup_atomic_kernel<<<(unsigned)((S + 127) / 128), 128, 0, ws>>>(d, p);

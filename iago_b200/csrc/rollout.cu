@@ -245,6 +245,7 @@ struct RolloutArgs {
     int8_t *move_log;
     u64 *counters;
     const u64 *game_ids;  // nullable: Philox game id of game g (default game_id0 + g)
+    int game_threads;     // paired kernel: threads of a CTA that own games (the rest only help to fill the tables); 0 = all
 };
 
 template <int MODE, bool LOG, bool FAST>
@@ -493,8 +494,11 @@ __global__ void __launch_bounds__(kPairMaxWarps * 32, 1) rollout_pair_kernel(Rol
     constexpr unsigned kFull = 0xFFFFFFFFu;
     const int h = threadIdx.x & 1;
     const unsigned pmask = 3u << (threadIdx.x & 30);
-    const long long g = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 1;
-    const bool valid = g < a.n;   // the same for both lanes of a pair, as is every predicate below
+    // small batches run in CTAs of at least 8 warps so that the 84 KB of tables are filled by 256 threads; only the first
+    // a.game_threads threads of a CTA own games, the others leave after the fill
+    const int gthreads = a.game_threads ? a.game_threads : (int)blockDim.x;
+    const long long g = ((long long)blockIdx.x * gthreads + threadIdx.x) >> 1;
+    const bool valid = g < a.n && (int)threadIdx.x < gthreads;   // the same for both lanes of a pair, as is every predicate below
     int placed = 0, turns = 0, color = 1, stone_num = 64;
     u64 gid = 0, own = 0, opp = 0;
     if (valid) {
@@ -799,6 +803,9 @@ static void launch_rollout(const RolloutArgs &a, const RolloutWeights *w, cudaSt
         long long wpc = (warps + sms - 1) / sms;
         wpc = wpc < 2 ? 2 : wpc > kPairMaxWarps ? kPairMaxWarps : wpc;
         const unsigned grid = (unsigned)((warps + wpc - 1) / wpc);
+        RolloutArgs ah = a;
+        ah.game_threads = (int)wpc * 32;
+        const unsigned cta_threads = (unsigned)(wpc < 8 ? 8 : wpc) * 32;   // helper warps for the table fill of a small CTA
         static int smem = 0;                          // the whole opt-in window (the kernel's layout is built around its 64 KB boundary)
         if (!smem) {
             int dev = 0;
@@ -808,11 +815,11 @@ static void launch_rollout(const RolloutArgs &a, const RolloutWeights *w, cudaSt
         if (a.move_log) {
             if (!attr_set[1]) cudaFuncSetAttribute(rollout_pair_kernel<MODE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             attr_set[1] = true;
-            rollout_pair_kernel<MODE, true><<<grid, (unsigned)wpc * 32, (size_t)smem, s>>>(a, w);
+            rollout_pair_kernel<MODE, true><<<grid, cta_threads, (size_t)smem, s>>>(ah, w);
         } else {
             if (!attr_set[0]) cudaFuncSetAttribute(rollout_pair_kernel<MODE, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
             attr_set[0] = true;
-            rollout_pair_kernel<MODE, false><<<grid, (unsigned)wpc * 32, (size_t)smem, s>>>(a, w);
+            rollout_pair_kernel<MODE, false><<<grid, cta_threads, (size_t)smem, s>>>(ah, w);
         }
         return;
     }

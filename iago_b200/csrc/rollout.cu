@@ -246,6 +246,8 @@ struct RolloutArgs {
     u64 *counters;
     const u64 *game_ids;  // nullable: Philox game id of game g (default game_id0 + g)
     int game_threads;     // paired kernel: threads of a CTA that own games (the rest only help to fill the tables); 0 = all
+    u64 *counters_out;    // paired kernel, nullable: the CTA that finishes last writes the two totals here (host-mapped memory: no
+    unsigned *ticket;     //   copy behind the kernel) and leaves counters[] and the ticket at zero for the next launch
 };
 
 template <int MODE, bool LOG, bool FAST>
@@ -654,6 +656,19 @@ __global__ void __launch_bounds__(kPairMaxWarps * 32, 1) rollout_pair_kernel(Rol
             atomicAdd(a.counters + 0, (u64)p);
             atomicAdd(a.counters + 1, (u64)t);
         }
+        if (a.counters_out) {
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                __threadfence();
+                if (atomicAdd(a.ticket, 1u) == gridDim.x - 1) {   // every other CTA fenced its adds before it took its ticket
+                    __threadfence();
+                    a.counters_out[0] = atomicExch(a.counters + 0, 0ULL);
+                    a.counters_out[1] = atomicExch(a.counters + 1, 0ULL);
+                    *a.ticket = 0u;
+                    __threadfence_system();
+                }
+            }
+        }
     }
 }
 
@@ -1044,17 +1059,22 @@ int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, con
     if (mapped) {
         // Pinned, device-mapped caller buffers and no replay stream: ONE launch over the whole batch whose loads and stores cross
         // PCIe themselves (17 B in / 21 B out per game, coalesced, once per game) — no staging, no copy engines, full occupancy.
+        // The plies / turns totals come back the same way: the last CTA writes them into the pinned staging block (no memset in
+        // front of the launch, no copy behind it: ctx->d_counters[0..1] and the ticket in [2] are zero between launches).
         cudaStream_t s = ctx->stream;
-        char *h = (char *)ctx->stage.host, *d = (char *)ctx->stage.dev;
-        IAGO_CUDA(cudaMemsetAsync(d + o_cnt, 0, 16, s));
+        char *h = (char *)ctx->stage.host;
+        void *h_cnt_dev = nullptr;
+        const bool publish = ctx->rollout_fast;   // the paired kernel; the one-thread kernel of unusual weight sets keeps the copy
+        if (publish) IAGO_CUDA(cudaHostGetDevicePointer(&h_cnt_dev, h + o_cnt, 0));
+        else IAGO_CUDA(cudaMemsetAsync(ctx->d_counters, 0, 16, s));
         RolloutArgs a{(const u64 *)m_p1, (const u64 *)m_p2, (const uint8_t *)m_col, (long long)n, rng->stream_id, rng->seed,
                       rng->game_id0, nullptr, 0, nullptr, 0, (int8_t *)m_res, (u64 *)m_f1, (u64 *)m_f2, (int32_t *)m_nm,
-                      (int8_t *)m_log, (u64 *)(d + o_cnt), nullptr};
+                      (int8_t *)m_log, (u64 *)ctx->d_counters, nullptr, 0, (u64 *)h_cnt_dev, (unsigned *)(ctx->d_counters + 2)};
         IAGO_CUDA(cudaEventRecord(ctx->ev0, s));
         launch_rollout_mode(a, rng->mode, ctx->rollout_fast, ctx->d_rollout, s);
         IAGO_CUDA(cudaGetLastError());
         IAGO_CUDA(cudaEventRecord(ctx->ev1, s));
-        IAGO_CUDA(cudaMemcpyAsync(h + o_cnt, d + o_cnt, 16, D2H, s));
+        if (!publish) IAGO_CUDA(cudaMemcpyAsync(h + o_cnt, ctx->d_counters, 16, cudaMemcpyDeviceToHost, s));
         ctx->timed = true;
         IAGO_CUDA(cudaStreamSynchronize(s));
         if (counters_host) memcpy(counters_host, h + o_cnt, 16);

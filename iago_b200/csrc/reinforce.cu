@@ -986,7 +986,9 @@ int iago_trainer_create(iago_ctx *ctx, int kind, const float *params, int64_t n_
     A(t->dymax, 8);
     t->slices = 24;                                  // fp32 weight-gradient kernel: position slices of the 64/128-input-channel layers
     t->slices0 = 2 * ctx->sm_count;                  // ... and of block 1 (2 input channels: one c tile, so the slices are the whole grid)
-    t->tc_slices = (ctx->sm_count + 2) / 3;          // 3 kernel rows x slices ~ one CTA per SM
+    t->tc_slices = ctx->sm_count >= 3 ? ctx->sm_count / 3 : 1;   // 3 kernel rows x slices <= one CTA per SM: the kernel's 188 KB of shared
+                                                                 // memory allow one CTA per SM, so rounding UP (150 CTAs on 148 SMs) ran
+                                                                 // every launch as two waves — twice the time of 147 CTAs
     t->partial_stride = (size_t)128 * 128 * 9 + 128;
     A(t->partial, (size_t)(t->tc_slices > t->slices ? t->tc_slices : t->slices) * t->partial_stride);
 #undef A

@@ -212,6 +212,63 @@ __global__ void __launch_bounds__(256) wgrad3x3_kernel(const float *__restrict__
     }
 }
 
+// Block 1 (2 input planes -> 64 channels): the generic kernel above keeps 16 input channels x 16 groups of 8 outputs busy, of which
+// this layer uses 2 x 8 (6 % of its FMAs).  Here a thread owns one output channel and a quarter of the board rows for both planes and
+// all nine taps (18 accumulators + the bias sum), the quarters are added in a fixed order at the end.  Same output layout:
+// partial[slice][(o * 2 + c) * 9 + tap], then the 64 bias sums.
+__global__ void __launch_bounds__(256) wgrad_block1_kernel(const float *__restrict__ x, const float *__restrict__ dy,
+                                                           float *__restrict__ partial, long long m, int pos_per_slice,
+                                                           size_t partial_stride) {
+    __shared__ float dy_s[64][65];
+    __shared__ float x_s[2][104];
+    __shared__ float red[4][64][19];
+    const int tid = threadIdx.x, o = tid & 63, q = tid >> 6;
+    const long long p_begin = (long long)blockIdx.x * pos_per_slice;
+    const long long p_end = min(m, p_begin + pos_per_slice);
+    float acc[2][9], bsum = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int t = 0; t < 9; t++) acc[c][t] = 0.0f;
+    for (int i = tid; i < 2 * 104; i += 256) (&x_s[0][0])[i] = 0.0f;   // the halo stays zero
+    for (long long p = p_begin; p < p_end; p++) {
+        __syncthreads();
+        for (int i = tid; i < 64 * 64; i += 256) dy_s[i >> 6][i & 63] = dy[(size_t)p * 64 * 64 + i];
+        if (tid < 128) {
+            const int c = tid >> 6, cell = tid & 63;
+            x_s[c][((cell >> 3) + 1) * 10 + (cell & 7) + 1] = x[((size_t)p * 2 + c) * 64 + cell];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 2; r++) {
+            const int row = q * 2 + r;
+#pragma unroll
+            for (int col = 0; col < 8; col++) {
+                const float d = dy_s[o][row * 8 + col];
+                bsum += d;
+#pragma unroll
+                for (int c = 0; c < 2; c++)
+#pragma unroll
+                    for (int t = 0; t < 9; t++) acc[c][t] = fmaf(d, x_s[c][(row + t / 3) * 10 + col + t % 3], acc[c][t]);
+            }
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < 2; c++)
+#pragma unroll
+        for (int t = 0; t < 9; t++) red[q][o][c * 9 + t] = acc[c][t];
+    red[q][o][18] = bsum;
+    __syncthreads();
+    float *dst = partial + (size_t)blockIdx.x * partial_stride;
+    for (int i = tid; i < 64 * 19; i += 256) {
+        const int oo = i / 19, k = i - oo * 19;
+        const float v = (red[0][oo][k] + red[1][oo][k]) + (red[2][oo][k] + red[3][oo][k]);
+        if (k < 18) dst[(size_t)oo * 18 + k] = v;        // (o * 2 + c) * 9 + tap = o * 18 + c * 9 + tap
+        else dst[(size_t)64 * 2 * 9 + oo] = v;
+    }
+}
+
 // ---------------------------------------------------------------- weight gradient on the tensor cores (layers with Cout = 128)
 // dW[o][c][tap] = sum_{p, cell} dY[p][o][cell] * X[p][c][cell + tap] as 9 GEMMs D_tap[o][c] += A[o][k] * B_tap[c][k], k = (p, cell).
 // One CTA owns one kernel row ky (3 taps, 3 x N fp32 TMEM columns) and one slice of positions; per position (one pipeline
@@ -560,18 +617,23 @@ __global__ void __launch_bounds__(64) head_kernel(const float *__restrict__ act8
 
 // dw9[c] = sum_{p,cell} dlogit[p][cell] * act8[p][c][cell]  (block c < 128); db10[cell] = sum_p dlogit[p][cell] (block 128 + cell);
 // block 192: loss numerator = sum_p loss_terms[p].  Fixed-order tree per block.
+// grid (193, kHeadSlices): block (b, s) sums its quantity over the s-th slice of the positions into partial[s * 193 + b] (one CTA per
+// quantity streamed the whole batch through one dependent accumulation chain: 0.31 ms per 8,192 positions); head_grad_reduce_kernel
+// adds the slices in order.
+constexpr int kHeadSlices = 16;
 __global__ void __launch_bounds__(256) head_grad_kernel(const float *__restrict__ act8, const float *__restrict__ dlogit,
-                                                        const float *__restrict__ loss_terms, float *__restrict__ gw9,
-                                                        float *__restrict__ gb10, float *__restrict__ gloss, long long m, int accumulate) {
+                                                        const float *__restrict__ loss_terms, float *__restrict__ partial, long long m) {
     __shared__ float red[256];
     const int blk = blockIdx.x, tid = threadIdx.x;
+    const long long per = (m + kHeadSlices - 1) / kHeadSlices;
+    const long long p0 = (long long)blockIdx.y * per, p1 = min(m, p0 + per);
     float s = 0.0f;
     if (blk < 128) {
-        for (long long i = tid; i < m * 64; i += 256) s += dlogit[i] * act8[((i >> 6) * 128 + blk) * 64 + (i & 63)];
+        for (long long i = p0 * 64 + tid; i < p1 * 64; i += 256) s += dlogit[i] * act8[((i >> 6) * 128 + blk) * 64 + (i & 63)];
     } else if (blk < 192) {
-        for (long long p = tid; p < m; p += 256) s += dlogit[p * 64 + (blk - 128)];
+        for (long long p = p0 + tid; p < p1; p += 256) s += dlogit[p * 64 + (blk - 128)];
     } else {
-        for (long long p = tid; p < m; p += 256) s += loss_terms[p];
+        for (long long p = p0 + tid; p < p1; p += 256) s += loss_terms[p];
     }
     red[tid] = s;
     __syncthreads();
@@ -579,10 +641,16 @@ __global__ void __launch_bounds__(256) head_grad_kernel(const float *__restrict_
         if (tid < o) red[tid] += red[tid + o];
         __syncthreads();
     }
-    if (tid == 0) {
-        float *dst = blk < 128 ? gw9 + blk : (blk < 192 ? gb10 + (blk - 128) : gloss);
-        *dst = accumulate ? *dst + red[0] : red[0];
-    }
+    if (tid == 0) partial[blockIdx.y * 193 + blk] = red[0];
+}
+__global__ void head_grad_reduce_kernel(const float *__restrict__ partial, float *__restrict__ gw9, float *__restrict__ gb10,
+                                        float *__restrict__ gloss, int accumulate) {
+    const int blk = threadIdx.x;
+    if (blk >= 193) return;
+    float v = 0.0f;
+    for (int s = 0; s < kHeadSlices; s++) v += partial[s * 193 + blk];
+    float *dst = blk < 128 ? gw9 + blk : (blk < 192 ? gb10 + (blk - 128) : gloss);
+    *dst = accumulate ? *dst + v : v;
 }
 
 // ---------------------------------------------------------------- Value head (network.py:92-95) forward + backward, train_value.py:50-56
@@ -1078,7 +1146,10 @@ static int backward_trunk(iago_trainer *t, int64_t m, float *grad, int accumulat
         } else {
             const int count = kCout[l] * kCin[l] * 9 + kCout[l];  // W then b are adjacent in the flat layout as well
             const size_t stride = l == 0 ? (size_t)count : t->partial_stride;
-            wgrad3x3_kernel<<<dim3((kCin[l] + 15) / 16, slices), 256, 0, s>>>(t->act[l], dy, t->partial, m, kCin[l], kCout[l], pos_per_slice, stride);
+            if (l == 0 && kCin[0] == 2 && kCout[0] == 64)
+                wgrad_block1_kernel<<<slices, 256, 0, s>>>(t->act[l], dy, t->partial, m, pos_per_slice, stride);
+            else
+                wgrad3x3_kernel<<<dim3((kCin[l] + 15) / 16, slices), 256, 0, s>>>(t->act[l], dy, t->partial, m, kCin[l], kCout[l], pos_per_slice, stride);
             reduce_slices_kernel<<<(count + 255) / 256, 256, 0, s>>>(t->partial, grad + t->w_off[l], count, slices, stride, accumulate);
         }
         if (!t->use_tc && l > 0) {
@@ -1106,7 +1177,8 @@ int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *op
     // ---- head forward + backward
     head_kernel<<<(unsigned)m, 64, 0, s>>>(t->act[8], t->params + t->w9_off, t->params + t->b10_off, action, reward, t->dlogit,
                                           t->dyb[7], t->loss_terms, probs_out, m);
-    head_grad_kernel<<<193, 256, 0, s>>>(t->act[8], t->dlogit, t->loss_terms, grad + t->w9_off, grad + t->b10_off, grad + kNP, m, accumulate);
+    head_grad_kernel<<<dim3(193, kHeadSlices), 256, 0, s>>>(t->act[8], t->dlogit, t->loss_terms, t->partial, m);
+    head_grad_reduce_kernel<<<1, 256, 0, s>>>(t->partial, grad + t->w9_off, grad + t->b10_off, grad + kNP, accumulate);
     IAGO_CUDA(cudaGetLastError());
     rc = backward_trunk(t, m, grad, accumulate, stream);
     if (rc) return rc;

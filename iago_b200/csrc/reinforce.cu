@@ -278,7 +278,12 @@ __global__ void __launch_bounds__(256) wgrad_block1_kernel(const float *__restri
 // zero filled) of [c group][padded row 0..9][c % 8][8 cells], so that a tap is just a descriptor start address: copy kx, padded
 // row y + ky.  One thread issues 4 K=16 MMAs per tap and stage; accumulators stay in TMEM until the slice is done.
 // Output: partial[slice][tap][o][c] (coalesced); reduce_taps_kernel sums the slices in order and writes [o][c][tap].
-constexpr int kWgThreads = 288;               // warps 0-7 producers (0-3 also epilogue), warp 8 = MMA issuer
+#ifndef IAGO_WG_PRODUCERS
+#define IAGO_WG_PRODUCERS 16
+#endif
+constexpr int kWgProducers = IAGO_WG_PRODUCERS;          // producer warps (8 or 16; warps 0-3 also run the epilogue), then one MMA issuer warp
+constexpr int kWgItems = 32 / kWgProducers;               // (channel group, row half) items of the dY tile per producer thread and position
+constexpr int kWgThreads = kWgProducers * 32 + 32;
 constexpr int kWgATile = 16 * 8 * 128;        // dY tile: 16 o-groups x 8 rows x 128 B = 16,384
 constexpr int kWgXCopy = 16 * 10 * 128;       // one shifted copy of the X tile: 20,480
 constexpr int kWgXBase = 2 * kWgATile;        // dY hi tile, dY lo tile, then the three X copies
@@ -343,13 +348,13 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
     for (int i = tid; i < kWgStages * kWgStage / 16; i += kWgThreads) reinterpret_cast<uint4 *>(smem)[i] = make_uint4(0, 0, 0, 0);  // halo rows stay zero
     if (tid == 0) {
         for (int s = 0; s < kWgStages; s++) {
-            mbar_init(bar_full + 8 * s, 256);
+            mbar_init(bar_full + 8 * s, kWgProducers * 32);
             mbar_init(bar_empty + 8 * s, 1);
         }
         mbar_init(bar_acc, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) {
+    if (warp == kWgProducers) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(512) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -359,7 +364,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp < 8) {
+    if (warp < kWgProducers) {
         // ================= producers: fp32 global -> 16-bit core matrices in shared memory =================
         // Software-pipelined through registers: the 16 x 16-byte loads of position p+1 are in flight while position p is
         // converted and stored, so HBM/L2 latency is covered without a third shared-memory stage.
@@ -367,30 +372,30 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
         // in bits 0-2, row % 4 in bits 3-4, so the 8 lanes of a quarter warp write 8 consecutive 16-byte slots (no bank conflicts; the
         // row-fastest mapping it replaces was an 8-way conflict on every store) while a warp still reads whole 128-byte lines.
         uint32_t stage = 0, phase = 0;
-        const int xchunks = cin >> 5;                 // (cin * 8 rows) / 256 threads = 4 (cin 128) or 2 (cin 64)
+        const int xchunks = cin / (4 * kWgProducers);   // (cin * 8 rows) / producer threads: 4 or 2 with 8 producer warps, 2 or 1 with 16
         const int lane = tid & 31, ch_low = lane & 7, row_low = lane >> 3;
-        int a_ch[4], a_row[4], x_ch[4], x_row[4];
+        int a_ch[kWgItems], a_row[kWgItems], x_ch[kWgItems], x_row[kWgItems];
 #pragma unroll
-        for (int it = 0; it < 4; it++) {
-            const int ca = (tid >> 5) * 4 + it;       // 0..31 -> (channel group 0..15, upper row half)
+        for (int it = 0; it < kWgItems; it++) {
+            const int ca = (tid >> 5) * kWgItems + it;   // 0..31 -> (channel group 0..15, upper row half)
             a_ch[it] = (ca >> 1) * 8 + ch_low;
             a_row[it] = (ca & 1) * 4 + row_low;
             const int cx = (tid >> 5) * xchunks + it; // 0..8*xchunks-1 -> (channel group 0..cin/8-1, upper row half)
             x_ch[it] = (cx >> 1) * 8 + ch_low;
             x_row[it] = (cx & 1) * 4 + row_low;
         }
-        float4 cur[16], nxt[16];
-        auto load = [&](float4 (&r)[16], long long p) {
+        float4 cur[4 * kWgItems], nxt[4 * kWgItems];
+        auto load = [&](float4 (&r)[4 * kWgItems], long long p) {
             const float *dsrc = dy + (size_t)p * 128 * 64;
             const float *xsrc = x + (size_t)p * cin * 64;
 #pragma unroll
-            for (int it = 0; it < 4; it++) {
+            for (int it = 0; it < kWgItems; it++) {
                 ldg256(dsrc + a_ch[it] * 64 + a_row[it] * 8, r[2 * it], r[2 * it + 1]);
             }
 #pragma unroll
-            for (int it = 0; it < 4; it++) {
+            for (int it = 0; it < kWgItems; it++) {
                 if (it < xchunks) {
-                    ldg256(xsrc + x_ch[it] * 64 + x_row[it] * 8, r[8 + 2 * it], r[8 + 2 * it + 1]);
+                    ldg256(xsrc + x_ch[it] * 64 + x_row[it] * 8, r[2 * kWgItems + 2 * it], r[2 * kWgItems + 2 * it + 1]);
                 }
             }
         };
@@ -401,7 +406,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
             uint8_t *st = smem + stage * kWgStage;
             // dY: 128 o x 8 rows of 8 cells
 #pragma unroll
-            for (int it = 0; it < 4; it++) {
+            for (int it = 0; it < kWgItems; it++) {
                 const int o = a_ch[it], row = a_row[it];
                 uint4 hi, lo;
                 pack_f16x8_split(cur[2 * it], cur[2 * it + 1], scale, hi, lo);
@@ -411,10 +416,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
             }
             // X: cin channels x 8 rows, three column-shifted copies
 #pragma unroll
-            for (int it = 0; it < 4; it++) {
+            for (int it = 0; it < kWgItems; it++) {
                 if (it < xchunks) {
                     const int c = x_ch[it], row = x_row[it];
-                    const uint4 v = pack_f16x8(cur[8 + 2 * it], cur[8 + 2 * it + 1]);
+                    const uint4 v = pack_f16x8(cur[2 * kWgItems + 2 * it], cur[2 * kWgItems + 2 * it + 1]);
                     const uint32_t off = kWgXBase + (((c >> 3) * 10 + row + 1) * 8 + (c & 7)) * 16;
                     // kx = 0: out[x] = in[x - 1]; kx = 1: in[x]; kx = 2: out[x] = in[x + 1]   (zero beyond the board edge)
                     const uint4 left = make_uint4(v.x << 16, __funnelshift_l(v.x, v.y, 16), __funnelshift_l(v.y, v.z, 16), __funnelshift_l(v.z, v.w, 16));
@@ -428,7 +433,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
             mbar_arrive(bar_full + 8 * stage);
             if (++stage == kWgStages) { stage = 0; phase ^= 1; }
 #pragma unroll
-            for (int i = 0; i < 16; i++) cur[i] = nxt[i];
+            for (int i = 0; i < 4 * kWgItems; i++) cur[i] = nxt[i];
         }
     } else if ((tid & 31) == 0) {
         // ================= MMA issuer =================
@@ -503,7 +508,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
+    if (warp == kWgProducers) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "n"(512) : "memory");
 }
 
 // grad[(o*cin + c)*9 + tap] (+)= sum over slices (in order) of partial[s][tap][o][c]

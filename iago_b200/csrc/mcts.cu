@@ -14,7 +14,7 @@
 //     same child).  Boards are not stored: a descent replays the moves on a bitboard pair in registers.
 //   * One wave = up to B playouts per tree:
 //       select (pass 1)  the B descents of a tree run in a fixed order, each seeing the virtual visits of the ones before it
-//                        (deterministic) — executed as a software pipeline over 8 warps per tree that preserves exactly that
+//                        (deterministic) — executed as a software pipeline over 12 warps per tree that preserves exactly that
 //                        order (mcts_select_pipe_kernel; mcts_select_kernel is the one-warp form, used for B < 8 and the
 //                        exact mode); lanes score the children in parallel (pipelined form: an fp32 screen, float64 only for
 //                        near-ties — the arg-max is the float64 one either way); a leaf that must be expanded and needs priors
@@ -312,7 +312,7 @@ __global__ void mcts_expand_kernel(MctsDev d) {
 // on: only descents parked on the same node meet in the tree (a pending node has no visible children, so no parked node lies
 // below another), those start at the same depth, and the wait chain is transitive.
 #ifndef IAGO_PIPE_WARPS
-#define IAGO_PIPE_WARPS 8
+#define IAGO_PIPE_WARPS 12   // 8 / 12 / 16 measured on the final kernel: 24.5 / 24.2 / 24.3 ms per 16,384-playout move of one tree
 #endif
 constexpr int kPipeWarps = IAGO_PIPE_WARPS;
 constexpr int kPipeMaxB = 1024;
@@ -682,7 +682,13 @@ __device__ __forceinline__ int slot_z(const MctsDev &d, const MctsParams &p, int
 }
 
 // exact mode: one thread per tree, slots in order, the reference's running mean (MCTS.py:61-72).
+// The last kernel of a wave leaves the two request counters at zero for the next wave (one memset node less per wave).
+__device__ __forceinline__ void reset_request_counts(const MctsDev &d) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) { d.counts[0] = 0; d.counts[1] = 0; }
+}
+
 __global__ void mcts_backup_exact_kernel(MctsDev d, MctsParams p) {
+    reset_request_counts(d);
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= d.T) return;
     MctsNode *nodes = d.nodes + (size_t)t * d.cap;
@@ -742,11 +748,15 @@ __device__ __forceinline__ void advance_done_one(const MctsDev &d, const MctsPar
     const long long left = p.target - d.done[t];
     d.done[t] += left < p.B ? (left > 0 ? left : 0) : p.B;
 }
-__global__ void mcts_advance_done_kernel(MctsDev d, MctsParams p) { advance_done_one(d, p, blockIdx.x * blockDim.x + threadIdx.x); }
+__global__ void mcts_advance_done_kernel(MctsDev d, MctsParams p) {
+    reset_request_counts(d);
+    advance_done_one(d, p, blockIdx.x * blockDim.x + threadIdx.x);
+}
 
 // The end of a wave as ONE launch when all slots fit one CTA (T * B <= 1,024: a single tree, a few root-parallel trees): every
 // playout backed up, then the playout counters advanced (a search of one tree is bound by dependent launches).
 __global__ void __launch_bounds__(1024) mcts_tail_kernel(MctsDev d, MctsParams p) {
+    reset_request_counts(d);
     backup_atomic_one(d, p, threadIdx.x);
     __syncthreads();
     advance_done_one(d, p, threadIdx.x);
@@ -989,8 +999,7 @@ int iago_mcts_search(iago_mcts *m, const iago_mcts_params *pp, void *stream) {
     // graph and replayed for the rest — a single-tree search is bound by dependent launches, not by work.  The legacy default stream
     // cannot be captured, so the search runs on the context's own stream, ordered behind the caller's stream by an event.
     auto wave = [&](cudaStream_t ws) -> int {
-        IAGO_CUDA(cudaMemsetAsync(d.counts, 0, 2 * sizeof(int), ws));
-        const bool pipe = !p.exact && p.B >= 8 && p.B <= kPipeMaxB;   // descents of a tree as a software pipeline over 8 warps
+        const bool pipe = !p.exact && p.B >= 8 && p.B <= kPipeMaxB;   // descents of a tree as a software pipeline over kPipeWarps warps
         if (pipe) mcts_select_pipe_kernel<<<m->T, kPipeWarps * 32, 0, ws>>>(d, p, 1, 0);
         else mcts_select_kernel<<<m->T, 32, 0, ws>>>(d, p, 1);
         IAGO_CUDA(cudaGetLastError());

@@ -1046,10 +1046,12 @@ int trunk_launch(iago_ctx *ctx, int slot, int want_kind, const uint64_t *p1, con
     if (n == 0) return IAGO_OK;
     DeviceGuard guard(ctx->device);
     if (int rc = set_trunk_attrs(st)) return rc;
-    // CTA pairs (4 boards per cluster) whenever the slot has the pair-layout blobs and no activations are dumped; IAGO_TRUNK_CG1=1 forces
-    // the single-CTA kernel (A/B measurements)
+    // CTA pairs (4 boards per cluster) whenever the slot has the pair-layout blobs — the trainer's forward with its activation dumps
+    // included (each CTA streams half of a weight unit from L2: 52.6 against 53.5 ms of gradient time per 2,048-game set);
+    // IAGO_TRUNK_CG1=1 forces the single-CTA kernel, IAGO_TRUNK_DUMP_CG1=1 only for launches that dump (A/B measurements)
     static const bool force_cg1 = getenv("IAGO_TRUNK_CG1") != nullptr;
-    const bool pairs = s.d_pair && !dump && !force_cg1;
+    static const bool dump_cg1 = getenv("IAGO_TRUNK_DUMP_CG1") != nullptr;   // A/B: the trainer's forward on single CTAs
+    const bool pairs = s.d_pair && !(dump && dump_cg1) && !force_cg1;
     const long long tiles = pairs ? (n + 3) / 4 : (n + 1) / 2;
     const long long max_groups = pairs ? ctx->sm_count / 2 : ctx->sm_count;
     const int grid = (int)(tiles < max_groups ? tiles : max_groups) * (pairs ? 2 : 1);

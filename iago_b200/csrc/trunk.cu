@@ -65,9 +65,9 @@ constexpr int kStageBytes = 32768;                // one weight unit: hi [8][128
 constexpr int kStages = 3;                        // one producer warp (9, 10, 11) per ring stage
 static_assert(kStages == 3, "the producer warps are numbered by ring stage");
 // 2-D tensor maps (256-byte rows) over a pair-layout weight blob, one per half-unit size: 64 rows (16 KB: the 128-channel layers),
-// 16 rows (4 KB: layer 1), 8 rows (2 KB: the value head's block9)
+// 16 rows (4 KB: layer 1), 8 rows (2 KB: the value head's block9), 32 rows (8 KB: the 64-column last layer of the backward chain)
 struct alignas(64) TrunkMaps {
-    CUtensorMap m[3];
+    CUtensorMap m[4];
 };
 constexpr int kMaxLayers = 9;
 constexpr int kEpiThreads = 512;                  // warps 0-15: four threads per tile row, 16 of a pass's 64 output channels each
@@ -208,11 +208,11 @@ __device__ __forceinline__ void arrive_leader(uint32_t bar) {
 // complete on the leader's "full" barrier.  The same 96 KB ring is then SIX units deep instead of three and each SM ingests half the
 // weight bytes — the L2 -> shared-memory latency of a unit (≈ 1,000 cycles end to end) is what paced precision 2 with a 3-deep ring.
 // The leader's warp 8 issues for the pair; commits are multicast to both CTAs; the epilogue threads of both CTAs arrive on the leader's
-// "activations written" barriers (tools/micro/umma2_check.cu is the known-answer test of these mechanisms).  Forward only.
+// "activations written" barriers (tools/micro/umma2_check.cu is the known-answer test of these mechanisms).
 template <int MODE, int CG>
 __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constant__ TrunkArgs a, const __grid_constant__ NetDesc net,
                                                             const __grid_constant__ TrunkMaps maps) {
-    static_assert(CG == 1 || (CG == 2 && MODE == 0), "the CTA-pair path is the forward kernel only");
+    static_assert(CG == 1 || CG == 2, "one CTA or a CTA pair per tile");
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x;
     const uint32_t rank = CG == 2 ? cluster_ctarank() : 0u;          // 0 = leader
@@ -295,7 +295,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                 const int nu = net.layer[l].n_units;
                 // pair: row (256 B) of this CTA's half of the layer's first unit, and the tensor map whose box is one half-unit
                 int row = (int)((net.unit_base[l] + (long long)rank * (unit_bytes / 2)) >> 8);
-                const void *map = &maps.m[net.layer[l].chunks == 0 ? 1 : net.layer[l].n == 16 ? 2 : 0];
+                const void *map = &maps.m[net.layer[l].chunks == 0 ? 1 : net.layer[l].n == 16 ? 2 : net.layer[l].n == 64 ? 3 : 0];
                 for (int u = 0; u < nu; u++) {
                     if (turn == my_turn) {
                         mbar_wait(bar_empty + 8 * stage, phase ^ 1);
@@ -766,6 +766,8 @@ struct NetSlot {
 struct TrunkState {
     NetSlot slot[IAGO_NET_SLOTS];
     bool attr_set = false;
+    const uint8_t *bwd_pair = nullptr;   // the pair-layout backward blob bwd_maps was built for
+    TrunkMaps bwd_maps;
     float *d_sw = nullptr;   // [kMaxLayers] scratch of trunk_refresh_slot: the FP8 weight scale per layer
 };
 
@@ -871,8 +873,8 @@ static int make_maps(uint8_t *d_blob, size_t bytes, TrunkMaps &out) {
             return IAGO_E_CUDA;
         }
     }
-    const cuuint32_t rows[3] = {64, 16, 8};
-    for (int i = 0; i < 3; i++) {
+    const cuuint32_t rows[4] = {64, 16, 8, 32};
+    for (int i = 0; i < 4; i++) {
         const cuuint64_t gdim[2] = {256, (cuuint64_t)(bytes / 256)}, gstride[1] = {256};
         const cuuint32_t box[2] = {256, rows[i]}, estr[2] = {1, 1};
         const CUresult r = encode(&out.m[i], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, d_blob, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1027,6 +1029,7 @@ static int set_trunk_attrs(TrunkState *st) {
     IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<0, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    IAGO_CUDA(cudaFuncSetAttribute(trunk_kernel<1, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     st->attr_set = true;
     return IAGO_OK;
 }
@@ -1239,14 +1242,15 @@ int trunk_refresh_slot(iago_ctx *ctx, int slot, int kind, const float *d_params,
 // ---------------------------------------------------------------- backward data-gradient chain (reinforce.cu)
 // Chain layer i = dgrad of block 8-i (i = 0..6): dX[c] = sum_{o,tap} dY[o] (shifted by tap) * W[o][c][8-tap], K = 128 output
 // channels of the block in two 64-channel chunks, N = its input channels (128, or 64 for block 2).
-size_t trunk_backward_blob_bytes() {
+static size_t backward_layout_bytes() {
     size_t b = 0;
     for (int i = 0; i < 7; i++) b += (size_t)18 * 2 * 8 * (i == 6 ? 64 : 128) * 16;
     return b;
 }
+size_t trunk_backward_blob_bytes() { return 2 * backward_layout_bytes(); }   // the single-CTA layout, then the pair layout
 
 // blob unit (chunk ch, tap): hi [8 k-groups][N][8] bf16 then lo; element (kg, n, e) = W_l[o = ch*64 + kg*8 + e][c = n][8 - tap].
-__global__ void pack_dgrad_kernel(const float *__restrict__ W, uint8_t *__restrict__ units, int cin) {
+__global__ void pack_dgrad_kernel(const float *__restrict__ W, uint8_t *__restrict__ units, uint8_t *__restrict__ pair_units, int cin) {
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;   // over [ch 2][tap 9][kg 8][n cin][e 8]
     const int total = 2 * 9 * 8 * cin * 8;
     if (idx >= total) return;
@@ -1261,6 +1265,12 @@ __global__ void pack_dgrad_kernel(const float *__restrict__ W, uint8_t *__restri
     const size_t off = ((size_t)kg * cin + n) * 8 + e;
     unit[off] = h;
     unit[half_elems + off] = l;
+    // pair layout (as pack_all_kernel's): [rank 0's half of the N columns | rank 1's half], each a complete unit of cin / 2 columns
+    const int nh = cin / 2, hh = n / nh, nn = n % nh;
+    __nv_bfloat16 *pu = reinterpret_cast<__nv_bfloat16 *>(pair_units) + (size_t)ut * 2 * half_elems + (size_t)hh * half_elems;
+    const size_t poff = ((size_t)kg * nh + nn) * 8 + e;
+    pu[poff] = h;
+    pu[half_elems / 2 + poff] = l;
 }
 
 // The chain's layer table (a function of the architecture alone; passed to the kernel by value).
@@ -1287,7 +1297,7 @@ int trunk_backward_pack(iago_ctx *ctx, const float *const *W /* W[l], l = 1..7: 
     for (int i = 0; i < 7; i++) {
         const int l = 7 - i, cin = l == 1 ? 64 : 128;
         const int total = 2 * 9 * 8 * cin * 8;
-        pack_dgrad_kernel<<<(total + 255) / 256, 256, 0, cs>>>(W[l], blob + d.unit_base[i], cin);
+        pack_dgrad_kernel<<<(total + 255) / 256, 256, 0, cs>>>(W[l], blob + d.unit_base[i], blob + backward_layout_bytes() + d.unit_base[i], cin);
     }
     IAGO_CUDA(cudaGetLastError());
     (void)ctx;
@@ -1301,8 +1311,13 @@ int trunk_backward_launch(iago_ctx *ctx, const uint8_t *blob, const float *dy_in
     if (n <= 0) return IAGO_OK;
     TrunkState *st = state(ctx);
     if (int rc = set_trunk_attrs(st)) return rc;
-    const long long tiles = (n + 1) / 2;
-    const int grid = (int)(tiles < ctx->sm_count ? tiles : ctx->sm_count);
+    // CTA pairs like the forward kernel (each CTA streams half of a weight unit from L2: a single-CTA chain, 148 SMs x 32 KB per unit,
+    // sits on the chip's L2 bandwidth together with its mask reads and gradient writes); IAGO_TRUNK_CG1=1 forces single CTAs
+    static const bool force_cg1 = getenv("IAGO_TRUNK_CG1") != nullptr || getenv("IAGO_TRUNK_BWD_CG1") != nullptr;
+    const bool pairs = !force_cg1;
+    const long long tiles = pairs ? (n + 3) / 4 : (n + 1) / 2;
+    const long long max_groups = pairs ? ctx->sm_count / 2 : ctx->sm_count;
+    const int grid = (int)(tiles < max_groups ? tiles : max_groups) * (pairs ? 2 : 1);
     TrunkArgs a{nullptr, nullptr, nullptr, n, nullptr, 0, precision, blob, nullptr, nullptr, nullptr, nullptr, {}, dy_in, {}};
     for (int i = 0; i < 7; i++) {
         a.dump[i] = dx_out[i];
@@ -1310,7 +1325,27 @@ int trunk_backward_launch(iago_ctx *ctx, const uint8_t *blob, const float *dy_in
     }
     a.dump[7] = nullptr;
     a.mask[7] = nullptr;
-    trunk_kernel<1, 1><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, backward_desc(), TrunkMaps{});
+    if (pairs) {
+        const uint8_t *pair_blob = blob + backward_layout_bytes();
+        if (st->bwd_pair != pair_blob) {
+            if (int rc = make_maps(const_cast<uint8_t *>(pair_blob), backward_layout_bytes(), st->bwd_maps)) return rc;
+            st->bwd_pair = pair_blob;
+        }
+        a.blob = pair_blob;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = kSmemBytes;
+        cfg.stream = (cudaStream_t)stream;
+        cudaLaunchAttribute at;
+        at.id = cudaLaunchAttributeClusterDimension;
+        at.val.clusterDim.x = 2; at.val.clusterDim.y = 1; at.val.clusterDim.z = 1;
+        cfg.attrs = &at;
+        cfg.numAttrs = 1;
+        IAGO_CUDA(cudaLaunchKernelEx(&cfg, trunk_kernel<1, 2>, a, backward_desc(), st->bwd_maps));
+    } else {
+        trunk_kernel<1, 1><<<grid, kThreads, kSmemBytes, (cudaStream_t)stream>>>(a, backward_desc(), TrunkMaps{});
+    }
     IAGO_CUDA(cudaGetLastError());
     return IAGO_OK;
 }

@@ -22,3 +22,24 @@ def test_reference_arm_line():
     assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == line["value"] and "sample" in cb
     e2e = line["e2e"]
     assert e2e["value"] == line["value"] and e2e["h2d_bytes_per_step"] == 0 and e2e["d2h_bytes_per_step"] == 0
+
+
+def test_measured_capture_file_feeds_the_roofline_block():
+    """roofline.traffic and the 'as issued' ALU counts are read from the committed ncu capture (profiles/ncu_traffic.json, written by
+    profiles/ncu_traffic.py), not typed into bench.py: the file carries both launches, their source reports and plausible counts."""
+    sys.path.insert(0, ROOT)
+    import bench
+    t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+    for key in ("rollout_pair_kernel", "rollout_pair_kernel_forced"):
+        e = t[key]
+        assert e["games_per_launch"] == bench.GAMES_PER_STEP and ".ncu-rep" in e["source"]
+        assert e["alu_pipe_warp_inst_per_launch"] > 0 and e["warp_inst_per_launch"] >= e["alu_pipe_warp_inst_per_launch"]
+        assert 0 < e["alu_pipe_pct"] <= 100 and e["kernel_us"] > 0 and e["captured"] and e["command"].startswith("python bench.py")
+    full = t["rollout_pair_kernel"]
+    assert full["dram_bytes_per_launch"] == full["dram_bytes_read"] + full["dram_bytes_write"]
+    assert bench.ncu_traffic()["dram_bytes_per_launch"] == full["dram_bytes_per_launch"]
+    plies = 59.84 * bench.GAMES_PER_STEP            # one launch of the bench workload (59.8 stones per game)
+    ops = bench.alu_lane_ops_per_ply("rollout_pair_kernel", plies)
+    ops_rules = bench.alu_lane_ops_per_ply("rollout_pair_kernel_forced", plies)
+    assert 200 < ops_rules < ops < 1000              # rules alone issue fewer ALU operations than rules + policy + sampling
+    assert bench.alu_lane_ops_per_ply("no_such_kernel", plies) is None

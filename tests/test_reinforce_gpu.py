@@ -181,6 +181,31 @@ def test_train_set_runs_and_checkpoints(engine, tmp_path):
     assert again.params["conv9/W"].shape == (1, 128, 1, 1)
 
 
+def test_gradient_is_bit_identical_from_run_to_run(engine):
+    """Every reduction of the gradient runs in a fixed order (TMEM accumulation over a slice's positions, in-order sums over slices,
+    taps and head slices), so repeating a gradient call must give the same bits — a missed hand-over between the producer warps, the
+    MMA issuer and the CTA pairs of the backward chain would show up here (tools/stress_wgrad.py is the long form)."""
+    import torch
+    from iago_b200 import network
+    from iago_b200.train_rl import ReinforceTrainer
+    opp = network.SLPolicy().load(model_file("RL/model0.npz"))
+    tr = ReinforceTrainer(model_file("RL/model2.npz"), max_positions=4096)
+    d = tr.play_set(opp, 160, seed=11)
+    total = d["own"].numel()
+    assert total > 3000
+    for n in (total, 2049, 333, 5):   # several chunkings: more positions than max_positions, ragged slices, fewer positions than slices
+        ref = None
+        for rep in range(4):
+            tr.gradient(d["own"][:n], d["opp"][:n], d["action"][:n], d["reward"][:n])
+            torch.cuda.synchronize()
+            g = tr.grad.clone()
+            if ref is None:
+                ref = g
+                assert torch.isfinite(g).all() and float(g.abs().max()) > 0
+            else:
+                assert torch.equal(g, ref), (n, rep, float((g - ref).abs().max()))
+
+
 def test_checkpoint_loads_into_the_unmodified_reference_network(engine, tmp_path):
     """src/train_rl.py:73-79 writes snapshots with serializers.save_npz and reads them back with load_npz(path, model): a snapshot of
     this trainer (plain and 'predictor/'-prefixed, as models/rl_model.npz is) is loaded by the chainer stand-in's serializers.load_npz

@@ -101,5 +101,6 @@ int trunk_refresh_slot(iago_ctx *ctx, int slot, int kind, const float *d_params,
 size_t trunk_backward_blob_bytes();
 int trunk_backward_pack(iago_ctx *ctx, const float *const *W, uint8_t *blob, void *stream);
 int trunk_backward_launch(iago_ctx *ctx, const uint8_t *blob, const float *dy_in, const float *const *mask,
-                          float *const *dx_out, int64_t n, int precision, void *stream);
+                          float *const *dx_out, int64_t n, int precision, void *stream,
+                          unsigned *const *dymax = nullptr);   // dymax[i] (nullable): atomicMax of the bit pattern of |dx_out[i]|
 }  // namespace iago

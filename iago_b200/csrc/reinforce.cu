@@ -325,7 +325,7 @@ __device__ __forceinline__ uint4 pack_f16x8(const float4 a, const float4 b) {
 __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__restrict__ x, const float *__restrict__ dy,
                                                                   float *__restrict__ partial, long long m, int cin,
                                                                   int pos_per_slice, size_t partial_stride,
-                                                                  const unsigned *__restrict__ dymax) {
+                                                                  const unsigned *__restrict__ dymax, float *__restrict__ bias_partial) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
     const int ky = blockIdx.y;                       // kernel row of this CTA: taps ky*3 + {0,1,2}
@@ -399,6 +399,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
                 }
             }
         };
+        // Bias gradient = sum of dY over positions and cells, taken by the ky = 0 CTA of each slice from the registers it converts anyway
+        // (a separate kernel used to read every dY tensor once more for it: 0.39 ms per 8,192 positions).  Both items of a thread are the
+        // two row halves of ONE channel; the four row_low lanes are folded by shuffles after the loop.  Fixed order throughout.
+        static_assert(kWgItems == 2, "the bias sums assume one channel per producer thread");
+        float bsum = 0.0f;
         if (n_pos > 0) load(cur, p_begin);
         for (int ip = 0; ip < n_pos; ip++) {
             if (ip + 1 < n_pos) load(nxt, p_begin + ip + 1);
@@ -410,6 +415,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
                 const int o = a_ch[it], row = a_row[it];
                 uint4 hi, lo;
                 pack_f16x8_split(cur[2 * it], cur[2 * it + 1], scale, hi, lo);
+                if (ky == 0) {
+                    const float4 u = cur[2 * it], v = cur[2 * it + 1];
+                    bsum += ((u.x + u.y) + (u.z + u.w)) + ((v.x + v.y) + (v.z + v.w));
+                }
                 const uint32_t off = (((o >> 3) * 8 + row) * 8 + (o & 7)) * 16;
                 *reinterpret_cast<uint4 *>(st + off) = hi;
                 *reinterpret_cast<uint4 *>(st + kWgATile + off) = lo;
@@ -434,6 +443,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
             if (++stage == kWgStages) { stage = 0; phase ^= 1; }
 #pragma unroll
             for (int i = 0; i < 4 * kWgItems; i++) cur[i] = nxt[i];
+        }
+        if (ky == 0) {
+            bsum += __shfl_xor_sync(0xFFFFFFFFu, bsum, 8);
+            bsum += __shfl_xor_sync(0xFFFFFFFFu, bsum, 16);
+            if (lane < 8) bias_partial[(size_t)blockIdx.x * 128 + warp * 8 + lane] = bsum;
         }
     } else if ((tid & 31) == 0) {
         // ================= MMA issuer =================
@@ -522,40 +536,6 @@ __global__ void reduce_taps_kernel(const float *__restrict__ partial, float *__r
     *dst = accumulate ? *dst + s : s;
 }
 
-// db[o] = sum_{p, cell} dY[p][o][cell]: block (o, slice) sums its slice of positions with a fixed-order tree into
-// partial[slice][o]; reduce_slices_kernel then adds the slices in order.
-constexpr int kBiasSlices = 16;
-// It also records max |dY| of the layer (order-free atomic max on the bit pattern of a non-negative float): the tensor-core
-// weight-gradient kernel scales dY by a power of two into fp16's range with it.
-__global__ void __launch_bounds__(256) bias_grad_kernel(const float *__restrict__ dy, float *__restrict__ partial, long long m, int cout,
-                                                        unsigned *__restrict__ dymax) {
-    __shared__ float red[256];
-    __shared__ float redm[256];
-    const int o = blockIdx.x, tid = threadIdx.x;
-    const long long per = (m + gridDim.y - 1) / gridDim.y;
-    const long long p0 = (long long)blockIdx.y * per, p1 = min(m, p0 + per);
-    float s = 0.0f, mx = 0.0f;
-    for (long long i = p0 * 64 + tid; i < p1 * 64; i += 256) {
-        const float v = dy[((i >> 6) * cout + o) * 64 + (i & 63)];
-        s += v;
-        mx = fmaxf(mx, fabsf(v));
-    }
-    red[tid] = s;
-    redm[tid] = mx;
-    __syncthreads();
-    for (int k = 128; k > 0; k >>= 1) {
-        if (tid < k) {
-            red[tid] += red[tid + k];
-            redm[tid] = fmaxf(redm[tid], redm[tid + k]);
-        }
-        __syncthreads();
-    }
-    if (tid == 0) {
-        partial[(size_t)blockIdx.y * cout + o] = red[0];
-        if (redm[0] < 3.0e38f) atomicMax(dymax, __float_as_uint(redm[0]));   // NaN / inf stay out: the scale then defaults to 1
-    }
-}
-
 // out[i] (+)= sum over slices of partial[s][i], slices in order.
 __global__ void reduce_slices_kernel(const float *__restrict__ partial, float *__restrict__ out, int count, int slices,
                                      size_t stride, int accumulate) {
@@ -587,10 +567,17 @@ __device__ __forceinline__ float block64_sum(float v, float *red) {
     return r;
 }
 
+// max |dY| of a layer as a bit pattern, collected where dY is written (the weight-gradient kernel scales its fp16 operands by it):
+// one atomicMax per warp; NaN / inf stay out, the scale then defaults to 1
+__device__ __forceinline__ void publish_absmax(float mx, unsigned *dymax) {
+    const unsigned w = __reduce_max_sync(0xFFFFFFFFu, mx < 3.0e38f ? __float_as_uint(mx) : 0u);
+    if ((threadIdx.x & 31) == 0 && w != 0u) atomicMax(dymax, w);
+}
+
 __global__ void __launch_bounds__(64) head_kernel(const float *__restrict__ act8, const float *__restrict__ w9, const float *__restrict__ b10,
                                                   const int8_t *__restrict__ action, const float *__restrict__ reward,
                                                   float *__restrict__ dlogit, float *__restrict__ dact8, float *__restrict__ loss_terms,
-                                                  float *__restrict__ probs_out, long long m) {
+                                                  float *__restrict__ probs_out, long long m, unsigned *__restrict__ dymax) {
     __shared__ float red[2];
     const long long p = blockIdx.x;
     const int cell = threadIdx.x;
@@ -617,7 +604,13 @@ __global__ void __launch_bounds__(64) head_kernel(const float *__restrict__ act8
     const float dl = pred * (dpred - dot);
     dlogit[p * 64 + cell] = dl;
     float *da = dact8 + (size_t)p * 128 * 64;
-    for (int c = 0; c < 128; c++) da[c * 64 + cell] = a[c * 64 + cell] > 0.0f ? w9[c] * dl : 0.0f;
+    float amax = 0.0f;
+    for (int c = 0; c < 128; c++) {
+        const float g = a[c * 64 + cell] > 0.0f ? w9[c] * dl : 0.0f;
+        da[c * 64 + cell] = g;
+        amax = fmaxf(amax, fabsf(g));
+    }
+    publish_absmax(amax, dymax);
 }
 
 // dw9[c] = sum_{p,cell} dlogit[p][cell] * act8[p][c][cell]  (block c < 128); db10[cell] = sum_p dlogit[p][cell] (block 128 + cell);
@@ -668,6 +661,7 @@ struct ValueHeadArgs {
     const float *act8, *w9, *b9, *fc10, *fc11, *target;
     float *pred, *loss_terms, *h9, *du, *z, *dpre9, *dv, *dact8;
     uint8_t *mask_out;   // nullable [m][128]: 1 = kept
+    unsigned *dymax;     // bit pattern of max |dact8| (atomicMax)
     long long m;
     float ratio;
     u64 seed, pos_id0;
@@ -743,6 +737,7 @@ __global__ void __launch_bounds__(128) value_head_kernel(ValueHeadArgs a) {
     }
     __syncthreads();
     float *dst = a.dact8 + (size_t)p * 128 * 64;
+    float amax = 0.0f;
     for (int i = tid; i < 128 * 64; i += 128) {
         const int c = i >> 6, cell = i & 63, y = cell >> 3, x = cell & 7;
         float g = 0.0f;
@@ -752,8 +747,11 @@ __global__ void __launch_bounds__(128) value_head_kernel(ValueHeadArgs a) {
             const int yy = y - (t / 3 - 1), xx = x - (t % 3 - 1);
             if (yy >= 0 && yy < 8 && xx >= 0 && xx < 8) g = fmaf(w9s[c * 9 + t], dps[yy * 8 + xx], g);
         }
-        dst[i] = a8[c][cell] > 0.0f ? g : 0.0f;
+        g = a8[c][cell] > 0.0f ? g : 0.0f;
+        dst[i] = g;
+        amax = fmaxf(amax, fabsf(g));
     }
+    publish_absmax(amax, a.dymax);
 }
 
 // Weight gradients of the value head, every sum in a fixed order.  Blocks [0,128): dW9[c][9 taps]; block 128: db9 and the loss
@@ -981,7 +979,7 @@ struct iago_trainer {
     uint8_t *bwd_blob = nullptr;      // bf16 hi/lo weight units of the data-gradient chain (trunk.cu, backward mode)
     int bwd_precision = 3;
     float *dlogit = nullptr, *loss_terms = nullptr, *partial = nullptr, *bias_partial = nullptr;
-    unsigned *dymax = nullptr;        // [8] bit pattern of max |dY| per layer (bias_grad_kernel)
+    unsigned *dymax = nullptr;        // [8] bit pattern of max |dY| per layer, collected by the kernels that write dyb[l]
     size_t partial_stride = 0;
     int slices = 0;
     int tc_slices = 0, slices0 = 0;
@@ -1055,7 +1053,6 @@ int iago_trainer_create(iago_ctx *ctx, int kind, const float *params, int64_t n_
     if (kind == 1) {
         A(t->h9, M * 64); A(t->du, M * 128); A(t->zbuf, M * 128); A(t->dpre9, M * 64); A(t->dv, M); A(t->vpred, M);
     }
-    A(t->bias_partial, (size_t)kBiasSlices * 128);
     A(t->dymax, 8);
     t->slices = 24;                                  // fp32 weight-gradient kernel: position slices of the 64/128-input-channel layers
     t->slices0 = 2 * ctx->sm_count;                  // ... and of block 1 (2 input channels: one c tile, so the slices are the whole grid)
@@ -1064,6 +1061,7 @@ int iago_trainer_create(iago_ctx *ctx, int kind, const float *params, int64_t n_
                                                                  // every launch as two waves — twice the time of 147 CTAs
     t->partial_stride = (size_t)128 * 128 * 9 + 128;
     A(t->partial, (size_t)(t->tc_slices > t->slices ? t->tc_slices : t->slices) * t->partial_stride);
+    A(t->bias_partial, (size_t)t->tc_slices * 128);
 #undef A
     if (rc) {
         for (void *p : t->allocs) cudaFree(p);
@@ -1128,7 +1126,9 @@ static int backward_trunk(iago_trainer *t, int64_t m, float *grad, int accumulat
         }
         int rc = trunk_backward_pack(t->ctx, W, t->bwd_blob, stream);
         if (rc) return rc;
-        rc = trunk_backward_launch(t->ctx, t->bwd_blob, t->dyb[7], mask, dx, m, t->bwd_precision, stream);
+        unsigned *dymax[7];
+        for (int i = 0; i < 7; i++) dymax[i] = kCout[6 - i] == 128 ? t->dymax + (6 - i) : nullptr;   // dx[i] = dY of block 7 - i (index 6 - i)
+        rc = trunk_backward_launch(t->ctx, t->bwd_blob, t->dyb[7], mask, dx, m, t->bwd_precision, stream, dymax);
         if (rc) return rc;
     }
     for (int l = 7; l >= 0; l--) {
@@ -1143,10 +1143,10 @@ static int backward_trunk(iago_trainer *t, int64_t m, float *grad, int accumulat
             }
             const int pps = (int)((m + t->tc_slices - 1) / t->tc_slices);
             const int sl = (int)((m + pps - 1) / pps);
-            IAGO_CUDA(cudaMemsetAsync(t->dymax + l, 0, 4, s));
-            bias_grad_kernel<<<dim3(kCout[l], kBiasSlices), 256, 0, s>>>(dy, t->bias_partial, m, kCout[l], t->dymax + l);
-            reduce_slices_kernel<<<1, 256, 0, s>>>(t->bias_partial, grad + t->b_off[l], kCout[l], kBiasSlices, (size_t)kCout[l], accumulate);
-            wgrad_tc_kernel<<<dim3(sl, 3), kWgThreads, kWgSmem, s>>>(t->act[l], dy, t->partial, m, kCin[l], pps, t->partial_stride, t->dymax + l);
+            // dymax[l] was collected by the kernel that wrote dyb[l] (the head for l = 7, the fused backward chain below it)
+            wgrad_tc_kernel<<<dim3(sl, 3), kWgThreads, kWgSmem, s>>>(t->act[l], dy, t->partial, m, kCin[l], pps, t->partial_stride, t->dymax + l,
+                                                                     t->bias_partial);
+            reduce_slices_kernel<<<1, 256, 0, s>>>(t->bias_partial, grad + t->b_off[l], kCout[l], sl, (size_t)kCout[l], accumulate);
             reduce_taps_kernel<<<(9 * 128 * kCin[l] + 255) / 256, 256, 0, s>>>(t->partial, grad + t->w_off[l], kCin[l], sl, t->partial_stride, accumulate);
         } else {
             const int count = kCout[l] * kCin[l] * 9 + kCout[l];  // W then b are adjacent in the flat layout as well
@@ -1180,8 +1180,9 @@ int iago_reinforce_grad(iago_trainer *t, const uint64_t *own, const uint64_t *op
     int rc = forward_acts(t, own, opp, m, stream);
     if (rc) return rc;
     // ---- head forward + backward
+    IAGO_CUDA(cudaMemsetAsync(t->dymax, 0, 8 * sizeof(unsigned), s));
     head_kernel<<<(unsigned)m, 64, 0, s>>>(t->act[8], t->params + t->w9_off, t->params + t->b10_off, action, reward, t->dlogit,
-                                          t->dyb[7], t->loss_terms, probs_out, m);
+                                          t->dyb[7], t->loss_terms, probs_out, m, t->dymax + 7);
     head_grad_kernel<<<dim3(193, kHeadSlices), 256, 0, s>>>(t->act[8], t->dlogit, t->loss_terms, t->partial, m);
     head_grad_reduce_kernel<<<1, 256, 0, s>>>(t->partial, grad + t->w9_off, grad + t->b10_off, grad + kNP, accumulate);
     IAGO_CUDA(cudaGetLastError());
@@ -1207,8 +1208,9 @@ int iago_value_grad(iago_trainer *t, const uint64_t *own, const uint64_t *opp, c
     if (rc) return rc;
     const float *P = t->params;
     ValueHeadArgs a{t->act[8], P + t->vw9_off, P + t->vb9_off, P + t->fc10_off, P + t->fc11_off, target,
-                    t->vpred, t->loss_terms, t->h9, t->du, t->zbuf, t->dpre9, t->dv, t->dyb[7], mask_out, m,
+                    t->vpred, t->loss_terms, t->h9, t->du, t->zbuf, t->dpre9, t->dv, t->dyb[7], mask_out, t->dymax + 7, m,
                     (float)dropout_ratio, dropout_seed, position_id0};
+    IAGO_CUDA(cudaMemsetAsync(t->dymax, 0, 8 * sizeof(unsigned), s));
     value_head_kernel<<<(unsigned)m, 128, 0, s>>>(a);
     value_head_grad_kernel<<<162, 256, 0, s>>>(t->act[8], t->h9, t->du, t->zbuf, t->dpre9, t->dv, t->loss_terms, grad + t->vw9_off,
                                                grad + t->vb9_off, grad + t->fc10_off, grad + t->fc11_off, grad + t->np, m, accumulate);

@@ -122,6 +122,8 @@ struct TrunkArgs {
     // backward mode only (trunk_kernel<1>, the data-gradient chain of reinforce.cu):
     const float *dy_in;   // [n][128][64] gradient w.r.t. the output of block 8, entering the chain
     const float *mask[8]; // mask[i]: [n][N_i][64] forward activation whose sign gates the output of chain layer i (ReLU backward)
+    unsigned *dymax[8];   // backward mode, nullable each: bit pattern of max |value written to dump[i]| (atomicMax; the weight-gradient
+                          // kernel scales its fp16 operands by it — reinforce.cu used to read every gradient tensor again for this)
 };
 
 // hi/lo split (fp16 in the forward, bf16 in the backward chain: gradients need the exponent range) of 16 values of this
@@ -619,6 +621,13 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                         if (valid) {
 #pragma unroll
                             for (int j = 0; j < 16; j++) dst[(size_t)(col0 + j) * 64] = x[j];
+                        }
+                        if (a.dymax[l] != nullptr) {   // (x = 0 for rows beyond the batch)
+                            float mx = 0.0f;
+#pragma unroll
+                            for (int j = 0; j < 16; j++) mx = fmaxf(mx, fabsf(x[j]));
+                            const unsigned wmx = __reduce_max_sync(0xFFFFFFFFu, mx < 3.0e38f ? __float_as_uint(mx) : 0u);   // NaN / inf stay out
+                            if ((tid & 31) == 0 && wmx != 0u) atomicMax(a.dymax[l], wmx);
                         }
                         if (writes_act) {
                             store_act16<true>(smem, x, (uint32_t)(col0 >> 3) * kGroupBytes + row_off, split);
@@ -1305,7 +1314,7 @@ int trunk_backward_pack(iago_ctx *ctx, const float *const *W /* W[l], l = 1..7: 
 }
 
 int trunk_backward_launch(iago_ctx *ctx, const uint8_t *blob, const float *dy_in, const float *const *mask,
-                          float *const *dx_out, int64_t n, int precision, void *stream) {
+                          float *const *dx_out, int64_t n, int precision, void *stream, unsigned *const *dymax) {
     IAGO_REQUIRE(ctx && blob && dy_in && mask && dx_out, "NULL argument");
     IAGO_REQUIRE(precision == 1 || precision == 3, "precision must be 1 (bf16) or 3 (bf16 hi/lo split)");
     if (n <= 0) return IAGO_OK;
@@ -1322,9 +1331,11 @@ int trunk_backward_launch(iago_ctx *ctx, const uint8_t *blob, const float *dy_in
     for (int i = 0; i < 7; i++) {
         a.dump[i] = dx_out[i];
         a.mask[i] = mask[i];
+        a.dymax[i] = dymax ? dymax[i] : nullptr;
     }
     a.dump[7] = nullptr;
     a.mask[7] = nullptr;
+    a.dymax[7] = nullptr;
     if (pairs) {
         const uint8_t *pair_blob = blob + backward_layout_bytes();
         if (st->bwd_pair != pair_blob) {

@@ -284,15 +284,22 @@ __global__ void __launch_bounds__(256) wgrad_block1_kernel(const float *__restri
 constexpr int kWgProducers = IAGO_WG_PRODUCERS;          // producer warps (8 or 16; warps 0-3 also run the epilogue), then one MMA issuer warp
 constexpr int kWgItems = 32 / kWgProducers;               // (channel group, row half) items of the dY tile per producer thread and position
 constexpr int kWgThreads = kWgProducers * 32 + 32;
-constexpr int kWgATile = 16 * 8 * 128;        // dY tile: 16 o-groups x 8 rows x 128 B = 16,384
-constexpr int kWgXCopy = 16 * 10 * 128;       // one shifted copy of the X tile: 20,480
-constexpr int kWgXBase = 2 * kWgATile;        // dY hi tile, dY lo tile, then the three X copies
-constexpr int kWgStage = kWgXBase + 3 * kWgXCopy;   // 94,208
+// Core matrices (8 channels x 16 B) sit 144 B apart along K (board rows), not 128: a quarter warp that stores the 8 rows of ONE channel
+// then hits 8 different 16-byte bank groups, so the producers can read global memory row-fastest — a warp's LDG.256 covers 1 KB of
+// consecutive addresses.  (With 128 B the conflict-free store mapping was channel-fastest, whose loads touch 8 lines in 32 separate
+// sectors: ncu counted 39 L1 wavefronts per load instruction and the LSU data pipe at 87 % of peak, the kernel's limiter.)
+constexpr int kWgLbo = 144;                       // bytes between K-adjacent core matrices (descriptor LBO)
+constexpr int kWgSboA = 8 * kWgLbo;               // dY: bytes between o groups (8 board rows each)
+constexpr int kWgSboB = 10 * kWgLbo;              // X: bytes between c groups (10 padded rows each)
+constexpr int kWgATile = 16 * kWgSboA;            // dY tile: 16 o-groups = 18,432
+constexpr int kWgXCopy = 16 * kWgSboB;            // one shifted copy of the X tile: 23,040
+constexpr int kWgXBase = 2 * kWgATile;            // dY hi tile, dY lo tile, then the three X copies
+constexpr int kWgStage = kWgXBase + 3 * kWgXCopy;   // 105,984
 constexpr int kWgStages = 2;
 constexpr int kWgSmem = kWgStages * kWgStage + 64;
 
 // One 32-byte sector per lane in ONE request (LDG.256, sm_100): with two 16-byte loads every sector was requested twice and the
-// second half had to survive in an L1 that the kernel's 188 KB of shared memory leaves almost no room for.
+// second half had to survive in an L1 that the kernel's 207 KB of shared memory leaves almost no room for.
 __device__ __forceinline__ void ldg256(const float *p, float4 &a, float4 &b) {
     asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
@@ -368,21 +375,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
         // ================= producers: fp32 global -> 16-bit core matrices in shared memory =================
         // Software-pipelined through registers: the 16 x 16-byte loads of position p+1 are in flight while position p is
         // converted and stored, so HBM/L2 latency is covered without a third shared-memory stage.
-        // Work item = one (channel, board row) chunk of 8 cells = 32 B of fp32 in, one 16-byte core-matrix row out.  Lane bits: channel % 8
-        // in bits 0-2, row % 4 in bits 3-4, so the 8 lanes of a quarter warp write 8 consecutive 16-byte slots (no bank conflicts; the
-        // row-fastest mapping it replaces was an 8-way conflict on every store) while a warp still reads whole 128-byte lines.
+        // Work item = one (channel, board row) chunk of 8 cells = 32 B of fp32 in, one 16-byte core-matrix row out.  Lane bits: board row in
+        // bits 0-2, channel % 4 in bits 3-4: a warp reads 1 KB of consecutive bytes per LDG.256, and the 8 lanes of a quarter warp store
+        // the 8 rows of one channel, kWgLbo = 144 B apart (8 different bank groups).
         uint32_t stage = 0, phase = 0;
         const int xchunks = cin / (4 * kWgProducers);   // (cin * 8 rows) / producer threads: 4 or 2 with 8 producer warps, 2 or 1 with 16
-        const int lane = tid & 31, ch_low = lane & 7, row_low = lane >> 3;
+        const int lane = tid & 31, row_of_lane = lane & 7, ch_of_lane = lane >> 3;
         int a_ch[kWgItems], a_row[kWgItems], x_ch[kWgItems], x_row[kWgItems];
 #pragma unroll
         for (int it = 0; it < kWgItems; it++) {
-            const int ca = (tid >> 5) * kWgItems + it;   // 0..31 -> (channel group 0..15, upper row half)
-            a_ch[it] = (ca >> 1) * 8 + ch_low;
-            a_row[it] = (ca & 1) * 4 + row_low;
-            const int cx = (tid >> 5) * xchunks + it; // 0..8*xchunks-1 -> (channel group 0..cin/8-1, upper row half)
-            x_ch[it] = (cx >> 1) * 8 + ch_low;
-            x_row[it] = (cx & 1) * 4 + row_low;
+            a_ch[it] = ((tid >> 5) * kWgItems + it) * 4 + ch_of_lane;   // a warp's load = 4 whole channels = 1 KB of consecutive bytes
+            a_row[it] = row_of_lane;
+            x_ch[it] = ((tid >> 5) * xchunks + it) * 4 + ch_of_lane;
+            x_row[it] = row_of_lane;
         }
         float4 cur[4 * kWgItems], nxt[4 * kWgItems];
         auto load = [&](float4 (&r)[4 * kWgItems], long long p) {
@@ -402,8 +407,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
         // Bias gradient = sum of dY over positions and cells, taken by the ky = 0 CTA of each slice from the registers it converts anyway
         // (a separate kernel used to read every dY tensor once more for it: 0.39 ms per 8,192 positions).  Both items of a thread are the
         // two row halves of ONE channel; the four row_low lanes are folded by shuffles after the loop.  Fixed order throughout.
-        static_assert(kWgItems == 2, "the bias sums assume one channel per producer thread");
-        float bsum = 0.0f;
+        float bsum[kWgItems];
+#pragma unroll
+        for (int it = 0; it < kWgItems; it++) bsum[it] = 0.0f;
         if (n_pos > 0) load(cur, p_begin);
         for (int ip = 0; ip < n_pos; ip++) {
             if (ip + 1 < n_pos) load(nxt, p_begin + ip + 1);
@@ -417,9 +423,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
                 pack_f16x8_split(cur[2 * it], cur[2 * it + 1], scale, hi, lo);
                 if (ky == 0) {
                     const float4 u = cur[2 * it], v = cur[2 * it + 1];
-                    bsum += ((u.x + u.y) + (u.z + u.w)) + ((v.x + v.y) + (v.z + v.w));
+                    bsum[it] += ((u.x + u.y) + (u.z + u.w)) + ((v.x + v.y) + (v.z + v.w));
                 }
-                const uint32_t off = (((o >> 3) * 8 + row) * 8 + (o & 7)) * 16;
+                const uint32_t off = (o >> 3) * kWgSboA + row * kWgLbo + (o & 7) * 16;
                 *reinterpret_cast<uint4 *>(st + off) = hi;
                 *reinterpret_cast<uint4 *>(st + kWgATile + off) = lo;
             }
@@ -429,7 +435,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
                 if (it < xchunks) {
                     const int c = x_ch[it], row = x_row[it];
                     const uint4 v = pack_f16x8(cur[2 * kWgItems + 2 * it], cur[2 * kWgItems + 2 * it + 1]);
-                    const uint32_t off = kWgXBase + (((c >> 3) * 10 + row + 1) * 8 + (c & 7)) * 16;
+                    const uint32_t off = kWgXBase + (c >> 3) * kWgSboB + (row + 1) * kWgLbo + (c & 7) * 16;
                     // kx = 0: out[x] = in[x - 1]; kx = 1: in[x]; kx = 2: out[x] = in[x + 1]   (zero beyond the board edge)
                     const uint4 left = make_uint4(v.x << 16, __funnelshift_l(v.x, v.y, 16), __funnelshift_l(v.y, v.z, 16), __funnelshift_l(v.z, v.w, 16));
                     const uint4 right = make_uint4(__funnelshift_r(v.x, v.y, 16), __funnelshift_r(v.y, v.z, 16), __funnelshift_r(v.z, v.w, 16), v.w >> 16);
@@ -445,30 +451,35 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
             for (int i = 0; i < 4 * kWgItems; i++) cur[i] = nxt[i];
         }
         if (ky == 0) {
-            bsum += __shfl_xor_sync(0xFFFFFFFFu, bsum, 8);
-            bsum += __shfl_xor_sync(0xFFFFFFFFu, bsum, 16);
-            if (lane < 8) bias_partial[(size_t)blockIdx.x * 128 + warp * 8 + lane] = bsum;
+#pragma unroll
+            for (int it = 0; it < kWgItems; it++) {
+                float b = bsum[it];
+                b += __shfl_xor_sync(0xFFFFFFFFu, b, 1);
+                b += __shfl_xor_sync(0xFFFFFFFFu, b, 2);
+                b += __shfl_xor_sync(0xFFFFFFFFu, b, 4);
+                if (row_of_lane == 0) bias_partial[(size_t)blockIdx.x * 128 + a_ch[it]] = b;
+            }
         }
     } else if ((tid & 31) == 0) {
         // ================= MMA issuer =================
         const uint32_t idesc = instr_desc(128, N), idesc256 = instr_desc(128, 256);   // fp16 operands, fp32 accumulate
-        const uint64_t hi_a = ((uint64_t)(1024 >> 4) << 32) | (1ULL << 46);   // SBO = 1,024 B between o groups
-        const uint64_t hi_b = ((uint64_t)(1280 >> 4) << 32) | (1ULL << 46);   // SBO = 1,280 B between c groups (10 padded rows)
-        const uint32_t lbo_word = (uint32_t)(128 >> 4) << 16;                 // LBO = 128 B between K-adjacent core matrices (board rows)
+        const uint64_t hi_a = ((uint64_t)(kWgSboA >> 4) << 32) | (1ULL << 46);   // SBO: bytes between o groups
+        const uint64_t hi_b = ((uint64_t)(kWgSboB >> 4) << 32) | (1ULL << 46);   // SBO: bytes between c groups (10 padded rows)
+        const uint32_t lbo_word = (uint32_t)(kWgLbo >> 4) << 16;                 // LBO: bytes between K-adjacent core matrices (board rows)
         uint32_t stage = 0, phase = 0;
         for (int ip = 0; ip < n_pos; ip++) {
             mbar_wait(bar_full + 8 * stage, phase);
             tc_fence_after();
             const uint32_t st = sbase + stage * kWgStage;
             if (N == 128) {
-                // The X copies for kx = 0 and kx = 1 are adjacent in units of the c-group stride (16 groups x 1,280 B = one copy), so
+                // The X copies for kx = 0 and kx = 1 are adjacent in units of the c-group stride (16 groups x kWgSboB = one copy), so
                 // one N = 256 MMA serves both taps and reads the dY tile once for the two of them; accumulator columns 0-255 are
                 // exactly taps kx = 0 | kx = 1.  (Shared-memory throughput is what bounds this kernel: 32 KB less per position.)
 #pragma unroll
                 for (int ks = 0; ks < 4; ks++) {   // board rows (2 ks, 2 ks + 1) of dY against padded rows (2 ks + ky, 2 ks + ky + 1) of X
-                    const uint32_t aw = ((st + ks * 256) >> 4) | lbo_word, alw = ((st + kWgATile + ks * 256) >> 4) | lbo_word;
-                    const uint32_t bw01 = ((st + kWgXBase + (2 * ks + ky) * 128) >> 4) | lbo_word;
-                    const uint32_t bw2 = ((st + kWgXBase + 2 * kWgXCopy + (2 * ks + ky) * 128) >> 4) | lbo_word;
+                    const uint32_t aw = ((st + ks * 2 * kWgLbo) >> 4) | lbo_word, alw = ((st + kWgATile + ks * 2 * kWgLbo) >> 4) | lbo_word;
+                    const uint32_t bw01 = ((st + kWgXBase + (2 * ks + ky) * kWgLbo) >> 4) | lbo_word;
+                    const uint32_t bw2 = ((st + kWgXBase + 2 * kWgXCopy + (2 * ks + ky) * kWgLbo) >> 4) | lbo_word;
                     const uint32_t acc = (ip > 0 || ks > 0) ? 1u : 0u;
                     umma_f16(tmem, hi_a | aw, hi_b | bw01, idesc256, acc);
                     umma_f16(tmem, hi_a | alw, hi_b | bw01, idesc256, 1u);
@@ -480,8 +491,8 @@ __global__ void __launch_bounds__(kWgThreads, 1) wgrad_tc_kernel(const float *__
                 for (int kx = 0; kx < 3; kx++) {
 #pragma unroll
                     for (int ks = 0; ks < 4; ks++) {
-                        const uint32_t aw = ((st + ks * 256) >> 4) | lbo_word, alw = ((st + kWgATile + ks * 256) >> 4) | lbo_word;
-                        const uint32_t bw = ((st + kWgXBase + kx * kWgXCopy + (2 * ks + ky) * 128) >> 4) | lbo_word;
+                        const uint32_t aw = ((st + ks * 2 * kWgLbo) >> 4) | lbo_word, alw = ((st + kWgATile + ks * 2 * kWgLbo) >> 4) | lbo_word;
+                        const uint32_t bw = ((st + kWgXBase + kx * kWgXCopy + (2 * ks + ky) * kWgLbo) >> 4) | lbo_word;
                         umma_f16(tmem + kx * 128, hi_a | aw, hi_b | bw, idesc, (ip > 0 || ks > 0) ? 1u : 0u);
                         umma_f16(tmem + kx * 128, hi_a | alw, hi_b | bw, idesc, 1u);
                     }
@@ -1056,7 +1067,7 @@ int iago_trainer_create(iago_ctx *ctx, int kind, const float *params, int64_t n_
     A(t->dymax, 8);
     t->slices = 24;                                  // fp32 weight-gradient kernel: position slices of the 64/128-input-channel layers
     t->slices0 = 2 * ctx->sm_count;                  // ... and of block 1 (2 input channels: one c tile, so the slices are the whole grid)
-    t->tc_slices = ctx->sm_count >= 3 ? ctx->sm_count / 3 : 1;   // 3 kernel rows x slices <= one CTA per SM: the kernel's 188 KB of shared
+    t->tc_slices = ctx->sm_count >= 3 ? ctx->sm_count / 3 : 1;   // 3 kernel rows x slices <= one CTA per SM: the kernel's 207 KB of shared
                                                                  // memory allow one CTA per SM, so rounding UP (150 CTAs on 148 SMs) ran
                                                                  // every launch as two waves — twice the time of 147 CTAs
     t->partial_stride = (size_t)128 * 128 * 9 + 128;

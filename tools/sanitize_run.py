@@ -67,3 +67,26 @@ if "selfplay" in what:
     res = eng.selfplay(0, 0, 64, greedy=False, rng=Rng.philox(seed=5, stream_id=1))
     torch.cuda.synchronize()
     print("selfplay: 64 sampled games ok,", res["stats"], flush=True)
+
+if "reinforce" in what:
+    # K6: REINFORCE and value gradients on the tensor-core path (fused backward chain, weight-gradient kernel, head kernels, Adam)
+    from iago_b200 import network
+    from iago_b200.train_rl import ReinforceTrainer
+    from iago_b200.train_value import ValueTrainer
+    opp_net = network.SLPolicy().load(os.path.join(mdir, "RL", "model0.npz"))
+    tr = ReinforceTrainer(os.path.join(mdir, "rl_model.npz"), max_positions=2048)
+    d = tr.play_set(opp_net, 32, seed=1)
+    tr.gradient(d["own"], d["opp"], d["action"], d["reward"])
+    tr.update()
+    torch.cuda.synchronize()
+    g = tr.grad.cpu().numpy()
+    assert np.isfinite(g).all() and np.abs(g).max() > 0
+    print(f"reinforce: 32 games, {d['own'].numel()} positions, gradient + Adam ok", flush=True)
+    m = 150   # not a multiple of the weight-gradient slice count: ragged slices
+    vt = ValueTrainer(os.path.join(mdir, "value_model.npz"), max_positions=256, slot=7, seed=11)
+    y = torch.sign(torch.randn(m, device=dev))
+    vt.gradient(d["own"][:m].contiguous(), d["opp"][:m].contiguous(), y)
+    torch.cuda.synchronize()
+    gv = vt.grad.cpu().numpy()
+    assert np.isfinite(gv).all() and np.abs(gv).max() > 0
+    print(f"value: {m} positions, gradient ok", flush=True)

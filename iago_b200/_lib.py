@@ -36,6 +36,8 @@ SIGNATURES = {
     "iago_place_stone": [_P, _P, _P, _P, _P, C.c_int64, _P],
     "iago_rollout": [_P, _P, _P, _P, C.c_int64, C.POINTER(IagoRng), _P, _P, _P, _P, _P, _P, _P],
     "iago_rollout_host": [_P, _P, _P, _P, C.c_int64, C.POINTER(IagoRng), _P, _P, _P, _P, _P, _P],
+    "iago_rollout_host_submit": [_P, C.c_int, _P, _P, _P, C.c_int64, C.POINTER(IagoRng), _P, _P, _P, _P, _P],
+    "iago_rollout_host_wait": [_P, C.c_int, _P],
     "iago_rollout_sample": [_P, _P, _P, _P, C.c_int64, C.POINTER(IagoRng), C.c_uint32, _P, _P],
     "iago_rollout_logits": [_P, _P, _P, _P, _P, C.c_int64, _P],
     "iago_load_net": [_P, C.c_int, C.c_int, _P, C.c_int64],

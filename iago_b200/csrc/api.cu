@@ -84,6 +84,15 @@ int iago_ctx_destroy(iago_ctx *ctx) {
     cudaEventDestroy(ctx->ev1);
     for (int c = 1; c < 4; c++)
         if (ctx->host_streams[c]) cudaStreamDestroy(ctx->host_streams[c]);
+    for (iago::HostLane &l : ctx->lanes) {
+        if (l.stream) {
+            cudaStreamSynchronize(l.stream);
+            cudaStreamDestroy(l.stream);
+        }
+        if (l.dev) cudaFree(l.dev);
+        if (l.d_cnt) cudaFree(l.d_cnt);
+        if (l.h_cnt) cudaFreeHost(l.h_cnt);
+    }
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return IAGO_OK;

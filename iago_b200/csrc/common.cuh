@@ -31,6 +31,17 @@ struct Staging {
     size_t bytes = 0;
 };
 
+// One in-flight iago_rollout_host_submit: its own stream, device block and counters (rollout.cu)
+struct HostLane {
+    cudaStream_t stream = nullptr;
+    char *dev = nullptr;          // p1 | p2 | color | final_p1 | final_p2 | n_moves | result | move log
+    size_t bytes = 0;
+    uint64_t *d_cnt = nullptr;    // {stones, turns, ticket, -}: zero between launches
+    uint64_t *h_cnt = nullptr;    // page-locked, device-mapped: the kernel's last CTA publishes the totals here
+    bool busy = false;
+};
+constexpr int kHostLanes = 4;
+
 }  // namespace iago
 
 struct iago_ctx {
@@ -44,6 +55,7 @@ struct iago_ctx {
     bool rollout_loaded = false;
     bool rollout_fast = false;   // every possible |logit| <= 300: the product-of-exponentials sampler cannot over/underflow in double
     iago::Staging stage;
+    iago::HostLane lanes[iago::kHostLanes];   // iago_rollout_host_submit / _wait
     uint64_t *d_counters = nullptr;
     void *trunk = nullptr;     // conv-net state (trunk.cu)
     void *selfplay = nullptr;  // self-play workspace (selfplay.cu)

@@ -1145,6 +1145,91 @@ int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t *p2, con
     return IAGO_OK;
 }
 
+// Asynchronous form of iago_rollout_host for a caller that streams batches: up to kHostLanes submissions are in flight, each on its
+// own stream — H2D copies of the three input arrays, the kernel on the lane's device block, D2H copies of the results — so the
+// copies of one batch run on the copy engines while the kernel of another has the SMs.  Page-locked buffers and Philox uniforms only.
+int iago_rollout_host_submit(iago_ctx *ctx, int lane, const uint64_t *p1, const uint64_t *p2, const uint8_t *color, int64_t n,
+                             const iago_rng *rng, int8_t *result, uint64_t *final_p1, uint64_t *final_p2, int32_t *n_moves,
+                             int8_t *move_log) {
+    IAGO_REQUIRE(ctx && p1 && p2 && color && result && final_p1 && final_p2, "NULL argument");
+    IAGO_REQUIRE(lane >= 0 && lane < kHostLanes, "lane out of range");
+    IAGO_REQUIRE(n >= 0, "n < 0");
+    int rc = check_rng(rng, true, ctx);
+    if (rc) return rc;
+    IAGO_REQUIRE(rng->mode == IAGO_RNG_PHILOX, "iago_rollout_host_submit draws Philox uniforms only (replay streams: iago_rollout_host)");
+    HostLane &l = ctx->lanes[lane];
+    if (l.busy) {
+        set_error("iago_rollout_host_submit: lane %d has a submission in flight (call iago_rollout_host_wait first)", lane);
+        return IAGO_E_STATE;
+    }
+    IAGO_REQUIRE(is_pinned(p1) && is_pinned(p2) && is_pinned(color) && is_pinned(result) && is_pinned(final_p1) && is_pinned(final_p2) &&
+                     is_pinned(n_moves) && is_pinned(move_log),
+                 "iago_rollout_host_submit needs page-locked buffers (cudaHostAlloc / cudaHostRegister / torch pin_memory)");
+    DeviceGuard guard(ctx->device);
+    if (!l.stream) {
+        IAGO_CUDA(cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking));
+        IAGO_CUDA(cudaMalloc(&l.d_cnt, 4 * sizeof(uint64_t)));
+        IAGO_CUDA(cudaMemset(l.d_cnt, 0, 4 * sizeof(uint64_t)));
+        IAGO_CUDA(cudaHostAlloc(&l.h_cnt, 2 * sizeof(uint64_t), cudaHostAllocMapped));
+    }
+    l.h_cnt[0] = l.h_cnt[1] = 0;
+    l.busy = true;
+    if (n == 0) return IAGO_OK;
+    auto up8 = [](size_t x) { return (x + 7) & ~(size_t)7; };
+    const size_t N = (size_t)n;
+    const size_t o_p1 = 0, o_p2 = o_p1 + 8 * N, o_col = o_p2 + 8 * N, o_f1 = o_col + up8(N), o_f2 = o_f1 + 8 * N, o_nm = o_f2 + 8 * N;
+    const size_t o_res = o_nm + up8(4 * N), o_log = o_res + up8(N), bytes = o_log + (move_log ? 64 * N : 0);
+    if (l.bytes < bytes) {
+        if (l.dev) cudaFree(l.dev);
+        l.dev = nullptr;
+        l.bytes = 0;
+        IAGO_CUDA(cudaMalloc(&l.dev, bytes + bytes / 4));
+        l.bytes = bytes + bytes / 4;
+    }
+    cudaStream_t s = l.stream;
+    char *d = l.dev;
+    const cudaMemcpyKind H2D = cudaMemcpyHostToDevice, D2H = cudaMemcpyDeviceToHost;
+    IAGO_CUDA(cudaMemcpyAsync(d + o_p1, p1, 8 * N, H2D, s));
+    IAGO_CUDA(cudaMemcpyAsync(d + o_p2, p2, 8 * N, H2D, s));
+    IAGO_CUDA(cudaMemcpyAsync(d + o_col, color, N, H2D, s));
+    const bool publish = ctx->rollout_fast;   // the paired kernel's last CTA writes the totals to h_cnt and re-zeroes d_cnt
+    void *h_cnt_dev = nullptr;
+    if (publish) IAGO_CUDA(cudaHostGetDevicePointer(&h_cnt_dev, l.h_cnt, 0));
+    else IAGO_CUDA(cudaMemsetAsync(l.d_cnt, 0, 16, s));
+    RolloutArgs a{(const u64 *)(d + o_p1), (const u64 *)(d + o_p2), (const uint8_t *)(d + o_col), (long long)n, rng->stream_id, rng->seed,
+                  rng->game_id0, nullptr, 0, nullptr, 0, (int8_t *)(d + o_res), (u64 *)(d + o_f1), (u64 *)(d + o_f2),
+                  n_moves ? (int32_t *)(d + o_nm) : nullptr, move_log ? (int8_t *)(d + o_log) : nullptr, (u64 *)l.d_cnt, nullptr, 0,
+                  (u64 *)h_cnt_dev, (unsigned *)(l.d_cnt + 2)};
+    launch_rollout_mode(a, rng->mode, ctx->rollout_fast, ctx->d_rollout, s);
+    IAGO_CUDA(cudaGetLastError());
+    IAGO_CUDA(cudaMemcpyAsync(final_p1, d + o_f1, 8 * N, D2H, s));
+    IAGO_CUDA(cudaMemcpyAsync(final_p2, d + o_f2, 8 * N, D2H, s));
+    IAGO_CUDA(cudaMemcpyAsync(result, d + o_res, N, D2H, s));
+    if (n_moves) IAGO_CUDA(cudaMemcpyAsync(n_moves, d + o_nm, 4 * N, D2H, s));
+    if (move_log) IAGO_CUDA(cudaMemcpyAsync(move_log, d + o_log, 64 * N, D2H, s));
+    if (!publish) IAGO_CUDA(cudaMemcpyAsync(l.h_cnt, l.d_cnt, 16, D2H, s));
+    return IAGO_OK;
+}
+
+// Blocks until the submission of `lane` has delivered its results; counters_host[2] (nullable) = {stones placed, turns taken}.
+int iago_rollout_host_wait(iago_ctx *ctx, int lane, uint64_t *counters_host) {
+    IAGO_REQUIRE(ctx != nullptr, "ctx is NULL");
+    IAGO_REQUIRE(lane >= 0 && lane < kHostLanes, "lane out of range");
+    HostLane &l = ctx->lanes[lane];
+    if (!l.busy) {
+        set_error("iago_rollout_host_wait: lane %d has nothing in flight", lane);
+        return IAGO_E_STATE;
+    }
+    DeviceGuard guard(ctx->device);
+    l.busy = false;
+    IAGO_CUDA(cudaStreamSynchronize(l.stream));
+    if (counters_host) {
+        counters_host[0] = l.h_cnt[0];
+        counters_host[1] = l.h_cnt[1];
+    }
+    return IAGO_OK;
+}
+
 int iago_measure_int_peak(iago_ctx *ctx, int iters, double *lane_ops_per_s) {
     IAGO_REQUIRE(ctx && lane_ops_per_s && iters > 0, "bad argument");
     DeviceGuard guard(ctx->device);

@@ -398,6 +398,34 @@ class Engine:
                                          _nptr(out.get("n_moves")), _nptr(out.get("moves")), _nptr(out.get("counters"))))
         return out
 
+    HOST_LANES = 4
+
+    def rollout_host_submit(self, lane, p1, p2, color, rng: Optional[Rng] = None, out=None):
+        """Asynchronous rollout_host on one of HOST_LANES lanes: returns at once; rollout_host_wait(lane) blocks until `out` (from
+        rollout_host_buffers) is filled.  Every array must be page-locked (pinned() / rollout_host_buffers()) and must not be
+        touched until the wait.  With two or three lanes in flight the copies of one batch overlap the kernel of another."""
+        rng = rng or Rng()
+        n = p1.shape[0]
+        for a, dt in ((p1, np.uint64), (p2, np.uint64), (color, np.uint8)):
+            if not (isinstance(a, np.ndarray) and a.dtype == dt and a.flags.c_contiguous and a.shape == (n,)):
+                raise ValueError("rollout_host_submit takes contiguous page-locked arrays p1, p2 (uint64) and color (uint8) of one length")
+        if out is None:
+            raise ValueError("rollout_host_submit needs `out` from rollout_host_buffers(n)")
+        r, keep = self._rng_struct(rng, n, host=True)
+        check(self.lib.iago_rollout_host_submit(self.ctx, int(lane), _nptr(p1), _nptr(p2), _nptr(color), n, C.byref(r),
+                                                _nptr(out["result"]), _nptr(out["final_p1"]), _nptr(out["final_p2"]),
+                                                _nptr(out.get("n_moves")), _nptr(out.get("moves"))))
+        self._lane_out = getattr(self, "_lane_out", {})
+        self._lane_out[int(lane)] = (out, p1, p2, color)   # keeps the buffers alive while the lane is in flight
+        return lane
+
+    def rollout_host_wait(self, lane):
+        """Blocks until the submission on `lane` is complete and returns its `out` dict (counters filled)."""
+        held = getattr(self, "_lane_out", {}).pop(int(lane), None)
+        out = held[0] if held else None
+        check(self.lib.iago_rollout_host_wait(self.ctx, int(lane), _nptr(out.get("counters") if out else None)))
+        return out
+
     def _to_dev(self, a, dtype):
         torch = _torch()
         a = np.array(a, copy=True)  # broadcast views are read-only; torch wants a writable buffer

@@ -116,6 +116,18 @@ IAGO_API int iago_rollout_host(iago_ctx *ctx, const uint64_t *p1, const uint64_t
                       const iago_rng *rng, int8_t *result, uint64_t *final_p1, uint64_t *final_p2,
                       int32_t *n_moves, int8_t *move_log, uint64_t *counters_host);
 
+/* The same work for a caller that streams batches (mcts_self_play.py:137-150 calls Simulate once per game in a loop; a batched
+ * caller keeps several batches in flight): submit returns at once, wait blocks until that lane's results are in the caller's
+ * buffers.  lane in [0, IAGO_HOST_LANES): each lane has its own stream and device block, so the H2D / D2H copies of one batch run
+ * on the copy engines while the kernel of another batch has the SMs.  Buffers must be page-locked and stay untouched until
+ * the wait; Philox uniforms only (replay streams go through iago_rollout_host).  Errors: IAGO_E_STATE when the lane is still
+ * in flight (submit) or idle (wait); IAGO_E_INVALID for pageable buffers. */
+#define IAGO_HOST_LANES 4
+IAGO_API int iago_rollout_host_submit(iago_ctx *ctx, int lane, const uint64_t *p1, const uint64_t *p2, const uint8_t *color,
+                             int64_t n, const iago_rng *rng, int8_t *result, uint64_t *final_p1, uint64_t *final_p2,
+                             int32_t *n_moves, int8_t *move_log);
+IAGO_API int iago_rollout_host_wait(iago_ctx *ctx, int lane, uint64_t *counters_host);
+
 /* One Simulate.get_action draw per board (mcts_self_play.py:100-110): legal moves, rollout policy, masked
  * renormalised inverse-cdf sample.  No board update.  action[i] = -1 when the side to move has no legal move.
  * PHILOX: the draw-th uniform of game game_id0+i; UNIFORMS: uniforms[i] (u_stride ignored). */

@@ -373,3 +373,50 @@ def test_host_call_on_pinned_buffers(engine, cref, rollout_weights):
         out3 = dict(out2, result=np.empty(n, np.int8))
         engine.rollout_host(p1, p2, col, rng=Rng.philox(seed=11, game_id0=5), out=out3)
         assert (out3["result"] == ref["results"]).all() and (out3["moves"] == ref["moves"]).all(), n
+
+
+def test_streamed_host_batches_vs_oracle(engine, cref, rollout_weights):
+    """iago_rollout_host_submit / _wait: several batches in flight on their own lanes (H2D copies, kernel, D2H copies per lane) give
+    the oracle's games batch by batch — different sizes, seeds and game ids per lane, with and without the optional outputs, lanes
+    reused — and the error paths (lane in flight, idle lane, pageable buffer, replay stream) report instead of running."""
+    from iago_b200 import Rng, boards
+    from iago_b200._lib import IagoError
+    W, b = rollout_weights
+    sizes = (4097, 1, 20000, 513)
+    lanes = []
+    for lane, n in enumerate(sizes):
+        p1, p2, col, out = engine.rollout_host_buffers(n, want_moves=(lane % 2 == 0))
+        p1[:], p2[:], col[:] = boards.START_P1, boards.START_P2, 1 + lane % 2
+        if out["moves"] is not None:
+            out["moves"][:] = 77
+        lanes.append((p1, p2, col, out))
+    for rnd in range(2):        # second round: the lanes and their device blocks are reused
+        for lane, (p1, p2, col, out) in enumerate(lanes):
+            engine.rollout_host_submit(lane, p1, p2, col, rng=Rng.philox(seed=21 + rnd, game_id0=1000 * lane), out=out)
+        with pytest.raises(IagoError):
+            engine.rollout_host_submit(0, *lanes[0][:3], rng=Rng.philox(seed=1), out=lanes[0][3])   # lane 0 is in flight
+        for lane in reversed(range(len(sizes))):
+            n = sizes[lane]
+            out = engine.rollout_host_wait(lane)
+            st = np.tile(boards.start_state().reshape(1, 64), (n, 1))
+            ref = cref.simulate_batch(st, 1 + lane % 2, W, b, mode=cref.RNG_PHILOX, seed=21 + rnd, game_id0=1000 * lane, threads=0)
+            r1, r2 = cref.to_bitboards(ref["final"])
+            assert (out["result"] == ref["results"]).all() and (out["final_p1"] == r1).all() and (out["final_p2"] == r2).all(), (rnd, lane)
+            assert (out["n_moves"] == ref["n_moves"]).all(), (rnd, lane)
+            if out["moves"] is not None:
+                assert (out["moves"] == ref["moves"]).all(), (rnd, lane)
+            assert int(out["counters"][0]) == int(ref["n_moves"].sum()) and int(out["counters"][1]) == int(ref["n_turns"].sum()), (rnd, lane)
+    with pytest.raises(IagoError):
+        engine.rollout_host_wait(2)                                             # nothing in flight
+    p1, p2, col, out = lanes[3]
+    with pytest.raises(IagoError):
+        engine.rollout_host_submit(1, p1, p2, col, rng=Rng.philox(seed=1), out=dict(out, result=np.empty(sizes[3], np.int8)))   # pageable
+    with pytest.raises(IagoError):
+        engine.rollout_host_submit(1, p1, p2, col, rng=Rng.replay_moves(np.zeros((sizes[3], 64), np.int8)), out=out)
+    with pytest.raises(IagoError):
+        engine.rollout_host_submit(engine.HOST_LANES, p1, p2, col, rng=Rng.philox(seed=1), out=out)
+    # the lanes still work after the refused calls, and the synchronous call beside them gives the same games
+    engine.rollout_host_submit(1, p1, p2, col, rng=Rng.philox(seed=5, game_id0=7), out=out)
+    got = {k: (v.copy() if v is not None else None) for k, v in engine.rollout_host_wait(1).items()}
+    sync = engine.rollout_host(p1, p2, col, rng=Rng.philox(seed=5, game_id0=7))
+    assert (got["result"] == sync["result"]).all() and (got["final_p1"] == sync["final_p1"]).all() and (got["n_moves"] == sync["n_moves"]).all()

@@ -40,6 +40,40 @@ def simulate_batch(states=None, colors=1, *, p1=None, p2=None, rng=None, want_mo
     return _engine(device).rollout_host(p1, p2, colors, rng=rng, want_moves=want_moves)
 
 
+def simulate_stream(batches, *, seed=0, game_id0=0, want_moves=False, device=0, in_flight=3):
+    """simulate_batch over an iterable of (p1, p2, colors) bitboard batches with up to `in_flight` of them on the GPU at a time
+    (Engine.rollout_host_submit / _wait: the copies of one batch overlap the kernel of another).  Yields one result dict per batch, in
+    order, as copies; game ids run on from `game_id0` across the batches, so the games are those of one simulate_batch call over the
+    concatenation with Rng.philox(seed, game_id0)."""
+    eng = _engine(device)
+    lanes = max(1, min(int(in_flight), eng.HOST_LANES))
+    bufs = [None] * lanes
+    pending = []                     # (lane, n) in submission order
+
+    def collect():
+        lane, n = pending.pop(0)
+        out = eng.rollout_host_wait(lane)
+        return {k: (np.array(v[:n]) if k != "counters" else np.array(v)) for k, v in out.items() if v is not None}
+
+    gid = int(game_id0)
+    for i, (p1, p2, colors) in enumerate(batches):
+        lane = i % lanes
+        if len(pending) == lanes:
+            yield collect()
+        p1 = np.asarray(p1, np.uint64).reshape(-1)
+        n = p1.shape[0]
+        if bufs[lane] is None or bufs[lane][0].shape[0] < n:
+            bufs[lane] = eng.rollout_host_buffers(max(n, 1), want_moves=want_moves)
+        b1, b2, bc, out = bufs[lane]
+        b1[:n], b2[:n], bc[:n] = p1, np.asarray(p2, np.uint64).reshape(n), np.broadcast_to(np.asarray(colors, np.uint8), (n,))
+        view = {k: (v[:n] if (v is not None and k != "counters") else v) for k, v in out.items()}
+        eng.rollout_host_submit(lane, b1[:n], b2[:n], bc[:n], rng=Rng.philox(seed=seed, game_id0=gid), out=view)
+        pending.append((lane, n))
+        gid += n
+    while pending:
+        yield collect()
+
+
 class Simulate:
     seed = 0  # class-level Philox key; each instance takes the next game id
 

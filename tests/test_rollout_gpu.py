@@ -420,3 +420,23 @@ def test_streamed_host_batches_vs_oracle(engine, cref, rollout_weights):
     got = {k: (v.copy() if v is not None else None) for k, v in engine.rollout_host_wait(1).items()}
     sync = engine.rollout_host(p1, p2, col, rng=Rng.philox(seed=5, game_id0=7))
     assert (got["result"] == sync["result"]).all() and (got["final_p1"] == sync["final_p1"]).all() and (got["n_moves"] == sync["n_moves"]).all()
+
+
+def test_facade_simulate_stream(engine):
+    """mcts_self_play.simulate_stream: batches of different sizes streamed with three in flight are the games of one simulate_batch
+    call over their concatenation (game ids run on across the batches)."""
+    from iago_b200 import Rng, boards, mcts_self_play
+    sizes = [700, 1, 4096, 33, 2500, 64, 900]
+    total = sum(sizes)
+    colors = (np.arange(total) % 2 + 1).astype(np.uint8)
+    p1 = np.full(total, boards.START_P1, np.uint64)
+    p2 = np.full(total, boards.START_P2, np.uint64)
+    whole = mcts_self_play.simulate_batch(p1=p1, p2=p2, colors=colors, rng=Rng.philox(seed=9, game_id0=123), want_moves=True)
+    cuts = np.cumsum([0] + sizes)
+    parts = list(mcts_self_play.simulate_stream(((p1[a:b], p2[a:b], colors[a:b]) for a, b in zip(cuts[:-1], cuts[1:])),
+                                                seed=9, game_id0=123, want_moves=True))
+    assert [len(r["result"]) for r in parts] == sizes
+    for k in ("result", "final_p1", "final_p2", "n_moves", "moves"):
+        assert (np.concatenate([r[k] for r in parts]) == whole[k]).all(), k
+    assert sum(int(r["counters"][0]) for r in parts) == int(whole["counters"][0])
+    assert list(mcts_self_play.simulate_stream([], seed=1)) == []

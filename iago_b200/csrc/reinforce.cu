@@ -301,7 +301,7 @@ constexpr int kWgSmem = kWgStages * kWgStage + 64;
 // One 32-byte sector per lane in ONE request (LDG.256, sm_100): with two 16-byte loads every sector was requested twice and the
 // second half had to survive in an L1 that the kernel's 207 KB of shared memory leaves almost no room for.
 __device__ __forceinline__ void ldg256(const float *p, float4 &a, float4 &b) {
-    asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+    asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"   // read once: no L1 line (6.12 against 6.18 ms per gradient)
                  : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
                  : "l"(p));
 }

@@ -43,3 +43,30 @@ def test_measured_capture_file_feeds_the_roofline_block():
     ops_rules = bench.alu_lane_ops_per_ply("rollout_pair_kernel_forced", plies)
     assert 200 < ops_rules < ops < 1000              # rules alone issue fewer ALU operations than rules + policy + sampling
     assert bench.alu_lane_ops_per_ply("no_such_kernel", plies) is None
+
+
+def test_committed_gpu_bench_line_has_the_contract_keys():
+    """The newest committed bench record of the GPU arm (profiles/r02_bench_v*.json, written by `python bench.py` on a B200) carries
+    every key the bench contract names, the end-to-end block counts its transfers, and the roofline block is self-consistent."""
+    import glob
+    import json
+    import os
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [f for f in glob.glob(os.path.join(root, "profiles", "r02_bench_v*.json")) if re.search(r"_v\d+\.json$", f)]
+    assert files
+    newest = max(files, key=lambda f: int(re.search(r"_v(\d+)\.json$", f).group(1)))
+    line = json.loads(open(newest).read().strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+                "dtype", "data", "config", "e2e", "gpu_launches", "clocks", "roofline", "cpu_baseline"):
+        assert key in line, (newest, key)
+    assert line["metric"] == "rollout_plies_per_s" and line["unit"] == "plies/s" and line["n_gpus"] == 1 and line["warmup"] >= 3
+    assert "workload" in line["config"] and "model" not in line["config"] and line["gpu_launches"] == line["steps"]
+    e2e = line["e2e"]
+    assert e2e["unit"] == line["unit"] and e2e["value"] > 0 and e2e["h2d_bytes_per_step"] > 0 and e2e["d2h_bytes_per_step"] > 0
+    assert abs(e2e["value"] - line["value"]) > 1e-6 * line["value"]          # measured on its own, not a copy of the device-timed value
+    rf = line["roofline"]
+    assert rf["bound"] in ("alu", "hbm", "tensor") and abs(rf["frac"] - rf["achieved"] / rf["peak"]) < 1e-9 and 0 < rf["frac"] <= 1
+    cb = line["cpu_baseline"]
+    assert cb["kind"] in ("port", "reference") and cb["cores"] >= 1 and cb["value"] > 0 and cb["sample"]
+    assert not set(line["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}

@@ -532,9 +532,54 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
         // the barriers the issuer waits on are the leader's: a pair's peer CTA arrives on them through the cluster address
         const uint32_t act_leader = CG == 2 ? mapa_rank(bar_act, 0) : bar_act, a1_leader = CG == 2 ? mapa_rank(bar_a1, 0) : bar_a1;
         const uint32_t hi_leader = CG == 2 ? mapa_rank(bar_hi, 0) : bar_hi;
+        // layer-1 input of position px: explicit im2col of the two bit planes, k = tap*2 + channel (0 = opponent, 1 = mover).  The tile
+        // lives in its own region (OFF_A1), free again as soon as the layer-1 MMAs that read it have retired, so the NEXT tile's boards
+        // are fetched and expanded while the current tile's last layer is on the tensor pipe: the issuer can put the next tile's layer 1
+        // behind that layer without waiting for an epilogue (≈ 5,000 cycles stood between two tiles before).
+        auto build_a1 = [&](long long px) {
+            if (qt == 0) {
+                u64 own = 0, opp = 0;
+                if (px < n_pos) {
+                    const bool first = a.color[px] == 1;
+                    const u64 x1 = a.p1[px], x2 = a.p2[px];
+                    own = first ? x1 : x2;
+                    opp = first ? x2 : x1;
+                }
+                uint32_t bits = 0;
+#pragma unroll
+                for (int t = 0; t < 9; t++) {
+                    const int y = r + t / 3 - 1, x = c + t % 3 - 1;
+                    if (y >= 0 && y < 8 && x >= 0 && x < 8) {
+                        const int k = y * 8 + x;
+                        bits |= (uint32_t)((opp >> k) & 1) << (2 * t);
+                        bits |= (uint32_t)((own >> k) & 1) << (2 * t + 1);
+                    }
+                }
+#pragma unroll
+                for (int kg = 0; kg < 4; kg++) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        const uint32_t lo = (bits >> (kg * 8 + 2 * e)) & 1, hi = (bits >> (kg * 8 + 2 * e + 1)) & 1;
+                        w[e] = (lo ? 0x3C00u : 0u) | (hi ? 0x3C000000u : 0u);  // fp16 1.0 = 0x3C00
+                    }
+                    *reinterpret_cast<uint4 *>(smem + OFF_A1 + kg * (kTileRows * 16) + m * 16) = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+            }
+            fence_async_smem();
+        };
+        // "im2col tile written AND accumulator buffer 0 drained by this warp": buffer 0 holds the layers with even index, so when the last
+        // layer's index is odd the arrival can precede its epilogue (the last even layer's accumulator was read before)
+        auto arrive_a1 = [&]() {
+            tc_fence_before();
+            __syncwarp();
+            if ((tid & 31) == 0) arrive_leader<CG>(a1_leader);
+        };
+        const bool a1_early = ((L - 1) & 1) == 1;
         for (long long tile = tile0, it = 0; tile < n_tiles; tile += tile_step, it++) {
             const long long pos = (tile * CG + rank) * 2 + b;
             const bool valid = pos < n_pos;
+            const bool has_next = tile + tile_step < n_tiles;
             if (MODE == 1) {
                 // ---- chain entry: the gradient tile [128 channels][cell] of this row's position -> bf16 hi/lo activation tile
                 const float *src = a.dy_in + (size_t)pos * 128 * 64 + cell;
@@ -551,40 +596,12 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                     if ((tid & 31) == 0) arrive_leader<CG>(act_leader + 8 * ps);
                 }
             } else {
-            // ---- layer-1 input: explicit im2col of the two bit planes, k = tap*2 + channel (0 = opponent, 1 = mover)
-                if (qt == 0) {
-                    u64 own = 0, opp = 0;
-                    if (valid) {
-                        const bool first = a.color[pos] == 1;
-                        const u64 x1 = a.p1[pos], x2 = a.p2[pos];
-                        own = first ? x1 : x2;
-                        opp = first ? x2 : x1;
-                    }
-                    uint32_t bits = 0;
-#pragma unroll
-                    for (int t = 0; t < 9; t++) {
-                        const int y = r + t / 3 - 1, x = c + t % 3 - 1;
-                        if (y >= 0 && y < 8 && x >= 0 && x < 8) {
-                            const int k = y * 8 + x;
-                            bits |= (uint32_t)((opp >> k) & 1) << (2 * t);
-                            bits |= (uint32_t)((own >> k) & 1) << (2 * t + 1);
-                        }
-                    }
-#pragma unroll
-                    for (int kg = 0; kg < 4; kg++) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int e = 0; e < 4; e++) {
-                            const uint32_t lo = (bits >> (kg * 8 + 2 * e)) & 1, hi = (bits >> (kg * 8 + 2 * e + 1)) & 1;
-                            w[e] = (lo ? 0x3C00u : 0u) | (hi ? 0x3C000000u : 0u);  // fp16 1.0 = 0x3C00
-                        }
-                        *reinterpret_cast<uint4 *>(smem + OFF_A1 + kg * (kTileRows * 16) + m * 16) = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
+            // ---- layer-1 input: the first tile's im2col tile is built here; every later one was built while the previous tile's last
+            //      layer ran (build_a1 / arrive_a1 below)
+                if (it == 0) {
+                    build_a1(pos);
+                    arrive_a1();
                 }
-                fence_async_smem();
-                tc_fence_before();
-                __syncwarp();
-                if ((tid & 31) == 0) arrive_leader<CG>(a1_leader);
             }
 
             for (int l = 0; l < L; l++) {
@@ -595,6 +612,10 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                 ld.cscale = (MODE == 0 && a.cscale) ? __ldg(a.cscale + l) : 0.0f;
                 float *const dump_l = MODE == 0 ? a.dump[l] : nullptr;
                 asm volatile("" ::"r"(ld.n), "f"(ld.cscale), "l"(dump_l));
+                if (MODE == 0 && l == L - 1 && has_next) {
+                    build_a1(((tile + tile_step) * CG + rank) * 2 + b);
+                    if (a1_early) arrive_a1();
+                }
                 mbar_wait(bar_acc + 8 * (l & 1), (acc_phase >> (l & 1)) & 1u);
                 acc_phase ^= 1u << (l & 1);
                 tc_fence_after();
@@ -744,6 +765,7 @@ __global__ void __launch_bounds__(kThreads, 1) trunk_kernel(const __grid_constan
                 }
                 tc_fence_before();
             }
+            if (MODE == 0 && has_next && !a1_early) arrive_a1();   // an even last layer sits in buffer 0: drained only now
         }
     }
 

@@ -433,6 +433,8 @@ def run_ours(args, rank, world, local_rank):
                            "(17 B per game), the kernel, D2H copies (21 B per game) on the step's own stream; wall clock from the "
                            "first submit to the last wait",
                     "ms_per_step": 1e3 * t_e2e / args.steps,
+                    "note": "can exceed `value`: `value` times every launch alone between two L2 flushes (its own ramp and tail of one "
+                            "147-CTA wave), streamed launches on different streams overlap those with the neighbouring batch",
                     "synchronous_call": {"value": sync_plies / t_sync, "ms_per_step": 1e3 * t_sync / args.steps,
                                          "api": "iago_rollout_host, one blocking call per step on pinned, device-mapped buffers: one "
                                                 "launch whose loads / stores cross PCIe + stream sync", "scope": "rank 0"},
